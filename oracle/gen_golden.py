@@ -1,0 +1,274 @@
+"""Pin the oracle against the UNMODIFIED reference and write tests/golden/*.pt.
+
+Run in the build container only (needs /root/reference):
+    python oracle/gen_golden.py
+For every case it (1) builds the reference module from /root/reference under the
+diffusers/mmgp shims, (2) loads the oracle's seeded state_dict into it, (3) runs both on
+the same seeded inputs in fp32 on CPU, (4) asserts they agree to float round-off, and
+(5) stores inputs' seeds + the REFERENCE outputs as small fixtures.  tests/test_oracle_golden.py
+re-checks the oracle against these fixtures on any machine (no reference needed).
+"""
+import contextlib
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(HERE, "refshim"))
+
+import load_reference  # noqa: E402
+
+load_reference.install()
+
+from oracle import ltx_oracle as O  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+os.makedirs(GOLD, exist_ok=True)
+torch.manual_seed(0)
+torch.set_grad_enabled(False)
+
+
+class _NoInterrupt:
+    _interrupt = False
+
+
+def _check(name, a, b, tol=2e-5):
+    err = O.rel_l2(a, b)
+    print(f"  {name}: rel_l2(oracle, reference) = {err:.3e}  max|d|={float((a - b).abs().max()):.3e}")
+    assert err < tol, f"{name}: oracle disagrees with the reference ({err})"
+    return err
+
+
+def build_ref_transformer(num_layers, sd):
+    from ltx_video.models.transformers.transformer3d import Transformer3DModel
+    from ltx_video.utils.diffusers_config_mapping import OURS_TRANSFORMER_CONFIG
+    cfg = dict(OURS_TRANSFORMER_CONFIG)
+    cfg["num_layers"] = num_layers
+    m = Transformer3DModel.from_config(cfg)
+    missing, unexpected = m.load_state_dict(sd, strict=True)
+    return m.eval()
+
+
+def case_transformer():
+    """Transformer3DModel.forward: t2v timestep, per-token (i2v) timestep, STG skip mask."""
+    from ltx_video.utils.skip_layer_strategy import SkipLayerStrategy
+    cfg = O.LTX_2B
+    L = 2
+    sd = O.make_transformer_state_dict(cfg, seed=0, num_layers=L)
+    ref = build_ref_transformer(L, sd)
+    f, h, w = 3, 4, 6
+    N = f * h * w
+    g = torch.Generator().manual_seed(11)
+    out = {"meta": dict(num_layers=L, f=f, h=h, w=w, seed_weights=0, seed_inputs=11)}
+    for B, tag in ((1, "t2v"), (3, "stg")):
+        hidden = torch.randn(B, N, 128, generator=g)
+        enc = torch.randn(B, 24, 4096, generator=g)
+        mask = torch.ones(B, 24)
+        mask[:, 17:] = 0
+        coords = O.latent_to_pixel_coords(O.latent_coords(f, h, w, 1)).float()
+        coords[:, 0] *= 1.0 / 25.0
+        cos_ref, sin_ref = ref.precompute_freqs_cis(coords)
+        cos, sin = O.precompute_freqs_cis(coords, 2048, cfg["rope_theta"], cfg["rope_max_pos"])
+        assert torch.equal(cos, cos_ref) and torch.equal(sin, sin_ref), "rope table not bit-exact"
+        if tag == "t2v":
+            ts = torch.full((B, 1), 0.7311)
+            skip, strat_ref, strat = None, None, None
+        else:
+            # per-token timesteps: first latent frame conditioned (t = 0), rest 0.61
+            ts = torch.full((B, N), 0.61)
+            ts[:, : h * w] = 0.0
+            skip = ref.create_skip_layer_mask(1, 3, 2, [1])
+            strat_ref, strat = SkipLayerStrategy.AttentionValues, O.SKIP_ATTENTION_VALUES
+        y_ref = ref(hidden.clone(), freqs_cis=(cos_ref, sin_ref), encoder_hidden_states=enc,
+                    timestep=ts, encoder_attention_mask=mask, skip_layer_mask=skip,
+                    skip_layer_strategy=strat_ref, latent_shape=(f, h, w), joint_pass=True,
+                    ltxv_model=_NoInterrupt(), return_dict=False)[0]
+        y = O.transformer_forward(sd, cfg, hidden, (cos, sin), enc, ts, mask, skip, strat, (f, h, w))
+        _check(f"transformer[{tag}]", y, y_ref)
+        out[tag] = dict(hidden=hidden, enc=enc, mask=mask, timestep=ts, out=y_ref,
+                        skip=skip)
+    out["rope_cos_row5"] = cos_ref[0, 5].clone()
+    out["rope_sin_row5"] = sin_ref[0, 5].clone()
+    torch.save(out, os.path.join(GOLD, "ltx_transformer.pt"))
+
+
+def case_scheduler():
+    from ltx_video.schedulers.rf import RectifiedFlowScheduler
+    from ltx_video.utils.diffusers_config_mapping import OURS_SCHEDULER_CONFIG
+    out = {}
+    for steps, shape in ((4, (1, 128, 2, 8, 8)), (30, (1, 128, 16, 16, 24)), (40, (2, 128, 4, 16, 16)), (7, (1, 77, 128))):
+        s = RectifiedFlowScheduler.from_config(dict(OURS_SCHEDULER_CONFIG))
+        s.set_timesteps(steps, samples_shape=shape, device="cpu")
+        mine = O.rf_timesteps(steps, shape)
+        assert torch.equal(mine, s.timesteps), (mine, s.timesteps)
+        g = torch.Generator().manual_seed(steps)
+        x = torch.randn(1, 24, 128, generator=g)
+        v = torch.randn(1, 24, 128, generator=g)
+        # per-token branch as the pipeline calls it ([1,1] timestep) and a ragged per-token one
+        for i in (0, steps // 2, steps - 1):
+            t = s.timesteps[i][None, None]
+            a = s.step(v, t, x, return_dict=False)[0]
+            b = O.rf_step(v, t, x, s.timesteps)
+            assert torch.equal(a, b)
+        tt = torch.full((1, 24), float(s.timesteps[1]))
+        tt[:, :5] = 0.0
+        a = s.step(v, tt, x, return_dict=False)[0]
+        b = O.rf_step(v, tt, x, s.timesteps)
+        assert torch.equal(a, b)
+        a0 = s.step(v, s.timesteps[1], x, return_dict=False)[0]
+        assert torch.equal(a0, O.rf_step(v, s.timesteps[1], x, s.timesteps))
+        out[f"{steps}_{'x'.join(map(str, shape))}"] = dict(steps=steps, shape=shape, timesteps=s.timesteps.clone(),
+                                                           x=x, v=v, tt=tt, stepped=a)
+    print("  scheduler: timesteps + step bit-exact")
+    torch.save(out, os.path.join(GOLD, "rf_scheduler.pt"))
+
+
+def case_patchifier():
+    from ltx_video.models.transformers.symmetric_patchifier import SymmetricPatchifier
+    from ltx_video.models.autoencoders.vae_encode import latent_to_pixel_coords_from_factors
+    p = SymmetricPatchifier(patch_size=1)
+    x = torch.arange(2 * 5 * 3 * 4 * 6, dtype=torch.float32).reshape(2, 5, 3, 4, 6)
+    tok, coords = p.patchify(x)
+    assert torch.equal(tok, O.patchify(x))
+    assert torch.equal(coords, O.latent_coords(3, 4, 6, 2))
+    back = p.unpatchify(tok, 4, 6, 5)
+    assert torch.equal(back, O.unpatchify(tok, 3, 4, 6)) and torch.equal(back, x)
+    for fix in (False, True):
+        a = latent_to_pixel_coords_from_factors(coords, (8, 32, 32), fix)
+        assert torch.equal(a, O.latent_to_pixel_coords(coords, (8, 32, 32), fix))
+    print("  patchifier/coords: bit-exact")
+    torch.save(dict(coords=coords, px=O.latent_to_pixel_coords(coords), px_fix=O.latent_to_pixel_coords(coords, causal_fix=True)),
+               os.path.join(GOLD, "patchifier.pt"))
+
+
+def build_ref_vae(sd):
+    from ltx_video.models.autoencoders.causal_video_autoencoder import CausalVideoAutoencoder
+    from ltx_video.utils.diffusers_config_mapping import OURS_VAE_CONFIG
+    vae = CausalVideoAutoencoder.from_config(dict(OURS_VAE_CONFIG))
+    dec_sd = {k[len("decoder."):]: v for k, v in sd.items() if k.startswith("decoder.")}
+    vae.decoder.load_state_dict(dec_sd, strict=True)
+    vae.register_buffer("std_of_means", sd["std_of_means"])
+    vae.register_buffer("mean_of_means", sd["mean_of_means"])
+    return vae.eval()
+
+
+def case_vae():
+    from ltx_video.models.autoencoders.vae_encode import vae_decode
+    sd = O.make_vae_decoder_state_dict(seed=1)
+    vae = build_ref_vae(sd)
+    g = torch.Generator().manual_seed(5)
+    z = torch.randn(1, 128, 2, 3, 4, generator=g)
+    y_ref = vae_decode(z, vae, is_video=True, vae_per_channel_normalize=True)
+    y = O.vae_decode(sd, z)
+    _check("vae_decode", y, y_ref, tol=1e-4)
+    assert y_ref.shape == (1, 3, 9, 96, 128)
+    # the reference's own in-file check: patchify∘unpatchify == identity (causal_video_autoencoder.py:1341-1347)
+    from ltx_video.models.autoencoders.causal_video_autoencoder import patchify as rp, unpatchify as ru
+    xx = torch.randn(2, 3, 8, 64, 64, generator=g)
+    assert torch.equal(ru(rp(xx, 4, 1), 4, 1), xx)
+    assert torch.equal(ru(rp(xx, 4, 1), 4, 1), O.vae_unpatchify(rp(xx, 4, 1), 4))
+    torch.save(dict(z=z, out=y_ref.to(torch.float16), seed_weights=1), os.path.join(GOLD, "ltx_vae_decode.pt"))
+
+
+@contextlib.contextmanager
+def _cuda_to_cpu():
+    """pipeline_ltx_video.py:1041 hard-codes .to("cuda"); map it to cpu for the CPU run."""
+    orig = torch.Tensor.to
+
+    def to(self, *a, **k):
+        a = tuple("cpu" if (isinstance(x, str) and x == "cuda") else x for x in a)
+        return orig(self, *a, **k)
+
+    torch.Tensor.to = to
+    try:
+        yield
+    finally:
+        torch.Tensor.to = orig
+
+
+def case_pipeline():
+    """LTXVideoPipeline.__call__ (output_type='latent'): guidance off, CFG+STG+rescale preset,
+    and the i2v per-token-timestep path via a conditioning mask (driven through latents)."""
+    from ltx_video.pipelines.pipeline_ltx_video import LTXVideoPipeline
+    from ltx_video.schedulers.rf import RectifiedFlowScheduler
+    from ltx_video.models.transformers.symmetric_patchifier import SymmetricPatchifier
+    from ltx_video.utils.diffusers_config_mapping import OURS_SCHEDULER_CONFIG
+    from ltx_video.utils.skip_layer_strategy import SkipLayerStrategy
+    cfg = O.LTX_2B
+    L = 2
+    sd = O.make_transformer_state_dict(cfg, seed=0, num_layers=L)
+    tr = build_ref_transformer(L, sd)
+    vsd = O.make_vae_decoder_state_dict(seed=1)
+    vae = build_ref_vae(vsd)
+    pipe = LTXVideoPipeline(tokenizer=None, text_encoder=None, vae=vae, transformer=tr,
+                            scheduler=RectifiedFlowScheduler.from_config(dict(OURS_SCHEDULER_CONFIG)),
+                            patchifier=SymmetricPatchifier(patch_size=1),
+                            prompt_enhancer_image_caption_model=None,
+                            prompt_enhancer_image_caption_processor=None,
+                            prompt_enhancer_llm_model=None, prompt_enhancer_llm_tokenizer=None)
+    H, W, F_, fps, steps = 128, 192, 17, 25.0, 4          # latent (1,128,3,4,6), N=72
+    g = torch.Generator().manual_seed(42)
+    pe = torch.randn(1, 32, 4096, generator=g)
+    ne = torch.randn(1, 32, 4096, generator=g)
+    pm = torch.ones(1, 32); pm[:, 20:] = 0
+    nm = torch.ones(1, 32); nm[:, 9:] = 0
+    out = {"meta": dict(H=H, W=W, F=F_, fps=fps, steps=steps, num_layers=L)}
+    cwd = os.getcwd()
+    os.chdir("/tmp")                                          # 'lala.pt' side effect (:1288)
+    try:
+        for tag, kw in (("plain", dict(guidance_scale=1.0, stg_scale=0.0, rescaling_scale=1.0)),
+                        ("cfg_stg", dict(guidance_scale=3.0, stg_scale=1.0, rescaling_scale=0.7,
+                                         skip_block_list=[1],
+                                         skip_layer_strategy=SkipLayerStrategy.AttentionValues))):
+            per_step = []
+            gen = torch.Generator().manual_seed(7)
+            with _cuda_to_cpu():
+                lat = pipe(height=H, width=W, num_frames=F_, frame_rate=fps, prompt_embeds=pe,
+                           prompt_attention_mask=pm, negative_prompt_embeds=ne,
+                           negative_prompt_attention_mask=nm, num_inference_steps=steps,
+                           generator=gen, output_type="latent", return_dict=False, joint_pass=True,
+                           ltxv_model=_NoInterrupt(), is_video=True, vae_per_channel_normalize=True,
+                           callback_on_step_end=None, **kw)[0]
+            # same initial noise the pipeline drew (prepare_latents :696-699)
+            gen = torch.Generator().manual_seed(7)
+            noise = torch.randn(1, 3 * 4 * 6, 128, generator=gen)
+            mine = O.denoise_loop(sd, cfg, noise, pe, pm, num_frames_lat=3, lat_h=4, lat_w=6,
+                                  frame_rate=fps, num_steps=steps, neg_enc=ne, neg_mask=nm,
+                                  guidance_scale=kw["guidance_scale"], stg_scale=kw["stg_scale"],
+                                  rescaling_scale=kw["rescaling_scale"],
+                                  skip_block_list=kw.get("skip_block_list"),
+                                  strategy=O.SKIP_ATTENTION_VALUES if "skip_block_list" in kw else None,
+                                  per_step=per_step)
+            mine5 = O.unpatchify(mine, 3, 4, 6)
+            _check(f"pipeline[{tag}] final latents", mine5, lat, tol=5e-5)
+            out[tag] = dict(latents=lat, kw={k: (v if not hasattr(v, "name") else v.name) for k, v in kw.items()})
+        # decoded frames for the plain case through the reference pipeline (full path)
+        gen = torch.Generator().manual_seed(7)
+        with _cuda_to_cpu():
+            img = pipe(height=H, width=W, num_frames=F_, frame_rate=fps, prompt_embeds=pe,
+                       prompt_attention_mask=pm, negative_prompt_embeds=ne,
+                       negative_prompt_attention_mask=nm, num_inference_steps=steps,
+                       generator=gen, output_type="pt", return_dict=False, joint_pass=True,
+                       ltxv_model=_NoInterrupt(), is_video=True, vae_per_channel_normalize=True,
+                       guidance_scale=1.0, stg_scale=0.0, rescaling_scale=1.0)[0]
+        mine_img = O.postprocess(O.vae_decode(vsd, O.unpatchify(
+            O.denoise_loop(sd, cfg, torch.randn(1, 72, 128, generator=torch.Generator().manual_seed(7)), pe, pm,
+                           num_frames_lat=3, lat_h=4, lat_w=6, frame_rate=fps, num_steps=steps), 3, 4, 6)))
+        print(f"  pipeline decoded frames: PSNR(oracle, reference) = {O.psnr(mine_img, img):.1f} dB")
+        assert O.psnr(mine_img, img) > 80
+        out["plain"]["frames_sub"] = img[:, :, ::4, ::8, ::8].to(torch.float16).clone()
+    finally:
+        os.chdir(cwd)
+    out.update(pe=pe, ne=ne, pm=pm, nm=nm, noise_seed=7)
+    torch.save(out, os.path.join(GOLD, "ltx_pipeline.pt"))
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["patchifier", "scheduler", "transformer", "vae", "pipeline"]
+    for w in which:
+        print(f"[{w}]")
+        globals()["case_" + w]()
+    print("golden fixtures written to", GOLD)

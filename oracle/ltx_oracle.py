@@ -1,0 +1,585 @@
+"""CPU oracle for the LTX-Video denoising hot path (TEST INFRASTRUCTURE ONLY).
+
+A plain-PyTorch restatement of the reference's algorithm, operating on a flat
+``state_dict`` with the reference's own key names.  It is the checker for the CUDA
+path: only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
+``--impl reference`` legs may import it.  The product package never does.
+
+Pinning: ``oracle/gen_golden.py`` runs the UNMODIFIED reference modules (imported
+from /root/reference through ``oracle/refshim``) on the same seeded weights/inputs
+and asserts this file reproduces them (fp32, CPU) before writing tests/golden/*.
+The diffusers pieces the reference calls (AdaLayerNormSingle, RMSNorm, GELU,
+PixArtAlphaTextProjection) are third-party (diffusers>=0.31, requirements.txt:4,
+not vendored): they are restated here from the published v0.31 source; no
+reference test pins them ("parity unpinned" for that boundary).
+
+Every function cites the reference file:line it follows.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+
+# --------------------------------------------------------------------------------------
+# Architecture constants (ltx_video/utils/diffusers_config_mapping.py:74-130)
+# --------------------------------------------------------------------------------------
+LTX_2B = dict(
+    num_layers=28, num_attention_heads=32, attention_head_dim=64, in_channels=128,
+    out_channels=128, cross_attention_dim=2048, caption_channels=4096,
+    norm_eps=1e-6, qk_norm_eps=1e-5, rope_theta=10000.0, rope_max_pos=(20, 2048, 2048),
+    timestep_scale_multiplier=1000.0, ff_mult=4,
+)
+
+# decoder block list = reversed(OURS_VAE_CONFIG["blocks"]) (causal_video_autoencoder.py:609,629)
+LTX_VAE = dict(
+    latent_channels=128, out_channels=3, patch_size=4, base_channels=128,
+    blocks=[["res_x", 4], ["compress_all", 1], ["res_x_y", 1], ["res_x", 3],
+            ["compress_all", 1], ["res_x_y", 1], ["res_x", 3], ["compress_all", 1],
+            ["res_x", 3], ["res_x", 4]],
+    causal_decoder=False,
+)
+
+SKIP_ATTENTION_VALUES = "attention_values"   # SkipLayerStrategy.AttentionValues
+SKIP_ATTENTION_SKIP = "attention_skip"
+SKIP_RESIDUAL = "residual"
+SKIP_TRANSFORMER_BLOCK = "transformer_block"
+
+
+# --------------------------------------------------------------------------------------
+# Seeded random-init weights of the named architecture (no checkpoints: no network)
+# --------------------------------------------------------------------------------------
+def _uniform(gen, shape, bound, dtype=torch.float32):
+    return (torch.rand(shape, generator=gen, dtype=torch.float32) * 2 - 1).mul_(bound).to(dtype)
+
+
+def _linear(sd, gen, name, out_f, in_f, bias=True):
+    b = 1.0 / math.sqrt(in_f)      # nn.Linear default: kaiming_uniform(a=sqrt(5)) == U(+-1/sqrt(fan_in))
+    sd[name + ".weight"] = _uniform(gen, (out_f, in_f), b)
+    if bias:
+        sd[name + ".bias"] = _uniform(gen, (out_f,), b)
+
+
+def make_transformer_state_dict(cfg: dict = LTX_2B, seed: int = 0, num_layers: Optional[int] = None
+                                ) -> Dict[str, Tensor]:
+    """Random-init fp32 state_dict with the key names/shapes of Transformer3DModel
+    (transformer3d.py:91-156, attention.py:124-185,477-558,1263-1310)."""
+    gen = torch.Generator(device="cpu").manual_seed(seed)
+    D = cfg["num_attention_heads"] * cfg["attention_head_dim"]
+    L = cfg["num_layers"] if num_layers is None else num_layers
+    sd: Dict[str, Tensor] = {}
+    sd["scale_shift_table"] = torch.randn(2, D, generator=gen) / D ** 0.5
+    _linear(sd, gen, "patchify_proj", D, cfg["in_channels"])
+    for i in range(L):
+        p = f"transformer_blocks.{i}."
+        sd[p + "scale_shift_table"] = torch.randn(6, D, generator=gen) / D ** 0.5
+        for a, kv_dim in (("attn1", D), ("attn2", cfg["cross_attention_dim"])):
+            # RMSNorm weights init to ones in the reference; perturb so the test sees them
+            sd[p + a + ".q_norm.weight"] = 1.0 + 0.1 * torch.randn(D, generator=gen)
+            sd[p + a + ".k_norm.weight"] = 1.0 + 0.1 * torch.randn(D, generator=gen)
+            _linear(sd, gen, p + a + ".to_q", D, D)
+            _linear(sd, gen, p + a + ".to_k", D, kv_dim)
+            _linear(sd, gen, p + a + ".to_v", D, kv_dim)
+            _linear(sd, gen, p + a + ".to_out.0", D, D)
+        _linear(sd, gen, p + "ff.net.0.proj", cfg["ff_mult"] * D, D)
+        _linear(sd, gen, p + "ff.net.2", D, cfg["ff_mult"] * D)
+    _linear(sd, gen, "proj_out", cfg["out_channels"], D)
+    _linear(sd, gen, "adaln_single.emb.timestep_embedder.linear_1", D, 256)
+    _linear(sd, gen, "adaln_single.emb.timestep_embedder.linear_2", D, D)
+    _linear(sd, gen, "adaln_single.linear", 6 * D, D)
+    _linear(sd, gen, "caption_projection.linear_1", D, cfg["caption_channels"])
+    _linear(sd, gen, "caption_projection.linear_2", D, D)
+    return sd
+
+
+def vae_decoder_plan(cfg: dict = LTX_VAE) -> List[Tuple[str, int, int, int]]:
+    """[(kind, index, c_in, c_out)] for decoder.up_blocks (causal_video_autoencoder.py:609-700).
+    kind in {"res_x" (n layers packed as index list), "res_x_y", "d2s"}."""
+    ch = cfg["base_channels"]
+    for name, p in reversed(cfg["blocks"]):
+        if name == "res_x_y":
+            ch *= 2
+    plan = []
+    for idx, (name, p) in enumerate(reversed(cfg["blocks"])):
+        if name == "res_x":
+            plan.append(("res_x", idx, ch, ch, int(p)))
+        elif name == "res_x_y":
+            plan.append(("res_x_y", idx, ch, ch // 2, 1))
+            ch //= 2
+        elif name == "compress_all":
+            plan.append(("d2s", idx, ch, ch, 1))
+        else:
+            raise ValueError(name)
+    return plan
+
+
+def vae_top_channels(cfg: dict = LTX_VAE) -> int:
+    ch = cfg["base_channels"]
+    for name, _ in cfg["blocks"]:
+        if name == "res_x_y":
+            ch *= 2
+    return ch
+
+
+def _conv3d(sd, gen, name, c_out, c_in, k=3):
+    fan_in = c_in * k * k * k
+    b = 1.0 / math.sqrt(fan_in)
+    sd[name + ".weight"] = _uniform(gen, (c_out, c_in, k, k, k), b)
+    sd[name + ".bias"] = _uniform(gen, (c_out,), b)
+
+
+def make_vae_decoder_state_dict(cfg: dict = LTX_VAE, seed: int = 1) -> Dict[str, Tensor]:
+    """Random-init decoder weights + per-channel latent statistics (keys as in
+    causal_video_autoencoder.py; statistics as registered by load_state_dict :285-297)."""
+    gen = torch.Generator(device="cpu").manual_seed(seed)
+    sd: Dict[str, Tensor] = {}
+    top = vae_top_channels(cfg)
+    _conv3d(sd, gen, "decoder.conv_in.conv", top, cfg["latent_channels"])
+    for kind, idx, cin, cout, n in vae_decoder_plan(cfg):
+        p = f"decoder.up_blocks.{idx}."
+        if kind == "res_x":
+            for j in range(n):
+                _conv3d(sd, gen, p + f"res_blocks.{j}.conv1.conv", cin, cin)
+                _conv3d(sd, gen, p + f"res_blocks.{j}.conv2.conv", cin, cin)
+        elif kind == "res_x_y":
+            _conv3d(sd, gen, p + "conv1.conv", cout, cin)
+            _conv3d(sd, gen, p + "conv2.conv", cout, cout)
+            _conv3d(sd, gen, p + "conv_shortcut", cout, cin, k=1)
+            sd[p + "norm3.norm.weight"] = 1.0 + 0.1 * torch.randn(cin, generator=gen)
+            sd[p + "norm3.norm.bias"] = 0.1 * torch.randn(cin, generator=gen)
+        else:
+            _conv3d(sd, gen, p + "conv.conv", 8 * cin, cin)
+    last = cfg["base_channels"]
+    _conv3d(sd, gen, "decoder.conv_out.conv", cfg["out_channels"] * cfg["patch_size"] ** 2, last)
+    sd["std_of_means"] = 0.5 + torch.rand(cfg["latent_channels"], generator=gen)
+    sd["mean_of_means"] = 0.1 * torch.randn(cfg["latent_channels"], generator=gen)
+    return sd
+
+
+# --------------------------------------------------------------------------------------
+# Patchifier / coordinates — integer, bit-exact (symmetric_patchifier.py:33-84,
+# vae_encode.py:190-225)
+# --------------------------------------------------------------------------------------
+def patchify(latents: Tensor) -> Tensor:
+    """b c f h w -> b (f h w) c   (patch size 1; symmetric_patchifier.py:55-65)"""
+    b, c, f, h, w = latents.shape
+    return latents.permute(0, 2, 3, 4, 1).reshape(b, f * h * w, c)
+
+
+def unpatchify(tokens: Tensor, f: int, h: int, w: int) -> Tensor:
+    """b (f h w) c -> b c f h w   (symmetric_patchifier.py:67-84)"""
+    b, n, c = tokens.shape
+    return tokens.reshape(b, f, h, w, c).permute(0, 4, 1, 2, 3)
+
+
+def latent_coords(f: int, h: int, w: int, batch: int, device="cpu") -> Tensor:
+    """int64 [b,3,f*h*w] of (t,y,x) latent corner coords (symmetric_patchifier.py:33-51)."""
+    g = torch.meshgrid(torch.arange(f, device=device), torch.arange(h, device=device),
+                       torch.arange(w, device=device), indexing="ij")
+    c = torch.stack(g, dim=0).reshape(3, -1)
+    return c.unsqueeze(0).repeat(batch, 1, 1)
+
+
+def latent_to_pixel_coords(coords: Tensor, scale=(8, 32, 32), causal_fix: bool = False) -> Tensor:
+    """vae_encode.py:214-225"""
+    px = coords * torch.tensor(scale, device=coords.device)[None, :, None]
+    if causal_fix:
+        px[:, 0] = (px[:, 0] + 1 - scale[0]).clamp(min=0)
+    return px
+
+
+# --------------------------------------------------------------------------------------
+# RoPE table (transformer3d.py:192-255) and application (attention.py:960-975)
+# --------------------------------------------------------------------------------------
+def rope_freq_indices(dim: int, theta: float, device="cpu") -> Tensor:
+    """theta ** linspace(0, 1, dim//6) * pi/2   (transformer3d.py:213-233, spacing 'exp')"""
+    idx = theta ** torch.linspace(math.log(1, theta), math.log(theta, theta), dim // 6,
+                                  device=device, dtype=torch.float32)
+    return idx.to(torch.float32) * math.pi / 2
+
+
+def precompute_freqs_cis(indices_grid: Tensor, dim: int, theta: float, max_pos: Sequence[int],
+                         out_dtype=torch.float32) -> Tuple[Tensor, Tensor]:
+    """indices_grid float [B,3,N] -> (cos, sin) [B,N,dim] (transformer3d.py:202-255)."""
+    frac = torch.stack([indices_grid[:, i] / max_pos[i] for i in range(3)], dim=-1)  # [B,N,3]
+    indices = rope_freq_indices(dim, theta, frac.device)
+    freqs = (indices * (frac.unsqueeze(-1) * 2 - 1)).transpose(-1, -2).flatten(2)   # [B,N,F*3] (freq-major)
+    cos = freqs.cos().repeat_interleave(2, dim=-1)
+    sin = freqs.sin().repeat_interleave(2, dim=-1)
+    if dim % 6 != 0:
+        cos = torch.cat([torch.ones_like(cos[:, :, : dim % 6]), cos], dim=-1)
+        sin = torch.cat([torch.zeros_like(sin[:, :, : dim % 6]), sin], dim=-1)
+    return cos.to(out_dtype), sin.to(out_dtype)
+
+
+def apply_rotary_emb(x: Tensor, cos: Tensor, sin: Tensor) -> Tensor:
+    """pairs (2i,2i+1) -> (-x[2i+1], x[2i]) (attention.py:960-975)"""
+    x2 = x.reshape(*x.shape[:-1], -1, 2)
+    rot = torch.stack((-x2[..., 1], x2[..., 0]), dim=-1).reshape(x.shape)
+    return x * cos + rot * sin
+
+
+# --------------------------------------------------------------------------------------
+# diffusers pieces (restated; see module docstring)
+# --------------------------------------------------------------------------------------
+def timestep_sinusoid(t: Tensor, dim: int = 256) -> Tensor:
+    """diffusers get_timestep_embedding(flip_sin_to_cos=True, downscale_freq_shift=0)."""
+    half = dim // 2
+    exponent = -math.log(10000) * torch.arange(half, dtype=torch.float32, device=t.device) / half
+    emb = t[:, None].float() * torch.exp(exponent)[None, :]
+    return torch.cat([torch.cos(emb), torch.sin(emb)], dim=-1)
+
+
+def rms_norm(x: Tensor, eps: float, weight: Optional[Tensor] = None) -> Tensor:
+    """diffusers RMSNorm.forward: fp32 variance, x*rsqrt, cast to weight dtype, *weight."""
+    dt = x.dtype
+    var = x.to(torch.float32).pow(2).mean(-1, keepdim=True)
+    y = x * torch.rsqrt(var + eps)
+    if weight is not None:
+        if weight.dtype in (torch.float16, torch.bfloat16):
+            y = y.to(weight.dtype)
+        return y * weight
+    return y.to(dt)
+
+
+def linear(sd, name, x):
+    return F.linear(x, sd[name + ".weight"], sd.get(name + ".bias"))
+
+
+def adaln_single(sd, t_flat: Tensor, dtype) -> Tuple[Tensor, Tensor]:
+    """AdaLayerNormSingle (diffusers) as used at transformer3d.py:428-433."""
+    proj = timestep_sinusoid(t_flat).to(dtype)
+    e = linear(sd, "adaln_single.emb.timestep_embedder.linear_1", proj)
+    e = linear(sd, "adaln_single.emb.timestep_embedder.linear_2", F.silu(e))
+    return linear(sd, "adaln_single.linear", F.silu(e)), e
+
+
+def attention_core(q: Tensor, k: Tensor, v: Tensor, bias: Optional[Tensor] = None) -> Tensor:
+    """Non-causal softmax attention, layout [B, L, H, d] in and out, scale d^-0.5
+    (utils/attention.py:99-116 sdpa_wrapper semantics).  bias: additive, broadcastable
+    to [B, H, Lq, Lk].  Explicit fp32 math, chunked over heads to bound memory."""
+    B, Lq, H, d = q.shape
+    out = torch.empty_like(q)
+    scale = d ** -0.5
+    hc = max(1, min(H, (1 << 28) // max(1, Lq * k.shape[1])))
+    for h0 in range(0, H, hc):
+        qs = q[:, :, h0:h0 + hc].permute(0, 2, 1, 3).float()
+        ks = k[:, :, h0:h0 + hc].permute(0, 2, 1, 3).float()
+        vs = v[:, :, h0:h0 + hc].permute(0, 2, 1, 3).float()
+        s = torch.matmul(qs, ks.transpose(-1, -2)) * scale
+        if bias is not None:
+            b = bias.float()
+            if b.shape[1] != 1:
+                b = b[:, h0:h0 + hc]
+            s = s + b
+        p = torch.softmax(s, dim=-1)
+        out[:, :, h0:h0 + hc] = torch.matmul(p, vs).permute(0, 2, 1, 3).to(q.dtype)
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# Transformer block and model forward
+# --------------------------------------------------------------------------------------
+def _attn(sd, p, x, ctx, heads, cos_sin, bias, eps_qk, skip_mask=None, strategy=None):
+    """AttnProcessor2_0.__call__ (attention.py:986-1173); p = 'transformer_blocks.i.attn1'."""
+    B = x.shape[0]
+    is_self = ctx is None
+    src = x if is_self else ctx
+    q = rms_norm(linear(sd, p + ".to_q", x), eps_qk, sd[p + ".q_norm.weight"])
+    k = rms_norm(linear(sd, p + ".to_k", src), eps_qk, sd[p + ".k_norm.weight"])
+    if is_self and cos_sin is not None:
+        k = apply_rotary_emb(k, *cos_sin)
+        q = apply_rotary_emb(q, *cos_sin)
+    v = linear(sd, p + ".to_v", src)
+    d = q.shape[-1] // heads
+    o = attention_core(q.reshape(B, -1, heads, d), k.reshape(B, -1, heads, d),
+                       v.reshape(B, -1, heads, d), bias).reshape(B, -1, heads * d)
+    if skip_mask is not None and strategy == SKIP_ATTENTION_VALUES:
+        m = skip_mask.reshape(B, 1, 1).to(o.dtype)
+        o = o * m + v * (1.0 - m)                       # attention.py:1134-1139
+    elif skip_mask is not None and strategy == SKIP_ATTENTION_SKIP:
+        m = skip_mask.reshape(B, 1, 1).to(o.dtype)
+        o = o * m + x * (1.0 - m)                       # attention.py:1127-1133
+    return linear(sd, p + ".to_out.0", o)
+
+
+def transformer_block(sd, i, h, cos_sin, ctx, ctx_bias, temb6, cfg, skip_mask=None, strategy=None):
+    """BasicTransformerBlock.forward (attention.py:205-364), adaptive_norm single_scale_shift,
+    rms_norm standardisation, no affine.  temb6: [B, T, 6*D] with T = 1 or latent frames."""
+    p = f"transformer_blocks.{i}."
+    B, N, D = h.shape
+    H = cfg["num_attention_heads"]
+    if skip_mask is not None and float(skip_mask.flatten().min()) == 1.0:
+        skip_mask = None
+    T = temb6.shape[1]
+    ada = sd[p + "scale_shift_table"][None, None] + temb6.reshape(B, T, 6, D)     # :239-241
+    shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp = [
+        a.unsqueeze(2) for a in ada.unbind(dim=2)]                                  # [B,T,1,D]
+
+    def mod(x, scale, shift):
+        x = x.reshape(B, T, -1, D)
+        x = x * (1 + scale) + shift
+        return x.reshape(B, N, D)
+
+    original = h
+    nh = mod(rms_norm(h, cfg["norm_eps"]), scale_msa, shift_msa)
+    a = _attn(sd, p + "attn1", nh, None, H, cos_sin, None, cfg["qk_norm_eps"], skip_mask, strategy)
+    h = h + (a.reshape(B, T, -1, D) * gate_msa).reshape(B, N, D)                    # :282-288
+    a = _attn(sd, p + "attn2", h, ctx, H, None, ctx_bias, cfg["qk_norm_eps"])       # :294-311
+    h = h + a
+    nh = mod(rms_norm(h, cfg["norm_eps"]), scale_mlp, shift_mlp)                    # :314-320
+    ff = linear(sd, p + "ff.net.2", F.gelu(linear(sd, p + "ff.net.0.proj", nh), approximate="tanh"))
+    h = h + (ff.reshape(B, T, -1, D) * gate_mlp).reshape(B, N, D)                   # :345-351
+    if skip_mask is not None and strategy == SKIP_TRANSFORMER_BLOCK:
+        m = skip_mask.reshape(-1, 1, 1).to(h.dtype)
+        h = h * m + original * (1.0 - m)                                            # :355-362
+    return h
+
+
+def transformer_forward(sd: Dict[str, Tensor], cfg: dict, hidden: Tensor, cos_sin, enc: Tensor,
+                        timestep: Tensor, enc_mask: Optional[Tensor] = None,
+                        skip_layer_mask: Optional[Tensor] = None, strategy: Optional[str] = None,
+                        latent_shape: Optional[Sequence[int]] = None,
+                        collect: Optional[list] = None) -> Tensor:
+    """Transformer3DModel.forward (transformer3d.py:328-507), joint_pass=True.
+    hidden [B,N,128]; cos_sin (cos,sin) [1|B,N,D]; enc [B,L,4096]; timestep [B,1]|[B,N];
+    enc_mask [B,L] (1 keep / 0 drop); skip_layer_mask [layers,B]."""
+    dtype = hidden.dtype
+    L = sum(1 for k in sd if k.endswith(".attn1.to_q.weight"))
+    ctx_bias = None
+    if enc_mask is not None:
+        ctx_bias = ((1 - enc_mask.to(dtype)) * -10000.0)[:, None, None, :]          # :411-415 -> [B,1,1,L]
+    h = linear(sd, "patchify_proj", hidden)                                         # :418
+    t = cfg["timestep_scale_multiplier"] * timestep                                  # :420-421
+    if t.shape[-1] > 1:                                                              # :423-425
+        t = t.reshape(t.shape[0], -1, latent_shape[-2] * latent_shape[-1])[:, :, 0]
+    B = h.shape[0]
+    temb6, emb = adaln_single(sd, t.flatten(), dtype)
+    temb6 = temb6.view(B, -1, temb6.shape[-1])
+    emb = emb.view(B, -1, emb.shape[-1])
+    ctx = linear(sd, "caption_projection.linear_2",
+                 F.gelu(linear(sd, "caption_projection.linear_1", enc), approximate="tanh"))
+    ctx = ctx.view(B, -1, h.shape[-1])                                              # :446-451
+    for i in range(L):
+        h = transformer_block(sd, i, h, cos_sin, ctx, ctx_bias, temb6, cfg,
+                              None if skip_layer_mask is None else skip_layer_mask[i], strategy)
+        if collect is not None:
+            collect.append(h)
+    ss = sd["scale_shift_table"][None, None] + emb[:, :, None]                      # :490-493
+    shift, scale = ss[:, :, 0].unsqueeze(-2), ss[:, :, 1].unsqueeze(-2)
+    D = h.shape[-1]
+    h = F.layer_norm(h, (D,), eps=1e-6)                                             # :494
+    T = scale.shape[1]
+    h = (h.reshape(B, T, -1, D) * (1 + scale) + shift).reshape(B, -1, D)            # :498-502
+    return linear(sd, "proj_out", h)
+
+
+# --------------------------------------------------------------------------------------
+# RectifiedFlowScheduler (rf.py)
+# --------------------------------------------------------------------------------------
+def rf_timesteps(num_steps: int, samples_shape: Sequence[int], terminal: Optional[float] = 0.1
+                 ) -> Tensor:
+    """set_timesteps with shifting='SD3' (rf.py:69-149,196-257)."""
+    t = torch.linspace(1, 1 / num_steps, num_steps)
+    m = samples_shape[1] if len(samples_shape) == 3 else math.prod(samples_shape[2:])
+    slope = (2.05 - 0.95) / (4096 - 1024)
+    mu = slope * m + (0.95 - slope * 1024)                                           # :73-82
+    ts = math.exp(mu) / (math.exp(mu) + (1 / t - 1) ** 1)                            # :69-70
+    if terminal is not None:                                                         # :85-109
+        one_minus = 1 - ts
+        ts = 1 - (one_minus / (one_minus[-1] / (1 - terminal)))
+    return ts
+
+
+def rf_step(model_output: Tensor, timestep: Tensor, sample: Tensor, timesteps: Tensor) -> Tensor:
+    """RectifiedFlowScheduler.step, deterministic branch (rf.py:311-380)."""
+    t_eps = 1e-6
+    padded = torch.cat([timesteps, torch.zeros(1, device=timesteps.device)])
+    if timestep.ndim == 0:
+        lower = padded[padded < timestep - t_eps][0]
+        dt = timestep - lower
+    else:
+        assert timestep.ndim == 2
+        lower_mask = padded[:, None, None] < timestep[None] - t_eps
+        lower, _ = (lower_mask * padded[:, None, None]).max(dim=0)
+        dt = (timestep - lower)[..., None]
+    return sample - dt * model_output
+
+
+# --------------------------------------------------------------------------------------
+# Guidance arithmetic + denoise loop (pipeline_ltx_video.py:1103-1256,1309-1342)
+# --------------------------------------------------------------------------------------
+def guidance_combine(noise_pred: Tensor, num_conds: int, do_cfg: bool, do_stg: bool,
+                     guidance_scale: float, stg_scale: float, rescaling_scale: float,
+                     do_rescaling: bool) -> Tensor:
+    """pipeline_ltx_video.py:1183-1222 (cfg_star_rescale=True).  noise_pred [num_conds*b, N, C]."""
+    chunks = noise_pred.chunk(num_conds)
+    batch = chunks[0].shape[0]
+    if do_stg:
+        text, perturb = chunks[-2:]
+    if do_cfg and guidance_scale != 0 and guidance_scale != 1:
+        uncond, text = chunks[:2]
+        pos = text.reshape(batch, -1)
+        neg = uncond.reshape(batch, -1)
+        alpha = torch.sum(pos * neg, dim=1, keepdim=True) / (torch.sum(neg ** 2, dim=1, keepdim=True) + 1e-8)
+        uncond = alpha.view(batch, 1, 1) * uncond if uncond.ndim == 3 else alpha * uncond
+        out = uncond + guidance_scale * (text - uncond)
+    elif do_stg:
+        out = text
+    else:
+        out = noise_pred
+    if do_stg:
+        out = out + stg_scale * (text - perturb)
+        if do_rescaling and stg_scale > 0.0:
+            f = text.reshape(batch, -1).std(dim=1, keepdim=True) / out.reshape(batch, -1).std(dim=1, keepdim=True)
+            f = rescaling_scale * f + (1 - rescaling_scale)
+            out = out * f.view(batch, 1, 1)
+    return out
+
+
+def denoise_loop(sd, cfg, latents: Tensor, enc: Tensor, enc_mask: Tensor, *, num_frames_lat: int,
+                 lat_h: int, lat_w: int, frame_rate: float, num_steps: int,
+                 neg_enc: Optional[Tensor] = None, neg_mask: Optional[Tensor] = None,
+                 guidance_scale: float = 1.0, stg_scale: float = 0.0, rescaling_scale: float = 1.0,
+                 skip_block_list: Optional[List[int]] = None, strategy: Optional[str] = None,
+                 conditioning_mask: Optional[Tensor] = None, model_dtype=torch.float32,
+                 per_step: Optional[list] = None, timesteps: Optional[Tensor] = None) -> Tensor:
+    """LTXVideoPipeline.__call__ denoise loop (pipeline_ltx_video.py:919-1268) on patchified
+    latents [b, N, C]; returns final patchified latents.  image_cond_noise_scale = 0."""
+    b, N, C = latents.shape
+    D = cfg["num_attention_heads"] * cfg["attention_head_dim"]
+    if timesteps is None:
+        timesteps = rf_timesteps(num_steps, (b, C, num_frames_lat, lat_h, lat_w))
+    timesteps = timesteps.to(latents.device)
+    gs = guidance_scale if guidance_scale > 1.0 else 0.0                             # :973-990
+    do_cfg, do_stg, do_resc = gs > 1.0, stg_scale > 0.0, rescaling_scale != 1.0
+    num_conds = 1 + int(do_cfg) + int(do_stg)
+    L = sum(1 for k in sd if k.endswith(".attn1.to_q.weight"))
+    skip_mask = None
+    if do_stg and skip_block_list:
+        skip_mask = torch.ones(L, b * num_conds, dtype=model_dtype, device=latents.device)
+        for bi in skip_block_list:
+            skip_mask[bi, num_conds - 1::num_conds] = 0                               # transformer3d.py:184-185
+    enc_b, mask_b = enc, enc_mask
+    if do_cfg:
+        enc_b = torch.cat([neg_enc, enc]); mask_b = torch.cat([neg_mask, enc_mask])
+    if do_stg:
+        enc_b = torch.cat([enc_b, enc]); mask_b = torch.cat([mask_b, enc_mask])
+    coords = latent_to_pixel_coords(latent_coords(num_frames_lat, lat_h, lat_w, b, latents.device))
+    frac = coords.to(torch.float32)
+    frac[:, 0] = frac[:, 0] * (1.0 / frame_rate)                                     # :1086-1087
+    cos_sin = precompute_freqs_cis(frac, D, cfg["rope_theta"], cfg["rope_max_pos"], model_dtype)
+    cmask = None if conditioning_mask is None else torch.cat([conditioning_mask] * num_conds)
+    for i, t in enumerate(timesteps):
+        x_in = torch.cat([latents] * num_conds) if num_conds > 1 else latents
+        cur_t = t[None].expand(x_in.shape[0]).unsqueeze(-1)                          # [B,1]
+        if cmask is not None:
+            cur_t = torch.min(cur_t, 1.0 - cmask)                                    # :1145-1150 -> [B,N]
+        noise_pred = transformer_forward(sd, cfg, x_in.to(model_dtype), cos_sin, enc_b.to(model_dtype),
+                                         cur_t, mask_b, skip_mask, strategy,
+                                         latent_shape=(num_frames_lat, lat_h, lat_w))
+        noise_pred = guidance_combine(noise_pred, num_conds, do_cfg, do_stg, gs, stg_scale,
+                                      rescaling_scale, do_resc)
+        cur_t = cur_t[:1]
+        denoised = rf_step(noise_pred, cur_t, latents, timesteps)                    # :1233, per-token branch
+        if conditioning_mask is not None:
+            keep = (t - 1e-6 < (1.0 - conditioning_mask)).unsqueeze(-1)              # :1341-1342
+            denoised = torch.where(keep, denoised, latents)
+        latents = denoised
+        if per_step is not None:
+            per_step.append(latents.clone())
+    return latents
+
+
+# --------------------------------------------------------------------------------------
+# CausalVideoAutoencoder decode (vae_encode.py:94-165,239-247; causal_video_autoencoder.py)
+# --------------------------------------------------------------------------------------
+def causal_conv3d(sd, name, x: Tensor, causal: bool) -> Tensor:
+    """CausalConv3d.forward (causal_conv3d.py:44-59): replicate-pad time, zero-pad space."""
+    if causal:
+        x = torch.cat([x[:, :, :1].repeat(1, 1, 2, 1, 1), x], dim=2)
+    else:
+        x = torch.cat([x[:, :, :1], x, x[:, :, -1:]], dim=2)
+    return F.conv3d(x, sd[name + ".conv.weight"], sd[name + ".conv.bias"], padding=(0, 1, 1))
+
+
+def pixel_norm(x: Tensor, eps: float = 1e-8) -> Tensor:
+    """pixel_norm.py:12"""
+    return x / torch.sqrt(torch.mean(x ** 2, dim=1, keepdim=True) + eps)
+
+
+def _resnet(sd, p, x, cin, cout, causal):
+    """ResnetBlock3D.forward (causal_video_autoencoder.py:1197-1258), pixel_norm, no noise/timestep."""
+    h = causal_conv3d(sd, p + "conv1", F.silu(pixel_norm(x)), causal)
+    h = causal_conv3d(sd, p + "conv2", F.silu(pixel_norm(h)), causal)
+    if cin != cout:
+        xs = x.permute(0, 2, 3, 4, 1)
+        xs = F.layer_norm(xs, (cin,), sd[p + "norm3.norm.weight"], sd[p + "norm3.norm.bias"], eps=1e-6)
+        x = F.conv3d(xs.permute(0, 4, 1, 2, 3), sd[p + "conv_shortcut.weight"], sd[p + "conv_shortcut.bias"])
+    return x + h
+
+
+def depth_to_space(x: Tensor) -> Tensor:
+    """'b (c p1 p2 p3) d h w -> b c (d p1) (h p2) (w p3)', p=2 (pixel_shuffle.py:12-20)"""
+    b, c8, d, h, w = x.shape
+    c = c8 // 8
+    x = x.reshape(b, c, 2, 2, 2, d, h, w).permute(0, 1, 5, 2, 6, 3, 7, 4)
+    return x.reshape(b, c, d * 2, h * 2, w * 2)
+
+
+def vae_unpatchify(x: Tensor, p: int) -> Tensor:
+    """'b (c p r q) f h w -> b c (f p) (h q) (w r)', p_t=1 (causal_video_autoencoder.py:1282-1299).
+    NOTE channel order is (c, r, q): r indexes width, q indexes height."""
+    b, cc, f, h, w = x.shape
+    c = cc // (p * p)
+    x = x.reshape(b, c, p, p, f, h, w)            # c, r, q
+    x = x.permute(0, 1, 4, 5, 3, 6, 2)            # b c f h q w r
+    return x.reshape(b, c, f, h * p, w * p)
+
+
+def vae_decode(sd: Dict[str, Tensor], latents: Tensor, cfg: dict = LTX_VAE,
+               per_channel_normalize: bool = True, collect: Optional[list] = None) -> Tensor:
+    """vae_decode -> un_normalize_latents -> Decoder.forward.  latents [B,128,F,H,W] ->
+    [B,3,8(F-1)+1,32H,32W]."""
+    causal = cfg["causal_decoder"]
+    dt = latents.dtype
+    if per_channel_normalize:
+        z = latents * sd["std_of_means"].to(dt).view(1, -1, 1, 1, 1) + sd["mean_of_means"].to(dt).view(1, -1, 1, 1, 1)
+    else:
+        z = latents
+    x = causal_conv3d(sd, "decoder.conv_in", z, causal)
+    if collect is not None:
+        collect.append(x)
+    for kind, idx, cin, cout, n in vae_decoder_plan(cfg):
+        p = f"decoder.up_blocks.{idx}."
+        if kind == "res_x":
+            for j in range(n):
+                x = _resnet(sd, p + f"res_blocks.{j}.", x, cin, cin, causal)
+        elif kind == "res_x_y":
+            x = _resnet(sd, p, x, cin, cout, causal)
+        else:
+            x = depth_to_space(causal_conv3d(sd, p + "conv", x, causal))[:, :, 1:]   # :1057-1062
+        if collect is not None:
+            collect.append(x)
+    x = F.silu(pixel_norm(x))
+    x = causal_conv3d(sd, "decoder.conv_out", x, causal)
+    return vae_unpatchify(x, cfg["patch_size"])
+
+
+def postprocess(image: Tensor) -> Tensor:
+    """VaeImageProcessor.postprocess for tensors: x/2+0.5 clamped to [0,1]."""
+    return (image / 2 + 0.5).clamp(0, 1)
+
+
+def rel_l2(a: Tensor, b: Tensor) -> float:
+    a = a.double(); b = b.double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def psnr(a: Tensor, b: Tensor, peak: float = 1.0) -> float:
+    mse = float(((a.double() - b.double()) ** 2).mean())
+    return float("inf") if mse == 0 else 10.0 * math.log10(peak * peak / mse)
