@@ -1,0 +1,121 @@
+/* ltx_b200.h — C ABI of libltx_b200.so: hand-written sm_100a kernels for the LTX-Video / Wan2.1
+ * denoising hot path.  This is the drop-in boundary: plain pointers and sizes, no torch types.
+ *
+ * Conventions (SURVEY.md §8b "What a C-ABI replacement must export"):
+ *   - every pointer is a DEVICE pointer unless named host_*; bf16 tensors are `const void*`
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream)
+ *   - functions never allocate, never synchronise, and are thread-safe on distinct streams
+ *   - return 0 on success, a negative LTXB200_ERR_* code otherwise (never throw)
+ *   - leading dimensions / strides are in ELEMENTS
+ *
+ * The reference has no FFI: every entry below replaces a PyTorch call site, cited as file:line of
+ * /root/reference (soasme/LTX-Video-GPUPoor).
+ */
+#ifndef LTX_B200_H_
+#define LTX_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LTXB200_OK 0
+#define LTXB200_ERR_BAD_SHAPE (-1)
+#define LTXB200_ERR_BAD_ALIGN (-2)
+#define LTXB200_ERR_CUDA (-3)
+#define LTXB200_ERR_TENSORMAP (-4)
+#define LTXB200_ERR_UNSUPPORTED (-5)
+
+#define LTXB200_ACT_NONE 0
+#define LTXB200_ACT_GELU_TANH 1
+#define LTXB200_ACT_SILU 2
+
+#define LTXB200_CONV_STORE_NDHWC 0   /* out[b,t,h,w,co] bf16 */
+#define LTXB200_CONV_STORE_D2S 1     /* depth-to-space 2x2x2, first frame dropped; co order (p1,p2,p3,c) */
+#define LTXB200_CONV_STORE_UNPATCH 2 /* unpatchify 4x4 to [b,c,t,4h,4w]; co order (c,q,r) */
+
+int ltxb200_abi_version(void);
+const char* ltxb200_error_string(int code);
+/* number of kernels launched through this library since load (per process); for bench.py's gpu_launches */
+long long ltxb200_launch_count(void);
+
+/* out[M,N] = epilogue(A[M,K] @ W[N,K]^T): tcgen05/TMEM GEMM, TMA-fed, fp32 accumulate.
+ * epilogue: v = acc + bias[n]; v = act(v); v = v * gate[m / rows_per_gate, n]; v = v + residual[m, n].
+ * Replaces every nn.Linear on the path: ltx_video/models/transformers/attention.py:543-558,1040-1059,
+ * 1147,339-340 (FFN), transformer3d.py:418,448,503; wan/modules/model.py:168-171,390-391; fused gate /
+ * residual replace attention.py:282-288,345-351.  out may alias residual.  K % 8 == 0, N % 8 == 0. */
+int ltxb200_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K,
+                      void* out, int64_t ldc, int out_f32, const void* bias, int act,
+                      const void* residual, int64_t ldr, const void* gate, int64_t gate_ld,
+                      int rows_per_gate, void* stream);
+
+/* 3x3x3 convolution as TMA-tiled implicit GEMM on tensor cores; x is NDHWC bf16 [B,T,H,W,Cin],
+ * w is [Cout, 27*Cin] bf16 with k = ((kt*3+kh)*3+kw)*Cin + ci.  Spatial zero padding, temporal replicate
+ * padding (causal: 2 leading frames; non-causal: 1 each side).  Replaces CausalConv3d.forward
+ * (ltx_video/models/autoencoders/causal_conv3d.py:44-59), DepthToSpaceUpsample.forward pixel-shuffle
+ * + frame drop (causal_video_autoencoder.py:1051-1065), the residual add (:1256) and the final
+ * unpatchify (:1282-1299) via store_mode.  Cin % 64 == 0, Cout % 8 == 0. */
+int ltxb200_conv3d_bf16(const void* x, const void* w, const void* bias, void* out, int B, int T, int H, int W,
+                        int Cin, int Cout, int causal, int store_mode, int out_f32, const void* residual,
+                        void* stream);
+
+/* Non-causal softmax attention, layout [B, L, H, d] (d = 64 or 128), fp32 softmax, bf16 in/out.
+ * q/k/v may be strided views (token stride ld*, batch stride bs*, head stride = d).
+ * key_bias: optional fp32 [B, Lk] additive mask bias (e.g. 0 / -10000).  scale <= 0 means d^-0.5.
+ * Replaces pay_attention / sdpa_wrapper (utils/attention.py:99-116,161-398). */
+int ltxb200_attention_bf16(const void* q, int64_t ldq, int64_t bsq, const void* k, int64_t ldk, int64_t bsk,
+                           const void* v, int64_t ldv, int64_t bsv, void* out, int64_t ldo, int64_t bso,
+                           int B, int H, int Lq, int Lk, int d, float scale, const float* key_bias,
+                           void* stream);
+
+/* y = norm(x) [* weight + bias] ; then y = y*(1+scale[g]) + shift[g], g = row / rows_per_group.
+ * layer_norm = 0: RMSNorm (attention.py:233-251,314-320); 1: LayerNorm (transformer3d.py:494-502,
+ * wan/modules/model.py:437-441,461,467-472).  D % 256 == 0, D <= 8192.  scale/shift/weight/bias may be NULL. */
+int ltxb200_norm_mod_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, int M, int D, const void* scale,
+                          const void* shift, int64_t mod_ld, int rows_per_group, const void* weight,
+                          const void* bias, float eps, int layer_norm, void* stream);
+
+/* In-place q/k RMSNorm (affine, over the whole inner dim) + LTX interleaved RoPE with [tokens, D] bf16
+ * cos/sin tables (attention.py:1040-1055, 960-975).  k or cos/sin may be NULL. */
+int ltxb200_qk_norm_rope_bf16(void* q, int64_t ldq, int Mq, void* k, int64_t ldk, int Mk, int D,
+                              const void* wq, const void* wk, const void* cos_table, const void* sin_table,
+                              int tokens_per_batch, float eps, void* stream);
+
+/* ada[l,g,j,:] = table[l,j,:] + temb[g, j*D:(j+1)*D]  (attention.py:239-241), JD = 6*D. */
+int ltxb200_ada_add_bf16(const void* table, const void* temb, void* out, int L, int G, int JD, void* stream);
+
+/* y = act(x) elementwise, n % 8 == 0.  mode: LTXB200_ACT_* */
+int ltxb200_act_bf16(const void* x, void* y, int64_t n, int mode, void* stream);
+
+/* STG AttentionValues blend: a[b] = a[b]*mask[b] + v[b]*(1-mask[b]) (attention.py:1134-1139). */
+int ltxb200_stg_blend_bf16(void* a, const void* v, int64_t ldv, const float* mask, int B, int64_t rows, int D,
+                           void* stream);
+
+/* diffusers Timesteps(256, flip_sin_to_cos=True, downscale_freq_shift=0): out[n, dim] bf16 from t[n] fp32 */
+int ltxb200_timestep_embed(const float* t, void* out, int n, int dim, void* stream);
+
+int ltxb200_cast_f32_to_bf16(const float* x, void* y, int64_t n, void* stream);
+
+/* Guidance combine (cfg-star CFG, STG, std-rescale) + RectifiedFlow Euler step with per-token dt and
+ * conditioning mask; latents fp32 updated in place (pipeline_ltx_video.py:1183-1222,1309-1342,
+ * ltx_video/schedulers/rf.py:350-375).  pred: cond c at pred + c*cond_stride, n = tokens*channels.
+ * scratch: >= 8*148 floats.  latents_bf16 (optional) receives the bf16 copy for the next forward. */
+int ltxb200_guidance_step(const void* pred, int64_t cond_stride, int64_t n, int channels, int has_cfg,
+                          int has_stg, int do_rescale, float guidance_scale, float stg_scale, float rescale,
+                          float* latents, void* latents_bf16, const float* timesteps, int num_steps, float t,
+                          const float* cond_mask, float* scratch, void* stream);
+
+/* PixelNorm over channels (+ optional SiLU) on NDHWC bf16 (pixel_norm.py:12; causal_video_autoencoder.py:1212,1240).
+ * C in {64,128,256,512,1024}. */
+int ltxb200_pixelnorm_silu_bf16(const void* x, void* y, int64_t voxels, int C, float eps, int apply_silu,
+                                void* stream);
+
+/* latents NCDHW (fp32 if is_f32 else bf16) -> x*std[c]+mean[c] -> NDHWC bf16 (vae_encode.py:239-247). */
+int ltxb200_latent_to_ndhwc(const void* z, int is_f32, void* out, int B, int C, int64_t FHW, const float* stdv,
+                            const float* meanv, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LTX_B200_H_ */

@@ -1,0 +1,441 @@
+// Memory-bound kernels of the denoising path: 16-byte vectorised, one warp per row (row reductions by
+// shuffles, values kept in registers so every row is read exactly once), bf16 rounding points mirrored
+// from the reference where it is free to do so.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+DEVI float bf16r(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+DEVI void load8(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 q = *reinterpret_cast<const uint4*>(p);
+  float2 a = unpack_bf16(q.x), b = unpack_bf16(q.y), c = unpack_bf16(q.z), d = unpack_bf16(q.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+DEVI void store8(__nv_bfloat16* p, const float (&f)[8]) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+}
+
+// ------------------------------------------------------------------------------------------
+// norm + AdaLN modulate:  y = norm(x) * (1 + scale[g]) + shift[g]          (g = row / rows_per_group)
+//   kLayerNorm = false: RMSNorm without affine (attention.py:233-251, 314-320; diffusers RMSNorm)
+//   kLayerNorm = true : LayerNorm without affine (transformer3d.py:490-502 ; Wan norm1/norm2)
+//   optional affine weight/bias (Wan norm3, VAE res_x_y norm3) applied before the modulation.
+// x, y: [M, D] bf16 (in-place allowed), scale/shift: row g at (ptr + g*mod_ld), null => no modulation.
+// One warp per row, NV uint4 per lane (D = 256*NV).
+// ------------------------------------------------------------------------------------------
+template <int NV, bool kLayerNorm>
+__global__ void __launch_bounds__(128)
+norm_mod_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int M, long long ldx, long long ldy,
+                const __nv_bfloat16* __restrict__ scale, const __nv_bfloat16* __restrict__ shift, long long mod_ld,
+                int rows_per_group, const __nv_bfloat16* __restrict__ weight, const __nv_bfloat16* __restrict__ bias,
+                float eps) {
+  constexpr int D = NV * 256;
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const __nv_bfloat16* xr = x + row * ldx;
+  float v[NV][8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) load8(xr + (i * 32 + lane) * 8, v[i]);
+  float sum = 0.f, sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sum += v[i][j]; sq += v[i][j] * v[i][j]; }
+  float mean = 0.f, rs;
+  if (kLayerNorm) {
+    mean = warp_sum(sum) * (1.0f / D);
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; var += d * d; }
+    rs = rsqrtf(warp_sum(var) * (1.0f / D) + eps);
+  } else {
+    rs = rsqrtf(warp_sum(sq) * (1.0f / D) + eps);
+  }
+  const long long g = row / rows_per_group;
+  const __nv_bfloat16* sc = scale ? scale + g * mod_ld : nullptr;
+  const __nv_bfloat16* sh = shift ? shift + g * mod_ld : nullptr;
+  __nv_bfloat16* yr = y + row * ldy;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 8;
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rs;
+    if (weight) {
+      float w[8];
+      load8(weight + c, w);
+      if (bias) {
+        float bb[8];
+        load8(bias + c, bb);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = o[j] * w[j] + bb[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = bf16r(o[j]) * w[j];
+      }
+    }
+    if (sc) {
+      float s[8], t[8];
+      load8(sc + c, s);
+      load8(sh + c, t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = bf16r(bf16r(bf16r(o[j]) * bf16r(1.0f + s[j])) + t[j]);
+    }
+    store8(yr + c, o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// LTX q/k RMSNorm (over the full inner dim, affine, eps 1e-5) + interleaved-pair RoPE, in place on
+// the q and k column slices of a fused QKV buffer (attention.py:1040-1055, 960-975, 477-479).
+//   y = bf16(x * rsqrt(mean(x^2)+eps)) * w ;  out = y*cos + rot(y)*sin,  rot: (2i,2i+1) -> (-y[2i+1], y[2i])
+// cos/sin: [tokens_per_batch, D] bf16 (row = token index within the batch), null => no RoPE.
+// grid.y selects the tensor: 0 = q, 1 = k.
+// ------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(128)
+qk_norm_rope_kernel(__nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict__ k, int Mq, int Mk, long long ldq, long long ldk,
+                    const __nv_bfloat16* __restrict__ wq, const __nv_bfloat16* __restrict__ wk,
+                    const __nv_bfloat16* __restrict__ cosT, const __nv_bfloat16* __restrict__ sinT,
+                    int tokens_per_batch, float eps) {
+  constexpr int D = NV * 256;
+  const bool is_k = blockIdx.y == 1;
+  __nv_bfloat16* base = is_k ? k : q;
+  if (base == nullptr) return;
+  const int M = is_k ? Mk : Mq;
+  const long long ld = is_k ? ldk : ldq;
+  const __nv_bfloat16* w = is_k ? wk : wq;
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  __nv_bfloat16* xr = base + row * ld;
+  float v[NV][8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) load8(xr + (i * 32 + lane) * 8, v[i]);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sq += v[i][j] * v[i][j];
+  const float rs = rsqrtf(warp_sum(sq) * (1.0f / D) + eps);
+  const long long trow = cosT ? static_cast<long long>(row % tokens_per_batch) * D : 0;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 8;
+    float ww[8], o[8];
+    load8(w + c, ww);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = bf16r(bf16r(v[i][j] * rs) * ww[j]);
+    if (cosT) {
+      float cs[8], sn[8], r[8];
+      load8(cosT + trow + c, cs);
+      load8(sinT + trow + c, sn);
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        r[j] = bf16r(bf16r(o[j] * cs[j]) + bf16r(-o[j + 1] * sn[j]));
+        r[j + 1] = bf16r(bf16r(o[j + 1] * cs[j + 1]) + bf16r(o[j] * sn[j + 1]));
+      }
+      store8(xr + c, r);
+    } else {
+      store8(xr + c, o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// ada[l, g, j, :] = table[l, j, :] + temb[g, j*D:(j+1)*D]   (bf16 add; attention.py:239-241)
+// ------------------------------------------------------------------------------------------
+__global__ void ada_add_kernel(const __nv_bfloat16* __restrict__ table, const __nv_bfloat16* __restrict__ temb,
+                               __nv_bfloat16* __restrict__ out, int L, int G, int JD /* = 6*D */) {
+  const long long n8 = static_cast<long long>(L) * G * JD / 8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long e = i * 8;
+    const int c = static_cast<int>(e % JD);
+    const int g = static_cast<int>((e / JD) % G);
+    const int l = static_cast<int>(e / JD / G);
+    float a[8], b[8];
+    load8(table + static_cast<long long>(l) * JD + c, a);
+    load8(temb + static_cast<long long>(g) * JD + c, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] += b[j];
+    store8(out + e, a);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// elementwise activation / blend helpers
+// ------------------------------------------------------------------------------------------
+// mode 0: copy, 1: silu, 2: gelu-tanh
+__global__ void act_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n, int mode) {
+  for (long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 8; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x * 8) {
+    float v[8];
+    load8(x + i, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      v[j] = mode == 1 ? __fdividef(v[j], 1.0f + __expf(-v[j])) : (mode == 2 ? gelu_tanh(v[j]) : v[j]);
+    store8(y + i, v);
+  }
+}
+
+// STG "AttentionValues" blend (attention.py:1134-1139): a[b] = a[b]*m[b] + v[b]*(1-m[b]),
+// a: [B, rows, D] contiguous, v: column slice with row stride ldv.
+__global__ void stg_blend_kernel(__nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ v, long long ldv,
+                                 const float* __restrict__ mask, int B, long long rows, int D) {
+  const long long per_b = rows * D / 8;
+  const long long n8 = per_b * B;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(i / per_b);
+    const float m = mask[b];
+    if (m == 1.0f) continue;
+    const long long e = i * 8;
+    const long long r = e / D;
+    const int c = static_cast<int>(e - r * D);
+    float x[8], y[8];
+    load8(a + e, x);
+    load8(v + r * ldv + c, y);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = bf16r(bf16r(x[j] * m) + bf16r(y[j] * (1.0f - m)));
+    store8(a + e, x);
+  }
+}
+
+// sinusoidal timestep embedding (diffusers get_timestep_embedding, flip_sin_to_cos=True, shift 0):
+// out[i, 0:half] = cos(t_i * f_k), out[i, half:] = sin(t_i * f_k), f_k = exp(-ln(10000) k / half)
+__global__ void timestep_embed_kernel(const float* __restrict__ t, __nv_bfloat16* __restrict__ out, int n, int dim,
+                                      int cos_first) {
+  const int half = dim / 2;
+  const int i = blockIdx.x;
+  if (i >= n) return;
+  for (int k = threadIdx.x; k < half; k += blockDim.x) {
+    const float f = expf(-9.210340371976184f * static_cast<float>(k) / static_cast<float>(half));
+    const float a = t[i] * f;
+    const float c = cosf(a), s = sinf(a);
+    out[static_cast<long long>(i) * dim + k] = __float2bfloat16_rn(cos_first ? c : s);
+    out[static_cast<long long>(i) * dim + half + k] = __float2bfloat16_rn(cos_first ? s : c);
+  }
+}
+
+// fp32 <-> bf16 casts (vectorised)
+__global__ void cast_f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+  for (long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 8; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x * 8) {
+    const float4 a = *reinterpret_cast<const float4*>(x + i), b = *reinterpret_cast<const float4*>(x + i + 4);
+    *reinterpret_cast<uint4*>(y + i) = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Guidance (CFG with cfg-star projection, STG, std-rescale) + rectified-flow Euler step
+// (pipeline_ltx_video.py:1183-1222,1309-1342 ; rf.py:350-375).  Three launches:
+//   1) guidance_reduce_kernel<0>: per-block partials of  sum(text*uncond), sum(uncond^2)
+//   2) guidance_reduce_kernel<1>: partials of sum/sumsq of text and of the combined prediction
+//   3) guidance_step_kernel: combine, rescale, x <- x - dt*v (per-token dt, conditioning mask)
+// noise_pred: [conds, n] bf16 with conds ordered (uncond?, text, perturbed?).  Partials are reduced in
+// a fixed order (deterministic).
+// ------------------------------------------------------------------------------------------
+struct GuidanceParams {
+  const __nv_bfloat16* pred;   // cond c at pred + c*cond_stride
+  long long cond_stride;
+  long long n;                 // elements per cond (tokens * channels)
+  int channels;
+  int has_cfg, has_stg, do_rescale;
+  float guidance_scale, stg_scale, rescale;
+  float* partials;             // [2 phases][4][kGuidanceBlocks]
+  // step
+  float* latents;              // [n] fp32, updated in place
+  const float* timesteps;      // [num_steps] descending
+  int num_steps;
+  float t;                     // current global timestep
+  const float* cond_mask;      // [tokens] or null
+  __nv_bfloat16* latents_bf16; // optional bf16 copy of the updated latents (next model input)
+};
+constexpr int kGuidanceBlocks = 148;
+
+DEVI float block_sum_256(float v, float* sm) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = 0.f;
+  if (threadIdx.x < 8) r = sm[threadIdx.x];
+  if (threadIdx.x < 32) {
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+  }
+  __syncthreads();
+  return r;   // valid in thread 0
+}
+
+DEVI float sum_partials(const float* p) {
+  float s = 0.f;
+  for (int i = 0; i < kGuidanceBlocks; ++i) s += p[i];
+  return s;
+}
+
+DEVI float cfg_alpha(const GuidanceParams& g) {
+  const float dot = bf16r(sum_partials(g.partials + 0 * kGuidanceBlocks));
+  const float nrm = bf16r(bf16r(sum_partials(g.partials + 1 * kGuidanceBlocks)) + 1e-8f);
+  return bf16r(dot / nrm);
+}
+
+// combined prediction for element i (before std-rescale)
+DEVI float guidance_combine(const GuidanceParams& g, long long i, float alpha, float* text_out) {
+  const int conds = 1 + g.has_cfg + g.has_stg;
+  float out, text;
+  if (g.has_cfg) {
+    float un = __bfloat162float(g.pred[i]);
+    text = __bfloat162float(g.pred[g.cond_stride + i]);
+    if (g.guidance_scale != 0.f && g.guidance_scale != 1.f) {
+      un = bf16r(alpha * un);
+      out = bf16r(un + bf16r(g.guidance_scale * bf16r(text - un)));
+    } else {
+      out = text;
+    }
+  } else {
+    text = __bfloat162float(g.pred[i]);
+    out = text;
+  }
+  if (g.has_stg) {
+    const float pert = __bfloat162float(g.pred[static_cast<long long>(conds - 1) * g.cond_stride + i]);
+    out = bf16r(out + bf16r(g.stg_scale * bf16r(text - pert)));
+  }
+  *text_out = text;
+  return out;
+}
+
+template <int kPhase>
+__global__ void __launch_bounds__(256) guidance_reduce_kernel(const GuidanceParams g) {
+  __shared__ float sm[8];
+  float a = 0.f, b = 0.f, c = 0.f, d = 0.f;
+  float alpha = 0.f;
+  if (kPhase == 1 && g.has_cfg) alpha = cfg_alpha(g);
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < g.n; i += static_cast<long long>(gridDim.x) * 256) {
+    if (kPhase == 0) {
+      const float un = __bfloat162float(g.pred[i]), tx = __bfloat162float(g.pred[g.cond_stride + i]);
+      a += bf16r(tx * un);
+      b += bf16r(un * un);
+    } else {
+      float tx;
+      const float o = guidance_combine(g, i, alpha, &tx);
+      a += tx; b += tx * tx; c += o; d += o * o;
+    }
+  }
+  float* P = g.partials + kPhase * 4 * kGuidanceBlocks;
+  float r;
+  r = block_sum_256(a, sm); if (threadIdx.x == 0) P[0 * kGuidanceBlocks + blockIdx.x] = r;
+  r = block_sum_256(b, sm); if (threadIdx.x == 0) P[1 * kGuidanceBlocks + blockIdx.x] = r;
+  if (kPhase == 1) {
+    r = block_sum_256(c, sm); if (threadIdx.x == 0) P[2 * kGuidanceBlocks + blockIdx.x] = r;
+    r = block_sum_256(d, sm); if (threadIdx.x == 0) P[3 * kGuidanceBlocks + blockIdx.x] = r;
+  }
+}
+
+__global__ void __launch_bounds__(256) guidance_step_kernel(const GuidanceParams g) {
+  float alpha = 0.f, factor = 1.f;
+  if (g.has_cfg) alpha = cfg_alpha(g);
+  if (g.has_stg && g.do_rescale && g.stg_scale > 0.f) {
+    const float* P = g.partials + 4 * kGuidanceBlocks;
+    const double n = static_cast<double>(g.n);
+    const double st = sum_partials(P), st2 = sum_partials(P + kGuidanceBlocks);
+    const double so = sum_partials(P + 2 * kGuidanceBlocks), so2 = sum_partials(P + 3 * kGuidanceBlocks);
+    // unbiased std, as torch.std
+    const float std_t = bf16r(static_cast<float>(sqrt(fmax((st2 - st * st / n) / (n - 1.0), 0.0))));
+    const float std_o = bf16r(static_cast<float>(sqrt(fmax((so2 - so * so / n) / (n - 1.0), 0.0))));
+    factor = bf16r(std_t / std_o);
+    factor = bf16r(bf16r(g.rescale * factor) + (1.0f - g.rescale));
+  }
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < g.n; i += static_cast<long long>(gridDim.x) * 256) {
+    float tx;
+    float v = guidance_combine(g, i, alpha, &tx);
+    if (factor != 1.f) v = bf16r(v * factor);
+    // per-token dt (rf.py:350-367): next lower timestep strictly below t_tok - 1e-6 (0 if none)
+    float t_tok = g.t;
+    bool update = true;
+    if (g.cond_mask) {
+      const float cm = g.cond_mask[i / g.channels];
+      t_tok = fminf(g.t, 1.0f - cm);
+      update = (g.t - 1e-6f) < (1.0f - cm);
+    }
+    float lower = 0.f;
+    for (int s = 0; s < g.num_steps; ++s) {
+      const float ts = g.timesteps[s];
+      if (ts < t_tok - 1e-6f) { lower = ts; break; }     // timesteps descend: first hit is the max
+    }
+    const float dt = t_tok - lower;
+    float x = g.latents[i];
+    if (update) x = x - dt * v;
+    g.latents[i] = x;
+    if (g.latents_bf16) g.latents_bf16[i] = __float2bfloat16_rn(x);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// VAE helpers (NDHWC bf16 activations)
+// ------------------------------------------------------------------------------------------
+// PixelNorm over channels (eps 1e-8) followed by SiLU (pixel_norm.py:12, causal_video_autoencoder.py:1212-1240).
+// A group of G = min(32, C/8) lanes owns one voxel; NV = C / (8*G) uint4 per lane.
+template <int C>
+__global__ void __launch_bounds__(256)
+pixelnorm_silu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long voxels, float eps,
+                      int apply_silu) {
+  constexpr int G = (C / 8 < 32) ? C / 8 : 32;
+  constexpr int NV = C / (8 * G);
+  constexpr int VPW = 32 / G;                                   // voxels per warp
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long vox = warp_global * VPW + lane / G;
+  const int gl = lane % G;
+  const bool ok = vox < voxels;
+  float v[NV][8];
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    if (ok) load8(x + vox * C + (i * G + gl) * 8, v[i]);
+    else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sq += v[i][j] * v[i][j];
+  }
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float inv = 1.0f / sqrtf(sq * (1.0f / C) + eps);
+  if (!ok) return;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float t = bf16r(v[i][j] * inv);
+      o[j] = apply_silu ? __fdividef(t, 1.0f + __expf(-t)) : t;
+    }
+    store8(y + vox * C + (i * G + gl) * 8, o);
+  }
+}
+
+// latents [B, C, F, H, W] fp32/bf16 (NCDHW) -> per-channel de-normalise (x*std+mean) -> NDHWC bf16
+// (vae_encode.py:239-247).  Small tensor: one thread per output element.
+template <typename T>
+__global__ void latent_to_ndhwc_kernel(const T* __restrict__ z, __nv_bfloat16* __restrict__ out, int B, int C,
+                                       long long FHW, const float* __restrict__ stdv, const float* __restrict__ meanv) {
+  const long long n = static_cast<long long>(B) * C * FHW;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const long long s = (i / C) % FHW;
+    const long long b = i / C / FHW;
+    float v = static_cast<float>(z[(b * C + c) * FHW + s]);
+    if (stdv) v = bf16r(bf16r(bf16r(v) * bf16r(stdv[c])) + bf16r(meanv[c]));
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+}  // namespace b200

@@ -1,0 +1,326 @@
+// Persistent warp-specialised bf16 GEMM / implicit-GEMM conv3d for sm_100a.
+//
+//   D[M,N] = A[M,K] * W[N,K]^T  (+ fused epilogue),  fp32 accumulation in TMEM.
+//
+// One CTA per SM, 192 threads: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (+ TMEM owner),
+// warps 2..5 = epilogue (TMEM -> registers -> global).  Operands are staged by TMA into 128B-swizzled
+// shared memory (K-major for both), kStages-deep mbarrier ring; the accumulator is double-buffered in
+// TMEM (2 x BN columns) so tile i's epilogue overlaps tile i+1's main loop.
+//
+// kConv = true turns the A producer into an implicit-GEMM gather for a 3x3x3 convolution over an
+// NDHWC activation: the M tile is a BH x BW spatial patch of one frame, each k-block is one
+// (tap, 64-channel slice); spatial zero padding comes from TMA out-of-bounds fill, temporal
+// replicate padding from clamping the frame coordinate (causal_conv3d.py:44-59).
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int kGemmBM = 128;
+constexpr int kGemmBK = 64;
+constexpr int kGemmThreads = 192;
+
+enum GemmAct : int { kActNone = 0, kActGeluTanh = 1, kActSilu = 2 };
+enum GemmStore : int {
+  kStoreRowMajor = 0,   // out[m*ldc + n]
+  kStoreConvD2S = 1,    // conv: depth-to-space 2x2x2 (+ drop first frame), channel order (p1,p2,p3,c)
+  kStoreConvUnpatch = 2 // conv: final unpatchify to NCFHW, channel order (c,q,r), patch 4x4
+};
+
+struct GemmParams {
+  int M, N, K;
+  // epilogue
+  void* out;
+  long long ldc;
+  const __nv_bfloat16* bias;       // [N] or null
+  int act;
+  const __nv_bfloat16* residual;   // [M, ldr] or null:   out = residual + gate * val
+  long long ldr;
+  const __nv_bfloat16* gate;       // [ceil(M/rows_per_gate), gate_ld] or null
+  int rows_per_gate;
+  long long gate_ld;
+  int out_f32;
+  int store_mode;
+  // conv geometry (kConv only): activation [B, T, H, W, Cin], tile = BH x BW patch
+  int cB, cT, cH, cW, cCin;
+  int cBH, cBW;
+  int c_tiles_h, c_tiles_w;
+  int c_causal;                    // 1: taps (t-2,t-1,t) ; 0: (t-1,t,t+1), both clamped (replicate)
+  int c_taps_t;                    // 3 for 3x3x3, 1 for 1x1x1 (then also 1x1 spatial)
+};
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int kStageBytesA = kGemmBM * kGemmBK * 2;          // 16 KB
+  static constexpr int kStageBytesB = BN * kGemmBK * 2;
+  static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kBarBytes = 256;
+  static constexpr int kTotal = kStages * kStageBytes + kBarBytes + 1024;  // +1024 alignment slack
+};
+
+template <int BN, bool kConv>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const GemmParams p) {
+  using S = GemmSmem<BN>;
+  constexpr int kStages = S::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * S::kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tfull_bar = empty_bar + kStages;     // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int tiles_m = kConv ? p.cB * p.cT * p.c_tiles_h * p.c_tiles_w : (p.M + kGemmBM - 1) / kGemmBM;
+  const int tiles_n = (p.N + BN - 1) / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int kb_per_tap = kConv ? (p.cCin + kGemmBK - 1) / kGemmBK : 1;
+  const int taps = kConv ? p.c_taps_t * p.c_taps_t * p.c_taps_t : 1;
+  const int num_kb = kConv ? taps * kb_per_tap : (p.K + kGemmBK - 1) / kGemmBK;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int tm = tile % tiles_m, tn = tile / tiles_m;
+        int cb = 0, ct = 0, ch0 = 0, cw0 = 0;
+        if (kConv) {
+          int r = tm;
+          cw0 = (r % p.c_tiles_w) * p.cBW; r /= p.c_tiles_w;
+          ch0 = (r % p.c_tiles_h) * p.cBH; r /= p.c_tiles_h;
+          ct = r % p.cT; cb = r / p.cT;
+        }
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * S::kStageBytes;
+          uint8_t* sb = sa + S::kStageBytesA;
+          mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
+          if (kConv) {
+            const int tap = kb / kb_per_tap, cblk = kb - tap * kb_per_tap;
+            int kt = 0, kh = 0, kw = 0;
+            if (p.c_taps_t == 3) { kt = tap / 9; kh = (tap / 3) % 3; kw = tap % 3; }
+            int tt = ct, hh = ch0, ww = cw0;
+            if (p.c_taps_t == 3) {
+              tt = p.c_causal ? ct + kt - 2 : ct + kt - 1;
+              tt = tt < 0 ? 0 : (tt > p.cT - 1 ? p.cT - 1 : tt);
+              hh = ch0 + kh - 1;
+              ww = cw0 + kw - 1;
+            }
+            tma_load_5d(sa, &tmA, &full_bar[stage], cblk * kGemmBK, ww, hh, tt, cb);
+            tma_load_2d(sb, &tmB, &full_bar[stage], tap * p.cCin + cblk * kGemmBK, tn * BN);
+          } else {
+            tma_load_2d(sa, &tmA, &full_bar[stage], kb * kGemmBK, tm * kGemmBM);
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * kGemmBK, tn * BN);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    constexpr uint32_t idesc = umma_idesc_bf16(kGemmBM, BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
+          const uint32_t sb = sa + S::kStageBytesA;
+#pragma unroll
+          for (int k = 0; k < kGemmBK / 16; ++k) {
+            const uint64_t ad = umma_smem_desc_sw128(sa + k * 32, 16, 1024);
+            const uint64_t bd = umma_smem_desc_sw128(sb + k * 32, 16, 1024);
+            umma_ss(d_tmem, ad, bd, idesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);                       // frees the smem slot when MMAs retire
+          if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);   // accumulator ready for the epilogue
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ================= epilogue =================
+    const int sub = warp & 3;                 // TMEM sub-partition this warp may read
+    const int row_in_tile = sub * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int tm = tile % tiles_m, tn = tile / tiles_m;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + acc * BN + (static_cast<uint32_t>(sub * 32) << 16);
+
+      // ---- where does this thread's row go? ----
+      bool row_ok;
+      long long m_lin = 0;                    // linear row index (for bias-free row-major / gate / residual)
+      int ob = 0, ot = 0, oh = 0, ow = 0;
+      if (kConv) {
+        int r = tm;
+        const int w0 = (r % p.c_tiles_w) * p.cBW; r /= p.c_tiles_w;
+        const int h0 = (r % p.c_tiles_h) * p.cBH; r /= p.c_tiles_h;
+        ot = r % p.cT; ob = r / p.cT;
+        oh = h0 + row_in_tile / p.cBW;
+        ow = w0 + row_in_tile % p.cBW;
+        row_ok = (oh < p.cH) && (ow < p.cW);
+        m_lin = ((static_cast<long long>(ob) * p.cT + ot) * p.cH + oh) * p.cW + ow;
+      } else {
+        m_lin = static_cast<long long>(tm) * kGemmBM + row_in_tile;
+        row_ok = m_lin < p.M;
+      }
+      const __nv_bfloat16* gate_row = nullptr;
+      if (p.gate) gate_row = p.gate + (m_lin / p.rows_per_gate) * p.gate_ld;
+      const __nv_bfloat16* res_row = p.residual ? p.residual + m_lin * p.ldr : nullptr;
+
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        const int n0 = tn * BN + c0;
+        if (n0 >= p.N) break;                 // warp-uniform
+        uint32_t v[32];
+        tmem_ld32(t_addr + c0, v);
+        tmem_wait_ld();
+        if (row_ok) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          const bool full = (n0 + 32 <= p.N);
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (full || n0 + j < p.N) {
+                const uint4 bq = *reinterpret_cast<const uint4*>(p.bias + n0 + j);
+                const float2 b0 = unpack_bf16(bq.x), b1 = unpack_bf16(bq.y), b2 = unpack_bf16(bq.z), b3 = unpack_bf16(bq.w);
+                f[j] += b0.x; f[j + 1] += b0.y; f[j + 2] += b1.x; f[j + 3] += b1.y;
+                f[j + 4] += b2.x; f[j + 5] += b2.y; f[j + 6] += b3.x; f[j + 7] += b3.y;
+              }
+            }
+          }
+          if (p.act == kActGeluTanh) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = gelu_tanh(f[j]);
+          } else if (p.act == kActSilu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __fdividef(f[j], 1.0f + __expf(-f[j]));
+          }
+          if (gate_row) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (full || n0 + j < p.N) {
+                const uint4 gq = *reinterpret_cast<const uint4*>(gate_row + n0 + j);
+                const float2 g0 = unpack_bf16(gq.x), g1 = unpack_bf16(gq.y), g2 = unpack_bf16(gq.z), g3 = unpack_bf16(gq.w);
+                f[j] *= g0.x; f[j + 1] *= g0.y; f[j + 2] *= g1.x; f[j + 3] *= g1.y;
+                f[j + 4] *= g2.x; f[j + 5] *= g2.y; f[j + 6] *= g3.x; f[j + 7] *= g3.y;
+              }
+            }
+          }
+          if (res_row) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (full || n0 + j < p.N) {
+                const uint4 rq = *reinterpret_cast<const uint4*>(res_row + n0 + j);
+                const float2 r0 = unpack_bf16(rq.x), r1 = unpack_bf16(rq.y), r2 = unpack_bf16(rq.z), r3 = unpack_bf16(rq.w);
+                f[j] += r0.x; f[j + 1] += r0.y; f[j + 2] += r1.x; f[j + 3] += r1.y;
+                f[j + 4] += r2.x; f[j + 5] += r2.y; f[j + 6] += r3.x; f[j + 7] += r3.y;
+              }
+            }
+          }
+          // ---- store ----
+          if (p.store_mode == kStoreRowMajor) {
+            if (p.out_f32) {
+              float* o = reinterpret_cast<float*>(p.out) + m_lin * p.ldc + n0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                if (full || n0 + j < p.N) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            } else {
+              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + m_lin * p.ldc + n0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8)
+                if (full || n0 + j < p.N)
+                  *reinterpret_cast<uint4*>(o + j) = make_uint4(pack_bf16(f[j], f[j + 1]), pack_bf16(f[j + 2], f[j + 3]),
+                                                                pack_bf16(f[j + 4], f[j + 5]), pack_bf16(f[j + 6], f[j + 7]));
+            }
+          } else if (p.store_mode == kStoreConvD2S) {
+            // N = 8*C, channel n = ((p1*2+p2)*2+p3)*C + c  ->  out[b, 2t+p1-1, 2h+p2, 2w+p3, c]  (NDHWC, T' = 2T-1)
+            const int C = p.N >> 3;
+            const int q = n0 / C, c = n0 - q * C;             // 32-col chunk never straddles (C % 32 == 0)
+            const int p1 = q >> 2, p2 = (q >> 1) & 1, p3 = q & 1;
+            const int t2 = 2 * ot + p1 - 1;
+            if (t2 >= 0) {
+              const long long vox = ((static_cast<long long>(ob) * (2 * p.cT - 1) + t2) * (2 * p.cH) + (2 * oh + p2)) * (2 * p.cW) + (2 * ow + p3);
+              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + vox * C + c;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8)
+                *reinterpret_cast<uint4*>(o + j) = make_uint4(pack_bf16(f[j], f[j + 1]), pack_bf16(f[j + 2], f[j + 3]),
+                                                              pack_bf16(f[j + 4], f[j + 5]), pack_bf16(f[j + 6], f[j + 7]));
+            }
+          } else {
+            // kStoreConvUnpatch: N = Cimg*16, n = (c*4+q)*4 + r -> out[b, c, t, 4h+q, 4w+r]  (NCFHW, fp32 or bf16)
+            const long long HW4 = static_cast<long long>(4 * p.cH) * (4 * p.cW);
+            const int Cimg = p.N >> 4;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const int n = n0 + j;
+              if (n < p.N) {
+                const int c = n >> 4, q = (n >> 2) & 3;
+                const long long off = ((static_cast<long long>(ob) * Cimg + c) * p.cT + ot) * HW4 +
+                                      static_cast<long long>(4 * oh + q) * (4 * p.cW) + 4 * ow;
+                if (p.out_f32)
+                  *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                else
+                  *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off) =
+                      make_uint2(pack_bf16(f[j], f[j + 1]), pack_bf16(f[j + 2], f[j + 3]));
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<2 * BN>(tmem_base);
+  }
+}
+
+}  // namespace b200

@@ -1,0 +1,379 @@
+// C-ABI entry points of libltx_b200.so (see include/ltx_b200.h).  Host-side launch logic only.
+#include "../../include/ltx_b200.h"
+
+#include <atomic>
+
+#include "attention.cuh"
+#include "common.cuh"
+#include "elementwise.cuh"
+#include "gemm.cuh"
+#include "tensormap.h"
+
+using namespace b200;
+
+static std::atomic<long long> g_launches{0};
+static int g_num_sms = 0;
+
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static inline int launch_status() {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return cudaPeekAtLastError() == cudaSuccess ? kOk : kErrCuda;
+}
+static inline int ew_blocks(long long work_items, int threads) {
+  long long b = (work_items + threads - 1) / threads;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  return static_cast<int>(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+extern "C" int ltxb200_abi_version(void) { return 1; }
+extern "C" long long ltxb200_launch_count(void) { return g_launches.load(); }
+extern "C" const char* ltxb200_error_string(int code) {
+  switch (code) {
+    case kOk: return "ok";
+    case kErrBadShape: return "bad shape";
+    case kErrBadAlign: return "pointer or stride not 16-byte aligned";
+    case kErrCuda: return "CUDA launch error";
+    case kErrTensorMap: return "cuTensorMapEncodeTiled failed";
+    case kErrUnsupported: return "unsupported configuration";
+    default: return "unknown error";
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// GEMM
+// ------------------------------------------------------------------------------------------
+template <int BN, bool kConv>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_tiles,
+                       cudaStream_t st) {
+  using S = GemmSmem<BN>;
+  static bool configured = false;
+  auto kern = gemm_bf16_kernel<BN, kConv>;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal) != cudaSuccess) return kErrCuda;
+    configured = true;
+  }
+  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  kern<<<grid, kGemmThreads, S::kTotal, st>>>(ta, tb, p);
+  return launch_status();
+}
+
+extern "C" int ltxb200_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K,
+                                 void* out, int64_t ldc, int out_f32, const void* bias, int act,
+                                 const void* residual, int64_t ldr, const void* gate, int64_t gate_ld,
+                                 int rows_per_gate, void* stream) {
+  if (M <= 0 || N <= 0 || K <= 0 || (K & 7) || (N & 7)) return kErrBadShape;
+  if (!aligned16(A) || !aligned16(W) || !aligned16(out) || (lda & 7) || (ldw & 7) || (ldc & (out_f32 ? 3 : 7)))
+    return kErrBadAlign;
+  if ((bias && !aligned16(bias)) || (residual && (!aligned16(residual) || (ldr & 7))) ||
+      (gate && (!aligned16(gate) || (gate_ld & 7) || rows_per_gate <= 0)))
+    return kErrBadAlign;
+  const int BN = (N <= 128) ? 128 : 256;
+  CUtensorMap ta, tb;
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
+    uint64_t str[1] = {static_cast<uint64_t>(lda) * 2};
+    uint32_t box[2] = {kGemmBK, kGemmBM};
+    if (make_tmap_bf16(&ta, A, 2, dims, str, box)) return kErrTensorMap;
+  }
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+    uint64_t str[1] = {static_cast<uint64_t>(ldw) * 2};
+    uint32_t box[2] = {kGemmBK, static_cast<uint32_t>(BN)};
+    if (make_tmap_bf16(&tb, W, 2, dims, str, box)) return kErrTensorMap;
+  }
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.out = out; p.ldc = ldc; p.out_f32 = out_f32;
+  p.bias = static_cast<const __nv_bfloat16*>(bias);
+  p.act = act;
+  p.residual = static_cast<const __nv_bfloat16*>(residual); p.ldr = ldr;
+  p.gate = static_cast<const __nv_bfloat16*>(gate); p.gate_ld = gate_ld; p.rows_per_gate = rows_per_gate > 0 ? rows_per_gate : 1;
+  p.store_mode = kStoreRowMajor;
+  const int tiles = ((M + kGemmBM - 1) / kGemmBM) * ((N + BN - 1) / BN);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return BN == 128 ? launch_gemm<128, false>(ta, tb, p, tiles, st) : launch_gemm<256, false>(ta, tb, p, tiles, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// conv3d (implicit GEMM)
+// ------------------------------------------------------------------------------------------
+extern "C" int ltxb200_conv3d_bf16(const void* x, const void* w, const void* bias, void* out, int B, int T, int H,
+                                   int W, int Cin, int Cout, int causal, int store_mode, int out_f32,
+                                   const void* residual, void* stream) {
+  if (B <= 0 || T <= 0 || H <= 0 || W <= 0 || (Cin % 64) || (Cout & 7)) return kErrBadShape;
+  if (!aligned16(x) || !aligned16(w) || !aligned16(out) || (bias && !aligned16(bias)) || (residual && !aligned16(residual)))
+    return kErrBadAlign;
+  if (store_mode == LTXB200_CONV_STORE_D2S && ((Cout % 8) || ((Cout / 8) % 32))) return kErrBadShape;
+  if (store_mode == LTXB200_CONV_STORE_UNPATCH && (Cout % 16)) return kErrBadShape;
+  if (store_mode != LTXB200_CONV_STORE_NDHWC && residual) return kErrUnsupported;
+  // pick the 128-voxel patch shape with the least padding
+  static const int shapes[8][2] = {{8, 16}, {16, 8}, {4, 32}, {32, 4}, {2, 64}, {64, 2}, {1, 128}, {128, 1}};
+  int best = 0;
+  long long best_area = -1;
+  for (int i = 0; i < 8; ++i) {
+    const long long th = (H + shapes[i][0] - 1) / shapes[i][0], tw = (W + shapes[i][1] - 1) / shapes[i][1];
+    const long long area = th * tw;
+    if (best_area < 0 || area < best_area) { best_area = area; best = i; }
+  }
+  const int BH = shapes[best][0], BW = shapes[best][1];
+  const int BN = (Cout <= 128) ? 128 : 256;
+  CUtensorMap ta, tb;
+  {
+    uint64_t dims[5] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                        static_cast<uint64_t>(T), static_cast<uint64_t>(B)};
+    uint64_t str[4] = {static_cast<uint64_t>(Cin) * 2, static_cast<uint64_t>(W) * Cin * 2,
+                       static_cast<uint64_t>(H) * W * Cin * 2, static_cast<uint64_t>(T) * H * W * Cin * 2};
+    uint32_t box[5] = {kGemmBK, static_cast<uint32_t>(BW), static_cast<uint32_t>(BH), 1, 1};
+    if (make_tmap_bf16(&ta, x, 5, dims, str, box)) return kErrTensorMap;
+  }
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(27) * Cin, static_cast<uint64_t>(Cout)};
+    uint64_t str[1] = {static_cast<uint64_t>(27) * Cin * 2};
+    uint32_t box[2] = {kGemmBK, static_cast<uint32_t>(BN)};
+    if (make_tmap_bf16(&tb, w, 2, dims, str, box)) return kErrTensorMap;
+  }
+  GemmParams p{};
+  p.M = B * T * H * W; p.N = Cout; p.K = 27 * Cin;
+  p.out = out; p.ldc = Cout; p.out_f32 = out_f32;
+  p.bias = static_cast<const __nv_bfloat16*>(bias);
+  p.act = kActNone;
+  p.residual = static_cast<const __nv_bfloat16*>(residual); p.ldr = Cout;
+  p.gate = nullptr; p.rows_per_gate = 1;
+  p.store_mode = store_mode == LTXB200_CONV_STORE_NDHWC ? kStoreRowMajor
+                 : (store_mode == LTXB200_CONV_STORE_D2S ? kStoreConvD2S : kStoreConvUnpatch);
+  p.cB = B; p.cT = T; p.cH = H; p.cW = W; p.cCin = Cin; p.cBH = BH; p.cBW = BW;
+  p.c_tiles_h = (H + BH - 1) / BH; p.c_tiles_w = (W + BW - 1) / BW;
+  p.c_causal = causal ? 1 : 0; p.c_taps_t = 3;
+  const int tiles = B * T * p.c_tiles_h * p.c_tiles_w * ((Cout + BN - 1) / BN);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return BN == 128 ? launch_gemm<128, true>(ta, tb, p, tiles, st) : launch_gemm<256, true>(ta, tb, p, tiles, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// attention
+// ------------------------------------------------------------------------------------------
+static int make_qkv_tmap(CUtensorMap* m, const void* base, int B, int H, int L, int d, int64_t ld, int64_t bs) {
+  uint64_t dims[4] = {static_cast<uint64_t>(d), static_cast<uint64_t>(H), static_cast<uint64_t>(L), static_cast<uint64_t>(B)};
+  uint64_t str[3] = {static_cast<uint64_t>(d) * 2, static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(bs) * 2};
+  uint32_t box[4] = {64, 1, 128, 1};
+  return make_tmap_bf16(m, base, 4, dims, str, box);
+}
+
+template <int D>
+static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
+                       cudaStream_t st) {
+  using S = AttnSmem<D>;
+  static bool configured = false;
+  auto kern = attention_fwd_kernel<D>;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal) != cudaSuccess) return kErrCuda;
+    configured = true;
+  }
+  dim3 grid((p.Lq + kAttnBM - 1) / kAttnBM, p.H, p.B);
+  kern<<<grid, kAttnThreads, S::kTotal, st>>>(tq, tk, tv, p);
+  return launch_status();
+}
+
+extern "C" int ltxb200_attention_bf16(const void* q, int64_t ldq, int64_t bsq, const void* k, int64_t ldk, int64_t bsk,
+                                      const void* v, int64_t ldv, int64_t bsv, void* out, int64_t ldo, int64_t bso,
+                                      int B, int H, int Lq, int Lk, int d, float scale, const float* key_bias,
+                                      void* stream) {
+  if (B <= 0 || H <= 0 || Lq <= 0 || Lk <= 0 || B > 65535 || H > 65535) return kErrBadShape;
+  if (d != 64 && d != 128) return kErrUnsupported;
+  if (!aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(out) || (ldq & 7) || (ldk & 7) || (ldv & 7) ||
+      (ldo & 7) || (bsq & 7) || (bsk & 7) || (bsv & 7) || (bso & 7))
+    return kErrBadAlign;
+  CUtensorMap tq, tk, tv;
+  if (make_qkv_tmap(&tq, q, B, H, Lq, d, ldq, bsq) || make_qkv_tmap(&tk, k, B, H, Lk, d, ldk, bsk) ||
+      make_qkv_tmap(&tv, v, B, H, Lk, d, ldv, bsv))
+    return kErrTensorMap;
+  AttnParams p{};
+  p.B = B; p.H = H; p.Lq = Lq; p.Lk = Lk;
+  const float sc = scale > 0.f ? scale : 1.0f / sqrtf(static_cast<float>(d));
+  p.scale_log2 = sc * 1.4426950408889634f;
+  p.key_bias = key_bias;
+  p.out = static_cast<__nv_bfloat16*>(out); p.out_ld = ldo; p.out_bs = bso;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return d == 64 ? launch_attn<64>(tq, tk, tv, p, st) : launch_attn<128>(tq, tk, tv, p, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// memory-bound kernels
+// ------------------------------------------------------------------------------------------
+template <bool LN>
+static int launch_norm(int NV, const __nv_bfloat16* x, __nv_bfloat16* y, int M, int64_t ldx, int64_t ldy,
+                       const __nv_bfloat16* sc, const __nv_bfloat16* sh, int64_t mod_ld, int rpg,
+                       const __nv_bfloat16* w, const __nv_bfloat16* b, float eps, cudaStream_t st) {
+  const int grid = (M + 3) / 4;
+#define NORM_CASE(n) \
+  case n: norm_mod_kernel<n, LN><<<grid, 128, 0, st>>>(x, y, M, ldx, ldy, sc, sh, mod_ld, rpg, w, b, eps); break;
+  switch (NV) {
+    NORM_CASE(1) NORM_CASE(2) NORM_CASE(4) NORM_CASE(6) NORM_CASE(8) NORM_CASE(12) NORM_CASE(16) NORM_CASE(20)
+    default: return kErrUnsupported;
+  }
+#undef NORM_CASE
+  return launch_status();
+}
+
+extern "C" int ltxb200_norm_mod_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, int M, int D, const void* scale,
+                                     const void* shift, int64_t mod_ld, int rows_per_group, const void* weight,
+                                     const void* bias, float eps, int layer_norm, void* stream) {
+  if (M <= 0 || D <= 0 || (D % 256)) return kErrBadShape;
+  if (!aligned16(x) || !aligned16(y) || (ldx & 7) || (ldy & 7) || (scale && (!aligned16(scale) || (mod_ld & 7))) ||
+      (shift && !aligned16(shift)) || (weight && !aligned16(weight)) || (bias && !aligned16(bias)))
+    return kErrBadAlign;
+  if ((scale == nullptr) != (shift == nullptr)) return kErrBadShape;
+  const int rpg = rows_per_group > 0 ? rows_per_group : M;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  auto X = static_cast<const __nv_bfloat16*>(x);
+  auto Y = static_cast<__nv_bfloat16*>(y);
+  auto SC = static_cast<const __nv_bfloat16*>(scale);
+  auto SH = static_cast<const __nv_bfloat16*>(shift);
+  auto Wt = static_cast<const __nv_bfloat16*>(weight);
+  auto Bs = static_cast<const __nv_bfloat16*>(bias);
+  return layer_norm ? launch_norm<true>(D / 256, X, Y, M, ldx, ldy, SC, SH, mod_ld, rpg, Wt, Bs, eps, st)
+                    : launch_norm<false>(D / 256, X, Y, M, ldx, ldy, SC, SH, mod_ld, rpg, Wt, Bs, eps, st);
+}
+
+extern "C" int ltxb200_qk_norm_rope_bf16(void* q, int64_t ldq, int Mq, void* k, int64_t ldk, int Mk, int D,
+                                         const void* wq, const void* wk, const void* cos_table,
+                                         const void* sin_table, int tokens_per_batch, float eps, void* stream) {
+  if (D <= 0 || (D % 256) || (q == nullptr && k == nullptr)) return kErrBadShape;
+  if ((q && (!aligned16(q) || (ldq & 7) || !wq)) || (k && (!aligned16(k) || (ldk & 7) || !wk))) return kErrBadAlign;
+  if ((cos_table == nullptr) != (sin_table == nullptr)) return kErrBadShape;
+  if (cos_table && tokens_per_batch <= 0) return kErrBadShape;
+  const int M = Mq > Mk ? Mq : Mk;
+  dim3 grid((M + 3) / 4, k ? 2 : 1);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  auto Q = static_cast<__nv_bfloat16*>(q);
+  auto Kp = static_cast<__nv_bfloat16*>(k);
+  auto WQ = static_cast<const __nv_bfloat16*>(wq);
+  auto WK = static_cast<const __nv_bfloat16*>(wk);
+  auto C = static_cast<const __nv_bfloat16*>(cos_table);
+  auto Sn = static_cast<const __nv_bfloat16*>(sin_table);
+#define QK_CASE(n) \
+  case n: qk_norm_rope_kernel<n><<<grid, 128, 0, st>>>(Q, Kp, q ? Mq : 0, Mk, ldq, ldk, WQ, WK, C, Sn, tokens_per_batch, eps); break;
+  switch (D / 256) {
+    QK_CASE(2) QK_CASE(4) QK_CASE(6) QK_CASE(8) QK_CASE(12) QK_CASE(16) QK_CASE(20)
+    default: return kErrUnsupported;
+  }
+#undef QK_CASE
+  return launch_status();
+}
+
+extern "C" int ltxb200_ada_add_bf16(const void* table, const void* temb, void* out, int L, int G, int JD, void* stream) {
+  if (L <= 0 || G <= 0 || JD <= 0 || (JD & 7)) return kErrBadShape;
+  if (!aligned16(table) || !aligned16(temb) || !aligned16(out)) return kErrBadAlign;
+  const long long n8 = static_cast<long long>(L) * G * JD / 8;
+  ada_add_kernel<<<ew_blocks(n8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(table), static_cast<const __nv_bfloat16*>(temb), static_cast<__nv_bfloat16*>(out), L, G, JD);
+  return launch_status();
+}
+
+extern "C" int ltxb200_act_bf16(const void* x, void* y, int64_t n, int mode, void* stream) {
+  if (n <= 0 || (n & 7)) return kErrBadShape;
+  if (!aligned16(x) || !aligned16(y)) return kErrBadAlign;
+  act_kernel<<<ew_blocks(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), n, mode);
+  return launch_status();
+}
+
+extern "C" int ltxb200_stg_blend_bf16(void* a, const void* v, int64_t ldv, const float* mask, int B, int64_t rows,
+                                      int D, void* stream) {
+  if (B <= 0 || rows <= 0 || D <= 0 || (D & 7)) return kErrBadShape;
+  if (!aligned16(a) || !aligned16(v) || (ldv & 7)) return kErrBadAlign;
+  // v rows are addressed as (b*rows + r) * ldv: the value slice of the fused QKV buffer
+  stg_blend_kernel<<<ew_blocks(B * rows * D / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<__nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(v), ldv, mask, B, rows, D);
+  return launch_status();
+}
+
+extern "C" int ltxb200_timestep_embed(const float* t, void* out, int n, int dim, void* stream) {
+  if (n <= 0 || dim <= 0 || (dim & 1)) return kErrBadShape;
+  timestep_embed_kernel<<<n, 128, 0, static_cast<cudaStream_t>(stream)>>>(t, static_cast<__nv_bfloat16*>(out), n, dim, 1);
+  return launch_status();
+}
+
+extern "C" int ltxb200_cast_f32_to_bf16(const float* x, void* y, int64_t n, void* stream) {
+  if (n <= 0 || (n & 7)) return kErrBadShape;
+  if (!aligned16(x) || !aligned16(y)) return kErrBadAlign;
+  cast_f32_to_bf16_kernel<<<ew_blocks(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<__nv_bfloat16*>(y), n);
+  return launch_status();
+}
+
+extern "C" int ltxb200_guidance_step(const void* pred, int64_t cond_stride, int64_t n, int channels, int has_cfg,
+                                     int has_stg, int do_rescale, float guidance_scale, float stg_scale,
+                                     float rescale, float* latents, void* latents_bf16, const float* timesteps,
+                                     int num_steps, float t, const float* cond_mask, float* scratch, void* stream) {
+  if (n <= 0 || channels <= 0 || num_steps <= 0 || !latents || !pred || !timesteps) return kErrBadShape;
+  if ((has_cfg || has_stg) && !scratch) return kErrBadShape;
+  GuidanceParams g{};
+  g.pred = static_cast<const __nv_bfloat16*>(pred);
+  g.cond_stride = cond_stride; g.n = n; g.channels = channels;
+  g.has_cfg = has_cfg ? 1 : 0; g.has_stg = has_stg ? 1 : 0; g.do_rescale = do_rescale ? 1 : 0;
+  g.guidance_scale = guidance_scale; g.stg_scale = stg_scale; g.rescale = rescale;
+  g.partials = scratch;
+  g.latents = latents; g.latents_bf16 = static_cast<__nv_bfloat16*>(latents_bf16);
+  g.timesteps = timesteps; g.num_steps = num_steps; g.t = t; g.cond_mask = cond_mask;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = kOk;
+  if (g.has_cfg && guidance_scale != 0.f && guidance_scale != 1.f) {
+    guidance_reduce_kernel<0><<<kGuidanceBlocks, 256, 0, st>>>(g);
+    rc = launch_status();
+    if (rc) return rc;
+  } else {
+    g.has_cfg = g.has_cfg;   // alpha unused when scale is 0/1 (combine falls back to text)
+  }
+  if (g.has_stg && g.do_rescale && stg_scale > 0.f) {
+    guidance_reduce_kernel<1><<<kGuidanceBlocks, 256, 0, st>>>(g);
+    rc = launch_status();
+    if (rc) return rc;
+  }
+  guidance_step_kernel<<<kGuidanceBlocks, 256, 0, st>>>(g);
+  return launch_status();
+}
+
+extern "C" int ltxb200_pixelnorm_silu_bf16(const void* x, void* y, int64_t voxels, int C, float eps, int apply_silu,
+                                           void* stream) {
+  if (voxels <= 0) return kErrBadShape;
+  if (!aligned16(x) || !aligned16(y)) return kErrBadAlign;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  auto X = static_cast<const __nv_bfloat16*>(x);
+  auto Y = static_cast<__nv_bfloat16*>(y);
+#define PN_CASE(c)                                                                             \
+  case c: {                                                                                    \
+    constexpr int G = (c / 8 < 32) ? c / 8 : 32;                                               \
+    const long long warps = (voxels + (32 / G) - 1) / (32 / G);                                \
+    const long long blocks = (warps + 7) / 8;                                                  \
+    pixelnorm_silu_kernel<c><<<static_cast<unsigned>(blocks), 256, 0, st>>>(X, Y, voxels, eps, apply_silu); \
+  } break;
+  switch (C) {
+    PN_CASE(64) PN_CASE(128) PN_CASE(256) PN_CASE(512) PN_CASE(1024)
+    default: return kErrUnsupported;
+  }
+#undef PN_CASE
+  return launch_status();
+}
+
+extern "C" int ltxb200_latent_to_ndhwc(const void* z, int is_f32, void* out, int B, int C, int64_t FHW,
+                                       const float* stdv, const float* meanv, void* stream) {
+  if (B <= 0 || C <= 0 || FHW <= 0) return kErrBadShape;
+  if ((stdv == nullptr) != (meanv == nullptr)) return kErrBadShape;
+  const long long n = static_cast<long long>(B) * C * FHW;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (is_f32)
+    latent_to_ndhwc_kernel<float><<<ew_blocks(n, 256), 256, 0, st>>>(static_cast<const float*>(z), static_cast<__nv_bfloat16*>(out), B, C, FHW, stdv, meanv);
+  else
+    latent_to_ndhwc_kernel<__nv_bfloat16><<<ew_blocks(n, 256), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(z), static_cast<__nv_bfloat16*>(out), B, C, FHW, stdv, meanv);
+  return launch_status();
+}

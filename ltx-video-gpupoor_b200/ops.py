@@ -1,0 +1,209 @@
+"""Torch-facing wrappers over the C ABI: torch owns device memory and streams, every arithmetic op
+below is a hand-written sm_100a kernel in libltx_b200.so.  All tensors must be CUDA tensors."""
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+BF16 = torch.bfloat16
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, dtype=BF16, name="tensor"):
+    if not t.is_cuda:
+        raise _lib.LtxB200Error(f"{name}: expected a CUDA tensor (this package has no CPU path)")
+    if t.dtype != dtype:
+        raise _lib.LtxB200Error(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if t.stride(-1) != 1:
+        raise _lib.LtxB200Error(f"{name}: last dimension must be contiguous")
+    return t
+
+
+ACT_NONE, ACT_GELU_TANH, ACT_SILU = 0, 1, 2
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
+         residual: Optional[torch.Tensor] = None, gate: Optional[torch.Tensor] = None, rows_per_gate: int = 1,
+         out: Optional[torch.Tensor] = None, out_f32: bool = False) -> torch.Tensor:
+    """out[M,N] = ((a @ w.T + bias) -> act) * gate[m // rows_per_gate] + residual.  a [M,K], w [N,K] bf16."""
+    _req(a, name="a"); _req(w, name="w")
+    assert a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1]
+    M, K = a.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty(M, N, device=a.device, dtype=torch.float32 if out_f32 else BF16)
+    _req(out, torch.float32 if out_f32 else BF16, "out")
+    if bias is not None:
+        _req(bias, name="bias"); assert bias.numel() == N
+    if residual is not None:
+        _req(residual, name="residual"); assert residual.shape == (M, N)
+    if gate is not None:
+        _req(gate, name="gate"); assert gate.dim() == 2 and gate.shape[1] == N
+    rc = _lib.lib().ltxb200_gemm_bf16(
+        a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, N, K, out.data_ptr(), out.stride(0),
+        1 if out_f32 else 0, _p(bias), act, _p(residual), residual.stride(0) if residual is not None else 0,
+        _p(gate), gate.stride(0) if gate is not None else 0, rows_per_gate, _stream())
+    _lib.check(rc, "gemm_bf16")
+    return out
+
+
+CONV_NDHWC, CONV_D2S, CONV_UNPATCH = 0, 1, 2
+
+
+def conv3d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], causal: bool = False,
+           store: int = CONV_NDHWC, residual: Optional[torch.Tensor] = None, out_f32: bool = False) -> torch.Tensor:
+    """x [B,T,H,W,Cin] bf16 (NDHWC, contiguous); w [Cout, 27*Cin] bf16 (tap-major K)."""
+    _req(x, name="x"); _req(w, name="w")
+    assert x.is_contiguous() and w.is_contiguous() and x.dim() == 5
+    B, T, H, W, Cin = x.shape
+    Cout = w.shape[0]
+    assert w.shape[1] == 27 * Cin
+    if store == CONV_NDHWC:
+        out = torch.empty(B, T, H, W, Cout, device=x.device, dtype=BF16)
+    elif store == CONV_D2S:
+        out = torch.empty(B, 2 * T - 1, 2 * H, 2 * W, Cout // 8, device=x.device, dtype=BF16)
+    else:
+        out = torch.empty(B, Cout // 16, T, 4 * H, 4 * W, device=x.device, dtype=torch.float32 if out_f32 else BF16)
+    if residual is not None:
+        _req(residual, name="residual"); assert residual.is_contiguous() and residual.shape == out.shape
+    rc = _lib.lib().ltxb200_conv3d_bf16(x.data_ptr(), w.data_ptr(), _p(bias), out.data_ptr(), B, T, H, W, Cin, Cout,
+                                        1 if causal else 0, store, 1 if out_f32 else 0, _p(residual), _stream())
+    _lib.check(rc, "conv3d_bf16")
+    return out
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_bias: Optional[torch.Tensor] = None,
+              scale: float = 0.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q [B,Lq,H,d], k/v [B,Lk,H,d] bf16 (strided views allowed, head stride must be d) -> [B,Lq,H,d]."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _req(t, name=n)
+        assert t.dim() == 4 and t.stride(2) == t.shape[3], f"{n}: heads must be packed (stride(2) == d)"
+    B, Lq, H, d = q.shape
+    Lk = k.shape[1]
+    if out is None:
+        out = torch.empty(B, Lq, H, d, device=q.device, dtype=BF16)
+    _req(out, name="out")
+    if key_bias is not None:
+        _req(key_bias, torch.float32, "key_bias"); assert key_bias.shape == (B, Lk) and key_bias.is_contiguous()
+    rc = _lib.lib().ltxb200_attention_bf16(
+        q.data_ptr(), q.stride(1), q.stride(0), k.data_ptr(), k.stride(1), k.stride(0),
+        v.data_ptr(), v.stride(1), v.stride(0), out.data_ptr(), out.stride(1), out.stride(0),
+        B, H, Lq, Lk, d, float(scale), _p(key_bias), _stream())
+    _lib.check(rc, "attention_bf16")
+    return out
+
+
+def norm_mod(x: torch.Tensor, scale: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None,
+             rows_per_group: int = 0, weight: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
+             eps: float = 1e-6, layer_norm: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [M,D]; scale/shift [G, D] row views with a common row stride."""
+    _req(x, name="x"); assert x.dim() == 2
+    M, D = x.shape
+    if out is None:
+        out = torch.empty(M, D, device=x.device, dtype=BF16)
+    mod_ld = 0
+    if scale is not None:
+        _req(scale, name="scale"); _req(shift, name="shift")
+        assert scale.dim() == 2 and shift.dim() == 2 and scale.stride(0) == shift.stride(0)
+        mod_ld = scale.stride(0)
+    rc = _lib.lib().ltxb200_norm_mod_bf16(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), M, D, _p(scale),
+                                          _p(shift), mod_ld, rows_per_group, _p(weight), _p(bias), float(eps),
+                                          1 if layer_norm else 0, _stream())
+    _lib.check(rc, "norm_mod_bf16")
+    return out
+
+
+def qk_norm_rope(q: Optional[torch.Tensor], k: Optional[torch.Tensor], wq, wk, cos=None, sin=None,
+                 tokens_per_batch: int = 0, eps: float = 1e-5):
+    """In-place on 2-D row views q [Mq,D], k [Mk,D]."""
+    D = (q if q is not None else k).shape[1]
+    rc = _lib.lib().ltxb200_qk_norm_rope_bf16(
+        _p(q), q.stride(0) if q is not None else 0, q.shape[0] if q is not None else 0,
+        _p(k), k.stride(0) if k is not None else 0, k.shape[0] if k is not None else 0, D,
+        _p(wq), _p(wk), _p(cos), _p(sin), tokens_per_batch, float(eps), _stream())
+    _lib.check(rc, "qk_norm_rope_bf16")
+
+
+def ada_add(table: torch.Tensor, temb: torch.Tensor) -> torch.Tensor:
+    """table [L, J, D], temb [G, J*D] -> [L, G, J, D]"""
+    _req(table, name="table"); _req(temb, name="temb")
+    L, J, D = table.shape
+    G = temb.shape[0]
+    assert table.is_contiguous() and temb.is_contiguous() and temb.shape[1] == J * D
+    out = torch.empty(L, G, J, D, device=table.device, dtype=BF16)
+    _lib.check(_lib.lib().ltxb200_ada_add_bf16(table.data_ptr(), temb.data_ptr(), out.data_ptr(), L, G, J * D, _stream()),
+               "ada_add_bf16")
+    return out
+
+
+def act(x: torch.Tensor, mode: int) -> torch.Tensor:
+    _req(x, name="x"); assert x.is_contiguous()
+    y = torch.empty_like(x)
+    _lib.check(_lib.lib().ltxb200_act_bf16(x.data_ptr(), y.data_ptr(), x.numel(), mode, _stream()), "act_bf16")
+    return y
+
+
+def stg_blend(a: torch.Tensor, v: torch.Tensor, mask: torch.Tensor):
+    """a [B, rows, D] contiguous (in place); v [B*rows, D] row view; mask [B] fp32"""
+    B, rows, D = a.shape
+    _req(a, name="a"); _req(v, name="v"); _req(mask, torch.float32, "mask")
+    assert a.is_contiguous()
+    _lib.check(_lib.lib().ltxb200_stg_blend_bf16(a.data_ptr(), v.data_ptr(), v.stride(0), mask.data_ptr(), B, rows, D,
+                                                 _stream()), "stg_blend_bf16")
+
+
+def timestep_embed(t: torch.Tensor, dim: int = 256) -> torch.Tensor:
+    _req(t, torch.float32, "t"); assert t.dim() == 1 and t.is_contiguous()
+    out = torch.empty(t.shape[0], dim, device=t.device, dtype=BF16)
+    _lib.check(_lib.lib().ltxb200_timestep_embed(t.data_ptr(), out.data_ptr(), t.shape[0], dim, _stream()), "timestep_embed")
+    return out
+
+
+def cast_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(x, torch.float32, "x"); assert x.is_contiguous()
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=BF16)
+    _lib.check(_lib.lib().ltxb200_cast_f32_to_bf16(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "cast")
+    return out
+
+
+def guidance_step(pred: torch.Tensor, latents: torch.Tensor, timesteps: torch.Tensor, t: float, *, num_conds: int,
+                  has_cfg: bool, has_stg: bool, do_rescale: bool, guidance_scale: float, stg_scale: float,
+                  rescale: float, channels: int, cond_mask: Optional[torch.Tensor], scratch: torch.Tensor,
+                  latents_bf16: Optional[torch.Tensor] = None):
+    """pred [num_conds, n] bf16 (batch 1), latents [n] fp32 in place."""
+    _req(pred, name="pred"); _req(latents, torch.float32, "latents"); _req(timesteps, torch.float32, "timesteps")
+    assert pred.is_contiguous() and latents.is_contiguous()
+    n = latents.numel()
+    assert pred.numel() == num_conds * n
+    rc = _lib.lib().ltxb200_guidance_step(pred.data_ptr(), n, n, channels, int(has_cfg), int(has_stg), int(do_rescale),
+                                          float(guidance_scale), float(stg_scale), float(rescale), latents.data_ptr(),
+                                          _p(latents_bf16), timesteps.data_ptr(), timesteps.numel(), float(t),
+                                          _p(cond_mask), scratch.data_ptr(), _stream())
+    _lib.check(rc, "guidance_step")
+
+
+def pixelnorm_silu(x: torch.Tensor, silu: bool = True, eps: float = 1e-8) -> torch.Tensor:
+    _req(x, name="x"); assert x.is_contiguous()
+    C = x.shape[-1]
+    y = torch.empty_like(x)
+    _lib.check(_lib.lib().ltxb200_pixelnorm_silu_bf16(x.data_ptr(), y.data_ptr(), x.numel() // C, C, float(eps),
+                                                      int(silu), _stream()), "pixelnorm_silu")
+    return y
+
+
+def latent_to_ndhwc(z: torch.Tensor, stdv: Optional[torch.Tensor], meanv: Optional[torch.Tensor]) -> torch.Tensor:
+    assert z.is_cuda and z.is_contiguous() and z.dim() == 5 and z.dtype in (torch.float32, BF16)
+    B, C, F_, H, W = z.shape
+    out = torch.empty(B, F_, H, W, C, device=z.device, dtype=BF16)
+    _lib.check(_lib.lib().ltxb200_latent_to_ndhwc(z.data_ptr(), int(z.dtype == torch.float32), out.data_ptr(), B, C,
+                                                  F_ * H * W, _p(stdv), _p(meanv), _stream()), "latent_to_ndhwc")
+    return out

@@ -1,0 +1,256 @@
+"""GPU parity tests of every C-ABI kernel against a plain PyTorch fp32 restatement of the same op
+(the oracle's functions where one exists).  Tolerances are for bf16 inputs/outputs with fp32 accumulation."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():  # collected but skipped on the CPU box (-m "not gpu" deselects anyway)
+    pytest.skip("needs a GPU", allow_module_level=True)
+
+from ltx_video_gpupoor_b200 import ops  # noqa: E402
+from oracle import ltx_oracle as O  # noqa: E402
+
+DEV = "cuda"
+BF = torch.bfloat16
+
+
+def rnd(*shape, seed=0, scale=1.0, dtype=BF):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dtype).to(DEV)
+
+
+def rel(a, b):
+    return O.rel_l2(a.float().cpu(), b.float().cpu())
+
+
+# ------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 128, 128), (300, 136, 72), (1, 512, 256), (3, 12288, 2048),
+                                   (6144, 2048, 2048), (1000, 8192, 2048), (777, 2048, 8192), (6144, 128, 2048),
+                                   (6144, 2048, 128)])
+def test_gemm_plain(M, N, K):
+    a, w, b = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=K ** -0.5), rnd(N, seed=3)
+    ref = a.float() @ w.float().t() + b.float()
+    out = ops.gemm(a, w, b)
+    torch.cuda.synchronize()
+    assert rel(out, ref) < 6e-3, rel(out, ref)
+
+
+def test_gemm_epilogues():
+    M, N, K = 515, 768, 320
+    a, w, b = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=K ** -0.5), rnd(N, seed=3)
+    res = rnd(M, N, seed=4)
+    rows_per_gate = 103
+    gate = rnd((M + rows_per_gate - 1) // rows_per_gate, N, seed=5)
+    base = a.float() @ w.float().t() + b.float()
+    assert rel(ops.gemm(a, w, b, act=ops.ACT_GELU_TANH), F.gelu(base, approximate="tanh")) < 6e-3
+    assert rel(ops.gemm(a, w, b, act=ops.ACT_SILU), F.silu(base)) < 6e-3
+    g_full = gate.float().repeat_interleave(rows_per_gate, dim=0)[:M]
+    ref = res.float() + g_full * base
+    out = ops.gemm(a, w, b, residual=res, gate=gate, rows_per_gate=rows_per_gate)
+    assert rel(out, ref) < 6e-3
+    # in place on the residual, fp32 output, strided A
+    r2 = res.clone()
+    ops.gemm(a, w, b, residual=r2, out=r2)
+    assert rel(r2, res.float() + base) < 6e-3
+    big = rnd(M, 2 * K, seed=7)
+    o32 = ops.gemm(big[:, K:], w, None, out_f32=True)
+    assert o32.dtype == torch.float32
+    assert rel(o32, big[:, K:].float() @ w.float().t()) < 2e-3
+
+
+# ------------------------------------------------------------------ attention
+def ref_attn(q, k, v, bias=None):
+    return O.attention_core(q.float().cpu(), k.float().cpu(), v.float().cpu(),
+                            None if bias is None else bias.cpu()[:, None, None, :])
+
+
+@pytest.mark.parametrize("d", [64, 128])
+@pytest.mark.parametrize("B,H,Lq,Lk", [(1, 2, 128, 128), (2, 3, 256, 384), (1, 2, 300, 333), (1, 4, 1024, 1000),
+                                       (2, 2, 130, 77)])
+def test_attention(d, B, H, Lq, Lk):
+    q, k, v = rnd(B, Lq, H, d, seed=1), rnd(B, Lk, H, d, seed=2), rnd(B, Lk, H, d, seed=3)
+    out = ops.attention(q, k, v)
+    torch.cuda.synchronize()
+    assert rel(out, ref_attn(q, k, v)) < 1e-2
+
+
+@pytest.mark.parametrize("d", [64, 128])
+def test_attention_bias_and_fused_qkv(d):
+    B, H, L, Lk = 2, 4, 384, 200
+    qkv = rnd(B, L, 3 * H * d, seed=5)
+    q, k, v = [qkv[:, :, i * H * d:(i + 1) * H * d].unflatten(-1, (H, d)) for i in range(3)]
+    out = ops.attention(q, k, v)
+    assert rel(out, ref_attn(q, k, v)) < 1e-2
+    kk, vv = rnd(B, Lk, H, d, seed=6), rnd(B, Lk, H, d, seed=7)
+    bias = torch.zeros(B, Lk, device=DEV)
+    bias[0, 150:] = -10000.0
+    bias[1, 31:] = -10000.0
+    out = ops.attention(q, kk, vv, key_bias=bias)
+    assert rel(out, ref_attn(q, kk, vv, bias)) < 1e-2
+    # large-magnitude logits exercise the lazy rescale
+    qs = (q.float() * 6).to(BF)
+    out = ops.attention(qs, k, v)
+    assert rel(out, ref_attn(qs, k, v)) < 1.5e-2
+
+
+# ------------------------------------------------------------------ conv3d
+def ref_conv(x_ndhwc, w5, b, causal):
+    x = x_ndhwc.float().permute(0, 4, 1, 2, 3)
+    if causal:
+        x = torch.cat([x[:, :, :1].repeat(1, 1, 2, 1, 1), x], dim=2)
+    else:
+        x = torch.cat([x[:, :, :1], x, x[:, :, -1:]], dim=2)
+    return F.conv3d(x, w5.float(), b.float(), padding=(0, 1, 1))          # NCDHW
+
+
+def pack_w(w5):   # [Cout, Cin, 3,3,3] -> [Cout, 27*Cin] tap-major
+    return w5.permute(0, 2, 3, 4, 1).reshape(w5.shape[0], -1).contiguous()
+
+
+@pytest.mark.parametrize("B,T,H,W,Cin,Cout,causal", [(1, 3, 8, 16, 64, 128, False), (2, 2, 5, 7, 128, 64, True),
+                                                     (1, 4, 16, 24, 128, 256, False), (1, 1, 3, 3, 64, 512, False)])
+def test_conv3d_plain(B, T, H, W, Cin, Cout, causal):
+    x = rnd(B, T, H, W, Cin, seed=1)
+    w5 = rnd(Cout, Cin, 3, 3, 3, seed=2, scale=(27 * Cin) ** -0.5)
+    b = rnd(Cout, seed=3)
+    ref = ref_conv(x, w5, b, causal).permute(0, 2, 3, 4, 1)
+    out = ops.conv3d(x, pack_w(w5), b, causal=causal)
+    torch.cuda.synchronize()
+    assert rel(out, ref) < 6e-3
+    res = rnd(B, T, H, W, Cout, seed=4)
+    out = ops.conv3d(x, pack_w(w5), b, causal=causal, residual=res)
+    assert rel(out, ref + res.float()) < 6e-3
+
+
+def test_conv3d_d2s_and_unpatch():
+    B, T, H, W, Cin = 1, 3, 6, 10, 64
+    x = rnd(B, T, H, W, Cin, seed=1)
+    # depth-to-space: Cout = 8*C, reference channel order (c p1 p2 p3); kernel wants (p1 p2 p3 c)
+    C = 32
+    w5 = rnd(8 * C, Cin, 3, 3, 3, seed=2, scale=(27 * Cin) ** -0.5)
+    b = rnd(8 * C, seed=3)
+    ref = O.depth_to_space(ref_conv(x, w5, b, False))[:, :, 1:].permute(0, 2, 3, 4, 1)
+    perm = torch.arange(8 * C).reshape(C, 8).t().reshape(-1).to(DEV)          # new row (p,c) <- old row c*8+p
+    out = ops.conv3d(x, pack_w(w5[perm]), b[perm].contiguous(), store=ops.CONV_D2S)
+    assert out.shape == ref.shape
+    assert rel(out, ref) < 6e-3
+    # unpatchify: Cout = 3*16, reference channel order (c r q); kernel wants (c q r)
+    w5 = rnd(48, Cin, 3, 3, 3, seed=4, scale=(27 * Cin) ** -0.5)
+    b = rnd(48, seed=5)
+    ref = O.vae_unpatchify(ref_conv(x, w5, b, False), 4)
+    perm = torch.arange(48).reshape(3, 4, 4).permute(0, 2, 1).reshape(-1).to(DEV)   # new (c,q,r) <- old (c,r,q)
+    out = ops.conv3d(x, pack_w(w5[perm]), b[perm].contiguous(), store=ops.CONV_UNPATCH, out_f32=True)
+    assert out.shape == ref.shape
+    assert rel(out, ref) < 6e-3
+
+
+# ------------------------------------------------------------------ memory-bound kernels
+@pytest.mark.parametrize("D", [2048, 1536, 512])
+@pytest.mark.parametrize("ln", [False, True])
+def test_norm_mod(D, ln):
+    M, rpg = 77, 20
+    x = rnd(M, D, seed=1, scale=3.0)
+    G = (M + rpg - 1) // rpg
+    mod = rnd(G, 6, D, seed=2, scale=0.3)
+    sc, sh = mod[:, 1], mod[:, 0]
+    xf = x.float()
+    base = F.layer_norm(xf, (D,), eps=1e-6) if ln else xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6)
+    ref = base * (1 + sc.float().repeat_interleave(rpg, 0)[:M]) + sh.float().repeat_interleave(rpg, 0)[:M]
+    out = ops.norm_mod(x, sc, sh, rows_per_group=rpg, eps=1e-6, layer_norm=ln)
+    assert rel(out, ref) < 8e-3
+    assert rel(ops.norm_mod(x, eps=1e-6, layer_norm=ln), base) < 5e-3
+    w, b = rnd(D, seed=3), rnd(D, seed=4)
+    if ln:
+        assert rel(ops.norm_mod(x, weight=w, bias=b, eps=1e-6, layer_norm=True),
+                   F.layer_norm(xf, (D,), w.float(), b.float(), eps=1e-6)) < 5e-3
+
+
+def test_qk_norm_rope_matches_oracle():
+    B, N, D = 2, 96, 2048
+    qkv = rnd(B * N, 3 * D, seed=1)
+    wq, wk = (1 + 0.1 * rnd(D, seed=2).float()).to(BF), (1 + 0.1 * rnd(D, seed=3).float()).to(BF)
+    coords = O.latent_to_pixel_coords(O.latent_coords(2, 6, 8, 1)).float()
+    coords[:, 0] /= 25.0
+    cos, sin = O.precompute_freqs_cis(coords, D, 10000.0, (20, 2048, 2048), BF)
+    cos, sin = cos[0].contiguous().to(DEV), sin[0].contiguous().to(DEV)
+    q, k = qkv[:, :D], qkv[:, D:2 * D]
+    refq = O.apply_rotary_emb(O.rms_norm(q.float().view(B, N, D), 1e-5, wq.float()), cos.float(), sin.float())
+    refk = O.apply_rotary_emb(O.rms_norm(k.float().view(B, N, D), 1e-5, wk.float()), cos.float(), sin.float())
+    v_before = qkv[:, 2 * D:].clone()
+    ops.qk_norm_rope(q, k, wq, wk, cos, sin, tokens_per_batch=N, eps=1e-5)
+    assert rel(q.reshape(B, N, D), refq) < 8e-3 and rel(k.reshape(B, N, D), refk) < 8e-3
+    assert torch.equal(qkv[:, 2 * D:], v_before)
+    # no rope, q only (cross-attention query)
+    q2 = rnd(50, D, seed=9)
+    ref = O.rms_norm(q2.float(), 1e-5, wq.float())
+    ops.qk_norm_rope(q2, None, wq, None)
+    assert rel(q2, ref) < 6e-3
+
+
+def test_small_elementwise():
+    L, G, D = 3, 5, 512
+    table, temb = rnd(L, 6, D, seed=1), rnd(G, 6 * D, seed=2)
+    ref = (table.float()[:, None] + temb.float().view(1, G, 6, D))
+    assert rel(ops.ada_add(table, temb), ref) < 5e-3
+    x = rnd(40, 256, seed=3)
+    assert rel(ops.act(x, ops.ACT_SILU), F.silu(x.float())) < 5e-3
+    assert rel(ops.act(x, ops.ACT_GELU_TANH), F.gelu(x.float(), approximate="tanh")) < 5e-3
+    t = torch.tensor([0.0, 731.1, 1000.0, 12.5], device=DEV)
+    assert rel(ops.timestep_embed(t), O.timestep_sinusoid(t.cpu())) < 5e-3
+    a, v = rnd(3, 10, 256, seed=4), rnd(30, 3 * 256, seed=5)
+    m = torch.tensor([1.0, 0.0, 1.0], device=DEV)
+    ref = a.float() * m.view(3, 1, 1) + v[:, 512:].float().view(3, 10, 256) * (1 - m.view(3, 1, 1))
+    ops.stg_blend(a, v[:, 512:], m)
+    assert rel(a, ref) < 5e-3
+    xf = torch.randn(1024, device=DEV)
+    assert torch.equal(ops.cast_bf16(xf), xf.to(BF))
+
+
+@pytest.mark.parametrize("C", [128, 256, 512])
+def test_pixelnorm_silu(C):
+    x = rnd(2, 3, 5, 7, C, seed=1, scale=2.0)
+    ref = F.silu(O.pixel_norm(x.float().permute(0, 4, 1, 2, 3))).permute(0, 2, 3, 4, 1)
+    assert rel(ops.pixelnorm_silu(x), ref) < 6e-3
+
+
+def test_latent_to_ndhwc():
+    z = torch.randn(1, 128, 2, 3, 4, device=DEV)
+    s, m = torch.rand(128, device=DEV) + 0.5, torch.randn(128, device=DEV) * 0.1
+    ref = (z * s.view(1, -1, 1, 1, 1) + m.view(1, -1, 1, 1, 1)).permute(0, 2, 3, 4, 1)
+    assert rel(ops.latent_to_ndhwc(z, s, m), ref) < 8e-3
+
+
+@pytest.mark.parametrize("mode", ["plain", "cfg", "cfg_stg", "stg_mask"])
+def test_guidance_step(mode):
+    N, C, steps = 96, 128, 8
+    has_cfg = mode in ("cfg", "cfg_stg")
+    has_stg = mode in ("cfg_stg", "stg_mask")
+    conds = 1 + has_cfg + has_stg
+    pred = rnd(conds, N * C, seed=1)
+    lat = torch.randn(N * C, device=DEV)
+    ts = O.rf_timesteps(steps, (1, C, 2, 6, 8)).to(DEV)
+    i = 3
+    cmask = None
+    if mode == "stg_mask":
+        cmask = torch.zeros(N, device=DEV)
+        cmask[:48] = 1.0
+    gs, ss, rs = (3.0 if has_cfg else 1.0), (1.0 if has_stg else 0.0), (0.7 if has_stg else 1.0)
+    npred = O.guidance_combine(pred.float().cpu().view(conds, N, C), conds, has_cfg, has_stg, gs, ss, rs, rs != 1.0)
+    cur = ts[i].cpu()[None, None]
+    if cmask is not None:
+        cur = torch.min(cur, 1.0 - cmask.cpu()[None])
+    ref = O.rf_step(npred, cur, lat.cpu().view(1, N, C), ts.cpu())
+    if cmask is not None:
+        keep = (ts[i].cpu() - 1e-6 < (1.0 - cmask.cpu()[None])).unsqueeze(-1)
+        ref = torch.where(keep, ref, lat.cpu().view(1, N, C))
+    scratch = torch.empty(8 * 148, device=DEV)
+    lb = torch.empty(N * C, device=DEV, dtype=BF)
+    ops.guidance_step(pred, lat, ts, float(ts[i]), num_conds=conds, has_cfg=has_cfg, has_stg=has_stg,
+                      do_rescale=rs != 1.0, guidance_scale=gs, stg_scale=ss, rescale=rs, channels=C,
+                      cond_mask=cmask, scratch=scratch, latents_bf16=lb)
+    assert rel(lat.view(1, N, C), ref) < 2e-3
+    assert torch.equal(lb, lat.to(BF))
