@@ -1,0 +1,220 @@
+"""CausalVideoAutoencoder (decode path) — B200-native drop-in for
+ltx_video/models/autoencoders/causal_video_autoencoder.py:33-300,560-802,1023-1258,1282-1299 and
+vae.py:343-413, vae_encode.py:94-165,239-247.
+
+Activations are kept NDHWC bf16 so that (a) every 3x3x3 convolution is a TMA-tiled implicit GEMM on
+tcgen05 (spatial zero padding = TMA out-of-bounds fill, temporal replicate padding = clamped frame
+coordinate, no concat), (b) PixelNorm is a per-voxel reduction over the contiguous channel vector,
+(c) depth-to-space, the first-frame drop, the residual add and the final 4x4 unpatchify are store
+patterns of the conv epilogue instead of extra passes.  Encoder = SURVEY §8(f) "next".
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from types import SimpleNamespace
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from .. import ops
+
+BF16 = torch.bfloat16
+
+# ltx_video/utils/diffusers_config_mapping.py:106-130 (OURS_VAE_CONFIG)
+LTX_VAE_CONFIG = dict(
+    _class_name="CausalVideoAutoencoder", dims=3, in_channels=3, out_channels=3, latent_channels=128,
+    blocks=[["res_x", 4], ["compress_all", 1], ["res_x_y", 1], ["res_x", 3], ["compress_all", 1], ["res_x_y", 1],
+            ["res_x", 3], ["compress_all", 1], ["res_x", 3], ["res_x", 4]],
+    scaling_factor=1.0, norm_layer="pixel_norm", patch_size=4, latent_log_var="uniform", use_quant_conv=False,
+    causal_decoder=False,
+)
+
+
+@dataclass
+class DecoderOutput:
+    sample: torch.Tensor
+
+
+def _pack_conv(w5: torch.Tensor, perm: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[Cout, Cin, 3,3,3] -> [Cout, 27*Cin] with k = ((kt*3+kh)*3+kw)*Cin + ci; optional output-row permutation."""
+    if perm is not None:
+        w5 = w5[perm]
+    return w5.permute(0, 2, 3, 4, 1).reshape(w5.shape[0], -1).to(BF16).contiguous()
+
+
+class _Decoder:
+    timestep_conditioning = False
+
+
+class CausalVideoAutoencoder:
+    def __init__(self, **config):
+        cfg = dict(LTX_VAE_CONFIG)
+        cfg.update({k: v for k, v in config.items()})
+        if cfg["norm_layer"] != "pixel_norm" or cfg["dims"] != 3:
+            raise NotImplementedError("only the pixel_norm / 3D configuration of the named 2B VAE is implemented")
+        if cfg.get("timestep_conditioning", False):
+            raise NotImplementedError("timestep-conditioned decoders are SURVEY §8(f) next")
+        self._cfg = cfg
+        self.config = SimpleNamespace(**{k: v for k, v in cfg.items() if not k.startswith("_")})
+        self.decoder = _Decoder()
+        self.decoder.causal = cfg["causal_decoder"]
+        self.decoder.patch_size = cfg["patch_size"]
+        self.dtype = BF16
+        self.device = torch.device("cuda")
+        self.use_z_tiling = False
+        self.use_hw_tiling = False
+        self.plan: List[Tuple] = []
+        self.w: Dict[str, torch.Tensor] = {}
+        self.std_of_means = None
+        self.mean_of_means = None
+
+    @staticmethod
+    def from_config(config):
+        assert config["_class_name"] == "CausalVideoAutoencoder"
+        return CausalVideoAutoencoder(**config)
+
+    # vae.py:92-115 — on a 180 GB part tiling is never needed
+    @staticmethod
+    def get_VAE_tile_size(vae_config, device_mem_capacity, mixed_precision):
+        return (0, 0)
+
+    @property
+    def spatial_downscale_factor(self):
+        n = len([b for b in self._cfg["blocks"] if b[0] in ("compress_space", "compress_all", "compress_all_res", "compress_space_res")])
+        return 2 ** n * self._cfg["patch_size"]
+
+    @property
+    def temporal_downscale_factor(self):
+        n = len([b for b in self._cfg["blocks"] if b[0] in ("compress_time", "compress_all", "compress_all_res", "compress_space_res")])
+        return 2 ** n
+
+    def _plan(self):
+        ch = 128 * (2 ** len([b for b in self._cfg["blocks"] if b[0] == "res_x_y"]))
+        plan = []
+        for idx, (name, p) in enumerate(reversed(self._cfg["blocks"])):
+            if name == "res_x":
+                plan.append(("res_x", idx, ch, ch, int(p)))
+            elif name == "res_x_y":
+                plan.append(("res_x_y", idx, ch, ch // 2, 1))
+                ch //= 2
+            elif name == "compress_all":
+                plan.append(("d2s", idx, ch, ch, 1))
+            else:
+                raise NotImplementedError(f"decoder block {name}")
+        return plan, ch
+
+    def load_state_dict(self, state_dict: Dict[str, torch.Tensor], strict: bool = True, device="cuda", **_):
+        """Reference key layout ('decoder.…', optional 'vae.' prefix, 'per_channel_statistics.*' or the
+        registered std_of_means / mean_of_means buffers; causal_video_autoencoder.py:239-297)."""
+        if any(k.startswith("vae.") for k in state_dict):
+            state_dict = {k.replace("vae.", "", 1): v for k, v in state_dict.items() if k.startswith("vae.")}
+        self.device = dev = torch.device(device)
+        sd = state_dict
+        w = {}
+
+        def conv(name, perm=None):
+            wt = sd[name + ".weight"].to(dev)
+            b = sd[name + ".bias"].to(dev)
+            if perm is not None:
+                b = b[perm]
+            return _pack_conv(wt, perm), b.to(BF16).contiguous()
+
+        self.plan, last = self._plan()
+        w["conv_in"] = conv("decoder.conv_in.conv")
+        for kind, idx, cin, cout, n in self.plan:
+            p = f"decoder.up_blocks.{idx}."
+            if kind == "res_x":
+                for j in range(n):
+                    w[p + f"{j}.conv1"] = conv(p + f"res_blocks.{j}.conv1.conv")
+                    w[p + f"{j}.conv2"] = conv(p + f"res_blocks.{j}.conv2.conv")
+            elif kind == "res_x_y":
+                w[p + "conv1"] = conv(p + "conv1.conv")
+                w[p + "conv2"] = conv(p + "conv2.conv")
+                w[p + "shortcut"] = (sd[p + "conv_shortcut.weight"].to(dev).reshape(cout, cin).to(BF16).contiguous(),
+                                     sd[p + "conv_shortcut.bias"].to(dev).to(BF16).contiguous())
+                w[p + "norm3"] = (sd[p + "norm3.norm.weight"].to(dev).to(BF16).contiguous(),
+                                  sd[p + "norm3.norm.bias"].to(dev).to(BF16).contiguous())
+            else:
+                # pixel-shuffle channel order (c p1 p2 p3) -> (p1 p2 p3 c) so each 2x2x2 sub-voxel is contiguous
+                perm = torch.arange(8 * cin, device=dev).reshape(cin, 8).t().reshape(-1)
+                w[p + "conv"] = conv(p + "conv.conv", perm)
+        ps = self._cfg["patch_size"]
+        co = self._cfg["out_channels"]
+        # unpatchify channel order (c r q) -> (c q r): r (width) innermost
+        perm = torch.arange(co * ps * ps, device=dev).reshape(co, ps, ps).permute(0, 2, 1).reshape(-1)
+        w["conv_out"] = conv("decoder.conv_out.conv", perm)
+        std = sd.get("std_of_means", sd.get("per_channel_statistics.std-of-means"))
+        mean = sd.get("mean_of_means", sd.get("per_channel_statistics.mean-of-means"))
+        if std is not None:
+            self.std_of_means = std.to(dev)
+            self.mean_of_means = (mean if mean is not None else torch.zeros_like(std)).to(dev)
+        self.w = w
+        return [], []
+
+    # ---------------------------------------------------------------------------------------------
+    def _resnet(self, x, c1, c2, causal, shortcut=None, norm3=None):
+        """ResnetBlock3D.forward (causal_video_autoencoder.py:1197-1258)"""
+        h = ops.conv3d(ops.pixelnorm_silu(x), c1[0], c1[1], causal=causal)
+        h = ops.pixelnorm_silu(h)
+        res = x
+        if shortcut is not None:
+            B, T, H, W, C = x.shape
+            xs = ops.norm_mod(x.view(-1, C), weight=norm3[0], bias=norm3[1], eps=1e-6, layer_norm=True)
+            res = ops.gemm(xs, shortcut[0], shortcut[1]).view(B, T, H, W, -1)
+        return ops.conv3d(h, c2[0], c2[1], causal=causal, residual=res)
+
+    def _decode(self, z: torch.Tensor, target_shape=None, timestep=None, per_channel_normalize: bool = False,
+                out_f32: bool = False) -> torch.Tensor:
+        """vae.py:343-355 + Decoder.forward (causal_video_autoencoder.py:735-802)."""
+        causal = self.decoder.causal
+        w = self.w
+        z = z.to(self.device)
+        if z.dtype not in (torch.float32, BF16):
+            z = z.float()
+        z = z.contiguous()
+        if per_channel_normalize:
+            x = ops.latent_to_ndhwc(z, self.std_of_means.float().contiguous(), self.mean_of_means.float().contiguous())
+        else:
+            x = ops.latent_to_ndhwc(z, None, None)
+        x = ops.conv3d(x, *w["conv_in"], causal=causal)
+        for kind, idx, cin, cout, n in self.plan:
+            p = f"decoder.up_blocks.{idx}."
+            if kind == "res_x":
+                for j in range(n):
+                    x = self._resnet(x, w[p + f"{j}.conv1"], w[p + f"{j}.conv2"], causal)
+            elif kind == "res_x_y":
+                x = self._resnet(x, w[p + "conv1"], w[p + "conv2"], causal, w[p + "shortcut"], w[p + "norm3"])
+            else:
+                x = ops.conv3d(x, *w[p + "conv"], causal=causal, store=ops.CONV_D2S)
+        x = ops.pixelnorm_silu(x)
+        return ops.conv3d(x, *w["conv_out"], causal=causal, store=ops.CONV_UNPATCH, out_f32=out_f32)
+
+    def decode(self, z: torch.Tensor, return_dict: bool = True, target_shape=None, timestep=None):
+        """vae.py:357-413 (tiling branches are low-VRAM workarounds and are not needed on 180 GB)."""
+        assert target_shape is not None, "target_shape must be provided for decoding"
+        dec = self._decode(z, target_shape=target_shape, timestep=timestep)
+        if not return_dict:
+            return (dec,)
+        return DecoderOutput(sample=dec)
+
+
+def un_normalize_latents(latents, vae, vae_per_channel_normalize=False):
+    """vae_encode.py:239-247 (kept for API parity; `vae_decode` below fuses it into the layout kernel)."""
+    if vae_per_channel_normalize:
+        return latents * vae.std_of_means.to(latents.dtype).view(1, -1, 1, 1, 1) + vae.mean_of_means.to(latents.dtype).view(1, -1, 1, 1, 1)
+    return latents / vae.config.scaling_factor
+
+
+def get_vae_size_scale_factor(vae) -> Tuple[int, int, int]:
+    """vae_encode.py:168-187"""
+    return (vae.temporal_downscale_factor, vae.spatial_downscale_factor, vae.spatial_downscale_factor)
+
+
+def vae_decode(latents: torch.Tensor, vae: CausalVideoAutoencoder, is_video: bool = True, split_size: int = 1,
+               vae_per_channel_normalize: bool = False, timestep=None) -> torch.Tensor:
+    """vae_encode.py:94-165: latents [B,128,F,H,W] -> frames [B,3,8(F-1)+1,32H,32W] (bf16)."""
+    if split_size != 1:
+        raise NotImplementedError("split_size > 1 is a memory workaround that is not needed here")
+    if not vae_per_channel_normalize and vae.config.scaling_factor != 1.0:
+        latents = latents / vae.config.scaling_factor
+    return vae._decode(latents.to(vae.dtype), per_channel_normalize=vae_per_channel_normalize)

@@ -1,0 +1,269 @@
+"""LTXVideoPipeline — B200-native drop-in for ltx_video/pipelines/pipeline_ltx_video.py:222-1707.
+
+Keeps the reference call signature (`__call__(height, width, num_frames, frame_rate, prompt_embeds=…,
+num_inference_steps, guidance_scale, stg_scale, rescaling_scale, skip_block_list, latents,
+conditioning_items, output_type, …)`) and semantics of the denoise loop (:1103-1256): timestep table,
+per-step guidance tables, cond batching [uncond, text, perturbed], per-token timesteps for conditioned
+tokens, cfg-star / STG / std-rescale guidance, rectified-flow Euler step with the conditioning mask, and
+the final VAE decode.  What differs is execution: latents live in fp32 on the device, each step is
+(optional CUDA-graph replay of) the transformer forward + one fused guidance/step kernel group, and
+nothing in the loop synchronises with the host.  Text encoding, prompt enhancement, media loading and the
+multi-scale wrapper are out of scope.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Callable, List, Optional, Tuple, Union
+
+import torch
+
+from .. import ops
+from .causal_video_autoencoder import CausalVideoAutoencoder, get_vae_size_scale_factor, vae_decode
+from .rf import RectifiedFlowScheduler
+from .skip_layer_strategy import SkipLayerStrategy
+from .symmetric_patchifier import SymmetricPatchifier, latent_to_pixel_coords_from_factors
+from .transformer3d import Transformer3DModel
+
+BF16 = torch.bfloat16
+
+
+@dataclass
+class ConditioningItem:
+    """pipeline_ltx_video.py:195-219.  `media_item` is pixels [b,3,f,h,w] in [-1,1] (needs the VAE encoder,
+    SURVEY §8f#3); `latents` (extension) carries already-encoded, normalised latents [b,128,f_l,h_l,w_l]."""
+    media_item: Optional[torch.Tensor] = None
+    media_frame_number: int = 0
+    conditioning_strength: float = 1.0
+    media_x: Optional[int] = None
+    media_y: Optional[int] = None
+    latents: Optional[torch.Tensor] = None
+
+
+def retrieve_timesteps(scheduler, num_inference_steps=None, device=None, timesteps=None, max_timestep=1.0,
+                       skip_initial_inference_steps=0, skip_final_inference_steps=0, **kwargs):
+    """pipeline_ltx_video.py:125-200"""
+    if timesteps is not None:
+        scheduler.set_timesteps(timesteps=timesteps, device=device, **kwargs)
+        timesteps = scheduler.timesteps
+        num_inference_steps = len(timesteps)
+    else:
+        scheduler.set_timesteps(num_inference_steps, device=device, **kwargs)
+        timesteps = scheduler.timesteps
+    if (skip_initial_inference_steps < 0 or skip_final_inference_steps < 0
+            or skip_initial_inference_steps + skip_final_inference_steps >= num_inference_steps):
+        raise ValueError("invalid skip inference step values: must be non-negative and the sum of "
+                         "skip_initial_inference_steps and skip_final_inference_steps must be less than the number of inference steps")
+    timesteps = timesteps[skip_initial_inference_steps: len(timesteps) - skip_final_inference_steps]
+    if max_timestep < 1.0:
+        if max_timestep < timesteps.min():
+            raise ValueError(f"max_timestep {max_timestep} is smaller than the minimum timestep {timesteps.min()}")
+        timesteps = timesteps[timesteps <= max_timestep]
+    num_inference_steps = len(timesteps)
+    scheduler.set_timesteps(timesteps=timesteps, device=device, **kwargs)
+    return timesteps, num_inference_steps
+
+
+class LTXVideoPipeline:
+    def __init__(self, tokenizer=None, text_encoder=None, vae: CausalVideoAutoencoder = None,
+                 transformer: Transformer3DModel = None, scheduler: RectifiedFlowScheduler = None,
+                 patchifier: SymmetricPatchifier = None, prompt_enhancer_image_caption_model=None,
+                 prompt_enhancer_image_caption_processor=None, prompt_enhancer_llm_model=None,
+                 prompt_enhancer_llm_tokenizer=None, allowed_inference_steps: Optional[List[float]] = None):
+        self.tokenizer, self.text_encoder = tokenizer, text_encoder
+        self.vae, self.transformer, self.scheduler = vae, transformer, scheduler
+        self.patchifier = patchifier or SymmetricPatchifier(1)
+        self.video_scale_factor, self.vae_scale_factor, _ = get_vae_size_scale_factor(vae) if vae is not None else (8, 32, 32)
+        self.allowed_inference_steps = allowed_inference_steps
+        self.use_cuda_graph = False
+        self._graphs = {}
+
+    @property
+    def _execution_device(self):
+        return self.transformer.device
+
+    # ---------------------------------------------------------------------------------------------
+    def prepare_latents(self, latents, media_items, timestep, latent_shape, dtype, device, generator):
+        """pipeline_ltx_video.py:632-710: noise drawn in the patchified shape (b, f*h*w, c) on the generator's device."""
+        if media_items is not None:
+            raise NotImplementedError("media_items need the VAE encoder (SURVEY §8f#3)")
+        assert latents is None or timestep < 1.0, "Input latents are provided, but they will be replaced with noise."
+        b, c, f, h, w = latent_shape
+        gdev = generator.device if isinstance(generator, torch.Generator) else device
+        noise = torch.randn((b, f * h * w, c), generator=generator, device=gdev, dtype=dtype).to(device)
+        noise = noise.reshape(b, f, h, w, c).permute(0, 4, 1, 2, 3) * self.scheduler.init_noise_sigma
+        if latents is None:
+            return noise
+        assert tuple(latents.shape) == tuple(latent_shape)
+        return timestep * noise + (1 - timestep) * latents.to(device=device, dtype=dtype)
+
+    def prepare_conditioning(self, conditioning_items, init_latents, num_frames, height, width):
+        """pipeline_ltx_video.py:1344-1548, first-frame (media_frame_number == 0) conditioning with pre-encoded
+        latents; returns (patchified latents, pixel coords, conditioning mask | None, num extra tokens)."""
+        cmask = None
+        if conditioning_items:
+            cmask = torch.zeros(init_latents[:, 0].shape, dtype=torch.float32, device=init_latents.device)
+            for item in conditioning_items:
+                if item.latents is None:
+                    raise NotImplementedError("pixel-space conditioning needs the VAE encoder (SURVEY §8f#3); pass ConditioningItem(latents=…)")
+                if item.media_frame_number != 0:
+                    raise NotImplementedError("only media_frame_number == 0 conditioning is implemented")
+                lat = item.latents.to(device=init_latents.device, dtype=init_latents.dtype)
+                _, _, f_l, h_l, w_l = lat.shape
+                s = item.conditioning_strength
+                init_latents[:, :, :f_l, :h_l, :w_l] = torch.lerp(init_latents[:, :, :f_l, :h_l, :w_l], lat, s)   # :1436-1445
+                cmask[:, :f_l, :h_l, :w_l] = s
+        tokens, coords = self.patchifier.patchify(init_latents)
+        px = latent_to_pixel_coords_from_factors(coords, get_vae_size_scale_factor(self.vae),
+                                                 self.transformer.config.causal_temporal_positioning)
+        if cmask is None:
+            return tokens, px, None, 0
+        cm, _ = self.patchifier.patchify(cmask.unsqueeze(1))
+        return tokens, px, cm.squeeze(-1), 0
+
+    # ---------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def __call__(self, height: int, width: int, num_frames: int, frame_rate: float, prompt=None, negative_prompt=None,
+                 num_inference_steps: int = 20, timesteps: List[int] = None,
+                 guidance_scale: Union[float, List[float]] = 4.5, skip_layer_strategy: Optional[SkipLayerStrategy] = None,
+                 skip_block_list=None, stg_scale: Union[float, List[float]] = 1.0,
+                 rescaling_scale: Union[float, List[float]] = 0.7, guidance_timesteps: Optional[List[int]] = None,
+                 num_images_per_prompt: Optional[int] = 1, eta: float = 0.0, generator=None,
+                 latents: Optional[torch.Tensor] = None, prompt_embeds: Optional[torch.Tensor] = None,
+                 prompt_attention_mask: Optional[torch.Tensor] = None, negative_prompt_embeds: Optional[torch.Tensor] = None,
+                 negative_prompt_attention_mask: Optional[torch.Tensor] = None, output_type: Optional[str] = "pil",
+                 return_dict: bool = True, callback_on_step_end: Optional[Callable] = None,
+                 conditioning_items: Optional[List[ConditioningItem]] = None, decode_timestep=0.0,
+                 decode_noise_scale=None, mixed_precision: bool = False, offload_to_cpu: bool = False,
+                 enhance_prompt: bool = False, text_encoder_max_tokens: int = 256, stochastic_sampling: bool = False,
+                 media_items: Optional[torch.Tensor] = None, strength: Optional[float] = 1.0,
+                 skip_initial_inference_steps: int = 0, skip_final_inference_steps: int = 0, joint_pass: bool = False,
+                 pass_no: int = -1, ltxv_model=None, callback=None, **kwargs):
+        if prompt is not None or prompt_embeds is None:
+            raise NotImplementedError("text encoding is out of scope: pass prompt_embeds / prompt_attention_mask")
+        if mixed_precision or stochastic_sampling:
+            raise NotImplementedError("mixed_precision / stochastic_sampling are not implemented")
+        is_video = kwargs.get("is_video", False)
+        vae_per_channel_normalize = kwargs.get("vae_per_channel_normalize", True)
+        image_cond_noise_scale = kwargs.get("image_cond_noise_scale", 0.0)
+        per_step = kwargs.get("_per_step_latents", None)          # test hook: list that receives each step's latents
+        device = self._execution_device
+        tr = self.transformer
+        batch_size = prompt_embeds.shape[0]
+        if batch_size * num_images_per_prompt != 1:
+            raise NotImplementedError("the fused guidance/step kernel handles one video per call (replicas give batch)")
+
+        video_scale = self.video_scale_factor if is_video else 1
+        latent_height, latent_width = height // self.vae_scale_factor, width // self.vae_scale_factor
+        latent_num_frames = num_frames // video_scale
+        if is_video:
+            latent_num_frames += 1
+        latent_shape = (batch_size * num_images_per_prompt, tr.config.in_channels, latent_num_frames, latent_height, latent_width)
+
+        ts, num_inference_steps = retrieve_timesteps(self.scheduler, num_inference_steps, None, timesteps, max_timestep=strength,
+                                                     skip_initial_inference_steps=skip_initial_inference_steps,
+                                                     skip_final_inference_steps=skip_final_inference_steps,
+                                                     samples_shape=latent_shape)
+        ts_host = [float(x) for x in ts]
+        ts_dev = ts.to(device=device, dtype=torch.float32).contiguous()
+        n_steps = len(ts_host)
+        if self.allowed_inference_steps is not None:
+            for t_ in [round(x, 4) for x in ts_host]:
+                assert t_ in self.allowed_inference_steps, f"Invalid inference timestep {t_}."
+
+        # ---- per-step guidance tables (:958-1017)
+        if guidance_timesteps:
+            mapping = []
+            for t_ in ts_host:
+                idx = [i for i, val in enumerate(guidance_timesteps) if val <= t_]
+                mapping.append(idx[0] if len(idx) > 0 else (len(guidance_timesteps) - 1))
+        per = lambda v: [v] * n_steps if not isinstance(v, list) else [v[mapping[i]] for i in range(n_steps)]
+        guidance_scale = [x if x > 1.0 else 0.0 for x in per(guidance_scale)]
+        stg_scale, rescaling_scale = per(stg_scale), per(rescaling_scale)
+        do_cfg = any(x > 1.0 for x in guidance_scale)
+        do_stg = any(x > 0.0 for x in stg_scale)
+        do_rescaling = any(x != 1.0 for x in rescaling_scale)
+        num_conds = 1 + int(do_cfg) + int(do_stg)
+        if skip_block_list is not None:
+            if len(skip_block_list) == 0 or not isinstance(skip_block_list[0], list):
+                skip_block_list = [skip_block_list] * n_steps
+            else:
+                skip_block_list = [skip_block_list[mapping[i]] for i in range(n_steps)]
+        skip_layer_masks = None
+        if do_stg and skip_block_list is not None:
+            skip_layer_masks = [tr.create_skip_layer_mask(batch_size, num_conds, num_conds - 1, sb) for sb in skip_block_list]
+
+        # ---- cond batch [uncond, text, perturbed] (:1034-1051)
+        pe = prompt_embeds.to(device=device, dtype=BF16)
+        pm = prompt_attention_mask.to(device)
+        enc_b, mask_b = pe, pm
+        if do_cfg:
+            enc_b = torch.cat([negative_prompt_embeds.to(device=device, dtype=BF16), pe], dim=0)
+            mask_b = torch.cat([negative_prompt_attention_mask.to(device), pm], dim=0)
+        if do_stg:
+            enc_b = torch.cat([enc_b, pe], dim=0)
+            mask_b = torch.cat([mask_b, pm], dim=0)
+        enc_b, mask_b = enc_b.contiguous(), mask_b.contiguous()
+
+        # ---- latents (:1056-1088); drawn in bf16 like the reference (dtype = prompt_embeds dtype), kept fp32
+        init = self.prepare_latents(latents, media_items, ts_host[0], latent_shape, BF16, device, generator)
+        tokens, pixel_coords, conditioning_mask, num_cond_latents = self.prepare_conditioning(
+            conditioning_items, init.clone(), num_frames, height, width)
+        init_tokens = tokens.clone()
+        frac = pixel_coords.to(torch.float32)
+        frac[:, 0] = frac[:, 0] * (1.0 / frame_rate)
+        freqs_cis = tr.precompute_freqs_cis(frac[:1])
+        N, C = tokens.shape[1], tokens.shape[2]
+        lat32 = tokens.to(torch.float32).contiguous().view(-1)            # [N*C] fp32 master copy
+        lat16 = tokens.to(BF16).contiguous().view(-1)                      # bf16 model input
+        cmask_dev = None if conditioning_mask is None else conditioning_mask.to(device=device, dtype=torch.float32).contiguous().view(-1)
+        scratch = torch.empty(8 * 148, device=device, dtype=torch.float32)
+        x_in = torch.empty(num_conds, N, C, device=device, dtype=BF16)
+        t_in = torch.empty(num_conds, N if cmask_dev is not None else 1, device=device, dtype=torch.float32)
+
+        if callback is not None:
+            callback(-1, None, True, override_num_inference_steps=num_inference_steps, pass_no=pass_no)
+
+        for i, t in enumerate(ts_host):
+            if cmask_dev is not None and image_cond_noise_scale > 0.0:
+                # :606-629 add timestep-dependent noise to hard-conditioned tokens (host-side glue, i2v only)
+                noise = torch.randn(tokens.shape, generator=generator,
+                                    device=generator.device if isinstance(generator, torch.Generator) else device,
+                                    dtype=BF16).to(device)
+                need = (cmask_dev.view(1, N) > 1.0 - 1e-6).unsqueeze(-1)
+                noised = init_tokens.float() + image_cond_noise_scale * noise.float() * (t ** 2)
+                lat32 = torch.where(need, noised, lat32.view(1, N, C)).contiguous().view(-1)
+                lat16 = lat32.to(BF16)
+            x_in.copy_(lat16.view(1, N, C).expand(num_conds, N, C))
+            if cmask_dev is None:
+                t_in.fill_(t)
+            else:
+                t_in.copy_(torch.clamp(1.0 - cmask_dev, max=t).view(1, N).expand(num_conds, N))   # min(t, 1-mask) :1145-1150
+            noise_pred = tr(x_in, freqs_cis=freqs_cis, encoder_hidden_states=enc_b, encoder_attention_mask=mask_b,
+                            timestep=t_in, skip_layer_mask=skip_layer_masks[i] if skip_layer_masks is not None else None,
+                            skip_layer_strategy=skip_layer_strategy, latent_shape=latent_shape[2:], joint_pass=joint_pass,
+                            ltxv_model=ltxv_model, return_dict=False)[0]
+            if noise_pred is None:
+                return None
+            ops.guidance_step(noise_pred.view(num_conds, N * C), lat32, ts_dev, t, num_conds=num_conds, has_cfg=do_cfg,
+                              has_stg=do_stg, do_rescale=do_rescaling, guidance_scale=guidance_scale[i],
+                              stg_scale=stg_scale[i], rescale=rescaling_scale[i], channels=C, cond_mask=cmask_dev,
+                              scratch=scratch, latents_bf16=lat16)
+            if per_step is not None:
+                per_step.append(lat32.view(1, N, C).clone())
+            if callback is not None:
+                prev = lat32.view(N, C).transpose(0, 1).reshape(C, latent_num_frames, latent_height, latent_width)
+                callback(i, prev, False, pass_no=pass_no)
+            if callback_on_step_end is not None:
+                callback_on_step_end(self, i, t, {})
+
+        lat = lat32.view(1, N, C)[:, num_cond_latents:]
+        lat = self.patchifier.unpatchify(lat, latent_height, latent_width, tr.in_channels // math.prod(self.patchifier.patch_size))
+        if output_type != "latent":
+            image = vae_decode(lat.contiguous(), self.vae, is_video, vae_per_channel_normalize=vae_per_channel_normalize)
+            image = (image.float() / 2 + 0.5).clamp(0, 1)          # VaeImageProcessor.postprocess (:1298)
+        else:
+            image = lat
+        if not return_dict:
+            return (image,)
+        return image

@@ -177,7 +177,7 @@ def cast_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tens
 
 def guidance_step(pred: torch.Tensor, latents: torch.Tensor, timesteps: torch.Tensor, t: float, *, num_conds: int,
                   has_cfg: bool, has_stg: bool, do_rescale: bool, guidance_scale: float, stg_scale: float,
-                  rescale: float, channels: int, cond_mask: Optional[torch.Tensor], scratch: torch.Tensor,
+                  rescale: float, channels: int, cond_mask: Optional[torch.Tensor], scratch: Optional[torch.Tensor],
                   latents_bf16: Optional[torch.Tensor] = None):
     """pred [num_conds, n] bf16 (batch 1), latents [n] fp32 in place."""
     _req(pred, name="pred"); _req(latents, torch.float32, "latents"); _req(timesteps, torch.float32, "timesteps")
@@ -187,7 +187,7 @@ def guidance_step(pred: torch.Tensor, latents: torch.Tensor, timesteps: torch.Te
     rc = _lib.lib().ltxb200_guidance_step(pred.data_ptr(), n, n, channels, int(has_cfg), int(has_stg), int(do_rescale),
                                           float(guidance_scale), float(stg_scale), float(rescale), latents.data_ptr(),
                                           _p(latents_bf16), timesteps.data_ptr(), timesteps.numel(), float(t),
-                                          _p(cond_mask), scratch.data_ptr(), _stream())
+                                          _p(cond_mask), _p(scratch), _stream())
     _lib.check(rc, "guidance_step")
 
 

@@ -1,0 +1,158 @@
+"""GPU parity of the LTX drop-ins (Transformer3DModel.forward, LTXVideoPipeline.__call__,
+CausalVideoAutoencoder decode) against (a) the fixtures recorded from the unmodified reference and
+(b) the oracle run live on the same seeded inputs.  Tolerances from BASELINE.json north_star: per-step
+latents <= 2e-2 relative L2 in bf16, decoded frames PSNR >= 40 dB, index work bit-exact."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+if not torch.cuda.is_available():
+    pytest.skip("needs a GPU", allow_module_level=True)
+
+from ltx_video_gpupoor_b200.ltx.causal_video_autoencoder import CausalVideoAutoencoder, vae_decode  # noqa: E402
+from ltx_video_gpupoor_b200.ltx.pipeline_ltx_video import ConditioningItem, LTXVideoPipeline  # noqa: E402
+from ltx_video_gpupoor_b200.ltx.rf import RectifiedFlowScheduler  # noqa: E402
+from ltx_video_gpupoor_b200.ltx.skip_layer_strategy import SkipLayerStrategy  # noqa: E402
+from ltx_video_gpupoor_b200.ltx.symmetric_patchifier import SymmetricPatchifier  # noqa: E402
+from ltx_video_gpupoor_b200.ltx.transformer3d import Transformer3DModel  # noqa: E402
+from oracle import ltx_oracle as O  # noqa: E402
+
+DEV = "cuda"
+# bf16 weights + bf16 activations vs the fp32 reference: the reference's own bf16-vs-fp32 noise floor on the
+# raw model output is 1.5e-2; the 2e-2 contract is on LATENTS.
+TOL_MODEL_OUT = 3e-2
+TOL_LATENTS = 2e-2
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name), weights_only=False)
+
+
+def _model(num_layers, seed=0):
+    sd = O.make_transformer_state_dict(O.LTX_2B, seed=seed, num_layers=num_layers)
+    m = Transformer3DModel(num_layers=num_layers)
+    m.load_state_dict(sd)
+    return m, sd
+
+
+def test_rope_table_and_coords_bit_exact():
+    m, _ = _model(1)
+    p = SymmetricPatchifier(1)
+    x = torch.randn(1, 128, 3, 4, 6, device=DEV)
+    tok, coords = p.patchify(x)
+    assert torch.equal(coords.cpu(), O.latent_coords(3, 4, 6, 1))
+    assert torch.equal(tok.cpu(), O.patchify(x.cpu()))
+    assert torch.equal(p.unpatchify(tok, 4, 6, 128), x)
+    px = O.latent_to_pixel_coords(coords.cpu()).float()
+    px[:, 0] /= 25.0
+    cos, sin = m.precompute_freqs_cis(px)             # same device as the oracle (cpu) -> bit-exact
+    c2, s2 = O.precompute_freqs_cis(px, 2048, 10000.0, (20, 2048, 2048), torch.bfloat16)
+    assert torch.equal(cos, c2) and torch.equal(sin, s2)
+
+
+def test_transformer_vs_reference_fixture(golden_dir):
+    g = _load(golden_dir, "ltx_transformer.pt")
+    meta = g["meta"]
+    m, sd = _model(meta["num_layers"], meta["seed_weights"])
+    f, h, w = meta["f"], meta["h"], meta["w"]
+    coords = O.latent_to_pixel_coords(O.latent_coords(f, h, w, 1)).float()
+    coords[:, 0] *= 1.0 / 25.0
+    fc = m.precompute_freqs_cis(coords.to(DEV))
+    for tag, strat in (("t2v", None), ("stg", SkipLayerStrategy.AttentionValues)):
+        c = g[tag]
+        skip = None if c["skip"] is None else m.create_skip_layer_mask(1, 3, 2, [1])
+        if skip is not None:
+            assert torch.equal(skip.float().cpu(), c["skip"].float())
+        y = m(c["hidden"].to(DEV), freqs_cis=fc, encoder_hidden_states=c["enc"].to(DEV), timestep=c["timestep"].to(DEV),
+              encoder_attention_mask=c["mask"].to(DEV), skip_layer_mask=skip, skip_layer_strategy=strat,
+              latent_shape=(f, h, w), return_dict=False)[0]
+        torch.cuda.synchronize()
+        err = O.rel_l2(y.float().cpu(), c["out"])
+        print(f"transformer[{tag}] rel_l2 vs reference fp32 = {err:.3e}")
+        assert err < TOL_MODEL_OUT
+
+
+def _pipe(num_layers):
+    m, sd = _model(num_layers)
+    vsd = O.make_vae_decoder_state_dict(seed=1)
+    vae = CausalVideoAutoencoder()
+    vae.load_state_dict(vsd)
+    pipe = LTXVideoPipeline(vae=vae, transformer=m, scheduler=RectifiedFlowScheduler(), patchifier=SymmetricPatchifier(1))
+    return pipe, sd, vsd
+
+
+def test_pipeline_latents_vs_reference_fixture(golden_dir):
+    g = _load(golden_dir, "ltx_pipeline.pt")
+    meta = g["meta"]
+    pipe, sd, _ = _pipe(meta["num_layers"])
+    for tag in ("plain", "cfg_stg"):
+        kw = dict(g[tag]["kw"])
+        if "skip_layer_strategy" in kw:
+            kw["skip_layer_strategy"] = SkipLayerStrategy[kw["skip_layer_strategy"]]
+        per_step = []
+        lat = pipe(height=meta["H"], width=meta["W"], num_frames=meta["F"], frame_rate=meta["fps"],
+                   prompt_embeds=g["pe"], prompt_attention_mask=g["pm"], negative_prompt_embeds=g["ne"],
+                   negative_prompt_attention_mask=g["nm"], num_inference_steps=meta["steps"],
+                   generator=torch.Generator().manual_seed(g["noise_seed"]), output_type="latent", return_dict=False,
+                   is_video=True, vae_per_channel_normalize=True, _per_step_latents=per_step, **kw)[0]
+        torch.cuda.synchronize()
+        # the fixture's run drew fp32 noise; ours draws bf16 noise like the reference does in bf16. Compare against
+        # the oracle on OUR initial noise, step by step, and against the fixture loosely.
+        noise = torch.randn(1, 72, 128, generator=torch.Generator().manual_seed(g["noise_seed"]), dtype=torch.bfloat16).float()
+        ref_steps = []
+        O.denoise_loop(sd, O.LTX_2B, noise, g["pe"], g["pm"], num_frames_lat=3, lat_h=4, lat_w=6, frame_rate=meta["fps"],
+                       num_steps=meta["steps"], neg_enc=g["ne"], neg_mask=g["nm"], guidance_scale=kw["guidance_scale"],
+                       stg_scale=kw["stg_scale"], rescaling_scale=kw["rescaling_scale"],
+                       skip_block_list=kw.get("skip_block_list"),
+                       strategy=O.SKIP_ATTENTION_VALUES if "skip_block_list" in kw else None, per_step=ref_steps)
+        for i, (a, b) in enumerate(zip(per_step, ref_steps)):
+            err = O.rel_l2(a.cpu(), b)
+            print(f"pipeline[{tag}] step {i}: latents rel_l2 vs oracle = {err:.3e}")
+            assert err < TOL_LATENTS
+        err = O.rel_l2(lat.float().cpu(), g[tag]["latents"])
+        print(f"pipeline[{tag}] final latents rel_l2 vs reference fixture (fp32 noise) = {err:.3e}")
+        assert err < 3e-2
+
+
+def test_pipeline_i2v_conditioning_vs_oracle():
+    pipe, sd, _ = _pipe(2)
+    g = torch.Generator().manual_seed(3)
+    pe = torch.randn(1, 16, 4096, generator=g)
+    pm = torch.ones(1, 16)
+    cond_lat = torch.randn(1, 128, 1, 4, 6, generator=g)
+    per_step = []
+    pipe(height=128, width=192, num_frames=17, frame_rate=25.0, prompt_embeds=pe, prompt_attention_mask=pm,
+         num_inference_steps=3, guidance_scale=1.0, stg_scale=0.0, rescaling_scale=1.0,
+         generator=torch.Generator().manual_seed(5), output_type="latent", return_dict=False, is_video=True,
+         conditioning_items=[ConditioningItem(latents=cond_lat, media_frame_number=0, conditioning_strength=1.0)],
+         _per_step_latents=per_step)
+    noise = torch.randn(1, 72, 128, generator=torch.Generator().manual_seed(5), dtype=torch.bfloat16).float()
+    init = O.unpatchify(noise, 3, 4, 6).clone()
+    init[:, :, :1] = cond_lat.bfloat16().float()
+    cmask = torch.zeros(1, 3, 4, 6); cmask[:, :1] = 1.0
+    ref_steps = []
+    O.denoise_loop(sd, O.LTX_2B, O.patchify(init), pe, pm, num_frames_lat=3, lat_h=4, lat_w=6, frame_rate=25.0,
+                   num_steps=3, conditioning_mask=cmask.reshape(1, -1), per_step=ref_steps)
+    for i, (a, b) in enumerate(zip(per_step, ref_steps)):
+        err = O.rel_l2(a.cpu(), b)
+        print(f"i2v step {i}: rel_l2 = {err:.3e}")
+        assert err < TOL_LATENTS
+    # hard-conditioned tokens are never touched
+    assert torch.equal(per_step[-1][:, :24].cpu(), O.patchify(init)[:, :24])
+
+
+def test_vae_decode_vs_reference_fixture(golden_dir):
+    g = _load(golden_dir, "ltx_vae_decode.pt")
+    vsd = O.make_vae_decoder_state_dict(seed=g["seed_weights"])
+    vae = CausalVideoAutoencoder()
+    vae.load_state_dict(vsd)
+    y = vae_decode(g["z"].to(DEV), vae, is_video=True, vae_per_channel_normalize=True)
+    torch.cuda.synchronize()
+    assert tuple(y.shape) == (1, 3, 9, 96, 128)
+    a = O.postprocess(y.float().cpu())
+    b = O.postprocess(g["out"].float())
+    ps = O.psnr(a, b)
+    print(f"vae decode PSNR vs reference = {ps:.1f} dB, rel_l2 = {O.rel_l2(y.float().cpu(), g['out'].float()):.3e}")
+    assert ps >= 40.0
