@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import math
 from dataclasses import dataclass
+from types import SimpleNamespace
 from typing import Callable, List, Optional, Tuple, Union
 
 import torch
@@ -121,6 +122,38 @@ class LTXVideoPipeline:
         cm, _ = self.patchifier.patchify(cmask.unsqueeze(1))
         return tokens, px, cm.squeeze(-1), 0
 
+    def denoise_step(self, st, i: int):
+        """One iteration of the loop at pipeline_ltx_video.py:1104-1256: cond batch, timestep tensor, transformer
+        forward, guidance, scheduler step.  No host synchronisation."""
+        t = st.ts_host[i]
+        N, C, num_conds, device = st.N, st.C, st.num_conds, self._execution_device
+        if st.cmask_dev is not None and st.image_cond_noise_scale > 0.0:
+            # :606-629 add timestep-dependent noise to hard-conditioned tokens (host-side glue, i2v only)
+            gen = st.generator
+            noise = torch.randn(st.tokens_shape, generator=gen,
+                                device=gen.device if isinstance(gen, torch.Generator) else device, dtype=BF16).to(device)
+            need = (st.cmask_dev.view(1, N) > 1.0 - 1e-6).unsqueeze(-1)
+            noised = st.init_tokens.float() + st.image_cond_noise_scale * noise.float() * (t ** 2)
+            st.lat32 = torch.where(need, noised, st.lat32.view(1, N, C)).contiguous().view(-1)
+            st.lat16 = st.lat32.to(BF16)
+        st.x_in.copy_(st.lat16.view(1, N, C).expand(num_conds, N, C))
+        if st.cmask_dev is None:
+            st.t_in.fill_(t)
+        else:
+            st.t_in.copy_(torch.clamp(1.0 - st.cmask_dev, max=t).view(1, N).expand(num_conds, N))   # min(t, 1-mask) :1145-1150
+        noise_pred = self.transformer(
+            st.x_in, freqs_cis=st.freqs_cis, encoder_hidden_states=st.enc_b, encoder_attention_mask=st.mask_b,
+            timestep=st.t_in, skip_layer_mask=st.skip_layer_masks[i] if st.skip_layer_masks is not None else None,
+            skip_layer_strategy=st.skip_layer_strategy, latent_shape=st.latent_shape[2:], joint_pass=st.joint_pass,
+            ltxv_model=st.ltxv_model, return_dict=False)[0]
+        if noise_pred is None:
+            return None
+        ops.guidance_step(noise_pred.view(num_conds, N * C), st.lat32, st.ts_dev, t, num_conds=num_conds,
+                          has_cfg=st.do_cfg, has_stg=st.do_stg, do_rescale=st.do_rescaling,
+                          guidance_scale=st.guidance_scale[i], stg_scale=st.stg_scale[i], rescale=st.rescaling_scale[i],
+                          channels=C, cond_mask=st.cmask_dev, scratch=st.scratch, latents_bf16=st.lat16)
+        return st
+
     # ---------------------------------------------------------------------------------------------
     @torch.no_grad()
     def __call__(self, height: int, width: int, num_frames: int, frame_rate: float, prompt=None, negative_prompt=None,
@@ -205,8 +238,9 @@ class LTXVideoPipeline:
             mask_b = torch.cat([mask_b, pm], dim=0)
         enc_b, mask_b = enc_b.contiguous(), mask_b.contiguous()
 
-        # ---- latents (:1056-1088); drawn in bf16 like the reference (dtype = prompt_embeds dtype), kept fp32
-        init = self.prepare_latents(latents, media_items, ts_host[0], latent_shape, BF16, device, generator)
+        # ---- latents (:1056-1088); drawn in prompt_embeds' dtype like the reference (:1061), kept as an fp32 master copy
+        noise_dtype = prompt_embeds.dtype if prompt_embeds.dtype in (torch.float32, BF16) else torch.float32
+        init = self.prepare_latents(latents, media_items, ts_host[0], latent_shape, noise_dtype, device, generator)
         tokens, pixel_coords, conditioning_mask, num_cond_latents = self.prepare_conditioning(
             conditioning_items, init.clone(), num_frames, height, width)
         init_tokens = tokens.clone()
@@ -224,38 +258,27 @@ class LTXVideoPipeline:
         if callback is not None:
             callback(-1, None, True, override_num_inference_steps=num_inference_steps, pass_no=pass_no)
 
-        for i, t in enumerate(ts_host):
-            if cmask_dev is not None and image_cond_noise_scale > 0.0:
-                # :606-629 add timestep-dependent noise to hard-conditioned tokens (host-side glue, i2v only)
-                noise = torch.randn(tokens.shape, generator=generator,
-                                    device=generator.device if isinstance(generator, torch.Generator) else device,
-                                    dtype=BF16).to(device)
-                need = (cmask_dev.view(1, N) > 1.0 - 1e-6).unsqueeze(-1)
-                noised = init_tokens.float() + image_cond_noise_scale * noise.float() * (t ** 2)
-                lat32 = torch.where(need, noised, lat32.view(1, N, C)).contiguous().view(-1)
-                lat16 = lat32.to(BF16)
-            x_in.copy_(lat16.view(1, N, C).expand(num_conds, N, C))
-            if cmask_dev is None:
-                t_in.fill_(t)
-            else:
-                t_in.copy_(torch.clamp(1.0 - cmask_dev, max=t).view(1, N).expand(num_conds, N))   # min(t, 1-mask) :1145-1150
-            noise_pred = tr(x_in, freqs_cis=freqs_cis, encoder_hidden_states=enc_b, encoder_attention_mask=mask_b,
-                            timestep=t_in, skip_layer_mask=skip_layer_masks[i] if skip_layer_masks is not None else None,
-                            skip_layer_strategy=skip_layer_strategy, latent_shape=latent_shape[2:], joint_pass=joint_pass,
-                            ltxv_model=ltxv_model, return_dict=False)[0]
-            if noise_pred is None:
+        st = SimpleNamespace(**dict(
+            ts_host=ts_host, ts_dev=ts_dev, num_conds=num_conds, do_cfg=do_cfg, do_stg=do_stg, do_rescaling=do_rescaling,
+            guidance_scale=guidance_scale, stg_scale=stg_scale, rescaling_scale=rescaling_scale,
+            skip_layer_masks=skip_layer_masks, skip_layer_strategy=skip_layer_strategy, enc_b=enc_b, mask_b=mask_b,
+            freqs_cis=freqs_cis, N=N, C=C, lat32=lat32, lat16=lat16, cmask_dev=cmask_dev, scratch=scratch, x_in=x_in,
+            t_in=t_in, latent_shape=latent_shape, joint_pass=joint_pass, ltxv_model=ltxv_model, generator=generator,
+            image_cond_noise_scale=image_cond_noise_scale, init_tokens=init_tokens, tokens_shape=tuple(tokens.shape)))
+        self._state = st
+        if kwargs.get("_prepare_only", False):
+            return st
+        for i in range(n_steps):
+            if self.denoise_step(st, i) is None:
                 return None
-            ops.guidance_step(noise_pred.view(num_conds, N * C), lat32, ts_dev, t, num_conds=num_conds, has_cfg=do_cfg,
-                              has_stg=do_stg, do_rescale=do_rescaling, guidance_scale=guidance_scale[i],
-                              stg_scale=stg_scale[i], rescale=rescaling_scale[i], channels=C, cond_mask=cmask_dev,
-                              scratch=scratch, latents_bf16=lat16)
             if per_step is not None:
-                per_step.append(lat32.view(1, N, C).clone())
+                per_step.append(st.lat32.view(1, N, C).clone())
             if callback is not None:
-                prev = lat32.view(N, C).transpose(0, 1).reshape(C, latent_num_frames, latent_height, latent_width)
+                prev = st.lat32.view(N, C).transpose(0, 1).reshape(C, latent_num_frames, latent_height, latent_width)
                 callback(i, prev, False, pass_no=pass_no)
             if callback_on_step_end is not None:
-                callback_on_step_end(self, i, t, {})
+                callback_on_step_end(self, i, ts_host[i], {})
+        lat32 = st.lat32
 
         lat = lat32.view(1, N, C)[:, num_cond_latents:]
         lat = self.patchifier.unpatchify(lat, latent_height, latent_width, tr.in_channels // math.prod(self.patchifier.patch_size))

@@ -68,6 +68,7 @@ class Transformer3DModel:
         self.device = torch.device("cuda")
         self.w: Dict[str, torch.Tensor] = {}
         self.layers: List[Dict[str, torch.Tensor]] = []
+        self._skip_host: Dict[int, torch.Tensor] = {}
 
     @classmethod
     def from_config(cls, config: dict):
@@ -135,8 +136,11 @@ class Transformer3DModel:
         if skip_block_list is None or len(skip_block_list) == 0:
             return None
         mask = torch.ones((self.num_layers, batch_size * num_conds), device=self.device, dtype=self.dtype)
+        host = torch.ones((self.num_layers, batch_size * num_conds), dtype=torch.float32)
         for block_idx in skip_block_list:
             mask[block_idx, ptb_index::num_conds] = 0
+            host[block_idx, ptb_index::num_conds] = 0
+        self._skip_host[mask.data_ptr()] = host        # lets forward() pick skipped layers without a device sync
         return mask
 
     def get_fractional_positions(self, indices_grid):
@@ -231,7 +235,9 @@ class Transformer3DModel:
 
         skip_host = None
         if skip_layer_mask is not None:
-            skip_host = skip_layer_mask.to(torch.float32).cpu()                     # one sync per forward, not per block
+            skip_host = self._skip_host.get(skip_layer_mask.data_ptr())
+            if skip_host is None:
+                skip_host = skip_layer_mask.to(torch.float32).cpu()                 # foreign mask: one sync per forward
             skip_dev = skip_layer_mask.to(device=dev, dtype=torch.float32).contiguous()
 
         for li, Lw in enumerate(self.layers):

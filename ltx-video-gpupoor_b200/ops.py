@@ -13,6 +13,32 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# Optional per-launch instrumentation (bench.py's roofline probe, never on during timed steps): when PROFILER is a
+# list, every wrapper appends (kernel_name, "flop"|"byte", algorithmic_amount, start_event, end_event), the events
+# recorded on the launching (current) stream around the single kernel launch.
+PROFILER = None
+
+
+class _Prof:
+    __slots__ = ("name", "kind", "amount", "e0")
+
+    def __init__(self, name, kind, amount):
+        self.name, self.kind, self.amount, self.e0 = name, kind, amount, None
+
+    def __enter__(self):
+        if PROFILER is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.e0 is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            PROFILER.append((self.name, self.kind, float(self.amount), self.e0, e1))
+        return False
+
+
 def _p(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
@@ -47,7 +73,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
         _req(residual, name="residual"); assert residual.shape == (M, N)
     if gate is not None:
         _req(gate, name="gate"); assert gate.dim() == 2 and gate.shape[1] == N
-    rc = _lib.lib().ltxb200_gemm_bf16(
+    with _Prof('gemm_bf16', 'flop', 2.0 * M * N * K):
+        rc = _lib.lib().ltxb200_gemm_bf16(
         a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, N, K, out.data_ptr(), out.stride(0),
         1 if out_f32 else 0, _p(bias), act, _p(residual), residual.stride(0) if residual is not None else 0,
         _p(gate), gate.stride(0) if gate is not None else 0, rows_per_gate, _stream())
@@ -74,7 +101,8 @@ def conv3d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], causa
         out = torch.empty(B, Cout // 16, T, 4 * H, 4 * W, device=x.device, dtype=torch.float32 if out_f32 else BF16)
     if residual is not None:
         _req(residual, name="residual"); assert residual.is_contiguous() and residual.shape == out.shape
-    rc = _lib.lib().ltxb200_conv3d_bf16(x.data_ptr(), w.data_ptr(), _p(bias), out.data_ptr(), B, T, H, W, Cin, Cout,
+    with _Prof('conv3d_bf16', 'flop', 2.0 * B * T * H * W * Cout * 27 * Cin):
+        rc = _lib.lib().ltxb200_conv3d_bf16(x.data_ptr(), w.data_ptr(), _p(bias), out.data_ptr(), B, T, H, W, Cin, Cout,
                                         1 if causal else 0, store, 1 if out_f32 else 0, _p(residual), _stream())
     _lib.check(rc, "conv3d_bf16")
     return out
@@ -93,7 +121,8 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_bias: Optio
     _req(out, name="out")
     if key_bias is not None:
         _req(key_bias, torch.float32, "key_bias"); assert key_bias.shape == (B, Lk) and key_bias.is_contiguous()
-    rc = _lib.lib().ltxb200_attention_bf16(
+    with _Prof('attention_bf16', 'flop', 4.0 * B * H * Lq * Lk * d):
+        rc = _lib.lib().ltxb200_attention_bf16(
         q.data_ptr(), q.stride(1), q.stride(0), k.data_ptr(), k.stride(1), k.stride(0),
         v.data_ptr(), v.stride(1), v.stride(0), out.data_ptr(), out.stride(1), out.stride(0),
         B, H, Lq, Lk, d, float(scale), _p(key_bias), _stream())
@@ -114,7 +143,8 @@ def norm_mod(x: torch.Tensor, scale: Optional[torch.Tensor] = None, shift: Optio
         _req(scale, name="scale"); _req(shift, name="shift")
         assert scale.dim() == 2 and shift.dim() == 2 and scale.stride(0) == shift.stride(0)
         mod_ld = scale.stride(0)
-    rc = _lib.lib().ltxb200_norm_mod_bf16(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), M, D, _p(scale),
+    with _Prof('norm_mod_bf16', 'byte', 4.0 * M * D):
+        rc = _lib.lib().ltxb200_norm_mod_bf16(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), M, D, _p(scale),
                                           _p(shift), mod_ld, rows_per_group, _p(weight), _p(bias), float(eps),
                                           1 if layer_norm else 0, _stream())
     _lib.check(rc, "norm_mod_bf16")
@@ -125,7 +155,8 @@ def qk_norm_rope(q: Optional[torch.Tensor], k: Optional[torch.Tensor], wq, wk, c
                  tokens_per_batch: int = 0, eps: float = 1e-5):
     """In-place on 2-D row views q [Mq,D], k [Mk,D]."""
     D = (q if q is not None else k).shape[1]
-    rc = _lib.lib().ltxb200_qk_norm_rope_bf16(
+    with _Prof('qk_norm_rope_bf16', 'byte', (4.0 if cos is None else 8.0) * D * ((q.shape[0] if q is not None else 0) + (k.shape[0] if k is not None else 0))):
+        rc = _lib.lib().ltxb200_qk_norm_rope_bf16(
         _p(q), q.stride(0) if q is not None else 0, q.shape[0] if q is not None else 0,
         _p(k), k.stride(0) if k is not None else 0, k.shape[0] if k is not None else 0, D,
         _p(wq), _p(wk), _p(cos), _p(sin), tokens_per_batch, float(eps), _stream())
@@ -184,7 +215,8 @@ def guidance_step(pred: torch.Tensor, latents: torch.Tensor, timesteps: torch.Te
     assert pred.is_contiguous() and latents.is_contiguous()
     n = latents.numel()
     assert pred.numel() == num_conds * n
-    rc = _lib.lib().ltxb200_guidance_step(pred.data_ptr(), n, n, channels, int(has_cfg), int(has_stg), int(do_rescale),
+    with _Prof('guidance_step', 'byte', n * (2.0 * num_conds + 10.0)):
+        rc = _lib.lib().ltxb200_guidance_step(pred.data_ptr(), n, n, channels, int(has_cfg), int(has_stg), int(do_rescale),
                                           float(guidance_scale), float(stg_scale), float(rescale), latents.data_ptr(),
                                           _p(latents_bf16), timesteps.data_ptr(), timesteps.numel(), float(t),
                                           _p(cond_mask), _p(scratch), _stream())

@@ -98,9 +98,8 @@ def test_pipeline_latents_vs_reference_fixture(golden_dir):
                    generator=torch.Generator().manual_seed(g["noise_seed"]), output_type="latent", return_dict=False,
                    is_video=True, vae_per_channel_normalize=True, _per_step_latents=per_step, **kw)[0]
         torch.cuda.synchronize()
-        # the fixture's run drew fp32 noise; ours draws bf16 noise like the reference does in bf16. Compare against
-        # the oracle on OUR initial noise, step by step, and against the fixture loosely.
-        noise = torch.randn(1, 72, 128, generator=torch.Generator().manual_seed(g["noise_seed"]), dtype=torch.bfloat16).float()
+        # noise is drawn in prompt_embeds' dtype (fp32 here) exactly as the reference does -> same initial latents
+        noise = torch.randn(1, 72, 128, generator=torch.Generator().manual_seed(g["noise_seed"]))
         ref_steps = []
         O.denoise_loop(sd, O.LTX_2B, noise, g["pe"], g["pm"], num_frames_lat=3, lat_h=4, lat_w=6, frame_rate=meta["fps"],
                        num_steps=meta["steps"], neg_enc=g["ne"], neg_mask=g["nm"], guidance_scale=kw["guidance_scale"],
@@ -128,9 +127,9 @@ def test_pipeline_i2v_conditioning_vs_oracle():
          generator=torch.Generator().manual_seed(5), output_type="latent", return_dict=False, is_video=True,
          conditioning_items=[ConditioningItem(latents=cond_lat, media_frame_number=0, conditioning_strength=1.0)],
          _per_step_latents=per_step)
-    noise = torch.randn(1, 72, 128, generator=torch.Generator().manual_seed(5), dtype=torch.bfloat16).float()
+    noise = torch.randn(1, 72, 128, generator=torch.Generator().manual_seed(5))
     init = O.unpatchify(noise, 3, 4, 6).clone()
-    init[:, :, :1] = cond_lat.bfloat16().float()
+    init[:, :, :1] = cond_lat
     cmask = torch.zeros(1, 3, 4, 6); cmask[:, :1] = 1.0
     ref_steps = []
     O.denoise_loop(sd, O.LTX_2B, O.patchify(init), pe, pm, num_frames_lat=3, lat_h=4, lat_w=6, frame_rate=25.0,
