@@ -40,7 +40,7 @@ struct AttnSmem {
   static constexpr int kTotal = kQBytes + kStages * (kKBytes + kVBytes) + kBarBytes + 1024;
 };
 
-template <int D>
+template <int D, bool kMasked>
 __global__ void __launch_bounds__(kAttnThreads, 2)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -101,12 +101,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       int st = 0;
       uint32_t ph = 0;
       for (int j = 0; j < nblk; ++j) {
-        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_wait_backoff(&k_empty[st], ph ^ 1);
         mbar_arrive_expect_tx(&k_full[st], S::kKBytes);
 #pragma unroll
         for (int c = 0; c < kChunks; ++c)
           tma_load_4d(sK + st * S::kKBytes + c * (kAttnBN * 128), &tmK, &k_full[st], c * 64, h, j * kAttnBN, b);
-        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_wait_backoff(&v_empty[st], ph ^ 1);
         mbar_arrive_expect_tx(&v_full[st], S::kVBytes);
 #pragma unroll
         for (int c = 0; c < kChunks; ++c)
@@ -162,35 +162,60 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const uint32_t tO = tmem_base + kColO + lane_addr;
     const float* bias = p.key_bias ? p.key_bias + static_cast<long long>(b) * p.Lk : nullptr;
     const float kLog2e = 1.4426950408889634f;
+    const float sc = p.scale_log2;
     float m_ref = 0.f, l = 0.f;
 
     for (int j = 0; j < nblk; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       const int kbase = j * kAttnBN;
-      const bool tail = (kbase + kAttnBN > p.Lk) || (bias != nullptr);
-      // ---- pass 1: block row-max ----
-      float m_blk = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < kAttnBN; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(tS + c, v);
-        tmem_wait_ld();
-        if (!tail) {
+      // ---- pass 1: block row-max (TMEM loads software-pipelined: chunk c+1 is in flight while c is reduced) ----
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+      {
+        uint32_t va[32], vb[32];
+        tmem_ld32(tS, va);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) m_blk = fmaxf(m_blk, __uint_as_float(v[i]));
-        } else {
+        for (int c = 0; c < kAttnBN; c += 64) {
+          tmem_wait_ld();
+          tmem_ld32(tS + c + 32, vb);
+          if (kMasked) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int k = kbase + c + i;
-            float s = __uint_as_float(v[i]) * p.scale_log2;
-            if (bias && k < p.Lk) s += __ldg(bias + k) * kLog2e;
-            if (k >= p.Lk) s = -INFINITY;
-            m_blk = fmaxf(m_blk, s);
+            for (int i = 0; i < 32; ++i) {
+              const int k = kbase + c + i;
+              float s = __uint_as_float(va[i]) * sc;
+              if (bias && k < p.Lk) s += __ldg(bias + k) * kLog2e;
+              if (k >= p.Lk) s = -INFINITY;
+              mx0 = fmaxf(mx0, s);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              mx0 = fmaxf(mx0, fmaxf(__uint_as_float(va[i]), __uint_as_float(va[i + 1])));
+              mx1 = fmaxf(mx1, fmaxf(__uint_as_float(va[i + 2]), __uint_as_float(va[i + 3])));
+            }
+          }
+          tmem_wait_ld();
+          if (c + 64 < kAttnBN) tmem_ld32(tS + c + 64, va);
+          if (kMasked) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int k = kbase + c + 32 + i;
+              float s = __uint_as_float(vb[i]) * sc;
+              if (bias && k < p.Lk) s += __ldg(bias + k) * kLog2e;
+              if (k >= p.Lk) s = -INFINITY;
+              mx1 = fmaxf(mx1, s);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              mx0 = fmaxf(mx0, fmaxf(__uint_as_float(vb[i]), __uint_as_float(vb[i + 1])));
+              mx1 = fmaxf(mx1, fmaxf(__uint_as_float(vb[i + 2]), __uint_as_float(vb[i + 3])));
+            }
           }
         }
       }
-      if (!tail) m_blk *= p.scale_log2;          // scale > 0: max commutes with the scaling
+      float m_blk = fmaxf(mx0, mx1);
+      if (!kMasked) m_blk *= sc;                 // scale > 0: max commutes with the scaling
       // ---- lazy rescale of O and l ----
       bool need;
       if (j == 0) {
@@ -214,35 +239,46 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           tmem_st32(tO + c, o);
         }
       }
-      // ---- pass 2: P = exp2(s - m_ref) -> bf16 pairs into TMEM (aliases S), l += rowsum ----
-#pragma unroll 1
-      for (int c = 0; c < kAttnBN; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(tS + c, v);
-        tmem_wait_ld();
-        uint32_t pk[16];
+      // ---- pass 2: P = exp2(s*scale - m_ref) -> bf16 pairs into TMEM (aliases S), l += rowsum ----
+      {
+        float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+        uint32_t va[32], vb[32];
+        tmem_ld32(tS, va);
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float s0, s1;
-          if (!tail) {
-            s0 = fmaf(__uint_as_float(v[i]), p.scale_log2, -m_ref);
-            s1 = fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -m_ref);
-          } else {
-            const int k = kbase + c + i;
-            s0 = __uint_as_float(v[i]) * p.scale_log2;
-            s1 = __uint_as_float(v[i + 1]) * p.scale_log2;
-            if (bias) {
-              if (k < p.Lk) s0 += __ldg(bias + k) * kLog2e;
-              if (k + 1 < p.Lk) s1 += __ldg(bias + k + 1) * kLog2e;
+        for (int c = 0; c < kAttnBN; c += 64) {
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t (&v)[32] = half ? vb : va;
+            uint32_t (&nx)[32] = half ? va : vb;
+            const int cc = c + half * 32;
+            tmem_wait_ld();
+            if (cc + 32 < kAttnBN) tmem_ld32(tS + cc + 32, nx);
+            float e[32];
+            if (kMasked) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const int k = kbase + cc + i;
+                float s = __uint_as_float(v[i]) * sc;
+                if (bias && k < p.Lk) s += __ldg(bias + k) * kLog2e;
+                e[i] = (k < p.Lk) ? fast_exp2(s - m_ref) : 0.f;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) e[i] = fmaf(__uint_as_float(v[i]), sc, -m_ref);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) e[i] = fast_exp2(e[i]);
             }
-            s0 = (k < p.Lk) ? s0 - m_ref : -INFINITY;
-            s1 = (k + 1 < p.Lk) ? s1 - m_ref : -INFINITY;
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              l0 += e[i]; l1 += e[i + 1]; l2 += e[i + 2]; l3 += e[i + 3];
+              pk[i >> 1] = pack_bf16(e[i], e[i + 1]);
+              pk[(i >> 1) + 1] = pack_bf16(e[i + 2], e[i + 3]);
+            }
+            tmem_st16(tS + (cc >> 1), pk);
           }
-          const float p0 = fast_exp2(s0), p1 = fast_exp2(s1);
-          l += p0 + p1;
-          pk[i >> 1] = pack_bf16(p0, p1);
         }
-        tmem_st16(tS + (c >> 1), pk);
+        l += (l0 + l1) + (l2 + l3);
       }
       tmem_wait_st();
       tc_fence_before();

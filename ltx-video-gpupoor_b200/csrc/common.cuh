@@ -104,6 +104,10 @@ DEVI void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// for single-thread producers that wait long: sleep between probes so they do not eat issue slots
+DEVI void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(64);
+}
 
 // ------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor) loads: global -> shared, completion on an mbarrier

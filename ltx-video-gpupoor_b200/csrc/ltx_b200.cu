@@ -169,12 +169,12 @@ static int make_qkv_tmap(CUtensorMap* m, const void* base, int B, int H, int L, 
   return make_tmap_bf16(m, base, 4, dims, str, box);
 }
 
-template <int D>
+template <int D, bool kMasked>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                        cudaStream_t st) {
   using S = AttnSmem<D>;
   static bool configured = false;
-  auto kern = attention_fwd_kernel<D>;
+  auto kern = attention_fwd_kernel<D, kMasked>;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal) != cudaSuccess) return kErrCuda;
     configured = true;
@@ -204,7 +204,9 @@ extern "C" int ltxb200_attention_bf16(const void* q, int64_t ldq, int64_t bsq, c
   p.key_bias = key_bias;
   p.out = static_cast<__nv_bfloat16*>(out); p.out_ld = ldo; p.out_bs = bso;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return d == 64 ? launch_attn<64>(tq, tk, tv, p, st) : launch_attn<128>(tq, tk, tv, p, st);
+  const bool masked = (key_bias != nullptr) || (Lk % kAttnBN != 0);
+  if (d == 64) return masked ? launch_attn<64, true>(tq, tk, tv, p, st) : launch_attn<64, false>(tq, tk, tv, p, st);
+  return masked ? launch_attn<128, true>(tq, tk, tv, p, st) : launch_attn<128, false>(tq, tk, tv, p, st);
 }
 
 // ------------------------------------------------------------------------------------------

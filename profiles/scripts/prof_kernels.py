@@ -1,0 +1,45 @@
+"""Launch the hot kernels at LTX-2B bench shapes a few times (for ncu captures and quick timing)."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import torch
+from ltx_video_gpupoor_b200 import ops
+
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+dev = "cuda"
+torch.manual_seed(0)
+
+
+def timeit(name, fn, flops):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / reps
+    print(f"{name}: {ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s", flush=True)
+
+
+if which in ("all", "attn"):
+    B, N, H, d = 3, 6144, 32, 64
+    qkv = torch.randn(B, N, 3 * H * d, device=dev).bfloat16()
+    q, k, v = [qkv[:, :, i * H * d:(i + 1) * H * d].unflatten(-1, (H, d)) for i in range(3)]
+    timeit("attention d64 B3 N6144 H32", lambda: ops.attention(q, k, v), 4.0 * B * H * N * N * d)
+if which in ("all", "attn128"):
+    B, N, H, d = 1, 8192, 12, 128
+    q, k, v = [torch.randn(B, N, H, d, device=dev).bfloat16() for _ in range(3)]
+    timeit("attention d128 B1 N8192 H12", lambda: ops.attention(q, k, v), 4.0 * B * H * N * N * d)
+if which in ("all", "gemm"):
+    M, N, K = 18432, 8192, 2048
+    a = torch.randn(M, K, device=dev).bfloat16(); w = torch.randn(N, K, device=dev).bfloat16() * 0.02; bias = torch.randn(N, device=dev).bfloat16()
+    timeit("gemm ffn_up 18432x8192x2048 gelu", lambda: ops.gemm(a, w, bias, act=ops.ACT_GELU_TANH), 2.0 * M * N * K)
+    M, N, K = 18432, 2048, 8192
+    a2 = torch.randn(M, K, device=dev).bfloat16(); w2 = torch.randn(N, K, device=dev).bfloat16() * 0.02
+    timeit("gemm ffn_down 18432x2048x8192", lambda: ops.gemm(a2, w2, None), 2.0 * M * N * K)
+    M, N, K = 18432, 6144, 2048
+    w3 = torch.randn(N, K, device=dev).bfloat16() * 0.02
+    timeit("gemm qkv 18432x6144x2048", lambda: ops.gemm(a, w3, None), 2.0 * M * N * K)
