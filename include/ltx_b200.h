@@ -82,6 +82,19 @@ int ltxb200_qk_norm_rope_bf16(void* q, int64_t ldq, int Mq, void* k, int64_t ldk
                               const void* wq, const void* wk, const void* cos_table, const void* sin_table,
                               int tokens_per_batch, float eps, void* stream);
 
+/* Wan variant: in-place q/k WanRMSNorm (wan/modules/model.py:99-111, two bf16 roundings) + per-head 3-axis RoPE
+ * from fp32 [tokens, head_dim] tables, fp32 math (wan/modules/posemb_layers.py:222-276).
+ * token = token_offset + row % tokens_per_batch: token_offset is the rank's first global token under Ulysses
+ * sequence parallelism (wan/distributed/xdit_context_parallel.py:52-57). */
+int ltxb200_qk_norm_rope_wan_bf16(void* q, int64_t ldq, int Mq, void* k, int64_t ldk, int Mk, int D, const void* wq,
+                                  const void* wk, const float* cos_table, const float* sin_table, int head_dim,
+                                  int tokens_per_batch, int token_offset, float eps, void* stream);
+
+/* out = sum_j coefs[j] * xs[j] (fp32, terms <= 6, n % 4 == 0; xs and coefs are HOST arrays of device pointers /
+ * scalars).  The UniPC predictor/corrector, x0 conversion and the CFG combine are such combinations
+ * (wan/utils/fm_solvers_unipc.py:321,458-484,590-626; wan/text2video.py:562).  out may alias an input. */
+int ltxb200_lincomb_f32(float* out, int64_t n, int terms, const float* const* xs, const float* coefs, void* stream);
+
 /* ada[l,g,j,:] = table[l,j,:] + temb[g, j*D:(j+1)*D]  (attention.py:239-241), JD = 6*D. */
 int ltxb200_ada_add_bf16(const void* table, const void* temb, void* out, int L, int G, int JD, void* stream);
 
@@ -105,6 +118,12 @@ int ltxb200_guidance_step(const void* pred, int64_t cond_stride, int64_t n, int 
                           int has_stg, int do_rescale, float guidance_scale, float stg_scale, float rescale,
                           float* latents, void* latents_bf16, const float* timesteps, int num_steps, float t,
                           const float* cond_mask, float* scratch, void* stream);
+
+/* Wan classifier-free guidance in fp32, optionally with the CFG-Zero* projection of the unconditional branch
+ * (wan/text2video.py:31-42 optimized_scale, :551-562): out = a*u + g*(c - a*u), a = <c,u>/(|u|^2+1e-8) or 1.
+ * scratch: >= 2*148 floats (only read when use_alpha). */
+int ltxb200_cfg_combine_f32(const float* cond, const float* uncond, float* out, int64_t n, float guide_scale,
+                            int use_alpha, float* scratch, void* stream);
 
 /* PixelNorm over channels (+ optional SiLU) on NDHWC bf16 (pixel_norm.py:12; causal_video_autoencoder.py:1212,1240).
  * C in {64,128,256,512,1024}. */

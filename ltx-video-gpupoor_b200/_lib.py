@@ -28,12 +28,15 @@ def _declare(lib):
         "ltxb200_attention_bf16": ([P, L, L, P, L, L, P, L, L, P, L, L, I, I, I, I, I, F, P, P], I),
         "ltxb200_norm_mod_bf16": ([P, L, P, L, I, I, P, P, L, I, P, P, F, I, P], I),
         "ltxb200_qk_norm_rope_bf16": ([P, L, I, P, L, I, I, P, P, P, P, I, F, P], I),
+        "ltxb200_qk_norm_rope_wan_bf16": ([P, L, I, P, L, I, I, P, P, P, P, I, I, I, F, P], I),
+        "ltxb200_lincomb_f32": ([P, L, I, P, P, P], I),
         "ltxb200_ada_add_bf16": ([P, P, P, I, I, I, P], I),
         "ltxb200_act_bf16": ([P, P, L, I, P], I),
         "ltxb200_stg_blend_bf16": ([P, P, L, P, I, L, I, P], I),
         "ltxb200_timestep_embed": ([P, P, I, I, P], I),
         "ltxb200_cast_f32_to_bf16": ([P, P, L, P], I),
         "ltxb200_guidance_step": ([P, L, L, I, I, I, I, F, F, F, P, P, P, I, F, P, P, P], I),
+        "ltxb200_cfg_combine_f32": ([P, P, P, L, F, I, P, P], I),
         "ltxb200_pixelnorm_silu_bf16": ([P, P, L, I, F, I, P], I),
         "ltxb200_latent_to_ndhwc": ([P, I, P, I, I, L, P, P, P], I),
     }

@@ -148,6 +148,87 @@ qk_norm_rope_kernel(__nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict__ k
 }
 
 // ------------------------------------------------------------------------------------------
+// Wan q/k RMSNorm (full inner dim, affine, eps 1e-6, two bf16 roundings: model.py:104-111) + 3-axis RoPE
+// applied per head with fp32 [tokens, HD] cos/sin tables, fp32 math, one rounding
+// (posemb_layers.py:222-276).  token = token_offset + row % tokens_per_batch  (token_offset = the rank's
+// first global token under Ulysses sequence parallelism, xdit_context_parallel.py:52-57).
+// ------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(128)
+qk_norm_rope_wan_kernel(__nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict__ k, int Mq, int Mk, long long ldq,
+                        long long ldk, const __nv_bfloat16* __restrict__ wq, const __nv_bfloat16* __restrict__ wk,
+                        const float* __restrict__ cosT, const float* __restrict__ sinT, int head_dim,
+                        int tokens_per_batch, int token_offset, float eps) {
+  constexpr int D = NV * 256;
+  const bool is_k = blockIdx.y == 1;
+  __nv_bfloat16* base = is_k ? k : q;
+  if (base == nullptr) return;
+  const int M = is_k ? Mk : Mq;
+  const long long ld = is_k ? ldk : ldq;
+  const __nv_bfloat16* w = is_k ? wk : wq;
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  __nv_bfloat16* xr = base + row * ld;
+  float v[NV][8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) load8(xr + (i * 32 + lane) * 8, v[i]);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sq += v[i][j] * v[i][j];
+  const float rs = rsqrtf(warp_sum(sq) * (1.0f / D) + eps);
+  const long long trow = cosT ? static_cast<long long>(token_offset + row % tokens_per_batch) * head_dim : 0;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 8;
+    float ww[8], o[8];
+    load8(w + c, ww);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = bf16r(bf16r(v[i][j] * rs) * ww[j]);
+    if (cosT) {
+      const int hd = c % head_dim;
+      const float4 c0 = *reinterpret_cast<const float4*>(cosT + trow + hd), c1 = *reinterpret_cast<const float4*>(cosT + trow + hd + 4);
+      const float4 s0 = *reinterpret_cast<const float4*>(sinT + trow + hd), s1 = *reinterpret_cast<const float4*>(sinT + trow + hd + 4);
+      const float cs[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+      const float sn[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+      float r[8];
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        r[j] = o[j] * cs[j] - o[j + 1] * sn[j];
+        r[j + 1] = o[j + 1] * cs[j + 1] + o[j] * sn[j + 1];
+      }
+      store8(xr + c, r);
+    } else {
+      store8(xr + c, o);
+    }
+  }
+}
+
+// out = sum_j coef[j] * x[j]   (fp32, up to 6 terms; the UniPC predictor/corrector and CFG combine are
+// linear combinations with host-computed scalars: fm_solvers_unipc.py:321,458-484,590-626; text2video.py:562)
+struct LinCombParams {
+  const float* x[6];
+  float c[6];
+  int terms;
+};
+__global__ void lincomb_f32_kernel(float* __restrict__ out, long long n, const LinCombParams p) {
+  for (long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 4; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x * 4) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      if (j < p.terms) {
+        const float4 v = *reinterpret_cast<const float4*>(p.x[j] + i);
+        acc.x += p.c[j] * v.x; acc.y += p.c[j] * v.y; acc.z += p.c[j] * v.z; acc.w += p.c[j] * v.w;
+      }
+    }
+    *reinterpret_cast<float4*>(out + i) = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // ada[l, g, j, :] = table[l, j, :] + temb[g, j*D:(j+1)*D]   (bf16 add; attention.py:239-241)
 // ------------------------------------------------------------------------------------------
 __global__ void ada_add_kernel(const __nv_bfloat16* __restrict__ table, const __nv_bfloat16* __restrict__ temb,
@@ -373,6 +454,35 @@ __global__ void __launch_bounds__(256) guidance_step_kernel(const GuidanceParams
     if (update) x = x - dt * v;
     g.latents[i] = x;
     if (g.latents_bf16) g.latents_bf16[i] = __float2bfloat16_rn(x);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Wan CFG / CFG-Zero* combine in fp32 (text2video.py:31-42,551-562):
+//   alpha = <cond, uncond> / (||uncond||^2 + 1e-8)   (only when use_alpha)
+//   out   = alpha*uncond + g * (cond - alpha*uncond)
+// phase 0 writes per-block partial sums (deterministic order), phase 1 combines.
+// ------------------------------------------------------------------------------------------
+template <int kPhase>
+__global__ void __launch_bounds__(256)
+cfg_combine_f32_kernel(const float* __restrict__ cond, const float* __restrict__ uncond, float* __restrict__ out,
+                       long long n, float g, int use_alpha, float* __restrict__ partials) {
+  __shared__ float sm[8];
+  if (kPhase == 0) {
+    float a = 0.f, b = 0.f;
+    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * 256) {
+      const float c = cond[i], u = uncond[i];
+      a += c * u; b += u * u;
+    }
+    float r = block_sum_256(a, sm); if (threadIdx.x == 0) partials[blockIdx.x] = r;
+    r = block_sum_256(b, sm); if (threadIdx.x == 0) partials[kGuidanceBlocks + blockIdx.x] = r;
+  } else {
+    float alpha = 1.f;
+    if (use_alpha) alpha = sum_partials(partials) / (sum_partials(partials + kGuidanceBlocks) + 1e-8f);
+    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * 256) {
+      const float u = alpha * uncond[i];
+      out[i] = u + g * (cond[i] - u);
+    }
   }
 }
 

@@ -273,6 +273,47 @@ extern "C" int ltxb200_qk_norm_rope_bf16(void* q, int64_t ldq, int Mq, void* k, 
   return launch_status();
 }
 
+extern "C" int ltxb200_qk_norm_rope_wan_bf16(void* q, int64_t ldq, int Mq, void* k, int64_t ldk, int Mk, int D,
+                                             const void* wq, const void* wk, const float* cos_table,
+                                             const float* sin_table, int head_dim, int tokens_per_batch,
+                                             int token_offset, float eps, void* stream) {
+  if (D <= 0 || (D % 256) || (q == nullptr && k == nullptr)) return kErrBadShape;
+  if ((q && (!aligned16(q) || (ldq & 7) || !wq)) || (k && (!aligned16(k) || (ldk & 7) || !wk))) return kErrBadAlign;
+  if ((cos_table == nullptr) != (sin_table == nullptr)) return kErrBadShape;
+  if (cos_table && (tokens_per_batch <= 0 || head_dim <= 0 || (head_dim & 7) || (D % head_dim) || !aligned16(cos_table) || !aligned16(sin_table)))
+    return kErrBadShape;
+  const int M = Mq > Mk ? Mq : Mk;
+  dim3 grid((M + 3) / 4, k ? 2 : 1);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  auto Q = static_cast<__nv_bfloat16*>(q);
+  auto Kp = static_cast<__nv_bfloat16*>(k);
+  auto WQ = static_cast<const __nv_bfloat16*>(wq);
+  auto WK = static_cast<const __nv_bfloat16*>(wk);
+#define QKW_CASE(n) \
+  case n: qk_norm_rope_wan_kernel<n><<<grid, 128, 0, st>>>(Q, Kp, q ? Mq : 0, Mk, ldq, ldk, WQ, WK, cos_table, sin_table, head_dim, tokens_per_batch, token_offset, eps); break;
+  switch (D / 256) {
+    QKW_CASE(1) QKW_CASE(2) QKW_CASE(4) QKW_CASE(6) QKW_CASE(8) QKW_CASE(12) QKW_CASE(16) QKW_CASE(20)
+    default: return kErrUnsupported;
+  }
+#undef QKW_CASE
+  return launch_status();
+}
+
+extern "C" int ltxb200_lincomb_f32(float* out, int64_t n, int terms, const float* const* xs, const float* coefs,
+                                   void* stream) {
+  if (n <= 0 || (n & 3) || terms <= 0 || terms > 6 || !xs || !coefs) return kErrBadShape;
+  if (!aligned16(out)) return kErrBadAlign;
+  LinCombParams p{};
+  p.terms = terms;
+  for (int j = 0; j < terms; ++j) {
+    if (!aligned16(xs[j])) return kErrBadAlign;
+    p.x[j] = xs[j];
+    p.c[j] = coefs[j];
+  }
+  lincomb_f32_kernel<<<ew_blocks(n / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(out, n, p);
+  return launch_status();
+}
+
 extern "C" int ltxb200_ada_add_bf16(const void* table, const void* temb, void* out, int L, int G, int JD, void* stream) {
   if (L <= 0 || G <= 0 || JD <= 0 || (JD & 7)) return kErrBadShape;
   if (!aligned16(table) || !aligned16(temb) || !aligned16(out)) return kErrBadAlign;
@@ -342,6 +383,20 @@ extern "C" int ltxb200_guidance_step(const void* pred, int64_t cond_stride, int6
     if (rc) return rc;
   }
   guidance_step_kernel<<<kGuidanceBlocks, 256, 0, st>>>(g);
+  return launch_status();
+}
+
+extern "C" int ltxb200_cfg_combine_f32(const float* cond, const float* uncond, float* out, int64_t n, float guide_scale,
+                                       int use_alpha, float* scratch, void* stream) {
+  if (n <= 0 || !cond || !uncond || !out) return kErrBadShape;
+  if (use_alpha && !scratch) return kErrBadShape;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (use_alpha) {
+    cfg_combine_f32_kernel<0><<<kGuidanceBlocks, 256, 0, st>>>(cond, uncond, out, n, guide_scale, 1, scratch);
+    const int rc = launch_status();
+    if (rc) return rc;
+  }
+  cfg_combine_f32_kernel<1><<<kGuidanceBlocks, 256, 0, st>>>(cond, uncond, out, n, guide_scale, use_alpha ? 1 : 0, scratch);
   return launch_status();
 }
 

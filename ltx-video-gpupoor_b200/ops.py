@@ -239,3 +239,50 @@ def latent_to_ndhwc(z: torch.Tensor, stdv: Optional[torch.Tensor], meanv: Option
     _lib.check(_lib.lib().ltxb200_latent_to_ndhwc(z.data_ptr(), int(z.dtype == torch.float32), out.data_ptr(), B, C,
                                                   F_ * H * W, _p(stdv), _p(meanv), _stream()), "latent_to_ndhwc")
     return out
+
+
+def qk_norm_rope_wan(q: Optional[torch.Tensor], k: Optional[torch.Tensor], wq, wk, cos=None, sin=None, head_dim: int = 128,
+                     tokens_per_batch: int = 0, token_offset: int = 0, eps: float = 1e-6):
+    """In-place on 2-D row views q [Mq,D], k [Mk,D]; cos/sin fp32 [tokens, head_dim]."""
+    D = (q if q is not None else k).shape[1]
+    if cos is not None:
+        _req(cos, torch.float32, "cos"); _req(sin, torch.float32, "sin")
+        assert cos.is_contiguous() and sin.is_contiguous() and cos.shape[1] == head_dim
+    with _Prof("qk_norm_rope_wan_bf16", "byte", (4.0 * D) * ((q.shape[0] if q is not None else 0) + (k.shape[0] if k is not None else 0))):
+        rc = _lib.lib().ltxb200_qk_norm_rope_wan_bf16(
+            _p(q), q.stride(0) if q is not None else 0, q.shape[0] if q is not None else 0,
+            _p(k), k.stride(0) if k is not None else 0, k.shape[0] if k is not None else 0, D,
+            _p(wq), _p(wk), _p(cos), _p(sin), head_dim, tokens_per_batch, token_offset, float(eps), _stream())
+    _lib.check(rc, "qk_norm_rope_wan_bf16")
+
+
+def lincomb(out: torch.Tensor, terms) -> torch.Tensor:
+    """out = sum(c * x for c, x in terms); fp32 contiguous tensors of identical numel (out may alias an x)."""
+    import ctypes
+    n = out.numel()
+    k = len(terms)
+    _req(out, torch.float32, "out"); assert out.is_contiguous()
+    ptrs = (ctypes.c_void_p * k)()
+    cs = (ctypes.c_float * k)()
+    for j, (c, x) in enumerate(terms):
+        _req(x, torch.float32, "x"); assert x.is_contiguous() and x.numel() == n
+        ptrs[j] = x.data_ptr(); cs[j] = float(c)
+    with _Prof("lincomb_f32", "byte", 4.0 * n * (k + 1)):
+        rc = _lib.lib().ltxb200_lincomb_f32(out.data_ptr(), n, k, ptrs, cs, _stream())
+    _lib.check(rc, "lincomb_f32")
+    return out
+
+
+def cfg_combine(cond: torch.Tensor, uncond: torch.Tensor, guide_scale: float, use_alpha: bool,
+                scratch: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(cond, torch.float32, "cond"); _req(uncond, torch.float32, "uncond")
+    assert cond.is_contiguous() and uncond.is_contiguous() and cond.shape == uncond.shape
+    if out is None:
+        out = torch.empty_like(cond)
+    if use_alpha and scratch is None:
+        scratch = torch.empty(2 * 148, device=cond.device, dtype=torch.float32)
+    with _Prof("cfg_combine_f32", "byte", 4.0 * cond.numel() * (5 if use_alpha else 3)):
+        rc = _lib.lib().ltxb200_cfg_combine_f32(cond.data_ptr(), uncond.data_ptr(), out.data_ptr(), cond.numel(),
+                                                float(guide_scale), int(use_alpha), _p(scratch), _stream())
+    _lib.check(rc, "cfg_combine_f32")
+    return out

@@ -1,0 +1,83 @@
+"""WanT2V — B200-native drop-in for the denoise loop of wan/text2video.py:281-607 (`WanT2V.generate`).
+
+Scope: noise, UniPC schedule, RoPE tables, the per-step two-sequence forward (cond / uncond
+batched), CFG with the optional CFG-Zero* projection, scheduler step.  Text encoding (T5), the Wan VAE
+(§8f#1 "next"), VACE / phantom / recam and TeaCache are out of scope: prompt embeddings are passed in
+(`context=`, `context_null=`) and the result is the denoised latent [16, (F-1)/4+1, H/8, W/8] (fp32).
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+
+from .. import ops
+from .fm_solvers_unipc import FlowUniPCMultistepScheduler
+from .model import WanModel
+from .posemb_layers import get_rotary_pos_embed
+
+
+class WanT2V:
+    def __init__(self, model: WanModel, device="cuda", num_train_timesteps: int = 1000, vae_stride=(4, 8, 8),
+                 patch_size=(1, 2, 2), z_dim: int = 16):
+        self.model = model
+        self.device = torch.device(device)
+        self.num_train_timesteps = num_train_timesteps
+        self.vae_stride, self.patch_size, self.z_dim = vae_stride, patch_size, z_dim
+        self._interrupt = False
+
+    @torch.no_grad()
+    def generate(self, input_prompt=None, input_frames=None, input_masks=None, input_ref_images=None, input_video=None,
+                 target_camera=None, context_scale=1.0, width=1280, height=720, fit_into_canvas=True, frame_num=81,
+                 shift=5.0, sample_solver="unipc", sampling_steps=50, guide_scale=5.0, n_prompt="", seed=-1,
+                 offload_model=True, callback=None, enable_RIFLEx=None, VAE_tile_size=0, joint_pass=False,
+                 slg_layers=None, slg_start=0.0, slg_end=1.0, cfg_star_switch=True, cfg_zero_step=5,
+                 overlapped_latents=None, return_latent_slice=None, overlap_noise=0, conditioning_latents_size=0,
+                 model_filename=None, context: Optional[torch.Tensor] = None, context_null: Optional[torch.Tensor] = None,
+                 noise: Optional[torch.Tensor] = None, _per_step_latents=None, **bbargs):
+        if input_frames is not None or input_ref_images is not None or target_camera is not None or overlapped_latents is not None:
+            raise NotImplementedError("VACE / phantom / recam inputs are out of scope")
+        if context is None or (guide_scale != 1 and context_null is None):
+            raise NotImplementedError("the T5 text encoder is out of scope: pass context= / context_null= embeddings [L, 4096]")
+        if sample_solver != "unipc":
+            raise NotImplementedError("only the default 'unipc' solver is implemented (SURVEY §2 row 15)")
+        dev = self.device
+        F = frame_num
+        target_shape = (self.z_dim, (F - 1) // self.vae_stride[0] + 1, height // self.vae_stride[1], width // self.vae_stride[2])
+        if noise is None:
+            seed_g = torch.Generator(device=dev)
+            seed_g.manual_seed(seed if seed >= 0 else 0)
+            noise = torch.randn(*target_shape, dtype=torch.float32, device=dev, generator=seed_g)     # :410
+        latents = noise.to(device=dev, dtype=torch.float32).contiguous()
+        assert tuple(latents.shape) == tuple(target_shape)
+        sch = FlowUniPCMultistepScheduler(num_train_timesteps=self.num_train_timesteps, shift=1, use_dynamic_shifting=False)
+        sch.set_timesteps(sampling_steps, device=dev, shift=shift)                                        # :419-422
+        freqs = get_rotary_pos_embed(latents.shape[1:], enable_RIFLEx=bool(enable_RIFLEx))
+        freqs = (freqs[0].to(dev), freqs[1].to(dev))
+        scratch = torch.empty(2 * 148, device=dev, dtype=torch.float32)
+        ctx = context.to(dev)
+        ctx0 = context_null.to(dev) if context_null is not None else None
+        if callback is not None:
+            callback(-1, None, True)
+        for i, t in enumerate(sch.timesteps_host):
+            ts = torch.tensor([t], device=dev)
+            if guide_scale == 1:
+                pred = self.model([latents], t=ts, context=[ctx], freqs=freqs, pipeline=self, current_step=i)[0]
+                if pred is None:
+                    return None
+            else:
+                # cond and uncond sequences in one batched forward (the reference's joint_pass list call, :509)
+                c, u = self.model([latents, latents], t=ts, context=[ctx, ctx0], freqs=freqs, pipeline=self, current_step=i)
+                if c is None:
+                    return None
+                pred = ops.cfg_combine(c.contiguous(), u.contiguous(), guide_scale,
+                                       use_alpha=bool(cfg_star_switch and i > cfg_zero_step), scratch=scratch)   # :551-562
+            latents = sch.step(pred.unsqueeze(0), t, latents.unsqueeze(0), return_dict=False)[0].squeeze(0)
+            if _per_step_latents is not None:
+                _per_step_latents.append(latents.clone())
+            if callback is not None:
+                callback(i, latents, False)
+            if self._interrupt:
+                return None
+        return latents
