@@ -32,6 +32,14 @@ WORKLOADS = {
                                          guidance_scale=1.0, stg_scale=0.0, rescaling_scale=1.0, skip_block_list=None,
                                          prompt_tokens=256, num_conds=1),
 }
+WAN_WORKLOADS = {
+    # BASELINE.json configs[3]: Wan2.1 T2V-1.3B 832x480x81, 50 steps, CFG 5.0 (2 forwards/step), Ulysses SP over all ranks
+    "wan1.3b_832x480x81_sp": dict(model="1.3B", width=832, height=480, frame_num=81, schedule_steps=50, shift=5.0,
+                                  guide_scale=5.0, prompt_tokens=128, fwd_flops=283.0e12),
+    # BASELINE.json configs[4]: Wan2.1 T2V-14B 1280x720x81
+    "wan14b_1280x720x81_sp": dict(model="14B", width=1280, height=720, frame_num=81, schedule_steps=50, shift=5.0,
+                                  guide_scale=5.0, prompt_tokens=128, fwd_flops=6523.0e12),
+}
 LAYER_FLOPS = 1.048e12      # per layer per cond at N=6144
 FWD_FLOPS = 29.36e12
 
@@ -141,6 +149,159 @@ def run_reference(args, wl_name, wl):
     print(json.dumps(line))
 
 
+
+# ------------------------------------------------------------------------------------------------------------
+# Wan2.1 T2V, Ulysses sequence parallel over all ranks (strong scaling: one video, N GPUs)
+# ------------------------------------------------------------------------------------------------------------
+def run_wan(args, wl):
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) == 0:
+            print(json.dumps({"impl": "reference", "unavailable": "Wan CPU reference arm not wired into bench.py yet (oracle/wan_oracle.py exists)"}))
+        return
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    group = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+    from ltx_video_gpupoor_b200 import _lib, ops
+    from ltx_video_gpupoor_b200.wan.fm_solvers_unipc import FlowUniPCMultistepScheduler
+    from ltx_video_gpupoor_b200.wan.model import WAN_T2V_1_3B, WAN_T2V_14B, WanModel
+    from ltx_video_gpupoor_b200.wan.posemb_layers import get_rotary_pos_embed
+
+    cfg = dict(WAN_T2V_1_3B if wl["model"] == "1.3B" else WAN_T2V_14B)
+    cfg["num_layers"] = args.layers if args.layers != 28 else cfg["num_layers"]
+    gen = torch.Generator(device=dev).manual_seed(0)          # same seed on every rank: replicated weights
+    D, Fd = cfg["dim"], cfg["ffn_dim"]
+
+    def u(shape, fan_in):
+        return ((torch.rand(shape, generator=gen, device=dev) * 2 - 1) / fan_in ** 0.5).to(torch.bfloat16)
+
+    sd = {"patch_embedding.weight": u((D, 16, 1, 2, 2), 64), "patch_embedding.bias": u((D,), 64)}
+    for n, o, i in (("text_embedding.0", D, 4096), ("text_embedding.2", D, D), ("time_embedding.0", D, 256),
+                    ("time_embedding.2", D, D), ("time_projection.1", 6 * D, D), ("head.head", 64, D)):
+        sd[n + ".weight"], sd[n + ".bias"] = u((o, i), i), u((o,), i)
+    sd["head.modulation"] = (torch.randn(1, 2, D, generator=gen, device=dev) / D ** 0.5).to(torch.bfloat16)
+    for li in range(cfg["num_layers"]):
+        p = f"blocks.{li}."
+        for a in ("self_attn", "cross_attn"):
+            for n in ("q", "k", "v", "o"):
+                sd[p + a + "." + n + ".weight"], sd[p + a + "." + n + ".bias"] = u((D, D), D), u((D,), D)
+            sd[p + a + ".norm_q.weight"] = torch.ones(D, device=dev, dtype=torch.bfloat16)
+            sd[p + a + ".norm_k.weight"] = torch.ones(D, device=dev, dtype=torch.bfloat16)
+        sd[p + "norm3.weight"] = torch.ones(D, device=dev, dtype=torch.bfloat16)
+        sd[p + "norm3.bias"] = torch.zeros(D, device=dev, dtype=torch.bfloat16)
+        sd[p + "ffn.0.weight"], sd[p + "ffn.0.bias"] = u((Fd, D), D), u((Fd,), D)
+        sd[p + "ffn.2.weight"], sd[p + "ffn.2.bias"] = u((D, Fd), Fd), u((D,), Fd)
+        sd[p + "modulation"] = (torch.randn(1, 6, D, generator=gen, device=dev) / D ** 0.5).to(torch.bfloat16)
+    model = WanModel(**{k: v for k, v in cfg.items() if k not in ("qk_norm", "cross_attn_norm")}, sp_group=group)
+    model.load_state_dict(sd, device=dev)
+    del sd
+
+    shape = (16, (wl["frame_num"] - 1) // 4 + 1, wl["height"] // 8, wl["width"] // 8)
+    g = torch.Generator().manual_seed(42)
+    ctx_h = torch.randn(wl["prompt_tokens"], 4096, generator=g).to(torch.bfloat16).pin_memory()
+    ctx0_h = torch.randn(wl["prompt_tokens"], 4096, generator=g).to(torch.bfloat16).pin_memory()
+    noise_h = torch.randn(*shape, generator=g).pin_memory()
+    freqs = get_rotary_pos_embed(shape[1:])
+    freqs = (freqs[0].to(dev), freqs[1].to(dev))
+    S = wl["schedule_steps"]
+    scratch = torch.empty(2 * 148, device=dev)
+
+    def run_steps(lat, ctx, ctx0, sch, idx):
+        for i in idx:
+            t = sch.timesteps_host[i]
+            c, uu = model([lat, lat], t=torch.tensor([t], device=dev), context=[ctx, ctx0], freqs=freqs)
+            pred = ops.cfg_combine(c.contiguous(), uu.contiguous(), wl["guide_scale"], use_alpha=i > 5, scratch=scratch)
+            lat = sch.step(pred.unsqueeze(0), t, lat.unsqueeze(0), return_dict=False)[0].squeeze(0)
+        return lat
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sch = FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False)
+    sch.set_timesteps(S, device=dev, shift=wl["shift"])
+    ctx, ctx0, lat = ctx_h.to(dev), ctx0_h.to(dev), noise_h.to(dev)
+    lat = run_steps(lat, ctx, ctx0, sch, range(args.warmup))
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    lat = run_steps(lat, ctx, ctx0, sch, range(args.warmup, args.warmup + args.steps))
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = _lib.launch_count() - l0
+    elapsed = e0.elapsed_time(e1) / 1e3
+    if dist is not None:
+        tt = torch.tensor([elapsed], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        elapsed = float(tt)
+    steps_per_s = args.steps / elapsed            # ONE video split over all ranks: strong scaling
+
+    ops.PROFILER = []
+    run_steps(lat, ctx, ctx0, sch, [args.warmup + args.steps])
+    torch.cuda.synchronize()
+    prof, ops.PROFILER = ops.PROFILER, None
+    agg = {}
+    for name, kind, amount, a, b in prof:
+        d = agg.setdefault(name, dict(kind=kind, amount=0.0, ms=0.0, n=0))
+        d["amount"] += amount; d["ms"] += a.elapsed_time(b); d["n"] += 1
+    total_ms = sum(d["ms"] for d in agg.values())
+    top = max(agg, key=lambda k: agg[k]["ms"])
+    pk = peaks()
+    d = agg[top]
+    achieved = d["amount"] / (d["ms"] * 1e-3) / (1e12 if d["kind"] == "flop" else 1e9)
+    peak = pk["tf_sust"] if d["kind"] == "flop" else pk["hbm"]
+    roofline = {"kernel": top, "bound": "tensor" if d["kind"] == "flop" else "hbm", "achieved": achieved, "peak": peak,
+                "peak_source": pk["src"], "unit": "TFLOP/s" if d["kind"] == "flop" else "GB/s", "frac": achieved / peak,
+                "traffic": None, "launches_per_step": d["n"], "share_of_kernel_time": d["ms"] / total_ms}
+    kernels = {k: {"ms_per_step": round(v["ms"], 3), "launches": v["n"], "share": round(v["ms"] / total_ms, 4),
+                   ("tflops" if v["kind"] == "flop" else "gbs"): round(v["amount"] / (v["ms"] * 1e-3) / (1e12 if v["kind"] == "flop" else 1e9), 1)}
+               for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
+
+    # e2e: host noise + host prompt embeddings in, latents back to the host, K steps of a K-step schedule
+    K = max(args.steps, 2)
+    barrier()
+    t0 = time.perf_counter()
+    sch2 = FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False)
+    sch2.set_timesteps(K, device=dev, shift=wl["shift"])
+    out = run_steps(noise_h.to(dev, non_blocking=True), ctx_h.to(dev, non_blocking=True), ctx0_h.to(dev, non_blocking=True), sch2, range(K))
+    out_h = out.cpu()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        tt = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt)
+    if rank == 0:
+        ms_step = elapsed / args.steps * 1e3
+        line = {"metric": "denoise_steps_per_s", "value": steps_per_s, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": args.workload, "model": f"Wan2.1-T2V-{wl['model']} (random-init, {cfg['num_layers']} layers)",
+                           "latent": list(shape), "tokens": shape[1] * shape[2] * shape[3] // 4, "schedule_steps": S,
+                           "forwards_per_step": 2, "parallelism": f"ulysses sp{world}",
+                           "l2_policy": "per-step working set (weights + activations) far exceeds the 126 MB L2"},
+                "e2e": {"value": K / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": (noise_h.numel() * 4 + 2 * ctx_h.numel() * 2) / K,
+                        "d2h_bytes_per_step": out_h.numel() * 4 / K, "steps_in_call": K},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": None,
+                "s_per_video_denoise": S * ms_step / 1e3,
+                "model_tflops_per_gpu": 2 * wl["fwd_flops"] * (cfg["num_layers"] / (30 if wl["model"] == "1.3B" else 40)) / (ms_step / 1e3) / 1e12 / world,
+                "kernels": kernels}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
 # ------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -148,12 +309,14 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="ltx2b_768x512x121_cfg_stg", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="ltx2b_768x512x121_cfg_stg", choices=sorted(WORKLOADS) + sorted(WAN_WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
     ap.add_argument("--layers", type=int, default=28, help="debug only: fewer layers makes the number INVALID")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 0)
+    if args.workload in WAN_WORKLOADS:
+        return run_wan(args, WAN_WORKLOADS[args.workload])
     wl = WORKLOADS[args.workload]
 
     if args.impl == "reference":
