@@ -235,9 +235,14 @@ def run_wan(args, wl):
     sampler.start()
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if os.environ.get("LTXB200_NCU_RANGE"):
+        torch.cuda.profiler.start()
     e0.record()
     lat = run_steps(lat, ctx, ctx0, sch, range(args.warmup, args.warmup + args.steps))
     e1.record()
+    if os.environ.get("LTXB200_NCU_RANGE"):
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     barrier()
     clocks = sampler.stop()
     launches = _lib.launch_count() - l0
@@ -378,10 +383,15 @@ def main():
     sampler.start()
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if os.environ.get("LTXB200_NCU_RANGE"):          # `ncu --profile-from-start off`: capture the timed region only
+        torch.cuda.profiler.start()
     e0.record()
     for i in range(args.steps):
         pipe.denoise_step(st, (args.warmup + i) % S)
     e1.record()
+    if os.environ.get("LTXB200_NCU_RANGE"):
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     barrier()
     clocks = sampler.stop()
     launches = _lib.launch_count() - l0

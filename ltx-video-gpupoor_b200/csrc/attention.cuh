@@ -3,24 +3,27 @@
 //   O[b, q, h, :] = softmax_k( scale * Q[b,q,h,:].K[b,k,h,:] + key_bias[b,k] ) V[b,k,h,:]
 //
 // Layout [B, L, H, d] for Q/K/V with arbitrary (16B-aligned) token and batch strides, so q/k/v may be
-// column slices of one fused QKV projection.  One CTA = one 128-row Q tile of one (b, h); two CTAs are
-// co-resident per SM so one CTA's softmax overlaps the other's MMAs.  192 threads: warp 0 = TMA
-// producer, warp 1 = MMA issuer + TMEM owner, warps 2..5 = softmax / correction / epilogue with one
-// query row per thread (TMEM lane == row).
+// column slices of one fused QKV projection.  Reference semantics: utils/attention.py:99-116
+// (sdpa_wrapper) incl. the additive key mask.
 //
-// TMEM columns: [0,128) S fp32, overwritten in place by P (bf16 pairs, 64 columns) ; [128,128+d) O fp32.
-// P is consumed straight from TMEM as the A operand of the P.V MMA (tcgen05.mma "TS" form); V is read
-// from shared memory as an MN-major B operand, so no transposes are materialised.
-// Rescaling of O is lazy (only when the running max grows by more than 2^8).
-// Reference semantics: utils/attention.py:99-116 (sdpa_wrapper) incl. the additive key mask.
+// Structure (persistent, warp-specialised, two query tiles in ping-pong per CTA):
+//   * a CTA walks work items (b, h, 256 query rows) round-robin; each item is two 128-row Q tiles that share
+//     every K/V block brought in by TMA (one producer warp, kStages-deep K and V rings);
+//   * one MMA warp issues, per key block j and tile t:  O_t += P_t(j-1).V(j-1)  then  S_t(j) = Q_t.K(j)^T,
+//     so the tensor pipe works on one tile while the other tile's softmax runs;
+//   * two softmax warpgroups (one per tile, one query row per thread = TMEM lane): the whole S row chunk is read
+//     from TMEM ONCE into registers, row max -> lazy rescale of O (only when the max grows by > 2^8) ->
+//     exp2 -> P (bf16 pairs) written over the first half of the S columns and consumed straight from TMEM as the
+//     A operand of the P.V MMA ("TS" form); V is an MN-major B operand, so nothing is transposed;
+//   * the same warpgroups normalise and store O when their tile is finished, while the MMA warp already runs
+//     the next work item's first S blocks.
+// TMEM columns: S_0 | S_1 | O_0 | O_1  (BN, BN, D, D).
 #pragma once
 #include "common.cuh"
 
 namespace b200 {
 
-constexpr int kAttnThreads = 192;
-constexpr int kAttnBM = 128;   // query rows per CTA
-constexpr int kAttnBN = 128;   // keys per block
+constexpr int kAttnBM = 128;   // query rows per tile (= TMEM lanes)
 
 struct AttnParams {
   int B, H, Lq, Lk;
@@ -28,352 +31,336 @@ struct AttnParams {
   const float* key_bias;         // [B, Lk] additive (natural-log domain) or null
   __nv_bfloat16* out;            // [B, Lq, H*d] contiguous rows, row stride out_ld
   long long out_ld, out_bs;
+  int pairs;                     // ceil(Lq / 256)
+  int total;                     // B * H * pairs work items
 };
 
-template <int D>
-struct AttnSmem {
-  static constexpr int kStages = (D == 64) ? 2 : 1;
-  static constexpr int kQBytes = kAttnBM * D * 2;
-  static constexpr int kKBytes = kAttnBN * D * 2;
-  static constexpr int kVBytes = kAttnBN * D * 2;
+constexpr uint32_t next_pow2_u32(uint32_t x) { uint32_t p = 32; while (p < x) p <<= 1; return p; }
+
+template <int D, int BN, int kCtasPerSm>
+struct AttnCfg {
+  static constexpr int kStages = (BN * D * 2 <= 8192) ? 4 : (BN * D * 2 <= 16384 ? 3 : 2);
+  static constexpr int kQBytes = kAttnBM * D * 2;            // one Q tile
+  static constexpr int kKBytes = BN * D * 2;                 // one K (or V) block
   static constexpr int kBarBytes = 256;
-  static constexpr int kTotal = kQBytes + kStages * (kKBytes + kVBytes) + kBarBytes + 1024;
+  static constexpr int kTotal = 2 * kQBytes + 2 * kStages * kKBytes + kBarBytes + 1024;
+  static constexpr bool kRegRealloc = (kCtasPerSm == 1);     // setmaxnreg: softmax warpgroups take the registers
+  static constexpr int kThreads = kRegRealloc ? 384 : 320;   // 8 softmax warps + TMA warp + MMA warp (+2 idle for WG alignment)
+  static constexpr uint32_t kTmemCols = next_pow2_u32(2 * BN + 2 * D);
+  static constexpr int kSoftmaxRegs = 208, kOtherRegs = 64;
 };
 
-// One 128-key block of the online softmax for one query row (one thread): S (TMEM fp32) -> P (TMEM, bf16 pairs),
-// running max m_ref (log2 domain) and row sum l updated, O rescaled lazily.  With kEarlyS, P has its own TMEM
-// columns: `s_free` is signalled as soon as the whole S row sits in registers (so the MMA warp can already issue
-// the next block's Q.K^T), and `pv_done` (previous block's P.V retired) is awaited before O or P are touched.
-template <int D, bool kPredicated, bool kEarlyS>
-DEVI void softmax_block(uint32_t tS, uint32_t tP, uint32_t tO, int j, int kbase, int Lk, const float* bias, float sc,
-                        float& m_ref, float& l, uint64_t* s_free, uint64_t* pv_done, int lane) {
+DEVI float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
+// One key block of the online softmax for one query row (one thread).  S (fp32, BN columns at tS) -> registers
+// (single TMEM pass) -> P (bf16 pairs, BN/2 columns written back at tS).  m_ref / l: running reference max
+// (log2 domain) and row sum.  O at tO is rescaled only when the max moved by more than 2^8 (warp-uniform branch,
+// the TMEM ops are warp-collective).  All previous P.V MMAs of this tile have retired when S(j) is visible
+// (same in-order pipe, the S commit covers them), so O may be touched here.
+template <int D, int BN, bool kPredicated>
+DEVI void softmax_block(uint32_t tS, uint32_t tO, int j, int kbase, int Lk, const float* bias, float sc,
+                        float& m_ref, float& l) {
   const float kLog2e = 1.4426950408889634f;
-  // ---- pass 1: block row-max (TMEM loads software-pipelined: chunk c+1 is in flight while c is reduced) ----
+  uint32_t v[BN];
   float mx0 = -INFINITY, mx1 = -INFINITY;
-  {
-    uint32_t va[32], vb[32];
-    tmem_ld32(tS, va);
+  tmem_ld32(tS, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
 #pragma unroll
-    for (int c = 0; c < kAttnBN; c += 64) {
-      tmem_wait_ld();
-      tmem_ld32(tS + c + 32, vb);
-      if (kPredicated) {
+  for (int c = 0; c < BN; c += 32) {
+    tmem_wait_ld();
+    if (c + 32 < BN) tmem_ld32(tS + c + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c + 32]));
+    if (kPredicated) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int k = kbase + c + i;
-          float s = __uint_as_float(va[i]) * sc;
-          if (bias && k < Lk) s += __ldg(bias + k) * kLog2e;
-          if (k >= Lk) s = -INFINITY;
-          mx0 = fmaxf(mx0, s);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          mx0 = fmaxf(mx0, fmaxf(__uint_as_float(va[i]), __uint_as_float(va[i + 1])));
-          mx1 = fmaxf(mx1, fmaxf(__uint_as_float(va[i + 2]), __uint_as_float(va[i + 3])));
-        }
+      for (int i = 0; i < 32; ++i) {
+        const int k = kbase + c + i;
+        float s = __uint_as_float(v[c + i]) * sc;
+        if (bias && k < Lk) s = fmaf(__ldg(bias + k), kLog2e, s);
+        if (k >= Lk) s = -INFINITY;
+        v[c + i] = __float_as_uint(s);
+        mx0 = fmaxf(mx0, s);
       }
-      tmem_wait_ld();
-      if (c + 64 < kAttnBN) tmem_ld32(tS + c + 64, va);
-      if (kPredicated) {
+    } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int k = kbase + c + 32 + i;
-          float s = __uint_as_float(vb[i]) * sc;
-          if (bias && k < Lk) s += __ldg(bias + k) * kLog2e;
-          if (k >= Lk) s = -INFINITY;
-          mx1 = fmaxf(mx1, s);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          mx0 = fmaxf(mx0, fmaxf(__uint_as_float(vb[i]), __uint_as_float(vb[i + 1])));
-          mx1 = fmaxf(mx1, fmaxf(__uint_as_float(vb[i + 2]), __uint_as_float(vb[i + 3])));
-        }
+      for (int i = 0; i < 32; i += 4) {
+        mx0 = fmax3(mx0, __uint_as_float(v[c + i]), __uint_as_float(v[c + i + 1]));
+        mx1 = fmax3(mx1, __uint_as_float(v[c + i + 2]), __uint_as_float(v[c + i + 3]));
       }
     }
   }
   float m_blk = fmaxf(mx0, mx1);
   if (!kPredicated) m_blk *= sc;                 // scale > 0: max commutes with the scaling
-  // ---- lazy rescale of O and l ----
-  bool need;
-  if (j == 0) {
-    m_ref = (m_blk == -INFINITY) ? 0.f : m_blk;
-    need = false;
-  } else {
-    need = m_blk > m_ref + 8.0f;
-  }
-  if (kEarlyS && j > 0) {          // P(j-1).V must have retired before O is rescaled or P is overwritten
-    mbar_wait(pv_done, (j - 1) & 1);
-    tc_fence_after();
-  }
+  bool need = false;
+  if (j == 0) m_ref = (m_blk == -INFINITY) ? 0.f : m_blk;
+  else need = m_blk > m_ref + 8.0f;
   if (__any_sync(0xffffffffu, need)) {
     const float m_new = need ? m_blk : m_ref;
     const float alpha = fast_exp2(m_ref - m_new);
     m_ref = m_new;
     l *= alpha;
 #pragma unroll 1
-    for (int c = 0; c < D; c += 32) {
-      uint32_t o[32];
-      tmem_ld32(tO + c, o);
+    for (int c = 0; c < D; c += 16) {
+      uint32_t o[16];
+      tmem_ld16(tO + c, o);
       tmem_wait_ld();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-      tmem_st32(tO + c, o);
+      for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+      tmem_st16(tO + c, o);
     }
   }
-  // ---- pass 2: P = exp2(s*scale - m_ref) -> bf16 pairs into TMEM, l += rowsum ----
   float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-  uint32_t va[32], vb[32];
-  tmem_ld32(tS, va);
+  const float neg_m = -m_ref;
 #pragma unroll
-  for (int c = 0; c < kAttnBN; c += 64) {
+  for (int c = 0; c < BN; c += 32) {
+    uint32_t pk[16];
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      uint32_t (&v)[32] = half ? vb : va;
-      uint32_t (&nx)[32] = half ? va : vb;
-      const int cc = c + half * 32;
-      tmem_wait_ld();
-      if (cc + 32 < kAttnBN) tmem_ld32(tS + cc + 32, nx);
-      if (kEarlyS && cc + 32 == kAttnBN) {     // every S column of this row is now in registers: S may be overwritten
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(s_free);
-      }
-      float e[32];
+    for (int i = 0; i < 32; i += 4) {
+      float e0, e1, e2, e3;
       if (kPredicated) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int k = kbase + cc + i;
-          float s = __uint_as_float(v[i]) * sc;
-          if (bias && k < Lk) s += __ldg(bias + k) * kLog2e;
-          e[i] = (k < Lk) ? fast_exp2(s - m_ref) : 0.f;
-        }
+        e0 = fast_exp2(__uint_as_float(v[c + i]) + neg_m);
+        e1 = fast_exp2(__uint_as_float(v[c + i + 1]) + neg_m);
+        e2 = fast_exp2(__uint_as_float(v[c + i + 2]) + neg_m);
+        e3 = fast_exp2(__uint_as_float(v[c + i + 3]) + neg_m);
       } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) e[i] = fmaf(__uint_as_float(v[i]), sc, -m_ref);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) e[i] = fast_exp2(e[i]);
+        e0 = fast_exp2(fmaf(__uint_as_float(v[c + i]), sc, neg_m));
+        e1 = fast_exp2(fmaf(__uint_as_float(v[c + i + 1]), sc, neg_m));
+        e2 = fast_exp2(fmaf(__uint_as_float(v[c + i + 2]), sc, neg_m));
+        e3 = fast_exp2(fmaf(__uint_as_float(v[c + i + 3]), sc, neg_m));
       }
-      uint32_t pk[16];
-#pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        l0 += e[i]; l1 += e[i + 1]; l2 += e[i + 2]; l3 += e[i + 3];
-        pk[i >> 1] = pack_bf16(e[i], e[i + 1]);
-        pk[(i >> 1) + 1] = pack_bf16(e[i + 2], e[i + 3]);
-      }
-      tmem_st16(tP + (cc >> 1), pk);
+      l0 += e0; l1 += e1; l2 += e2; l3 += e3;
+      pk[i >> 1] = pack_bf16(e0, e1);
+      pk[(i >> 1) + 1] = pack_bf16(e2, e3);
     }
+    tmem_st16(tS + (c >> 1), pk);
   }
   l += (l0 + l1) + (l2 + l3);
 }
 
-template <int D, bool kMasked>
-__global__ void __launch_bounds__(kAttnThreads, 2)
+template <int D, int BN, int kCtasPerSm, bool kMasked>
+__global__ void __launch_bounds__((AttnCfg<D, BN, kCtasPerSm>::kThreads), kCtasPerSm)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
-  using S = AttnSmem<D>;
-  constexpr int kStages = S::kStages;
+  using C = AttnCfg<D, BN, kCtasPerSm>;
+  constexpr int kStages = C::kStages;
   constexpr int kChunks = D / 64;                    // 64-wide (128 B) column chunks per row
-  constexpr uint32_t kTmemCols = 256;
-  // d=64: P has its own columns so S(j+1) can be issued while softmax(j) is still exponentiating (kEarlyS);
-  // d=128: 128 (S) + 128 (O) fill the 256-column budget of a 2-CTA/SM kernel, so P aliases S.
-  constexpr bool kEarlyS = (D == 64);
-  constexpr uint32_t kColS = 0, kColP = kEarlyS ? 128 : 0, kColO = kEarlyS ? 192 : 128;
+  constexpr int kTmaWarp = 8, kMmaWarp = 9;
+  constexpr uint32_t kColS0 = 0, kColO0 = 2 * BN;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + S::kQBytes;
-  uint8_t* sV = sK + kStages * S::kKBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kStages * S::kVBytes);
-  uint64_t* q_full = bars;               // 1
-  uint64_t* k_full = bars + 1;           // kStages
-  uint64_t* k_empty = k_full + 2;
-  uint64_t* v_full = k_empty + 2;
-  uint64_t* v_empty = v_full + 2;
-  uint64_t* s_full = v_empty + 2;        // 1
-  uint64_t* p_full = s_full + 1;         // 1
-  uint64_t* o_done = p_full + 1;         // 1
-  uint64_t* s_free = o_done + 1;         // 1  softmax finished READING S(j)          (kEarlyS)
-  uint64_t* pv_done = s_free + 1;        // 1  P(j).V MMA retired: P and O may be touched (kEarlyS)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+  uint8_t* sQ = smem;                                 // [2][128][D]
+  uint8_t* sK = sQ + 2 * C::kQBytes;                  // [kStages][BN][D]
+  uint8_t* sV = sK + kStages * C::kKBytes;            // [kStages][BN][D]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kStages * C::kKBytes);
+  uint64_t* q_full = bars;                // [2]  TMA -> MMA
+  uint64_t* q_empty = q_full + 2;         // [2]  last S of the item issued: Q tile may be overwritten
+  uint64_t* k_full = q_empty + 2;         // [kStages]
+  uint64_t* k_empty = k_full + kStages;
+  uint64_t* v_full = k_empty + kStages;
+  uint64_t* v_empty = v_full + kStages;
+  uint64_t* s_full = v_empty + kStages;   // [2]  S_t(j) complete (and every earlier MMA of the pipe)
+  uint64_t* p_full = s_full + 2;          // [2]  P_t(j) written (4 warps arrive)
+  uint64_t* o_done = p_full + 2;          // [2]  last P.V of the item retired
+  uint64_t* o_free = o_done + 2;          // [2]  epilogue has read O_t (4 warps arrive)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * kAttnBM, h = blockIdx.y, b = blockIdx.z;
-  const int nblk = (p.Lk + kAttnBN - 1) / kAttnBN;
+  const int nblk = (p.Lk + BN - 1) / BN;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
-    mbar_init(q_full, 1);
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&q_full[t], 1);
+      mbar_init(&q_empty[t], 1);
+      mbar_init(&s_full[t], 1);
+      mbar_init(&p_full[t], 4);
+      mbar_init(&o_done[t], 1);
+      mbar_init(&o_free[t], 4);
+    }
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&k_empty[i], 1);
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 4);
-    mbar_init(o_done, 1);
-    mbar_init(s_free, 4);
-    mbar_init(pv_done, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+  if (warp == kMmaWarp) tmem_alloc<C::kTmemCols>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    // ================= TMA producer =================
-    if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, S::kQBytes);
+  if (warp >= 8) {
+    if (C::kRegRealloc) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(C::kOtherRegs));
+    if (warp == kTmaWarp && lane == 0) {
+      // ================= TMA producer =================
+      uint32_t kc = 0;
+      int it = 0;
+      for (int w = blockIdx.x; w < p.total; w += gridDim.x, ++it) {
+        const int qp = w % p.pairs, bh = w / p.pairs, h = bh % p.H, b = bh / p.H;
 #pragma unroll
-      for (int c = 0; c < kChunks; ++c) tma_load_4d(sQ + c * (kAttnBM * 128), &tmQ, q_full, c * 64, h, q0, b);
-      int st = 0;
-      uint32_t ph = 0;
-      for (int j = 0; j < nblk; ++j) {
-        mbar_wait_backoff(&k_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&k_full[st], S::kKBytes);
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait_backoff(&q_empty[t], (it & 1) ^ 1);
+          mbar_arrive_expect_tx(&q_full[t], C::kQBytes);
 #pragma unroll
-        for (int c = 0; c < kChunks; ++c)
-          tma_load_4d(sK + st * S::kKBytes + c * (kAttnBN * 128), &tmK, &k_full[st], c * 64, h, j * kAttnBN, b);
-        mbar_wait_backoff(&v_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&v_full[st], S::kVBytes);
-#pragma unroll
-        for (int c = 0; c < kChunks; ++c)
-          tma_load_4d(sV + st * S::kVBytes + c * (kAttnBN * 128), &tmV, &v_full[st], c * 64, h, j * kAttnBN, b);
-        if (++st == kStages) { st = 0; ph ^= 1; }
-      }
-    }
-  } else if (warp == 1) {
-    // ================= MMA issuer =================
-    constexpr uint32_t idesc_s = umma_idesc_bf16(kAttnBM, kAttnBN, 0, 0);   // S = Q K^T  (both K-major)
-    constexpr uint32_t idesc_o = umma_idesc_bf16(kAttnBM, D, 0, 1);         // O += P V   (V is MN-major)
-    mbar_wait(q_full, 0);
-    auto issue_s = [&](int stage) {
-      const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK + stage * S::kKBytes);
-#pragma unroll
-      for (int ks = 0; ks < D / 16; ++ks) {
-        const uint32_t off = (ks >> 2) * (kAttnBM * 128) + (ks & 3) * 32;
-        umma_ss(tmem_base + kColS, umma_smem_desc_sw128(qa + off, 16, 1024), umma_smem_desc_sw128(ka + off, 16, 1024),
-                idesc_s, ks ? 1u : 0u);
-      }
-      umma_commit(&k_empty[stage]);
-      umma_commit(s_full);
-    };
-    auto issue_pv = [&](int stage, int j) {
-      const uint32_t va = smem_u32(sV + stage * S::kVBytes);
-#pragma unroll
-      for (int ks = 0; ks < kAttnBN / 16; ++ks) {
-        // B = V[16 keys (K), D (N)], N contiguous: 8-key groups 1024 B apart (SBO), 64-col groups one chunk apart (LBO)
-        const uint64_t vd = umma_smem_desc_sw128(va + ks * 2048, kAttnBN * 128, 1024);
-        umma_ts(tmem_base + kColO, tmem_base + kColP + ks * 8, vd, idesc_o, (j | ks) ? 1u : 0u);
-      }
-      umma_commit(&v_empty[stage]);
-      if (kEarlyS) umma_commit(pv_done);
-      if (j == nblk - 1) umma_commit(o_done);
-    };
-    if (kEarlyS) {
-      // S(j+1) is issued as soon as softmax(j) has read S(j) out of TMEM, ahead of P(j).V, so the next block's
-      // scores are ready when the softmax warps come back for them.
-      int st_k = 0, st_v = 0;
-      uint32_t ph_k = 0, ph_v = 0;
-      mbar_wait(&k_full[0], 0);
-      tc_fence_after();
-      if (lane == 0) issue_s(0);
-      __syncwarp();
-      if (++st_k == kStages) { st_k = 0; ph_k ^= 1; }
-      for (int j = 0; j < nblk; ++j) {
-        if (j + 1 < nblk) {
-          mbar_wait(&k_full[st_k], ph_k);
-          mbar_wait(s_free, j & 1);
-          tc_fence_after();
-          if (lane == 0) issue_s(st_k);
-          __syncwarp();
-          if (++st_k == kStages) { st_k = 0; ph_k ^= 1; }
+          for (int c = 0; c < kChunks; ++c)
+            tma_load_4d(sQ + t * C::kQBytes + c * (kAttnBM * 128), &tmQ, &q_full[t], c * 64, h, qp * 256 + t * kAttnBM, b);
         }
-        mbar_wait(&v_full[st_v], ph_v);
-        mbar_wait(p_full, j & 1);
-        tc_fence_after();
-        if (lane == 0) issue_pv(st_v, j);
-        __syncwarp();
-        if (++st_v == kStages) { st_v = 0; ph_v ^= 1; }
+        for (int j = 0; j < nblk; ++j, ++kc) {
+          const int st = kc % kStages;
+          const uint32_t ph = (kc / kStages) & 1;
+          mbar_wait_backoff(&k_empty[st], ph ^ 1);
+          mbar_arrive_expect_tx(&k_full[st], C::kKBytes);
+#pragma unroll
+          for (int c = 0; c < kChunks; ++c)
+            tma_load_4d(sK + st * C::kKBytes + c * (BN * 128), &tmK, &k_full[st], c * 64, h, j * BN, b);
+          mbar_wait_backoff(&v_empty[st], ph ^ 1);
+          mbar_arrive_expect_tx(&v_full[st], C::kKBytes);
+#pragma unroll
+          for (int c = 0; c < kChunks; ++c)
+            tma_load_4d(sV + st * C::kKBytes + c * (BN * 128), &tmV, &v_full[st], c * 64, h, j * BN, b);
+        }
       }
-    } else {
-      int st = 0;
-      uint32_t ph = 0;
-      for (int j = 0; j < nblk; ++j) {
-        mbar_wait(&k_full[st], ph);
-        tc_fence_after();
-        if (lane == 0) issue_s(st);
-        __syncwarp();
-        mbar_wait(&v_full[st], ph);
-        mbar_wait(p_full, j & 1);
-        tc_fence_after();
-        if (lane == 0) issue_pv(st, j);
-        __syncwarp();
-        if (++st == kStages) { st = 0; ph ^= 1; }
+    } else if (warp == kMmaWarp && lane == 0) {
+      // ================= MMA issuer =================
+      constexpr uint32_t idesc_s = umma_idesc_bf16(kAttnBM, BN, 0, 0);   // S = Q K^T  (both K-major)
+      constexpr uint32_t idesc_o = umma_idesc_bf16(kAttnBM, D, 0, 1);    // O += P V   (V is MN-major)
+      // descriptors = (constant high bits | start address >> 4); tile / stage / k-step offsets are added to the
+      // low word at issue time (the 14-bit address field cannot carry: shared memory is < 256 KB)
+      const uint64_t qdesc = umma_smem_desc_sw128(smem_u32(sQ), 16, 1024);
+      const uint64_t kdesc = umma_smem_desc_sw128(smem_u32(sK), 16, 1024);
+      const uint64_t vdesc = umma_smem_desc_sw128(smem_u32(sV), BN * 128, 1024);
+      auto issue_s = [&](int t, int stage) {
+        const uint64_t qa = qdesc + static_cast<uint32_t>(t * (C::kQBytes >> 4));
+        const uint64_t ka = kdesc + static_cast<uint32_t>(stage * (C::kKBytes >> 4));
+        const uint32_t ts = tmem_base + kColS0 + t * BN;
+#pragma unroll
+        for (int ks = 0; ks < D / 16; ++ks) {
+          const uint32_t offa = ((ks >> 2) * (kAttnBM * 128) + (ks & 3) * 32) >> 4;
+          const uint32_t offb = ((ks >> 2) * (BN * 128) + (ks & 3) * 32) >> 4;
+          umma_ss(ts, qa + offa, ka + offb, idesc_s, ks ? 1u : 0u);
+        }
+      };
+      auto issue_pv = [&](int t, int stage, bool acc) {
+        // B = V[16 keys (K), D (N)], N contiguous: 8-key groups 1024 B apart (SBO), 64-col groups one chunk apart (LBO)
+        const uint64_t va = vdesc + static_cast<uint32_t>(stage * (C::kKBytes >> 4));
+        const uint32_t to = tmem_base + kColO0 + t * D, tp = tmem_base + kColS0 + t * BN;
+#pragma unroll
+        for (int ks = 0; ks < BN / 16; ++ks)
+          umma_ts(to, tp + ks * 8, va + static_cast<uint32_t>(ks * (2048 >> 4)), idesc_o, (acc || ks) ? 1u : 0u);
+      };
+      uint32_t kc = 0, vc = 0;       // K / V ring counters
+      uint32_t pc = 0;               // p_full phase counter (same for both tiles)
+      int it = 0;
+      for (int w = blockIdx.x; w < p.total; w += gridDim.x, ++it) {
+        {  // S_t(0)
+          const int st = kc % kStages;
+          mbar_wait(&k_full[st], (kc / kStages) & 1);
+#pragma unroll 1
+          for (int t = 0; t < 2; ++t) {
+            mbar_wait(&q_full[t], it & 1);
+            tc_fence_after();
+            issue_s(t, st);
+            umma_commit(&s_full[t]);
+            if (nblk == 1) umma_commit(&q_empty[t]);
+          }
+          umma_commit(&k_empty[st]);
+          ++kc;
+        }
+        // step = (key block j, tile t): O_t += P_t(j).V(j), then S_t(j+1) = Q_t.K(j+1)^T
+#pragma unroll 1
+        for (int step = 0; step < 2 * nblk; ++step) {
+          const int j = step >> 1, t = step & 1;
+          const int sv = vc % kStages, sk = kc % kStages;
+          mbar_wait(&p_full[t], pc & 1);
+          if (j == 0) mbar_wait(&o_free[t], (it & 1) ^ 1);
+          if (t == 0) mbar_wait(&v_full[sv], (vc / kStages) & 1);
+          tc_fence_after();
+          issue_pv(t, sv, j > 0);
+          if (t == 1) umma_commit(&v_empty[sv]);
+          if (j + 1 < nblk) {
+            if (t == 0) { mbar_wait(&k_full[sk], (kc / kStages) & 1); tc_fence_after(); }
+            issue_s(t, sk);
+            umma_commit(&s_full[t]);
+            if (j + 2 == nblk) umma_commit(&q_empty[t]);
+            if (t == 1) umma_commit(&k_empty[sk]);
+          } else {
+            umma_commit(&o_done[t]);
+          }
+          if (t == 1) {
+            ++vc; ++pc;
+            if (j + 1 < nblk) ++kc;
+          }
+        }
       }
     }
   } else {
-    // ================= softmax / correction / epilogue =================
+    // ================= softmax / correction / epilogue: warpgroup t owns query tile t =================
+    if (C::kRegRealloc) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(C::kSoftmaxRegs));
+    const int t = warp >> 2;
     const int sub = warp & 3;
     const int row = sub * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(sub * 32) << 16;
-    const uint32_t tS = tmem_base + kColS + lane_addr;
-    const uint32_t tP = tmem_base + kColP + lane_addr;
-    const uint32_t tO = tmem_base + kColO + lane_addr;
-    const float* bias = p.key_bias ? p.key_bias + static_cast<long long>(b) * p.Lk : nullptr;
-    float m_ref = 0.f, l = 0.f;
-
-    for (int j = 0; j < nblk; ++j) {
-      mbar_wait(s_full, j & 1);
+    const uint32_t tS = tmem_base + kColS0 + t * BN + lane_addr;
+    const uint32_t tO = tmem_base + kColO0 + t * D + lane_addr;
+    uint32_t sc_cnt = 0;
+    int it = 0;
+    for (int w = blockIdx.x; w < p.total; w += gridDim.x, ++it) {
+      const int qp = w % p.pairs, bh = w / p.pairs, h = bh % p.H, b = bh / p.H;
+      const float* bias = p.key_bias ? p.key_bias + static_cast<long long>(b) * p.Lk : nullptr;
+      float m_ref = 0.f, l = 0.f;
+      for (int j = 0; j < nblk; ++j, ++sc_cnt) {
+        mbar_wait(&s_full[t], sc_cnt & 1);
+        tc_fence_after();
+        const int kbase = j * BN;
+        // full blocks without a bias take the lean path; the tail block / biased blocks take the predicated one
+        if (kMasked && (bias != nullptr || kbase + BN > p.Lk))
+          softmax_block<D, BN, true>(tS, tO, j, kbase, p.Lk, bias, p.scale_log2, m_ref, l);
+        else
+          softmax_block<D, BN, false>(tS, tO, j, kbase, p.Lk, bias, p.scale_log2, m_ref, l);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[t]);
+      }
+      // ---- epilogue: O / l -> bf16 -> global ----
+      mbar_wait(&o_done[t], it & 1);
       tc_fence_after();
-      const int kbase = j * kAttnBN;
-      // full blocks without a bias take the lean path; the tail block / biased blocks take the predicated one
-      if (kMasked && (bias != nullptr || kbase + kAttnBN > p.Lk))
-        softmax_block<D, true, kEarlyS>(tS, tP, tO, j, kbase, p.Lk, bias, p.scale_log2, m_ref, l, s_free, pv_done, lane);
-      else
-        softmax_block<D, false, kEarlyS>(tS, tP, tO, j, kbase, p.Lk, bias, p.scale_log2, m_ref, l, s_free, pv_done, lane);
-      tmem_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
-    }
-
-    // ---- epilogue: O / l -> bf16 -> global ----
-    mbar_wait(o_done, 0);
-    tc_fence_after();
-    const float inv = (l > 0.f) ? __fdividef(1.0f, l) : 0.f;
-    const int q = q0 + row;
-    __nv_bfloat16* orow = p.out + static_cast<long long>(b) * p.out_bs + static_cast<long long>(q) * p.out_ld + h * D;
+      const float inv = (l > 0.f) ? __fdividef(1.0f, l) : 0.f;
+      const int q = qp * 256 + t * kAttnBM + row;
+      __nv_bfloat16* orow = p.out + static_cast<long long>(b) * p.out_bs + static_cast<long long>(q) * p.out_ld + h * D;
 #pragma unroll 1
-    for (int c = 0; c < D; c += 32) {
-      uint32_t o[32];
-      tmem_ld32(tO + c, o);
-      tmem_wait_ld();
-      if (q < p.Lq) {
+      for (int c = 0; c < D; c += 32) {
+        uint32_t o[32];
+        tmem_ld32(tO + c, o);
+        tmem_wait_ld();
+        if (q < p.Lq) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          *reinterpret_cast<uint4*>(orow + c + i) = make_uint4(
-              pack_bf16(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv),
-              pack_bf16(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv),
-              pack_bf16(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv),
-              pack_bf16(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv));
+          for (int i = 0; i < 32; i += 8) {
+            *reinterpret_cast<uint4*>(orow + c + i) = make_uint4(
+                pack_bf16(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv),
+                pack_bf16(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv),
+                pack_bf16(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv),
+                pack_bf16(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv));
+          }
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_free[t]);
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
-    tmem_dealloc<kTmemCols>(tmem_base);
+    tmem_dealloc<C::kTmemCols>(tmem_base);
   }
 }
 

@@ -2,6 +2,7 @@
 #include "../../include/ltx_b200.h"
 
 #include <atomic>
+#include <cstdlib>
 
 #include "attention.cuh"
 #include "common.cuh"
@@ -162,26 +163,37 @@ extern "C" int ltxb200_conv3d_bf16(const void* x, const void* w, const void* bia
 // ------------------------------------------------------------------------------------------
 // attention
 // ------------------------------------------------------------------------------------------
-static int make_qkv_tmap(CUtensorMap* m, const void* base, int B, int H, int L, int d, int64_t ld, int64_t bs) {
+static int make_qkv_tmap(CUtensorMap* m, const void* base, int B, int H, int L, int d, int64_t ld, int64_t bs, int box_rows) {
   uint64_t dims[4] = {static_cast<uint64_t>(d), static_cast<uint64_t>(H), static_cast<uint64_t>(L), static_cast<uint64_t>(B)};
   uint64_t str[3] = {static_cast<uint64_t>(d) * 2, static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(bs) * 2};
-  uint32_t box[4] = {64, 1, 128, 1};
+  uint32_t box[4] = {64, 1, static_cast<uint32_t>(box_rows), 1};
   return make_tmap_bf16(m, base, 4, dims, str, box);
 }
 
-template <int D, bool kMasked>
+template <int D, int BN, int kCtasPerSm, bool kMasked>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                        cudaStream_t st) {
-  using S = AttnSmem<D>;
+  using C = AttnCfg<D, BN, kCtasPerSm>;
   static bool configured = false;
-  auto kern = attention_fwd_kernel<D, kMasked>;
+  auto kern = attention_fwd_kernel<D, BN, kCtasPerSm, kMasked>;
   if (!configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal) != cudaSuccess) return kErrCuda;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal) != cudaSuccess) return kErrCuda;
     configured = true;
   }
-  dim3 grid((p.Lq + kAttnBM - 1) / kAttnBM, p.H, p.B);
-  kern<<<grid, kAttnThreads, S::kTotal, st>>>(tq, tk, tv, p);
+  const int cap = num_sms() * kCtasPerSm;
+  const int grid = p.total < cap ? p.total : cap;          // persistent: each CTA walks work items round-robin
+  kern<<<grid, C::kThreads, C::kTotal, st>>>(tq, tk, tv, p);
   return launch_status();
+}
+
+// d=64 key-block size: 64 (two co-resident CTAs, 16 softmax warps per SM) unless LTXB200_ATTN64_BN=128
+static int attn64_bn() {
+  static int bn = 0;
+  if (bn == 0) {
+    const char* e = getenv("LTXB200_ATTN64_BN");
+    bn = (e && atoi(e) == 128) ? 128 : 64;
+  }
+  return bn;
 }
 
 extern "C" int ltxb200_attention_bf16(const void* q, int64_t ldq, int64_t bsq, const void* k, int64_t ldk, int64_t bsk,
@@ -193,9 +205,10 @@ extern "C" int ltxb200_attention_bf16(const void* q, int64_t ldq, int64_t bsq, c
   if (!aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(out) || (ldq & 7) || (ldk & 7) || (ldv & 7) ||
       (ldo & 7) || (bsq & 7) || (bsk & 7) || (bsv & 7) || (bso & 7))
     return kErrBadAlign;
+  const int BN = (d == 64) ? attn64_bn() : 128;
   CUtensorMap tq, tk, tv;
-  if (make_qkv_tmap(&tq, q, B, H, Lq, d, ldq, bsq) || make_qkv_tmap(&tk, k, B, H, Lk, d, ldk, bsk) ||
-      make_qkv_tmap(&tv, v, B, H, Lk, d, ldv, bsv))
+  if (make_qkv_tmap(&tq, q, B, H, Lq, d, ldq, bsq, kAttnBM) || make_qkv_tmap(&tk, k, B, H, Lk, d, ldk, bsk, BN) ||
+      make_qkv_tmap(&tv, v, B, H, Lk, d, ldv, bsv, BN))
     return kErrTensorMap;
   AttnParams p{};
   p.B = B; p.H = H; p.Lq = Lq; p.Lk = Lk;
@@ -203,10 +216,17 @@ extern "C" int ltxb200_attention_bf16(const void* q, int64_t ldq, int64_t bsq, c
   p.scale_log2 = sc * 1.4426950408889634f;
   p.key_bias = key_bias;
   p.out = static_cast<__nv_bfloat16*>(out); p.out_ld = ldo; p.out_bs = bso;
+  p.pairs = (Lq + 2 * kAttnBM - 1) / (2 * kAttnBM);
+  const long long total = static_cast<long long>(B) * H * p.pairs;
+  if (total > 0x7fffffffLL) return kErrBadShape;
+  p.total = static_cast<int>(total);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const bool masked = (key_bias != nullptr) || (Lk % kAttnBN != 0);
-  if (d == 64) return masked ? launch_attn<64, true>(tq, tk, tv, p, st) : launch_attn<64, false>(tq, tk, tv, p, st);
-  return masked ? launch_attn<128, true>(tq, tk, tv, p, st) : launch_attn<128, false>(tq, tk, tv, p, st);
+  const bool masked = (key_bias != nullptr) || (Lk % BN != 0);
+  if (d == 64 && BN == 64)
+    return masked ? launch_attn<64, 64, 2, true>(tq, tk, tv, p, st) : launch_attn<64, 64, 2, false>(tq, tk, tv, p, st);
+  if (d == 64)
+    return masked ? launch_attn<64, 128, 1, true>(tq, tk, tv, p, st) : launch_attn<64, 128, 1, false>(tq, tk, tv, p, st);
+  return masked ? launch_attn<128, 128, 1, true>(tq, tk, tv, p, st) : launch_attn<128, 128, 1, false>(tq, tk, tv, p, st);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -29,7 +29,18 @@ if which in ("all", "attn"):
     qkv = torch.randn(B, N, 3 * H * d, device=dev).bfloat16()
     q, k, v = [qkv[:, :, i * H * d:(i + 1) * H * d].unflatten(-1, (H, d)) for i in range(3)]
     timeit("attention d64 B3 N6144 H32", lambda: ops.attention(q, k, v), 4.0 * B * H * N * N * d)
+if which in ("all", "attn", "xattn"):
+    B, N, H, d, L = 3, 6144, 32, 64, 256
+    q = torch.randn(B, N, H, d, device=dev).bfloat16()
+    kv = torch.randn(B, L, 2 * H * d, device=dev).bfloat16()
+    k, v = kv[:, :, :H * d].unflatten(-1, (H, d)), kv[:, :, H * d:].unflatten(-1, (H, d))
+    bias = torch.zeros(B, L, device=dev)
+    timeit("cross-attention d64 B3 N6144 L256 bias", lambda: ops.attention(q, k, v, key_bias=bias), 4.0 * B * H * N * L * d)
+    timeit("cross-attention d64 B3 N6144 L256 nobias", lambda: ops.attention(q, k, v), 4.0 * B * H * N * L * d)
 if which in ("all", "attn128"):
+    B, N, H, d = 1, 32760, 12, 128
+    q, k, v = [torch.randn(B, N, H, d, device=dev).bfloat16() for _ in range(3)]
+    timeit("attention d128 B1 N32760 H12 (Wan-1.3B)", lambda: ops.attention(q, k, v), 4.0 * B * H * N * N * d)
     B, N, H, d = 1, 8192, 12, 128
     q, k, v = [torch.randn(B, N, H, d, device=dev).bfloat16() for _ in range(3)]
     timeit("attention d128 B1 N8192 H12", lambda: ops.attention(q, k, v), 4.0 * B * H * N * N * d)

@@ -70,7 +70,7 @@ def ref_attn(q, k, v, bias=None):
 
 @pytest.mark.parametrize("d", [64, 128])
 @pytest.mark.parametrize("B,H,Lq,Lk", [(1, 2, 128, 128), (2, 3, 256, 384), (1, 2, 300, 333), (1, 4, 1024, 1000),
-                                       (2, 2, 130, 77)])
+                                       (2, 2, 130, 77), (1, 2, 257, 40), (3, 40, 1500, 700), (1, 1, 64, 1)])
 def test_attention(d, B, H, Lq, Lk):
     q, k, v = rnd(B, Lq, H, d, seed=1), rnd(B, Lk, H, d, seed=2), rnd(B, Lk, H, d, seed=3)
     out = ops.attention(q, k, v)
