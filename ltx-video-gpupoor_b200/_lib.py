@@ -8,7 +8,8 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_int64, c_longlong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libltx_b200.so")
+# LTXB200_LIB selects another build of the same ABI (e.g. the -DLTXB200_DEBUG_HANG watchdog build used while developing)
+LIB_PATH = os.environ.get("LTXB200_LIB") or os.path.join(_HERE, "libltx_b200.so")
 
 _lib = None
 

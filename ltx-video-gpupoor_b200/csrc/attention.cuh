@@ -6,18 +6,21 @@
 // column slices of one fused QKV projection.  Reference semantics: utils/attention.py:99-116
 // (sdpa_wrapper) incl. the additive key mask.
 //
-// Structure (persistent, warp-specialised, two query tiles in ping-pong per CTA):
+// Structure (persistent, warp-specialised, two query tiles per CTA, one CTA per SM):
 //   * a CTA walks work items (b, h, 256 query rows) round-robin; each item is two 128-row Q tiles that share
-//     every K/V block brought in by TMA (one producer warp, kStages-deep K and V rings);
-//   * one MMA warp issues, per key block j and tile t:  O_t += P_t(j-1).V(j-1)  then  S_t(j) = Q_t.K(j)^T,
-//     so the tensor pipe works on one tile while the other tile's softmax runs;
-//   * two softmax warpgroups (one per tile, one query row per thread = TMEM lane): the whole S row chunk is read
-//     from TMEM ONCE into registers, row max -> lazy rescale of O (only when the max grows by > 2^8) ->
-//     exp2 -> P (bf16 pairs) written over the first half of the S columns and consumed straight from TMEM as the
-//     A operand of the P.V MMA ("TS" form); V is an MN-major B operand, so nothing is transposed;
+//     every 128-key K/V block brought in by TMA (one producer warp, kStages-deep K and V rings);
+//   * the unit of work is a step n = 2*j + t (key block j, tile t).  S(n) = Q_t.K(j)^T lives in TMEM buffer
+//     n % kSBufs.  One MMA warp issues, in order:  O_t += P(n).V(j)  then  S(n + kSBufs)  into the buffer P(n)
+//     just left.  With kSBufs = 3 (d = 64: 3*128 + 2*64 = 512 columns) the scores of a tile's next block are
+//     computed while its current block is still in the softmax, so the softmax warpgroups never wait for the
+//     tensor pipe; with kSBufs = 2 (d = 128: 2*128 + 2*128 columns) the two tiles ping-pong;
+//   * two softmax warpgroups (one per tile, one query row per thread = TMEM lane): the S row is read from TMEM
+//     ONCE into registers, row max -> lazy rescale of O (only when the max grows by > 2^8) -> exp2 -> P (bf16
+//     pairs) written over the first half of that S buffer and consumed straight from TMEM as the A operand of
+//     the P.V MMA ("TS" form); V is an MN-major B operand, so nothing is transposed;
 //   * the same warpgroups normalise and store O when their tile is finished, while the MMA warp already runs
 //     the next work item's first S blocks.
-// TMEM columns: S_0 | S_1 | O_0 | O_1  (BN, BN, D, D).
+// TMEM columns: S buffers (kSBufs x 128) | O_0 | O_1.
 #pragma once
 #include "common.cuh"
 
@@ -35,19 +38,20 @@ struct AttnParams {
   int total;                     // B * H * pairs work items
 };
 
-constexpr uint32_t next_pow2_u32(uint32_t x) { uint32_t p = 32; while (p < x) p <<= 1; return p; }
+constexpr int kAttnBN = 128;   // keys per block
 
-template <int D, int BN, int kCtasPerSm>
+template <int D>
 struct AttnCfg {
-  static constexpr int kStages = (BN * D * 2 <= 8192) ? 4 : (BN * D * 2 <= 16384 ? 3 : 2);
+  static constexpr int BN = kAttnBN;
+  static constexpr int kSBufs = (D == 64) ? 3 : 2;           // S/P buffers in TMEM, used in rotation by the steps
   static constexpr int kQBytes = kAttnBM * D * 2;            // one Q tile
   static constexpr int kKBytes = BN * D * 2;                 // one K (or V) block
-  static constexpr int kBarBytes = 256;
+  static constexpr int kStages = (D == 64) ? 4 : 2;          // 128 KB of K/V in flight
+  static constexpr int kBarBytes = 512;
   static constexpr int kTotal = 2 * kQBytes + 2 * kStages * kKBytes + kBarBytes + 1024;
-  static constexpr bool kRegRealloc = (kCtasPerSm == 1);     // setmaxnreg: softmax warpgroups take the registers
-  static constexpr int kThreads = kRegRealloc ? 384 : 320;   // 8 softmax warps + TMA warp + MMA warp (+2 idle for WG alignment)
-  static constexpr uint32_t kTmemCols = next_pow2_u32(2 * BN + 2 * D);
-  static constexpr int kSoftmaxRegs = 208, kOtherRegs = 64;
+  static constexpr int kThreads = 384;                       // 8 softmax warps + TMA warp + MMA warp + 2 idle (warpgroup alignment)
+  static constexpr uint32_t kTmemCols = 512;                 // kSBufs*BN + 2*D = 512 for both head dims
+  static constexpr int kSoftmaxRegs = 208, kOtherRegs = 64;  // setmaxnreg: the softmax warpgroups take the registers
 };
 
 DEVI float fmax3(float a, float b, float c) {
@@ -56,14 +60,59 @@ DEVI float fmax3(float a, float b, float c) {
   return d;
 }
 
-// One key block of the online softmax for one query row (one thread).  S (fp32, BN columns at tS) -> registers
-// (single TMEM pass) -> P (bf16 pairs, BN/2 columns written back at tS).  m_ref / l: running reference max
-// (log2 domain) and row sum.  O at tO is rescaled only when the max moved by more than 2^8 (warp-uniform branch,
-// the TMEM ops are warp-collective).  All previous P.V MMAs of this tile have retired when S(j) is visible
-// (same in-order pipe, the S commit covers them), so O may be touched here.
+// Lazy rescale of O_t and l: the reference max moves to m_new only for rows whose running max outgrew it by more
+// than 2^8 (warp-uniform branch: the TMEM ops are warp-collective), after the previous block's P.V MMA has retired.
+template <int D>
+DEVI void rescale_o(uint32_t tO, bool need, float m_new, float& m_ref, float& l, uint64_t* pv_done, uint32_t pv_parity) {
+  if (__any_sync(0xffffffffu, need)) {
+    mbar_wait(pv_done, pv_parity);
+    tc_fence_after();
+    const float alpha = need ? fast_exp2(m_ref - m_new) : 1.0f;
+    if (need) m_ref = m_new;
+    l *= alpha;
+#pragma unroll 1
+    for (int c = 0; c < D; c += 16) {
+      uint32_t o[16];
+      tmem_ld16(tO + c, o);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+      tmem_st16(tO + c, o);
+    }
+  }
+}
+
+// exp2 of 32 scores (already in registers) -> 16 packed bf16 pairs at tP, partial row sums in ls[4]
+template <bool kScaled>
+DEVI void exp_chunk(const uint32_t* v, float sc, float neg_m, uint32_t tP, float (&ls)[4]) {
+  uint32_t pk[16];
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    float e0, e1, e2, e3;
+    if (kScaled) {       // v already holds scale*s + bias
+      e0 = fast_exp2(__uint_as_float(v[i]) + neg_m);
+      e1 = fast_exp2(__uint_as_float(v[i + 1]) + neg_m);
+      e2 = fast_exp2(__uint_as_float(v[i + 2]) + neg_m);
+      e3 = fast_exp2(__uint_as_float(v[i + 3]) + neg_m);
+    } else {
+      e0 = fast_exp2(fmaf(__uint_as_float(v[i]), sc, neg_m));
+      e1 = fast_exp2(fmaf(__uint_as_float(v[i + 1]), sc, neg_m));
+      e2 = fast_exp2(fmaf(__uint_as_float(v[i + 2]), sc, neg_m));
+      e3 = fast_exp2(fmaf(__uint_as_float(v[i + 3]), sc, neg_m));
+    }
+    ls[0] += e0; ls[1] += e1; ls[2] += e2; ls[3] += e3;
+    pk[i >> 1] = pack_bf16(e0, e1);
+    pk[(i >> 1) + 1] = pack_bf16(e2, e3);
+  }
+  tmem_st16(tP, pk);
+}
+
+// One key block of the online softmax for one query row (one thread): S (fp32, BN columns at tS) -> registers in
+// ONE TMEM pass -> block max -> (lazy) rescale -> exp2 -> P (bf16 pairs) over the first BN/2 columns of tS.
+// m_ref: reference max of the row (log2 domain), m_run: largest score seen so far, l: row sum relative to m_ref.
 template <int D, int BN, bool kPredicated>
-DEVI void softmax_block(uint32_t tS, uint32_t tO, int j, int kbase, int Lk, const float* bias, float sc,
-                        float& m_ref, float& l) {
+DEVI void softmax_block(uint32_t tS, uint32_t tO, bool first, int kbase, int Lk, const float* bias, float sc,
+                              float& m_ref, float& m_run, float& l, uint64_t* pv_done, uint32_t pv_parity) {
   const float kLog2e = 1.4426950408889634f;
   uint32_t v[BN];
   float mx0 = -INFINITY, mx1 = -INFINITY;
@@ -92,61 +141,30 @@ DEVI void softmax_block(uint32_t tS, uint32_t tO, int j, int kbase, int Lk, cons
   }
   float m_blk = fmaxf(mx0, mx1);
   if (!kPredicated) m_blk *= sc;                 // scale > 0: max commutes with the scaling
-  bool need = false;
-  if (j == 0) m_ref = (m_blk == -INFINITY) ? 0.f : m_blk;
-  else need = m_blk > m_ref + 8.0f;
-  if (__any_sync(0xffffffffu, need)) {
-    const float m_new = need ? m_blk : m_ref;
-    const float alpha = fast_exp2(m_ref - m_new);
-    m_ref = m_new;
-    l *= alpha;
-#pragma unroll 1
-    for (int c = 0; c < D; c += 16) {
-      uint32_t o[16];
-      tmem_ld16(tO + c, o);
-      tmem_wait_ld();
-#pragma unroll
-      for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-      tmem_st16(tO + c, o);
-    }
+  if (first) {
+    m_run = m_blk;
+    m_ref = (m_blk == -INFINITY) ? 0.f : m_blk;
+  } else {
+    m_run = fmaxf(m_run, m_blk);
+    rescale_o<D>(tO, m_run > m_ref + 8.0f, m_run, m_ref, l, pv_done, pv_parity);
   }
-  float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-  const float neg_m = -m_ref;
+  float ls[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int c = 0; c < BN; c += 32) {
-    uint32_t pk[16];
-#pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      float e0, e1, e2, e3;
-      if (kPredicated) {
-        e0 = fast_exp2(__uint_as_float(v[c + i]) + neg_m);
-        e1 = fast_exp2(__uint_as_float(v[c + i + 1]) + neg_m);
-        e2 = fast_exp2(__uint_as_float(v[c + i + 2]) + neg_m);
-        e3 = fast_exp2(__uint_as_float(v[c + i + 3]) + neg_m);
-      } else {
-        e0 = fast_exp2(fmaf(__uint_as_float(v[c + i]), sc, neg_m));
-        e1 = fast_exp2(fmaf(__uint_as_float(v[c + i + 1]), sc, neg_m));
-        e2 = fast_exp2(fmaf(__uint_as_float(v[c + i + 2]), sc, neg_m));
-        e3 = fast_exp2(fmaf(__uint_as_float(v[c + i + 3]), sc, neg_m));
-      }
-      l0 += e0; l1 += e1; l2 += e2; l3 += e3;
-      pk[i >> 1] = pack_bf16(e0, e1);
-      pk[(i >> 1) + 1] = pack_bf16(e2, e3);
-    }
-    tmem_st16(tS + (c >> 1), pk);
-  }
-  l += (l0 + l1) + (l2 + l3);
+  for (int c = 0; c < BN; c += 32) exp_chunk<kPredicated>(&v[c], sc, -m_ref, tS + (c >> 1), ls);
+  l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
 }
 
-template <int D, int BN, int kCtasPerSm, bool kMasked>
-__global__ void __launch_bounds__((AttnCfg<D, BN, kCtasPerSm>::kThreads), kCtasPerSm)
+template <int D, bool kMasked>
+__global__ void __launch_bounds__(AttnCfg<D>::kThreads, 1)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
-  using C = AttnCfg<D, BN, kCtasPerSm>;
+  using C = AttnCfg<D>;
+  constexpr int BN = C::BN;
   constexpr int kStages = C::kStages;
+  constexpr int kSBufs = C::kSBufs;
   constexpr int kChunks = D / 64;                    // 64-wide (128 B) column chunks per row
   constexpr int kTmaWarp = 8, kMmaWarp = 9;
-  constexpr uint32_t kColS0 = 0, kColO0 = 2 * BN;
+  constexpr uint32_t kColS0 = 0, kColO0 = kSBufs * BN;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -154,20 +172,22 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint8_t* sK = sQ + 2 * C::kQBytes;                  // [kStages][BN][D]
   uint8_t* sV = sK + kStages * C::kKBytes;            // [kStages][BN][D]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kStages * C::kKBytes);
-  uint64_t* q_full = bars;                // [2]  TMA -> MMA
-  uint64_t* q_empty = q_full + 2;         // [2]  last S of the item issued: Q tile may be overwritten
+  uint64_t* q_full = bars;                // [2]       TMA -> MMA
+  uint64_t* q_empty = q_full + 2;         // [2]       last S of the item issued: Q tile may be overwritten
   uint64_t* k_full = q_empty + 2;         // [kStages]
   uint64_t* k_empty = k_full + kStages;
   uint64_t* v_full = k_empty + kStages;
   uint64_t* v_empty = v_full + kStages;
-  uint64_t* s_full = v_empty + kStages;   // [2]  S_t(j) complete (and every earlier MMA of the pipe)
-  uint64_t* p_full = s_full + 2;          // [2]  P_t(j) written (4 warps arrive)
-  uint64_t* o_done = p_full + 2;          // [2]  last P.V of the item retired
-  uint64_t* o_free = o_done + 2;          // [2]  epilogue has read O_t (4 warps arrive)
+  uint64_t* s_full = v_empty + kStages;   // [kSBufs]  S(n) complete in buffer n % kSBufs
+  uint64_t* p_full = s_full + kSBufs;     // [kSBufs]  P(n) written over it (4 warps arrive)
+  uint64_t* pv_done = p_full + kSBufs;    // [2]       P.V of tile t's block retired (lazy-rescale guard)
+  uint64_t* o_done = pv_done + 2;         // [2]       last P.V of the item retired
+  uint64_t* o_free = o_done + 2;          // [2]       epilogue has read O_t (4 warps arrive)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nblk = (p.Lk + BN - 1) / BN;
+  const int nsteps = 2 * nblk;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ);
@@ -176,10 +196,13 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     for (int t = 0; t < 2; ++t) {
       mbar_init(&q_full[t], 1);
       mbar_init(&q_empty[t], 1);
-      mbar_init(&s_full[t], 1);
-      mbar_init(&p_full[t], 4);
+      mbar_init(&pv_done[t], 1);
       mbar_init(&o_done[t], 1);
       mbar_init(&o_free[t], 4);
+    }
+    for (int i = 0; i < kSBufs; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
     }
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&k_full[i], 1);
@@ -196,8 +219,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp >= 8) {
-    if (C::kRegRealloc) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(C::kOtherRegs));
-    if (warp == kTmaWarp && lane == 0) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(C::kOtherRegs));
+    if (warp == kTmaWarp && elect_one()) {
       // ================= TMA producer =================
       uint32_t kc = 0;
       int it = 0;
@@ -226,7 +249,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             tma_load_4d(sV + st * C::kKBytes + c * (BN * 128), &tmV, &v_full[st], c * 64, h, j * BN, b);
         }
       }
-    } else if (warp == kMmaWarp && lane == 0) {
+    } else if (warp == kMmaWarp && elect_one()) {
       // ================= MMA issuer =================
       constexpr uint32_t idesc_s = umma_idesc_bf16(kAttnBM, BN, 0, 0);   // S = Q K^T  (both K-major)
       constexpr uint32_t idesc_o = umma_idesc_bf16(kAttnBM, D, 0, 1);    // O += P V   (V is MN-major)
@@ -235,98 +258,88 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const uint64_t qdesc = umma_smem_desc_sw128(smem_u32(sQ), 16, 1024);
       const uint64_t kdesc = umma_smem_desc_sw128(smem_u32(sK), 16, 1024);
       const uint64_t vdesc = umma_smem_desc_sw128(smem_u32(sV), BN * 128, 1024);
-      auto issue_s = [&](int t, int stage) {
+      uint32_t kc = 0, vc = 0;       // K / V ring counters (consumption order)
+      uint32_t N0 = 0;               // global step counter at the start of the item
+      int it = 0;
+      // S(m), m = item-local step: tile m&1, key block m>>1, TMEM buffer (N0+m) % kSBufs
+      auto issue_s = [&](int m) {
+        const int t = m & 1, j = m >> 1;
+        const int st = kc % kStages;
+        if (t == 0) mbar_wait(&k_full[st], (kc / kStages) & 1);
+        if (j == 0) mbar_wait(&q_full[t], it & 1);
+        tc_fence_after();
+        const uint32_t buf = (N0 + m) % kSBufs;
         const uint64_t qa = qdesc + static_cast<uint32_t>(t * (C::kQBytes >> 4));
-        const uint64_t ka = kdesc + static_cast<uint32_t>(stage * (C::kKBytes >> 4));
-        const uint32_t ts = tmem_base + kColS0 + t * BN;
+        const uint64_t ka = kdesc + static_cast<uint32_t>(st * (C::kKBytes >> 4));
+        const uint32_t ts = tmem_base + kColS0 + buf * BN;
 #pragma unroll
         for (int ks = 0; ks < D / 16; ++ks) {
           const uint32_t offa = ((ks >> 2) * (kAttnBM * 128) + (ks & 3) * 32) >> 4;
           const uint32_t offb = ((ks >> 2) * (BN * 128) + (ks & 3) * 32) >> 4;
           umma_ss(ts, qa + offa, ka + offb, idesc_s, ks ? 1u : 0u);
         }
+        umma_commit(&s_full[buf]);
+        if (j + 1 == nblk) umma_commit(&q_empty[t]);
+        if (t == 1) { umma_commit(&k_empty[st]); ++kc; }
       };
-      auto issue_pv = [&](int t, int stage, bool acc) {
-        // B = V[16 keys (K), D (N)], N contiguous: 8-key groups 1024 B apart (SBO), 64-col groups one chunk apart (LBO)
-        const uint64_t va = vdesc + static_cast<uint32_t>(stage * (C::kKBytes >> 4));
-        const uint32_t to = tmem_base + kColO0 + t * D, tp = tmem_base + kColS0 + t * BN;
-#pragma unroll
-        for (int ks = 0; ks < BN / 16; ++ks)
-          umma_ts(to, tp + ks * 8, va + static_cast<uint32_t>(ks * (2048 >> 4)), idesc_o, (acc || ks) ? 1u : 0u);
-      };
-      uint32_t kc = 0, vc = 0;       // K / V ring counters
-      uint32_t pc = 0;               // p_full phase counter (same for both tiles)
-      int it = 0;
       for (int w = blockIdx.x; w < p.total; w += gridDim.x, ++it) {
-        {  // S_t(0)
-          const int st = kc % kStages;
-          mbar_wait(&k_full[st], (kc / kStages) & 1);
 #pragma unroll 1
-          for (int t = 0; t < 2; ++t) {
-            mbar_wait(&q_full[t], it & 1);
-            tc_fence_after();
-            issue_s(t, st);
-            umma_commit(&s_full[t]);
-            if (nblk == 1) umma_commit(&q_empty[t]);
-          }
-          umma_commit(&k_empty[st]);
-          ++kc;
-        }
-        // step = (key block j, tile t): O_t += P_t(j).V(j), then S_t(j+1) = Q_t.K(j+1)^T
+        for (int m = 0; m < kSBufs && m < nsteps; ++m) issue_s(m);
+        // step n: O_t += P(n).V(j), then S(n + kSBufs) into the buffer P(n) leaves
 #pragma unroll 1
-        for (int step = 0; step < 2 * nblk; ++step) {
-          const int j = step >> 1, t = step & 1;
-          const int sv = vc % kStages, sk = kc % kStages;
-          mbar_wait(&p_full[t], pc & 1);
+        for (int n = 0; n < nsteps; ++n) {
+          const int t = n & 1, j = n >> 1;
+          const int sv = vc % kStages;
+          const uint32_t N = N0 + n, buf = N % kSBufs;
+          mbar_wait(&p_full[buf], (N / kSBufs) & 1);
           if (j == 0) mbar_wait(&o_free[t], (it & 1) ^ 1);
           if (t == 0) mbar_wait(&v_full[sv], (vc / kStages) & 1);
           tc_fence_after();
-          issue_pv(t, sv, j > 0);
-          if (t == 1) umma_commit(&v_empty[sv]);
-          if (j + 1 < nblk) {
-            if (t == 0) { mbar_wait(&k_full[sk], (kc / kStages) & 1); tc_fence_after(); }
-            issue_s(t, sk);
-            umma_commit(&s_full[t]);
-            if (j + 2 == nblk) umma_commit(&q_empty[t]);
-            if (t == 1) umma_commit(&k_empty[sk]);
-          } else {
-            umma_commit(&o_done[t]);
+          {
+            // B = V[16 keys (K), D (N)], N contiguous: 8-key groups 1024 B apart (SBO), 64-col groups one chunk apart (LBO)
+            const uint64_t va = vdesc + static_cast<uint32_t>(sv * (C::kKBytes >> 4));
+            const uint32_t to = tmem_base + kColO0 + t * D, tp = tmem_base + kColS0 + buf * BN;
+#pragma unroll
+            for (int ks = 0; ks < BN / 16; ++ks)
+              umma_ts(to, tp + ks * 8, va + static_cast<uint32_t>(ks * (2048 >> 4)), idesc_o, (j > 0 || ks) ? 1u : 0u);
           }
-          if (t == 1) {
-            ++vc; ++pc;
-            if (j + 1 < nblk) ++kc;
-          }
+          umma_commit(&pv_done[t]);
+          if (t == 1) { umma_commit(&v_empty[sv]); ++vc; }
+          if (j + 1 == nblk) umma_commit(&o_done[t]);
+          if (n + kSBufs < nsteps) issue_s(n + kSBufs);
         }
+        N0 += nsteps;
       }
     }
   } else {
     // ================= softmax / correction / epilogue: warpgroup t owns query tile t =================
-    if (C::kRegRealloc) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(C::kSoftmaxRegs));
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(C::kSoftmaxRegs));
     const int t = warp >> 2;
     const int sub = warp & 3;
     const int row = sub * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(sub * 32) << 16;
-    const uint32_t tS = tmem_base + kColS0 + t * BN + lane_addr;
     const uint32_t tO = tmem_base + kColO0 + t * D + lane_addr;
-    uint32_t sc_cnt = 0;
+    uint32_t G = 0;                  // global key-block counter of this tile; its step is N = 2*G + t
     int it = 0;
     for (int w = blockIdx.x; w < p.total; w += gridDim.x, ++it) {
       const int qp = w % p.pairs, bh = w / p.pairs, h = bh % p.H, b = bh / p.H;
       const float* bias = p.key_bias ? p.key_bias + static_cast<long long>(b) * p.Lk : nullptr;
-      float m_ref = 0.f, l = 0.f;
-      for (int j = 0; j < nblk; ++j, ++sc_cnt) {
-        mbar_wait(&s_full[t], sc_cnt & 1);
+      float m_ref = 0.f, m_run = 0.f, l = 0.f;
+      for (int j = 0; j < nblk; ++j, ++G) {
+        const uint32_t N = 2 * G + t, buf = N % kSBufs;
+        mbar_wait(&s_full[buf], (N / kSBufs) & 1);
         tc_fence_after();
         const int kbase = j * BN;
+        const uint32_t tS = tmem_base + kColS0 + buf * BN + lane_addr;
         // full blocks without a bias take the lean path; the tail block / biased blocks take the predicated one
         if (kMasked && (bias != nullptr || kbase + BN > p.Lk))
-          softmax_block<D, BN, true>(tS, tO, j, kbase, p.Lk, bias, p.scale_log2, m_ref, l);
+          softmax_block<D, BN, true>(tS, tO, j == 0, kbase, p.Lk, bias, p.scale_log2, m_ref, m_run, l, &pv_done[t], (G - 1) & 1);
         else
-          softmax_block<D, BN, false>(tS, tO, j, kbase, p.Lk, bias, p.scale_log2, m_ref, l);
+          softmax_block<D, BN, false>(tS, tO, j == 0, kbase, p.Lk, bias, p.scale_log2, m_ref, m_run, l, &pv_done[t], (G - 1) & 1);
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[t]);
+        if (lane == 0) mbar_arrive(&p_full[buf]);
       }
       // ---- epilogue: O / l -> bf16 -> global ----
       mbar_wait(&o_done[t], it & 1);
@@ -359,6 +372,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   tc_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) {
+    __syncwarp();
     tc_fence_after();
     tmem_dealloc<C::kTmemCols>(tmem_base);
   }

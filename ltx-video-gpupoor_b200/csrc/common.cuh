@@ -5,6 +5,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #define DEVI __device__ __forceinline__
 
@@ -100,14 +101,32 @@ DEVI bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+#ifdef LTXB200_DEBUG_HANG
+// debug build: a wait that does not complete within ~1 s reports who is stuck and traps instead of hanging the GPU
+#define mbar_wait(bar, parity) ::b200::mbar_wait_dbg((bar), (parity), __LINE__)
+DEVI void mbar_wait_dbg(uint64_t* bar, uint32_t parity, int line) {
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 2000000000LL) {
+      printf("HANG: block %d thread %d line %d bar@%u parity %u\n", blockIdx.x, threadIdx.x, line, smem_u32(bar), parity);
+      __trap();
+    }
+  }
+}
+#else
 DEVI void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+#endif
 // for single-thread producers that wait long: sleep between probes so they do not eat issue slots
+#ifdef LTXB200_DEBUG_HANG
+#define mbar_wait_backoff(bar, parity) ::b200::mbar_wait_dbg((bar), (parity), __LINE__)
+#else
 DEVI void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) __nanosleep(64);
 }
+#endif
 
 // ------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor) loads: global -> shared, completion on an mbarrier

@@ -104,7 +104,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0) {
+    if (elect_one()) {     // elect.sync (not lane == 0): ptxas then knows a single lane runs this and issues the
+                           // uniform-datapath TMA / MMA instructions directly instead of through per-lane ELECT loops
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -156,7 +157,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
           const uint32_t sb = sa + S::kStageBytesA;
 #pragma unroll

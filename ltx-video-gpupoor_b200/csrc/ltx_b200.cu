@@ -170,30 +170,19 @@ static int make_qkv_tmap(CUtensorMap* m, const void* base, int B, int H, int L, 
   return make_tmap_bf16(m, base, 4, dims, str, box);
 }
 
-template <int D, int BN, int kCtasPerSm, bool kMasked>
+template <int D, bool kMasked>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                        cudaStream_t st) {
-  using C = AttnCfg<D, BN, kCtasPerSm>;
+  using C = AttnCfg<D>;
   static bool configured = false;
-  auto kern = attention_fwd_kernel<D, BN, kCtasPerSm, kMasked>;
+  auto kern = attention_fwd_kernel<D, kMasked>;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal) != cudaSuccess) return kErrCuda;
     configured = true;
   }
-  const int cap = num_sms() * kCtasPerSm;
-  const int grid = p.total < cap ? p.total : cap;          // persistent: each CTA walks work items round-robin
+  const int grid = p.total < num_sms() ? p.total : num_sms();   // persistent: each CTA walks work items round-robin
   kern<<<grid, C::kThreads, C::kTotal, st>>>(tq, tk, tv, p);
   return launch_status();
-}
-
-// d=64 key-block size: 64 (two co-resident CTAs, 16 softmax warps per SM) unless LTXB200_ATTN64_BN=128
-static int attn64_bn() {
-  static int bn = 0;
-  if (bn == 0) {
-    const char* e = getenv("LTXB200_ATTN64_BN");
-    bn = (e && atoi(e) == 128) ? 128 : 64;
-  }
-  return bn;
 }
 
 extern "C" int ltxb200_attention_bf16(const void* q, int64_t ldq, int64_t bsq, const void* k, int64_t ldk, int64_t bsk,
@@ -205,7 +194,7 @@ extern "C" int ltxb200_attention_bf16(const void* q, int64_t ldq, int64_t bsq, c
   if (!aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(out) || (ldq & 7) || (ldk & 7) || (ldv & 7) ||
       (ldo & 7) || (bsq & 7) || (bsk & 7) || (bsv & 7) || (bso & 7))
     return kErrBadAlign;
-  const int BN = (d == 64) ? attn64_bn() : 128;
+  const int BN = kAttnBN;
   CUtensorMap tq, tk, tv;
   if (make_qkv_tmap(&tq, q, B, H, Lq, d, ldq, bsq, kAttnBM) || make_qkv_tmap(&tk, k, B, H, Lk, d, ldk, bsk, BN) ||
       make_qkv_tmap(&tv, v, B, H, Lk, d, ldv, bsv, BN))
@@ -222,11 +211,8 @@ extern "C" int ltxb200_attention_bf16(const void* q, int64_t ldq, int64_t bsq, c
   p.total = static_cast<int>(total);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool masked = (key_bias != nullptr) || (Lk % BN != 0);
-  if (d == 64 && BN == 64)
-    return masked ? launch_attn<64, 64, 2, true>(tq, tk, tv, p, st) : launch_attn<64, 64, 2, false>(tq, tk, tv, p, st);
-  if (d == 64)
-    return masked ? launch_attn<64, 128, 1, true>(tq, tk, tv, p, st) : launch_attn<64, 128, 1, false>(tq, tk, tv, p, st);
-  return masked ? launch_attn<128, 128, 1, true>(tq, tk, tv, p, st) : launch_attn<128, 128, 1, false>(tq, tk, tv, p, st);
+  if (d == 64) return masked ? launch_attn<64, true>(tq, tk, tv, p, st) : launch_attn<64, false>(tq, tk, tv, p, st);
+  return masked ? launch_attn<128, true>(tq, tk, tv, p, st) : launch_attn<128, false>(tq, tk, tv, p, st);
 }
 
 // ------------------------------------------------------------------------------------------
