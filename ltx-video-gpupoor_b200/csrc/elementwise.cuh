@@ -17,13 +17,30 @@ DEVI void store8(__nv_bfloat16* p, const float (&f)[8]) {
   *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
 }
 
+// packed bf16x2 helpers: the reference's in-place bf16 tensor ops (x *= a; x += b) each round once to bf16, which is
+// exactly what HMUL2.BF16 / HADD2.BF16 do on two lanes at a time (no F2F round trips through the XU pipe)
+DEVI uint32_t bf2_mul(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hmul2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+DEVI uint32_t bf2_add(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hadd2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+DEVI void unpack8(const uint4& q, float (&f)[8]) {
+  float2 a = unpack_bf16(q.x), b = unpack_bf16(q.y), c = unpack_bf16(q.z), d = unpack_bf16(q.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+DEVI uint4 ldg16(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
 // ------------------------------------------------------------------------------------------
 // norm + AdaLN modulate:  y = norm(x) * (1 + scale[g]) + shift[g]          (g = row / rows_per_group)
 //   kLayerNorm = false: RMSNorm without affine (attention.py:233-251, 314-320; diffusers RMSNorm)
 //   kLayerNorm = true : LayerNorm without affine (transformer3d.py:490-502 ; Wan norm1/norm2)
 //   optional affine weight/bias (Wan norm3, VAE res_x_y norm3) applied before the modulation.
 // x, y: [M, D] bf16 (in-place allowed), scale/shift: row g at (ptr + g*mod_ld), null => no modulation.
-// One warp per row, NV uint4 per lane (D = 256*NV).
+// One warp per row, NV uint4 per lane (D = 256*NV); the row stays packed in registers (read once), every load of
+// the row and of its modulation vectors is issued before the first use.
 // ------------------------------------------------------------------------------------------
 template <int NV, bool kLayerNorm>
 __global__ void __launch_bounds__(128)
@@ -36,42 +53,50 @@ norm_mod_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
   const __nv_bfloat16* xr = x + row * ldx;
-  float v[NV][8];
+  uint4 xv[NV];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) load8(xr + (i * 32 + lane) * 8, v[i]);
+  for (int i = 0; i < NV; ++i) xv[i] = *reinterpret_cast<const uint4*>(xr + (i * 32 + lane) * 8);
+  const long long g = row / rows_per_group;
+  const __nv_bfloat16* sc = scale ? scale + g * mod_ld : nullptr;
+  const __nv_bfloat16* sh = shift ? shift + g * mod_ld : nullptr;
   float sum = 0.f, sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < NV; ++i)
+  for (int i = 0; i < NV; ++i) {
+    float v[8];
+    unpack8(xv[i], v);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { sum += v[i][j]; sq += v[i][j] * v[i][j]; }
+    for (int j = 0; j < 8; ++j) { sum += v[j]; sq += v[j] * v[j]; }
+  }
   float mean = 0.f, rs;
   if (kLayerNorm) {
     mean = warp_sum(sum) * (1.0f / D);
     float var = 0.f;
 #pragma unroll
-    for (int i = 0; i < NV; ++i)
+    for (int i = 0; i < NV; ++i) {
+      float v[8];
+      unpack8(xv[i], v);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; var += d * d; }
+      for (int j = 0; j < 8; ++j) { const float d = v[j] - mean; var += d * d; }
+    }
     rs = rsqrtf(warp_sum(var) * (1.0f / D) + eps);
   } else {
     rs = rsqrtf(warp_sum(sq) * (1.0f / D) + eps);
   }
-  const long long g = row / rows_per_group;
-  const __nv_bfloat16* sc = scale ? scale + g * mod_ld : nullptr;
-  const __nv_bfloat16* sh = shift ? shift + g * mod_ld : nullptr;
   __nv_bfloat16* yr = y + row * ldy;
+  const uint32_t one2 = 0x3f803f80u;           // bf16x2 (1.0, 1.0)
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = (i * 32 + lane) * 8;
-    float o[8];
+    float v[8], o[8];
+    unpack8(xv[i], v);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rs;
+    for (int j = 0; j < 8; ++j) o[j] = (v[j] - mean) * rs;
     if (weight) {
       float w[8];
-      load8(weight + c, w);
+      unpack8(ldg16(weight + c), w);
       if (bias) {
         float bb[8];
-        load8(bias + c, bb);
+        unpack8(ldg16(bias + c), bb);
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = o[j] * w[j] + bb[j];
       } else {
@@ -79,14 +104,15 @@ norm_mod_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
         for (int j = 0; j < 8; ++j) o[j] = bf16r(o[j]) * w[j];
       }
     }
-    if (sc) {
-      float s[8], t[8];
-      load8(sc + c, s);
-      load8(sh + c, t);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = bf16r(bf16r(bf16r(o[j]) * bf16r(1.0f + s[j])) + t[j]);
+    uint4 r = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+    if (sc) {      // bf16( bf16( bf16(o) * bf16(1 + s) ) + t ), the reference's rounding points
+      const uint4 s4 = ldg16(sc + c), t4 = ldg16(sh + c);
+      r.x = bf2_add(bf2_mul(r.x, bf2_add(one2, s4.x)), t4.x);
+      r.y = bf2_add(bf2_mul(r.y, bf2_add(one2, s4.y)), t4.y);
+      r.z = bf2_add(bf2_mul(r.z, bf2_add(one2, s4.z)), t4.z);
+      r.w = bf2_add(bf2_mul(r.w, bf2_add(one2, s4.w)), t4.w);
     }
-    store8(yr + c, o);
+    *reinterpret_cast<uint4*>(yr + c) = r;
   }
 }
 
@@ -95,7 +121,7 @@ norm_mod_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
 // the q and k column slices of a fused QKV buffer (attention.py:1040-1055, 960-975, 477-479).
 //   y = bf16(x * rsqrt(mean(x^2)+eps)) * w ;  out = y*cos + rot(y)*sin,  rot: (2i,2i+1) -> (-y[2i+1], y[2i])
 // cos/sin: [tokens_per_batch, D] bf16 (row = token index within the batch), null => no RoPE.
-// grid.y selects the tensor: 0 = q, 1 = k.
+// grid.y selects the tensor: 0 = q, 1 = k.  All products / sums are bf16x2 ops with the reference's rounding points.
 // ------------------------------------------------------------------------------------------
 template <int NV>
 __global__ void __launch_bounds__(128)
@@ -114,36 +140,37 @@ qk_norm_rope_kernel(__nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict__ k
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
   __nv_bfloat16* xr = base + row * ld;
-  float v[NV][8];
+  uint4 xv[NV];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) load8(xr + (i * 32 + lane) * 8, v[i]);
+  for (int i = 0; i < NV; ++i) xv[i] = *reinterpret_cast<const uint4*>(xr + (i * 32 + lane) * 8);
+  const long long trow = cosT ? static_cast<long long>(row % tokens_per_batch) * D : 0;
   float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < NV; ++i)
+  for (int i = 0; i < NV; ++i) {
+    float v[8];
+    unpack8(xv[i], v);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) sq += v[i][j] * v[i][j];
+    for (int j = 0; j < 8; ++j) sq += v[j] * v[j];
+  }
   const float rs = rsqrtf(warp_sum(sq) * (1.0f / D) + eps);
-  const long long trow = cosT ? static_cast<long long>(row % tokens_per_batch) * D : 0;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = (i * 32 + lane) * 8;
-    float ww[8], o[8];
-    load8(w + c, ww);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = bf16r(bf16r(v[i][j] * rs) * ww[j]);
+    float v[8];
+    unpack8(xv[i], v);
+    const uint4 w4 = ldg16(w + c);
+    uint32_t o[4] = {bf2_mul(pack_bf16(v[0] * rs, v[1] * rs), w4.x), bf2_mul(pack_bf16(v[2] * rs, v[3] * rs), w4.y),
+                     bf2_mul(pack_bf16(v[4] * rs, v[5] * rs), w4.z), bf2_mul(pack_bf16(v[6] * rs, v[7] * rs), w4.w)};
     if (cosT) {
-      float cs[8], sn[8], r[8];
-      load8(cosT + trow + c, cs);
-      load8(sinT + trow + c, sn);
+      const uint4 c4 = ldg16(cosT + trow + c), s4 = ldg16(sinT + trow + c);
+      const uint32_t cs[4] = {c4.x, c4.y, c4.z, c4.w}, sn[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
-      for (int j = 0; j < 8; j += 2) {
-        r[j] = bf16r(bf16r(o[j] * cs[j]) + bf16r(-o[j + 1] * sn[j]));
-        r[j + 1] = bf16r(bf16r(o[j + 1] * cs[j + 1]) + bf16r(o[j] * sn[j + 1]));
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t rot = __byte_perm(o[j], 0, 0x1032) ^ 0x00008000u;     // (-y[2i+1], y[2i])
+        o[j] = bf2_add(bf2_mul(o[j], cs[j]), bf2_mul(rot, sn[j]));
       }
-      store8(xr + c, r);
-    } else {
-      store8(xr + c, o);
     }
+    *reinterpret_cast<uint4*>(xr + c) = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -183,10 +210,13 @@ qk_norm_rope_wan_kernel(__nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = (i * 32 + lane) * 8;
-    float ww[8], o[8];
-    load8(w + c, ww);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = bf16r(bf16r(v[i][j] * rs) * ww[j]);
+    float o[8];
+    {
+      const uint4 w4 = ldg16(w + c);
+      const float (&vv)[8] = v[i];
+      unpack8(make_uint4(bf2_mul(pack_bf16(vv[0] * rs, vv[1] * rs), w4.x), bf2_mul(pack_bf16(vv[2] * rs, vv[3] * rs), w4.y),
+                         bf2_mul(pack_bf16(vv[4] * rs, vv[5] * rs), w4.z), bf2_mul(pack_bf16(vv[6] * rs, vv[7] * rs), w4.w)), o);
+    }
     if (cosT) {
       const int hd = c % head_dim;
       const float4 c0 = *reinterpret_cast<const float4*>(cosT + trow + hd), c1 = *reinterpret_cast<const float4*>(cosT + trow + hd + 4);

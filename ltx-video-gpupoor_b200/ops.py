@@ -155,7 +155,9 @@ def qk_norm_rope(q: Optional[torch.Tensor], k: Optional[torch.Tensor], wq, wk, c
                  tokens_per_batch: int = 0, eps: float = 1e-5):
     """In-place on 2-D row views q [Mq,D], k [Mk,D]."""
     D = (q if q is not None else k).shape[1]
-    with _Prof('qk_norm_rope_bf16', 'byte', (4.0 if cos is None else 8.0) * D * ((q.shape[0] if q is not None else 0) + (k.shape[0] if k is not None else 0))):
+    rows = (q.shape[0] if q is not None else 0) + (k.shape[0] if k is not None else 0)
+    # algorithmic bytes: q/k rows read + written once; the cos/sin tables once per launch (they are shared by the batch)
+    with _Prof('qk_norm_rope_bf16', 'byte', 4.0 * D * rows + (0.0 if cos is None else 4.0 * D * tokens_per_batch)):
         rc = _lib.lib().ltxb200_qk_norm_rope_bf16(
         _p(q), q.stride(0) if q is not None else 0, q.shape[0] if q is not None else 0,
         _p(k), k.stride(0) if k is not None else 0, k.shape[0] if k is not None else 0, D,

@@ -54,3 +54,29 @@ if which in ("all", "gemm"):
     M, N, K = 18432, 6144, 2048
     w3 = torch.randn(N, K, device=dev).bfloat16() * 0.02
     timeit("gemm qkv 18432x6144x2048", lambda: ops.gemm(a, w3, None), 2.0 * M * N * K)
+if which in ("all", "ew"):
+    M, D = 18432, 2048
+    x = torch.randn(M, D, device=dev).bfloat16()
+    ada = torch.randn(3, 6, D, device=dev).bfloat16() * 0.1
+    def timeit_bw(name, fn, nbytes):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / reps
+        print(f"{name}: {ms * 1e3:.1f} us  {nbytes / ms / 1e6:.0f} GB/s", flush=True)
+    sc, sh = ada[:, 0], ada[:, 1]
+    out = torch.empty_like(x)
+    timeit_bw("norm_mod rms+adaln 18432x2048", lambda: ops.norm_mod(x, sc, sh, rows_per_group=6144, out=out), 4.0 * M * D)
+    qkv = torch.randn(M, 3 * D, device=dev).bfloat16()
+    w = torch.randn(D, device=dev).bfloat16()
+    cos = torch.randn(6144, D, device=dev).bfloat16(); sin = torch.randn(6144, D, device=dev).bfloat16()
+    timeit_bw("qk_norm_rope q,k 18432x2048 (in fused qkv)", lambda: ops.qk_norm_rope(qkv[:, :D], qkv[:, D:2 * D], w, w, cos, sin, tokens_per_batch=6144),
+              8.0 * M * D + 4.0 * 6144 * D)
+    q2 = torch.randn(M, D, device=dev).bfloat16()
+    timeit_bw("qk_norm (cross-attn q only) 18432x2048", lambda: ops.qk_norm_rope(q2, None, w, None), 4.0 * M * D)
