@@ -14,6 +14,7 @@
 #ifndef LTX_B200_H_
 #define LTX_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -133,6 +134,34 @@ int ltxb200_pixelnorm_silu_bf16(const void* x, void* y, int64_t voxels, int C, f
 /* latents NCDHW (fp32 if is_f32 else bf16) -> x*std[c]+mean[c] -> NDHWC bf16 (vae_encode.py:239-247). */
 int ltxb200_latent_to_ndhwc(const void* z, int is_f32, void* out, int B, int C, int64_t FHW, const float* stdv,
                             const float* meanv, void* stream);
+
+/* ---- peer-memory exchange for Ulysses sequence parallelism (one process per GPU, NVLink P2P) ----
+ * Replaces xFuserLongContextAttention's head<->sequence all-to-alls as called at
+ * wan/distributed/xdit_context_parallel.py:179-184: the producing kernels store straight into the destination rank's
+ * buffer; see csrc/comm.cuh for the flag protocol.  comm_alloc/open/close/free are the only entry points of the library
+ * that allocate or synchronise (setup time, not the data path). */
+int ltxb200_comm_alloc(size_t bytes, void** dev_ptr, void* ipc_handle_64B);   /* cudaMalloc (zeroed) + cudaIpcGetMemHandle */
+int ltxb200_comm_open(const void* ipc_handle_64B, void** dev_ptr);            /* map a peer's buffer (enables P2P lazily) */
+int ltxb200_comm_close(void* dev_ptr);
+int ltxb200_comm_free(void* dev_ptr);
+/* stream-ordered wait until flags[0..P) (this rank's flag array) have all reached `epoch` */
+int ltxb200_comm_wait(const void* flags, int P, unsigned int epoch, void* stream);
+/* Wan q/k RMSNorm + RoPE (as ltxb200_qk_norm_rope_wan_bf16) on the local fused QKV rows [B*n_loc, 3*D], v passed through,
+ * each head group stored into recv_ptrs[g] laid out [N, B, 3, H/P, head_dim] in global token order; then flag[rank] =
+ * epoch is published on every peer.  recv_ptrs / flag_ptrs: HOST arrays of P device pointers (peer mappings). */
+int ltxb200_qk_norm_rope_wan_scatter_bf16(const void* qkv, int64_t ld, int M, int D, const void* wq, const void* wk,
+                                          const float* cos_table, const float* sin_table, int head_dim,
+                                          int tokens_per_batch, int token_offset, float eps, int B, int P, int rank,
+                                          void* const* recv_ptrs, void* const* flag_ptrs, unsigned int epoch,
+                                          void* counter, void* stream);
+/* ltxb200_attention_bf16 whose epilogue stores query token t's row to out_ptrs[t / tokens_per_peer] at row
+ * b*tokens_per_peer + t % tokens_per_peer, head head_offset + h of a [B*tokens_per_peer, ldo] matrix (the Ulysses
+ * return exchange, xdit_context_parallel.py:186-190), then publishes the epoch flag on every peer. */
+int ltxb200_attention_scatter_bf16(const void* q, int64_t ldq, int64_t bsq, const void* k, int64_t ldk, int64_t bsk,
+                                   const void* v, int64_t ldv, int64_t bsv, int64_t ldo, int B, int H, int Lq, int Lk,
+                                   int d, float scale, const float* key_bias, int P, int rank, void* const* out_ptrs,
+                                   void* const* flag_ptrs, unsigned int epoch, void* counter, int tokens_per_peer,
+                                   int head_offset, void* stream);
 
 #ifdef __cplusplus
 }

@@ -5,7 +5,7 @@ No fallback: if the shared library is missing or a call fails, this raises.  Bui
 """
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_int64, c_longlong, c_void_p
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_longlong, c_size_t, c_uint, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # LTXB200_LIB selects another build of the same ABI (e.g. the -DLTXB200_DEBUG_HANG watchdog build used while developing)
@@ -40,6 +40,13 @@ def _declare(lib):
         "ltxb200_cfg_combine_f32": ([P, P, P, L, F, I, P, P], I),
         "ltxb200_pixelnorm_silu_bf16": ([P, P, L, I, F, I, P], I),
         "ltxb200_latent_to_ndhwc": ([P, I, P, I, I, L, P, P, P], I),
+        "ltxb200_comm_alloc": ([c_size_t, POINTER(c_void_p), P], I),
+        "ltxb200_comm_open": ([P, POINTER(c_void_p)], I),
+        "ltxb200_comm_close": ([P], I),
+        "ltxb200_comm_free": ([P], I),
+        "ltxb200_comm_wait": ([P, I, c_uint, P], I),
+        "ltxb200_qk_norm_rope_wan_scatter_bf16": ([P, L, I, I, P, P, P, P, I, I, I, F, I, I, I, POINTER(c_void_p), POINTER(c_void_p), c_uint, P, P], I),
+        "ltxb200_attention_scatter_bf16": ([P, L, L, P, L, L, P, L, L, L, I, I, I, I, I, F, P, I, I, POINTER(c_void_p), POINTER(c_void_p), c_uint, P, I, I, P], I),
     }
     for name, (args, res) in sig.items():
         fn = getattr(lib, name)

@@ -23,6 +23,7 @@
 // TMEM columns: S buffers (kSBufs x 128) | O_0 | O_1.
 #pragma once
 #include "common.cuh"
+#include "comm.cuh"
 
 namespace b200 {
 
@@ -36,6 +37,11 @@ struct AttnParams {
   long long out_ld, out_bs;
   int pairs;                     // ceil(Lq / 256)
   int total;                     // B * H * pairs work items
+  // Ulysses return path (xdit_context_parallel.py:186-190) fused into the epilogue: when peers.P > 0 the row of
+  // query token q goes to rank q / tokens_per_peer, at row b*tokens_per_peer + q % tokens_per_peer and head
+  // head_offset + h of that rank's [B*n_loc, H_total*d] matrix (out_ld = its row stride), over NVLink.
+  PeerPtrs peers;
+  int tokens_per_peer, head_offset;
 };
 
 constexpr int kAttnBN = 128;   // keys per block
@@ -346,7 +352,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       tc_fence_after();
       const float inv = (l > 0.f) ? __fdividef(1.0f, l) : 0.f;
       const int q = qp * 256 + t * kAttnBM + row;
-      __nv_bfloat16* orow = p.out + static_cast<long long>(b) * p.out_bs + static_cast<long long>(q) * p.out_ld + h * D;
+      __nv_bfloat16* orow;
+      if (p.peers.P > 0) {
+        const int dst = q / p.tokens_per_peer, nl = q - dst * p.tokens_per_peer;
+        orow = static_cast<__nv_bfloat16*>(p.peers.data[dst < p.peers.P ? dst : 0]) +
+               (static_cast<long long>(b) * p.tokens_per_peer + nl) * p.out_ld + (p.head_offset + h) * D;
+      } else {
+        orow = p.out + static_cast<long long>(b) * p.out_bs + static_cast<long long>(q) * p.out_ld + h * D;
+      }
 #pragma unroll 1
       for (int c = 0; c < D; c += 32) {
         uint32_t o[32];
@@ -376,6 +389,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     tc_fence_after();
     tmem_dealloc<C::kTmemCols>(tmem_base);
   }
+  if (p.peers.P > 0) peer_signal_done(p.peers, gridDim.x);
 }
 
 }  // namespace b200

@@ -3,6 +3,7 @@
 // from the reference where it is free to do so.
 #pragma once
 #include "common.cuh"
+#include "comm.cuh"
 
 namespace b200 {
 
@@ -234,6 +235,75 @@ qk_norm_rope_wan_kernel(__nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict
       store8(xr + c, o);
     }
   }
+}
+
+// Same arithmetic, fused with the Ulysses head-scatter (xdit_context_parallel.py:149-184): the rows of the local
+// fused QKV projection [B*n_loc, 3*D] are normalised / rotated (q, k) or passed through (v) and each head group's
+// slice is stored straight into the receive buffer of the rank that owns those heads,
+//   recv_g[T, b, sel, h_local, :]   (T = global token, sel = q|k|v, g = head / Hp),
+// i.e. [N, B, 3, Hp, d] in global token order -- exactly the layout the attention kernel's TMA maps read.
+// grid.y = 3 (q, k, v).  The last CTA publishes the epoch flag on every peer (comm.cuh).
+template <int NV>
+__global__ void __launch_bounds__(128)
+qk_norm_rope_wan_scatter_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int M, const __nv_bfloat16* __restrict__ wq,
+                                const __nv_bfloat16* __restrict__ wk, const float* __restrict__ cosT,
+                                const float* __restrict__ sinT, int head_dim, int tokens_per_batch, int token_offset,
+                                float eps, int B, int Hp, const PeerPtrs pp) {
+  constexpr int D = NV * 256;
+  const int sel = blockIdx.y;                       // 0 q, 1 k, 2 v
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row < M) {
+    const __nv_bfloat16* xr = qkv + row * ld + sel * D;
+    uint4 xv[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) xv[i] = *reinterpret_cast<const uint4*>(xr + (i * 32 + lane) * 8);
+    const int b = row / tokens_per_batch, n = row - b * tokens_per_batch;
+    const long long T = token_offset + n;
+    float rs = 1.f;
+    if (sel < 2) {
+      float sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        float v[8];
+        unpack8(xv[i], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sq += v[j] * v[j];
+      }
+      rs = rsqrtf(warp_sum(sq) * (1.0f / D) + eps);
+    }
+    const __nv_bfloat16* w = sel == 1 ? wk : wq;
+    const long long trow = T * head_dim;
+    const int group_cols = Hp * head_dim;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      uint4 r = xv[i];
+      if (sel < 2) {
+        float v[8], o[8];
+        unpack8(xv[i], v);
+        const uint4 w4 = ldg16(w + c);
+        unpack8(make_uint4(bf2_mul(pack_bf16(v[0] * rs, v[1] * rs), w4.x), bf2_mul(pack_bf16(v[2] * rs, v[3] * rs), w4.y),
+                           bf2_mul(pack_bf16(v[4] * rs, v[5] * rs), w4.z), bf2_mul(pack_bf16(v[6] * rs, v[7] * rs), w4.w)), o);
+        const int hd = c % head_dim;
+        const float4 c0 = *reinterpret_cast<const float4*>(cosT + trow + hd), c1 = *reinterpret_cast<const float4*>(cosT + trow + hd + 4);
+        const float4 s0 = *reinterpret_cast<const float4*>(sinT + trow + hd), s1 = *reinterpret_cast<const float4*>(sinT + trow + hd + 4);
+        const float cs[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+        const float sn[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        float q[8];
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          q[j] = o[j] * cs[j] - o[j + 1] * sn[j];
+          q[j + 1] = o[j + 1] * cs[j + 1] + o[j] * sn[j + 1];
+        }
+        r = make_uint4(pack_bf16(q[0], q[1]), pack_bf16(q[2], q[3]), pack_bf16(q[4], q[5]), pack_bf16(q[6], q[7]));
+      }
+      const int g = c / group_cols, cc = c - g * group_cols;
+      __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(pp.data[g]) + ((T * B + b) * 3 + sel) * group_cols + cc;
+      *reinterpret_cast<uint4*>(dst) = r;
+    }
+  }
+  peer_signal_done(pp, gridDim.x * gridDim.y);
 }
 
 // out = sum_j coef[j] * x[j]   (fp32, up to 6 terms; the UniPC predictor/corrector and CFG combine are

@@ -3,8 +3,10 @@
 
 #include <atomic>
 #include <cstdlib>
+#include <cstring>
 
 #include "attention.cuh"
+#include "comm.cuh"
 #include "common.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
@@ -36,7 +38,7 @@ static inline int ew_blocks(long long work_items, int threads) {
   return static_cast<int>(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
-extern "C" int ltxb200_abi_version(void) { return 1; }
+extern "C" int ltxb200_abi_version(void) { return 2; }
 extern "C" long long ltxb200_launch_count(void) { return g_launches.load(); }
 extern "C" const char* ltxb200_error_string(int code) {
   switch (code) {
@@ -185,13 +187,14 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
   return launch_status();
 }
 
-extern "C" int ltxb200_attention_bf16(const void* q, int64_t ldq, int64_t bsq, const void* k, int64_t ldk, int64_t bsk,
-                                      const void* v, int64_t ldv, int64_t bsv, void* out, int64_t ldo, int64_t bso,
-                                      int B, int H, int Lq, int Lk, int d, float scale, const float* key_bias,
-                                      void* stream) {
+static int attention_impl(const void* q, int64_t ldq, int64_t bsq, const void* k, int64_t ldk, int64_t bsk,
+                          const void* v, int64_t ldv, int64_t bsv, void* out, int64_t ldo, int64_t bso, int B, int H,
+                          int Lq, int Lk, int d, float scale, const float* key_bias, const PeerPtrs* peers,
+                          int tokens_per_peer, int head_offset, void* stream) {
   if (B <= 0 || H <= 0 || Lq <= 0 || Lk <= 0 || B > 65535 || H > 65535) return kErrBadShape;
   if (d != 64 && d != 128) return kErrUnsupported;
-  if (!aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(out) || (ldq & 7) || (ldk & 7) || (ldv & 7) ||
+  if (!peers && !out) return kErrBadAlign;
+  if (!aligned16(q) || !aligned16(k) || !aligned16(v) || (out && !aligned16(out)) || (ldq & 7) || (ldk & 7) || (ldv & 7) ||
       (ldo & 7) || (bsq & 7) || (bsk & 7) || (bsv & 7) || (bso & 7))
     return kErrBadAlign;
   const int BN = kAttnBN;
@@ -209,10 +212,100 @@ extern "C" int ltxb200_attention_bf16(const void* q, int64_t ldq, int64_t bsq, c
   const long long total = static_cast<long long>(B) * H * p.pairs;
   if (total > 0x7fffffffLL) return kErrBadShape;
   p.total = static_cast<int>(total);
+  if (peers) { p.peers = *peers; p.tokens_per_peer = tokens_per_peer; p.head_offset = head_offset; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool masked = (key_bias != nullptr) || (Lk % BN != 0);
   if (d == 64) return masked ? launch_attn<64, true>(tq, tk, tv, p, st) : launch_attn<64, false>(tq, tk, tv, p, st);
   return masked ? launch_attn<128, true>(tq, tk, tv, p, st) : launch_attn<128, false>(tq, tk, tv, p, st);
+}
+
+extern "C" int ltxb200_attention_bf16(const void* q, int64_t ldq, int64_t bsq, const void* k, int64_t ldk, int64_t bsk,
+                                      const void* v, int64_t ldv, int64_t bsv, void* out, int64_t ldo, int64_t bso,
+                                      int B, int H, int Lq, int Lk, int d, float scale, const float* key_bias,
+                                      void* stream) {
+  return attention_impl(q, ldq, bsq, k, ldk, bsk, v, ldv, bsv, out, ldo, bso, B, H, Lq, Lk, d, scale, key_bias, nullptr, 0, 0, stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// peer-memory exchange (Ulysses sequence parallelism over NVLink P2P)
+// ------------------------------------------------------------------------------------------
+static int fill_peers(PeerPtrs* pp, int P, int rank, void* const* data_ptrs, void* const* flag_ptrs, unsigned int epoch,
+                      void* counter) {
+  if (P < 1 || P > kMaxPeers || rank < 0 || rank >= P || !data_ptrs || !flag_ptrs || !counter) return kErrBadShape;
+  *pp = PeerPtrs{};
+  for (int r = 0; r < P; ++r) {
+    if (!data_ptrs[r] || !flag_ptrs[r] || !aligned16(data_ptrs[r])) return kErrBadAlign;
+    pp->data[r] = data_ptrs[r];
+    pp->flags[r] = static_cast<unsigned int*>(flag_ptrs[r]);
+  }
+  pp->P = P; pp->rank = rank; pp->epoch = epoch; pp->counter = static_cast<unsigned int*>(counter);
+  return kOk;
+}
+
+extern "C" int ltxb200_comm_alloc(size_t bytes, void** dev_ptr, void* ipc_handle_64B) {
+  if (!dev_ptr || !ipc_handle_64B || bytes == 0) return kErrBadShape;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) return kErrCuda;
+  if (cudaMemset(p, 0, bytes) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) { cudaFree(p); return kErrCuda; }
+  cudaIpcMemHandle_t h;
+  if (cudaIpcGetMemHandle(&h, p) != cudaSuccess) { cudaFree(p); return kErrCuda; }
+  memcpy(ipc_handle_64B, &h, sizeof(h));
+  *dev_ptr = p;
+  return kOk;
+}
+extern "C" int ltxb200_comm_open(const void* ipc_handle_64B, void** dev_ptr) {
+  if (!dev_ptr || !ipc_handle_64B) return kErrBadShape;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, ipc_handle_64B, sizeof(h));
+  return cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess ? kOk : kErrCuda;
+}
+extern "C" int ltxb200_comm_close(void* dev_ptr) { return cudaIpcCloseMemHandle(dev_ptr) == cudaSuccess ? kOk : kErrCuda; }
+extern "C" int ltxb200_comm_free(void* dev_ptr) { return cudaFree(dev_ptr) == cudaSuccess ? kOk : kErrCuda; }
+
+extern "C" int ltxb200_comm_wait(const void* flags, int P, unsigned int epoch, void* stream) {
+  if (!flags || P < 1 || P > kMaxPeers) return kErrBadShape;
+  comm_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const unsigned int*>(flags), P, epoch);
+  return launch_status();
+}
+
+extern "C" int ltxb200_qk_norm_rope_wan_scatter_bf16(const void* qkv, int64_t ld, int M, int D, const void* wq, const void* wk,
+                                                     const float* cos_table, const float* sin_table, int head_dim,
+                                                     int tokens_per_batch, int token_offset, float eps, int B, int P,
+                                                     int rank, void* const* recv_ptrs, void* const* flag_ptrs,
+                                                     unsigned int epoch, void* counter, void* stream) {
+  if (M <= 0 || D <= 0 || (D % 256) || B <= 0 || tokens_per_batch <= 0 || M != B * tokens_per_batch) return kErrBadShape;
+  if (!qkv || !aligned16(qkv) || (ld & 7) || !wq || !wk || !cos_table || !sin_table || !aligned16(cos_table) || !aligned16(sin_table))
+    return kErrBadAlign;
+  if (head_dim <= 0 || (head_dim & 7) || (D % head_dim) || ((D / head_dim) % P)) return kErrBadShape;
+  PeerPtrs pp;
+  if (int rc = fill_peers(&pp, P, rank, recv_ptrs, flag_ptrs, epoch, counter)) return rc;
+  const int Hp = D / head_dim / P;
+  dim3 grid((M + 3) / 4, 3);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  auto X = static_cast<const __nv_bfloat16*>(qkv);
+  auto WQ = static_cast<const __nv_bfloat16*>(wq);
+  auto WK = static_cast<const __nv_bfloat16*>(wk);
+#define QKS_CASE(n) \
+  case n: qk_norm_rope_wan_scatter_kernel<n><<<grid, 128, 0, st>>>(X, ld, M, WQ, WK, cos_table, sin_table, head_dim, tokens_per_batch, token_offset, eps, B, Hp, pp); break;
+  switch (D / 256) {
+    QKS_CASE(1) QKS_CASE(2) QKS_CASE(4) QKS_CASE(6) QKS_CASE(8) QKS_CASE(12) QKS_CASE(16) QKS_CASE(20)
+    default: return kErrUnsupported;
+  }
+#undef QKS_CASE
+  return launch_status();
+}
+
+extern "C" int ltxb200_attention_scatter_bf16(const void* q, int64_t ldq, int64_t bsq, const void* k, int64_t ldk, int64_t bsk,
+                                              const void* v, int64_t ldv, int64_t bsv, int64_t ldo, int B, int H, int Lq,
+                                              int Lk, int d, float scale, const float* key_bias, int P, int rank,
+                                              void* const* out_ptrs, void* const* flag_ptrs, unsigned int epoch,
+                                              void* counter, int tokens_per_peer, int head_offset, void* stream) {
+  PeerPtrs pp;
+  if (int rc = fill_peers(&pp, P, rank, out_ptrs, flag_ptrs, epoch, counter)) return rc;
+  if (tokens_per_peer <= 0 || static_cast<long long>(tokens_per_peer) * P < Lq || head_offset < 0) return kErrBadShape;
+  return attention_impl(q, ldq, bsq, k, ldk, bsk, v, ldv, bsv, nullptr, ldo, 0, B, H, Lq, Lk, d, scale, key_bias, &pp,
+                        tokens_per_peer, head_offset, stream);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -58,6 +58,10 @@ class WanModel:
         self.w: Dict[str, torch.Tensor] = {}
         self.layers: List[Dict[str, torch.Tensor]] = []
         self.sp_group = sp_group
+        # "p2p": producing kernels store into the peers' buffers over NVLink (distributed/ulysses.py:PeerExchange);
+        # "nccl": pack + all_to_all_single (kept as the comparison baseline, LTXB200_SP_EXCHANGE=nccl)
+        import os
+        self.sp_exchange = os.environ.get("LTXB200_SP_EXCHANGE", "p2p")
         self._sp_bufs = {}
 
     # ---------------------------------------------------------------------------------------------
@@ -128,6 +132,13 @@ class WanModel:
         import torch.distributed as dist
         return dist.get_world_size(g), dist.get_rank(g)
 
+    def _peer_exchange(self, B: int, n_loc: int):
+        key = (B, n_loc)
+        if key not in self._sp_bufs:
+            from .distributed.ulysses import PeerExchange
+            self._sp_bufs[key] = PeerExchange(self.sp_group, B, n_loc, self.num_heads, 128, self.device)
+        return self._sp_bufs[key]
+
     def _self_attention_sp(self, qkv: torch.Tensor, B: int, n_loc: int, P: int) -> torch.Tensor:
         """Ulysses exchange around self-attention (see distributed/ulysses.py)."""
         from .distributed.ulysses import ulysses_self_attention
@@ -183,14 +194,18 @@ class WanModel:
             m = mods[li]                                                              # [1, 6, D]
             xm = ops.norm_mod(xs, m[:, 1], m[:, 0], rows_per_group=M, eps=eps, layer_norm=True)        # :437-441
             qkv = ops.gemm(xm, Lw["qkv.w"], Lw["qkv.b"])
-            ops.qk_norm_rope_wan(qkv[:, :D], qkv[:, D:2 * D], Lw["qn"], Lw["kn"], cos, sin, head_dim=128,
-                                 tokens_per_batch=n_loc, token_offset=rank * n_loc, eps=eps)
-            if P == 1:
-                q3 = qkv.view(B, n_loc, 3 * D)
-                o = ops.attention(q3[:, :, :D].unflatten(-1, (H, 128)), q3[:, :, D:2 * D].unflatten(-1, (H, 128)),
-                                  q3[:, :, 2 * D:].unflatten(-1, (H, 128))).view(M, D)
+            if P > 1 and self.sp_exchange == "p2p":
+                # q/k norm + RoPE fused with the head scatter, attention epilogue fused with the return scatter
+                o = self._peer_exchange(B, n_loc).self_attention(qkv, Lw["qn"], Lw["kn"], cos, sin, eps, ops._stream())
             else:
-                o = self._self_attention_sp(qkv, B, n_loc, P)
+                ops.qk_norm_rope_wan(qkv[:, :D], qkv[:, D:2 * D], Lw["qn"], Lw["kn"], cos, sin, head_dim=128,
+                                     tokens_per_batch=n_loc, token_offset=rank * n_loc, eps=eps)
+                if P == 1:
+                    q3 = qkv.view(B, n_loc, 3 * D)
+                    o = ops.attention(q3[:, :, :D].unflatten(-1, (H, 128)), q3[:, :, D:2 * D].unflatten(-1, (H, 128)),
+                                      q3[:, :, 2 * D:].unflatten(-1, (H, 128))).view(M, D)
+                else:
+                    o = self._self_attention_sp(qkv, B, n_loc, P)
             ops.gemm(o, Lw["o.w"], Lw["o.b"], residual=xs, gate=m[:, 2], rows_per_gate=M, out=xs)      # x.addcmul_(y, e2) :458
             y3 = ops.norm_mod(xs, weight=Lw["n3.w"], bias=Lw["n3.b"], eps=eps, layer_norm=True)         # norm3 :461
             q2 = ops.gemm(y3, Lw["q2.w"], Lw["q2.b"])

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/ltx_b200.h but not exported"
     assert sorted(_lib.EXPORTED_SYMBOLS) == names, "ctypes signatures out of sync with the header"
-    assert lib.ltxb200_abi_version() == 1
+    assert lib.ltxb200_abi_version() == 2
     assert lib.ltxb200_error_string(-2).decode().startswith("pointer")
 
 
@@ -36,6 +36,8 @@ def test_bad_arguments_return_error_codes_not_crashes():
     assert lib.ltxb200_gemm_bf16(None, 0, None, 0, 0, 8, 8, None, 0, 0, None, 0, None, 0, None, 0, 1, None) == -1
     assert lib.ltxb200_attention_bf16(None, 0, 0, None, 0, 0, None, 0, 0, None, 0, 0, 1, 1, 128, 128, 96, 0.0, None, None) == -5
     assert lib.ltxb200_norm_mod_bf16(None, 0, None, 0, 4, 100, None, None, 0, 1, None, None, 1e-6, 0, None) == -1
+    assert lib.ltxb200_comm_wait(None, 2, 1, None) == -1
+    assert lib.ltxb200_comm_alloc(0, None, None) == -1
 
 
 def test_no_cpu_fallback():

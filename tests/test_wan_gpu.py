@@ -120,9 +120,14 @@ def _sp_worker(rank, world, port, golden_dir, ret):
                      sp_group=dist.group.WORLD)
         m.load_state_dict(sd, device=dev)
         cos, sin = get_rotary_pos_embed(g["lat"].shape[1:])
-        y = m([g["lat"].to(dev), g["lat"].to(dev)], t=g["t"].to(dev), context=[g["ctx"].to(dev), g["ctx0"].to(dev)], freqs=(cos, sin))
-        torch.cuda.synchronize()
-        ret[rank] = max(W.rel_l2(a.cpu(), b) for a, b in zip(y, g["fwd"]))
+        errs = {}
+        for mode in ("p2p", "nccl"):      # fused peer-memory exchange (product path) and the NCCL all-to-all baseline
+            m.sp_exchange = mode
+            for rep in range(3):          # several forwards: the peer buffers / epoch flags are reused across calls
+                y = m([g["lat"].to(dev), g["lat"].to(dev)], t=g["t"].to(dev), context=[g["ctx"].to(dev), g["ctx0"].to(dev)], freqs=(cos, sin))
+            torch.cuda.synchronize()
+            errs[mode] = max(W.rel_l2(a.cpu(), b) for a, b in zip(y, g["fwd"]))
+        ret[rank] = errs
     finally:
         dist.destroy_process_group()
 
@@ -134,6 +139,7 @@ def test_wan_sequence_parallel_two_gpus(golden_dir):
     ret = mgr.dict()
     mp.spawn(_sp_worker, args=(2, 29650 + os.getpid() % 300, golden_dir, ret), nprocs=2, join=True)
     assert len(ret) == 2
-    for r, e in ret.items():
-        print(f"rank {r}: SP forward rel_l2 vs single-GPU reference = {e:.3e}")
-        assert e < 3e-2
+    for r, errs in ret.items():
+        for mode, e in errs.items():
+            print(f"rank {r}: SP forward ({mode} exchange) rel_l2 vs single-GPU reference = {e:.3e}")
+            assert e < 3e-2
