@@ -296,6 +296,7 @@ def run_wan(args, wl):
                 "config": {"workload": args.workload, "model": f"Wan2.1-T2V-{wl['model']} (random-init, {cfg['num_layers']} layers)",
                            "latent": list(shape), "tokens": shape[1] * shape[2] * shape[3] // 4, "schedule_steps": S,
                            "forwards_per_step": 2, "parallelism": f"ulysses sp{world}",
+                           "sp_exchange": (os.environ.get("LTXB200_SP_EXCHANGE", "p2p") + (" (fused peer-memory stores over NVLink)" if os.environ.get("LTXB200_SP_EXCHANGE", "p2p") == "p2p" else " (all_to_all_single)")) if world > 1 else None,
                            "l2_policy": "per-step working set (weights + activations) far exceeds the 126 MB L2"},
                 "e2e": {"value": K / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": (noise_h.numel() * 4 + 2 * ctx_h.numel() * 2) / K,
                         "d2h_bytes_per_step": out_h.numel() * 4 / K, "steps_in_call": K},

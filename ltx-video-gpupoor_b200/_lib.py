@@ -48,7 +48,10 @@ def _declare(lib):
         "ltxb200_qk_norm_rope_wan_scatter_bf16": ([P, L, I, I, P, P, P, P, I, I, I, F, I, I, I, POINTER(c_void_p), POINTER(c_void_p), c_uint, P, P], I),
         "ltxb200_attention_scatter_bf16": ([P, L, L, P, L, L, P, L, L, L, I, I, I, I, I, F, P, I, I, POINTER(c_void_p), POINTER(c_void_p), c_uint, P, I, I, P], I),
     }
-    for name, (args, res) in sig.items():
+    for name, (args, res) in list(sig.items()):
+        if os.environ.get("LTXB200_LIB") and not hasattr(lib, name):      # older development build selected by hand
+            del sig[name]
+            continue
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = res

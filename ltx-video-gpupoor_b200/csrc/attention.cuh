@@ -50,6 +50,11 @@ template <int D>
 struct AttnCfg {
   static constexpr int BN = kAttnBN;
   static constexpr int kSBufs = (D == 64) ? 3 : 2;           // S/P buffers in TMEM, used in rotation by the steps
+  // With only two S buffers (d = 128 fills TMEM) a tile's next scores cannot be computed ahead in a spare buffer, so
+  // the block is pipelined in halves instead: keys 64..127 of S(n+2) are issued as soon as softmax(n) has READ S(n)
+  // (P(n) only overwrites columns 0..63), P.V of keys 0..63 starts when the first half of P(n) is written, and only
+  // P.V of keys 64..127 plus the low half of S(n+2) remain between "P complete" and "next S ready".
+  static constexpr bool kSplit = (kSBufs == 2);
   static constexpr int kQBytes = kAttnBM * D * 2;            // one Q tile
   static constexpr int kKBytes = BN * D * 2;                 // one K (or V) block
   static constexpr int kStages = (D == 64) ? 4 : 2;          // 128 KB of K/V in flight
@@ -118,7 +123,8 @@ DEVI void exp_chunk(const uint32_t* v, float sc, float neg_m, uint32_t tP, float
 // m_ref: reference max of the row (log2 domain), m_run: largest score seen so far, l: row sum relative to m_ref.
 template <int D, int BN, bool kPredicated>
 DEVI void softmax_block(uint32_t tS, uint32_t tO, bool first, int kbase, int Lk, const float* bias, float sc,
-                              float& m_ref, float& m_run, float& l, uint64_t* pv_done, uint32_t pv_parity) {
+                        float& m_ref, float& m_run, float& l, uint64_t* pv_done, uint32_t pv_parity,
+                        uint64_t* s_read, uint64_t* p_half, int lane) {
   const float kLog2e = 1.4426950408889634f;
   uint32_t v[BN];
   float mx0 = -INFINITY, mx1 = -INFINITY;
@@ -145,6 +151,11 @@ DEVI void softmax_block(uint32_t tS, uint32_t tO, bool first, int kbase, int Lk,
       }
     }
   }
+  if (s_read) {                                  // the whole S row is in registers: columns 64.. may be overwritten
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(s_read);
+  }
   float m_blk = fmaxf(mx0, mx1);
   if (!kPredicated) m_blk *= sc;                 // scale > 0: max commutes with the scaling
   if (first) {
@@ -156,7 +167,15 @@ DEVI void softmax_block(uint32_t tS, uint32_t tO, bool first, int kbase, int Lk,
   }
   float ls[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int c = 0; c < BN; c += 32) exp_chunk<kPredicated>(&v[c], sc, -m_ref, tS + (c >> 1), ls);
+  for (int c = 0; c < BN; c += 32) {
+    exp_chunk<kPredicated>(&v[c], sc, -m_ref, tS + (c >> 1), ls);
+    if (p_half && c + 32 == BN / 2) {            // P of keys 0..BN/2-1 is in TMEM: their P.V may start
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_half);
+    }
+  }
   l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
 }
 
@@ -168,6 +187,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   constexpr int BN = C::BN;
   constexpr int kStages = C::kStages;
   constexpr int kSBufs = C::kSBufs;
+  constexpr bool kSplit = C::kSplit;
   constexpr int kChunks = D / 64;                    // 64-wide (128 B) column chunks per row
   constexpr int kTmaWarp = 8, kMmaWarp = 9;
   constexpr uint32_t kColS0 = 0, kColO0 = kSBufs * BN;
@@ -189,7 +209,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint64_t* pv_done = p_full + kSBufs;    // [2]       P.V of tile t's block retired (lazy-rescale guard)
   uint64_t* o_done = pv_done + 2;         // [2]       last P.V of the item retired
   uint64_t* o_free = o_done + 2;          // [2]       epilogue has read O_t (4 warps arrive)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
+  uint64_t* s_read = o_free + 2;          // [kSBufs]  softmax holds S(n) in registers (kSplit; 4 warps arrive)
+  uint64_t* p_half = s_read + kSBufs;     // [kSBufs]  first half of P(n) written (kSplit; 4 warps arrive)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_half + kSBufs);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nblk = (p.Lk + BN - 1) / BN;
@@ -209,6 +231,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     for (int i = 0; i < kSBufs; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 4);
+      mbar_init(&s_read[i], 4);
+      mbar_init(&p_half[i], 4);
     }
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&k_full[i], 1);
@@ -258,63 +282,85 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     } else if (warp == kMmaWarp && elect_one()) {
       // ================= MMA issuer =================
       constexpr uint32_t idesc_s = umma_idesc_bf16(kAttnBM, BN, 0, 0);   // S = Q K^T  (both K-major)
+      constexpr uint32_t idesc_sh = umma_idesc_bf16(kAttnBM, BN / 2, 0, 0);   // one half of the keys
       constexpr uint32_t idesc_o = umma_idesc_bf16(kAttnBM, D, 0, 1);    // O += P V   (V is MN-major)
       // descriptors = (constant high bits | start address >> 4); tile / stage / k-step offsets are added to the
       // low word at issue time (the 14-bit address field cannot carry: shared memory is < 256 KB)
       const uint64_t qdesc = umma_smem_desc_sw128(smem_u32(sQ), 16, 1024);
       const uint64_t kdesc = umma_smem_desc_sw128(smem_u32(sK), 16, 1024);
       const uint64_t vdesc = umma_smem_desc_sw128(smem_u32(sV), BN * 128, 1024);
-      uint32_t kc = 0, vc = 0;       // K / V ring counters (consumption order)
+      uint32_t kc0 = 0, vc = 0;      // K ring position of the item's first block / V ring counter
       uint32_t N0 = 0;               // global step counter at the start of the item
       int it = 0;
-      // S(m), m = item-local step: tile m&1, key block m>>1, TMEM buffer (N0+m) % kSBufs
-      auto issue_s = [&](int m) {
+      // S(m), m = item-local step: tile m&1, key block m>>1, TMEM buffer (N0+m) % kSBufs.
+      // part: -1 = all BN keys; 1 = keys BN/2.. (issued first in split mode); 0 = keys 0..BN/2-1 (completes S(m))
+      auto issue_s = [&](int m, int part) {
         const int t = m & 1, j = m >> 1;
-        const int st = kc % kStages;
-        if (t == 0) mbar_wait(&k_full[st], (kc / kStages) & 1);
+        const uint32_t kpos = kc0 + j;
+        const int st = kpos % kStages;
+        if (t == 0 && part != 0) mbar_wait(&k_full[st], (kpos / kStages) & 1);
         if (j == 0) mbar_wait(&q_full[t], it & 1);
         tc_fence_after();
         const uint32_t buf = (N0 + m) % kSBufs;
         const uint64_t qa = qdesc + static_cast<uint32_t>(t * (C::kQBytes >> 4));
-        const uint64_t ka = kdesc + static_cast<uint32_t>(st * (C::kKBytes >> 4));
-        const uint32_t ts = tmem_base + kColS0 + buf * BN;
+        const uint64_t ka = kdesc + static_cast<uint32_t>(st * (C::kKBytes >> 4)) + (part == 1 ? ((BN / 2) * 128) >> 4 : 0);
+        const uint32_t ts = tmem_base + kColS0 + buf * BN + (part == 1 ? BN / 2 : 0);
+        const uint32_t idesc = part < 0 ? idesc_s : idesc_sh;
 #pragma unroll
         for (int ks = 0; ks < D / 16; ++ks) {
           const uint32_t offa = ((ks >> 2) * (kAttnBM * 128) + (ks & 3) * 32) >> 4;
           const uint32_t offb = ((ks >> 2) * (BN * 128) + (ks & 3) * 32) >> 4;
-          umma_ss(ts, qa + offa, ka + offb, idesc_s, ks ? 1u : 0u);
+          umma_ss(ts, qa + offa, ka + offb, idesc, ks ? 1u : 0u);
         }
-        umma_commit(&s_full[buf]);
-        if (j + 1 == nblk) umma_commit(&q_empty[t]);
-        if (t == 1) { umma_commit(&k_empty[st]); ++kc; }
+        if (part != 1) {
+          umma_commit(&s_full[buf]);
+          if (j + 1 == nblk) umma_commit(&q_empty[t]);
+          if (t == 1) umma_commit(&k_empty[st]);
+        }
+      };
+      // O_t += P(n)[:, keys] . V(j)[keys, :]   (k-steps [ks0, ks1) of 16 keys)
+      auto issue_pv = [&](int t, uint32_t buf, int sv, int ks0, int ks1, bool acc) {
+        // B = V[16 keys (K), D (N)], N contiguous: 8-key groups 1024 B apart (SBO), 64-col groups one chunk apart (LBO)
+        const uint64_t va = vdesc + static_cast<uint32_t>(sv * (C::kKBytes >> 4));
+        const uint32_t to = tmem_base + kColO0 + t * D, tp = tmem_base + kColS0 + buf * BN;
+#pragma unroll
+        for (int ks = ks0; ks < ks1; ++ks)
+          umma_ts(to, tp + ks * 8, va + static_cast<uint32_t>(ks * (2048 >> 4)), idesc_o, (acc || ks > ks0) ? 1u : 0u);
       };
       for (int w = blockIdx.x; w < p.total; w += gridDim.x, ++it) {
 #pragma unroll 1
-        for (int m = 0; m < kSBufs && m < nsteps; ++m) issue_s(m);
+        for (int m = 0; m < kSBufs && m < nsteps; ++m) issue_s(m, -1);
         // step n: O_t += P(n).V(j), then S(n + kSBufs) into the buffer P(n) leaves
 #pragma unroll 1
         for (int n = 0; n < nsteps; ++n) {
           const int t = n & 1, j = n >> 1;
           const int sv = vc % kStages;
-          const uint32_t N = N0 + n, buf = N % kSBufs;
-          mbar_wait(&p_full[buf], (N / kSBufs) & 1);
-          if (j == 0) mbar_wait(&o_free[t], (it & 1) ^ 1);
-          if (t == 0) mbar_wait(&v_full[sv], (vc / kStages) & 1);
-          tc_fence_after();
-          {
-            // B = V[16 keys (K), D (N)], N contiguous: 8-key groups 1024 B apart (SBO), 64-col groups one chunk apart (LBO)
-            const uint64_t va = vdesc + static_cast<uint32_t>(sv * (C::kKBytes >> 4));
-            const uint32_t to = tmem_base + kColO0 + t * D, tp = tmem_base + kColS0 + buf * BN;
-#pragma unroll
-            for (int ks = 0; ks < BN / 16; ++ks)
-              umma_ts(to, tp + ks * 8, va + static_cast<uint32_t>(ks * (2048 >> 4)), idesc_o, (j > 0 || ks) ? 1u : 0u);
+          const uint32_t N = N0 + n, buf = N % kSBufs, par = (N / kSBufs) & 1;
+          const bool more = n + kSBufs < nsteps;
+          if (kSplit) {
+            if (more) { mbar_wait(&s_read[buf], par); issue_s(n + kSBufs, 1); }
+            mbar_wait(&p_half[buf], par);
+            if (j == 0) mbar_wait(&o_free[t], (it & 1) ^ 1);
+            if (t == 0) mbar_wait(&v_full[sv], (vc / kStages) & 1);
+            tc_fence_after();
+            issue_pv(t, buf, sv, 0, BN / 32, j > 0);
+            mbar_wait(&p_full[buf], par);
+            tc_fence_after();
+            issue_pv(t, buf, sv, BN / 32, BN / 16, true);
+          } else {
+            mbar_wait(&p_full[buf], par);
+            if (j == 0) mbar_wait(&o_free[t], (it & 1) ^ 1);
+            if (t == 0) mbar_wait(&v_full[sv], (vc / kStages) & 1);
+            tc_fence_after();
+            issue_pv(t, buf, sv, 0, BN / 16, j > 0);
           }
           umma_commit(&pv_done[t]);
           if (t == 1) { umma_commit(&v_empty[sv]); ++vc; }
           if (j + 1 == nblk) umma_commit(&o_done[t]);
-          if (n + kSBufs < nsteps) issue_s(n + kSBufs);
+          if (more) issue_s(n + kSBufs, kSplit ? 0 : -1);
         }
         N0 += nsteps;
+        kc0 += nblk;
       }
     }
   } else {
@@ -339,9 +385,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const uint32_t tS = tmem_base + kColS0 + buf * BN + lane_addr;
         // full blocks without a bias take the lean path; the tail block / biased blocks take the predicated one
         if (kMasked && (bias != nullptr || kbase + BN > p.Lk))
-          softmax_block<D, BN, true>(tS, tO, j == 0, kbase, p.Lk, bias, p.scale_log2, m_ref, m_run, l, &pv_done[t], (G - 1) & 1);
+          softmax_block<D, BN, true>(tS, tO, j == 0, kbase, p.Lk, bias, p.scale_log2, m_ref, m_run, l, &pv_done[t], (G - 1) & 1,
+                                      kSplit ? &s_read[buf] : nullptr, kSplit ? &p_half[buf] : nullptr, lane);
         else
-          softmax_block<D, BN, false>(tS, tO, j == 0, kbase, p.Lk, bias, p.scale_log2, m_ref, m_run, l, &pv_done[t], (G - 1) & 1);
+          softmax_block<D, BN, false>(tS, tO, j == 0, kbase, p.Lk, bias, p.scale_log2, m_ref, m_run, l, &pv_done[t], (G - 1) & 1,
+                                      kSplit ? &s_read[buf] : nullptr, kSplit ? &p_half[buf] : nullptr, lane);
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();

@@ -47,6 +47,9 @@ struct GemmParams {
   int c_tiles_h, c_tiles_w;
   int c_causal;                    // 1: taps (t-2,t-1,t) ; 0: (t-1,t,t+1), both clamped (replicate)
   int c_taps_t;                    // 3 for 3x3x3, 1 for 1x1x1 (then also 1x1 spatial)
+  // tile rasterisation of the persistent schedule: 0 = M fastest (one weight panel per wave, all of A re-read per
+  // N tile), 1 = N fastest (a wave = a few row panels x every N tile: A streams through once, W stays in L2)
+  int n_fastest;
 };
 
 template <int BN>
@@ -109,7 +112,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int tm = tile % tiles_m, tn = tile / tiles_m;
+        const int tm = p.n_fastest ? tile / tiles_n : tile % tiles_m, tn = p.n_fastest ? tile % tiles_n : tile / tiles_m;
         int cb = 0, ct = 0, ch0 = 0, cw0 = 0;
         if (kConv) {
           int r = tm;
@@ -181,7 +184,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int tm = tile % tiles_m, tn = tile / tiles_m;
+      const int tm = p.n_fastest ? tile / tiles_n : tile % tiles_m, tn = p.n_fastest ? tile % tiles_n : tile / tiles_m;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * BN + (static_cast<uint32_t>(sub * 32) << 16);

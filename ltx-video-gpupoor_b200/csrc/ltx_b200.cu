@@ -102,6 +102,9 @@ extern "C" int ltxb200_gemm_bf16(const void* A, int64_t lda, const void* W, int6
   p.residual = static_cast<const __nv_bfloat16*>(residual); p.ldr = ldr;
   p.gate = static_cast<const __nv_bfloat16*>(gate); p.gate_ld = gate_ld; p.rows_per_gate = rows_per_gate > 0 ? rows_per_gate : 1;
   p.store_mode = kStoreRowMajor;
+  // the weights of this path always fit the 126 MB L2 (<= 34 MB); A often does not (FFN-down: 302 MB)
+  p.n_fastest = (static_cast<long long>(N) * K * 2 <= (48ll << 20)) ? 1 : 0;
+  if (const char* e = getenv("LTXB200_GEMM_RASTER")) p.n_fastest = atoi(e);
   const int tiles = ((M + kGemmBM - 1) / kGemmBM) * ((N + BN - 1) / BN);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   return BN == 128 ? launch_gemm<128, false>(ta, tb, p, tiles, st) : launch_gemm<256, false>(ta, tb, p, tiles, st);
@@ -157,6 +160,8 @@ extern "C" int ltxb200_conv3d_bf16(const void* x, const void* w, const void* bia
   p.cB = B; p.cT = T; p.cH = H; p.cW = W; p.cCin = Cin; p.cBH = BH; p.cBW = BW;
   p.c_tiles_h = (H + BH - 1) / BH; p.c_tiles_w = (W + BW - 1) / BW;
   p.c_causal = causal ? 1 : 0; p.c_taps_t = 3;
+  p.n_fastest = (static_cast<long long>(Cout) * 27 * Cin * 2 <= (48ll << 20)) ? 1 : 0;
+  if (const char* e = getenv("LTXB200_GEMM_RASTER")) p.n_fastest = atoi(e);
   const int tiles = B * T * p.c_tiles_h * p.c_tiles_w * ((Cout + BN - 1) / BN);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   return BN == 128 ? launch_gemm<128, true>(ta, tb, p, tiles, st) : launch_gemm<256, true>(ta, tb, p, tiles, st);

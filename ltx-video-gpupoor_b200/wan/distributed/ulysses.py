@@ -123,19 +123,24 @@ class PeerExchange:
         f0 = self._arr([p + self.flag_off(0, par) for p in self.peer[ctl]])
         f1 = self._arr([p + self.flag_off(1, par) for p in self.peer[ctl]])
         recv, back = f"recv{par}", f"back{par}"
-        self._check(lib.ltxb200_qk_norm_rope_wan_scatter_bf16(
+        from ... import ops
+        with ops._Prof("qk_norm_rope_wan_scatter_bf16", "byte", 2.0 * 2 * B * n_loc * 3 * D):
+          self._check(lib.ltxb200_qk_norm_rope_wan_scatter_bf16(
             qkv.data_ptr(), qkv.stride(0), B * n_loc, D, wq.data_ptr(), wk.data_ptr(), cos.data_ptr(), sin.data_ptr(), d,
             n_loc, self.rank * n_loc, float(eps), B, P, self.rank, self._arr(self.peer[recv]), f0, epoch,
             self.local[ctl] + self.counter_off(0), stream_ptr), "qk_norm_rope_wan_scatter")
-        self._check(lib.ltxb200_comm_wait(self.local[ctl] + self.flag_off(0, par), P, epoch, stream_ptr), "comm_wait")
+        with ops._Prof("comm_wait", "byte", 0.0):
+            self._check(lib.ltxb200_comm_wait(self.local[ctl] + self.flag_off(0, par), P, epoch, stream_ptr), "comm_wait")
         base = self.local[recv]
         tok = B * 3 * Hp * d                    # elements per global token in recv
         q, k, v = base, base + Hp * d * 2, base + 2 * Hp * d * 2
-        self._check(lib.ltxb200_attention_scatter_bf16(
+        with ops._Prof("attention_bf16", "flop", 4.0 * B * Hp * N * N * d):
+          self._check(lib.ltxb200_attention_scatter_bf16(
             q, tok, 3 * Hp * d, k, tok, 3 * Hp * d, v, tok, 3 * Hp * d, D, B, Hp, N, N, d, 0.0, None, P, self.rank,
             self._arr(self.peer[back]), f1, epoch, self.local[ctl] + self.counter_off(1), n_loc, self.rank * Hp, stream_ptr),
             "attention_scatter")
-        self._check(lib.ltxb200_comm_wait(self.local[ctl] + self.flag_off(1, par), P, epoch, stream_ptr), "comm_wait")
+        with ops._Prof("comm_wait", "byte", 0.0):
+            self._check(lib.ltxb200_comm_wait(self.local[ctl] + self.flag_off(1, par), P, epoch, stream_ptr), "comm_wait")
         return self._view(back, (B * n_loc, D))
 
     def close(self):
