@@ -126,6 +126,7 @@ DEVI void softmax_block(uint32_t tS, uint32_t tO, bool first, int kbase, int Lk,
                         float& m_ref, float& m_run, float& l, uint64_t* pv_done, uint32_t pv_parity,
                         uint64_t* s_read, uint64_t* p_half, int lane) {
   const float kLog2e = 1.4426950408889634f;
+  const bool bias_vec = bias != nullptr && ((reinterpret_cast<uintptr_t>(bias) | (static_cast<uintptr_t>(kbase) << 2)) & 15) == 0;
   uint32_t v[BN];
   float mx0 = -INFINITY, mx1 = -INFINITY;
   tmem_ld32(tS, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
@@ -134,14 +135,29 @@ DEVI void softmax_block(uint32_t tS, uint32_t tO, bool first, int kbase, int Lk,
     tmem_wait_ld();
     if (c + 32 < BN) tmem_ld32(tS + c + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c + 32]));
     if (kPredicated) {
+      if (kbase + BN <= Lk && bias_vec) {
+        // full block with a 16B-aligned bias row: vector loads (every lane reads the same addresses: one broadcast
+        // transaction each), no tail predication
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int k = kbase + c + i;
-        float s = __uint_as_float(v[c + i]) * sc;
-        if (bias && k < Lk) s = fmaf(__ldg(bias + k), kLog2e, s);
-        if (k >= Lk) s = -INFINITY;
-        v[c + i] = __float_as_uint(s);
-        mx0 = fmaxf(mx0, s);
+        for (int i = 0; i < 32; i += 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + kbase + c + i));
+          const float s0 = fmaf(__uint_as_float(v[c + i]), sc, b4.x * kLog2e), s1 = fmaf(__uint_as_float(v[c + i + 1]), sc, b4.y * kLog2e);
+          const float s2 = fmaf(__uint_as_float(v[c + i + 2]), sc, b4.z * kLog2e), s3 = fmaf(__uint_as_float(v[c + i + 3]), sc, b4.w * kLog2e);
+          v[c + i] = __float_as_uint(s0); v[c + i + 1] = __float_as_uint(s1);
+          v[c + i + 2] = __float_as_uint(s2); v[c + i + 3] = __float_as_uint(s3);
+          mx0 = fmax3(mx0, s0, s1);
+          mx1 = fmax3(mx1, s2, s3);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int k = kbase + c + i;
+          float s = __uint_as_float(v[c + i]) * sc;
+          if (bias && k < Lk) s = fmaf(__ldg(bias + k), kLog2e, s);
+          if (k >= Lk) s = -INFINITY;
+          v[c + i] = __float_as_uint(s);
+          mx0 = fmaxf(mx0, s);
+        }
       }
     } else {
 #pragma unroll
