@@ -153,10 +153,62 @@ def run_reference(args, wl_name, wl):
 # ------------------------------------------------------------------------------------------------------------
 # Wan2.1 T2V, Ulysses sequence parallel over all ranks (strong scaling: one video, N GPUs)
 # ------------------------------------------------------------------------------------------------------------
+def wan_cpu_sample(wl):
+    """Bounded sample of one Wan denoise step on the CPU (oracle port, torch fp32): full-width WanModel.forward with 1 and 2
+    layers at two reduced token counts; the per-layer cost is fitted as a*N + b*N^2 (projections/FFN vs self-attention)
+    and extrapolated to the workload's token count, 30/40 layers and 2 forwards per step."""
+    from oracle import wan_oracle as W
+    cfg = dict(W.WAN_1_3B if wl["model"] == "1.3B" else W.WAN_14B)
+    lat_full = (16, (wl["frame_num"] - 1) // 4 + 1, wl["height"] // 8, wl["width"] // 8)
+    N_full = lat_full[1] * lat_full[2] * lat_full[3] // 4
+    torch.manual_seed(0)
+    t = torch.tensor([500])
+    ctx = [torch.randn(wl["prompt_tokens"], 4096)]
+    grids = [(4, 32, 32), (4, 32, 64)]            # latent (f, h, w) -> 1024 / 2048 tokens
+    per_layer, fixed = {}, {}
+    with torch.no_grad():
+        for (f, h, w) in grids:
+            n = f * h * w // 4
+            x = [torch.randn(16, f, h, w)]
+            cos, sin = W.rope_tables((f, h, w))
+            tt = {}
+            for L in (1, 2):
+                sd = W.make_wan_state_dict(cfg, seed=0, num_layers=L)
+                t0 = time.perf_counter()
+                W.wan_forward(sd, cfg, x, t, ctx, cos, sin)
+                tt[L] = time.perf_counter() - t0
+                del sd
+            per_layer[n] = max(tt[2] - tt[1], 1e-9)
+            fixed[n] = max(tt[1] - per_layer[n], 0.0)
+    (n1, t1), (n2, t2) = sorted(per_layer.items())
+    b = max((t2 / n2 - t1 / n1) / (n2 - n1), 0.0)
+    a = max(t1 / n1 - b * n1, 0.0)
+    layer_full = a * N_full + b * N_full * N_full
+    fixed_full = fixed[n2] * N_full / n2
+    step_s = 2 * (fixed_full + cfg["num_layers"] * layer_full)
+    return dict(step_s=step_s, tokens=N_full, fit=dict(a=a, b=b), sample_tokens=[n1, n2], per_layer_s=[t1, t2])
+
+
 def run_wan(args, wl):
     if args.impl == "reference":
-        if int(os.environ.get("RANK", "0")) == 0:
-            print(json.dumps({"impl": "reference", "unavailable": "Wan CPU reference arm not wired into bench.py yet (oracle/wan_oracle.py exists)"}))
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        cores = torch.get_num_threads()
+        vals = []
+        for i in range(args.warmup + args.steps):
+            smp = wan_cpu_sample(wl)
+            if i >= args.warmup:
+                vals.append(smp["step_s"])
+        step_s = sum(vals) / len(vals)
+        v = 1.0 / step_s
+        sample = (f"oracle port (torch fp32, {cores} threads) of WanModel.forward, full width, 1- and 2-layer forwards at "
+                  f"{smp['sample_tokens']} tokens; per-layer cost fitted a*N + b*N^2 and extrapolated to N={smp['tokens']}, all layers, 2 forwards/step")
+        print(json.dumps({"impl": "reference", "metric": "denoise_steps_per_s", "value": v, "unit": "steps/s", "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
+                          "scaling": "strong", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+                          "config": {"workload": args.workload, "model": f"Wan2.1-T2V-{wl['model']}", "tokens": smp["tokens"]},
+                          "cpu_baseline": {"value": v, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
+                          "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -289,6 +341,13 @@ def run_wan(args, wl):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt)
     if rank == 0:
+        cpu_baseline = None
+        if world == 1 and not args.no_cpu_baseline:
+            smp = wan_cpu_sample(wl)
+            cores = torch.get_num_threads()
+            cpu_baseline = {"value": 1.0 / smp["step_s"], "unit": "steps/s", "cores": cores, "kind": "port",
+                            "sample": (f"oracle port (torch fp32, {cores} threads) of WanModel.forward, full width, 1- and 2-layer forwards at "
+                                       f"{smp['sample_tokens']} tokens; per-layer cost fitted a*N + b*N^2, extrapolated to N={smp['tokens']}, all layers, 2 forwards/step")}
         ms_step = elapsed / args.steps * 1e3
         line = {"metric": "denoise_steps_per_s", "value": steps_per_s, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -300,7 +359,7 @@ def run_wan(args, wl):
                            "l2_policy": "per-step working set (weights + activations) far exceeds the 126 MB L2"},
                 "e2e": {"value": K / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": (noise_h.numel() * 4 + 2 * ctx_h.numel() * 2) / K,
                         "d2h_bytes_per_step": out_h.numel() * 4 / K, "steps_in_call": K},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": None,
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "s_per_video_denoise": S * ms_step / 1e3,
                 "model_tflops_per_gpu": 2 * wl["fwd_flops"] * (cfg["num_layers"] / (30 if wl["model"] == "1.3B" else 40)) / (ms_step / 1e3) / 1e12 / world,
                 "kernels": kernels}

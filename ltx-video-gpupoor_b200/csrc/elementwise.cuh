@@ -50,70 +50,92 @@ norm_mod_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
                 int rows_per_group, const __nv_bfloat16* __restrict__ weight, const __nv_bfloat16* __restrict__ bias,
                 float eps) {
   constexpr int D = NV * 256;
-  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  const int stride = gridDim.x * 4;
+  int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (row >= M) return;
-  const __nv_bfloat16* xr = x + row * ldx;
-  uint4 xv[NV];
+  // rows are walked grid-stride with the NEXT row's loads issued before the current row is reduced, so every warp
+  // keeps a full row (NV x 512 B) in flight at all times
+  constexpr bool kPrefetch = NV <= 12;       // wider rows would not fit two copies in registers
+  uint4 xv[NV], xn[kPrefetch ? NV : 1];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) xv[i] = *reinterpret_cast<const uint4*>(xr + (i * 32 + lane) * 8);
-  const long long g = row / rows_per_group;
-  const __nv_bfloat16* sc = scale ? scale + g * mod_ld : nullptr;
-  const __nv_bfloat16* sh = shift ? shift + g * mod_ld : nullptr;
-  float sum = 0.f, sq = 0.f;
+  for (int i = 0; i < NV; ++i) xv[i] = *reinterpret_cast<const uint4*>(x + row * ldx + (i * 32 + lane) * 8);
+  for (; row < M; row += stride) {
+    const int nrow = row + stride;
+    if (kPrefetch && nrow < M) {
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    float v[8];
-    unpack8(xv[i], v);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { sum += v[j]; sq += v[j] * v[j]; }
-  }
-  float mean = 0.f, rs;
-  if (kLayerNorm) {
-    mean = warp_sum(sum) * (1.0f / D);
-    float var = 0.f;
+      for (int i = 0; i < NV; ++i) xn[kPrefetch ? i : 0] = *reinterpret_cast<const uint4*>(x + nrow * ldx + (i * 32 + lane) * 8);
+    }
+    const long long g = row / rows_per_group;
+    const __nv_bfloat16* sc = scale ? scale + g * mod_ld : nullptr;
+    const __nv_bfloat16* sh = shift ? shift + g * mod_ld : nullptr;
+    float sum = 0.f, sq = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       float v[8];
       unpack8(xv[i], v);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { const float d = v[j] - mean; var += d * d; }
+      for (int j = 0; j < 8; ++j) { sum += v[j]; sq += v[j] * v[j]; }
     }
-    rs = rsqrtf(warp_sum(var) * (1.0f / D) + eps);
-  } else {
-    rs = rsqrtf(warp_sum(sq) * (1.0f / D) + eps);
-  }
-  __nv_bfloat16* yr = y + row * ldy;
-  const uint32_t one2 = 0x3f803f80u;           // bf16x2 (1.0, 1.0)
+    float mean = 0.f, rs;
+    if (kLayerNorm) {
+      mean = warp_sum(sum) * (1.0f / D);
+      float var = 0.f;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int c = (i * 32 + lane) * 8;
-    float v[8], o[8];
-    unpack8(xv[i], v);
+      for (int i = 0; i < NV; ++i) {
+        if (NV > 12) asm volatile("" : "+r"(xv[i].x), "+r"(xv[i].y), "+r"(xv[i].z), "+r"(xv[i].w));
+        float v[8];
+        unpack8(xv[i], v);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = (v[j] - mean) * rs;
-    if (weight) {
-      float w[8];
-      unpack8(ldg16(weight + c), w);
-      if (bias) {
-        float bb[8];
-        unpack8(ldg16(bias + c), bb);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = o[j] * w[j] + bb[j];
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = bf16r(o[j]) * w[j];
+        for (int j = 0; j < 8; ++j) { const float d = v[j] - mean; var += d * d; }
       }
+      rs = rsqrtf(warp_sum(var) * (1.0f / D) + eps);
+    } else {
+      rs = rsqrtf(warp_sum(sq) * (1.0f / D) + eps);
     }
-    uint4 r = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
-    if (sc) {      // bf16( bf16( bf16(o) * bf16(1 + s) ) + t ), the reference's rounding points
-      const uint4 s4 = ldg16(sc + c), t4 = ldg16(sh + c);
-      r.x = bf2_add(bf2_mul(r.x, bf2_add(one2, s4.x)), t4.x);
-      r.y = bf2_add(bf2_mul(r.y, bf2_add(one2, s4.y)), t4.y);
-      r.z = bf2_add(bf2_mul(r.z, bf2_add(one2, s4.z)), t4.z);
-      r.w = bf2_add(bf2_mul(r.w, bf2_add(one2, s4.w)), t4.w);
+    // the row is kept PACKED between the passes: hide it from CSE, or the compiler keeps all D unpacked floats live
+#pragma unroll
+    for (int i = 0; i < NV; ++i) asm volatile("" : "+r"(xv[i].x), "+r"(xv[i].y), "+r"(xv[i].z), "+r"(xv[i].w));
+    __nv_bfloat16* yr = y + row * ldy;
+    const uint32_t one2 = 0x3f803f80u;           // bf16x2 (1.0, 1.0)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      float v[8], o[8];
+      unpack8(xv[i], v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (v[j] - mean) * rs;
+      if (weight) {
+        float w[8];
+        unpack8(ldg16(weight + c), w);
+        if (bias) {
+          float bb[8];
+          unpack8(ldg16(bias + c), bb);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = o[j] * w[j] + bb[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = bf16r(o[j]) * w[j];
+        }
+      }
+      uint4 r = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+      if (sc) {      // bf16( bf16( bf16(o) * bf16(1 + s) ) + t ), the reference's rounding points
+        const uint4 s4 = ldg16(sc + c), t4 = ldg16(sh + c);
+        r.x = bf2_add(bf2_mul(r.x, bf2_add(one2, s4.x)), t4.x);
+        r.y = bf2_add(bf2_mul(r.y, bf2_add(one2, s4.y)), t4.y);
+        r.z = bf2_add(bf2_mul(r.z, bf2_add(one2, s4.z)), t4.z);
+        r.w = bf2_add(bf2_mul(r.w, bf2_add(one2, s4.w)), t4.w);
+      }
+      *reinterpret_cast<uint4*>(yr + c) = r;
+      if (NV > 12) asm volatile("" ::: "memory");   // wide rows: keep the modulation loads of later chunks from being hoisted (registers)
     }
-    *reinterpret_cast<uint4*>(yr + c) = r;
+    if (kPrefetch) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) xv[i] = xn[kPrefetch ? i : 0];
+    } else if (nrow < M) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) xv[i] = *reinterpret_cast<const uint4*>(x + nrow * ldx + (i * 32 + lane) * 8);
+    }
   }
 }
 

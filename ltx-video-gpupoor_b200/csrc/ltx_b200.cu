@@ -320,7 +320,9 @@ template <bool LN>
 static int launch_norm(int NV, const __nv_bfloat16* x, __nv_bfloat16* y, int M, int64_t ldx, int64_t ldy,
                        const __nv_bfloat16* sc, const __nv_bfloat16* sh, int64_t mod_ld, int rpg,
                        const __nv_bfloat16* w, const __nv_bfloat16* b, float eps, cudaStream_t st) {
-  const int grid = (M + 3) / 4;
+  int grid = (M + 3) / 4;
+  const int cap = num_sms() * 4;            // rows are walked grid-stride (4 resident CTAs per SM at ~120 registers)
+  if (grid > cap) grid = cap;
 #define NORM_CASE(n) \
   case n: norm_mod_kernel<n, LN><<<grid, 128, 0, st>>>(x, y, M, ldx, ldy, sc, sh, mod_ld, rpg, w, b, eps); break;
   switch (NV) {
