@@ -31,6 +31,7 @@ extern "C" {
 #define LTXB200_ACT_NONE 0
 #define LTXB200_ACT_GELU_TANH 1
 #define LTXB200_ACT_SILU 2
+#define LTXB200_ACT_GELU_ERF 3   /* exact GELU (torch.nn.GELU()): Wan MLPProj, wan/modules/model.py:583 */
 
 #define LTXB200_CONV_STORE_NDHWC 0   /* out[b,t,h,w,co] bf16 */
 #define LTXB200_CONV_STORE_D2S 1     /* depth-to-space 2x2x2, first frame dropped; co order (p1,p2,p3,c) */
@@ -134,6 +135,12 @@ int ltxb200_pixelnorm_silu_bf16(const void* x, void* y, int64_t voxels, int C, f
 /* latents NCDHW (fp32 if is_f32 else bf16) -> x*std[c]+mean[c] -> NDHWC bf16 (vae_encode.py:239-247). */
 int ltxb200_latent_to_ndhwc(const void* z, int is_f32, void* out, int B, int C, int64_t FHW, const float* stdv,
                             const float* meanv, void* stream);
+
+/* as ltxb200_attention_bf16, but out += attention(q, k, v) (bf16 read-modify-write in the epilogue): the image-token
+ * branch of WanI2VCrossAttention, `x += img_x` (wan/modules/model.py:329-337), without a separate add pass. */
+int ltxb200_attention_acc_bf16(const void* q, int64_t ldq, int64_t bsq, const void* k, int64_t ldk, int64_t bsk,
+                               const void* v, int64_t ldv, int64_t bsv, void* out, int64_t ldo, int64_t bso, int B, int H,
+                               int Lq, int Lk, int d, float scale, const float* key_bias, void* stream);
 
 /* ---- peer-memory exchange for Ulysses sequence parallelism (one process per GPU, NVLink P2P) ----
  * Replaces xFuserLongContextAttention's head<->sequence all-to-alls as called at

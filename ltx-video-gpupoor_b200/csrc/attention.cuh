@@ -42,6 +42,7 @@ struct AttnParams {
   // head_offset + h of that rank's [B*n_loc, H_total*d] matrix (out_ld = its row stride), over NVLink.
   PeerPtrs peers;
   int tokens_per_peer, head_offset;
+  int accumulate;                // out += result (bf16 read-modify-write): the second attention of WanI2VCrossAttention (x += img_x)
 };
 
 constexpr int kAttnBN = 128;   // keys per block
@@ -432,11 +433,16 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         if (q < p.Lq) {
 #pragma unroll
           for (int i = 0; i < 32; i += 8) {
-            *reinterpret_cast<uint4*>(orow + c + i) = make_uint4(
-                pack_bf16(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv),
-                pack_bf16(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv),
-                pack_bf16(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv),
-                pack_bf16(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv));
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(o[i + e]) * inv;
+            if (p.accumulate) {
+              const uint4 prev = *reinterpret_cast<const uint4*>(orow + c + i);
+              const float2 a = unpack_bf16(prev.x), b2 = unpack_bf16(prev.y), c2 = unpack_bf16(prev.z), d2 = unpack_bf16(prev.w);
+              f[0] += a.x; f[1] += a.y; f[2] += b2.x; f[3] += b2.y; f[4] += c2.x; f[5] += c2.y; f[6] += d2.x; f[7] += d2.y;
+            }
+            *reinterpret_cast<uint4*>(orow + c + i) =
+                make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
           }
         }
       }

@@ -74,6 +74,9 @@ DEVI float gelu_tanh(float x) {
   return 0.5f * x * (1.0f + t);
 }
 
+// exact GELU (torch.nn.GELU() default, used by Wan's MLPProj, model.py:583)
+DEVI float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.7071067811865476f)); }
+
 // ------------------------------------------------------------------------------------------
 // mbarrier
 // ------------------------------------------------------------------------------------------

@@ -374,7 +374,7 @@ __global__ void ada_add_kernel(const __nv_bfloat16* __restrict__ table, const __
 // ------------------------------------------------------------------------------------------
 // elementwise activation / blend helpers
 // ------------------------------------------------------------------------------------------
-// mode 0: copy, 1: gelu-tanh, 2: silu   (LTXB200_ACT_*)
+// mode 0: copy, 1: gelu-tanh, 2: silu, 3: exact gelu   (LTXB200_ACT_*)
 __global__ void act_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n, int mode) {
   for (long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 8; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x * 8) {
@@ -382,7 +382,7 @@ __global__ void act_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* _
     load8(x + i, v);
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-      v[j] = mode == 2 ? __fdividef(v[j], 1.0f + __expf(-v[j])) : (mode == 1 ? gelu_tanh(v[j]) : v[j]);
+      v[j] = mode == 2 ? __fdividef(v[j], 1.0f + __expf(-v[j])) : (mode == 1 ? gelu_tanh(v[j]) : (mode == 3 ? gelu_erf(v[j]) : v[j]));
     store8(y + i, v);
   }
 }

@@ -20,7 +20,7 @@ constexpr int kGemmBM = 128;
 constexpr int kGemmBK = 64;
 constexpr int kGemmThreads = 192;
 
-enum GemmAct : int { kActNone = 0, kActGeluTanh = 1, kActSilu = 2 };
+enum GemmAct : int { kActNone = 0, kActGeluTanh = 1, kActSilu = 2, kActGeluErf = 3 };
 enum GemmStore : int {
   kStoreRowMajor = 0,   // out[m*ldc + n]
   kStoreConvD2S = 1,    // conv: depth-to-space 2x2x2 (+ drop first frame), channel order (p1,p2,p3,c)
@@ -239,6 +239,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           } else if (p.act == kActSilu) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = __fdividef(f[j], 1.0f + __expf(-f[j]));
+          } else if (p.act == kActGeluErf) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
           }
           if (gate_row) {
 #pragma unroll

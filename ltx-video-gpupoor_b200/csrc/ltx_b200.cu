@@ -195,7 +195,7 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
 static int attention_impl(const void* q, int64_t ldq, int64_t bsq, const void* k, int64_t ldk, int64_t bsk,
                           const void* v, int64_t ldv, int64_t bsv, void* out, int64_t ldo, int64_t bso, int B, int H,
                           int Lq, int Lk, int d, float scale, const float* key_bias, const PeerPtrs* peers,
-                          int tokens_per_peer, int head_offset, void* stream) {
+                          int tokens_per_peer, int head_offset, int accumulate, void* stream) {
   if (B <= 0 || H <= 0 || Lq <= 0 || Lk <= 0 || B > 65535 || H > 65535) return kErrBadShape;
   if (d != 64 && d != 128) return kErrUnsupported;
   if (!peers && !out) return kErrBadAlign;
@@ -218,6 +218,7 @@ static int attention_impl(const void* q, int64_t ldq, int64_t bsq, const void* k
   if (total > 0x7fffffffLL) return kErrBadShape;
   p.total = static_cast<int>(total);
   if (peers) { p.peers = *peers; p.tokens_per_peer = tokens_per_peer; p.head_offset = head_offset; }
+  p.accumulate = accumulate;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool masked = (key_bias != nullptr) || (Lk % BN != 0);
   if (d == 64) return masked ? launch_attn<64, true>(tq, tk, tv, p, st) : launch_attn<64, false>(tq, tk, tv, p, st);
@@ -228,7 +229,14 @@ extern "C" int ltxb200_attention_bf16(const void* q, int64_t ldq, int64_t bsq, c
                                       const void* v, int64_t ldv, int64_t bsv, void* out, int64_t ldo, int64_t bso,
                                       int B, int H, int Lq, int Lk, int d, float scale, const float* key_bias,
                                       void* stream) {
-  return attention_impl(q, ldq, bsq, k, ldk, bsk, v, ldv, bsv, out, ldo, bso, B, H, Lq, Lk, d, scale, key_bias, nullptr, 0, 0, stream);
+  return attention_impl(q, ldq, bsq, k, ldk, bsk, v, ldv, bsv, out, ldo, bso, B, H, Lq, Lk, d, scale, key_bias, nullptr, 0, 0, 0, stream);
+}
+
+extern "C" int ltxb200_attention_acc_bf16(const void* q, int64_t ldq, int64_t bsq, const void* k, int64_t ldk, int64_t bsk,
+                                          const void* v, int64_t ldv, int64_t bsv, void* out, int64_t ldo, int64_t bso,
+                                          int B, int H, int Lq, int Lk, int d, float scale, const float* key_bias,
+                                          void* stream) {
+  return attention_impl(q, ldq, bsq, k, ldk, bsk, v, ldv, bsv, out, ldo, bso, B, H, Lq, Lk, d, scale, key_bias, nullptr, 0, 0, 1, stream);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -310,7 +318,7 @@ extern "C" int ltxb200_attention_scatter_bf16(const void* q, int64_t ldq, int64_
   if (int rc = fill_peers(&pp, P, rank, out_ptrs, flag_ptrs, epoch, counter)) return rc;
   if (tokens_per_peer <= 0 || static_cast<long long>(tokens_per_peer) * P < Lq || head_offset < 0) return kErrBadShape;
   return attention_impl(q, ldq, bsq, k, ldk, bsk, v, ldv, bsv, nullptr, ldo, 0, B, H, Lq, Lk, d, scale, key_bias, &pp,
-                        tokens_per_peer, head_offset, stream);
+                        tokens_per_peer, head_offset, 0, stream);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -326,7 +334,7 @@ static int launch_norm(int NV, const __nv_bfloat16* x, __nv_bfloat16* y, int M, 
 #define NORM_CASE(n) \
   case n: norm_mod_kernel<n, LN><<<grid, 128, 0, st>>>(x, y, M, ldx, ldy, sc, sh, mod_ld, rpg, w, b, eps); break;
   switch (NV) {
-    NORM_CASE(1) NORM_CASE(2) NORM_CASE(4) NORM_CASE(6) NORM_CASE(8) NORM_CASE(12) NORM_CASE(16) NORM_CASE(20)
+    NORM_CASE(1) NORM_CASE(2) NORM_CASE(4) NORM_CASE(5) NORM_CASE(6) NORM_CASE(8) NORM_CASE(12) NORM_CASE(16) NORM_CASE(20)
     default: return kErrUnsupported;
   }
 #undef NORM_CASE

@@ -53,7 +53,7 @@ def _req(t: torch.Tensor, dtype=BF16, name="tensor"):
     return t
 
 
-ACT_NONE, ACT_GELU_TANH, ACT_SILU = 0, 1, 2
+ACT_NONE, ACT_GELU_TANH, ACT_SILU, ACT_GELU_ERF = 0, 1, 2, 3
 
 
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
@@ -109,20 +109,24 @@ def conv3d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], causa
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_bias: Optional[torch.Tensor] = None,
-              scale: float = 0.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """q [B,Lq,H,d], k/v [B,Lk,H,d] bf16 (strided views allowed, head stride must be d) -> [B,Lq,H,d]."""
+              scale: float = 0.0, out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    """q [B,Lq,H,d], k/v [B,Lk,H,d] bf16 (strided views allowed, head stride must be d) -> [B,Lq,H,d].
+    accumulate: out += attention (out must be given)."""
     for t, n in ((q, "q"), (k, "k"), (v, "v")):
         _req(t, name=n)
         assert t.dim() == 4 and t.stride(2) == t.shape[3], f"{n}: heads must be packed (stride(2) == d)"
     B, Lq, H, d = q.shape
     Lk = k.shape[1]
+    if accumulate and out is None:
+        raise ValueError("accumulate=True needs out=")
     if out is None:
         out = torch.empty(B, Lq, H, d, device=q.device, dtype=BF16)
     _req(out, name="out")
     if key_bias is not None:
         _req(key_bias, torch.float32, "key_bias"); assert key_bias.shape == (B, Lk) and key_bias.is_contiguous()
     with _Prof('attention_bf16', 'flop', 4.0 * B * H * Lq * Lk * d):
-        rc = _lib.lib().ltxb200_attention_bf16(
+        fn = _lib.lib().ltxb200_attention_acc_bf16 if accumulate else _lib.lib().ltxb200_attention_bf16
+        rc = fn(
         q.data_ptr(), q.stride(1), q.stride(0), k.data_ptr(), k.stride(1), k.stride(0),
         v.data_ptr(), v.stride(1), v.stride(0), out.data_ptr(), out.stride(1), out.stride(0),
         B, H, Lq, Lk, d, float(scale), _p(key_bias), _stream())

@@ -1,0 +1,88 @@
+"""WanI2V — B200-native drop-in for the denoise loop of wan/image2video.py:124-414 (`WanI2V.generate`).
+
+Scope: noise, UniPC schedule, RoPE tables, the per-step two-sequence forward with the i2v conditioning
+(`y` = [mask(4) | image latent(16)] channels concatenated to the noisy latent, :232-244,279-280, and the 257 CLIP tokens
+consumed by WanI2VCrossAttention), CFG with the optional CFG-Zero* projection, scheduler step.  The encoders that PRODUCE
+the conditioning — CLIP visual (:219-224), the Wan VAE encode of the padded image video (:262-277) and T5 —
+are out of scope: pass `clip_fea=` [1, 257, 1280], `y=` [20, (F-1)/4+1, H/8, W/8] and `context=` / `context_null=`.
+The result is the denoised latent [16, (F-1)/4+1, H/8, W/8] (fp32).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from .. import ops
+from .fm_solvers_unipc import FlowUniPCMultistepScheduler
+from .model import WanModel
+from .posemb_layers import get_rotary_pos_embed
+
+
+class WanI2V:
+    def __init__(self, model: WanModel, device="cuda", num_train_timesteps: int = 1000, vae_stride=(4, 8, 8),
+                 patch_size=(1, 2, 2), z_dim: int = 16):
+        assert model.model_type == "i2v"
+        self.model = model
+        self.device = torch.device(device)
+        self.num_train_timesteps = num_train_timesteps
+        self.vae_stride, self.patch_size, self.z_dim = vae_stride, patch_size, z_dim
+        self._interrupt = False
+
+    @torch.no_grad()
+    def generate(self, input_prompt=None, image_start=None, image_end=None, height=720, width=1280, fit_into_canvas=True,
+                 frame_num=81, shift=5.0, sample_solver="unipc", sampling_steps=40, guide_scale=5.0, n_prompt="", seed=-1,
+                 offload_model=True, callback=None, enable_RIFLEx=False, VAE_tile_size=0, joint_pass=False, slg_layers=None,
+                 slg_start=0.0, slg_end=1.0, cfg_star_switch=True, cfg_zero_step=5, audio_scale=None, audio_cfg_scale=None,
+                 audio_proj=None, audio_context_lens=None, model_filename=None,
+                 context: Optional[torch.Tensor] = None, context_null: Optional[torch.Tensor] = None,
+                 clip_fea: Optional[torch.Tensor] = None, y: Optional[torch.Tensor] = None,
+                 noise: Optional[torch.Tensor] = None, _per_step_latents=None, **bbargs):
+        if audio_proj is not None or audio_scale is not None or image_end is not None:
+            raise NotImplementedError("fantasytalking audio / end-frame conditioning are out of scope")
+        if clip_fea is None or y is None:
+            raise NotImplementedError("CLIP visual and the Wan VAE encoder are out of scope: pass clip_fea= [1,257,1280] and y= [20,T,H/8,W/8]")
+        if context is None or (guide_scale != 1 and context_null is None):
+            raise NotImplementedError("the T5 text encoder is out of scope: pass context= / context_null= embeddings [L, 4096]")
+        if sample_solver != "unipc":
+            raise NotImplementedError("only the default 'unipc' solver is implemented (SURVEY §2 row 15)")
+        dev = self.device
+        target_shape = (self.z_dim, (frame_num - 1) // self.vae_stride[0] + 1, height // self.vae_stride[1], width // self.vae_stride[2])
+        assert tuple(y.shape) == (20,) + target_shape[1:], f"y must be [20, {target_shape[1:]}]"
+        if noise is None:
+            seed_g = torch.Generator(device=dev)
+            seed_g.manual_seed(seed if seed >= 0 else 0)
+            noise = torch.randn(*target_shape, dtype=torch.float32, device=dev, generator=seed_g)     # :226-230
+        latents = noise.to(device=dev, dtype=torch.float32).contiguous()
+        assert tuple(latents.shape) == tuple(target_shape)
+        sch = FlowUniPCMultistepScheduler(num_train_timesteps=self.num_train_timesteps, shift=1, use_dynamic_shifting=False)
+        sch.set_timesteps(sampling_steps, device=dev, shift=shift)                                        # :290-296
+        freqs = get_rotary_pos_embed(latents.shape[1:], enable_RIFLEx=bool(enable_RIFLEx))
+        freqs = (freqs[0].to(dev), freqs[1].to(dev))
+        scratch = torch.empty(2 * 148, device=dev, dtype=torch.float32)
+        ctx = context.to(dev)
+        ctx0 = context_null.to(dev) if context_null is not None else None
+        yd, clip = y.to(dev), clip_fea.to(dev)
+        if callback is not None:
+            callback(-1, None, True)
+        for i, t in enumerate(sch.timesteps_host):
+            ts = torch.tensor([t], device=dev)
+            kw = dict(t=ts, clip_fea=clip, y=yd, freqs=freqs, pipeline=self, current_step=i)
+            if guide_scale == 1:
+                pred = self.model([latents], context=[ctx], **kw)[0]                                     # :340-341
+                if pred is None:
+                    return None
+            else:
+                c, u = self.model([latents, latents], context=[ctx, ctx0], **kw)                        # joint pass :345-349
+                if c is None:
+                    return None
+                pred = ops.cfg_combine(c.contiguous(), u.contiguous(), guide_scale,
+                                       use_alpha=bool(cfg_star_switch and i > cfg_zero_step), scratch=scratch)   # :384-398
+            latents = sch.step(pred.unsqueeze(0), t, latents.unsqueeze(0), return_dict=False)[0].squeeze(0)      # :403-409
+            if _per_step_latents is not None:
+                _per_step_latents.append(latents.clone())
+            if callback is not None:
+                callback(i, latents, False)
+            if self._interrupt:
+                return None
+        return latents

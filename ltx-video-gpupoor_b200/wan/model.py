@@ -31,6 +31,8 @@ WAN_T2V_1_3B = dict(model_type="t2v", patch_size=(1, 2, 2), text_len=512, in_dim
                     freq_dim=256, text_dim=4096, out_dim=16, num_heads=12, num_layers=30, qk_norm=True,
                     cross_attn_norm=True, eps=1e-6)        # wan/configs/wan_t2v_1_3B.py:19-29
 WAN_T2V_14B = dict(WAN_T2V_1_3B, dim=5120, ffn_dim=13824, num_heads=40, num_layers=40)   # wan_t2v_14B.py:19-29
+WAN_I2V_14B = dict(WAN_T2V_14B, model_type="i2v", in_dim=36)                              # wan_i2v_14B.py:25-35
+CLIP_TOKENS = 257                                                                         # WanI2VCrossAttention :306-307
 
 
 class WanModel:
@@ -38,8 +40,8 @@ class WanModel:
                  in_dim=16, dim=2048, ffn_dim=8192, freq_dim=256, text_dim=4096, out_dim=16, num_heads=16,
                  num_layers=32, window_size=(-1, -1), qk_norm=True, cross_attn_norm=True, eps=1e-6, recammaster=False,
                  inject_sample_info=False, fantasytalking_dim=0, sp_group=None):
-        if model_type != "t2v":
-            raise NotImplementedError("i2v (CLIP branch, model.py:277-344) is SURVEY §8(f)#3")
+        if model_type not in ("t2v", "i2v"):
+            raise NotImplementedError("model_type must be 't2v' or 'i2v' (model.py:717)")
         if vace_layers is not None or recammaster or inject_sample_info or fantasytalking_dim:
             raise NotImplementedError("VACE / recam / sample-info / fantasytalking branches are out of scope")
         if not (qk_norm and cross_attn_norm) or tuple(window_size) != (-1, -1):
@@ -98,10 +100,18 @@ class WanModel:
             L["kv2.w"] = torch.cat([kw, vw], 0).contiguous(); L["kv2.b"] = torch.cat([kb, vb], 0).contiguous()
             L["o2.w"], L["o2.b"] = lin(p + "cross_attn.o")
             L["qn2"], L["kn2"] = get(p + "cross_attn.norm_q.weight"), get(p + "cross_attn.norm_k.weight")
+            if self.model_type == "i2v":        # WanI2VCrossAttention k_img / v_img / norm_k_img (:288-291)
+                kw, kb = lin(p + "cross_attn.k_img"); vw, vb = lin(p + "cross_attn.v_img")
+                L["kvi.w"] = torch.cat([kw, vw], 0).contiguous(); L["kvi.b"] = torch.cat([kb, vb], 0).contiguous()
+                L["kni"] = get(p + "cross_attn.norm_k_img.weight")
             L["n3.w"], L["n3.b"] = get(p + "norm3.weight"), get(p + "norm3.bias")
             L["ff1.w"], L["ff1.b"] = lin(p + "ffn.0"); L["ff2.w"], L["ff2.b"] = lin(p + "ffn.2")
             layers.append(L)
         w["block_mods"] = torch.stack(mods, 0).contiguous()                          # [L, 6, D]
+        if self.model_type == "i2v":            # img_emb = MLPProj(1280, dim) (:576-588, :768-769)
+            w["ie.ln0.w"], w["ie.ln0.b"] = get("img_emb.proj.0.weight"), get("img_emb.proj.0.bias")
+            w["ie.1.w"], w["ie.1.b"] = lin("img_emb.proj.1"); w["ie.3.w"], w["ie.3.b"] = lin("img_emb.proj.3")
+            w["ie.ln4.w"], w["ie.ln4.b"] = get("img_emb.proj.4.weight"), get("img_emb.proj.4.bias")
         extra = [k for k in state_dict if k not in used]
         if strict and extra:
             raise KeyError(f"unexpected keys in state_dict: {extra[:5]} ...")
@@ -153,8 +163,12 @@ class WanModel:
                 fps=None, causal_block_size=1, causal_attention=False, audio_proj=None, audio_context_lens=None,
                 audio_scale=None):
         """model.py:902-1111 (t2v)."""
-        if vace_context is not None or clip_fea is not None or y is not None or cam_emb is not None or audio_proj is not None:
-            raise NotImplementedError("VACE / i2v / camera / audio inputs are out of scope")
+        if vace_context is not None or cam_emb is not None or audio_proj is not None:
+            raise NotImplementedError("VACE / camera / audio inputs are out of scope")
+        if self.model_type == "i2v":
+            assert clip_fea is not None and y is not None                             # :930-931
+        elif clip_fea is not None or y is not None:
+            raise ValueError("clip_fea / y are i2v inputs (model_type='i2v')")
         if slg_layers is not None or self.enable_teacache:
             raise NotImplementedError("SLG / TeaCache step skipping is SURVEY §8(f)#4")
         w, D, H, eps = self.w, self.dim, self.num_heads, self.eps
@@ -168,7 +182,10 @@ class WanModel:
         assert N % P == 0 and H % P == 0, "Ulysses needs tokens and heads divisible by the group size"
         n_loc = N // P
         # ---- embeddings (replicated; the token shard is taken right after the patch rows are built, :131-133)
-        rows = torch.stack([self._patchify(u.to(dev)) for u in x_list], 0)            # [B, N, 64]
+        if y is not None:                       # i2v: [mask(4) | image latent(16)] channels appended to every sequence (:948-949)
+            yd = y.to(dev)
+            x_list = [torch.cat([u.to(dev), yd.to(u.dtype)], dim=0) for u in x_list]
+        rows = torch.stack([self._patchify(u.to(dev)) for u in x_list], 0)            # [B, N, C*4]
         rows = rows[:, rank * n_loc:(rank + 1) * n_loc].to(BF16).reshape(B * n_loc, -1).contiguous()
         xs = ops.gemm(rows, w["patch.w"], w["patch.b"])                               # [B*n_loc, D]
         tt = t.to(device=dev, dtype=torch.float32).flatten().contiguous()
@@ -182,6 +199,13 @@ class WanModel:
             ctx_in[i, : u.shape[0]] = u.to(device=dev, dtype=BF16)
         ctx = ops.gemm(ops.gemm(ctx_in.view(B * self.text_len, -1), w["text0.w"], w["text0.b"], act=ops.ACT_GELU_TANH),
                        w["text2.w"], w["text2.b"])                                    # [B*512, D]
+        ctx_img = None
+        if clip_fea is not None:                # img_emb: LayerNorm -> Linear -> GELU(erf) -> Linear -> LayerNorm (:996-998)
+            cf = clip_fea.to(device=dev, dtype=BF16).reshape(-1, clip_fea.shape[-1]).contiguous()          # [257, 1280]
+            assert cf.shape[0] == CLIP_TOKENS, "clip_fea must be [1, 257, 1280] (one image for all sequences)"
+            c1 = ops.norm_mod(cf, weight=w["ie.ln0.w"], bias=w["ie.ln0.b"], eps=1e-5, layer_norm=True)
+            c2 = ops.gemm(ops.gemm(c1, w["ie.1.w"], w["ie.1.b"], act=ops.ACT_GELU_ERF), w["ie.3.w"], w["ie.3.b"])
+            ctx_img = ops.norm_mod(c2, weight=w["ie.ln4.w"], bias=w["ie.ln4.b"], eps=1e-5, layer_norm=True)  # [257, D]
         cos, sin = freqs
         cos = cos.to(device=dev, dtype=torch.float32).contiguous()
         sin = sin.to(device=dev, dtype=torch.float32).contiguous()
@@ -213,6 +237,12 @@ class WanModel:
             ops.qk_norm_rope_wan(q2, kv[:, :D], Lw["qn2"], Lw["kn2"], None, None, eps=eps)
             kv3 = kv.view(B, Lc, 2 * D)
             o2 = ops.attention(q2.view(B, n_loc, H, 128), kv3[:, :, :D].unflatten(-1, (H, 128)), kv3[:, :, D:].unflatten(-1, (H, 128)))
+            if ctx_img is not None:             # WanI2VCrossAttention :323-337: same q over the 257 image tokens, x += img_x
+                kvi = ops.gemm(ctx_img, Lw["kvi.w"], Lw["kvi.b"])                                       # [257, 2D]
+                ops.qk_norm_rope_wan(None, kvi[:, :D], None, Lw["kni"], None, None, eps=eps)
+                kvb = kvi.unsqueeze(0).repeat(B, 1, 1) if B > 1 else kvi.unsqueeze(0)                   # same image for every sequence
+                ops.attention(q2.view(B, n_loc, H, 128), kvb[:, :, :D].unflatten(-1, (H, 128)),
+                              kvb[:, :, D:].unflatten(-1, (H, 128)), out=o2, accumulate=True)
             ops.gemm(o2.view(M, D), Lw["o2.w"], Lw["o2.b"], residual=xs, out=xs)                       # x += cross_attn :465
             y2 = ops.norm_mod(xs, m[:, 4], m[:, 3], rows_per_group=M, eps=eps, layer_norm=True)        # :467-472
             ff = ops.gemm(y2, Lw["ff1.w"], Lw["ff1.b"], act=ops.ACT_GELU_TANH)

@@ -33,8 +33,8 @@ class _Pipe:
 
 def build_ref(cfg, sd):
     from wan.modules.model import WanModel
-    m = WanModel(model_type="t2v", dim=cfg["dim"], ffn_dim=cfg["ffn_dim"], num_heads=cfg["num_heads"],
-                 num_layers=cfg["num_layers"], in_dim=16, out_dim=16, text_len=512, freq_dim=256, eps=1e-6)
+    m = WanModel(model_type=cfg.get("model_type", "t2v"), dim=cfg["dim"], ffn_dim=cfg["ffn_dim"], num_heads=cfg["num_heads"],
+                 num_layers=cfg["num_layers"], in_dim=cfg["in_dim"], out_dim=16, text_len=512, freq_dim=256, eps=1e-6)
     missing, unexpected = m.load_state_dict(sd, strict=True)
     m.enable_teacache = False
     return m.double().eval()
@@ -101,6 +101,50 @@ def main():
                     cos_row=cos_r[17].clone(), sin_row=sin_r[17].clone()),
                os.path.join(GOLD, "wan_t2v.pt"))
     print("written", os.path.join(GOLD, "wan_t2v.pt"))
+    main_i2v()
+
+
+def main_i2v():
+    """WanModel(model_type='i2v'): y channels (in_dim 36), img_emb MLPProj over 257 CLIP tokens, WanI2VCrossAttention
+    (model.py:277-344, 576-588, 930-998) and the image2video.py:328-414 loop (CFG over cond / uncond with shared y, clip)."""
+    from wan.modules.posemb_layers import get_rotary_pos_embed
+    from wan.utils.fm_solvers_unipc import FlowUniPCMultistepScheduler
+    cfg = dict(TINY, model_type="i2v", in_dim=36, clip_dim=1280)
+    sd = {k: v.double() for k, v in W.make_wan_state_dict(cfg, seed=1).items()}
+    ref = build_ref(cfg, sd)
+    g = torch.Generator().manual_seed(5)
+    lat = torch.randn(16, 3, 8, 12, generator=g).double()
+    yy = torch.randn(20, 3, 8, 12, generator=g).double()
+    clip = torch.randn(1, 257, 1280, generator=g).double()
+    ctx = torch.randn(20, 4096, generator=g).double()
+    ctx0 = torch.randn(11, 4096, generator=g).double()
+    cos_r, sin_r = get_rotary_pos_embed(lat.shape[1:], enable_RIFLEx=False)
+    cos, sin = W.rope_tables(lat.shape[1:])
+    t = torch.tensor([833])
+    y_ref = ref([lat.clone(), lat.clone()], t=t, context=[ctx, ctx0], clip_fea=clip, y=yy, freqs=(cos_r, sin_r), pipeline=_Pipe())
+    y = W.wan_forward(sd, cfg, [lat, lat], t, [ctx, ctx0], cos, sin, clip_fea=clip, y=yy)
+    for a, b in zip(y, y_ref):
+        e = rel_l2(a, b)
+        print(f"  i2v wan_forward: rel_l2(oracle, reference) = {e:.3e}")
+        assert e < 2e-5
+    s = FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False)
+    s.set_timesteps(4, device="cpu", shift=5.0)
+    latents = lat.clone()
+    ref_steps = []
+    for tt in s.timesteps:
+        c, u = ref([latents, latents], t=torch.stack([tt]), context=[ctx, ctx0], clip_fea=clip, y=yy, freqs=(cos_r, sin_r), pipeline=_Pipe())
+        pred = u + 5.0 * (c - u)
+        latents = s.step(pred.unsqueeze(0), tt, latents.unsqueeze(0), return_dict=False)[0].squeeze(0)
+        ref_steps.append(latents.clone())
+    mine = []
+    W.t2v_denoise(sd, cfg, lat, ctx, ctx0, steps=4, shift=5.0, guide_scale=5.0, per_step=mine, clip_fea=clip, y=yy)
+    for i, (a, b) in enumerate(zip(mine, ref_steps)):
+        e = rel_l2(a, b)
+        print(f"  i2v loop step {i}: rel_l2 = {e:.3e}")
+        assert e < 5e-5
+    torch.save(dict(cfg=cfg, lat=lat.float(), y=yy.float(), clip=clip.float(), ctx=ctx.float(), ctx0=ctx0.float(), t=t,
+                    fwd=[a.clone() for a in y_ref], loop=[a.float() for a in ref_steps]), os.path.join(GOLD, "wan_i2v.pt"))
+    print("written", os.path.join(GOLD, "wan_i2v.pt"))
 
 
 if __name__ == "__main__":

@@ -60,6 +60,16 @@ def make_wan_state_dict(cfg: dict, seed: int = 0, num_layers: Optional[int] = No
         sd[p + "modulation"] = torch.randn(1, 6, D, generator=g) / D ** 0.5
     lin("head.head", cfg["out_dim"] * math.prod(cfg["patch_size"]), D)
     sd["head.modulation"] = torch.randn(1, 2, D, generator=g) / D ** 0.5
+    if cfg.get("model_type", "t2v") == "i2v":
+        # WanI2VCrossAttention k_img / v_img / norm_k_img (model.py:288-291) and MLPProj img_emb (:576-588, :768-769)
+        for i in range(L):
+            p = f"blocks.{i}.cross_attn."
+            lin(p + "k_img", D, D); lin(p + "v_img", D, D)
+            sd[p + "norm_k_img.weight"] = 1.0 + 0.1 * torch.randn(D, generator=g)
+        C = cfg.get("clip_dim", 1280)
+        sd["img_emb.proj.0.weight"] = 1.0 + 0.1 * torch.randn(C, generator=g); sd["img_emb.proj.0.bias"] = 0.1 * torch.randn(C, generator=g)
+        lin("img_emb.proj.1", C, C); lin("img_emb.proj.3", D, C)
+        sd["img_emb.proj.4.weight"] = 1.0 + 0.1 * torch.randn(D, generator=g); sd["img_emb.proj.4.bias"] = 0.1 * torch.randn(D, generator=g)
     return sd
 
 
@@ -128,9 +138,17 @@ def wan_block(sd, i, x, e0, cos, sin, ctx, cfg, attn_fn=None):
     x = x + y * e[2]                                                                    # :458 addcmul_
     y = F.layer_norm(x, (D,), sd[p + "norm3.weight"], sd[p + "norm3.bias"], eps=eps)    # :461
     q = wan_rms_norm(_lin(sd, p + "cross_attn.q", y), sd[p + "cross_attn.norm_q.weight"], eps).view(B, N, H, d)
+    ctx_img = None
+    if (p + "cross_attn.k_img.weight") in sd:                                           # WanI2VCrossAttention :292-344
+        ctx_img, ctx = ctx[:, :257], ctx[:, 257:]
     k = wan_rms_norm(_lin(sd, p + "cross_attn.k", ctx), sd[p + "cross_attn.norm_k.weight"], eps).view(B, -1, H, d)
     v = _lin(sd, p + "cross_attn.v", ctx).view(B, -1, H, d)
-    x = x + _lin(sd, p + "cross_attn.o", attention_core(q, k, v).flatten(2))            # :465
+    a2 = attention_core(q, k, v).flatten(2)
+    if ctx_img is not None:
+        ki = wan_rms_norm(_lin(sd, p + "cross_attn.k_img", ctx_img), sd[p + "cross_attn.norm_k_img.weight"], eps).view(B, -1, H, d)
+        vi = _lin(sd, p + "cross_attn.v_img", ctx_img).view(B, -1, H, d)
+        a2 = a2 + attention_core(q, ki, vi).flatten(2)                                   # x += img_x :337
+    x = x + _lin(sd, p + "cross_attn.o", a2)                                            # :465
     y = F.layer_norm(x, (D,), eps=eps) * (1 + e[4]) + e[3]                              # :467-472
     y = _lin(sd, p + "ffn.2", F.gelu(_lin(sd, p + "ffn.0", y), approximate="tanh"))     # :479-488
     return x + y * e[5]                                                                 # :491
@@ -151,7 +169,7 @@ def unpatchify(u: Tensor, grid: Sequence[int], cfg) -> Tensor:
 
 
 def wan_forward(sd: Dict[str, Tensor], cfg: dict, x_list: List[Tensor], t: Tensor, context: List[Tensor],
-                cos: Tensor, sin: Tensor, attn_fn=None) -> List[Tensor]:
+                cos: Tensor, sin: Tensor, attn_fn=None, clip_fea: Optional[Tensor] = None, y: Optional[Tensor] = None) -> List[Tensor]:
     """WanModel.forward for t2v (model.py:902-1111): x_list of [16, F, H, W]; t [1]; context list of [L<=512, 4096];
     returns list of float32 [16, F, H, W].  Sequences are batched (the reference iterates them per block)."""
     D = cfg["dim"]
@@ -162,12 +180,21 @@ def wan_forward(sd: Dict[str, Tensor], cfg: dict, x_list: List[Tensor], t: Tenso
     for x in x_list:
         Fr, H, W = x.shape[1:]
         grid = (Fr, H // 2, W // 2)
+        if y is not None:
+            x = torch.cat([x, y.to(x.dtype)], dim=0)                                      # i2v: [mask(4) | image latent(16)] channels, model.py:948-949
         xs.append(F.linear(patchify(x.to(dt), cfg), w, sd["patch_embedding.bias"]))
     x = torch.stack(xs, 0)                                                               # [B, N, D]
     e = _lin(sd, "time_embedding.2", F.silu(_lin(sd, "time_embedding.0", sinusoidal_embedding_1d(cfg["freq_dim"], t.flatten()).to(dt))))
     e0 = _lin(sd, "time_projection.1", F.silu(e)).unflatten(1, (6, D))                    # [1, 6, D]
     ctx = torch.stack([_lin(sd, "text_embedding.2", F.gelu(_lin(sd, "text_embedding.0", torch.cat(
         [u.to(dt), u.new_zeros(cfg["text_len"] - u.size(0), u.size(1)).to(dt)])), approximate="tanh")) for u in context], 0)
+    if clip_fea is not None:                                                             # img_emb MLPProj, model.py:996-998
+        c = clip_fea.to(dt)
+        C = c.shape[-1]
+        c = F.layer_norm(c, (C,), sd["img_emb.proj.0.weight"], sd["img_emb.proj.0.bias"])
+        c = _lin(sd, "img_emb.proj.3", F.gelu(_lin(sd, "img_emb.proj.1", c)))
+        c = F.layer_norm(c, (D,), sd["img_emb.proj.4.weight"], sd["img_emb.proj.4.bias"])
+        ctx = torch.cat([c.expand(ctx.shape[0], -1, -1), ctx], dim=1)
     for i in range(L):
         x = wan_block(sd, i, x, e0, cos, sin, ctx, cfg, attn_fn)
     eh = (sd["head.modulation"] + e.unsqueeze(1)).chunk(2, dim=1)                         # model.py:566-572
@@ -267,8 +294,10 @@ class UniPC:
 
 def t2v_denoise(sd, cfg, noise: Tensor, context: Tensor, context_null: Tensor, steps: int, shift: float = 5.0,
                 guide_scale: float = 5.0, per_step: Optional[list] = None, attn_fn=None,
-                cfg_star_switch: bool = False, cfg_zero_step: int = 5) -> Tensor:
-    """WanT2V.generate denoise loop, UniPC, plain CFG (text2video.py:399-575).  noise [16, F, H, W] fp32."""
+                cfg_star_switch: bool = False, cfg_zero_step: int = 5, clip_fea: Optional[Tensor] = None,
+                y: Optional[Tensor] = None) -> Tensor:
+    """WanT2V.generate denoise loop, UniPC, plain CFG (text2video.py:399-575).  noise [16, F, H, W] fp32.
+    With clip_fea / y it is the WanI2V.generate loop (image2video.py:328-414): same y and CLIP tokens for both passes."""
     sch = UniPC()
     sch.set_timesteps(steps, shift)
     cos, sin = rope_tables(noise.shape[1:])
@@ -276,9 +305,9 @@ def t2v_denoise(sd, cfg, noise: Tensor, context: Tensor, context_null: Tensor, s
     for i, t in enumerate(sch.timesteps):
         ts = torch.stack([t])
         if guide_scale == 1:
-            pred = wan_forward(sd, cfg, [lat], ts, [context], cos, sin, attn_fn)[0]
+            pred = wan_forward(sd, cfg, [lat], ts, [context], cos, sin, attn_fn, clip_fea=clip_fea, y=y)[0]
         else:
-            c, u = wan_forward(sd, cfg, [lat, lat], ts, [context, context_null], cos, sin, attn_fn)
+            c, u = wan_forward(sd, cfg, [lat, lat], ts, [context, context_null], cos, sin, attn_fn, clip_fea=clip_fea, y=y)
             if cfg_star_switch and i > cfg_zero_step:                                     # :551-561 (optimized_scale :31-42)
                 alpha = torch.sum(c.flatten() * u.flatten()) / (torch.sum(u.flatten() ** 2) + 1e-8)
                 u = u * alpha

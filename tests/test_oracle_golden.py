@@ -74,3 +74,20 @@ def test_pipeline_matches_reference(golden_dir):
                              rescaling_scale=kw["rescaling_scale"], skip_block_list=kw.get("skip_block_list"),
                              strategy=O.SKIP_ATTENTION_VALUES if "skip_block_list" in kw else None)
         assert O.rel_l2(O.unpatchify(lat, 3, 4, 6), g[tag]["latents"]) < 5e-5
+
+
+def test_wan_i2v_oracle_matches_reference(golden_dir):
+    """wan_oracle with the i2v branch (y channels, img_emb MLPProj, WanI2VCrossAttention) vs the fixture recorded from
+    the unmodified reference WanModel(model_type='i2v') in fp64 (oracle/gen_golden_wan.py:main_i2v)."""
+    from oracle import wan_oracle as W
+    g = _load(golden_dir, "wan_i2v.pt")
+    cfg = g["cfg"]
+    sd = W.make_wan_state_dict(cfg, seed=1)
+    cos, sin = W.rope_tables(g["lat"].shape[1:])
+    y = W.wan_forward(sd, cfg, [g["lat"], g["lat"]], g["t"], [g["ctx"], g["ctx0"]], cos, sin, clip_fea=g["clip"], y=g["y"])
+    for a, b in zip(y, g["fwd"]):
+        assert W.rel_l2(a, b.float()) < 5e-5          # fp32 oracle vs fp64 reference
+    steps = []
+    W.t2v_denoise(sd, cfg, g["lat"], g["ctx"], g["ctx0"], steps=4, shift=5.0, guide_scale=5.0, per_step=steps, clip_fea=g["clip"], y=g["y"])
+    for a, b in zip(steps, g["loop"]):
+        assert W.rel_l2(a, b) < 2e-4

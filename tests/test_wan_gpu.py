@@ -143,3 +143,54 @@ def test_wan_sequence_parallel_two_gpus(golden_dir):
         for mode, e in errs.items():
             print(f"rank {r}: SP forward ({mode} exchange) rel_l2 vs single-GPU reference = {e:.3e}")
             assert e < 3e-2
+
+
+# ------------------------------------------------------------------ i2v (WanI2VCrossAttention, img_emb, y channels)
+def test_wan_i2v_forward_and_loop_vs_reference_fixture(golden_dir):
+    from ltx_video_gpupoor_b200.wan.image2video import WanI2V
+    g = torch.load(os.path.join(golden_dir, "wan_i2v.pt"), weights_only=False)
+    cfg = g["cfg"]
+    sd = W.make_wan_state_dict(cfg, seed=1)
+    m = WanModel(model_type="i2v", in_dim=cfg["in_dim"], dim=cfg["dim"], ffn_dim=cfg["ffn_dim"], num_heads=cfg["num_heads"],
+                 num_layers=cfg["num_layers"])
+    m.load_state_dict(sd)
+    cos, sin = get_rotary_pos_embed(g["lat"].shape[1:])
+    y = m([g["lat"].to(DEV), g["lat"].to(DEV)], t=g["t"].to(DEV), context=[g["ctx"].to(DEV), g["ctx0"].to(DEV)],
+          clip_fea=g["clip"].to(DEV), y=g["y"].to(DEV), freqs=(cos, sin))
+    torch.cuda.synchronize()
+    for a, b in zip(y, g["fwd"]):
+        e = W.rel_l2(a.cpu(), b.float())
+        print(f"wan i2v forward rel_l2 vs reference = {e:.3e}")
+        assert e < 2e-2
+    steps = []
+    pipe = WanI2V(m)
+    pipe.generate(width=96, height=64, frame_num=9, shift=5.0, sampling_steps=4, guide_scale=5.0, cfg_star_switch=False,
+                  context=g["ctx"], context_null=g["ctx0"], clip_fea=g["clip"], y=g["y"], noise=g["lat"], _per_step_latents=steps)
+    for i, (a, b) in enumerate(zip(steps, g["loop"])):
+        e = W.rel_l2(a.cpu(), b)
+        print(f"wan i2v step {i}: latents rel_l2 vs reference = {e:.3e}")
+        assert e < 2e-2
+    with pytest.raises(NotImplementedError):
+        pipe.generate(context=g["ctx"], context_null=g["ctx0"])           # raw images need the (out-of-scope) encoders
+
+
+def test_attention_accumulate_and_exact_gelu():
+    B, H, Lq, Lk, d = 2, 3, 200, 257, 128
+    gq = torch.Generator().manual_seed(11)
+    q, k, v = [torch.randn(B, L, H, d, generator=gq).bfloat16().to(DEV) for L in (Lq, Lk, Lk)]
+    base = torch.randn(B, Lq, H, d, generator=gq).bfloat16().to(DEV)
+    out = base.clone()
+    ops.attention(q, k, v, out=out, accumulate=True)
+    ref = base.float().cpu() + W.attention_core(q.float().cpu(), k.float().cpu(), v.float().cpu())
+    assert W.rel_l2(out.float().cpu(), ref) < 1e-2
+    x = torch.randn(64, 256, generator=gq).bfloat16().to(DEV)
+    assert W.rel_l2(ops.act(x, ops.ACT_GELU_ERF).float().cpu(), torch.nn.functional.gelu(x.float().cpu())) < 5e-3
+    w = (torch.randn(128, 256, generator=gq) * 0.06).bfloat16().to(DEV)
+    bsum = torch.randn(128, generator=gq).bfloat16().to(DEV)
+    yy = ops.gemm(x, w, bsum, act=ops.ACT_GELU_ERF)
+    assert W.rel_l2(yy.float().cpu(), torch.nn.functional.gelu(x.float().cpu() @ w.float().cpu().T + bsum.float().cpu())) < 6e-3
+    # LayerNorm over 1280 channels (CLIP width) with affine
+    c = torch.randn(257, 1280, generator=gq).bfloat16().to(DEV)
+    lw, lb = (1 + 0.1 * torch.randn(1280, generator=gq)).bfloat16().to(DEV), (0.1 * torch.randn(1280, generator=gq)).bfloat16().to(DEV)
+    ln = ops.norm_mod(c, weight=lw, bias=lb, eps=1e-5, layer_norm=True)
+    assert W.rel_l2(ln.float().cpu(), torch.nn.functional.layer_norm(c.float().cpu(), (1280,), lw.float().cpu(), lb.float().cpu(), 1e-5)) < 6e-3
