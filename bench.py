@@ -340,6 +340,23 @@ def run_wan(args, wl):
         tt = torch.tensor([e2e_s], device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt)
+    decode_s = None
+    if rank == 0 and not args.no_decode and wl["model"] == "1.3B":
+        # WanVAE.decode of the full latent video on one GPU (text2video.py:590): part of s/video
+        from ltx_video_gpupoor_b200.wan.vae import WanVAE
+        from ltx_video_gpupoor_b200.wan.init_weights import random_wan_vae_decoder_state_dict
+        vae = WanVAE(device=dev)
+        vae.load_state_dict(random_wan_vae_decoder_state_dict(seed=1), device=dev)
+        z = torch.randn(*shape, device=dev)
+        vae.decode([z], 0)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        img = vae.decode([z], 0)[0]
+        b.record()
+        torch.cuda.synchronize()
+        decode_s = a.elapsed_time(b) / 1e3
+        del img, vae
     if rank == 0:
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
@@ -360,7 +377,8 @@ def run_wan(args, wl):
                 "e2e": {"value": K / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": (noise_h.numel() * 4 + 2 * ctx_h.numel() * 2) / K,
                         "d2h_bytes_per_step": out_h.numel() * 4 / K, "steps_in_call": K},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-                "s_per_video_denoise": S * ms_step / 1e3,
+                "s_per_video_denoise": S * ms_step / 1e3, "vae_decode_s": decode_s,
+                "s_per_video": (S * ms_step / 1e3 + decode_s) if decode_s is not None else None,
                 "model_tflops_per_gpu": 2 * wl["fwd_flops"] * (cfg["num_layers"] / (30 if wl["model"] == "1.3B" else 40)) / (ms_step / 1e3) / 1e12 / world,
                 "kernels": kernels}
         print(json.dumps(line))

@@ -136,6 +136,22 @@ int ltxb200_pixelnorm_silu_bf16(const void* x, void* y, int64_t voxels, int C, f
 int ltxb200_latent_to_ndhwc(const void* z, int is_f32, void* out, int B, int C, int64_t FHW, const float* stdv,
                             const float* meanv, void* stream);
 
+/* ---- Wan2.1 VAE decode (wan/modules/vae.py:386-493): the pieces the LTX decoder kernels do not already cover ---- */
+/* convolution with taps_t x taps_hw x taps_hw taps (each 1 or 3) on NDHWC bf16, w = [Cout, taps*Cin] tap-major, causal in time
+ * (taps t-2,t-1,t) with ZERO temporal padding when causal_zero_pad != 0 (Wan CausalConv3d, vae.py:17-37; Conv2d 3x3 of
+ * Resample with taps_t = 1, :80-88; time_conv with taps_hw = 1, :86-88) or replicate padding otherwise; optional residual. */
+int ltxb200_conv_taps_bf16(const void* x, const void* w, const void* bias, void* out, int B, int T, int H, int W, int Cin,
+                           int Cout, int taps_t, int taps_hw, int causal_zero_pad, const void* residual, void* stream);
+/* RMS_norm (vae.py:41-58: F.normalize over channels * sqrt(c_real) * gamma) + optional SiLU on [voxels, C] bf16 */
+int ltxb200_l2norm_silu_bf16(const void* x, void* y, int64_t voxels, int C, int c_real, const void* gamma, int apply_silu,
+                             void* stream);
+/* nearest(-exact) x2 upsample of NHWC frames (vae.py:61-67,80-82): [frames, H, W, C] -> [frames, 2H, 2W, C] */
+int ltxb200_upsample2x_nhwc_bf16(const void* x, void* y, int64_t frames, int H, int W, int C, void* stream);
+/* P = softmax(scale * S) row-wise, S fp32 [rows, ld_s] -> P bf16 [rows, ld_p] (AttentionBlock, vae.py:257-263: one head of
+ * width C = 384, computed as two tcgen05 GEMMs around this kernel) */
+int ltxb200_softmax_rows_f32_bf16(const float* s, int64_t ld_s, void* p, int64_t ld_p, int rows, int cols, float scale,
+                                  void* stream);
+
 /* as ltxb200_attention_bf16, but out += attention(q, k, v) (bf16 read-modify-write in the epilogue): the image-token
  * branch of WanI2VCrossAttention, `x += img_x` (wan/modules/model.py:329-337), without a separate add pass. */
 int ltxb200_attention_acc_bf16(const void* q, int64_t ldq, int64_t bsq, const void* k, int64_t ldk, int64_t bsk,

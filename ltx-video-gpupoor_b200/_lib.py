@@ -41,6 +41,10 @@ def _declare(lib):
         "ltxb200_cfg_combine_f32": ([P, P, P, L, F, I, P, P], I),
         "ltxb200_pixelnorm_silu_bf16": ([P, P, L, I, F, I, P], I),
         "ltxb200_latent_to_ndhwc": ([P, I, P, I, I, L, P, P, P], I),
+        "ltxb200_conv_taps_bf16": ([P, P, P, P, I, I, I, I, I, I, I, I, I, P, P], I),
+        "ltxb200_l2norm_silu_bf16": ([P, P, L, I, I, P, I, P], I),
+        "ltxb200_upsample2x_nhwc_bf16": ([P, P, L, I, I, I, P], I),
+        "ltxb200_softmax_rows_f32_bf16": ([P, L, P, L, I, I, F, P], I),
         "ltxb200_comm_alloc": ([c_size_t, POINTER(c_void_p), P], I),
         "ltxb200_comm_open": ([P, POINTER(c_void_p)], I),
         "ltxb200_comm_close": ([P], I),

@@ -653,6 +653,89 @@ pixelnorm_silu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __rest
   }
 }
 
+// Wan VAE RMS_norm (wan/modules/vae.py:41-58) + optional SiLU on NDHWC voxels:
+//   y = x / max(||x||_2, 1e-12) * sqrt(c_real) * gamma[c]      (F.normalize over the channel dim)
+// C is the stored (64-padded) channel count, c_real the model's; pad channels hold zeros and gamma = 0 there.
+__host__ __device__ constexpr int l2_group(int c8) { int g = 32; while (c8 % g) g >>= 1; return g; }   // largest power of two <= 32 dividing C/8
+template <int C>
+__global__ void __launch_bounds__(256)
+l2norm_silu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long voxels,
+                   const __nv_bfloat16* __restrict__ gamma, float scale, int apply_silu) {
+  constexpr int G = l2_group(C / 8);
+  constexpr int NV = C / (8 * G);
+  constexpr int VPW = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long vox = warp_global * VPW + lane / G;
+  const int gl = lane % G;
+  const bool ok = vox < voxels;
+  float v[NV][8];
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    if (ok) load8(x + vox * C + (i * G + gl) * 8, v[i]);
+    else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sq += v[i][j] * v[i][j];
+  }
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float inv = scale / fmaxf(sqrtf(sq), 1e-12f);
+  if (!ok) return;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float g[8], o[8];
+    load8(gamma + (i * G + gl) * 8, g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float t = bf16r(v[i][j] * inv * g[j]);
+      o[j] = apply_silu ? __fdividef(t, 1.0f + __expf(-t)) : t;
+    }
+    store8(y + vox * C + (i * G + gl) * 8, o);
+  }
+}
+
+// nearest x2 spatial upsample of NDHWC frames (Upsample(scale_factor=(2,2), mode='nearest-exact'), vae.py:61-88):
+// out[f, 2h+a, 2w+b, :] = in[f, h, w, :].  One thread per 16 B of OUTPUT.
+__global__ void upsample2x_nhwc_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long frames,
+                                       int H, int W, int C) {
+  const int c8 = C / 8;
+  const long long n = frames * (2LL * H) * (2LL * W) * c8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % c8);
+    long long r = i / c8;
+    const int ow = static_cast<int>(r % (2 * W)); r /= 2 * W;
+    const int oh = static_cast<int>(r % (2 * H));
+    const long long f = r / (2 * H);
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + ((f * H + (oh >> 1)) * W + (ow >> 1)) * C) + c);
+    reinterpret_cast<uint4*>(y)[i] = v;
+  }
+}
+
+// row softmax: P[r, :] = softmax(scale * S[r, :]) ; S fp32 [rows, ld_s], P bf16 [rows, ld_p]; one warp per row.
+// (the single 384-wide head of the Wan VAE AttentionBlock, vae.py:249-272, does not fit the flash kernel's head dims)
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(const float* __restrict__ S, __nv_bfloat16* __restrict__ P, int rows, int cols, long long ld_s,
+                    long long ld_p, float scale_log2) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* s = S + row * ld_s;
+  float m = -INFINITY;
+  for (int c = lane; c < cols; c += 32) m = fmaxf(m, s[c]);
+  m = warp_max(m) * scale_log2;
+  float l = 0.f;
+  for (int c = lane; c < cols; c += 32) l += fast_exp2(fmaf(s[c], scale_log2, -m));
+  l = warp_sum(l);
+  const float inv = 1.0f / l;
+  __nv_bfloat16* pr = P + row * ld_p;
+  for (int c = lane; c < cols; c += 32) pr[c] = __float2bfloat16_rn(fast_exp2(fmaf(s[c], scale_log2, -m)) * inv);
+}
+
 // latents [B, C, F, H, W] fp32/bf16 (NCDHW) -> per-channel de-normalise (x*std+mean) -> NDHWC bf16
 // (vae_encode.py:239-247).  Small tensor: one thread per output element.
 template <typename T>

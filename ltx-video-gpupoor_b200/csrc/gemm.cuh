@@ -45,8 +45,10 @@ struct GemmParams {
   int cB, cT, cH, cW, cCin;
   int cBH, cBW;
   int c_tiles_h, c_tiles_w;
-  int c_causal;                    // 1: taps (t-2,t-1,t) ; 0: (t-1,t,t+1), both clamped (replicate)
-  int c_taps_t;                    // 3 for 3x3x3, 1 for 1x1x1 (then also 1x1 spatial)
+  int c_causal;                    // 1: taps (t-2,t-1,t) ; 0: (t-1,t,t+1)
+  int c_taps_t;                    // temporal taps: 3 or 1
+  int c_taps_hw;                   // spatial taps per axis: 3 (zero padding) or 1
+  int c_tpad_zero;                 // temporal padding: 0 = replicate (clamped frame index, LTX), 1 = zeros (TMA OOB fill, Wan)
   // tile rasterisation of the persistent schedule: 0 = M fastest (one weight panel per wave, all of A re-read per
   // N tile), 1 = N fastest (a wave = a few row panels x every N tile: A streams through once, W stays in L2)
   int n_fastest;
@@ -83,7 +85,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int tiles_n = (p.N + BN - 1) / BN;
   const int num_tiles = tiles_m * tiles_n;
   const int kb_per_tap = kConv ? (p.cCin + kGemmBK - 1) / kGemmBK : 1;
-  const int taps = kConv ? p.c_taps_t * p.c_taps_t * p.c_taps_t : 1;
+  const int taps = kConv ? p.c_taps_t * p.c_taps_hw * p.c_taps_hw : 1;
   const int num_kb = kConv ? taps * kb_per_tap : (p.K + kGemmBK - 1) / kGemmBK;
 
   if (threadIdx.x == 0) {
@@ -127,12 +129,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
           if (kConv) {
             const int tap = kb / kb_per_tap, cblk = kb - tap * kb_per_tap;
-            int kt = 0, kh = 0, kw = 0;
-            if (p.c_taps_t == 3) { kt = tap / 9; kh = (tap / 3) % 3; kw = tap % 3; }
+            const int thw = p.c_taps_hw * p.c_taps_hw;
+            const int kt = tap / thw, kh = (tap % thw) / p.c_taps_hw, kw = tap % p.c_taps_hw;     // tap-major K: (kt, kh, kw, ci)
             int tt = ct, hh = ch0, ww = cw0;
             if (p.c_taps_t == 3) {
               tt = p.c_causal ? ct + kt - 2 : ct + kt - 1;
-              tt = tt < 0 ? 0 : (tt > p.cT - 1 ? p.cT - 1 : tt);
+              if (!p.c_tpad_zero) tt = tt < 0 ? 0 : (tt > p.cT - 1 ? p.cT - 1 : tt);            // replicate; else TMA zero-fills t < 0
+            }
+            if (p.c_taps_hw == 3) {
               hh = ch0 + kh - 1;
               ww = cw0 + kw - 1;
             }

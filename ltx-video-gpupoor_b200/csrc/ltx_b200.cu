@@ -113,10 +113,11 @@ extern "C" int ltxb200_gemm_bf16(const void* A, int64_t lda, const void* W, int6
 // ------------------------------------------------------------------------------------------
 // conv3d (implicit GEMM)
 // ------------------------------------------------------------------------------------------
-extern "C" int ltxb200_conv3d_bf16(const void* x, const void* w, const void* bias, void* out, int B, int T, int H,
-                                   int W, int Cin, int Cout, int causal, int store_mode, int out_f32,
-                                   const void* residual, void* stream) {
+static int conv_impl(const void* x, const void* w, const void* bias, void* out, int B, int T, int H, int W, int Cin, int Cout,
+                     int taps_t, int taps_hw, int causal, int tpad_zero, int store_mode, int out_f32, const void* residual,
+                     void* stream) {
   if (B <= 0 || T <= 0 || H <= 0 || W <= 0 || (Cin % 64) || (Cout & 7)) return kErrBadShape;
+  if ((taps_t != 1 && taps_t != 3) || (taps_hw != 1 && taps_hw != 3)) return kErrUnsupported;
   if (!aligned16(x) || !aligned16(w) || !aligned16(out) || (bias && !aligned16(bias)) || (residual && !aligned16(residual)))
     return kErrBadAlign;
   if (store_mode == LTXB200_CONV_STORE_D2S && ((Cout % 8) || ((Cout / 8) % 32))) return kErrBadShape;
@@ -133,6 +134,7 @@ extern "C" int ltxb200_conv3d_bf16(const void* x, const void* w, const void* bia
   }
   const int BH = shapes[best][0], BW = shapes[best][1];
   const int BN = (Cout <= 128) ? 128 : 256;
+  const int taps = taps_t * taps_hw * taps_hw;
   CUtensorMap ta, tb;
   {
     uint64_t dims[5] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
@@ -143,13 +145,13 @@ extern "C" int ltxb200_conv3d_bf16(const void* x, const void* w, const void* bia
     if (make_tmap_bf16(&ta, x, 5, dims, str, box)) return kErrTensorMap;
   }
   {
-    uint64_t dims[2] = {static_cast<uint64_t>(27) * Cin, static_cast<uint64_t>(Cout)};
-    uint64_t str[1] = {static_cast<uint64_t>(27) * Cin * 2};
+    uint64_t dims[2] = {static_cast<uint64_t>(taps) * Cin, static_cast<uint64_t>(Cout)};
+    uint64_t str[1] = {static_cast<uint64_t>(taps) * Cin * 2};
     uint32_t box[2] = {kGemmBK, static_cast<uint32_t>(BN)};
     if (make_tmap_bf16(&tb, w, 2, dims, str, box)) return kErrTensorMap;
   }
   GemmParams p{};
-  p.M = B * T * H * W; p.N = Cout; p.K = 27 * Cin;
+  p.M = B * T * H * W; p.N = Cout; p.K = taps * Cin;
   p.out = out; p.ldc = Cout; p.out_f32 = out_f32;
   p.bias = static_cast<const __nv_bfloat16*>(bias);
   p.act = kActNone;
@@ -159,12 +161,25 @@ extern "C" int ltxb200_conv3d_bf16(const void* x, const void* w, const void* bia
                  : (store_mode == LTXB200_CONV_STORE_D2S ? kStoreConvD2S : kStoreConvUnpatch);
   p.cB = B; p.cT = T; p.cH = H; p.cW = W; p.cCin = Cin; p.cBH = BH; p.cBW = BW;
   p.c_tiles_h = (H + BH - 1) / BH; p.c_tiles_w = (W + BW - 1) / BW;
-  p.c_causal = causal ? 1 : 0; p.c_taps_t = 3;
-  p.n_fastest = (static_cast<long long>(Cout) * 27 * Cin * 2 <= (48ll << 20)) ? 1 : 0;
+  p.c_causal = causal ? 1 : 0; p.c_taps_t = taps_t; p.c_taps_hw = taps_hw; p.c_tpad_zero = tpad_zero ? 1 : 0;
+  p.n_fastest = (static_cast<long long>(Cout) * taps * Cin * 2 <= (48ll << 20)) ? 1 : 0;
   if (const char* e = getenv("LTXB200_GEMM_RASTER")) p.n_fastest = atoi(e);
   const int tiles = B * T * p.c_tiles_h * p.c_tiles_w * ((Cout + BN - 1) / BN);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   return BN == 128 ? launch_gemm<128, true>(ta, tb, p, tiles, st) : launch_gemm<256, true>(ta, tb, p, tiles, st);
+}
+
+extern "C" int ltxb200_conv3d_bf16(const void* x, const void* w, const void* bias, void* out, int B, int T, int H,
+                                   int W, int Cin, int Cout, int causal, int store_mode, int out_f32,
+                                   const void* residual, void* stream) {
+  return conv_impl(x, w, bias, out, B, T, H, W, Cin, Cout, 3, 3, causal, 0, store_mode, out_f32, residual, stream);
+}
+
+extern "C" int ltxb200_conv_taps_bf16(const void* x, const void* w, const void* bias, void* out, int B, int T, int H, int W,
+                                      int Cin, int Cout, int taps_t, int taps_hw, int causal_zero_pad, const void* residual,
+                                      void* stream) {
+  return conv_impl(x, w, bias, out, B, T, H, W, Cin, Cout, taps_t, taps_hw, 1, causal_zero_pad, LTXB200_CONV_STORE_NDHWC, 0,
+                   residual, stream);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -533,6 +548,47 @@ extern "C" int ltxb200_pixelnorm_silu_bf16(const void* x, void* y, int64_t voxel
     default: return kErrUnsupported;
   }
 #undef PN_CASE
+  return launch_status();
+}
+
+extern "C" int ltxb200_l2norm_silu_bf16(const void* x, void* y, int64_t voxels, int C, int c_real, const void* gamma,
+                                        int apply_silu, void* stream) {
+  if (voxels <= 0 || c_real <= 0 || c_real > C || !gamma) return kErrBadShape;
+  if (!aligned16(x) || !aligned16(y) || !aligned16(gamma)) return kErrBadAlign;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  auto X = static_cast<const __nv_bfloat16*>(x);
+  auto Y = static_cast<__nv_bfloat16*>(y);
+  auto G_ = static_cast<const __nv_bfloat16*>(gamma);
+  const float scale = sqrtf(static_cast<float>(c_real));
+#define L2_CASE(c)                                                                             \
+  case c: {                                                                                    \
+    constexpr int G = l2_group(c / 8);                                                         \
+    const long long warps = (voxels + (32 / G) - 1) / (32 / G);                                \
+    const long long blocks = (warps + 7) / 8;                                                  \
+    l2norm_silu_kernel<c><<<static_cast<unsigned>(blocks), 256, 0, st>>>(X, Y, voxels, G_, scale, apply_silu); \
+  } break;
+  switch (C) {
+    L2_CASE(64) L2_CASE(128) L2_CASE(192) L2_CASE(256) L2_CASE(384) L2_CASE(512)
+    default: return kErrUnsupported;
+  }
+#undef L2_CASE
+  return launch_status();
+}
+
+extern "C" int ltxb200_upsample2x_nhwc_bf16(const void* x, void* y, int64_t frames, int H, int W, int C, void* stream) {
+  if (frames <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 7)) return kErrBadShape;
+  if (!aligned16(x) || !aligned16(y)) return kErrBadAlign;
+  const long long n = frames * 4LL * H * W * (C / 8);
+  upsample2x_nhwc_kernel<<<ew_blocks(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), frames, H, W, C);
+  return launch_status();
+}
+
+extern "C" int ltxb200_softmax_rows_f32_bf16(const float* s, int64_t ld_s, void* p, int64_t ld_p, int rows, int cols,
+                                             float scale, void* stream) {
+  if (rows <= 0 || cols <= 0 || !s || !p) return kErrBadShape;
+  softmax_rows_kernel<<<(rows + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      s, static_cast<__nv_bfloat16*>(p), rows, cols, ld_s, ld_p, scale * 1.4426950408889634f);
   return launch_status();
 }
 

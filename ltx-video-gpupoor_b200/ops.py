@@ -292,3 +292,58 @@ def cfg_combine(cond: torch.Tensor, uncond: torch.Tensor, guide_scale: float, us
                                                 float(guide_scale), int(use_alpha), _p(scratch), _stream())
     _lib.check(rc, "cfg_combine_f32")
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Wan VAE decode pieces
+# ------------------------------------------------------------------------------------------------------------------
+def conv_taps(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], taps_t: int, taps_hw: int,
+              zero_pad_t: bool = True, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [B,T,H,W,Cin] bf16 NDHWC; w [Cout, taps_t*taps_hw^2*Cin] bf16 (tap-major K); causal in time."""
+    _req(x, name="x"); _req(w, name="w")
+    assert x.is_contiguous() and w.is_contiguous() and x.dim() == 5
+    B, T, H, W, Cin = x.shape
+    Cout = w.shape[0]
+    assert w.shape[1] == taps_t * taps_hw * taps_hw * Cin
+    out = torch.empty(B, T, H, W, Cout, device=x.device, dtype=BF16)
+    if residual is not None:
+        _req(residual, name="residual"); assert residual.is_contiguous() and residual.shape == out.shape
+    with _Prof('conv_taps_bf16', 'flop', 2.0 * B * T * H * W * Cout * w.shape[1]):
+        rc = _lib.lib().ltxb200_conv_taps_bf16(x.data_ptr(), w.data_ptr(), _p(bias), out.data_ptr(), B, T, H, W, Cin, Cout,
+                                               taps_t, taps_hw, 1 if zero_pad_t else 0, _p(residual), _stream())
+    _lib.check(rc, "conv_taps_bf16")
+    return out
+
+
+def l2norm_silu(x: torch.Tensor, gamma: torch.Tensor, c_real: int, silu: bool = True) -> torch.Tensor:
+    """x [..., C] bf16 contiguous (C = stored, 64-padded channels) -> RMS_norm(+SiLU)."""
+    _req(x, name="x"); _req(gamma, name="gamma")
+    assert x.is_contiguous()
+    C = x.shape[-1]
+    y = torch.empty_like(x)
+    with _Prof('l2norm_silu_bf16', 'byte', 4.0 * x.numel()):
+        rc = _lib.lib().ltxb200_l2norm_silu_bf16(x.data_ptr(), y.data_ptr(), x.numel() // C, C, c_real, gamma.data_ptr(),
+                                                 1 if silu else 0, _stream())
+    _lib.check(rc, "l2norm_silu_bf16")
+    return y
+
+
+def upsample2x(x: torch.Tensor) -> torch.Tensor:
+    """x [F, H, W, C] bf16 -> [F, 2H, 2W, C] (nearest)."""
+    _req(x, name="x"); assert x.is_contiguous() and x.dim() == 4
+    Fr, H, W, C = x.shape
+    y = torch.empty(Fr, 2 * H, 2 * W, C, device=x.device, dtype=BF16)
+    with _Prof('upsample2x_bf16', 'byte', 2.5 * y.numel()):
+        rc = _lib.lib().ltxb200_upsample2x_nhwc_bf16(x.data_ptr(), y.data_ptr(), Fr, H, W, C, _stream())
+    _lib.check(rc, "upsample2x_nhwc_bf16")
+    return y
+
+
+def softmax_rows(s: torch.Tensor, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """s [rows, cols] fp32 (row-strided view allowed) -> softmax(scale*s) bf16."""
+    _req(s, torch.float32, "s"); assert s.dim() == 2 and s.stride(1) == 1
+    p = out if out is not None else torch.empty(s.shape, device=s.device, dtype=BF16)
+    _req(p, name="out"); assert p.shape == s.shape and p.stride(1) == 1
+    _lib.check(_lib.lib().ltxb200_softmax_rows_f32_bf16(s.data_ptr(), s.stride(0), p.data_ptr(), p.stride(0), s.shape[0], s.shape[1],
+                                                        float(scale), _stream()), "softmax_rows_f32_bf16")
+    return p

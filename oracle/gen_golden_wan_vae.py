@@ -1,0 +1,59 @@
+"""Pin oracle/wan_vae_oracle.py against the UNMODIFIED reference WanVAE_ (wan/modules/vae.py) run the way the reference runs
+it — one latent frame per decoder call with the CACHE_T feature cache — and write tests/golden/wan_vae_decode.pt.
+Build container only (needs /root/reference):  python oracle/gen_golden_wan_vae.py"""
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(HERE, "refshim"))
+import load_reference  # noqa: E402
+
+load_reference.install()
+from oracle import wan_vae_oracle as V  # noqa: E402
+from oracle.ltx_oracle import rel_l2  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+torch.set_grad_enabled(False)
+
+TINY = dict(V.WAN_VAE, dim=32)          # channels 128 / 64 / 32: every code path of the 96-wide model, 27x fewer FLOPs
+
+
+def build_ref(cfg, sd):
+    from wan.modules.vae import WanVAE_
+    m = WanVAE_(dim=cfg["dim"], z_dim=cfg["z_dim"], dim_mult=cfg["dim_mult"], num_res_blocks=cfg["num_res_blocks"], attn_scales=[],
+                temperal_downsample=cfg["temperal_upsample"][::-1], dropout=0.0)
+    own = m.state_dict()
+    missing = [k for k in own if (k.startswith("decoder.") or k.startswith("conv2.")) and k not in sd]
+    assert not missing, missing
+    unexpected = [k for k in sd if k not in own]
+    assert not unexpected, unexpected
+    for k, v in sd.items():
+        assert own[k].shape == v.shape, (k, own[k].shape, v.shape)
+    m.load_state_dict(sd, strict=False)
+    return m.eval()
+
+
+def main():
+    cfg = TINY
+    sd = V.make_wan_vae_decoder_state_dict(cfg, seed=0)
+    for dtype, tol in ((torch.float64, 1e-9), (torch.float32, 2e-5)):
+        sdd = {k: v.to(dtype) for k, v in sd.items()}
+        ref = build_ref(cfg, sdd).to(dtype)
+        g = torch.Generator().manual_seed(7)
+        z = torch.randn(16, 4, 6, 10, generator=g).to(dtype)
+        mean, std = torch.tensor(V.WAN_VAE_MEAN, dtype=dtype), torch.tensor(V.WAN_VAE_STD, dtype=dtype)
+        y_ref = ref.decode(z.unsqueeze(0), [mean, 1.0 / std]).clamp_(-1, 1).float().squeeze(0)      # WanVAE.decode (:825-829), tile_size 0
+        y = V.wan_vae_decode(sdd, z, cfg, mean, std)
+        e = rel_l2(y, y_ref)
+        print(f"  wan vae decode ({dtype}): out {tuple(y.shape)}, rel_l2(oracle batched, reference streaming) = {e:.3e}, clamp hits {(y_ref.abs() >= 1).float().mean():.3f}")
+        assert y.shape == (3, 13, 48, 80) and e < tol
+    torch.save(dict(cfg=cfg, seed_weights=0, z=z.float(), out=y_ref.half()), os.path.join(GOLD, "wan_vae_decode.pt"))
+    print("written", os.path.join(GOLD, "wan_vae_decode.pt"))
+
+
+if __name__ == "__main__":
+    main()

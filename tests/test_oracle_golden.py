@@ -91,3 +91,14 @@ def test_wan_i2v_oracle_matches_reference(golden_dir):
     W.t2v_denoise(sd, cfg, g["lat"], g["ctx"], g["ctx0"], steps=4, shift=5.0, guide_scale=5.0, per_step=steps, clip_fea=g["clip"], y=g["y"])
     for a, b in zip(steps, g["loop"]):
         assert W.rel_l2(a, b) < 2e-4
+
+
+def test_wan_vae_decode_oracle_matches_reference(golden_dir):
+    """The one-pass Wan VAE decode oracle vs the fixture recorded from the unmodified reference's frame-by-frame streaming decode
+    with its CACHE_T feature cache (oracle/gen_golden_wan_vae.py: identical in fp64, 1.7e-6 in fp32)."""
+    from oracle import wan_vae_oracle as V
+    g = _load(golden_dir, "wan_vae_decode.pt")
+    sd = V.make_wan_vae_decoder_state_dict(g["cfg"], seed=g["seed_weights"])
+    y = V.wan_vae_decode(sd, g["z"], g["cfg"], torch.tensor(V.WAN_VAE_MEAN), torch.tensor(V.WAN_VAE_STD))
+    assert y.shape == (3, 13, 48, 80)
+    assert O.rel_l2(y, g["out"].float()) < 2e-3      # fixture stored as fp16

@@ -1,0 +1,78 @@
+"""GPU parity of the Wan VAE decode drop-in against the fixture recorded from the unmodified reference (streaming decode) and the
+live oracle; kernels new to this path (tap-shaped causal conv with zero padding, RMS_norm+SiLU, x2 upsample, row softmax) vs torch."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+if not torch.cuda.is_available():
+    pytest.skip("needs a GPU", allow_module_level=True)
+
+from ltx_video_gpupoor_b200 import ops  # noqa: E402
+from ltx_video_gpupoor_b200.wan.vae import WanVAE  # noqa: E402
+from oracle import wan_vae_oracle as V  # noqa: E402
+from oracle.ltx_oracle import psnr, rel_l2  # noqa: E402
+
+DEV = "cuda"
+BF = torch.bfloat16
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    return (torch.randn(*shape, generator=torch.Generator().manual_seed(seed)) * scale).to(BF).to(DEV)
+
+
+@pytest.mark.parametrize("kt,khw,Cin,Cout", [(3, 3, 64, 128), (1, 3, 128, 64), (3, 1, 64, 128), (1, 1, 192, 64)])
+def test_conv_taps_zero_causal(kt, khw, Cin, Cout):
+    B, T, H, W = 1, 4, 9, 13
+    x = rnd(B, T, H, W, Cin, seed=1)
+    w5 = rnd(Cout, Cin, kt, khw, khw, seed=2, scale=(kt * khw * khw * Cin) ** -0.5)
+    b = rnd(Cout, seed=3)
+    xr = F.pad(x.float().permute(0, 4, 1, 2, 3), (khw // 2, khw // 2, khw // 2, khw // 2, kt - 1, 0))
+    ref = F.conv3d(xr, w5.float(), b.float()).permute(0, 2, 3, 4, 1)
+    wp = w5.permute(0, 2, 3, 4, 1).reshape(Cout, -1).contiguous()
+    out = ops.conv_taps(x, wp, b, kt, khw, True)
+    torch.cuda.synchronize()
+    assert rel_l2(out.float().cpu(), ref.cpu()) < 6e-3
+    res = rnd(B, T, H, W, Cout, seed=4)
+    out = ops.conv_taps(x, wp, b, kt, khw, True, residual=res)
+    assert rel_l2(out.float().cpu(), (ref + res.float()).cpu()) < 6e-3
+
+
+@pytest.mark.parametrize("C,c_real", [(64, 64), (128, 96), (192, 192), (384, 384)])
+def test_l2norm_silu_upsample_softmax(C, c_real):
+    x = rnd(3, 5, 7, C, seed=1)
+    x[..., c_real:] = 0
+    g = rnd(C, seed=2, scale=0.1) + 1
+    g[c_real:] = 0
+    ref = F.normalize(x.float()[..., :c_real], dim=-1) * c_real ** 0.5 * g.float()[:c_real]
+    y = ops.l2norm_silu(x, g, c_real, silu=True)
+    assert rel_l2(y.float()[..., :c_real].cpu(), F.silu(ref).cpu()) < 6e-3
+    assert float(y.float()[..., c_real:].abs().max() if c_real < C else 0.0) == 0.0
+    up = ops.upsample2x(x)
+    assert torch.equal(up, x.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2))
+    s = torch.randn(37, 333, generator=torch.Generator().manual_seed(3)).to(DEV) * 4
+    p = ops.softmax_rows(s, 0.3)
+    assert rel_l2(p.float().cpu(), torch.softmax(s.cpu() * 0.3, dim=-1)) < 6e-3
+
+
+def test_wan_vae_decode_vs_reference_fixture(golden_dir):
+    g = torch.load(os.path.join(golden_dir, "wan_vae_decode.pt"), weights_only=False)
+    cfg = g["cfg"]
+    sd = V.make_wan_vae_decoder_state_dict(cfg, seed=g["seed_weights"])
+    vae = WanVAE(dim=cfg["dim"], dim_mult=cfg["dim_mult"], num_res_blocks=cfg["num_res_blocks"],
+                 temperal_downsample=cfg["temperal_upsample"][::-1])
+    vae.load_state_dict(sd)
+    y = vae.decode([g["z"].to(DEV)], tile_size=0)[0]
+    torch.cuda.synchronize()
+    ref = g["out"].float()
+    assert tuple(y.shape) == tuple(ref.shape) == (3, 13, 48, 80)
+    p = psnr(y.cpu() * 0.5 + 0.5, ref * 0.5 + 0.5)
+    e = rel_l2(y.cpu(), ref)
+    print(f"wan vae decode: PSNR vs reference = {p:.1f} dB, rel_l2 = {e:.3e}")
+    assert p >= 40.0
+    # and against the live oracle in fp32 on the same weights
+    mean, std = torch.tensor(V.WAN_VAE_MEAN), torch.tensor(V.WAN_VAE_STD)
+    yo = V.wan_vae_decode(sd, g["z"], cfg, mean, std)
+    assert psnr(y.cpu() * 0.5 + 0.5, yo * 0.5 + 0.5) >= 40.0
