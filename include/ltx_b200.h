@@ -136,6 +136,13 @@ int ltxb200_pixelnorm_silu_bf16(const void* x, void* y, int64_t voxels, int C, f
 int ltxb200_latent_to_ndhwc(const void* z, int is_f32, void* out, int B, int C, int64_t FHW, const float* stdv,
                             const float* meanv, void* stream);
 
+/* 3x3x3 CAUSAL convolution (two replicated leading frames, zero spatial padding) with output strides stride_t / stride_hw in
+ * {1, 2}: x [B,T,H,W,Cin] -> out [B,(T-1)/stride_t+1,(H-1)/stride_hw+1,(W-1)/stride_hw+1,Cout].  The "compress_all/time/space"
+ * blocks of the LTX VAE Encoder (causal_video_autoencoder.py:404-447 via make_conv_nd(stride=...)); the TMA descriptor strides
+ * over the input, so no im2col or space-to-depth copy is made. */
+int ltxb200_conv3d_strided_bf16(const void* x, const void* w, const void* bias, void* out, int B, int T, int H, int W, int Cin,
+                                int Cout, int stride_t, int stride_hw, void* stream);
+
 /* ---- Wan2.1 VAE decode (wan/modules/vae.py:386-493): the pieces the LTX decoder kernels do not already cover ---- */
 /* convolution with taps_t x taps_hw x taps_hw taps (each 1 or 3) on NDHWC bf16, w = [Cout, taps*Cin] tap-major, causal in time
  * (taps t-2,t-1,t) with ZERO temporal padding when causal_zero_pad != 0 (Wan CausalConv3d, vae.py:17-37; Conv2d 3x3 of

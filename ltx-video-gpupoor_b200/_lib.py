@@ -41,6 +41,7 @@ def _declare(lib):
         "ltxb200_cfg_combine_f32": ([P, P, P, L, F, I, P, P], I),
         "ltxb200_pixelnorm_silu_bf16": ([P, P, L, I, F, I, P], I),
         "ltxb200_latent_to_ndhwc": ([P, I, P, I, I, L, P, P, P], I),
+        "ltxb200_conv3d_strided_bf16": ([P, P, P, P, I, I, I, I, I, I, I, I, P], I),
         "ltxb200_conv_taps_bf16": ([P, P, P, P, I, I, I, I, I, I, I, I, I, P, P], I),
         "ltxb200_l2norm_silu_bf16": ([P, P, L, I, I, P, I, P], I),
         "ltxb200_upsample2x_nhwc_bf16": ([P, P, L, I, I, I, P], I),

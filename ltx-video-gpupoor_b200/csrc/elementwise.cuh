@@ -653,6 +653,46 @@ pixelnorm_silu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __rest
   }
 }
 
+// LayerNorm with affine over a NARROW channel vector (C = 64 / 128: the res_x_y shortcut of the LTX VAE encoder,
+// causal_video_autoencoder.py:1244-1250), G = C/8 lanes per row; rows are contiguous [rows, C].
+template <int C>
+__global__ void __launch_bounds__(256)
+layernorm_narrow_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long rows,
+                        const __nv_bfloat16* __restrict__ weight, const __nv_bfloat16* __restrict__ bias, float eps) {
+  constexpr int G = C / 8;
+  constexpr int RPW = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long row = warp_global * RPW + lane / G;
+  const int gl = lane % G;
+  const bool ok = row < rows;
+  float v[8];
+  if (ok) load8(x + row * C + gl * 8, v);
+  else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sum += v[j];
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum * (1.0f / C);
+  float var = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { const float d = v[j] - mean; var += d * d; }
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  const float rs = rsqrtf(var * (1.0f / C) + eps);
+  if (!ok) return;
+  float w[8], b[8], o[8];
+  load8(weight + gl * 8, w);
+  load8(bias + gl * 8, b);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = (v[j] - mean) * rs * w[j] + b[j];
+  store8(y + row * C + gl * 8, o);
+}
+
 // Wan VAE RMS_norm (wan/modules/vae.py:41-58) + optional SiLU on NDHWC voxels:
 //   y = x / max(||x||_2, 1e-12) * sqrt(c_real) * gamma[c]      (F.normalize over the channel dim)
 // C is the stored (64-padded) channel count, c_real the model's; pad channels hold zeros and gamma = 0 there.

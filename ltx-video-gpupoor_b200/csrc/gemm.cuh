@@ -49,6 +49,8 @@ struct GemmParams {
   int c_taps_t;                    // temporal taps: 3 or 1
   int c_taps_hw;                   // spatial taps per axis: 3 (zero padding) or 1
   int c_tpad_zero;                 // temporal padding: 0 = replicate (clamped frame index, LTX), 1 = zeros (TMA OOB fill, Wan)
+  int c_st, c_shw;                 // output strides (1 or 2): cT/cH/cW are OUTPUT dims, the TMA map strides over the input
+  int cTin;                        // input frames (temporal clamp)
   // tile rasterisation of the persistent schedule: 0 = M fastest (one weight panel per wave, all of A re-read per
   // N tile), 1 = N fastest (a wave = a few row panels x every N tile: A streams through once, W stays in L2)
   int n_fastest;
@@ -132,13 +134,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int thw = p.c_taps_hw * p.c_taps_hw;
             const int kt = tap / thw, kh = (tap % thw) / p.c_taps_hw, kw = tap % p.c_taps_hw;     // tap-major K: (kt, kh, kw, ci)
             int tt = ct, hh = ch0, ww = cw0;
+            tt = ct * p.c_st; hh = ch0 * p.c_shw; ww = cw0 * p.c_shw;
             if (p.c_taps_t == 3) {
-              tt = p.c_causal ? ct + kt - 2 : ct + kt - 1;
-              if (!p.c_tpad_zero) tt = tt < 0 ? 0 : (tt > p.cT - 1 ? p.cT - 1 : tt);            // replicate; else TMA zero-fills t < 0
+              tt += p.c_causal ? kt - 2 : kt - 1;
+              if (!p.c_tpad_zero) tt = tt < 0 ? 0 : (tt > p.cTin - 1 ? p.cTin - 1 : tt);        // replicate; else TMA zero-fills t < 0
             }
             if (p.c_taps_hw == 3) {
-              hh = ch0 + kh - 1;
-              ww = cw0 + kw - 1;
+              hh += kh - 1;
+              ww += kw - 1;
             }
             tma_load_5d(sa, &tmA, &full_bar[stage], cblk * kGemmBK, ww, hh, tt, cb);
             tma_load_2d(sb, &tmB, &full_bar[stage], tap * p.cCin + cblk * kGemmBK, tn * BN);

@@ -113,10 +113,14 @@ extern "C" int ltxb200_gemm_bf16(const void* A, int64_t lda, const void* W, int6
 // ------------------------------------------------------------------------------------------
 // conv3d (implicit GEMM)
 // ------------------------------------------------------------------------------------------
-static int conv_impl(const void* x, const void* w, const void* bias, void* out, int B, int T, int H, int W, int Cin, int Cout,
+// x: [B, Tin, Hin, Win, Cin]; out: [B, T, H, W, Cout] with T = (Tin - 1) / st + 1 etc. (st, shw = output strides)
+static int conv_impl(const void* x, const void* w, const void* bias, void* out, int B, int Tin, int Hin, int Win, int Cin, int Cout,
                      int taps_t, int taps_hw, int causal, int tpad_zero, int store_mode, int out_f32, const void* residual,
-                     void* stream) {
-  if (B <= 0 || T <= 0 || H <= 0 || W <= 0 || (Cin % 64) || (Cout & 7)) return kErrBadShape;
+                     void* stream, int st_t = 1, int st_hw = 1) {
+  if (B <= 0 || Tin <= 0 || Hin <= 0 || Win <= 0 || (Cin % 64) || (Cout & 7)) return kErrBadShape;
+  if ((st_t != 1 && st_t != 2) || (st_hw != 1 && st_hw != 2)) return kErrUnsupported;
+  if ((st_t != 1 || st_hw != 1) && (taps_t != 3 || taps_hw != 3 || !causal || store_mode != LTXB200_CONV_STORE_NDHWC)) return kErrUnsupported;
+  const int T = (Tin - 1) / st_t + 1, H = (Hin - 1) / st_hw + 1, W = (Win - 1) / st_hw + 1;
   if ((taps_t != 1 && taps_t != 3) || (taps_hw != 1 && taps_hw != 3)) return kErrUnsupported;
   if (!aligned16(x) || !aligned16(w) || !aligned16(out) || (bias && !aligned16(bias)) || (residual && !aligned16(residual)))
     return kErrBadAlign;
@@ -137,12 +141,14 @@ static int conv_impl(const void* x, const void* w, const void* bias, void* out, 
   const int taps = taps_t * taps_hw * taps_hw;
   CUtensorMap ta, tb;
   {
-    uint64_t dims[5] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
-                        static_cast<uint64_t>(T), static_cast<uint64_t>(B)};
-    uint64_t str[4] = {static_cast<uint64_t>(Cin) * 2, static_cast<uint64_t>(W) * Cin * 2,
-                       static_cast<uint64_t>(H) * W * Cin * 2, static_cast<uint64_t>(T) * H * W * Cin * 2};
-    uint32_t box[5] = {kGemmBK, static_cast<uint32_t>(BW), static_cast<uint32_t>(BH), 1, 1};
-    if (make_tmap_bf16(&ta, x, 5, dims, str, box)) return kErrTensorMap;
+    uint64_t dims[5] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(Win), static_cast<uint64_t>(Hin),
+                        static_cast<uint64_t>(Tin), static_cast<uint64_t>(B)};
+    uint64_t str[4] = {static_cast<uint64_t>(Cin) * 2, static_cast<uint64_t>(Win) * Cin * 2,
+                       static_cast<uint64_t>(Hin) * Win * Cin * 2, static_cast<uint64_t>(Tin) * Hin * Win * Cin * 2};
+    // strided convolution: the box spans st_hw * BW source pixels and the traversal stride picks every st_hw-th one
+    uint32_t box[5] = {kGemmBK, static_cast<uint32_t>(BW * st_hw), static_cast<uint32_t>(BH * st_hw), 1, 1};
+    uint32_t es[5] = {1, static_cast<uint32_t>(st_hw), static_cast<uint32_t>(st_hw), 1, 1};
+    if (make_tmap_bf16(&ta, x, 5, dims, str, box, es)) return kErrTensorMap;
   }
   {
     uint64_t dims[2] = {static_cast<uint64_t>(taps) * Cin, static_cast<uint64_t>(Cout)};
@@ -162,6 +168,7 @@ static int conv_impl(const void* x, const void* w, const void* bias, void* out, 
   p.cB = B; p.cT = T; p.cH = H; p.cW = W; p.cCin = Cin; p.cBH = BH; p.cBW = BW;
   p.c_tiles_h = (H + BH - 1) / BH; p.c_tiles_w = (W + BW - 1) / BW;
   p.c_causal = causal ? 1 : 0; p.c_taps_t = taps_t; p.c_taps_hw = taps_hw; p.c_tpad_zero = tpad_zero ? 1 : 0;
+  p.c_st = st_t; p.c_shw = st_hw; p.cTin = Tin;
   p.n_fastest = (static_cast<long long>(Cout) * taps * Cin * 2 <= (48ll << 20)) ? 1 : 0;
   if (const char* e = getenv("LTXB200_GEMM_RASTER")) p.n_fastest = atoi(e);
   const int tiles = B * T * p.c_tiles_h * p.c_tiles_w * ((Cout + BN - 1) / BN);
@@ -173,6 +180,12 @@ extern "C" int ltxb200_conv3d_bf16(const void* x, const void* w, const void* bia
                                    int W, int Cin, int Cout, int causal, int store_mode, int out_f32,
                                    const void* residual, void* stream) {
   return conv_impl(x, w, bias, out, B, T, H, W, Cin, Cout, 3, 3, causal, 0, store_mode, out_f32, residual, stream);
+}
+
+extern "C" int ltxb200_conv3d_strided_bf16(const void* x, const void* w, const void* bias, void* out, int B, int T, int H, int W,
+                                           int Cin, int Cout, int stride_t, int stride_hw, void* stream) {
+  return conv_impl(x, w, bias, out, B, T, H, W, Cin, Cout, 3, 3, 1, 0, LTXB200_CONV_STORE_NDHWC, 0, nullptr, stream, stride_t,
+                   stride_hw);
 }
 
 extern "C" int ltxb200_conv_taps_bf16(const void* x, const void* w, const void* bias, void* out, int B, int T, int H, int W,
@@ -359,11 +372,23 @@ static int launch_norm(int NV, const __nv_bfloat16* x, __nv_bfloat16* y, int M, 
 extern "C" int ltxb200_norm_mod_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, int M, int D, const void* scale,
                                      const void* shift, int64_t mod_ld, int rows_per_group, const void* weight,
                                      const void* bias, float eps, int layer_norm, void* stream) {
-  if (M <= 0 || D <= 0 || (D % 256)) return kErrBadShape;
+  if (M <= 0 || D <= 0) return kErrBadShape;
   if (!aligned16(x) || !aligned16(y) || (ldx & 7) || (ldy & 7) || (scale && (!aligned16(scale) || (mod_ld & 7))) ||
       (shift && !aligned16(shift)) || (weight && !aligned16(weight)) || (bias && !aligned16(bias)))
     return kErrBadAlign;
   if ((scale == nullptr) != (shift == nullptr)) return kErrBadShape;
+  if (D == 64 || D == 128) {          // narrow affine LayerNorm (VAE encoder shortcut): contiguous rows, no modulation
+    if (!layer_norm || !weight || !bias || scale || ldx != D || ldy != D) return kErrUnsupported;
+    const int rpw = 32 / (D / 8);
+    const long long warps = (static_cast<long long>(M) + rpw - 1) / rpw, blocks = (warps + 7) / 8;
+    cudaStream_t s2 = static_cast<cudaStream_t>(stream);
+    if (D == 64)
+      layernorm_narrow_kernel<64><<<static_cast<unsigned>(blocks), 256, 0, s2>>>(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), M, static_cast<const __nv_bfloat16*>(weight), static_cast<const __nv_bfloat16*>(bias), eps);
+    else
+      layernorm_narrow_kernel<128><<<static_cast<unsigned>(blocks), 256, 0, s2>>>(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), M, static_cast<const __nv_bfloat16*>(weight), static_cast<const __nv_bfloat16*>(bias), eps);
+    return launch_status();
+  }
+  if (D % 256) return kErrBadShape;
   const int rpg = rows_per_group > 0 ? rows_per_group : M;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   auto X = static_cast<const __nv_bfloat16*>(x);

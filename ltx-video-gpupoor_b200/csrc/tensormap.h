@@ -26,8 +26,11 @@ inline PFN_tmapEncodeTiled tmap_encode_fn() {
 
 // bf16 tensor, `rank` dims (dim 0 innermost, contiguous), strides in BYTES for dims 1..rank-1,
 // 128B swizzle, zero OOB fill.  Returns 0 on success.
+// elem_strides (optional): traversal stride per dimension — with stride s the box spans box[i] source elements and loads
+// ceil(box[i] / s) of them (used by the strided encoder convolutions).
 inline int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                          const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box) {
+                          const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box,
+                          const uint32_t* elem_strides = nullptr) {
   PFN_tmapEncodeTiled fn = tmap_encode_fn();
   if (!fn) return -4;
   cuuint64_t gdim[5];
@@ -37,7 +40,7 @@ inline int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const ui
   for (int i = 0; i < rank; ++i) {
     gdim[i] = dims[i];
     bx[i] = box[i];
-    es[i] = 1;
+    es[i] = elem_strides ? elem_strides[i] : 1;
   }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,

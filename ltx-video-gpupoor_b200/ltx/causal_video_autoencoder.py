@@ -1,4 +1,4 @@
-"""CausalVideoAutoencoder (decode path) — B200-native drop-in for
+"""CausalVideoAutoencoder (decode + encode) — B200-native drop-in for
 ltx_video/models/autoencoders/causal_video_autoencoder.py:33-300,560-802,1023-1258,1282-1299 and
 vae.py:343-413, vae_encode.py:94-165,239-247.
 
@@ -6,7 +6,10 @@ Activations are kept NDHWC bf16 so that (a) every 3x3x3 convolution is a TMA-til
 tcgen05 (spatial zero padding = TMA out-of-bounds fill, temporal replicate padding = clamped frame
 coordinate, no concat), (b) PixelNorm is a per-voxel reduction over the contiguous channel vector,
 (c) depth-to-space, the first-frame drop, the residual add and the final 4x4 unpatchify are store
-patterns of the conv epilogue instead of extra passes.  Encoder = SURVEY §8(f) "next".
+patterns of the conv epilogue instead of extra passes.
+Encoder (causal_video_autoencoder.py:313-557, vae.py:265-306, vae_encode.py:22-91,228-237): the same
+kernels, always causal; the stride-2 "compress_all" convolutions run on a TMA descriptor that strides over the input
+(no im2col / space-to-depth copy).
 """
 from __future__ import annotations
 
@@ -40,6 +43,26 @@ def _pack_conv(w5: torch.Tensor, perm: Optional[torch.Tensor] = None) -> torch.T
     if perm is not None:
         w5 = w5[perm]
     return w5.permute(0, 2, 3, 4, 1).reshape(w5.shape[0], -1).to(BF16).contiguous()
+
+
+class DiagonalGaussianDistribution:
+    """diffusers.models.autoencoders.vae.DiagonalGaussianDistribution as used at vae.py:306 / vae_encode.py:77:
+    logvar clamped to [-30, 20], sample = mean + exp(0.5 logvar) * randn."""
+
+    def __init__(self, mean: torch.Tensor, logvar: torch.Tensor):
+        self.mean = mean
+        self.logvar = torch.clamp(logvar, -30.0, 20.0).expand_as(mean)
+        self.std = torch.exp(0.5 * self.logvar)
+        self.var = torch.exp(self.logvar)
+
+    def sample(self, generator=None, noise: Optional[torch.Tensor] = None):
+        if noise is None:
+            noise = torch.randn(self.mean.shape, generator=generator, device=self.mean.device if generator is None or
+                                generator.device.type != "cpu" else "cpu", dtype=self.mean.dtype)
+        return self.mean + self.std * noise.to(self.mean.device)
+
+    def mode(self):
+        return self.mean
 
 
 class _Decoder:
@@ -143,6 +166,34 @@ class CausalVideoAutoencoder:
         # unpatchify channel order (c r q) -> (c q r): r (width) innermost
         perm = torch.arange(co * ps * ps, device=dev).reshape(co, ps, ps).permute(0, 2, 1).reshape(-1)
         w["conv_out"] = conv("decoder.conv_out.conv", perm)
+        self.enc_plan = self._enc_plan()
+        self.has_encoder = "encoder.conv_in.conv.weight" in sd
+        if self.has_encoder:
+            cin0 = self._cfg["in_channels"] * ps * ps                         # 48 patchified channels, stored 64-padded
+            wt = torch.zeros(sd["encoder.conv_in.conv.weight"].shape[0], 64, 3, 3, 3, device=dev)
+            wt[:, :cin0] = sd["encoder.conv_in.conv.weight"].to(dev)
+            w["enc.conv_in"] = (_pack_conv(wt), sd["encoder.conv_in.conv.bias"].to(dev).to(BF16).contiguous())
+            for kind, idx, cin, cout, n in self.enc_plan:
+                p = f"encoder.down_blocks.{idx}."
+                if kind == "res_x":
+                    for j in range(n):
+                        w[p + f"{j}.conv1"] = conv(p + f"res_blocks.{j}.conv1.conv")
+                        w[p + f"{j}.conv2"] = conv(p + f"res_blocks.{j}.conv2.conv")
+                elif kind == "res_x_y":
+                    w[p + "conv1"] = conv(p + "conv1.conv")
+                    w[p + "conv2"] = conv(p + "conv2.conv")
+                    w[p + "shortcut"] = (sd[p + "conv_shortcut.weight"].to(dev).reshape(cout, cin).to(BF16).contiguous(),
+                                         sd[p + "conv_shortcut.bias"].to(dev).to(BF16).contiguous())
+                    w[p + "norm3"] = (sd[p + "norm3.norm.weight"].to(dev).to(BF16).contiguous(),
+                                      sd[p + "norm3.norm.bias"].to(dev).to(BF16).contiguous())
+                else:
+                    w[p + "conv"] = conv(p + "conv")      # the block IS a CausalConv3d: keys down_blocks.N.conv.{weight,bias}
+            # conv_out: latent_channels + 1 ("uniform" log-variance) output channels, stored padded to a multiple of 8
+            wo, bo = sd["encoder.conv_out.conv.weight"].to(dev), sd["encoder.conv_out.conv.bias"].to(dev)
+            cop = (wo.shape[0] + 7) // 8 * 8
+            wp = torch.zeros(cop, *wo.shape[1:], device=dev); wp[: wo.shape[0]] = wo
+            bp = torch.zeros(cop, device=dev); bp[: bo.shape[0]] = bo
+            w["enc.conv_out"] = (_pack_conv(wp), bp.to(BF16).contiguous())
         std = sd.get("std_of_means", sd.get("per_channel_statistics.std-of-means"))
         mean = sd.get("mean_of_means", sd.get("per_channel_statistics.mean-of-means"))
         if std is not None:
@@ -150,6 +201,55 @@ class CausalVideoAutoencoder:
             self.mean_of_means = (mean if mean is not None else torch.zeros_like(std)).to(dev)
         self.w = w
         return [], []
+
+    def _enc_plan(self):
+        """encoder.down_blocks (causal_video_autoencoder.py:373-478)"""
+        ch, plan = 128, []
+        for idx, (name, p) in enumerate(self._cfg["blocks"]):
+            if name == "res_x":
+                plan.append(("res_x", idx, ch, ch, int(p)))
+            elif name == "res_x_y":
+                plan.append(("res_x_y", idx, ch, ch * 2, 1)); ch *= 2
+            elif name == "compress_all":
+                plan.append(("down", idx, ch, ch, 1))
+            else:
+                raise NotImplementedError(f"encoder block {name}")
+        return plan
+
+    def _encode(self, x: torch.Tensor):
+        """Encoder.forward (:510-557): x [B,3,F,H,W] in [-1,1] -> (mean [B,128,F',H',W'], logvar [B,1,F',H',W']) fp32."""
+        if not self.has_encoder:
+            raise RuntimeError("this CausalVideoAutoencoder was loaded without encoder weights")
+        w, ps = self.w, self._cfg["patch_size"]
+        B, C, Fr, H, W = x.shape
+        assert C == 3 and H % ps == 0 and W % ps == 0
+        h, wd = H // ps, W // ps
+        # patchify 'b c (h q) (w r) -> b (c r q) f h w' (:1261-1279) straight into NDHWC, 48 -> 64 padded channels
+        xp = torch.zeros(B, Fr, h, wd, 64, device=self.device, dtype=BF16)
+        xp[..., : C * ps * ps] = (x.to(self.device, torch.float32).view(B, C, Fr, h, ps, wd, ps)
+                                  .permute(0, 2, 3, 5, 1, 6, 4).reshape(B, Fr, h, wd, C * ps * ps).to(BF16))
+        y = ops.conv3d(xp, *w["enc.conv_in"], causal=True)
+        for kind, idx, cin, cout, n in self.enc_plan:
+            p = f"encoder.down_blocks.{idx}."
+            if kind == "res_x":
+                for j in range(n):
+                    y = self._resnet(y, w[p + f"{j}.conv1"], w[p + f"{j}.conv2"], True)
+            elif kind == "res_x_y":
+                y = self._resnet(y, w[p + "conv1"], w[p + "conv2"], True, w[p + "shortcut"], w[p + "norm3"])
+            else:
+                y = ops.conv3d_strided(y, *w[p + "conv"], stride_t=2, stride_hw=2)
+        y = ops.conv3d(ops.pixelnorm_silu(y), *w["enc.conv_out"], causal=True)            # [B, F', H', W', 136]
+        lc = self._cfg["latent_channels"]
+        mom = y[..., : lc + 1].permute(0, 4, 1, 2, 3).float()
+        return mom[:, :lc].contiguous(), mom[:, lc:].contiguous()
+
+    def encode(self, z: torch.Tensor, return_dict: bool = True):
+        """vae.py:265-306: returns the DiagonalGaussianDistribution of the latent (mean, uniform log-variance)."""
+        mean, logvar = self._encode(z)
+        post = DiagonalGaussianDistribution(mean, logvar)
+        if not return_dict:
+            return (post,)
+        return SimpleNamespace(latent_dist=post)
 
     # ---------------------------------------------------------------------------------------------
     def _resnet(self, x, c1, c2, causal, shortcut=None, norm3=None):
@@ -218,3 +318,22 @@ def vae_decode(latents: torch.Tensor, vae: CausalVideoAutoencoder, is_video: boo
     if not vae_per_channel_normalize and vae.config.scaling_factor != 1.0:
         latents = latents / vae.config.scaling_factor
     return vae._decode(latents.to(vae.dtype), per_channel_normalize=vae_per_channel_normalize)
+
+
+def normalize_latents(latents, vae, vae_per_channel_normalize=False):
+    """vae_encode.py:228-237"""
+    if vae_per_channel_normalize:
+        return (latents - vae.mean_of_means.to(latents.dtype).view(1, -1, 1, 1, 1)) / vae.std_of_means.to(latents.dtype).view(1, -1, 1, 1, 1)
+    return latents * vae.config.scaling_factor
+
+
+def vae_encode(media_items: torch.Tensor, vae: CausalVideoAutoencoder, split_size: int = 1, vae_per_channel_normalize: bool = False,
+               generator=None, noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """vae_encode.py:22-91: media [B,3,F,H,W] (F = 8k+1) in [-1,1] -> normalised latents [B,128,F/8+1,H/32,W/32] (fp32).
+    `latent_dist.sample()` is kept (the reference draws from the global RNG; pass `generator` or `noise` for reproducibility)."""
+    if media_items.dim() != 5 or media_items.shape[1] != 3:
+        raise ValueError(f"Expects [B, 3, F, H, W] tensors, got {tuple(media_items.shape)}")
+    if split_size != 1:
+        raise NotImplementedError("split_size > 1 is a memory workaround that is not needed here")
+    latents = vae.encode(media_items).latent_dist.sample(generator=generator, noise=noise)
+    return normalize_latents(latents, vae, vae_per_channel_normalize)

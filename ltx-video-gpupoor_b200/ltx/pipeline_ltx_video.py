@@ -20,7 +20,7 @@ from typing import Callable, List, Optional, Tuple, Union
 import torch
 
 from .. import ops
-from .causal_video_autoencoder import CausalVideoAutoencoder, get_vae_size_scale_factor, vae_decode
+from .causal_video_autoencoder import CausalVideoAutoencoder, get_vae_size_scale_factor, vae_decode, vae_encode
 from .rf import RectifiedFlowScheduler
 from .skip_layer_strategy import SkipLayerStrategy
 from .symmetric_patchifier import SymmetricPatchifier, latent_to_pixel_coords_from_factors
@@ -31,14 +31,16 @@ BF16 = torch.bfloat16
 
 @dataclass
 class ConditioningItem:
-    """pipeline_ltx_video.py:195-219.  `media_item` is pixels [b,3,f,h,w] in [-1,1] (needs the VAE encoder,
-    SURVEY §8f#3); `latents` (extension) carries already-encoded, normalised latents [b,128,f_l,h_l,w_l]."""
+    """pipeline_ltx_video.py:195-219.  `media_item` is pixels [b,3,f,h,w] in [-1,1] (encoded here with the VAE encoder);
+    `latents` (extension) carries already-encoded, normalised latents [b,128,f_l,h_l,w_l]; `encode_noise` (extension) fixes
+    the noise of `latent_dist.sample()` (the reference draws it from the global RNG, vae_encode.py:77)."""
     media_item: Optional[torch.Tensor] = None
     media_frame_number: int = 0
     conditioning_strength: float = 1.0
     media_x: Optional[int] = None
     media_y: Optional[int] = None
     latents: Optional[torch.Tensor] = None
+    encode_noise: Optional[torch.Tensor] = None
 
 
 def retrieve_timesteps(scheduler, num_inference_steps=None, device=None, timesteps=None, max_timestep=1.0,
@@ -98,18 +100,26 @@ class LTXVideoPipeline:
         assert tuple(latents.shape) == tuple(latent_shape)
         return timestep * noise + (1 - timestep) * latents.to(device=device, dtype=dtype)
 
-    def prepare_conditioning(self, conditioning_items, init_latents, num_frames, height, width):
-        """pipeline_ltx_video.py:1344-1548, first-frame (media_frame_number == 0) conditioning with pre-encoded
-        latents; returns (patchified latents, pixel coords, conditioning mask | None, num extra tokens)."""
+    def prepare_conditioning(self, conditioning_items, init_latents, num_frames, height, width,
+                             vae_per_channel_normalize: bool = False, generator=None):
+        """pipeline_ltx_video.py:1344-1548, first-frame / first-sequence (media_frame_number == 0) conditioning from pixels
+        (encoded with the VAE, :1420-1424) or pre-encoded latents; returns (patchified latents, pixel coords,
+        conditioning mask | None, num extra tokens)."""
         cmask = None
         if conditioning_items:
             cmask = torch.zeros(init_latents[:, 0].shape, dtype=torch.float32, device=init_latents.device)
             for item in conditioning_items:
-                if item.latents is None:
-                    raise NotImplementedError("pixel-space conditioning needs the VAE encoder (SURVEY §8f#3); pass ConditioningItem(latents=…)")
                 if item.media_frame_number != 0:
                     raise NotImplementedError("only media_frame_number == 0 conditioning is implemented")
-                lat = item.latents.to(device=init_latents.device, dtype=init_latents.dtype)
+                if item.latents is None:
+                    m = item.media_item
+                    assert m is not None and m.ndim == 5 and m.shape[2] % 8 == 1                  # :1409-1415
+                    if tuple(m.shape[-2:]) != (height, width):
+                        raise NotImplementedError("conditioning media must have the target size (resize / border stripping is not implemented)")
+                    lat = vae_encode(m, self.vae, vae_per_channel_normalize=vae_per_channel_normalize,
+                                     noise=item.encode_noise).to(device=init_latents.device, dtype=init_latents.dtype)
+                else:
+                    lat = item.latents.to(device=init_latents.device, dtype=init_latents.dtype)
                 _, _, f_l, h_l, w_l = lat.shape
                 s = item.conditioning_strength
                 init_latents[:, :, :f_l, :h_l, :w_l] = torch.lerp(init_latents[:, :, :f_l, :h_l, :w_l], lat, s)   # :1436-1445
@@ -242,7 +252,8 @@ class LTXVideoPipeline:
         noise_dtype = prompt_embeds.dtype if prompt_embeds.dtype in (torch.float32, BF16) else torch.float32
         init = self.prepare_latents(latents, media_items, ts_host[0], latent_shape, noise_dtype, device, generator)
         tokens, pixel_coords, conditioning_mask, num_cond_latents = self.prepare_conditioning(
-            conditioning_items, init.clone(), num_frames, height, width)
+            conditioning_items, init.clone(), num_frames, height, width, vae_per_channel_normalize=vae_per_channel_normalize,
+            generator=generator)
         init_tokens = tokens.clone()
         frac = pixel_coords.to(torch.float32)
         frac[:, 0] = frac[:, 0] * (1.0 / frame_rate)

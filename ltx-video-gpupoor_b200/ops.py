@@ -347,3 +347,19 @@ def softmax_rows(s: torch.Tensor, scale: float, out: Optional[torch.Tensor] = No
     _lib.check(_lib.lib().ltxb200_softmax_rows_f32_bf16(s.data_ptr(), s.stride(0), p.data_ptr(), p.stride(0), s.shape[0], s.shape[1],
                                                         float(scale), _stream()), "softmax_rows_f32_bf16")
     return p
+
+
+def conv3d_strided(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], stride_t: int = 2, stride_hw: int = 2) -> torch.Tensor:
+    """Causal 3x3x3 conv with output strides: x [B,T,H,W,Cin] bf16 NDHWC, w [Cout, 27*Cin] tap-major."""
+    _req(x, name="x"); _req(w, name="w")
+    assert x.is_contiguous() and w.is_contiguous() and x.dim() == 5
+    B, T, H, W, Cin = x.shape
+    Cout = w.shape[0]
+    assert w.shape[1] == 27 * Cin
+    To, Ho, Wo = (T - 1) // stride_t + 1, (H - 1) // stride_hw + 1, (W - 1) // stride_hw + 1
+    out = torch.empty(B, To, Ho, Wo, Cout, device=x.device, dtype=BF16)
+    with _Prof('conv3d_bf16', 'flop', 2.0 * B * To * Ho * Wo * Cout * 27 * Cin):
+        rc = _lib.lib().ltxb200_conv3d_strided_bf16(x.data_ptr(), w.data_ptr(), _p(bias), out.data_ptr(), B, T, H, W, Cin, Cout,
+                                                    stride_t, stride_hw, _stream())
+    _lib.check(rc, "conv3d_strided_bf16")
+    return out

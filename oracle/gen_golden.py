@@ -155,6 +155,37 @@ def build_ref_vae(sd):
     return vae.eval()
 
 
+def case_vae_encode():
+    """Encoder.forward + DiagonalGaussianDistribution + normalize_latents as driven by vae_encode (vae_encode.py:22-91)."""
+    from ltx_video.models.autoencoders.causal_video_autoencoder import CausalVideoAutoencoder
+    from ltx_video.models.autoencoders.vae_encode import vae_encode
+    from ltx_video.utils.diffusers_config_mapping import OURS_VAE_CONFIG
+    sd = O.make_vae_encoder_state_dict(seed=2)
+    vae = CausalVideoAutoencoder.from_config(dict(OURS_VAE_CONFIG))
+    vae.encoder.load_state_dict({k[len("encoder."):]: v for k, v in sd.items() if k.startswith("encoder.")}, strict=True)
+    vae.register_buffer("std_of_means", sd["std_of_means"])
+    vae.register_buffer("mean_of_means", sd["mean_of_means"])
+    vae = vae.eval()
+    g = torch.Generator().manual_seed(11)
+    video = (torch.rand(1, 3, 9, 64, 96, generator=g) * 2 - 1)
+    image = video[:, :, :1].contiguous()                                   # single conditioning frame (i2v)
+    out = {}
+    for tag, x in (("video", video), ("image", image)):
+        post = vae.encode(x).latent_dist
+        mean, logvar = O.vae_encode_moments(sd, x)
+        _check(f"vae_encode moments mean ({tag})", mean, post.mean, tol=1e-4)
+        assert O.rel_l2(logvar.expand_as(post.logvar).clamp(-30, 20), post.logvar) < 1e-4
+        torch.manual_seed(123)
+        z_ref = vae_encode(x, vae, vae_per_channel_normalize=True)
+        torch.manual_seed(123)
+        noise = torch.randn(mean.shape)
+        z = O.vae_encode(sd, x, noise=noise)
+        _check(f"vae_encode sample+normalize ({tag})", z, z_ref, tol=1e-4)
+        out[tag] = dict(x=x.half(), mean=post.mean.clone(), logvar=post.logvar[:, :1].clone(), z=z_ref.clone(), noise=noise)
+    assert O.vae_encode_moments(sd, video)[0].shape == (1, 128, 2, 2, 3)
+    torch.save(dict(seed_weights=2, **out), os.path.join(GOLD, "ltx_vae_encode.pt"))
+
+
 def case_vae():
     from ltx_video.models.autoencoders.vae_encode import vae_decode
     sd = O.make_vae_decoder_state_dict(seed=1)
@@ -267,7 +298,7 @@ def case_pipeline():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["patchifier", "scheduler", "transformer", "vae", "pipeline"]
+    which = sys.argv[1:] or ["patchifier", "scheduler", "transformer", "vae", "vae_encode", "pipeline"]
     for w in which:
         print(f"[{w}]")
         globals()["case_" + w]()

@@ -570,6 +570,98 @@ def vae_decode(sd: Dict[str, Tensor], latents: Tensor, cfg: dict = LTX_VAE,
     return vae_unpatchify(x, cfg["patch_size"])
 
 
+# --------------------------------------------------------------------------------------
+# VAE encode (i2v / v2v conditioning): vae_encode.py:22-91 -> AutoencoderKLWrapper.encode (vae.py:265-306) ->
+# Encoder.forward (causal_video_autoencoder.py:510-557), always causal, strided "compress_all" convolutions
+# --------------------------------------------------------------------------------------
+def vae_encoder_plan(cfg: dict = LTX_VAE) -> List[Tuple[str, int, int, int, int]]:
+    """[(kind, index, c_in, c_out, n)] for encoder.down_blocks (causal_video_autoencoder.py:373-478)."""
+    ch = cfg["base_channels"]
+    plan = []
+    for idx, (name, p) in enumerate(cfg["blocks"]):
+        if name == "res_x":
+            plan.append(("res_x", idx, ch, ch, int(p)))
+        elif name == "res_x_y":
+            plan.append(("res_x_y", idx, ch, ch * 2, 1))
+            ch *= 2
+        elif name == "compress_all":
+            plan.append(("down", idx, ch, ch, 1))
+        else:
+            raise ValueError(name)
+    return plan
+
+
+def make_vae_encoder_state_dict(cfg: dict = LTX_VAE, seed: int = 2) -> Dict[str, Tensor]:
+    """Random-init encoder weights (keys as in causal_video_autoencoder.py) + the latent statistics of the decoder dict."""
+    gen = torch.Generator(device="cpu").manual_seed(seed)
+    sd: Dict[str, Tensor] = {}
+    _conv3d(sd, gen, "encoder.conv_in.conv", cfg["base_channels"], cfg.get("in_channels", 3) * cfg["patch_size"] ** 2)
+    ch = cfg["base_channels"]
+    for kind, idx, cin, cout, n in vae_encoder_plan(cfg):
+        p = f"encoder.down_blocks.{idx}."
+        if kind == "res_x":
+            for j in range(n):
+                _conv3d(sd, gen, p + f"res_blocks.{j}.conv1.conv", cin, cin)
+                _conv3d(sd, gen, p + f"res_blocks.{j}.conv2.conv", cin, cin)
+        elif kind == "res_x_y":
+            _conv3d(sd, gen, p + "conv1.conv", cout, cin)
+            _conv3d(sd, gen, p + "conv2.conv", cout, cout)
+            _conv3d(sd, gen, p + "conv_shortcut", cout, cin, k=1)
+            sd[p + "norm3.norm.weight"] = 1.0 + 0.1 * torch.randn(cin, generator=gen)
+            sd[p + "norm3.norm.bias"] = 0.1 * torch.randn(cin, generator=gen)
+        else:
+            _conv3d(sd, gen, p + "conv", cout, cin)
+        ch = cout
+    _conv3d(sd, gen, "encoder.conv_out.conv", cfg["latent_channels"] + 1, ch)      # latent_log_var "uniform": +1 channel
+    sd["std_of_means"] = 0.5 + torch.rand(cfg["latent_channels"], generator=gen)
+    sd["mean_of_means"] = 0.1 * torch.randn(cfg["latent_channels"], generator=gen)
+    return sd
+
+
+def vae_patchify(x: Tensor, p: int) -> Tensor:
+    """'b c (f 1) (h q) (w r) -> b (c 1 r q) f h w' (causal_video_autoencoder.py:1261-1279): channel order (c, r, q)."""
+    b, c, f, hh, ww = x.shape
+    h, w = hh // p, ww // p
+    x = x.reshape(b, c, f, h, p, w, p)              # b c f h q w r
+    x = x.permute(0, 1, 6, 4, 2, 3, 5)              # b c r q f h w
+    return x.reshape(b, c * p * p, f, h, w)
+
+
+def strided_causal_conv3d(sd, name, x: Tensor, stride=(2, 2, 2)) -> Tensor:
+    """make_conv_nd(..., stride, causal=True): replicate the first frame twice in front, zero-pad space by 1."""
+    x = torch.cat([x[:, :, :1].repeat(1, 1, 2, 1, 1), x], dim=2)
+    return F.conv3d(x, sd[name + ".conv.weight"], sd[name + ".conv.bias"], stride=stride, padding=(0, 1, 1))
+
+
+def vae_encode_moments(sd: Dict[str, Tensor], video: Tensor, cfg: dict = LTX_VAE) -> Tuple[Tensor, Tensor]:
+    """Encoder.forward + the 'uniform' log-variance expansion (:510-545) -> (mean [B,128,F',H',W'], logvar [B,1,F',H',W'])
+    of the DiagonalGaussianDistribution.  video [B,3,F,H,W] in [-1, 1], F = 8k+1."""
+    x = vae_patchify(video, cfg["patch_size"])
+    x = causal_conv3d(sd, "encoder.conv_in", x, True)
+    for kind, idx, cin, cout, n in vae_encoder_plan(cfg):
+        p = f"encoder.down_blocks.{idx}."
+        if kind == "res_x":
+            for j in range(n):
+                x = _resnet(sd, p + f"res_blocks.{j}.", x, cin, cin, True)
+        elif kind == "res_x_y":
+            x = _resnet(sd, p, x, cin, cout, True)
+        else:
+            x = strided_causal_conv3d(sd, p[:-1], x)
+    x = causal_conv3d(sd, "encoder.conv_out", F.silu(pixel_norm(x)), True)
+    return x[:, :-1], x[:, -1:]
+
+
+def vae_encode(sd: Dict[str, Tensor], video: Tensor, cfg: dict = LTX_VAE, noise: Optional[Tensor] = None,
+               per_channel_normalize: bool = True) -> Tensor:
+    """vae_encode (vae_encode.py:22-91): latent_dist.sample() = mean + exp(0.5*clamp(logvar,-30,20))*noise (diffusers
+    DiagonalGaussianDistribution; noise=None -> the mode), then normalize_latents (:228-237)."""
+    mean, logvar = vae_encode_moments(sd, video, cfg)
+    z = mean if noise is None else mean + torch.exp(0.5 * logvar.clamp(-30.0, 20.0)) * noise
+    if per_channel_normalize:
+        z = (z - sd["mean_of_means"].to(z.dtype).view(1, -1, 1, 1, 1)) / sd["std_of_means"].to(z.dtype).view(1, -1, 1, 1, 1)
+    return z * cfg.get("scaling_factor", 1.0)
+
+
 def postprocess(image: Tensor) -> Tensor:
     """VaeImageProcessor.postprocess for tensors: x/2+0.5 clamped to [0,1]."""
     return (image / 2 + 0.5).clamp(0, 1)

@@ -155,3 +155,73 @@ def test_vae_decode_vs_reference_fixture(golden_dir):
     ps = O.psnr(a, b)
     print(f"vae decode PSNR vs reference = {ps:.1f} dB, rel_l2 = {O.rel_l2(y.float().cpu(), g['out'].float()):.3e}")
     assert ps >= 40.0
+
+
+# ------------------------------------------------------------------ VAE encode (i2v / v2v conditioning from pixels)
+@pytest.mark.parametrize("st,shw,T,H,W", [(2, 2, 9, 16, 24), (1, 2, 3, 7, 10), (2, 1, 5, 6, 9)])
+def test_conv3d_strided(st, shw, T, H, W):
+    import torch.nn.functional as F
+    from ltx_video_gpupoor_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    Cin, Cout = 64, 128
+    x = torch.randn(1, T, H, W, Cin, generator=g).bfloat16().cuda()
+    w5 = (torch.randn(Cout, Cin, 3, 3, 3, generator=g) * (27 * Cin) ** -0.5).bfloat16().cuda()
+    b = torch.randn(Cout, generator=g).bfloat16().cuda()
+    xr = x.float().permute(0, 4, 1, 2, 3)
+    xr = torch.cat([xr[:, :, :1].repeat(1, 1, 2, 1, 1), xr], dim=2)
+    ref = F.conv3d(xr, w5.float(), b.float(), stride=(st, shw, shw), padding=(0, 1, 1)).permute(0, 2, 3, 4, 1)
+    out = ops.conv3d_strided(x, w5.permute(0, 2, 3, 4, 1).reshape(Cout, -1).contiguous(), b, st, shw)
+    torch.cuda.synchronize()
+    assert out.shape == ref.shape
+    assert O.rel_l2(out.float().cpu(), ref.cpu()) < 6e-3
+
+
+def test_vae_encode_vs_reference_fixture(golden_dir):
+    from ltx_video_gpupoor_b200.ltx.causal_video_autoencoder import CausalVideoAutoencoder, vae_encode
+    g = torch.load(os.path.join(golden_dir, "ltx_vae_encode.pt"), weights_only=False)
+    sd = O.make_vae_encoder_state_dict(seed=g["seed_weights"])
+    sd.update({k: v for k, v in O.make_vae_decoder_state_dict(seed=1).items() if k.startswith("decoder.")})
+    vae = CausalVideoAutoencoder()
+    vae.load_state_dict(sd)
+    for tag in ("video", "image"):
+        c = g[tag]
+        post = vae.encode(c["x"].float().cuda()).latent_dist
+        e = O.rel_l2(post.mean.cpu(), c["mean"])
+        print(f"vae encode ({tag}): mean rel_l2 vs reference = {e:.3e}")
+        assert e < 2e-2
+        assert O.rel_l2(post.logvar[:, :1].cpu(), c["logvar"].clamp(-30, 20)) < 2e-2
+        z = vae_encode(c["x"].float().cuda(), vae, vae_per_channel_normalize=True, noise=c["noise"])
+        assert O.rel_l2(z.cpu(), c["z"]) < 2e-2
+
+
+def test_pipeline_i2v_from_pixels_vs_oracle():
+    """BASELINE config 3 in small: the conditioning image goes through the VAE ENCODER (vae_encode.py:22-91), the loop runs with
+    the per-token timesteps / conditioning mask, and the result is compared with the oracle driven by the oracle's own encode."""
+    pipe, sd, _ = _pipe(2)
+    esd = O.make_vae_encoder_state_dict(seed=2)
+    vsd = dict(O.make_vae_decoder_state_dict(seed=1))
+    vsd.update({k: v for k, v in esd.items()})                      # encoder.* + the latent statistics of the encoder dict
+    pipe.vae.load_state_dict(vsd)
+    g = torch.Generator().manual_seed(4)
+    pe, pm = torch.randn(1, 16, 4096, generator=g), torch.ones(1, 16)
+    image = torch.rand(1, 3, 1, 128, 192, generator=g) * 2 - 1
+    noise_e = torch.zeros(1, 128, 1, 4, 6)                             # latent_dist.mode(): deterministic
+    per_step = []
+    pipe(height=128, width=192, num_frames=17, frame_rate=25.0, prompt_embeds=pe, prompt_attention_mask=pm,
+         num_inference_steps=3, guidance_scale=1.0, stg_scale=0.0, rescaling_scale=1.0,
+         generator=torch.Generator().manual_seed(5), output_type="latent", return_dict=False, is_video=True,
+         vae_per_channel_normalize=True,
+         conditioning_items=[ConditioningItem(media_item=image, media_frame_number=0, conditioning_strength=1.0, encode_noise=noise_e)],
+         _per_step_latents=per_step)
+    cond_lat = O.vae_encode(esd, image, noise=None)
+    noise = torch.randn(1, 72, 128, generator=torch.Generator().manual_seed(5))
+    init = O.unpatchify(noise, 3, 4, 6).clone()
+    init[:, :, :1] = cond_lat
+    cmask = torch.zeros(1, 3, 4, 6); cmask[:, :1] = 1.0
+    ref_steps = []
+    O.denoise_loop(sd, O.LTX_2B, O.patchify(init), pe, pm, num_frames_lat=3, lat_h=4, lat_w=6, frame_rate=25.0,
+                   num_steps=3, conditioning_mask=cmask.reshape(1, -1), per_step=ref_steps)
+    for i, (a, b) in enumerate(zip(per_step, ref_steps)):
+        err = O.rel_l2(a.cpu(), b)
+        print(f"i2v-from-pixels step {i}: rel_l2 = {err:.3e}")
+        assert err < TOL_LATENTS

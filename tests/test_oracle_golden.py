@@ -102,3 +102,16 @@ def test_wan_vae_decode_oracle_matches_reference(golden_dir):
     y = V.wan_vae_decode(sd, g["z"], g["cfg"], torch.tensor(V.WAN_VAE_MEAN), torch.tensor(V.WAN_VAE_STD))
     assert y.shape == (3, 13, 48, 80)
     assert O.rel_l2(y, g["out"].float()) < 2e-3      # fixture stored as fp16
+
+
+def test_vae_encode_oracle_matches_reference(golden_dir):
+    """Encoder.forward + latent_dist.sample() + normalize_latents (oracle) vs the fixture recorded from the unmodified reference
+    (oracle/gen_golden.py:case_vae_encode — bit-identical there)."""
+    g = _load(golden_dir, "ltx_vae_encode.pt")
+    sd = O.make_vae_encoder_state_dict(seed=g["seed_weights"])
+    for tag in ("video", "image"):
+        c = g[tag]
+        mean, logvar = O.vae_encode_moments(sd, c["x"].float())
+        assert O.rel_l2(mean, c["mean"]) < 2e-3                         # input stored as fp16
+        z = O.vae_encode(sd, c["x"].float(), noise=c["noise"])
+        assert O.rel_l2(z, c["z"]) < 2e-3
