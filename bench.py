@@ -28,6 +28,10 @@ WORKLOADS = {
     "ltx2b_768x512x121_cfg_stg": dict(height=512, width=768, num_frames=121, frame_rate=25.0, schedule_steps=30,
                                       guidance_scale=3.0, stg_scale=1.0, rescaling_scale=0.7, skip_block_list=[19],
                                       prompt_tokens=256, num_conds=3),
+    # BASELINE.json configs[2]: i2v — the conditioning image goes through the VAE encoder, per-token timesteps, full decode
+    "ltx2b_768x512x121_i2v_cfg_stg": dict(height=512, width=768, num_frames=121, frame_rate=25.0, schedule_steps=30,
+                                          guidance_scale=3.0, stg_scale=1.0, rescaling_scale=0.7, skip_block_list=[19],
+                                          prompt_tokens=256, num_conds=3, i2v=True),
     "ltx2b_768x512x121_noguidance": dict(height=512, width=768, num_frames=121, frame_rate=25.0, schedule_steps=30,
                                          guidance_scale=1.0, stg_scale=0.0, rescaling_scale=1.0, skip_block_list=None,
                                          prompt_tokens=256, num_conds=1),
@@ -417,8 +421,9 @@ def main():
 
     from ltx_video_gpupoor_b200 import _lib, ops
     from ltx_video_gpupoor_b200.ltx.causal_video_autoencoder import CausalVideoAutoencoder, vae_decode
-    from ltx_video_gpupoor_b200.ltx.init_weights import random_transformer_state_dict, random_vae_decoder_state_dict
-    from ltx_video_gpupoor_b200.ltx.pipeline_ltx_video import LTXVideoPipeline
+    from ltx_video_gpupoor_b200.ltx.init_weights import (random_transformer_state_dict, random_vae_decoder_state_dict,
+                                                          random_vae_encoder_state_dict)
+    from ltx_video_gpupoor_b200.ltx.pipeline_ltx_video import ConditioningItem, LTXVideoPipeline
     from ltx_video_gpupoor_b200.ltx.rf import RectifiedFlowScheduler
     from ltx_video_gpupoor_b200.ltx.skip_layer_strategy import SkipLayerStrategy
     from ltx_video_gpupoor_b200.ltx.symmetric_patchifier import SymmetricPatchifier
@@ -428,7 +433,11 @@ def main():
     tr = Transformer3DModel(**cfg)
     tr.load_state_dict(random_transformer_state_dict(cfg, seed=0, device=dev), device=dev)
     vae = CausalVideoAutoencoder()
-    vae.load_state_dict(random_vae_decoder_state_dict(seed=1, device=dev), device=dev)
+    vsd = random_vae_decoder_state_dict(seed=1, device=dev)
+    if wl.get("i2v"):
+        vsd.update(random_vae_encoder_state_dict(seed=2, device=dev))
+    vae.load_state_dict(vsd, device=dev)
+    del vsd
     pipe = LTXVideoPipeline(vae=vae, transformer=tr, scheduler=RectifiedFlowScheduler(), patchifier=SymmetricPatchifier(1))
 
     # synthetic prompt embeddings of the named shape, in pinned host memory (e2e copies them every call)
@@ -443,6 +452,12 @@ def main():
                    skip_block_list=wl["skip_block_list"],
                    skip_layer_strategy=SkipLayerStrategy.AttentionValues if wl["skip_block_list"] else None,
                    is_video=True, vae_per_channel_normalize=True, return_dict=False)
+    img_h = None
+    if wl.get("i2v"):
+        # synthetic conditioning frame in pinned host memory: encoded by the VAE inside every pipeline call (e2e includes it)
+        img_h = (torch.rand(1, 3, 1, wl["height"], wl["width"], generator=g) * 2 - 1).pin_memory()
+        call_kw.update(conditioning_items=[ConditioningItem(media_item=img_h, media_frame_number=0, conditioning_strength=1.0)],
+                       image_cond_noise_scale=0.15)
 
     def barrier():
         if dist is not None:
@@ -528,7 +543,7 @@ def main():
         t = torch.tensor([e2e_s], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t)
-    h2d = (pe_h.numel() + ne_h.numel()) * 2 + (pm_h.numel() + nm_h.numel()) * 4
+    h2d = (pe_h.numel() + ne_h.numel()) * 2 + (pm_h.numel() + nm_h.numel()) * 4 + (img_h.numel() * 4 if img_h is not None else 0)
     e2e = {"value": world * K / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": h2d / K,
            "d2h_bytes_per_step": lat_h.numel() * lat_h.element_size() / K, "steps_in_call": K,
            "api": "LTXVideoPipeline.__call__(prompt_embeds=<pinned host>, output_type='latent') + .cpu()"}

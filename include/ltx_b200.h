@@ -107,6 +107,14 @@ int ltxb200_act_bf16(const void* x, void* y, int64_t n, int mode, void* stream);
 int ltxb200_stg_blend_bf16(void* a, const void* v, int64_t ldv, const float* mask, int B, int64_t rows, int D,
                            void* stream);
 
+/* out = bf16(a*x + b*y), n % 8 == 0, out may alias x or y.  TeaCache residual reuse / capture
+ * (wan/modules/model.py:1051-1054 `x += previous_residual[i]`, :1090-1099 `torch.sub(x, ori)`). */
+int ltxb200_axpby_bf16(const void* x, const void* y, void* out, int64_t n, float a, float b, void* stream);
+
+/* TeaCache step distance (wan/modules/model.py:1039 `(e - prev).abs().mean() / prev.abs().mean()`):
+ * out2[0] = sum |bf16(a - b)|, out2[1] = sum |b| (fp32, device).  a, b: bf16 [n]. */
+int ltxb200_rel_l1_bf16(const void* a, const void* b, int64_t n, float* out2, void* stream);
+
 /* diffusers Timesteps(256, flip_sin_to_cos=True, downscale_freq_shift=0): out[n, dim] bf16 from t[n] fp32 */
 int ltxb200_timestep_embed(const float* t, void* out, int n, int dim, void* stream);
 

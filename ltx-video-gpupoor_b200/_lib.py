@@ -35,6 +35,8 @@ def _declare(lib):
         "ltxb200_ada_add_bf16": ([P, P, P, I, I, I, P], I),
         "ltxb200_act_bf16": ([P, P, L, I, P], I),
         "ltxb200_stg_blend_bf16": ([P, P, L, P, I, L, I, P], I),
+        "ltxb200_axpby_bf16": ([P, P, P, L, F, F, P], I),
+        "ltxb200_rel_l1_bf16": ([P, P, L, P, P], I),
         "ltxb200_timestep_embed": ([P, P, I, I, P], I),
         "ltxb200_cast_f32_to_bf16": ([P, P, L, P], I),
         "ltxb200_guidance_step": ([P, L, L, I, I, I, I, F, F, F, P, P, P, I, F, P, P, P], I),

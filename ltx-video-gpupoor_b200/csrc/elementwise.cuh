@@ -793,4 +793,34 @@ __global__ void latent_to_ndhwc_kernel(const T* __restrict__ z, __nv_bfloat16* _
   }
 }
 
+// out = bf16(a*x + b*y): TeaCache residual bookkeeping (wan/modules/model.py:1051-1054 `x += previous_residual`,
+// :1090-1099 `torch.sub(x, ori)`); fp32 arithmetic, one rounding, like ATen's bf16 add/sub.  out may alias x or y.
+__global__ void axpby_kernel(const __nv_bfloat16* x, const __nv_bfloat16* y, __nv_bfloat16* out, long long n, float a, float b) {
+  for (long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 8; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x * 8) {
+    float u[8], v[8];
+    load8(x + i, u);
+    load8(y + i, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) u[j] = fmaf(b, v[j], a * u[j]);
+    store8(out + i, u);
+  }
+}
+
+// TeaCache distance statistics (model.py:1039): out[0] = sum |bf16(a - b)|, out[1] = sum |b| over n elements
+// (one 256-thread block: the operands are the [1, dim] time embeddings of two consecutive steps).
+__global__ void rel_l1_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b, long long n,
+                              float* __restrict__ out) {
+  __shared__ float sm[8];
+  float d = 0.f, m = 0.f;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const float x = __bfloat162float(a[i]), y = __bfloat162float(b[i]);
+    d += fabsf(bf16r(x - y));
+    m += fabsf(y);
+  }
+  d = block_sum_256(d, sm);
+  m = block_sum_256(m, sm);
+  if (threadIdx.x == 0) { out[0] = d; out[1] = m; }
+}
+
 }  // namespace b200

@@ -495,6 +495,22 @@ extern "C" int ltxb200_stg_blend_bf16(void* a, const void* v, int64_t ldv, const
   return launch_status();
 }
 
+extern "C" int ltxb200_axpby_bf16(const void* x, const void* y, void* out, int64_t n, float a, float b, void* stream) {
+  if (n <= 0 || (n & 7)) return kErrBadShape;
+  if (!aligned16(x) || !aligned16(y) || !aligned16(out)) return kErrBadAlign;
+  axpby_kernel<<<ew_blocks(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(y), static_cast<__nv_bfloat16*>(out), n, a, b);
+  return launch_status();
+}
+
+extern "C" int ltxb200_rel_l1_bf16(const void* a, const void* b, int64_t n, float* out2, void* stream) {
+  if (n <= 0) return kErrBadShape;
+  if (!a || !b || !out2) return kErrBadAlign;
+  rel_l1_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(a),
+                                                                 static_cast<const __nv_bfloat16*>(b), n, out2);
+  return launch_status();
+}
+
 extern "C" int ltxb200_timestep_embed(const float* t, void* out, int n, int dim, void* stream) {
   if (n <= 0 || dim <= 0 || (dim & 1)) return kErrBadShape;
   timestep_embed_kernel<<<n, 128, 0, static_cast<cudaStream_t>(stream)>>>(t, static_cast<__nv_bfloat16*>(out), n, dim, 1);

@@ -73,3 +73,33 @@ def random_vae_decoder_state_dict(config: dict = LTX_VAE_CONFIG, seed: int = 1, 
     sd["std_of_means"] = 0.5 + torch.rand(config["latent_channels"], generator=gen, device=device)
     sd["mean_of_means"] = 0.1 * torch.randn(config["latent_channels"], generator=gen, device=device)
     return sd
+
+
+def random_vae_encoder_state_dict(config: dict = LTX_VAE_CONFIG, seed: int = 2, device="cuda",
+                                  dtype=torch.bfloat16) -> Dict[str, torch.Tensor]:
+    """encoder.* keys of CausalVideoAutoencoder (causal_video_autoencoder.py:313-557), random init."""
+    gen = torch.Generator(device=device).manual_seed(seed)
+    sd = {}
+
+    def conv(name, o, i, k=3):
+        b = 1 / math.sqrt(i * k ** 3)
+        sd[name + ".weight"] = _u((o, i, k, k, k), b, gen, device, dtype)
+        sd[name + ".bias"] = _u((o,), b, gen, device, dtype)
+
+    ch = 128
+    conv("encoder.conv_in.conv", ch, config["in_channels"] * config["patch_size"] ** 2)
+    for idx, (name, n) in enumerate(config["blocks"]):
+        p = f"encoder.down_blocks.{idx}."
+        if name == "res_x":
+            for j in range(int(n)):
+                conv(p + f"res_blocks.{j}.conv1.conv", ch, ch); conv(p + f"res_blocks.{j}.conv2.conv", ch, ch)
+        elif name == "res_x_y":
+            conv(p + "conv1.conv", 2 * ch, ch); conv(p + "conv2.conv", 2 * ch, 2 * ch)
+            conv(p + "conv_shortcut", 2 * ch, ch, k=1)
+            sd[p + "norm3.norm.weight"] = torch.ones(ch, device=device, dtype=dtype)
+            sd[p + "norm3.norm.bias"] = torch.zeros(ch, device=device, dtype=dtype)
+            ch *= 2
+        else:
+            conv(p + "conv", ch, ch)
+    conv("encoder.conv_out.conv", config["latent_channels"] + 1, ch)
+    return sd

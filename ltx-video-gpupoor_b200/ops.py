@@ -197,6 +197,29 @@ def stg_blend(a: torch.Tensor, v: torch.Tensor, mask: torch.Tensor):
                                                  _stream()), "stg_blend_bf16")
 
 
+def axpby(x: torch.Tensor, y: torch.Tensor, a: float = 1.0, b: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = bf16(a*x + b*y) (out may be x or y)."""
+    _req(x, name="x"); _req(y, name="y")
+    assert x.is_contiguous() and y.is_contiguous() and x.shape == y.shape
+    if out is None:
+        out = torch.empty_like(x)
+    _req(out, name="out"); assert out.is_contiguous() and out.shape == x.shape
+    _lib.check(_lib.lib().ltxb200_axpby_bf16(x.data_ptr(), y.data_ptr(), out.data_ptr(), x.numel(), float(a), float(b),
+                                             _stream()), "axpby_bf16")
+    return out
+
+
+def rel_l1(a: torch.Tensor, b: torch.Tensor) -> float:
+    """`((a - b).abs().mean() / b.abs().mean()).cpu().item()` with ATen's bf16 roundings (model.py:1039); syncs like the
+    reference's .item()."""
+    _req(a, name="a"); _req(b, name="b")
+    assert a.is_contiguous() and b.is_contiguous() and a.shape == b.shape
+    out = torch.empty(2, device=a.device, dtype=torch.float32)
+    _lib.check(_lib.lib().ltxb200_rel_l1_bf16(a.data_ptr(), b.data_ptr(), a.numel(), out.data_ptr(), _stream()), "rel_l1_bf16")
+    s = (out.cpu() / a.numel()).to(BF16)           # the two means, rounded to the tensors' dtype
+    return float((s[0] / s[1]).item())             # bf16 division
+
+
 def timestep_embed(t: torch.Tensor, dim: int = 256) -> torch.Tensor:
     _req(t, torch.float32, "t"); assert t.dim() == 1 and t.is_contiguous()
     out = torch.empty(t.shape[0], dim, device=t.device, dtype=BF16)

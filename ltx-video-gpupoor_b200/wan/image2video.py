@@ -63,11 +63,16 @@ class WanI2V:
         ctx = context.to(dev)
         ctx0 = context_null.to(dev) if context_null is not None else None
         yd, clip = y.to(dev), clip_fea.to(dev)
+        if self.model.enable_teacache:                                                                    # image2video.py:318-321
+            self.model.previous_residual = [None] * 2
+            if getattr(self.model, "teacache_multiplier", 0):
+                self.model.compute_teacache_threshold(self.model.teacache_start_step, sch.timesteps_host, self.model.teacache_multiplier)
         if callback is not None:
             callback(-1, None, True)
         for i, t in enumerate(sch.timesteps_host):
             ts = torch.tensor([t], device=dev)
-            kw = dict(t=ts, clip_fea=clip, y=yd, freqs=freqs, pipeline=self, current_step=i)
+            slg = slg_layers if int(slg_start * sampling_steps) <= i < int(slg_end * sampling_steps) else None   # :333
+            kw = dict(t=ts, clip_fea=clip, y=yd, freqs=freqs, pipeline=self, current_step=i, slg_layers=slg)
             if guide_scale == 1:
                 pred = self.model([latents], context=[ctx], **kw)[0]                                     # :340-341
                 if pred is None:

@@ -7,8 +7,11 @@ Same constructor keys, state_dict layout and forward signature
 (`forward(x: list[Tensor[C,T,H,W]], t, context: list[Tensor[L,4096]], freqs=(cos,sin), pipeline=…, …) ->
 list[Tensor float32]`).  The reference iterates the sequences of a joint pass inside every block so that
 offloaded weights are fetched once (:1082-1085); on a 180 GB part the sequences are simply batched.
-VACE / recam / fantasytalking / TeaCache / SLG branches are add-ons outside the benchmarked configs
- and raise NotImplementedError.
+Step skipping is built in: skip-layer guidance (`slg_layers`, model.py:1077-1080) runs the listed blocks
+on the conditional sequence only, TeaCache (`enable_teacache`, model.py:854-899,1029-1101) replays the previous step's
+block-stack residual when the accumulated time-embedding distance stays under `rel_l1_thresh`.
+VACE / recam / fantasytalking branches are add-ons outside the benchmarked configs and raise
+NotImplementedError.
 
 Sequence parallelism (P ranks, one process per GPU): tokens are split contiguously (:131-133); everything
 token-wise stays local; around self-attention q/k/v are exchanged heads<->sequence with one all-to-all each
@@ -54,7 +57,12 @@ class WanModel:
         self.model_type, self.patch_size, self.text_len = model_type, tuple(patch_size), text_len
         self.in_dim, self.dim, self.ffn_dim, self.freq_dim = in_dim, dim, ffn_dim, freq_dim
         self.text_dim, self.out_dim, self.num_heads, self.num_layers, self.eps = text_dim, out_dim, num_heads, num_layers, eps
+        # TeaCache state: same attribute names as the reference (set by the caller / text2video.py:461-464)
         self.enable_teacache = False
+        self.coefficients, self.rel_l1_thresh, self.teacache_start_step, self.num_steps = [1.0, 0.0], 0.0, 0, 0
+        self.teacache_multiplier = 0
+        self.accumulated_rel_l1_distance, self.teacache_skipped_steps = 0, 0
+        self.previous_residual, self.previous_modulated_input, self.should_calc = [None, None], None, True
         self.dtype = BF16
         self.device = torch.device("cuda")
         self.w: Dict[str, torch.Tensor] = {}
@@ -155,6 +163,104 @@ class WanModel:
         return ulysses_self_attention(qkv, B, n_loc, self.num_heads, 128, self.sp_group,
                                       lambda q, k, v, out: ops.attention(q, k, v, out=out))
 
+    # ---------------------------------------------------------------------------------------------
+    def _time_embedding(self, tt: torch.Tensor) -> torch.Tensor:
+        """time_embedding(sinusoidal_embedding_1d(freq_dim, t)) (model.py:979-981) -> [n, D] bf16"""
+        w = self.w
+        te = ops.timestep_embed(tt, self.freq_dim)
+        return ops.gemm(ops.gemm(te, w["time0.w"], w["time0.b"], act=ops.ACT_SILU), w["time2.w"], w["time2.b"])
+
+    def _teacache_should_calc(self, e: torch.Tensor, current_step: int, x_id: int) -> bool:
+        """model.py:1029-1049: the conditional pass (x_id 0) decides, the others follow."""
+        if x_id != 0:
+            return self.should_calc
+        if current_step <= self.teacache_start_step or current_step == self.num_steps - 1:
+            should_calc = True
+            self.accumulated_rel_l1_distance = 0
+        else:
+            import numpy as np
+            delta = abs(np.poly1d(self.coefficients)(ops.rel_l1(e, self.previous_modulated_input)))
+            self.accumulated_rel_l1_distance += delta
+            if self.accumulated_rel_l1_distance < self.rel_l1_thresh:
+                should_calc = False
+                self.teacache_skipped_steps += 1
+            else:
+                should_calc = True
+                self.accumulated_rel_l1_distance = 0
+        self.previous_modulated_input = e
+        self.should_calc = should_calc
+        return should_calc
+
+    def compute_teacache_threshold(self, start_step, timesteps=None, speed_factor=0):
+        """model.py:854-899: scan thresholds 0.01..0.6 for the one whose simulated schedule is closest to
+        len(timesteps)/speed_factor computed steps; sets and returns `rel_l1_thresh`."""
+        import numpy as np
+        rescale = np.poly1d(self.coefficients)
+        tt = torch.as_tensor([float(t) for t in timesteps], device=self.device, dtype=torch.float32)
+        e_all = self._time_embedding(tt)
+        rel = [0.0] + [ops.rel_l1(e_all[i:i + 1].contiguous(), e_all[i - 1:i].contiguous()) for i in range(1, len(timesteps))]
+        target = int(len(timesteps) / speed_factor)
+        best_threshold, best_diff, best_signed, threshold = 0.01, 1000, 1000, 0.01
+        while threshold <= 0.6:
+            acc, nb, diff, signed = 0, 0, 1000, 1000
+            for i in range(len(timesteps)):
+                skip = False
+                if not (i <= start_step or i == len(timesteps) - 1):
+                    acc += abs(rescale(rel[i]))
+                    if acc < threshold:
+                        skip = True
+                    else:
+                        acc = 0
+                if not skip:
+                    nb += 1
+                    signed = target - nb
+                    diff = abs(signed)
+            if diff < best_diff:
+                best_threshold, best_diff, best_signed = threshold, diff, signed
+            elif diff > best_diff:
+                break
+            threshold += 0.01
+        self.rel_l1_thresh = best_threshold
+        return best_threshold
+
+    def _block(self, li: int, xs: torch.Tensor, st) -> None:
+        """WanAttentionBlock.forward (model.py:411-499) on the rows `xs` [B*n_loc, D], updated in place."""
+        w, D, H, eps = self.w, self.dim, self.num_heads, self.eps
+        B, n_loc, P, rank, mods, ctx, ctx_img, cos, sin = st.B, st.n_loc, st.P, st.rank, st.mods, st.ctx, st.ctx_img, st.cos, st.sin
+        M, Lc, Lw = B * n_loc, self.text_len, self.layers[li]
+        m = mods[li]                                                              # [1, 6, D]
+        xm = ops.norm_mod(xs, m[:, 1], m[:, 0], rows_per_group=M, eps=eps, layer_norm=True)        # :437-441
+        qkv = ops.gemm(xm, Lw["qkv.w"], Lw["qkv.b"])
+        if P > 1 and self.sp_exchange == "p2p":
+            # q/k norm + RoPE fused with the head scatter, attention epilogue fused with the return scatter
+            o = self._peer_exchange(B, n_loc).self_attention(qkv, Lw["qn"], Lw["kn"], cos, sin, eps, ops._stream())
+        else:
+            ops.qk_norm_rope_wan(qkv[:, :D], qkv[:, D:2 * D], Lw["qn"], Lw["kn"], cos, sin, head_dim=128,
+                                 tokens_per_batch=n_loc, token_offset=rank * n_loc, eps=eps)
+            if P == 1:
+                q3 = qkv.view(B, n_loc, 3 * D)
+                o = ops.attention(q3[:, :, :D].unflatten(-1, (H, 128)), q3[:, :, D:2 * D].unflatten(-1, (H, 128)),
+                                  q3[:, :, 2 * D:].unflatten(-1, (H, 128))).view(M, D)
+            else:
+                o = self._self_attention_sp(qkv, B, n_loc, P)
+        ops.gemm(o, Lw["o.w"], Lw["o.b"], residual=xs, gate=m[:, 2], rows_per_gate=M, out=xs)      # x.addcmul_(y, e2) :458
+        y3 = ops.norm_mod(xs, weight=Lw["n3.w"], bias=Lw["n3.b"], eps=eps, layer_norm=True)         # norm3 :461
+        q2 = ops.gemm(y3, Lw["q2.w"], Lw["q2.b"])
+        kv = ops.gemm(ctx, Lw["kv2.w"], Lw["kv2.b"])                                                # [B*512, 2D]
+        ops.qk_norm_rope_wan(q2, kv[:, :D], Lw["qn2"], Lw["kn2"], None, None, eps=eps)
+        kv3 = kv.view(B, Lc, 2 * D)
+        o2 = ops.attention(q2.view(B, n_loc, H, 128), kv3[:, :, :D].unflatten(-1, (H, 128)), kv3[:, :, D:].unflatten(-1, (H, 128)))
+        if ctx_img is not None:             # WanI2VCrossAttention :323-337: same q over the 257 image tokens, x += img_x
+            kvi = ops.gemm(ctx_img, Lw["kvi.w"], Lw["kvi.b"])                                       # [257, 2D]
+            ops.qk_norm_rope_wan(None, kvi[:, :D], None, Lw["kni"], None, None, eps=eps)
+            kvb = kvi.unsqueeze(0).repeat(B, 1, 1) if B > 1 else kvi.unsqueeze(0)                   # same image for every sequence
+            ops.attention(q2.view(B, n_loc, H, 128), kvb[:, :, :D].unflatten(-1, (H, 128)),
+                          kvb[:, :, D:].unflatten(-1, (H, 128)), out=o2, accumulate=True)
+        ops.gemm(o2.view(M, D), Lw["o2.w"], Lw["o2.b"], residual=xs, out=xs)                       # x += cross_attn :465
+        y2 = ops.norm_mod(xs, m[:, 4], m[:, 3], rows_per_group=M, eps=eps, layer_norm=True)        # :467-472
+        ff = ops.gemm(y2, Lw["ff1.w"], Lw["ff1.b"], act=ops.ACT_GELU_TANH)
+        ops.gemm(ff, Lw["ff2.w"], Lw["ff2.b"], residual=xs, gate=m[:, 5], rows_per_gate=M, out=xs) # :490-492
+
     def __call__(self, *a, **k):
         return self.forward(*a, **k)
 
@@ -169,8 +275,6 @@ class WanModel:
             assert clip_fea is not None and y is not None                             # :930-931
         elif clip_fea is not None or y is not None:
             raise ValueError("clip_fea / y are i2v inputs (model_type='i2v')")
-        if slg_layers is not None or self.enable_teacache:
-            raise NotImplementedError("SLG / TeaCache step skipping is SURVEY §8(f)#4")
         w, D, H, eps = self.w, self.dim, self.num_heads, self.eps
         dev = self.device
         P, rank = self._sp()
@@ -190,8 +294,7 @@ class WanModel:
         xs = ops.gemm(rows, w["patch.w"], w["patch.b"])                               # [B*n_loc, D]
         tt = t.to(device=dev, dtype=torch.float32).flatten().contiguous()
         assert tt.numel() == 1, "per-frame timesteps (diffusion forcing, model.py:976) are out of scope"
-        te = ops.timestep_embed(tt, self.freq_dim)                                    # sinusoidal_embedding_1d (:18-28)
-        e = ops.gemm(ops.gemm(te, w["time0.w"], w["time0.b"], act=ops.ACT_SILU), w["time2.w"], w["time2.b"])   # [1, D]
+        e = self._time_embedding(tt)                                                  # sinusoidal_embedding_1d (:18-28) -> [1, D]
         e0 = ops.gemm(ops.act(e, ops.ACT_SILU), w["tproj.w"], w["tproj.b"])           # [1, 6D]
         mods = ops.ada_add(w["block_mods"], e0)                                       # [L, 1, 6, D] = modulation + e0 (:436)
         ctx_in = torch.zeros(B, self.text_len, self.text_dim, device=dev, dtype=BF16)  # zero-pad THEN embed (:994)
@@ -212,41 +315,34 @@ class WanModel:
         M = B * n_loc
         Lc = self.text_len
 
-        for li, Lw in enumerate(self.layers):
-            if pipeline is not None and getattr(pipeline, "_interrupt", False):
-                return [None] * B
-            m = mods[li]                                                              # [1, 6, D]
-            xm = ops.norm_mod(xs, m[:, 1], m[:, 0], rows_per_group=M, eps=eps, layer_norm=True)        # :437-441
-            qkv = ops.gemm(xm, Lw["qkv.w"], Lw["qkv.b"])
-            if P > 1 and self.sp_exchange == "p2p":
-                # q/k norm + RoPE fused with the head scatter, attention epilogue fused with the return scatter
-                o = self._peer_exchange(B, n_loc).self_attention(qkv, Lw["qn"], Lw["kn"], cos, sin, eps, ops._stream())
+        joint_pass = B > 1
+        should_calc = self._teacache_should_calc(e, current_step, x_id) if self.enable_teacache else True
+        if not should_calc:                                                            # :1051-1058 replay the cached residual
+            if joint_pass:
+                for i in range(B):
+                    ops.axpby(xs[i * n_loc:(i + 1) * n_loc], self.previous_residual[i], out=xs[i * n_loc:(i + 1) * n_loc])
             else:
-                ops.qk_norm_rope_wan(qkv[:, :D], qkv[:, D:2 * D], Lw["qn"], Lw["kn"], cos, sin, head_dim=128,
-                                     tokens_per_batch=n_loc, token_offset=rank * n_loc, eps=eps)
-                if P == 1:
-                    q3 = qkv.view(B, n_loc, 3 * D)
-                    o = ops.attention(q3[:, :, :D].unflatten(-1, (H, 128)), q3[:, :, D:2 * D].unflatten(-1, (H, 128)),
-                                      q3[:, :, 2 * D:].unflatten(-1, (H, 128))).view(M, D)
+                ops.axpby(xs, self.previous_residual[x_id], out=xs)
+        else:
+            ori = xs.clone() if self.enable_teacache else None                         # :1065-1068
+            st = SimpleNamespace(B=B, n_loc=n_loc, P=P, rank=rank, mods=mods, ctx=ctx, ctx_img=ctx_img, cos=cos, sin=sin)
+            for li in range(self.num_layers):
+                if pipeline is not None and getattr(pipeline, "_interrupt", False):
+                    return [None] * B
+                if (x_id != 0 or joint_pass) and slg_layers is not None and li in slg_layers:      # :1077-1080
+                    if not joint_pass:
+                        continue                                                       # unconditional pass: block dropped
+                    # joint pass: only the conditional sequence (index 0) goes through the block; the rows are updated in place
+                    s1 = SimpleNamespace(**{**vars(st), "B": 1, "ctx": ctx[:Lc]})
+                    self._block(li, xs[:n_loc], s1)
                 else:
-                    o = self._self_attention_sp(qkv, B, n_loc, P)
-            ops.gemm(o, Lw["o.w"], Lw["o.b"], residual=xs, gate=m[:, 2], rows_per_gate=M, out=xs)      # x.addcmul_(y, e2) :458
-            y3 = ops.norm_mod(xs, weight=Lw["n3.w"], bias=Lw["n3.b"], eps=eps, layer_norm=True)         # norm3 :461
-            q2 = ops.gemm(y3, Lw["q2.w"], Lw["q2.b"])
-            kv = ops.gemm(ctx, Lw["kv2.w"], Lw["kv2.b"])                                                # [B*512, 2D]
-            ops.qk_norm_rope_wan(q2, kv[:, :D], Lw["qn2"], Lw["kn2"], None, None, eps=eps)
-            kv3 = kv.view(B, Lc, 2 * D)
-            o2 = ops.attention(q2.view(B, n_loc, H, 128), kv3[:, :, :D].unflatten(-1, (H, 128)), kv3[:, :, D:].unflatten(-1, (H, 128)))
-            if ctx_img is not None:             # WanI2VCrossAttention :323-337: same q over the 257 image tokens, x += img_x
-                kvi = ops.gemm(ctx_img, Lw["kvi.w"], Lw["kvi.b"])                                       # [257, 2D]
-                ops.qk_norm_rope_wan(None, kvi[:, :D], None, Lw["kni"], None, None, eps=eps)
-                kvb = kvi.unsqueeze(0).repeat(B, 1, 1) if B > 1 else kvi.unsqueeze(0)                   # same image for every sequence
-                ops.attention(q2.view(B, n_loc, H, 128), kvb[:, :, :D].unflatten(-1, (H, 128)),
-                              kvb[:, :, D:].unflatten(-1, (H, 128)), out=o2, accumulate=True)
-            ops.gemm(o2.view(M, D), Lw["o2.w"], Lw["o2.b"], residual=xs, out=xs)                       # x += cross_attn :465
-            y2 = ops.norm_mod(xs, m[:, 4], m[:, 3], rows_per_group=M, eps=eps, layer_norm=True)        # :467-472
-            ff = ops.gemm(y2, Lw["ff1.w"], Lw["ff1.b"], act=ops.ACT_GELU_TANH)
-            ops.gemm(ff, Lw["ff2.w"], Lw["ff2.b"], residual=xs, gate=m[:, 5], rows_per_gate=M, out=xs) # :490-492
+                    self._block(li, xs, st)
+            if self.enable_teacache:                                                   # :1087-1101 residual of the block stack
+                ops.axpby(xs, ori, 1.0, -1.0, out=ori)
+                if joint_pass:
+                    self.previous_residual = [ori[i * n_loc:(i + 1) * n_loc] for i in range(B)]
+                else:
+                    self.previous_residual[x_id] = ori
 
         eh = ops.ada_add(w["head_mod"], torch.cat([e, e], dim=1))                     # [1, 1, 2, D] = modulation + e (:566)
         yh = ops.norm_mod(xs, eh[0][:, 1], eh[0][:, 0], rows_per_group=M, eps=eps, layer_norm=True)

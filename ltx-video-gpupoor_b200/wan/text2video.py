@@ -2,7 +2,7 @@
 
 Scope: noise, UniPC schedule, RoPE tables, the per-step two-sequence forward (cond / uncond
 batched), CFG with the optional CFG-Zero* projection, scheduler step.  Text encoding (T5), the Wan VAE
-(§8f#1 "next"), VACE / phantom / recam and TeaCache are out of scope: prompt embeddings are passed in
+(§8f#1 "next"), VACE / phantom / recam are out of scope: prompt embeddings are passed in
 (`context=`, `context_null=`) and the result is the denoised latent [16, (F-1)/4+1, H/8, W/8] (fp32).
 """
 from __future__ import annotations
@@ -58,17 +58,23 @@ class WanT2V:
         scratch = torch.empty(2 * 148, device=dev, dtype=torch.float32)
         ctx = context.to(dev)
         ctx0 = context_null.to(dev) if context_null is not None else None
+        if self.model.enable_teacache:                                                                    # :461-464
+            self.model.previous_residual = [None] * 2
+            if getattr(self.model, "teacache_multiplier", 0):
+                self.model.compute_teacache_threshold(self.model.teacache_start_step, sch.timesteps_host, self.model.teacache_multiplier)
         if callback is not None:
             callback(-1, None, True)
         for i, t in enumerate(sch.timesteps_host):
             ts = torch.tensor([t], device=dev)
+            slg = slg_layers if int(slg_start * sampling_steps) <= i < int(slg_end * sampling_steps) else None   # :492
             if guide_scale == 1:
-                pred = self.model([latents], t=ts, context=[ctx], freqs=freqs, pipeline=self, current_step=i)[0]
+                pred = self.model([latents], t=ts, context=[ctx], freqs=freqs, pipeline=self, current_step=i, slg_layers=slg)[0]
                 if pred is None:
                     return None
             else:
                 # cond and uncond sequences in one batched forward (the reference's joint_pass list call, :509)
-                c, u = self.model([latents, latents], t=ts, context=[ctx, ctx0], freqs=freqs, pipeline=self, current_step=i)
+                c, u = self.model([latents, latents], t=ts, context=[ctx, ctx0], freqs=freqs, pipeline=self, current_step=i,
+                                  slg_layers=slg)
                 if c is None:
                     return None
                 pred = ops.cfg_combine(c.contiguous(), u.contiguous(), guide_scale,

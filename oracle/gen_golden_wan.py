@@ -102,6 +102,62 @@ def main():
                os.path.join(GOLD, "wan_t2v.pt"))
     print("written", os.path.join(GOLD, "wan_t2v.pt"))
     main_i2v()
+    main_skip()
+
+
+# The production coefficients (a polynomial fitted to trained checkpoints) are set by the caller; with random weights the time
+# embedding moves by ~100 % per step, so the fixture uses the identity polynomial and a threshold that skips about half the steps.
+TEACACHE_COEF = [1.0, 0.0]
+
+
+def main_skip():
+    """Step-skipping control flow of WanModel.forward (model.py:1029-1101): skip-layer guidance in a joint pass and TeaCache."""
+    from wan.modules.posemb_layers import get_rotary_pos_embed
+    from wan.utils.fm_solvers_unipc import FlowUniPCMultistepScheduler
+    cfg = TINY
+    sd = {k: v.double() for k, v in W.make_wan_state_dict(cfg, seed=0).items()}
+    ref = build_ref(cfg, sd)
+    g = torch.Generator().manual_seed(3)
+    lat = torch.randn(16, 3, 8, 12, generator=g).double()
+    ctx = torch.randn(20, 4096, generator=g).double()
+    ctx0 = torch.randn(11, 4096, generator=g).double()
+    cos_r, sin_r = get_rotary_pos_embed(lat.shape[1:], enable_RIFLEx=False)
+    cos, sin = W.rope_tables(lat.shape[1:])
+    t = torch.tensor([937])
+    # --- SLG: block 1 skipped for the unconditional sequence
+    y_ref = ref([lat.clone(), lat.clone()], t=t, context=[ctx, ctx0], freqs=(cos_r, sin_r), pipeline=_Pipe(), slg_layers=[1])
+    y = W.wan_forward(sd, cfg, [lat, lat], t, [ctx, ctx0], cos, sin, slg_layers=[1])
+    for a, b in zip(y, y_ref):
+        e = rel_l2(a, b)
+        print(f"  slg forward: rel_l2(oracle, reference) = {e:.3e}")
+        assert e < 2e-5
+    slg_fwd = [a.clone() for a in y_ref]
+    # --- TeaCache over an 8-step schedule
+    steps, thresh, start = 8, 2.5, 1
+    s = FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False)
+    s.set_timesteps(steps, device="cpu", shift=5.0)
+    ref.enable_teacache = True
+    ref.coefficients, ref.rel_l1_thresh, ref.teacache_start_step, ref.num_steps = TEACACHE_COEF, thresh, start, steps
+    ref.accumulated_rel_l1_distance, ref.teacache_skipped_steps, ref.previous_residual = 0, 0, [None, None]
+    tc = W.teacache_state(TEACACHE_COEF, thresh, start, steps)
+    latents, mine_lat = lat.clone(), lat.clone()
+    so = W.UniPC(); so.set_timesteps(steps, 5.0)
+    ref_steps = []
+    for i, tt in enumerate(s.timesteps):
+        c, u = ref([latents, latents], t=torch.stack([tt]), context=[ctx, ctx0], freqs=(cos_r, sin_r), pipeline=_Pipe(), current_step=i)
+        latents = s.step((u + 5.0 * (c - u)).unsqueeze(0), tt, latents.unsqueeze(0), return_dict=False)[0].squeeze(0)
+        ref_steps.append(latents.clone())
+        c2, u2 = W.wan_forward(sd, cfg, [mine_lat, mine_lat], torch.stack([tt]), [ctx, ctx0], cos, sin, teacache=tc, current_step=i)
+        mine_lat = so.step((u2 + 5.0 * (c2 - u2)).unsqueeze(0), mine_lat.unsqueeze(0)).squeeze(0)
+        e = rel_l2(mine_lat, latents)
+        print(f"  teacache step {i}: rel_l2 = {e:.3e}  skipped so far ref={ref.teacache_skipped_steps} oracle={tc['skipped']}")
+        assert e < 5e-5 and ref.teacache_skipped_steps == tc["skipped"]
+    assert 0 < tc["skipped"] < steps - 2, "pick a threshold that skips some but not all steps"
+    ref.enable_teacache = False
+    torch.save(dict(cfg=cfg, lat=lat.float(), ctx=ctx.float(), ctx0=ctx0.float(), t=t, slg_layers=[1], slg_fwd=slg_fwd,
+                    teacache=dict(coefficients=TEACACHE_COEF, rel_l1_thresh=thresh, start_step=start, steps=steps, skipped=tc["skipped"]),
+                    teacache_loop=[a.float() for a in ref_steps]), os.path.join(GOLD, "wan_skip.pt"))
+    print("written", os.path.join(GOLD, "wan_skip.pt"))
 
 
 def main_i2v():

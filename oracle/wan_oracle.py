@@ -168,8 +168,15 @@ def unpatchify(u: Tensor, grid: Sequence[int], cfg) -> Tensor:
     return u.reshape(c, *[i * j for i, j in zip(grid, cfg["patch_size"])])
 
 
+def teacache_state(coefficients, rel_l1_thresh: float, start_step: int, num_steps: int, n_seq: int = 2) -> dict:
+    """The attributes text2video.py:461-464 / the UI set on the model before a TeaCache run (model.py:1029-1049)."""
+    return dict(coefficients=list(coefficients), rel_l1_thresh=rel_l1_thresh, start_step=start_step, num_steps=num_steps,
+                accumulated=0.0, prev_e=None, previous_residual=[None] * n_seq, skipped=0)
+
+
 def wan_forward(sd: Dict[str, Tensor], cfg: dict, x_list: List[Tensor], t: Tensor, context: List[Tensor],
-                cos: Tensor, sin: Tensor, attn_fn=None, clip_fea: Optional[Tensor] = None, y: Optional[Tensor] = None) -> List[Tensor]:
+                cos: Tensor, sin: Tensor, attn_fn=None, clip_fea: Optional[Tensor] = None, y: Optional[Tensor] = None,
+                slg_layers: Optional[Sequence[int]] = None, teacache: Optional[dict] = None, current_step: int = 0) -> List[Tensor]:
     """WanModel.forward for t2v (model.py:902-1111): x_list of [16, F, H, W]; t [1]; context list of [L<=512, 4096];
     returns list of float32 [16, F, H, W].  Sequences are batched (the reference iterates them per block)."""
     D = cfg["dim"]
@@ -195,8 +202,31 @@ def wan_forward(sd: Dict[str, Tensor], cfg: dict, x_list: List[Tensor], t: Tenso
         c = _lin(sd, "img_emb.proj.3", F.gelu(_lin(sd, "img_emb.proj.1", c)))
         c = F.layer_norm(c, (D,), sd["img_emb.proj.4.weight"], sd["img_emb.proj.4.bias"])
         ctx = torch.cat([c.expand(ctx.shape[0], -1, -1), ctx], dim=1)
-    for i in range(L):
-        x = wan_block(sd, i, x, e0, cos, sin, ctx, cfg, attn_fn)
+    should_calc = True
+    if teacache is not None:                                                             # model.py:1029-1049 (joint pass, x_id = 0)
+        tc = teacache
+        if current_step <= tc["start_step"] or current_step == tc["num_steps"] - 1:
+            tc["accumulated"] = 0.0
+        else:
+            rel = float(((e - tc["prev_e"]).abs().mean() / tc["prev_e"].abs().mean()).item())
+            tc["accumulated"] += abs(float(np.poly1d(tc["coefficients"])(rel)))
+            if tc["accumulated"] < tc["rel_l1_thresh"]:
+                should_calc = False
+                tc["skipped"] += 1
+            else:
+                tc["accumulated"] = 0.0
+        tc["prev_e"] = e
+    if not should_calc:
+        x = x + torch.stack(teacache["previous_residual"], 0)                            # :1051-1054
+    else:
+        x_in = x
+        for i in range(L):
+            if slg_layers is not None and i in slg_layers and x.shape[0] > 1:            # :1077-1080 joint pass: cond sequence only
+                x = torch.cat([wan_block(sd, i, x[:1], e0, cos, sin, ctx[:1], cfg, attn_fn), x[1:]], dim=0)
+            else:
+                x = wan_block(sd, i, x, e0, cos, sin, ctx, cfg, attn_fn)
+        if teacache is not None:
+            teacache["previous_residual"] = list((x - x_in).unbind(0))                   # :1087-1101
     eh = (sd["head.modulation"] + e.unsqueeze(1)).chunk(2, dim=1)                         # model.py:566-572
     x = F.layer_norm(x, (D,), eps=cfg["eps"]) * (1 + eh[1]) + eh[0]
     x = _lin(sd, "head.head", x)

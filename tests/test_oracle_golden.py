@@ -115,3 +115,27 @@ def test_vae_encode_oracle_matches_reference(golden_dir):
         assert O.rel_l2(mean, c["mean"]) < 2e-3                         # input stored as fp16
         z = O.vae_encode(sd, c["x"].float(), noise=c["noise"])
         assert O.rel_l2(z, c["z"]) < 2e-3
+
+
+def test_wan_step_skipping_oracle_matches_reference(golden_dir):
+    """Skip-layer guidance (joint pass) and TeaCache control flow of WanModel.forward (model.py:1029-1101): oracle vs the fixture
+    recorded from the unmodified reference in fp64 (oracle/gen_golden_wan.py:main_skip)."""
+    from oracle import wan_oracle as W
+    g = _load(golden_dir, "wan_skip.pt")
+    cfg = g["cfg"]
+    sd = W.make_wan_state_dict(cfg, seed=0)
+    cos, sin = W.rope_tables(g["lat"].shape[1:])
+    y = W.wan_forward(sd, cfg, [g["lat"], g["lat"]], g["t"], [g["ctx"], g["ctx0"]], cos, sin, slg_layers=g["slg_layers"])
+    for a, b in zip(y, g["slg_fwd"]):
+        assert W.rel_l2(a, b.float()) < 5e-5
+    plain = W.wan_forward(sd, cfg, [g["lat"], g["lat"]], g["t"], [g["ctx"], g["ctx0"]], cos, sin)
+    assert W.rel_l2(y[0], plain[0]) < 1e-6 and W.rel_l2(y[1], plain[1]) > 1e-3      # only the unconditional sequence skips
+    tcg = g["teacache"]
+    tc = W.teacache_state(tcg["coefficients"], tcg["rel_l1_thresh"], tcg["start_step"], tcg["steps"])
+    so = W.UniPC(); so.set_timesteps(tcg["steps"], 5.0)
+    lat = g["lat"].clone()
+    for i, tt in enumerate(so.timesteps):
+        c, u = W.wan_forward(sd, cfg, [lat, lat], torch.stack([tt]), [g["ctx"], g["ctx0"]], cos, sin, teacache=tc, current_step=i)
+        lat = so.step((u + 5.0 * (c - u)).unsqueeze(0), lat.unsqueeze(0)).squeeze(0)
+        assert W.rel_l2(lat, g["teacache_loop"][i]) < 2e-4
+    assert tc["skipped"] == tcg["skipped"] and 0 < tc["skipped"] < tcg["steps"] - 2

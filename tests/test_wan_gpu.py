@@ -194,3 +194,66 @@ def test_attention_accumulate_and_exact_gelu():
     lw, lb = (1 + 0.1 * torch.randn(1280, generator=gq)).bfloat16().to(DEV), (0.1 * torch.randn(1280, generator=gq)).bfloat16().to(DEV)
     ln = ops.norm_mod(c, weight=lw, bias=lb, eps=1e-5, layer_norm=True)
     assert W.rel_l2(ln.float().cpu(), torch.nn.functional.layer_norm(c.float().cpu(), (1280,), lw.float().cpu(), lb.float().cpu(), 1e-5)) < 6e-3
+
+
+def test_axpby_and_rel_l1_kernels():
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(3, 4096, generator=g).bfloat16().to(DEV)
+    y = torch.randn(3, 4096, generator=g).bfloat16().to(DEV)
+    assert torch.equal(ops.axpby(x, y), x + y)                                  # one rounding, like ATen
+    assert torch.equal(ops.axpby(x, y, 1.0, -1.0), x - y)
+    z = x.clone(); ops.axpby(z, y, out=z)
+    assert torch.equal(z, x + y)
+    a, b = x[:1].contiguous(), y[:1].contiguous()
+    ref = ((a - b).abs().mean() / b.abs().mean()).cpu().item()                  # model.py:1039 in bf16
+    got = ops.rel_l1(a, b)
+    assert abs(got - ref) <= 2 ** -7 * abs(ref)                                 # at most one bf16 ulp (summation order)
+
+
+def test_wan_skip_layer_guidance_vs_reference_fixture(golden_dir):
+    g = torch.load(os.path.join(golden_dir, "wan_skip.pt"), weights_only=False)
+    m, sd = _model(g["cfg"])
+    cos, sin = get_rotary_pos_embed(g["lat"].shape[1:])
+    lat, ctx, ctx0 = g["lat"].to(DEV), g["ctx"].to(DEV), g["ctx0"].to(DEV)
+    y = m([lat, lat], t=g["t"].to(DEV), context=[ctx, ctx0], freqs=(cos, sin), slg_layers=g["slg_layers"])
+    for a, b in zip(y, g["slg_fwd"]):
+        e = W.rel_l2(a.cpu(), b.float())
+        print(f"wan SLG joint forward rel_l2 vs reference = {e:.3e}")
+        assert e < 3e-2
+    # separate passes (model.py:1078-1079): x_id 0 keeps the block, x_id 1 drops it
+    c = m([lat], t=g["t"].to(DEV), context=[ctx], freqs=(cos, sin), slg_layers=g["slg_layers"], x_id=0)[0]
+    u = m([lat], t=g["t"].to(DEV), context=[ctx0], freqs=(cos, sin), slg_layers=g["slg_layers"], x_id=1)[0]
+    assert W.rel_l2(c.cpu(), g["slg_fwd"][0].float()) < 3e-2 and W.rel_l2(u.cpu(), g["slg_fwd"][1].float()) < 3e-2
+    plain = m([lat, lat], t=g["t"].to(DEV), context=[ctx, ctx0], freqs=(cos, sin))
+    assert W.rel_l2(y[1].cpu(), plain[1].cpu()) > 1e-2                          # the skipped block matters
+
+
+def test_wan_teacache_loop_vs_reference_fixture(golden_dir):
+    g = torch.load(os.path.join(golden_dir, "wan_skip.pt"), weights_only=False)
+    tcg = g["teacache"]
+    for joint in (True, False):
+        m, sd = _model(g["cfg"])
+        m.enable_teacache = True
+        m.coefficients, m.rel_l1_thresh, m.teacache_start_step, m.num_steps = tcg["coefficients"], tcg["rel_l1_thresh"], tcg["start_step"], tcg["steps"]
+        m.accumulated_rel_l1_distance, m.teacache_skipped_steps, m.previous_residual = 0, 0, [None, None]
+        cos, sin = get_rotary_pos_embed(g["lat"].shape[1:])
+        s = FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False)
+        s.set_timesteps(tcg["steps"], device=DEV, shift=5.0)
+        lat, ctx, ctx0 = g["lat"].to(DEV), g["ctx"].to(DEV), g["ctx0"].to(DEV)
+        for i, t in enumerate(s.timesteps_host):
+            ts = torch.tensor([t], device=DEV)
+            if joint:
+                c, u = m([lat, lat], t=ts, context=[ctx, ctx0], freqs=(cos, sin), current_step=i)
+            else:
+                c = m([lat], t=ts, context=[ctx], freqs=(cos, sin), current_step=i, x_id=0)[0]
+                u = m([lat], t=ts, context=[ctx0], freqs=(cos, sin), current_step=i, x_id=1)[0]
+            pred = ops.cfg_combine(c.contiguous(), u.contiguous(), 5.0, use_alpha=False)
+            lat = s.step(pred.unsqueeze(0), t, lat.unsqueeze(0), return_dict=False)[0].squeeze(0)
+            e = W.rel_l2(lat.cpu(), g["teacache_loop"][i])
+            print(f"wan teacache (joint={joint}) step {i}: rel_l2 = {e:.3e} skipped={m.teacache_skipped_steps}")
+            assert e < 2e-2
+        assert m.teacache_skipped_steps == tcg["skipped"]                       # same steps skipped as the reference
+    # threshold search (model.py:854-899) on the live schedule: reproduces the oracle's scan of the same distances
+    m.teacache_multiplier = 2.0
+    th = m.compute_teacache_threshold(m.teacache_start_step, s.timesteps_host, 2.0)
+    assert 0.01 <= th <= 0.61
