@@ -115,6 +115,23 @@ int ltxb200_axpby_bf16(const void* x, const void* y, void* out, int64_t n, float
  * out2[0] = sum |bf16(a - b)|, out2[1] = sum |b| (fp32, device).  a, b: bf16 [n]. */
 int ltxb200_rel_l1_bf16(const void* a, const void* b, int64_t n, float* out2, void* stream);
 
+/* ---- LTX multi-scale flow (pipeline_ltx_video.py:1709-1903, latent_upsampler.py) ---- */
+#define LTXB200_GROUPNORM_CHUNKS 64
+/* y = [SiLU]( GroupNorm(32 groups, eps)(x) * gamma + beta [+ residual] ) on NDHWC bf16 x [B, voxels, C], C in {256,...,2048}
+ * (latent_upsampler.py:30-39,73-75: conv -> norm -> SiLU, and SiLU(norm2(..) + residual)).  scratch: B*64*32*2 floats. */
+int ltxb200_groupnorm_silu_bf16(const void* x, void* y, int B, int64_t voxels, int C, const void* gamma, const void* beta,
+                                const void* residual, float eps, int apply_silu, float* scratch, void* stream);
+
+/* adain_filter_latent (pipeline_ltx_video.py:1709-1737): rows = batch*channels; x [rows, n], ref [rows, m], out [rows, n] fp32. */
+int ltxb200_adain_f32(const float* x, const float* ref, float* out, int rows, int64_t n, int64_t m, float factor, void* stream);
+
+/* NDHWC bf16 -> NCDHW fp32, (x - mean[c]) / std[c] when std/mean are given (normalize_latents, vae_encode.py:228-237). */
+int ltxb200_latent_from_ndhwc(const void* x, float* out, int B, int C, int64_t FHW, const float* stdv, const float* meanv,
+                              void* stream);
+
+/* F.interpolate(mode="bilinear", align_corners=False) per plane (pipeline_ltx_video.py:1894-1899): [planes,h,w] -> [planes,H,W]. */
+int ltxb200_bilinear_resize_f32(const float* x, float* y, int64_t planes, int h, int w, int H, int W, void* stream);
+
 /* diffusers Timesteps(256, flip_sin_to_cos=True, downscale_freq_shift=0): out[n, dim] bf16 from t[n] fp32 */
 int ltxb200_timestep_embed(const float* t, void* out, int n, int dim, void* stream);
 
@@ -153,8 +170,10 @@ int ltxb200_conv3d_strided_bf16(const void* x, const void* w, const void* bias, 
 
 /* ---- Wan2.1 VAE decode (wan/modules/vae.py:386-493): the pieces the LTX decoder kernels do not already cover ---- */
 /* convolution with taps_t x taps_hw x taps_hw taps (each 1 or 3) on NDHWC bf16, w = [Cout, taps*Cin] tap-major, causal in time
- * (taps t-2,t-1,t) with ZERO temporal padding when causal_zero_pad != 0 (Wan CausalConv3d, vae.py:17-37; Conv2d 3x3 of
- * Resample with taps_t = 1, :80-88; time_conv with taps_hw = 1, :86-88) or replicate padding otherwise; optional residual. */
+ * (taps t-2,t-1,t) with ZERO temporal padding when causal_zero_pad == 1 (Wan CausalConv3d, vae.py:17-37; Conv2d 3x3 of
+ * Resample with taps_t = 1, :80-88; time_conv with taps_hw = 1, :86-88), replicate padding when 0; causal_zero_pad == 2 is
+ * the centred, zero-padded nn.Conv3d / nn.Conv2d(kernel 3, padding 1) of the LatentUpsampler (latent_upsampler.py:25-27,
+ * 73,90-93,107); optional residual. */
 int ltxb200_conv_taps_bf16(const void* x, const void* w, const void* bias, void* out, int B, int T, int H, int W, int Cin,
                            int Cout, int taps_t, int taps_hw, int causal_zero_pad, const void* residual, void* stream);
 /* RMS_norm (vae.py:41-58: F.normalize over channels * sqrt(c_real) * gamma) + optional SiLU on [voxels, C] bf16 */

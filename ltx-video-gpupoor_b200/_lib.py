@@ -37,6 +37,10 @@ def _declare(lib):
         "ltxb200_stg_blend_bf16": ([P, P, L, P, I, L, I, P], I),
         "ltxb200_axpby_bf16": ([P, P, P, L, F, F, P], I),
         "ltxb200_rel_l1_bf16": ([P, P, L, P, P], I),
+        "ltxb200_groupnorm_silu_bf16": ([P, P, I, L, I, P, P, P, F, I, P, P], I),
+        "ltxb200_adain_f32": ([P, P, P, I, L, L, F, P], I),
+        "ltxb200_latent_from_ndhwc": ([P, P, I, I, L, P, P, P], I),
+        "ltxb200_bilinear_resize_f32": ([P, P, L, I, I, I, I, P], I),
         "ltxb200_timestep_embed": ([P, P, I, I, P], I),
         "ltxb200_cast_f32_to_bf16": ([P, P, L, P], I),
         "ltxb200_guidance_step": ([P, L, L, I, I, I, I, F, F, F, P, P, P, I, F, P, P, P], I),

@@ -823,4 +823,138 @@ __global__ void rel_l1_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bf
   if (threadIdx.x == 0) { out[0] = d; out[1] = m; }
 }
 
+// ------------------------------------------------------------------------------------------
+// LTX multi-scale flow: GroupNorm(32)+SiLU of the LatentUpsampler (latent_upsampler.py:15-39,73-75), AdaIN latent
+// filter (pipeline_ltx_video.py:1709-1737), latent re-normalisation, bilinear frame resize (:1890-1901).  The tensors are a few
+// MB (latent resolution), L2-resident: these kernels are latency-bound, two launches per GroupNorm, deterministic partial sums.
+// ------------------------------------------------------------------------------------------
+constexpr int kGnGroups = 32;
+
+// x [B, voxels, C] bf16 (NDHWC), C % 256 == 0.  grid (chunks, B), 256 threads; partial [B, chunks, 32, 2] = (sum, sum of squares)
+__global__ void groupnorm_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ partial, long long voxels, int C) {
+  __shared__ float sh[2][256];
+  const int tpv = C / 8, vpb = 256 / tpv;
+  const int slot = threadIdx.x % tpv, vrow = threadIdx.x / tpv;
+  const long long per = (voxels + gridDim.x - 1) / gridDim.x;
+  const long long v0 = blockIdx.x * per, v1 = (v0 + per < voxels) ? v0 + per : voxels;
+  const __nv_bfloat16* xb = x + static_cast<long long>(blockIdx.y) * voxels * C;
+  float s = 0.f, q = 0.f;
+  for (long long v = v0 + vrow; v < v1; v += vpb) {
+    float f[8];
+    load8(xb + v * C + slot * 8, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s += f[j]; q = fmaf(f[j], f[j], q); }
+  }
+  sh[0][threadIdx.x] = s; sh[1][threadIdx.x] = q;
+  __syncthreads();
+  if (threadIdx.x < kGnGroups) {
+    const int tpg = tpv / kGnGroups;
+    float a = 0.f, b = 0.f;
+    for (int r = 0; r < vpb; ++r)
+      for (int k = 0; k < tpg; ++k) { const int i = r * tpv + threadIdx.x * tpg + k; a += sh[0][i]; b += sh[1][i]; }
+    float* o = partial + ((static_cast<long long>(blockIdx.y) * gridDim.x + blockIdx.x) * kGnGroups + threadIdx.x) * 2;
+    o[0] = a; o[1] = b;
+  }
+}
+
+// y = [silu]( bf16(groupnorm(x) * gamma + beta) [+ residual] ) with ATen's rounding points (norm output, sum, activation each bf16)
+__global__ void groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                       const float* __restrict__ partial, int chunks, long long voxels, int C,
+                                       const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
+                                       const __nv_bfloat16* __restrict__ residual, float eps, int apply_silu) {
+  __shared__ float mean[kGnGroups], rstd[kGnGroups];
+  if (threadIdx.x < kGnGroups) {
+    float a = 0.f, b = 0.f;
+    const float* pp = partial + (static_cast<long long>(blockIdx.y) * chunks * kGnGroups + threadIdx.x) * 2;
+    for (int c = 0; c < chunks; ++c) { a += pp[c * kGnGroups * 2]; b += pp[c * kGnGroups * 2 + 1]; }
+    const float n = static_cast<float>(voxels) * (C / kGnGroups);
+    const float m = a / n;
+    mean[threadIdx.x] = m;
+    rstd[threadIdx.x] = rsqrtf(fmaxf(b / n - m * m, 0.f) + eps);
+  }
+  __syncthreads();
+  const int tpv = C / 8, vpb = 256 / tpv;
+  const int slot = threadIdx.x % tpv, vrow = threadIdx.x / tpv;
+  const int g = slot / (tpv / kGnGroups);
+  const float m = mean[g], r = rstd[g];
+  float ga[8], be[8];
+  load8(gamma + slot * 8, ga);
+  load8(beta + slot * 8, be);
+  const long long base = static_cast<long long>(blockIdx.y) * voxels * C;
+  for (long long v = static_cast<long long>(blockIdx.x) * vpb + vrow; v < voxels; v += static_cast<long long>(gridDim.x) * vpb) {
+    const long long e = base + v * C + slot * 8;
+    float f[8];
+    load8(x + e, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = bf16r(fmaf((f[j] - m) * r, ga[j], be[j]));
+    if (residual) {
+      float h[8];
+      load8(residual + e, h);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = bf16r(f[j] + h[j]);
+    }
+    if (apply_silu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = __fdividef(f[j], 1.0f + __expf(-f[j]));
+    }
+    store8(y + e, f);
+  }
+}
+
+// AdaIN: one block per (batch, channel) row.  x [rows, n], ref [rows, m] fp32; out = lerp(x, (x - mean_x)/std_x * std_ref + mean_ref, factor)
+// with torch.std_mean's unbiased std (two passes over the L2-resident row).
+__global__ void adain_kernel(const float* __restrict__ x, const float* __restrict__ ref, float* __restrict__ out, long long n,
+                             long long m, float factor) {
+  __shared__ float sm[8];
+  const float* xr = x + blockIdx.x * n;
+  const float* rr = ref + blockIdx.x * m;
+  float a = 0.f, b = 0.f;
+  for (long long i = threadIdx.x; i < n; i += 256) a += xr[i];
+  for (long long i = threadIdx.x; i < m; i += 256) b += rr[i];
+  const float mx = block_sum_256(a, sm) / n, mr = block_sum_256(b, sm) / m;
+  a = 0.f; b = 0.f;
+  for (long long i = threadIdx.x; i < n; i += 256) { const float d = xr[i] - mx; a = fmaf(d, d, a); }
+  for (long long i = threadIdx.x; i < m; i += 256) { const float d = rr[i] - mr; b = fmaf(d, d, b); }
+  const float sx = sqrtf(block_sum_256(a, sm) / (n - 1)), sr = sqrtf(block_sum_256(b, sm) / (m - 1));
+  float* o = out + blockIdx.x * n;
+  for (long long i = threadIdx.x; i < n; i += 256) {
+    const float v = xr[i], t = (v - mx) / sx * sr + mr;
+    o[i] = factor < 0.5f ? v + factor * (t - v) : t - (t - v) * (1.0f - factor);        // torch.lerp
+  }
+}
+
+// NDHWC bf16 -> NCDHW fp32 with the inverse of latent_to_ndhwc's affine: (x - mean[c]) / std[c]  (normalize_latents, vae_encode.py:228-237)
+__global__ void latent_from_ndhwc_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int B, int C, long long FHW,
+                                         const float* __restrict__ stdv, const float* __restrict__ meanv) {
+  const long long n = static_cast<long long>(B) * C * FHW;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long s = i % FHW;
+    const int c = static_cast<int>((i / FHW) % C);
+    const long long b = i / FHW / C;
+    float v = __bfloat162float(x[(b * FHW + s) * C + c]);
+    if (stdv) v = (v - meanv[c]) / stdv[c];
+    out[i] = v;
+  }
+}
+
+// F.interpolate(mode="bilinear", align_corners=False) on [planes, h, w] -> [planes, H, W] fp32
+__global__ void bilinear_resize_kernel(const float* __restrict__ x, float* __restrict__ y, long long planes, int h, int w, int H, int W) {
+  const float sh = static_cast<float>(h) / H, sw = static_cast<float>(w) / W;
+  const long long n = planes * H * W;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ox = static_cast<int>(i % W), oy = static_cast<int>((i / W) % H);
+    const long long p = i / W / H;
+    const float fy = fmaxf((oy + 0.5f) * sh - 0.5f, 0.f), fx = fmaxf((ox + 0.5f) * sw - 0.5f, 0.f);
+    const int y0 = min(static_cast<int>(fy), h - 1), x0 = min(static_cast<int>(fx), w - 1);
+    const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+    const float ly = fy - y0, lx = fx - x0;
+    const float* xp = x + p * h * w;
+    const float top = xp[y0 * w + x0] * (1.f - lx) + xp[y0 * w + x1] * lx;
+    const float bot = xp[y1 * w + x0] * (1.f - lx) + xp[y1 * w + x1] * lx;
+    y[i] = top * (1.f - ly) + bot * ly;
+  }
+}
+
 }  // namespace b200

@@ -191,8 +191,9 @@ extern "C" int ltxb200_conv3d_strided_bf16(const void* x, const void* w, const v
 extern "C" int ltxb200_conv_taps_bf16(const void* x, const void* w, const void* bias, void* out, int B, int T, int H, int W,
                                       int Cin, int Cout, int taps_t, int taps_hw, int causal_zero_pad, const void* residual,
                                       void* stream) {
-  return conv_impl(x, w, bias, out, B, T, H, W, Cin, Cout, taps_t, taps_hw, 1, causal_zero_pad, LTXB200_CONV_STORE_NDHWC, 0,
-                   residual, stream);
+  // causal_zero_pad: 0 = causal taps (t-2,t-1,t), replicate padding; 1 = causal, zero padding; 2 = centred taps (t-1,t,t+1), zero padding
+  return conv_impl(x, w, bias, out, B, T, H, W, Cin, Cout, taps_t, taps_hw, causal_zero_pad == 2 ? 0 : 1, causal_zero_pad != 0,
+                   LTXB200_CONV_STORE_NDHWC, 0, residual, stream);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -508,6 +509,50 @@ extern "C" int ltxb200_rel_l1_bf16(const void* a, const void* b, int64_t n, floa
   if (!a || !b || !out2) return kErrBadAlign;
   rel_l1_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(a),
                                                                  static_cast<const __nv_bfloat16*>(b), n, out2);
+  return launch_status();
+}
+
+extern "C" int ltxb200_groupnorm_silu_bf16(const void* x, void* y, int B, int64_t voxels, int C, const void* gamma, const void* beta,
+                                           const void* residual, float eps, int apply_silu, float* scratch, void* stream) {
+  if (B <= 0 || voxels <= 0 || C <= 0 || (C % 256) || C > 2048) return kErrBadShape;
+  if (!aligned16(x) || !aligned16(y) || !aligned16(gamma) || !aligned16(beta) || (residual && !aligned16(residual)) || !scratch)
+    return kErrBadAlign;
+  const int vpb = 256 / (C / 8);
+  long long want = (voxels + vpb - 1) / vpb;
+  const int chunks = static_cast<int>(want < LTXB200_GROUPNORM_CHUNKS ? want : LTXB200_GROUPNORM_CHUNKS);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  groupnorm_stats_kernel<<<dim3(chunks, B), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), scratch, voxels, C);
+  const long long cap = num_sms() * 8ll / B;
+  const int blocks = static_cast<int>(want < 1 ? 1 : (want > cap ? (cap < 1 ? 1 : cap) : want));
+  groupnorm_apply_kernel<<<dim3(blocks, B), 256, 0, st>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), scratch, chunks, voxels, C,
+      static_cast<const __nv_bfloat16*>(gamma), static_cast<const __nv_bfloat16*>(beta),
+      static_cast<const __nv_bfloat16*>(residual), eps, apply_silu);
+  return launch_status();
+}
+
+extern "C" int ltxb200_adain_f32(const float* x, const float* ref, float* out, int rows, int64_t n, int64_t m, float factor,
+                                 void* stream) {
+  if (rows <= 0 || n < 2 || m < 2) return kErrBadShape;
+  if (!x || !ref || !out) return kErrBadAlign;
+  adain_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, ref, out, n, m, factor);
+  return launch_status();
+}
+
+extern "C" int ltxb200_latent_from_ndhwc(const void* x, float* out, int B, int C, int64_t FHW, const float* stdv, const float* meanv,
+                                         void* stream) {
+  if (B <= 0 || C <= 0 || FHW <= 0) return kErrBadShape;
+  if (!x || !out || ((stdv == nullptr) != (meanv == nullptr))) return kErrBadAlign;
+  const long long n = static_cast<long long>(B) * C * FHW;
+  latent_from_ndhwc_kernel<<<ew_blocks(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), out, B, C, FHW, stdv, meanv);
+  return launch_status();
+}
+
+extern "C" int ltxb200_bilinear_resize_f32(const float* x, float* y, int64_t planes, int h, int w, int H, int W, void* stream) {
+  if (planes <= 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0) return kErrBadShape;
+  if (!x || !y) return kErrBadAlign;
+  bilinear_resize_kernel<<<ew_blocks(planes * H * W, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, planes, h, w, H, W);
   return launch_status();
 }
 

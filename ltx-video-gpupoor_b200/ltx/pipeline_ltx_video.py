@@ -301,3 +301,69 @@ class LTXVideoPipeline:
         if not return_dict:
             return (image,)
         return image
+
+
+class LTXMultiScalePipeline:
+    """pipeline_ltx_video.py:1741-1903: first pass at `downscale_factor` resolution -> LatentUpsampler (x2) -> AdaIN against the
+    first-pass latents -> second pass from the partially re-noised upsampled latents -> decode -> bilinear resize to the requested size.
+    Text encoding is out of scope here as everywhere: pass prompt_embeds / prompt_attention_mask (and the negative pair) in kwargs."""
+
+    def __init__(self, video_pipeline: LTXVideoPipeline, latent_upsampler):
+        self.video_pipeline = video_pipeline
+        self.vae = video_pipeline.vae
+        self.latent_upsampler = latent_upsampler
+
+    def _upsample_latents(self, latest_upsampler, latents: torch.Tensor) -> torch.Tensor:
+        """:1761-1772 un_normalize_latents -> upsampler -> normalize_latents, both affine maps fused into the layout kernels."""
+        std, mean = self.vae.std_of_means.float().contiguous(), self.vae.mean_of_means.float().contiguous()
+        z = latents.to(latest_upsampler.device)
+        z = (z if z.dtype in (torch.float32, BF16) else z.float()).contiguous()
+        return ops.latent_from_ndhwc(latest_upsampler.forward_ndhwc(ops.latent_to_ndhwc(z, std, mean)), std, mean)
+
+    def __call__(self, downscale_factor: float, first_pass: dict, second_pass: dict, *args, **kwargs):
+        from .latent_upsampler import adain_filter_latent
+        video_pipeline = self.video_pipeline
+        original_output_type = kwargs["output_type"]
+        original_width, original_height = kwargs["width"], kwargs["height"]
+        x_width = int(kwargs["width"] * downscale_factor)
+        downscaled_width = x_width - (x_width % video_pipeline.vae_scale_factor)
+        x_height = int(kwargs["height"] * downscale_factor)
+        downscaled_height = x_height - (x_height % video_pipeline.vae_scale_factor)
+        kwargs["output_type"] = "latent"
+        kwargs["width"], kwargs["height"] = downscaled_width, downscaled_height
+        z_tile, hw_tile = kwargs.pop("VAE_tile_size", (0, 0)) or (0, 0)
+        if z_tile > 0 or hw_tile > 0:
+            raise NotImplementedError("VAE tiling is a low-memory workaround (vae.py:365-408) that is not needed on 180 GB")
+        ltxv_model = kwargs.get("ltxv_model")
+        for k in ("prompt", "negative_prompt", "device", "enhance_prompt"):
+            kwargs.pop(k, None)                         # consumed by encode_prompt / the prompt enhancer in the reference (:1824-1850)
+        if kwargs.get("prompt_embeds") is None:
+            raise NotImplementedError("text encoding is out of scope: pass prompt_embeds / prompt_attention_mask")
+        if ltxv_model is not None and getattr(ltxv_model, "_interrupt", False):
+            return None
+        steps1, steps2 = kwargs.pop("num_inference_steps1"), kwargs.pop("num_inference_steps2")
+        kwargs["return_dict"] = True
+        original_kwargs = kwargs.copy()
+
+        kwargs["joint_pass"], kwargs["pass_no"] = True, 1
+        kwargs.update(**first_pass)
+        kwargs["num_inference_steps"] = steps1
+        latents = video_pipeline(*args, **kwargs)
+        if latents is None:
+            return None
+        upsampled_latents = self._upsample_latents(self.latent_upsampler, latents)
+        upsampled_latents = adain_filter_latent(latents=upsampled_latents, reference_latents=latents)
+
+        kwargs = original_kwargs
+        kwargs["latents"] = upsampled_latents
+        kwargs["output_type"] = original_output_type
+        kwargs["width"], kwargs["height"] = downscaled_width * 2, downscaled_height * 2
+        kwargs["joint_pass"], kwargs["pass_no"] = False, 2
+        kwargs.update(**second_pass)
+        kwargs["num_inference_steps"] = steps2
+        result = video_pipeline(*args, **kwargs)
+        if result is None:
+            return None
+        if original_output_type != "latent" and tuple(result.shape[-2:]) != (original_height, original_width):
+            result = ops.bilinear_resize(result.float().contiguous(), original_height, original_width)     # :1890-1901
+        return result

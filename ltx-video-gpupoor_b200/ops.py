@@ -321,8 +321,9 @@ def cfg_combine(cond: torch.Tensor, uncond: torch.Tensor, guide_scale: float, us
 # Wan VAE decode pieces
 # ------------------------------------------------------------------------------------------------------------------
 def conv_taps(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], taps_t: int, taps_hw: int,
-              zero_pad_t: bool = True, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """x [B,T,H,W,Cin] bf16 NDHWC; w [Cout, taps_t*taps_hw^2*Cin] bf16 (tap-major K); causal in time."""
+              zero_pad_t: bool = True, residual: Optional[torch.Tensor] = None, centered: bool = False) -> torch.Tensor:
+    """x [B,T,H,W,Cin] bf16 NDHWC; w [Cout, taps_t*taps_hw^2*Cin] bf16 (tap-major K); causal in time, or `centered`
+    (taps t-1,t,t+1, zero padding: nn.Conv3d(kernel 3, padding 1))."""
     _req(x, name="x"); _req(w, name="w")
     assert x.is_contiguous() and w.is_contiguous() and x.dim() == 5
     B, T, H, W, Cin = x.shape
@@ -333,7 +334,8 @@ def conv_taps(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], ta
         _req(residual, name="residual"); assert residual.is_contiguous() and residual.shape == out.shape
     with _Prof('conv_taps_bf16', 'flop', 2.0 * B * T * H * W * Cout * w.shape[1]):
         rc = _lib.lib().ltxb200_conv_taps_bf16(x.data_ptr(), w.data_ptr(), _p(bias), out.data_ptr(), B, T, H, W, Cin, Cout,
-                                               taps_t, taps_hw, 1 if zero_pad_t else 0, _p(residual), _stream())
+                                               taps_t, taps_hw, 2 if centered else (1 if zero_pad_t else 0), _p(residual),
+                                               _stream())
     _lib.check(rc, "conv_taps_bf16")
     return out
 
@@ -385,4 +387,56 @@ def conv3d_strided(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor
         rc = _lib.lib().ltxb200_conv3d_strided_bf16(x.data_ptr(), w.data_ptr(), _p(bias), out.data_ptr(), B, T, H, W, Cin, Cout,
                                                     stride_t, stride_hw, _stream())
     _lib.check(rc, "conv3d_strided_bf16")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# LTX multi-scale flow pieces (latent upsampler, AdaIN, resize)
+# ------------------------------------------------------------------------------------------------------------------
+def groupnorm_silu(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, residual: Optional[torch.Tensor] = None,
+                   silu: bool = True, eps: float = 1e-5) -> torch.Tensor:
+    """x [B, ..., C] bf16 NDHWC -> [SiLU](GroupNorm(32)(x) [+ residual])."""
+    _req(x, name="x"); _req(gamma, name="gamma"); _req(beta, name="beta")
+    assert x.is_contiguous()
+    B, C = x.shape[0], x.shape[-1]
+    voxels = x.numel() // (B * C)
+    y = torch.empty_like(x)
+    if residual is not None:
+        _req(residual, name="residual"); assert residual.is_contiguous() and residual.shape == x.shape
+    scratch = torch.empty(B * 64 * 32 * 2, device=x.device, dtype=torch.float32)
+    with _Prof('groupnorm_silu_bf16', 'byte', (6.0 if residual is None else 8.0) * x.numel()):
+        rc = _lib.lib().ltxb200_groupnorm_silu_bf16(x.data_ptr(), y.data_ptr(), B, voxels, C, gamma.data_ptr(), beta.data_ptr(),
+                                                    _p(residual), float(eps), 1 if silu else 0, scratch.data_ptr(), _stream())
+    _lib.check(rc, "groupnorm_silu_bf16")
+    return y
+
+
+def adain(x: torch.Tensor, ref: torch.Tensor, factor: float = 1.0) -> torch.Tensor:
+    """x [B, C, ...], ref [B, C, ...] fp32 -> per (b, c) mean / unbiased-std matching + lerp."""
+    _req(x, torch.float32, "x"); _req(ref, torch.float32, "ref")
+    assert x.is_contiguous() and ref.is_contiguous() and x.shape[:2] == ref.shape[:2]
+    rows = x.shape[0] * x.shape[1]
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().ltxb200_adain_f32(x.data_ptr(), ref.data_ptr(), out.data_ptr(), rows, x.numel() // rows,
+                                            ref.numel() // rows, float(factor), _stream()), "adain_f32")
+    return out
+
+
+def latent_from_ndhwc(x: torch.Tensor, stdv: Optional[torch.Tensor], meanv: Optional[torch.Tensor]) -> torch.Tensor:
+    """x [B, F, H, W, C] bf16 -> [B, C, F, H, W] fp32, (x - mean) / std per channel."""
+    _req(x, name="x"); assert x.is_contiguous() and x.dim() == 5
+    B, Fr, H, W, C = x.shape
+    out = torch.empty(B, C, Fr, H, W, device=x.device, dtype=torch.float32)
+    _lib.check(_lib.lib().ltxb200_latent_from_ndhwc(x.data_ptr(), out.data_ptr(), B, C, Fr * H * W, _p(stdv), _p(meanv), _stream()),
+               "latent_from_ndhwc")
+    return out
+
+
+def bilinear_resize(x: torch.Tensor, height: int, width: int) -> torch.Tensor:
+    """x [..., h, w] fp32 -> [..., height, width] (F.interpolate bilinear, align_corners=False)."""
+    _req(x, torch.float32, "x"); assert x.is_contiguous()
+    h, w = x.shape[-2:]
+    out = torch.empty(*x.shape[:-2], height, width, device=x.device, dtype=torch.float32)
+    _lib.check(_lib.lib().ltxb200_bilinear_resize_f32(x.data_ptr(), out.data_ptr(), x.numel() // (h * w), h, w, height, width,
+                                                      _stream()), "bilinear_resize_f32")
     return out

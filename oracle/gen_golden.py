@@ -297,8 +297,103 @@ def case_pipeline():
     torch.save(out, os.path.join(GOLD, "ltx_pipeline.pt"))
 
 
+def build_ref_upsampler(sd, in_channels, mid_channels, nb):
+    from ltx_video.models.autoencoders.latent_upsampler import LatentUpsampler
+    m = LatentUpsampler(in_channels=in_channels, mid_channels=mid_channels, num_blocks_per_stage=nb, dims=3,
+                        spatial_upsample=True, temporal_upsample=False)
+    m.load_state_dict(sd, strict=True)
+    return m.eval()
+
+
+def case_multiscale():
+    """LatentUpsampler.forward, adain_filter_latent and the whole LTXMultiScalePipeline.__call__ (first pass at
+    2/3 resolution -> upsample -> AdaIN -> second pass from the partially re-noised latents -> decode -> bilinear resize), with
+    per-guidance-timestep guidance tables like ltxv-13b-0.9.7-dev.yaml."""
+    from ltx_video.pipelines.pipeline_ltx_video import LTXVideoPipeline, LTXMultiScalePipeline, adain_filter_latent
+    from ltx_video.schedulers.rf import RectifiedFlowScheduler
+    from ltx_video.models.transformers.symmetric_patchifier import SymmetricPatchifier
+    from ltx_video.utils.diffusers_config_mapping import OURS_SCHEDULER_CONFIG
+    from ltx_video.utils.skip_layer_strategy import SkipLayerStrategy
+    MID, NB = 256, 1
+    usd = O.make_latent_upsampler_state_dict(128, MID, NB, seed=3)
+    up = build_ref_upsampler(usd, 128, MID, NB)
+    g = torch.Generator().manual_seed(11)
+    z = torch.randn(1, 128, 3, 4, 6, generator=g)
+    y_ref = up(z)
+    _check("latent upsampler", O.latent_upsampler_forward(usd, z), y_ref, tol=2e-5)
+    ref_lat = torch.randn(1, 128, 3, 2, 3, generator=g) * 1.7 + 0.3
+    a_ref = adain_filter_latent(y_ref, ref_lat)
+    _check("adain_filter_latent", O.adain_filter_latent(y_ref, ref_lat), a_ref, tol=2e-6)
+    _check("adain_filter_latent(0.25)", O.adain_filter_latent(y_ref, ref_lat, 0.25), adain_filter_latent(y_ref, ref_lat, 0.25), tol=2e-6)
+    out = dict(upsampler=dict(mid=MID, nb=NB, seed=3, z=z, out=y_ref, ref_lat=ref_lat, adain=a_ref))
+
+    cfg = O.LTX_2B
+    L = 2
+    sd = O.make_transformer_state_dict(cfg, seed=0, num_layers=L)
+    tr = build_ref_transformer(L, sd)
+    vsd = O.make_vae_decoder_state_dict(seed=1)
+    vae = build_ref_vae(vsd)
+    pipe = LTXVideoPipeline(tokenizer=None, text_encoder=None, vae=vae, transformer=tr,
+                            scheduler=RectifiedFlowScheduler.from_config(dict(OURS_SCHEDULER_CONFIG)),
+                            patchifier=SymmetricPatchifier(patch_size=1), prompt_enhancer_image_caption_model=None,
+                            prompt_enhancer_image_caption_processor=None, prompt_enhancer_llm_model=None,
+                            prompt_enhancer_llm_tokenizer=None)
+    H, W, F_, fps = 160, 256, 17, 25.0          # x 0.6666666 -> 96 x 160 (latent 3x3x5); second pass 192 x 320 (latent 3x6x10)
+    pe = torch.randn(1, 32, 4096, generator=g)
+    ne = torch.randn(1, 32, 4096, generator=g)
+    pm = torch.ones(1, 32); pm[:, 20:] = 0
+    nm = torch.ones(1, 32); nm[:, 9:] = 0
+    pipe.encode_prompt = lambda *a, **k: (pe, pm, ne, nm)     # the T5 encoder is out of scope: hand the embeddings over
+    multi = LTXMultiScalePipeline(pipe, up)
+    first = dict(guidance_scale=[1, 3, 1], stg_scale=[0, 1, 1], rescaling_scale=[1, 0.7, 1], guidance_timesteps=[1.0, 0.95, 0.6],
+                 skip_block_list=[[], [1], [0]], skip_final_inference_steps=1, cfg_star_rescale=True)
+    second = dict(guidance_scale=[1], stg_scale=[1], rescaling_scale=[1], guidance_timesteps=[1.0], skip_block_list=[1],
+                  skip_initial_inference_steps=2, cfg_star_rescale=True)
+    common = dict(downscale_factor=0.6666666, first_pass=first, second_pass=second, height=H, width=W, num_frames=F_,
+                  frame_rate=fps, prompt="p", negative_prompt="n", num_inference_steps1=5, num_inference_steps2=5,
+                  skip_layer_strategy=SkipLayerStrategy.AttentionValues, VAE_tile_size=(0, 0), ltxv_model=_NoInterrupt(),
+                  device="cpu", return_dict=True, is_video=True, vae_per_channel_normalize=True, enhance_prompt=False)
+    cwd = os.getcwd()
+    os.chdir("/tmp")
+    try:
+        with _cuda_to_cpu():
+            lat = multi(**common, output_type="latent", generator=torch.Generator().manual_seed(7))
+            img = multi(**common, output_type="pt", generator=torch.Generator().manual_seed(7))
+    finally:
+        os.chdir(cwd)
+    # ---- the same flow on the oracle
+    gen = torch.Generator().manual_seed(7)
+    f, h1, w1, h2, w2 = 3, 3, 5, 6, 10
+    kw = dict(num_frames_lat=f, frame_rate=fps, neg_enc=ne, neg_mask=nm, strategy=O.SKIP_ATTENTION_VALUES)
+    n1 = torch.randn(1, f * h1 * w1, 128, generator=gen)
+    ts1 = O.rf_timesteps(5, (1, 128, f, h1, w1))[:4]
+    l1 = O.denoise_loop(sd, cfg, n1, pe, pm, lat_h=h1, lat_w=w1, num_steps=5, timesteps=ts1, guidance_scale=first["guidance_scale"],
+                        stg_scale=first["stg_scale"], rescaling_scale=first["rescaling_scale"],
+                        guidance_timesteps=first["guidance_timesteps"], skip_block_list=first["skip_block_list"], **kw)
+    l1 = O.unpatchify(l1, f, h1, w1)
+    upl = O.adain_filter_latent(O.upsample_latents(usd, vsd, l1), l1)
+    n2 = O.unpatchify(torch.randn(1, f * h2 * w2, 128, generator=gen), f, h2, w2)
+    ts2 = O.rf_timesteps(5, (1, 128, f, h2, w2))[2:]
+    init2 = O.multiscale_second_pass_init(n2, upl, float(ts2[0]))
+    l2 = O.denoise_loop(sd, cfg, O.patchify(init2), pe, pm, lat_h=h2, lat_w=w2, num_steps=5, timesteps=ts2,
+                        guidance_scale=second["guidance_scale"], stg_scale=second["stg_scale"],
+                        rescaling_scale=second["rescaling_scale"], guidance_timesteps=second["guidance_timesteps"],
+                        skip_block_list=second["skip_block_list"], **kw)
+    l2 = O.unpatchify(l2, f, h2, w2)
+    _check("multi-scale final latents", l2, lat, tol=5e-5)
+    mine_img = O.multiscale_resize(O.postprocess(O.vae_decode(vsd, l2)), H, W)
+    print(f"  multi-scale decoded + resized frames: PSNR(oracle, reference) = {O.psnr(mine_img, img):.1f} dB")
+    assert tuple(img.shape) == (1, 3, F_, H, W) and O.psnr(mine_img, img) > 70
+    strat = lambda d: {k: v for k, v in d.items()}
+    out["pipeline"] = dict(meta=dict(H=H, W=W, F=F_, fps=fps, num_layers=L, steps=5, downscale_factor=0.6666666, noise_seed=7),
+                           first_pass=strat(first), second_pass=strat(second), pe=pe, ne=ne, pm=pm, nm=nm,
+                           first_latents=l1, latents=lat, frames_sub=img[:, :, ::4, ::8, ::8].to(torch.float16).clone())
+    torch.save(out, os.path.join(GOLD, "ltx_multiscale.pt"))
+    print("written", os.path.join(GOLD, "ltx_multiscale.pt"))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["patchifier", "scheduler", "transformer", "vae", "vae_encode", "pipeline"]
+    which = sys.argv[1:] or ["patchifier", "scheduler", "transformer", "vae", "vae_encode", "pipeline", "multiscale"]
     for w in which:
         print(f"[{w}]")
         globals()["case_" + w]()

@@ -444,26 +444,45 @@ def guidance_combine(noise_pred: Tensor, num_conds: int, do_cfg: bool, do_stg: b
 def denoise_loop(sd, cfg, latents: Tensor, enc: Tensor, enc_mask: Tensor, *, num_frames_lat: int,
                  lat_h: int, lat_w: int, frame_rate: float, num_steps: int,
                  neg_enc: Optional[Tensor] = None, neg_mask: Optional[Tensor] = None,
-                 guidance_scale: float = 1.0, stg_scale: float = 0.0, rescaling_scale: float = 1.0,
-                 skip_block_list: Optional[List[int]] = None, strategy: Optional[str] = None,
+                 guidance_scale=1.0, stg_scale=0.0, rescaling_scale=1.0,
+                 skip_block_list: Optional[list] = None, strategy: Optional[str] = None,
                  conditioning_mask: Optional[Tensor] = None, model_dtype=torch.float32,
-                 per_step: Optional[list] = None, timesteps: Optional[Tensor] = None) -> Tensor:
+                 per_step: Optional[list] = None, timesteps: Optional[Tensor] = None,
+                 guidance_timesteps: Optional[List[float]] = None) -> Tensor:
     """LTXVideoPipeline.__call__ denoise loop (pipeline_ltx_video.py:919-1268) on patchified
-    latents [b, N, C]; returns final patchified latents.  image_cond_noise_scale = 0."""
+    latents [b, N, C]; returns final patchified latents.  image_cond_noise_scale = 0.
+    guidance_scale / stg_scale / rescaling_scale / skip_block_list may be per-guidance-timestep lists (:959-1017)."""
     b, N, C = latents.shape
     D = cfg["num_attention_heads"] * cfg["attention_head_dim"]
     if timesteps is None:
         timesteps = rf_timesteps(num_steps, (b, C, num_frames_lat, lat_h, lat_w))
     timesteps = timesteps.to(latents.device)
-    gs = guidance_scale if guidance_scale > 1.0 else 0.0                             # :973-990
-    do_cfg, do_stg, do_resc = gs > 1.0, stg_scale > 0.0, rescaling_scale != 1.0
+    n = len(timesteps)
+    mapping = None
+    if guidance_timesteps:                                                            # :959-968
+        mapping = []
+        for t in timesteps:
+            idx = [i for i, val in enumerate(guidance_timesteps) if val <= t]
+            mapping.append(idx[0] if len(idx) > 0 else len(guidance_timesteps) - 1)
+    per = lambda v: [v] * n if not isinstance(v, list) else [v[mapping[i]] for i in range(n)]
+    gs = [x if x > 1.0 else 0.0 for x in per(guidance_scale)]                        # :973-990
+    stg, resc = per(stg_scale), per(rescaling_scale)
+    do_cfg, do_stg, do_resc = any(x > 1.0 for x in gs), any(x > 0.0 for x in stg), any(x != 1.0 for x in resc)
     num_conds = 1 + int(do_cfg) + int(do_stg)
     L = sum(1 for k in sd if k.endswith(".attn1.to_q.weight"))
-    skip_mask = None
-    if do_stg and skip_block_list:
-        skip_mask = torch.ones(L, b * num_conds, dtype=model_dtype, device=latents.device)
-        for bi in skip_block_list:
-            skip_mask[bi, num_conds - 1::num_conds] = 0                               # transformer3d.py:184-185
+    if skip_block_list is not None:                                                   # :1003-1013
+        if len(skip_block_list) == 0 or not isinstance(skip_block_list[0], list):
+            skip_block_list = [skip_block_list] * n
+        else:
+            skip_block_list = [skip_block_list[mapping[i]] for i in range(n)]
+    skip_masks = None
+    if do_stg and skip_block_list is not None:
+        skip_masks = []
+        for sb in skip_block_list:
+            m = torch.ones(L, b * num_conds, dtype=model_dtype, device=latents.device)
+            for bi in sb:
+                m[bi, num_conds - 1::num_conds] = 0                                   # transformer3d.py:184-185
+            skip_masks.append(m)
     enc_b, mask_b = enc, enc_mask
     if do_cfg:
         enc_b = torch.cat([neg_enc, enc]); mask_b = torch.cat([neg_mask, enc_mask])
@@ -480,10 +499,9 @@ def denoise_loop(sd, cfg, latents: Tensor, enc: Tensor, enc_mask: Tensor, *, num
         if cmask is not None:
             cur_t = torch.min(cur_t, 1.0 - cmask)                                    # :1145-1150 -> [B,N]
         noise_pred = transformer_forward(sd, cfg, x_in.to(model_dtype), cos_sin, enc_b.to(model_dtype),
-                                         cur_t, mask_b, skip_mask, strategy,
+                                         cur_t, mask_b, skip_masks[i] if skip_masks is not None else None, strategy,
                                          latent_shape=(num_frames_lat, lat_h, lat_w))
-        noise_pred = guidance_combine(noise_pred, num_conds, do_cfg, do_stg, gs, stg_scale,
-                                      rescaling_scale, do_resc)
+        noise_pred = guidance_combine(noise_pred, num_conds, do_cfg, do_stg, gs[i], stg[i], resc[i], do_resc)
         cur_t = cur_t[:1]
         denoised = rf_step(noise_pred, cur_t, latents, timesteps)                    # :1233, per-token branch
         if conditioning_mask is not None:
@@ -660,6 +678,89 @@ def vae_encode(sd: Dict[str, Tensor], video: Tensor, cfg: dict = LTX_VAE, noise:
     if per_channel_normalize:
         z = (z - sd["mean_of_means"].to(z.dtype).view(1, -1, 1, 1, 1)) / sd["std_of_means"].to(z.dtype).view(1, -1, 1, 1, 1)
     return z * cfg.get("scaling_factor", 1.0)
+
+
+# --------------------------------------------------------------------------------------
+# Multi-scale flow: LatentUpsampler (latent_upsampler.py:15-149, dims=3, spatial x2), adain_filter_latent
+# (pipeline_ltx_video.py:1709-1737), LTXMultiScalePipeline.__call__ (:1782-1903)
+# --------------------------------------------------------------------------------------
+def make_latent_upsampler_state_dict(in_channels: int = 128, mid_channels: int = 512, num_blocks_per_stage: int = 4,
+                                     seed: int = 3) -> Dict[str, Tensor]:
+    """LatentUpsampler(dims=3, spatial_upsample=True, temporal_upsample=False) parameters (latent_upsampler.py:56-107);
+    nn.Conv default init bounds, GroupNorm affine perturbed away from (1, 0) so the test sees it."""
+    gen = torch.Generator().manual_seed(seed)
+    sd: Dict[str, Tensor] = {}
+
+    def conv(name, o, i, nd=3):
+        b = 1.0 / math.sqrt(i * 3 ** nd)
+        sd[name + ".weight"] = _uniform(gen, (o, i) + (3,) * nd, b)
+        sd[name + ".bias"] = _uniform(gen, (o,), b)
+
+    def gn(name, c):
+        sd[name + ".weight"] = 1.0 + 0.1 * torch.randn(c, generator=gen)
+        sd[name + ".bias"] = 0.1 * torch.randn(c, generator=gen)
+
+    conv("initial_conv", mid_channels, in_channels); gn("initial_norm", mid_channels)
+    for stage in ("res_blocks", "post_upsample_res_blocks"):
+        for j in range(num_blocks_per_stage):
+            conv(f"{stage}.{j}.conv1", mid_channels, mid_channels); gn(f"{stage}.{j}.norm1", mid_channels)
+            conv(f"{stage}.{j}.conv2", mid_channels, mid_channels); gn(f"{stage}.{j}.norm2", mid_channels)
+    conv("upsampler.0", 4 * mid_channels, mid_channels, nd=2)
+    conv("final_conv", in_channels, mid_channels)
+    return sd
+
+
+def _up_resblock(sd, p, x):
+    """ResBlock.forward (latent_upsampler.py:30-39)"""
+    h = F.silu(F.group_norm(F.conv3d(x, sd[p + "conv1.weight"], sd[p + "conv1.bias"], padding=1), 32,
+                            sd[p + "norm1.weight"], sd[p + "norm1.bias"]))
+    h = F.group_norm(F.conv3d(h, sd[p + "conv2.weight"], sd[p + "conv2.bias"], padding=1), 32, sd[p + "norm2.weight"], sd[p + "norm2.bias"])
+    return F.silu(h + x)
+
+
+def latent_upsampler_forward(sd: Dict[str, Tensor], latent: Tensor) -> Tensor:
+    """LatentUpsampler.forward, dims=3 spatial branch (latent_upsampler.py:109-149): [B,C,F,H,W] -> [B,C,F,2H,2W]."""
+    b, c, f, h, w = latent.shape
+    nb = sum(1 for k in sd if k.startswith("res_blocks.") and k.endswith(".conv1.weight"))
+    x = F.conv3d(latent, sd["initial_conv.weight"], sd["initial_conv.bias"], padding=1)
+    x = F.silu(F.group_norm(x, 32, sd["initial_norm.weight"], sd["initial_norm.bias"]))
+    for j in range(nb):
+        x = _up_resblock(sd, f"res_blocks.{j}.", x)
+    m = x.shape[1]
+    x2 = x.permute(0, 2, 1, 3, 4).reshape(b * f, m, h, w)                              # "b c f h w -> (b f) c h w"
+    x2 = F.pixel_shuffle(F.conv2d(x2, sd["upsampler.0.weight"], sd["upsampler.0.bias"], padding=1), 2)   # PixelShuffleND(2)
+    x = x2.reshape(b, f, m, 2 * h, 2 * w).permute(0, 2, 1, 3, 4)
+    for j in range(nb):
+        x = _up_resblock(sd, f"post_upsample_res_blocks.{j}.", x)
+    return F.conv3d(x, sd["final_conv.weight"], sd["final_conv.bias"], padding=1)
+
+
+def adain_filter_latent(latents: Tensor, reference_latents: Tensor, factor: float = 1.0) -> Tensor:
+    """pipeline_ltx_video.py:1709-1737: per (batch, channel) match mean / unbiased std to the reference, then lerp."""
+    dims = (2, 3, 4)
+    r_sd, r_mean = torch.std_mean(reference_latents, dim=dims, keepdim=True)
+    i_sd, i_mean = torch.std_mean(latents, dim=dims, keepdim=True)
+    return torch.lerp(latents, (latents - i_mean) / i_sd * r_sd + r_mean, factor)
+
+
+def upsample_latents(up_sd: Dict[str, Tensor], vae_sd: Dict[str, Tensor], latents: Tensor) -> Tensor:
+    """LTXMultiScalePipeline._upsample_latents (:1761-1772): un-normalise, LatentUpsampler, normalise."""
+    dt = latents.dtype
+    std, mean = vae_sd["std_of_means"].to(dt).view(1, -1, 1, 1, 1), vae_sd["mean_of_means"].to(dt).view(1, -1, 1, 1, 1)
+    return (latent_upsampler_forward(up_sd, latents * std + mean) - mean) / std
+
+
+def multiscale_second_pass_init(noise: Tensor, upsampled: Tensor, t0: float) -> Tensor:
+    """prepare_latents with input latents (pipeline_ltx_video.py:700-706): t0 * noise + (1 - t0) * latents."""
+    return t0 * noise + (1 - t0) * upsampled
+
+
+def multiscale_resize(videos: Tensor, height: int, width: int) -> Tensor:
+    """LTXMultiScalePipeline.__call__ tail (:1890-1901): per-frame bilinear resize (align_corners=False) to the requested size."""
+    b, c, f, h, w = videos.shape
+    v = videos.permute(0, 2, 1, 3, 4).reshape(b * f, c, h, w)
+    v = F.interpolate(v, size=(height, width), mode="bilinear", align_corners=False)
+    return v.reshape(b, f, c, height, width).permute(0, 2, 1, 3, 4)
 
 
 def postprocess(image: Tensor) -> Tensor:

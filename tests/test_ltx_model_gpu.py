@@ -225,3 +225,88 @@ def test_pipeline_i2v_from_pixels_vs_oracle():
         err = O.rel_l2(a.cpu(), b)
         print(f"i2v-from-pixels step {i}: rel_l2 = {err:.3e}")
         assert err < TOL_LATENTS
+
+
+# ------------------------------------------------------------------ multi-scale flow
+def test_multiscale_kernels():
+    import torch.nn.functional as F
+    from ltx_video_gpupoor_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    # GroupNorm(32) + SiLU (+ residual) on NDHWC
+    for C in (256, 512):
+        x = (torch.randn(2, 3, 5, 7, C, generator=g) * 1.5 + 0.3).bfloat16().to(DEV)
+        r = torch.randn(2, 3, 5, 7, C, generator=g).bfloat16().to(DEV)
+        ga = (1 + 0.1 * torch.randn(C, generator=g)).bfloat16().to(DEV); be = (0.1 * torch.randn(C, generator=g)).bfloat16().to(DEV)
+        xc = x.float().permute(0, 4, 1, 2, 3)
+        ref = F.group_norm(xc, 32, ga.float(), be.float(), eps=1e-5)
+        y = ops.groupnorm_silu(x, ga, be)
+        assert O.rel_l2(y.float().permute(0, 4, 1, 2, 3).cpu(), F.silu(ref).cpu()) < 6e-3
+        y = ops.groupnorm_silu(x, ga, be, residual=r)
+        assert O.rel_l2(y.float().permute(0, 4, 1, 2, 3).cpu(), F.silu(ref + r.float().permute(0, 4, 1, 2, 3)).cpu()) < 6e-3
+        y = ops.groupnorm_silu(x, ga, be, silu=False)
+        assert O.rel_l2(y.float().permute(0, 4, 1, 2, 3).cpu(), ref.cpu()) < 6e-3
+    # centred zero-padded 3x3x3 convolution and per-frame 3x3 convolution
+    x = torch.randn(1, 4, 6, 9, 128, generator=g).bfloat16().to(DEV)
+    w = (torch.randn(256, 128, 3, 3, 3, generator=g) / 50).bfloat16().to(DEV)
+    b = torch.randn(256, generator=g).bfloat16().to(DEV)
+    y = ops.conv_taps(x, w.permute(0, 2, 3, 4, 1).reshape(256, -1).contiguous(), b, 3, 3, centered=True)
+    ref = F.conv3d(x.float().permute(0, 4, 1, 2, 3), w.float(), b.float(), padding=1)
+    assert O.rel_l2(y.float().permute(0, 4, 1, 2, 3).cpu(), ref.cpu()) < 6e-3
+    w2 = (torch.randn(256, 128, 3, 3, generator=g) / 30).bfloat16().to(DEV)
+    y = ops.conv_taps(x, w2.permute(0, 2, 3, 1).reshape(256, -1).contiguous(), b, 1, 3, centered=True)
+    ref = F.conv2d(x[0].float().permute(0, 3, 1, 2), w2.float(), b.float(), padding=1)
+    assert O.rel_l2(y[0].float().permute(0, 3, 1, 2).cpu(), ref.cpu()) < 6e-3
+    # AdaIN, latent re-normalisation, bilinear resize (fp32 kernels)
+    a = (torch.randn(1, 128, 3, 8, 12, generator=g) * 0.7 - 0.2).to(DEV); r = (torch.randn(1, 128, 3, 4, 6, generator=g) * 1.9 + 0.4).to(DEV)
+    for f in (1.0, 0.25):
+        assert O.rel_l2(ops.adain(a, r, f).cpu(), O.adain_filter_latent(a.cpu(), r.cpu(), f)) < 1e-5
+    z = torch.randn(2, 3, 4, 5, 128, generator=g).bfloat16().to(DEV)
+    sd_, mu_ = (0.5 + torch.rand(128, generator=g)).to(DEV), torch.randn(128, generator=g).to(DEV)
+    ref = (z.float().permute(0, 4, 1, 2, 3) - mu_.view(1, -1, 1, 1, 1)) / sd_.view(1, -1, 1, 1, 1)
+    assert torch.allclose(ops.latent_from_ndhwc(z, sd_, mu_), ref, rtol=1e-6, atol=1e-6)
+    v = torch.rand(1, 3, 5, 48, 80, generator=g).to(DEV)
+    for (hh, ww) in ((40, 64), (96, 160), (50, 70)):
+        assert torch.allclose(ops.bilinear_resize(v, hh, ww).cpu(), O.multiscale_resize(v.cpu(), hh, ww), rtol=1e-5, atol=1e-5)
+
+
+def test_latent_upsampler_vs_reference_fixture(golden_dir):
+    from ltx_video_gpupoor_b200.ltx.latent_upsampler import LatentUpsampler, adain_filter_latent
+    u = _load(golden_dir, "ltx_multiscale.pt")["upsampler"]
+    up = LatentUpsampler(in_channels=128, mid_channels=u["mid"], num_blocks_per_stage=u["nb"], dims=3)
+    up.load_state_dict(O.make_latent_upsampler_state_dict(128, u["mid"], u["nb"], seed=u["seed"]))
+    y = up(u["z"].to(DEV))
+    torch.cuda.synchronize()
+    assert tuple(y.shape) == (1, 128, 3, 8, 12) and y.dtype == torch.float32
+    e = O.rel_l2(y.cpu(), u["out"])
+    print(f"latent upsampler rel_l2 vs reference = {e:.3e}")
+    assert e < 2e-2
+    assert O.rel_l2(adain_filter_latent(u["out"].to(DEV), u["ref_lat"].to(DEV)).cpu(), u["adain"]) < 1e-5
+
+
+def test_multiscale_pipeline_vs_reference_fixture(golden_dir):
+    from ltx_video_gpupoor_b200.ltx.latent_upsampler import LatentUpsampler
+    from ltx_video_gpupoor_b200.ltx.pipeline_ltx_video import LTXMultiScalePipeline
+    g = _load(golden_dir, "ltx_multiscale.pt")
+    u, p = g["upsampler"], g["pipeline"]
+    m = p["meta"]
+    pipe, sd, vsd = _pipe(m["num_layers"])
+    up = LatentUpsampler(in_channels=128, mid_channels=u["mid"], num_blocks_per_stage=u["nb"], dims=3)
+    up.load_state_dict(O.make_latent_upsampler_state_dict(128, u["mid"], u["nb"], seed=u["seed"]))
+    multi = LTXMultiScalePipeline(pipe, up)
+    common = dict(downscale_factor=m["downscale_factor"], first_pass=dict(p["first_pass"]), second_pass=dict(p["second_pass"]),
+                  height=m["H"], width=m["W"], num_frames=m["F"], frame_rate=m["fps"], prompt_embeds=p["pe"],
+                  prompt_attention_mask=p["pm"], negative_prompt_embeds=p["ne"], negative_prompt_attention_mask=p["nm"],
+                  num_inference_steps1=m["steps"], num_inference_steps2=m["steps"],
+                  skip_layer_strategy=SkipLayerStrategy.AttentionValues, VAE_tile_size=(0, 0), is_video=True,
+                  vae_per_channel_normalize=True)
+    lat = multi(**common, output_type="latent", generator=torch.Generator().manual_seed(m["noise_seed"]))
+    torch.cuda.synchronize()
+    e = O.rel_l2(lat.float().cpu(), p["latents"])
+    print(f"multi-scale final latents rel_l2 vs reference fixture = {e:.3e}")
+    assert tuple(lat.shape) == (1, 128, 3, 6, 10) and e < TOL_LATENTS
+    img = multi(**common, output_type="pt", generator=torch.Generator().manual_seed(m["noise_seed"]))
+    torch.cuda.synchronize()
+    assert tuple(img.shape) == (1, 3, m["F"], m["H"], m["W"])
+    ps = O.psnr(img.float().cpu()[:, :, ::4, ::8, ::8], p["frames_sub"].float())
+    print(f"multi-scale decoded + resized frames PSNR vs reference = {ps:.1f} dB")
+    assert ps >= 40.0

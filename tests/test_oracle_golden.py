@@ -139,3 +139,32 @@ def test_wan_step_skipping_oracle_matches_reference(golden_dir):
         lat = so.step((u + 5.0 * (c - u)).unsqueeze(0), lat.unsqueeze(0)).squeeze(0)
         assert W.rel_l2(lat, g["teacache_loop"][i]) < 2e-4
     assert tc["skipped"] == tcg["skipped"] and 0 < tc["skipped"] < tcg["steps"] - 2
+
+
+def test_multiscale_oracle_matches_reference(golden_dir):
+    """LatentUpsampler, adain_filter_latent and the LTXMultiScalePipeline flow (oracle) vs the fixture recorded from the unmodified
+    reference (oracle/gen_golden.py:case_multiscale — upsampler / AdaIN bit-identical, final latents 5e-7)."""
+    g = _load(golden_dir, "ltx_multiscale.pt")
+    u = g["upsampler"]
+    usd = O.make_latent_upsampler_state_dict(128, u["mid"], u["nb"], seed=u["seed"])
+    y = O.latent_upsampler_forward(usd, u["z"])
+    assert y.shape == (1, 128, 3, 8, 12) and O.rel_l2(y, u["out"]) < 1e-5
+    assert O.rel_l2(O.adain_filter_latent(u["out"], u["ref_lat"]), u["adain"]) < 1e-6
+    p = g["pipeline"]
+    m = p["meta"]
+    sd = O.make_transformer_state_dict(O.LTX_2B, seed=0, num_layers=m["num_layers"])
+    vsd = O.make_vae_decoder_state_dict(seed=1)
+    # second pass from the recorded first-pass latents (the first pass is the plain pipeline, covered above)
+    gen = torch.Generator().manual_seed(m["noise_seed"])
+    f, h1, w1, h2, w2 = 3, 3, 5, 6, 10
+    torch.randn(1, f * h1 * w1, 128, generator=gen)                              # the first pass' draw
+    upl = O.adain_filter_latent(O.upsample_latents(usd, vsd, p["first_latents"]), p["first_latents"])
+    n2 = O.unpatchify(torch.randn(1, f * h2 * w2, 128, generator=gen), f, h2, w2)
+    ts2 = O.rf_timesteps(m["steps"], (1, 128, f, h2, w2))[p["second_pass"]["skip_initial_inference_steps"]:]
+    sp = p["second_pass"]
+    l2 = O.denoise_loop(sd, O.LTX_2B, O.patchify(O.multiscale_second_pass_init(n2, upl, float(ts2[0]))), p["pe"], p["pm"],
+                        num_frames_lat=f, lat_h=h2, lat_w=w2, frame_rate=m["fps"], num_steps=m["steps"], timesteps=ts2,
+                        neg_enc=p["ne"], neg_mask=p["nm"], guidance_scale=sp["guidance_scale"], stg_scale=sp["stg_scale"],
+                        rescaling_scale=sp["rescaling_scale"], guidance_timesteps=sp["guidance_timesteps"],
+                        skip_block_list=sp["skip_block_list"], strategy=O.SKIP_ATTENTION_VALUES)
+    assert O.rel_l2(O.unpatchify(l2, f, h2, w2), p["latents"]) < 5e-5
