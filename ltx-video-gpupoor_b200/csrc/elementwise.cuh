@@ -903,19 +903,29 @@ __global__ void groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv
 
 // AdaIN: one block per (batch, channel) row.  x [rows, n], ref [rows, m] fp32; out = lerp(x, (x - mean_x)/std_x * std_ref + mean_ref, factor)
 // with torch.std_mean's unbiased std (two passes over the L2-resident row).
+DEVI float block_sum_256_all(float v, float* sm, float* bcast) {      // the sum, in every thread
+  const float r = block_sum_256(v, sm);
+  if (threadIdx.x == 0) *bcast = r;
+  __syncthreads();
+  const float out = *bcast;
+  __syncthreads();
+  return out;
+}
+
 __global__ void adain_kernel(const float* __restrict__ x, const float* __restrict__ ref, float* __restrict__ out, long long n,
                              long long m, float factor) {
   __shared__ float sm[8];
+  __shared__ float bc;
   const float* xr = x + blockIdx.x * n;
   const float* rr = ref + blockIdx.x * m;
   float a = 0.f, b = 0.f;
   for (long long i = threadIdx.x; i < n; i += 256) a += xr[i];
   for (long long i = threadIdx.x; i < m; i += 256) b += rr[i];
-  const float mx = block_sum_256(a, sm) / n, mr = block_sum_256(b, sm) / m;
+  const float mx = block_sum_256_all(a, sm, &bc) / n, mr = block_sum_256_all(b, sm, &bc) / m;
   a = 0.f; b = 0.f;
   for (long long i = threadIdx.x; i < n; i += 256) { const float d = xr[i] - mx; a = fmaf(d, d, a); }
   for (long long i = threadIdx.x; i < m; i += 256) { const float d = rr[i] - mr; b = fmaf(d, d, b); }
-  const float sx = sqrtf(block_sum_256(a, sm) / (n - 1)), sr = sqrtf(block_sum_256(b, sm) / (m - 1));
+  const float sx = sqrtf(block_sum_256_all(a, sm, &bc) / (n - 1)), sr = sqrtf(block_sum_256_all(b, sm, &bc) / (m - 1));
   float* o = out + blockIdx.x * n;
   for (long long i = threadIdx.x; i < n; i += 256) {
     const float v = xr[i], t = (v - mx) / sx * sr + mr;
