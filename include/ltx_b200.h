@@ -157,6 +157,11 @@ int ltxb200_cfg_combine_f32(const float* cond, const float* uncond, float* out, 
 int ltxb200_pixelnorm_silu_bf16(const void* x, void* y, int64_t voxels, int C, float eps, int apply_silu,
                                 void* stream);
 
+/* PixelNorm -> x * (1 + scale[c]) + shift[c] -> optional SiLU: the timestep-conditioned ResnetBlock3D / decoder tail
+ * (causal_video_autoencoder.py:773-797,1212-1240); scale, shift: bf16 [C] (one video per call). */
+int ltxb200_pixelnorm_mod_silu_bf16(const void* x, void* y, int64_t voxels, int C, float eps, const void* scale,
+                                    const void* shift, int apply_silu, void* stream);
+
 /* latents NCDHW (fp32 if is_f32 else bf16) -> x*std[c]+mean[c] -> NDHWC bf16 (vae_encode.py:239-247). */
 int ltxb200_latent_to_ndhwc(const void* z, int is_f32, void* out, int B, int C, int64_t FHW, const float* stdv,
                             const float* meanv, void* stream);

@@ -46,6 +46,7 @@ def _declare(lib):
         "ltxb200_guidance_step": ([P, L, L, I, I, I, I, F, F, F, P, P, P, I, F, P, P, P], I),
         "ltxb200_cfg_combine_f32": ([P, P, P, L, F, I, P, P], I),
         "ltxb200_pixelnorm_silu_bf16": ([P, P, L, I, F, I, P], I),
+        "ltxb200_pixelnorm_mod_silu_bf16": ([P, P, L, I, F, P, P, I, P], I),
         "ltxb200_latent_to_ndhwc": ([P, I, P, I, I, L, P, P, P], I),
         "ltxb200_conv3d_strided_bf16": ([P, P, P, P, I, I, I, I, I, I, I, I, P], I),
         "ltxb200_conv_taps_bf16": ([P, P, P, P, I, I, I, I, I, I, I, I, I, P, P], I),

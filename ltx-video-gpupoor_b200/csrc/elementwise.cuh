@@ -616,7 +616,8 @@ cfg_combine_f32_kernel(const float* __restrict__ cond, const float* __restrict__
 template <int C>
 __global__ void __launch_bounds__(256)
 pixelnorm_silu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long voxels, float eps,
-                      int apply_silu) {
+                      int apply_silu, const __nv_bfloat16* __restrict__ scale = nullptr,
+                      const __nv_bfloat16* __restrict__ shift = nullptr) {
   constexpr int G = (C / 8 < 32) ? C / 8 : 32;
   constexpr int NV = C / (8 * G);
   constexpr int VPW = 32 / G;                                   // voxels per warp
@@ -643,10 +644,15 @@ pixelnorm_silu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __rest
   if (!ok) return;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    float o[8];
+    float o[8], sc[8], sh[8];
+    if (scale) {        // timestep-conditioned decoder: x * (1 + scale) + shift per channel (causal_video_autoencoder.py:1224-1237)
+      load8(scale + (i * G + gl) * 8, sc);
+      load8(shift + (i * G + gl) * 8, sh);
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float t = bf16r(v[i][j] * inv);
+      float t = bf16r(v[i][j] * inv);
+      if (scale) t = bf16r(bf16r(t * bf16r(1.0f + sc[j])) + sh[j]);
       o[j] = apply_silu ? __fdividef(t, 1.0f + __expf(-t)) : t;
     }
     store8(y + vox * C + (i * G + gl) * 8, o);

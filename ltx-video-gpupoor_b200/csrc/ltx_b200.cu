@@ -615,19 +615,22 @@ extern "C" int ltxb200_cfg_combine_f32(const float* cond, const float* uncond, f
   return launch_status();
 }
 
-extern "C" int ltxb200_pixelnorm_silu_bf16(const void* x, void* y, int64_t voxels, int C, float eps, int apply_silu,
-                                           void* stream) {
+static int pixelnorm_impl(const void* x, void* y, int64_t voxels, int C, float eps, int apply_silu, const void* scale,
+                          const void* shift, void* stream) {
   if (voxels <= 0) return kErrBadShape;
-  if (!aligned16(x) || !aligned16(y)) return kErrBadAlign;
+  if (!aligned16(x) || !aligned16(y) || ((scale == nullptr) != (shift == nullptr)) || (scale && (!aligned16(scale) || !aligned16(shift))))
+    return kErrBadAlign;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   auto X = static_cast<const __nv_bfloat16*>(x);
   auto Y = static_cast<__nv_bfloat16*>(y);
+  auto SC = static_cast<const __nv_bfloat16*>(scale);
+  auto SH = static_cast<const __nv_bfloat16*>(shift);
 #define PN_CASE(c)                                                                             \
   case c: {                                                                                    \
     constexpr int G = (c / 8 < 32) ? c / 8 : 32;                                               \
     const long long warps = (voxels + (32 / G) - 1) / (32 / G);                                \
     const long long blocks = (warps + 7) / 8;                                                  \
-    pixelnorm_silu_kernel<c><<<static_cast<unsigned>(blocks), 256, 0, st>>>(X, Y, voxels, eps, apply_silu); \
+    pixelnorm_silu_kernel<c><<<static_cast<unsigned>(blocks), 256, 0, st>>>(X, Y, voxels, eps, apply_silu, SC, SH); \
   } break;
   switch (C) {
     PN_CASE(64) PN_CASE(128) PN_CASE(256) PN_CASE(512) PN_CASE(1024)
@@ -635,6 +638,17 @@ extern "C" int ltxb200_pixelnorm_silu_bf16(const void* x, void* y, int64_t voxel
   }
 #undef PN_CASE
   return launch_status();
+}
+
+extern "C" int ltxb200_pixelnorm_silu_bf16(const void* x, void* y, int64_t voxels, int C, float eps, int apply_silu,
+                                           void* stream) {
+  return pixelnorm_impl(x, y, voxels, C, eps, apply_silu, nullptr, nullptr, stream);
+}
+
+extern "C" int ltxb200_pixelnorm_mod_silu_bf16(const void* x, void* y, int64_t voxels, int C, float eps, const void* scale,
+                                               const void* shift, int apply_silu, void* stream) {
+  if (!scale || !shift) return kErrBadAlign;
+  return pixelnorm_impl(x, y, voxels, C, eps, apply_silu, scale, shift, stream);
 }
 
 extern "C" int ltxb200_l2norm_silu_bf16(const void* x, void* y, int64_t voxels, int C, int c_real, const void* gamma,

@@ -75,13 +75,12 @@ class CausalVideoAutoencoder:
         cfg.update({k: v for k, v in config.items()})
         if cfg["norm_layer"] != "pixel_norm" or cfg["dims"] != 3:
             raise NotImplementedError("only the pixel_norm / 3D configuration of the named 2B VAE is implemented")
-        if cfg.get("timestep_conditioning", False):
-            raise NotImplementedError("timestep-conditioned decoders are SURVEY §8(f) next")
         self._cfg = cfg
         self.config = SimpleNamespace(**{k: v for k, v in cfg.items() if not k.startswith("_")})
         self.decoder = _Decoder()
         self.decoder.causal = cfg["causal_decoder"]
         self.decoder.patch_size = cfg["patch_size"]
+        self.decoder.timestep_conditioning = bool(cfg.get("timestep_conditioning", False))     # read by the pipeline (:1271)
         self.dtype = BF16
         self.device = torch.device("cuda")
         self.use_z_tiling = False
@@ -95,6 +94,15 @@ class CausalVideoAutoencoder:
     def from_config(config):
         assert config["_class_name"] == "CausalVideoAutoencoder"
         return CausalVideoAutoencoder(**config)
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, *args, device="cuda", **kwargs):
+        """causal_video_autoencoder.py:34-120: legacy directory, diffusers directory or single .safetensors."""
+        from .checkpoint_io import load_vae_checkpoint
+        config, sd = load_vae_checkpoint(pretrained_model_name_or_path)
+        vae = cls.from_config(config)
+        vae.load_state_dict(sd, device=device)
+        return vae
 
     # vae.py:92-115 — on a 180 GB part tiling is never needed
     @staticmethod
@@ -142,14 +150,28 @@ class CausalVideoAutoencoder:
                 b = b[perm]
             return _pack_conv(wt, perm), b.to(BF16).contiguous()
 
+        tc = self.decoder.timestep_conditioning
+
+        def temb(name):
+            lin = lambda n_: (sd[n_ + ".weight"].to(dev).to(BF16).contiguous(), sd[n_ + ".bias"].to(dev).to(BF16).contiguous())
+            return lin(name + ".timestep_embedder.linear_1") + lin(name + ".timestep_embedder.linear_2")
+
         self.plan, last = self._plan()
         w["conv_in"] = conv("decoder.conv_in.conv")
+        if tc:
+            self.timestep_scale_multiplier = float(sd["decoder.timestep_scale_multiplier"])
+            w["last_temb"] = temb("decoder.last_time_embedder")
+            w["last_sst"] = sd["decoder.last_scale_shift_table"].to(dev).to(BF16).unsqueeze(0).contiguous()      # [1, 2, C]
         for kind, idx, cin, cout, n in self.plan:
             p = f"decoder.up_blocks.{idx}."
             if kind == "res_x":
                 for j in range(n):
                     w[p + f"{j}.conv1"] = conv(p + f"res_blocks.{j}.conv1.conv")
                     w[p + f"{j}.conv2"] = conv(p + f"res_blocks.{j}.conv2.conv")
+                if tc:                                   # UNetMidBlock3D.time_embedder + per-block tables (:850-853, 1207-1210)
+                    w[p + "temb"] = temb(p + "time_embedder")
+                    w[p + "sst"] = torch.stack([sd[p + f"res_blocks.{j}.scale_shift_table"].to(dev) for j in range(n)], 0) \
+                        .to(BF16).contiguous()                                                    # [n, 4, C]
             elif kind == "res_x_y":
                 w[p + "conv1"] = conv(p + "conv1.conv")
                 w[p + "conv2"] = conv(p + "conv2.conv")
@@ -252,8 +274,17 @@ class CausalVideoAutoencoder:
         return SimpleNamespace(latent_dist=post)
 
     # ---------------------------------------------------------------------------------------------
-    def _resnet(self, x, c1, c2, causal, shortcut=None, norm3=None):
-        """ResnetBlock3D.forward (causal_video_autoencoder.py:1197-1258)"""
+    def _time_embed(self, t: torch.Tensor, tw) -> torch.Tensor:
+        """PixArtAlphaCombinedTimestepSizeEmbeddings(dim, 0): Timesteps(256) -> Linear -> SiLU -> Linear; t [1] fp32 -> [1, dim]"""
+        return ops.gemm(ops.gemm(ops.timestep_embed(t, 256), tw[0], tw[1], act=ops.ACT_SILU), tw[2], tw[3])
+
+    def _resnet(self, x, c1, c2, causal, shortcut=None, norm3=None, ada=None):
+        """ResnetBlock3D.forward (causal_video_autoencoder.py:1197-1258); `ada` [4, C] = scale_shift_table + timestep embedding
+        (shift1, scale1, shift2, scale2) for timestep-conditioned decoders (:1212-1237)."""
+        if ada is not None:
+            h = ops.conv3d(ops.pixelnorm_silu(x, scale=ada[1], shift=ada[0]), c1[0], c1[1], causal=causal)
+            h = ops.pixelnorm_silu(h, scale=ada[3], shift=ada[2])
+            return ops.conv3d(h, c2[0], c2[1], causal=causal, residual=x)
         h = ops.conv3d(ops.pixelnorm_silu(x), c1[0], c1[1], causal=causal)
         h = ops.pixelnorm_silu(h)
         res = x
@@ -276,17 +307,28 @@ class CausalVideoAutoencoder:
             x = ops.latent_to_ndhwc(z, self.std_of_means.float().contiguous(), self.mean_of_means.float().contiguous())
         else:
             x = ops.latent_to_ndhwc(z, None, None)
+        tc = self.decoder.timestep_conditioning
+        if tc:
+            assert timestep is not None, "should pass timestep with timestep_conditioning=True"          # :757-761
+            if x.shape[0] != 1:
+                raise NotImplementedError("timestep-conditioned decode handles one video per call")
+            ts = (torch.as_tensor(timestep, dtype=torch.float32).flatten()[:1] * self.timestep_scale_multiplier).to(self.device)
         x = ops.conv3d(x, *w["conv_in"], causal=causal)
         for kind, idx, cin, cout, n in self.plan:
             p = f"decoder.up_blocks.{idx}."
             if kind == "res_x":
+                ada = ops.ada_add(w[p + "sst"], self._time_embed(ts, w[p + "temb"])).view(n, 4, cin) if tc else None
                 for j in range(n):
-                    x = self._resnet(x, w[p + f"{j}.conv1"], w[p + f"{j}.conv2"], causal)
+                    x = self._resnet(x, w[p + f"{j}.conv1"], w[p + f"{j}.conv2"], causal, ada=ada[j] if tc else None)
             elif kind == "res_x_y":
                 x = self._resnet(x, w[p + "conv1"], w[p + "conv2"], causal, w[p + "shortcut"], w[p + "norm3"])
             else:
                 x = ops.conv3d(x, *w[p + "conv"], causal=causal, store=ops.CONV_D2S)
-        x = ops.pixelnorm_silu(x)
+        if tc:                                                                         # :773-797
+            ada = ops.ada_add(w["last_sst"], self._time_embed(ts, w["last_temb"])).view(2, -1)
+            x = ops.pixelnorm_silu(x, scale=ada[1], shift=ada[0])
+        else:
+            x = ops.pixelnorm_silu(x)
         return ops.conv3d(x, *w["conv_out"], causal=causal, store=ops.CONV_UNPATCH, out_f32=out_f32)
 
     def decode(self, z: torch.Tensor, return_dict: bool = True, target_shape=None, timestep=None):
@@ -317,7 +359,7 @@ def vae_decode(latents: torch.Tensor, vae: CausalVideoAutoencoder, is_video: boo
         raise NotImplementedError("split_size > 1 is a memory workaround that is not needed here")
     if not vae_per_channel_normalize and vae.config.scaling_factor != 1.0:
         latents = latents / vae.config.scaling_factor
-    return vae._decode(latents.to(vae.dtype), per_channel_normalize=vae_per_channel_normalize)
+    return vae._decode(latents.to(vae.dtype), per_channel_normalize=vae_per_channel_normalize, timestep=timestep)
 
 
 def normalize_latents(latents, vae, vae_per_channel_normalize=False):

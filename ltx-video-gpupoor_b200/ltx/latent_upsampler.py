@@ -43,6 +43,15 @@ class LatentUpsampler:
                    num_blocks_per_stage=config.get("num_blocks_per_stage", 4), dims=config.get("dims", 2),
                    spatial_upsample=config.get("spatial_upsample", True), temporal_upsample=config.get("temporal_upsample", False))
 
+    @classmethod
+    def from_pretrained(cls, pretrained_model_path, *args, device="cuda", **kwargs):
+        """latent_upsampler.py:177-199: .safetensors with the config in its metadata."""
+        from .checkpoint_io import load_upsampler_checkpoint
+        config, sd = load_upsampler_checkpoint(pretrained_model_path)
+        up = cls.from_config(config)
+        up.load_state_dict(sd, device=device)
+        return up
+
     def config(self):
         return {"_class_name": "LatentUpsampler", "in_channels": self.in_channels, "mid_channels": self.mid_channels,
                 "num_blocks_per_stage": self.num_blocks_per_stage, "dims": self.dims, "spatial_upsample": self.spatial_upsample,

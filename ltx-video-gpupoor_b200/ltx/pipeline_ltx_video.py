@@ -294,7 +294,18 @@ class LTXVideoPipeline:
         lat = lat32.view(1, N, C)[:, num_cond_latents:]
         lat = self.patchifier.unpatchify(lat, latent_height, latent_width, tr.in_channels // math.prod(self.patchifier.patch_size))
         if output_type != "latent":
-            image = vae_decode(lat.contiguous(), self.vae, is_video, vae_per_channel_normalize=vae_per_channel_normalize)
+            if getattr(self.vae.decoder, "timestep_conditioning", False):          # :1271-1285 re-noise for the conditioned decoder
+                dt = decode_timestep[0] if isinstance(decode_timestep, list) else decode_timestep
+                dn = dt if decode_noise_scale is None else (decode_noise_scale[0] if isinstance(decode_noise_scale, list) else decode_noise_scale)
+                noise = kwargs.get("_decode_noise")                                # test hook; the reference draws torch.randn_like
+                if noise is None:
+                    noise = torch.randn(lat.shape, device=lat.device, dtype=lat.dtype)
+                lat = lat * (1 - dn) + noise.to(lat.device, lat.dtype) * dn
+                decode_timestep = torch.tensor([dt], dtype=torch.float32)
+            else:
+                decode_timestep = None
+            image = vae_decode(lat.contiguous(), self.vae, is_video, vae_per_channel_normalize=vae_per_channel_normalize,
+                               timestep=decode_timestep)
             image = (image.float() / 2 + 0.5).clamp(0, 1)          # VaeImageProcessor.postprocess (:1298)
         else:
             image = lat

@@ -74,6 +74,16 @@ class Transformer3DModel:
     def from_config(cls, config: dict):
         return cls(**config)
 
+    @classmethod
+    def from_pretrained(cls, pretrained_model_path, *args, device="cuda", **kwargs):
+        """transformer3d.py:271-326: a diffusers directory (config mapped, keys renamed) or a single .safetensors with its config
+        in the metadata."""
+        from .checkpoint_io import load_transformer_checkpoint
+        config, sd = load_transformer_checkpoint(pretrained_model_path)
+        model = cls.from_config(config)
+        model.load_state_dict(sd, device=device)
+        return model
+
     # ---------------------------------------------------------------------------------------------
     # weights
     # ---------------------------------------------------------------------------------------------

@@ -252,10 +252,19 @@ def guidance_step(pred: torch.Tensor, latents: torch.Tensor, timesteps: torch.Te
     _lib.check(rc, "guidance_step")
 
 
-def pixelnorm_silu(x: torch.Tensor, silu: bool = True, eps: float = 1e-8) -> torch.Tensor:
+def pixelnorm_silu(x: torch.Tensor, silu: bool = True, eps: float = 1e-8, scale: Optional[torch.Tensor] = None,
+                   shift: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """PixelNorm [-> x*(1+scale)+shift, scale/shift bf16 [C]] [-> SiLU] on [..., C] bf16."""
     _req(x, name="x"); assert x.is_contiguous()
     C = x.shape[-1]
     y = torch.empty_like(x)
+    if scale is not None:
+        _req(scale, name="scale"); _req(shift, name="shift")
+        assert scale.is_contiguous() and shift.is_contiguous() and scale.numel() == C and shift.numel() == C
+        _lib.check(_lib.lib().ltxb200_pixelnorm_mod_silu_bf16(x.data_ptr(), y.data_ptr(), x.numel() // C, C, float(eps),
+                                                              scale.data_ptr(), shift.data_ptr(), int(silu), _stream()),
+                   "pixelnorm_mod_silu")
+        return y
     _lib.check(_lib.lib().ltxb200_pixelnorm_silu_bf16(x.data_ptr(), y.data_ptr(), x.numel() // C, C, float(eps),
                                                       int(silu), _stream()), "pixelnorm_silu")
     return y

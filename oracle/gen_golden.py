@@ -144,10 +144,10 @@ def case_patchifier():
                os.path.join(GOLD, "patchifier.pt"))
 
 
-def build_ref_vae(sd):
+def build_ref_vae(sd, **cfg_overrides):
     from ltx_video.models.autoencoders.causal_video_autoencoder import CausalVideoAutoencoder
     from ltx_video.utils.diffusers_config_mapping import OURS_VAE_CONFIG
-    vae = CausalVideoAutoencoder.from_config(dict(OURS_VAE_CONFIG))
+    vae = CausalVideoAutoencoder.from_config(dict(OURS_VAE_CONFIG, **cfg_overrides))
     dec_sd = {k[len("decoder."):]: v for k, v in sd.items() if k.startswith("decoder.")}
     vae.decoder.load_state_dict(dec_sd, strict=True)
     vae.register_buffer("std_of_means", sd["std_of_means"])
@@ -202,6 +202,16 @@ def case_vae():
     assert torch.equal(ru(rp(xx, 4, 1), 4, 1), xx)
     assert torch.equal(ru(rp(xx, 4, 1), 4, 1), O.vae_unpatchify(rp(xx, 4, 1), 4))
     torch.save(dict(z=z, out=y_ref.to(torch.float16), seed_weights=1), os.path.join(GOLD, "ltx_vae_decode.pt"))
+    # timestep-conditioned decoder (causal_video_autoencoder.py:724-733,757-795,1207-1237; the 0.9.x VAEs, decode_timestep 0.05)
+    tcfg = dict(O.LTX_VAE, timestep_conditioning=True)
+    tsd = O.make_vae_decoder_state_dict(tcfg, seed=4)
+    tvae = build_ref_vae(tsd, timestep_conditioning=True)
+    t = torch.tensor([0.05])
+    yt_ref = vae_decode(z, tvae, is_video=True, vae_per_channel_normalize=True, timestep=t)
+    yt = O.vae_decode(tsd, z, tcfg, timestep=t)
+    _check("vae_decode(timestep-conditioned)", yt, yt_ref, tol=1e-4)
+    assert O.rel_l2(O.vae_decode(tsd, z, tcfg, timestep=torch.tensor([0.5])), yt_ref) > 1e-3      # the timestep matters
+    torch.save(dict(z=z, out=yt_ref.to(torch.float16), seed_weights=4, timestep=t), os.path.join(GOLD, "ltx_vae_decode_timestep.pt"))
 
 
 @contextlib.contextmanager

@@ -157,6 +157,19 @@ def make_vae_decoder_state_dict(cfg: dict = LTX_VAE, seed: int = 1) -> Dict[str,
     _conv3d(sd, gen, "decoder.conv_out.conv", cfg["out_channels"] * cfg["patch_size"] ** 2, last)
     sd["std_of_means"] = 0.5 + torch.rand(cfg["latent_channels"], generator=gen)
     sd["mean_of_means"] = 0.1 * torch.randn(cfg["latent_channels"], generator=gen)
+    if cfg.get("timestep_conditioning", False):          # causal_video_autoencoder.py:724-733, 850-853, 1207-1210
+        def temb(name, dim):
+            _linear(sd, gen, name + ".timestep_embedder.linear_1", dim, 256)
+            _linear(sd, gen, name + ".timestep_embedder.linear_2", dim, dim)
+        sd["decoder.timestep_scale_multiplier"] = torch.tensor(1000.0)
+        for kind, idx, cin, cout, n in vae_decoder_plan(cfg):
+            if kind == "res_x":
+                p = f"decoder.up_blocks.{idx}."
+                temb(p + "time_embedder", 4 * cin)
+                for j in range(n):
+                    sd[p + f"res_blocks.{j}.scale_shift_table"] = torch.randn(4, cin, generator=gen) / cin ** 0.5
+        temb("decoder.last_time_embedder", 2 * last)
+        sd["decoder.last_scale_shift_table"] = torch.randn(2, last, generator=gen) / last ** 0.5
     return sd
 
 
@@ -530,10 +543,24 @@ def pixel_norm(x: Tensor, eps: float = 1e-8) -> Tensor:
     return x / torch.sqrt(torch.mean(x ** 2, dim=1, keepdim=True) + eps)
 
 
-def _resnet(sd, p, x, cin, cout, causal):
-    """ResnetBlock3D.forward (causal_video_autoencoder.py:1197-1258), pixel_norm, no noise/timestep."""
-    h = causal_conv3d(sd, p + "conv1", F.silu(pixel_norm(x)), causal)
-    h = causal_conv3d(sd, p + "conv2", F.silu(pixel_norm(h)), causal)
+def _vae_time_embed(sd, name, t: Tensor) -> Tensor:
+    """PixArtAlphaCombinedTimestepSizeEmbeddings(dim, 0) (diffusers): Timesteps(256) -> Linear -> SiLU -> Linear; t [B] -> [B, dim]"""
+    h = F.silu(linear(sd, name + ".timestep_embedder.linear_1", timestep_sinusoid(t, 256)))
+    return linear(sd, name + ".timestep_embedder.linear_2", h)
+
+
+def _resnet(sd, p, x, cin, cout, causal, temb: Optional[Tensor] = None):
+    """ResnetBlock3D.forward (causal_video_autoencoder.py:1197-1258), pixel_norm, no noise; `temb` [B, 4*cin] is the mid-block's
+    timestep embedding when the decoder is timestep-conditioned (:1207-1237)."""
+    h = pixel_norm(x)
+    if temb is not None:
+        ada = sd[p + "scale_shift_table"][None, :, :, None, None, None] + temb.reshape(x.shape[0], 4, -1, 1, 1, 1)
+        shift1, scale1, shift2, scale2 = ada.unbind(dim=1)
+        h = h * (1 + scale1) + shift1
+    h = pixel_norm(causal_conv3d(sd, p + "conv1", F.silu(h), causal))
+    if temb is not None:
+        h = h * (1 + scale2) + shift2
+    h = causal_conv3d(sd, p + "conv2", F.silu(h), causal)
     if cin != cout:
         xs = x.permute(0, 2, 3, 4, 1)
         xs = F.layer_norm(xs, (cin,), sd[p + "norm3.norm.weight"], sd[p + "norm3.norm.bias"], eps=1e-6)
@@ -560,10 +587,14 @@ def vae_unpatchify(x: Tensor, p: int) -> Tensor:
 
 
 def vae_decode(sd: Dict[str, Tensor], latents: Tensor, cfg: dict = LTX_VAE,
-               per_channel_normalize: bool = True, collect: Optional[list] = None) -> Tensor:
+               per_channel_normalize: bool = True, collect: Optional[list] = None, timestep: Optional[Tensor] = None) -> Tensor:
     """vae_decode -> un_normalize_latents -> Decoder.forward.  latents [B,128,F,H,W] ->
-    [B,3,8(F-1)+1,32H,32W]."""
+    [B,3,8(F-1)+1,32H,32W].  timestep [B] for timestep-conditioned decoders (:757-795)."""
     causal = cfg["causal_decoder"]
+    tc = cfg.get("timestep_conditioning", False)
+    if tc:
+        assert timestep is not None, "should pass timestep with timestep_conditioning=True"
+        scaled_t = timestep.to(latents.dtype) * sd["decoder.timestep_scale_multiplier"]
     dt = latents.dtype
     if per_channel_normalize:
         z = latents * sd["std_of_means"].to(dt).view(1, -1, 1, 1, 1) + sd["mean_of_means"].to(dt).view(1, -1, 1, 1, 1)
@@ -575,15 +606,22 @@ def vae_decode(sd: Dict[str, Tensor], latents: Tensor, cfg: dict = LTX_VAE,
     for kind, idx, cin, cout, n in vae_decoder_plan(cfg):
         p = f"decoder.up_blocks.{idx}."
         if kind == "res_x":
+            temb = _vae_time_embed(sd, p + "time_embedder", scaled_t.flatten()) if tc else None      # UNetMidBlock3D :903-918
             for j in range(n):
-                x = _resnet(sd, p + f"res_blocks.{j}.", x, cin, cin, causal)
+                x = _resnet(sd, p + f"res_blocks.{j}.", x, cin, cin, causal, temb)
         elif kind == "res_x_y":
             x = _resnet(sd, p, x, cin, cout, causal)
         else:
             x = depth_to_space(causal_conv3d(sd, p + "conv", x, causal))[:, :, 1:]   # :1057-1062
         if collect is not None:
             collect.append(x)
-    x = F.silu(pixel_norm(x))
+    x = pixel_norm(x)
+    if tc:                                                                            # :773-795
+        e = _vae_time_embed(sd, "decoder.last_time_embedder", scaled_t.flatten())
+        ada = sd["decoder.last_scale_shift_table"][None, :, :, None, None, None] + e.reshape(x.shape[0], 2, -1, 1, 1, 1)
+        shift, scale = ada.unbind(dim=1)
+        x = x * (1 + scale) + shift
+    x = F.silu(x)
     x = causal_conv3d(sd, "decoder.conv_out", x, causal)
     return vae_unpatchify(x, cfg["patch_size"])
 

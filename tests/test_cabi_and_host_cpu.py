@@ -83,3 +83,80 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, f"{f} touches oracle/"
+
+
+# ------------------------------------------------------------------ checkpoint formats, host-side only
+def test_checkpoint_formats_round_trip(tmp_path):
+    import json
+    import torch
+    from safetensors.torch import save_file
+    from ltx_video_gpupoor_b200.ltx import checkpoint_io as C
+    from ltx_video_gpupoor_b200.ltx.causal_video_autoencoder import LTX_VAE_CONFIG
+    from ltx_video_gpupoor_b200.ltx.transformer3d import LTX_2B_CONFIG
+    g = torch.Generator().manual_seed(0)
+    tsd = {"model.diffusion_model.patchify_proj.weight": torch.randn(8, 4, generator=g),
+           "model.diffusion_model.transformer_blocks.0.attn1.q_norm.weight": torch.randn(8, generator=g),
+           "vae.decoder.conv_in.conv.weight": torch.randn(4, 2, 3, 3, 3, generator=g),
+           "vae.per_channel_statistics.std-of-means": torch.rand(4, generator=g)}
+    # --- single file with the configs in the metadata (transformer3d.py:313-325, causal_video_autoencoder.py:104-114)
+    cfg = {"transformer": dict(LTX_2B_CONFIG, num_layers=1), "vae": dict(LTX_VAE_CONFIG)}
+    f = tmp_path / "ltxv.safetensors"
+    save_file(tsd, str(f), metadata={"config": json.dumps(cfg)})
+    c, sd = C.load_transformer_checkpoint(f)
+    assert c == cfg["transformer"] and set(sd) == set(tsd) and torch.equal(sd["vae.decoder.conv_in.conv.weight"], tsd["vae.decoder.conv_in.conv.weight"])
+    c, sd = C.load_vae_checkpoint(f)
+    assert c == cfg["vae"] and c["_class_name"] == "CausalVideoAutoencoder"
+    # --- diffusers directory: config looked up in the mapping, keys renamed (diffusers_config_mapping.py:133-174)
+    d = tmp_path / "repo"
+    (d / "transformer").mkdir(parents=True); (d / "vae").mkdir()
+    (d / "transformer" / "config.json").write_text(json.dumps(C.DIFFUSERS_TRANSFORMER_CONFIG))
+    (d / "vae" / "config.json").write_text(json.dumps(C.DIFFUSERS_VAE_CONFIG))
+    dsd = {"proj_in.weight": torch.randn(8, 4, generator=g), "time_embed.linear.bias": torch.randn(8, generator=g),
+           "transformer_blocks.3.attn1.norm_q.weight": torch.randn(8, generator=g), "transformer_blocks.3.attn2.norm_k.weight": torch.randn(8, generator=g)}
+    save_file({k: v for k, v in list(dsd.items())[:2]}, str(d / "transformer" / "diffusion_pytorch_model-00001-of-00002.safetensors"))
+    save_file({k: v for k, v in list(dsd.items())[2:]}, str(d / "transformer" / "diffusion_pytorch_model-00002-of-00002.safetensors"))
+    c, sd = C.load_transformer_checkpoint(d)
+    assert c["num_layers"] == 28 and c["qk_norm"] == "rms_norm" and c["_class_name"] == "Transformer3DModel"
+    assert set(sd) == {"patchify_proj.weight", "adaln_single.linear.bias", "transformer_blocks.3.attn1.q_norm.weight",
+                       "transformer_blocks.3.attn2.k_norm.weight"}
+    assert torch.equal(sd["patchify_proj.weight"], dsd["proj_in.weight"])
+    vsd = {"decoder.mid_block.resnets.2.conv1.conv.weight": torch.zeros(1), "decoder.up_blocks.0.resnets.0.conv2.conv.bias": torch.zeros(1),
+           "decoder.up_blocks.1.upsamplers.0.conv.conv.weight": torch.zeros(1), "decoder.up_blocks.2.conv_in.norm3.weight": torch.zeros(1),
+           "decoder.up_blocks.2.conv_in.conv_shortcut.conv.weight": torch.zeros(1), "decoder.up_blocks.3.resnets.3.conv1.conv.weight": torch.zeros(1),
+           "encoder.down_blocks.0.downsamplers.0.conv.weight": torch.zeros(1), "encoder.mid_block.resnets.0.conv1.conv.weight": torch.zeros(1),
+           "latents_mean": torch.zeros(128), "latents_std": torch.ones(128)}
+    save_file(vsd, str(d / "vae" / "diffusion_pytorch_model.safetensors"))
+    c, sd = C.load_vae_checkpoint(d)
+    assert c["blocks"] == LTX_VAE_CONFIG["blocks"]
+    assert set(sd) == {"decoder.up_blocks.0.res_blocks.2.conv1.conv.weight", "decoder.up_blocks.1.res_blocks.0.conv2.conv.bias",
+                       "decoder.up_blocks.2.conv.conv.weight", "decoder.up_blocks.4.norm3.norm.weight",
+                       "decoder.up_blocks.4.conv_shortcut.weight", "decoder.up_blocks.9.res_blocks.3.conv1.conv.weight",
+                       "encoder.down_blocks.1.conv.weight", "encoder.down_blocks.9.res_blocks.0.conv1.conv.weight",
+                       "per_channel_statistics.mean-of-means", "per_channel_statistics.std-of-means"}
+    import pytest
+    (d / "vae" / "config.json").write_text(json.dumps(dict(C.DIFFUSERS_VAE_CONFIG, latent_channels=64)))
+    with pytest.raises(AssertionError):
+        C.load_vae_checkpoint(d)
+    # --- legacy VAE directory with per_channel_statistics.json (causal_video_autoencoder.py:42-70)
+    lv = tmp_path / "legacy"; lv.mkdir()
+    (lv / "config.json").write_text(json.dumps(dict(LTX_VAE_CONFIG)))
+    torch.save({"decoder.conv_in.conv.weight": torch.zeros(1)}, lv / "autoencoder.pth")
+    (lv / "per_channel_statistics.json").write_text(json.dumps({"columns": ["std-of-means", "mean-of-means"], "data": [[1.0, 0.5], [2.0, 0.25]]}))
+    c, sd = C.load_vae_checkpoint(lv)
+    assert torch.equal(sd["per_channel_statistics.std-of-means"], torch.tensor([1.0, 2.0]))
+    assert torch.equal(sd["per_channel_statistics.mean-of-means"], torch.tensor([0.5, 0.25]))
+    # --- upsampler
+    uf = tmp_path / "up.safetensors"
+    ucfg = {"_class_name": "LatentUpsampler", "in_channels": 128, "mid_channels": 512, "num_blocks_per_stage": 4, "dims": 3,
+            "spatial_upsample": True, "temporal_upsample": False}
+    save_file({"final_conv.bias": torch.zeros(128)}, str(uf), metadata={"config": json.dumps(ucfg)})
+    c, sd = C.load_upsampler_checkpoint(uf)
+    assert c == ucfg and "final_conv.bias" in sd
+    # --- LoRA merge: W += mult * alpha/rank * up @ down
+    W0 = torch.randn(6, 5, generator=g)
+    sdw = {"transformer_blocks.0.attn1.to_q.weight": W0.clone()}
+    down, up = torch.randn(2, 5, generator=g), torch.randn(6, 2, generator=g)
+    n = C.merge_lora(sdw, {"diffusion_model.transformer_blocks.0.attn1.to_q.lora_down.weight": down,
+                           "diffusion_model.transformer_blocks.0.attn1.to_q.lora_up.weight": up,
+                           "diffusion_model.transformer_blocks.0.attn1.to_q.alpha": torch.tensor(4.0)}, multiplier=0.5)
+    assert n == 1 and torch.allclose(sdw["transformer_blocks.0.attn1.to_q.weight"], W0 + 0.5 * (4.0 / 2) * up @ down, atol=1e-6)

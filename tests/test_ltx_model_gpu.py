@@ -157,6 +157,22 @@ def test_vae_decode_vs_reference_fixture(golden_dir):
     assert ps >= 40.0
 
 
+def test_vae_decode_timestep_conditioned_vs_reference_fixture(golden_dir):
+    g = _load(golden_dir, "ltx_vae_decode_timestep.pt")
+    cfg = dict(O.LTX_VAE, timestep_conditioning=True)
+    vsd = O.make_vae_decoder_state_dict(cfg, seed=g["seed_weights"])
+    vae = CausalVideoAutoencoder(timestep_conditioning=True)
+    vae.load_state_dict(vsd)
+    assert vae.decoder.timestep_conditioning
+    y = vae_decode(g["z"].to(DEV), vae, is_video=True, vae_per_channel_normalize=True, timestep=g["timestep"])
+    torch.cuda.synchronize()
+    ps = O.psnr(O.postprocess(y.float().cpu()), O.postprocess(g["out"].float()))
+    print(f"timestep-conditioned vae decode PSNR vs reference = {ps:.1f} dB")
+    assert tuple(y.shape) == (1, 3, 9, 96, 128) and ps >= 40.0
+    y2 = vae_decode(g["z"].to(DEV), vae, is_video=True, vae_per_channel_normalize=True, timestep=torch.tensor([0.5]))
+    assert O.psnr(O.postprocess(y2.float().cpu()), O.postprocess(g["out"].float())) < ps - 3      # the timestep is used
+
+
 # ------------------------------------------------------------------ VAE encode (i2v / v2v conditioning from pixels)
 @pytest.mark.parametrize("st,shw,T,H,W", [(2, 2, 9, 16, 24), (1, 2, 3, 7, 10), (2, 1, 5, 6, 9)])
 def test_conv3d_strided(st, shw, T, H, W):
@@ -310,3 +326,35 @@ def test_multiscale_pipeline_vs_reference_fixture(golden_dir):
     ps = O.psnr(img.float().cpu()[:, :, ::4, ::8, ::8], p["frames_sub"].float())
     print(f"multi-scale decoded + resized frames PSNR vs reference = {ps:.1f} dB")
     assert ps >= 40.0
+
+
+def test_from_pretrained_single_file(tmp_path, golden_dir):
+    """transformer3d.py:313-325 / causal_video_autoencoder.py:104-114 / latent_upsampler.py:183-199: one .safetensors holding
+    `model.diffusion_model.*` and `vae.*` tensors with the configs in its metadata -> identical to loading the state dicts directly."""
+    import json
+    from safetensors.torch import save_file
+    from ltx_video_gpupoor_b200.ltx.causal_video_autoencoder import LTX_VAE_CONFIG
+    from ltx_video_gpupoor_b200.ltx.latent_upsampler import LatentUpsampler
+    from ltx_video_gpupoor_b200.ltx.transformer3d import LTX_2B_CONFIG
+    m0, sd = _model(1)
+    vsd = O.make_vae_decoder_state_dict(seed=1)
+    one = {"model.diffusion_model." + k: v.contiguous() for k, v in sd.items()}
+    one.update({"vae." + k: v.contiguous() for k, v in vsd.items() if k.startswith("decoder.")})
+    one["vae.per_channel_statistics.std-of-means"] = vsd["std_of_means"]
+    one["vae.per_channel_statistics.mean-of-means"] = vsd["mean_of_means"]
+    f = tmp_path / "ltxv-test.safetensors"
+    save_file(one, str(f), metadata={"config": json.dumps({"transformer": dict(LTX_2B_CONFIG, num_layers=1), "vae": dict(LTX_VAE_CONFIG)})})
+    m1 = Transformer3DModel.from_pretrained(f)
+    assert m1.num_layers == 1 and all(torch.equal(m0.w[k], m1.w[k]) for k in m0.w)
+    vae = CausalVideoAutoencoder.from_pretrained(f)
+    g = _load(golden_dir, "ltx_vae_decode.pt")
+    y = vae_decode(g["z"].to(DEV), vae, is_video=True, vae_per_channel_normalize=True)
+    assert O.psnr(O.postprocess(y.float().cpu()), O.postprocess(g["out"].float())) >= 40.0
+    u = _load(golden_dir, "ltx_multiscale.pt")["upsampler"]
+    usd = O.make_latent_upsampler_state_dict(128, u["mid"], u["nb"], seed=u["seed"])
+    uf = tmp_path / "up.safetensors"
+    save_file({k: v.contiguous() for k, v in usd.items()}, str(uf), metadata={"config": json.dumps(
+        {"_class_name": "LatentUpsampler", "in_channels": 128, "mid_channels": u["mid"], "num_blocks_per_stage": u["nb"], "dims": 3,
+         "spatial_upsample": True, "temporal_upsample": False})})
+    up = LatentUpsampler.from_pretrained(uf)
+    assert O.rel_l2(up(u["z"].to(DEV)).cpu(), u["out"]) < 2e-2

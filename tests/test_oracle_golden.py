@@ -168,3 +168,14 @@ def test_multiscale_oracle_matches_reference(golden_dir):
                         rescaling_scale=sp["rescaling_scale"], guidance_timesteps=sp["guidance_timesteps"],
                         skip_block_list=sp["skip_block_list"], strategy=O.SKIP_ATTENTION_VALUES)
     assert O.rel_l2(O.unpatchify(l2, f, h2, w2), p["latents"]) < 5e-5
+
+
+def test_vae_decode_timestep_conditioned_oracle_matches_reference(golden_dir):
+    """Timestep-conditioned decoder (causal_video_autoencoder.py:724-733,757-795,1207-1237) vs the fixture recorded from the
+    unmodified reference (oracle/gen_golden.py:case_vae — bit-identical there)."""
+    g = _load(golden_dir, "ltx_vae_decode_timestep.pt")
+    cfg = dict(O.LTX_VAE, timestep_conditioning=True)
+    sd = O.make_vae_decoder_state_dict(cfg, seed=g["seed_weights"])
+    y = O.vae_decode(sd, g["z"], cfg, timestep=g["timestep"])
+    assert y.shape == (1, 3, 9, 96, 128)
+    assert O.rel_l2(y, g["out"].float()) < 2e-3      # fixture stored as fp16
