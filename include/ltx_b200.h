@@ -146,6 +146,12 @@ int ltxb200_guidance_step(const void* pred, int64_t cond_stride, int64_t n, int 
                           float* latents, void* latents_bf16, const float* timesteps, int num_steps, float t,
                           const float* cond_mask, float* scratch, void* stream);
 
+/* Same, with the stochastic update of rf.py:370-373: x0 = x - t*v, x <- (1 - t_next)*x0 + t_next*noise (noise: fp32 [n], N(0,1)). */
+int ltxb200_guidance_step_stochastic(const void* pred, int64_t cond_stride, int64_t n, int channels, int has_cfg,
+                          int has_stg, int do_rescale, float guidance_scale, float stg_scale, float rescale,
+                          float* latents, void* latents_bf16, const float* timesteps, int num_steps, float t,
+                          const float* cond_mask, float* scratch, const float* noise, void* stream);
+
 /* Wan classifier-free guidance in fp32, optionally with the CFG-Zero* projection of the unconditional branch
  * (wan/text2video.py:31-42 optimized_scale, :551-562): out = a*u + g*(c - a*u), a = <c,u>/(|u|^2+1e-8) or 1.
  * scratch: >= 2*148 floats (only read when use_alpha). */

@@ -44,6 +44,7 @@ def _declare(lib):
         "ltxb200_timestep_embed": ([P, P, I, I, P], I),
         "ltxb200_cast_f32_to_bf16": ([P, P, L, P], I),
         "ltxb200_guidance_step": ([P, L, L, I, I, I, I, F, F, F, P, P, P, I, F, P, P, P], I),
+        "ltxb200_guidance_step_stochastic": ([P, L, L, I, I, I, I, F, F, F, P, P, P, I, F, P, P, P, P], I),
         "ltxb200_cfg_combine_f32": ([P, P, P, L, F, I, P, P], I),
         "ltxb200_pixelnorm_silu_bf16": ([P, P, L, I, F, I, P], I),
         "ltxb200_pixelnorm_mod_silu_bf16": ([P, P, L, I, F, P, P, I, P], I),

@@ -459,6 +459,7 @@ struct GuidanceParams {
   float t;                     // current global timestep
   const float* cond_mask;      // [tokens] or null
   __nv_bfloat16* latents_bf16; // optional bf16 copy of the updated latents (next model input)
+  const float* noise;          // stochastic sampling (rf.py:370-373): fresh N(0,1) per element, or null (Euler step)
 };
 constexpr int kGuidanceBlocks = 148;
 
@@ -573,7 +574,10 @@ __global__ void __launch_bounds__(256) guidance_step_kernel(const GuidanceParams
     }
     const float dt = t_tok - lower;
     float x = g.latents[i];
-    if (update) x = x - dt * v;
+    if (update) {
+      if (g.noise) x = (1.0f - lower) * (x - t_tok * v) + lower * g.noise[i];   // add_noise(x0, noise, t - dt) (rf.py:382-392)
+      else x = x - dt * v;
+    }
     g.latents[i] = x;
     if (g.latents_bf16) g.latents_bf16[i] = __float2bfloat16_rn(x);
   }

@@ -569,10 +569,10 @@ extern "C" int ltxb200_cast_f32_to_bf16(const float* x, void* y, int64_t n, void
   return launch_status();
 }
 
-extern "C" int ltxb200_guidance_step(const void* pred, int64_t cond_stride, int64_t n, int channels, int has_cfg,
-                                     int has_stg, int do_rescale, float guidance_scale, float stg_scale,
-                                     float rescale, float* latents, void* latents_bf16, const float* timesteps,
-                                     int num_steps, float t, const float* cond_mask, float* scratch, void* stream) {
+static int guidance_step_impl(const void* pred, int64_t cond_stride, int64_t n, int channels, int has_cfg,
+                              int has_stg, int do_rescale, float guidance_scale, float stg_scale,
+                              float rescale, float* latents, void* latents_bf16, const float* timesteps,
+                              int num_steps, float t, const float* cond_mask, float* scratch, const float* noise, void* stream) {
   if (n <= 0 || channels <= 0 || num_steps <= 0 || !latents || !pred || !timesteps) return kErrBadShape;
   if ((has_cfg || has_stg) && !scratch) return kErrBadShape;
   GuidanceParams g{};
@@ -582,7 +582,7 @@ extern "C" int ltxb200_guidance_step(const void* pred, int64_t cond_stride, int6
   g.guidance_scale = guidance_scale; g.stg_scale = stg_scale; g.rescale = rescale;
   g.partials = scratch;
   g.latents = latents; g.latents_bf16 = static_cast<__nv_bfloat16*>(latents_bf16);
-  g.timesteps = timesteps; g.num_steps = num_steps; g.t = t; g.cond_mask = cond_mask;
+  g.timesteps = timesteps; g.num_steps = num_steps; g.t = t; g.cond_mask = cond_mask; g.noise = noise;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc = kOk;
   if (g.has_cfg && guidance_scale != 0.f && guidance_scale != 1.f) {
@@ -599,6 +599,24 @@ extern "C" int ltxb200_guidance_step(const void* pred, int64_t cond_stride, int6
   }
   guidance_step_kernel<<<kGuidanceBlocks, 256, 0, st>>>(g);
   return launch_status();
+}
+
+extern "C" int ltxb200_guidance_step(const void* pred, int64_t cond_stride, int64_t n, int channels, int has_cfg,
+                                     int has_stg, int do_rescale, float guidance_scale, float stg_scale,
+                                     float rescale, float* latents, void* latents_bf16, const float* timesteps,
+                                     int num_steps, float t, const float* cond_mask, float* scratch, void* stream) {
+  return guidance_step_impl(pred, cond_stride, n, channels, has_cfg, has_stg, do_rescale, guidance_scale, stg_scale, rescale,
+                            latents, latents_bf16, timesteps, num_steps, t, cond_mask, scratch, nullptr, stream);
+}
+
+extern "C" int ltxb200_guidance_step_stochastic(const void* pred, int64_t cond_stride, int64_t n, int channels, int has_cfg,
+                                                int has_stg, int do_rescale, float guidance_scale, float stg_scale,
+                                                float rescale, float* latents, void* latents_bf16, const float* timesteps,
+                                                int num_steps, float t, const float* cond_mask, float* scratch,
+                                                const float* noise, void* stream) {
+  if (!noise) return kErrBadAlign;
+  return guidance_step_impl(pred, cond_stride, n, channels, has_cfg, has_stg, do_rescale, guidance_scale, stg_scale, rescale,
+                            latents, latents_bf16, timesteps, num_steps, t, cond_mask, scratch, noise, stream);
 }
 
 extern "C" int ltxb200_cfg_combine_f32(const float* cond, const float* uncond, float* out, int64_t n, float guide_scale,

@@ -132,6 +132,12 @@ class LTXVideoPipeline:
         cm, _ = self.patchifier.patchify(cmask.unsqueeze(1))
         return tokens, px, cm.squeeze(-1), 0
 
+    def _step_noise(self, st):
+        """rf.py:372 `torch.randn_like(sample)` for the stochastic sampler, drawn from the call's generator when there is one."""
+        gen = st.generator if isinstance(st.generator, torch.Generator) else None
+        gdev = gen.device if gen is not None else self._execution_device
+        return torch.randn(st.N * st.C, generator=gen, device=gdev, dtype=torch.float32).to(self._execution_device)
+
     def denoise_step(self, st, i: int):
         """One iteration of the loop at pipeline_ltx_video.py:1104-1256: cond batch, timestep tensor, transformer
         forward, guidance, scheduler step.  No host synchronisation."""
@@ -161,7 +167,8 @@ class LTXVideoPipeline:
         ops.guidance_step(noise_pred.view(num_conds, N * C), st.lat32, st.ts_dev, t, num_conds=num_conds,
                           has_cfg=st.do_cfg, has_stg=st.do_stg, do_rescale=st.do_rescaling,
                           guidance_scale=st.guidance_scale[i], stg_scale=st.stg_scale[i], rescale=st.rescaling_scale[i],
-                          channels=C, cond_mask=st.cmask_dev, scratch=st.scratch, latents_bf16=st.lat16)
+                          channels=C, cond_mask=st.cmask_dev, scratch=st.scratch, latents_bf16=st.lat16,
+                          noise=self._step_noise(st) if st.stochastic_sampling else None)
         return st
 
     # ---------------------------------------------------------------------------------------------
@@ -184,8 +191,8 @@ class LTXVideoPipeline:
                  pass_no: int = -1, ltxv_model=None, callback=None, **kwargs):
         if prompt is not None or prompt_embeds is None:
             raise NotImplementedError("text encoding is out of scope: pass prompt_embeds / prompt_attention_mask")
-        if mixed_precision or stochastic_sampling:
-            raise NotImplementedError("mixed_precision / stochastic_sampling are not implemented")
+        if mixed_precision:
+            raise NotImplementedError("mixed_precision (fp32 residual stream) is not implemented")
         is_video = kwargs.get("is_video", False)
         vae_per_channel_normalize = kwargs.get("vae_per_channel_normalize", True)
         image_cond_noise_scale = kwargs.get("image_cond_noise_scale", 0.0)
@@ -275,7 +282,8 @@ class LTXVideoPipeline:
             skip_layer_masks=skip_layer_masks, skip_layer_strategy=skip_layer_strategy, enc_b=enc_b, mask_b=mask_b,
             freqs_cis=freqs_cis, N=N, C=C, lat32=lat32, lat16=lat16, cmask_dev=cmask_dev, scratch=scratch, x_in=x_in,
             t_in=t_in, latent_shape=latent_shape, joint_pass=joint_pass, ltxv_model=ltxv_model, generator=generator,
-            image_cond_noise_scale=image_cond_noise_scale, init_tokens=init_tokens, tokens_shape=tuple(tokens.shape)))
+            image_cond_noise_scale=image_cond_noise_scale, init_tokens=init_tokens, tokens_shape=tuple(tokens.shape),
+            stochastic_sampling=bool(stochastic_sampling)))
         self._state = st
         if kwargs.get("_prepare_only", False):
             return st

@@ -109,21 +109,26 @@ class RectifiedFlowScheduler:
 
     def step(self, model_output: torch.Tensor, timestep, sample: torch.Tensor, return_dict: bool = True,
              stochastic_sampling: Optional[bool] = False, **kwargs) -> Union[RectifiedFlowSchedulerOutput, Tuple]:
-        """rf.py:311-380, deterministic branch.  `timestep`: 0-d (global) or [1,1]; per-token timesteps
-        are expressed through the pipeline's conditioning mask path (`ops.guidance_step`)."""
+        """rf.py:311-380.  `timestep`: 0-d (global) or [1,1]; per-token timesteps are expressed through the pipeline's conditioning
+        mask path (`ops.guidance_step`).  stochastic_sampling (:370-373) re-noises the x0 estimate to the next timestep; the
+        N(0,1) draw comes from `generator=` / `noise=` in kwargs (the reference uses the global RNG)."""
         if self.num_inference_steps is None:
             raise ValueError("Number of inference steps is 'None', you need to run 'set_timesteps' after creating the scheduler")
-        if stochastic_sampling:
-            raise NotImplementedError("stochastic sampling (rf.py:370-373) is not implemented")
         t = float(torch.as_tensor(timestep).reshape(-1)[0])
         assert torch.as_tensor(timestep).numel() == 1, "use the pipeline path for per-token timesteps"
         dev = model_output.device
         lat = sample.to(torch.float32).contiguous().clone().view(-1)
         pred = model_output.to(torch.bfloat16).contiguous().view(1, -1)
         ts = self.timesteps.to(device=dev, dtype=torch.float32).contiguous()
+        noise = None
+        if stochastic_sampling:
+            noise = kwargs.get("noise")
+            if noise is None:
+                noise = torch.randn(sample.shape, device=dev, dtype=torch.float32, generator=kwargs.get("generator"))
+            noise = noise.to(device=dev, dtype=torch.float32).contiguous().view(-1)
         ops.guidance_step(pred, lat, ts, t, num_conds=1, has_cfg=False, has_stg=False, do_rescale=False,
                           guidance_scale=1.0, stg_scale=0.0, rescale=1.0, channels=sample.shape[-1], cond_mask=None,
-                          scratch=None)
+                          scratch=None, noise=noise)
         prev = lat.view(sample.shape)
         if not return_dict:
             return (prev,)

@@ -238,17 +238,21 @@ def cast_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tens
 def guidance_step(pred: torch.Tensor, latents: torch.Tensor, timesteps: torch.Tensor, t: float, *, num_conds: int,
                   has_cfg: bool, has_stg: bool, do_rescale: bool, guidance_scale: float, stg_scale: float,
                   rescale: float, channels: int, cond_mask: Optional[torch.Tensor], scratch: Optional[torch.Tensor],
-                  latents_bf16: Optional[torch.Tensor] = None):
-    """pred [num_conds, n] bf16 (batch 1), latents [n] fp32 in place."""
+                  latents_bf16: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None):
+    """pred [num_conds, n] bf16 (batch 1), latents [n] fp32 in place; `noise` [n] fp32 selects the stochastic update (rf.py:370-373)."""
     _req(pred, name="pred"); _req(latents, torch.float32, "latents"); _req(timesteps, torch.float32, "timesteps")
     assert pred.is_contiguous() and latents.is_contiguous()
     n = latents.numel()
     assert pred.numel() == num_conds * n
+    args = (pred.data_ptr(), n, n, channels, int(has_cfg), int(has_stg), int(do_rescale), float(guidance_scale), float(stg_scale),
+            float(rescale), latents.data_ptr(), _p(latents_bf16), timesteps.data_ptr(), timesteps.numel(), float(t), _p(cond_mask),
+            _p(scratch))
     with _Prof('guidance_step', 'byte', n * (2.0 * num_conds + 10.0)):
-        rc = _lib.lib().ltxb200_guidance_step(pred.data_ptr(), n, n, channels, int(has_cfg), int(has_stg), int(do_rescale),
-                                          float(guidance_scale), float(stg_scale), float(rescale), latents.data_ptr(),
-                                          _p(latents_bf16), timesteps.data_ptr(), timesteps.numel(), float(t),
-                                          _p(cond_mask), _p(scratch), _stream())
+        if noise is None:
+            rc = _lib.lib().ltxb200_guidance_step(*args, _stream())
+        else:
+            _req(noise, torch.float32, "noise"); assert noise.is_contiguous() and noise.numel() == n
+            rc = _lib.lib().ltxb200_guidance_step_stochastic(*args, noise.data_ptr(), _stream())
     _lib.check(rc, "guidance_step")
 
 

@@ -14,6 +14,7 @@ from typing import Optional
 import torch
 
 from .. import ops
+from .fm_solvers import FlowDPMSolverMultistepScheduler, get_sampling_sigmas, retrieve_timesteps
 from .fm_solvers_unipc import FlowUniPCMultistepScheduler
 from .model import WanModel
 from .posemb_layers import get_rotary_pos_embed
@@ -44,8 +45,8 @@ class WanI2V:
             raise NotImplementedError("CLIP visual and the Wan VAE encoder are out of scope: pass clip_fea= [1,257,1280] and y= [20,T,H/8,W/8]")
         if context is None or (guide_scale != 1 and context_null is None):
             raise NotImplementedError("the T5 text encoder is out of scope: pass context= / context_null= embeddings [L, 4096]")
-        if sample_solver != "unipc":
-            raise NotImplementedError("only the default 'unipc' solver is implemented (SURVEY §2 row 15)")
+        if sample_solver not in ("unipc", "dpm++"):
+            raise NotImplementedError("Unsupported solver.")
         dev = self.device
         target_shape = (self.z_dim, (frame_num - 1) // self.vae_stride[0] + 1, height // self.vae_stride[1], width // self.vae_stride[2])
         assert tuple(y.shape) == (20,) + target_shape[1:], f"y must be [20, {target_shape[1:]}]"
@@ -55,8 +56,12 @@ class WanI2V:
             noise = torch.randn(*target_shape, dtype=torch.float32, device=dev, generator=seed_g)     # :226-230
         latents = noise.to(device=dev, dtype=torch.float32).contiguous()
         assert tuple(latents.shape) == tuple(target_shape)
-        sch = FlowUniPCMultistepScheduler(num_train_timesteps=self.num_train_timesteps, shift=1, use_dynamic_shifting=False)
-        sch.set_timesteps(sampling_steps, device=dev, shift=shift)                                        # :290-296
+        if sample_solver == "unipc":
+            sch = FlowUniPCMultistepScheduler(num_train_timesteps=self.num_train_timesteps, shift=1, use_dynamic_shifting=False)
+            sch.set_timesteps(sampling_steps, device=dev, shift=shift)
+        else:                                                                                             # 'dpm++'
+            sch = FlowDPMSolverMultistepScheduler(num_train_timesteps=self.num_train_timesteps, shift=1, use_dynamic_shifting=False)
+            retrieve_timesteps(sch, device=dev, sigmas=get_sampling_sigmas(sampling_steps, shift))                                        # :290-296
         freqs = get_rotary_pos_embed(latents.shape[1:], enable_RIFLEx=bool(enable_RIFLEx))
         freqs = (freqs[0].to(dev), freqs[1].to(dev))
         scratch = torch.empty(2 * 148, device=dev, dtype=torch.float32)

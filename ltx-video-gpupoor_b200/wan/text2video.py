@@ -13,6 +13,7 @@ from typing import Optional
 import torch
 
 from .. import ops
+from .fm_solvers import FlowDPMSolverMultistepScheduler, get_sampling_sigmas, retrieve_timesteps
 from .fm_solvers_unipc import FlowUniPCMultistepScheduler
 from .model import WanModel
 from .posemb_layers import get_rotary_pos_embed
@@ -40,8 +41,8 @@ class WanT2V:
             raise NotImplementedError("VACE / phantom / recam inputs are out of scope")
         if context is None or (guide_scale != 1 and context_null is None):
             raise NotImplementedError("the T5 text encoder is out of scope: pass context= / context_null= embeddings [L, 4096]")
-        if sample_solver != "unipc":
-            raise NotImplementedError("only the default 'unipc' solver is implemented (SURVEY §2 row 15)")
+        if sample_solver not in ("unipc", "dpm++"):
+            raise NotImplementedError("Unsupported solver.")
         dev = self.device
         F = frame_num
         target_shape = (self.z_dim, (F - 1) // self.vae_stride[0] + 1, height // self.vae_stride[1], width // self.vae_stride[2])
@@ -51,8 +52,12 @@ class WanT2V:
             noise = torch.randn(*target_shape, dtype=torch.float32, device=dev, generator=seed_g)     # :410
         latents = noise.to(device=dev, dtype=torch.float32).contiguous()
         assert tuple(latents.shape) == tuple(target_shape)
-        sch = FlowUniPCMultistepScheduler(num_train_timesteps=self.num_train_timesteps, shift=1, use_dynamic_shifting=False)
-        sch.set_timesteps(sampling_steps, device=dev, shift=shift)                                        # :419-422
+        if sample_solver == "unipc":
+            sch = FlowUniPCMultistepScheduler(num_train_timesteps=self.num_train_timesteps, shift=1, use_dynamic_shifting=False)
+            sch.set_timesteps(sampling_steps, device=dev, shift=shift)
+        else:                                                                                             # 'dpm++'
+            sch = FlowDPMSolverMultistepScheduler(num_train_timesteps=self.num_train_timesteps, shift=1, use_dynamic_shifting=False)
+            retrieve_timesteps(sch, device=dev, sigmas=get_sampling_sigmas(sampling_steps, shift))                                        # :419-422
         freqs = get_rotary_pos_embed(latents.shape[1:], enable_RIFLEx=bool(enable_RIFLEx))
         freqs = (freqs[0].to(dev), freqs[1].to(dev))
         scratch = torch.empty(2 * 148, device=dev, dtype=torch.float32)

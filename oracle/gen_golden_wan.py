@@ -103,6 +103,7 @@ def main():
     print("written", os.path.join(GOLD, "wan_t2v.pt"))
     main_i2v()
     main_skip()
+    main_dpm()
 
 
 # The production coefficients (a polynomial fitted to trained checkpoints) are set by the caller; with random weights the time
@@ -160,6 +161,33 @@ def main_skip():
     print("written", os.path.join(GOLD, "wan_skip.pt"))
 
 
+def main_dpm():
+    """sample_solver='dpm++' (text2video.py:423-432): FlowDPMSolverMultistepScheduler driven through retrieve_timesteps with
+    get_sampling_sigmas, against the oracle's DPMpp on seeded velocities."""
+    from wan.utils.fm_solvers import FlowDPMSolverMultistepScheduler, get_sampling_sigmas, retrieve_timesteps
+    g = torch.Generator().manual_seed(21)
+    out = {}
+    for steps, shift in ((4, 5.0), (20, 5.0), (9, 3.0)):
+        s = FlowDPMSolverMultistepScheduler(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False)
+        timesteps, _ = retrieve_timesteps(s, device="cpu", sigmas=get_sampling_sigmas(steps, shift))
+        o = W.DPMpp(); o.set_timesteps(steps, shift)
+        assert torch.equal(timesteps, o.timesteps) and torch.equal(s.sigmas, o.sigmas)
+        x0 = torch.randn(1, 16, 3, 8, 12, generator=g)
+        x, xo, vs, xs = x0.clone(), x0.clone(), [], []
+        for tt in timesteps:
+            v = torch.randn(1, 16, 3, 8, 12, generator=g)
+            x = s.step(v, tt, x, return_dict=False)[0]
+            xo = o.step(v, xo)
+            assert rel_l2(xo, x) < 1e-5, rel_l2(xo, x)
+            vs.append(v); xs.append(x.clone())
+        out[(steps, shift)] = dict(timesteps=timesteps.clone(), sigmas=s.sigmas.clone())
+        if steps < 15:                                                           # keep the fixture small: trajectories for the short runs
+            out[(steps, shift)].update(x0=x0, v=torch.stack(vs), x=torch.stack(xs))
+    print("  DPM++: timesteps/sigmas bit-exact, steps agree to fp32 round-off")
+    torch.save(out, os.path.join(GOLD, "wan_dpmpp.pt"))
+    print("written", os.path.join(GOLD, "wan_dpmpp.pt"))
+
+
 def main_i2v():
     """WanModel(model_type='i2v'): y channels (in_dim 36), img_emb MLPProj over 257 CLIP tokens, WanI2VCrossAttention
     (model.py:277-344, 576-588, 930-998) and the image2video.py:328-414 loop (CFG over cond / uncond with shared y, clip)."""
@@ -204,4 +232,8 @@ def main_i2v():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1:
+        for name in sys.argv[1:]:
+            globals()["main_" + name]()
+    else:
+        main()

@@ -322,13 +322,62 @@ class UniPC:
         return x_t
 
 
+def get_sampling_sigmas(sampling_steps: int, shift: float) -> np.ndarray:
+    """wan/utils/fm_solvers.py:22-26"""
+    sigma = np.linspace(1, 0, sampling_steps + 1)[:sampling_steps]
+    return shift * sigma / (1 + (shift - 1) * sigma)
+
+
+class DPMpp:
+    """FlowDPMSolverMultistepScheduler(solver_order=2, algorithm dpmsolver++, midpoint, flow_prediction, final sigma zero,
+    lower_order_final) as `sample_solver='dpm++'` builds it (wan/utils/fm_solvers.py:69-800, text2video.py:423-432)."""
+
+    def __init__(self, num_train_timesteps: int = 1000):
+        self.T = num_train_timesteps
+
+    def set_timesteps(self, steps: int, shift: float):
+        """text2video.py:428-432 -> set_timesteps(sigmas=get_sampling_sigmas(steps, shift)) with config.shift = 1 (:226-285)"""
+        sigmas = get_sampling_sigmas(steps, shift)
+        sigmas = 1.0 * sigmas / (1 + (1.0 - 1) * sigmas)
+        self.timesteps = torch.from_numpy(sigmas * self.T).to(dtype=torch.int64)
+        self.sigmas = torch.from_numpy(np.concatenate([sigmas, [0]]).astype(np.float32))
+        self.model_outputs = [None, None]
+        self.lower_order_nums = 0
+        self.step_index = 0
+
+    def step(self, model_output: Tensor, sample: Tensor) -> Tensor:
+        """:706-798 (convert_model_output :378-380, first order :415-484, second order midpoint :486-594)"""
+        i, n = self.step_index, len(self.timesteps)
+        lower_order_final = i == n - 1                                          # final_sigmas_type == "zero"
+        lower_order_second = i == n - 2 and n < 15
+        x0 = sample - self.sigmas[i] * model_output
+        self.model_outputs = [self.model_outputs[1], x0]
+        s_t, s_s0 = self.sigmas[i + 1], self.sigmas[i]
+        a_t, a_s0 = 1 - s_t, 1 - s_s0
+        lam_t, lam_s0 = torch.log(a_t) - torch.log(s_t), torch.log(a_s0) - torch.log(s_s0)
+        h = lam_t - lam_s0
+        if self.lower_order_nums < 1 or lower_order_final:
+            x_t = (s_t / s_s0) * sample - (a_t * (torch.exp(-h) - 1.0)) * x0
+        else:                                                                   # solver_order == 2 (lower_order_second is moot)
+            s_s1 = self.sigmas[i - 1]
+            lam_s1 = torch.log(1 - s_s1) - torch.log(s_s1)
+            m0, m1 = self.model_outputs[-1], self.model_outputs[-2]
+            r0 = (lam_s0 - lam_s1) / h
+            D0, D1 = m0, (1.0 / r0) * (m0 - m1)
+            x_t = (s_t / s_s0) * sample - (a_t * (torch.exp(-h) - 1.0)) * D0 - 0.5 * (a_t * (torch.exp(-h) - 1.0)) * D1
+        if self.lower_order_nums < 2:
+            self.lower_order_nums += 1
+        self.step_index += 1
+        return x_t
+
+
 def t2v_denoise(sd, cfg, noise: Tensor, context: Tensor, context_null: Tensor, steps: int, shift: float = 5.0,
                 guide_scale: float = 5.0, per_step: Optional[list] = None, attn_fn=None,
                 cfg_star_switch: bool = False, cfg_zero_step: int = 5, clip_fea: Optional[Tensor] = None,
-                y: Optional[Tensor] = None) -> Tensor:
+                y: Optional[Tensor] = None, sample_solver: str = "unipc") -> Tensor:
     """WanT2V.generate denoise loop, UniPC, plain CFG (text2video.py:399-575).  noise [16, F, H, W] fp32.
     With clip_fea / y it is the WanI2V.generate loop (image2video.py:328-414): same y and CLIP tokens for both passes."""
-    sch = UniPC()
+    sch = UniPC() if sample_solver == "unipc" else DPMpp()
     sch.set_timesteps(steps, shift)
     cos, sin = rope_tables(noise.shape[1:])
     lat = noise

@@ -179,3 +179,18 @@ def test_vae_decode_timestep_conditioned_oracle_matches_reference(golden_dir):
     y = O.vae_decode(sd, g["z"], cfg, timestep=g["timestep"])
     assert y.shape == (1, 3, 9, 96, 128)
     assert O.rel_l2(y, g["out"].float()) < 2e-3      # fixture stored as fp16
+
+
+def test_wan_dpmpp_oracle_matches_reference(golden_dir):
+    """sample_solver='dpm++' (wan/utils/fm_solvers.py via text2video.py:423-432): oracle DPMpp vs the trajectories recorded from the
+    unmodified FlowDPMSolverMultistepScheduler (oracle/gen_golden_wan.py:main_dpm)."""
+    from oracle import wan_oracle as W
+    g = _load(golden_dir, "wan_dpmpp.pt")
+    for (steps, shift), c in g.items():
+        o = W.DPMpp(); o.set_timesteps(steps, shift)
+        assert torch.equal(o.timesteps, c["timesteps"]) and torch.equal(o.sigmas, c["sigmas"])
+        if "x0" in c:
+            x = c["x0"]
+            for i in range(steps):
+                x = o.step(c["v"][i], x)
+                assert W.rel_l2(x, c["x"][i]) < 1e-5

@@ -257,3 +257,26 @@ def test_wan_teacache_loop_vs_reference_fixture(golden_dir):
     m.teacache_multiplier = 2.0
     th = m.compute_teacache_threshold(m.teacache_start_step, s.timesteps_host, 2.0)
     assert 0.01 <= th <= 0.61
+
+
+def test_dpmpp_scheduler_vs_reference_fixture(golden_dir):
+    from ltx_video_gpupoor_b200.wan.fm_solvers import FlowDPMSolverMultistepScheduler, get_sampling_sigmas, retrieve_timesteps
+    g = torch.load(os.path.join(golden_dir, "wan_dpmpp.pt"), weights_only=False)
+    for (steps, shift), c in g.items():
+        s = FlowDPMSolverMultistepScheduler(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False)
+        ts, n = retrieve_timesteps(s, device=DEV, sigmas=get_sampling_sigmas(steps, shift))
+        assert n == steps and torch.equal(ts.cpu(), c["timesteps"]) and torch.equal(s.sigmas, c["sigmas"])     # bit-exact tables
+        if "x0" in c:
+            x = c["x0"].to(DEV)
+            for i, t in enumerate(s.timesteps_host):
+                x = s.step(c["v"][i].to(DEV), t, x, return_dict=False)[0]
+                assert W.rel_l2(x.cpu(), c["x"][i]) < 1e-5
+    # through WanT2V.generate vs the oracle loop
+    gg = _golden(golden_dir)
+    m, sd = _model(gg["cfg"])
+    steps_, ref = [], []
+    WanT2V(m).generate(width=96, height=64, frame_num=9, shift=5.0, sampling_steps=4, guide_scale=5.0, cfg_star_switch=False,
+                       sample_solver="dpm++", context=gg["ctx"], context_null=gg["ctx0"], noise=gg["lat"], _per_step_latents=steps_)
+    W.t2v_denoise(sd, gg["cfg"], gg["lat"], gg["ctx"], gg["ctx0"], steps=4, shift=5.0, guide_scale=5.0, per_step=ref, sample_solver="dpm++")
+    for a, b in zip(steps_, ref):
+        assert W.rel_l2(a.cpu(), b) < 2e-2
