@@ -187,6 +187,15 @@ int ltxb200_conv3d_strided_bf16(const void* x, const void* w, const void* bias, 
  * 73,90-93,107); optional residual. */
 int ltxb200_conv_taps_bf16(const void* x, const void* w, const void* bias, void* out, int B, int T, int H, int W, int Cin,
                            int Cout, int taps_t, int taps_hw, int causal_zero_pad, const void* residual, void* stream);
+/* ---- Wan2.1 VAE encode (wan/modules/vae.py:275-383, 536-575): the strided pieces of Resample('downsample2d'|'downsample3d') ----
+ * zero-padded causal convolution as above with output strides stride_t / stride_hw in {1, 2}:
+ *   out [B, (T-1)/stride_t+1, (H-1-off_hw)/stride_hw+1, (W-1-off_hw)/stride_hw+1, Cout];
+ * off_hw = 1 moves the spatial taps to (h, h+1, h+2): nn.ZeroPad2d((0,1,0,1)) + Conv2d(dim, dim, 3, stride 2) (:90-93, taps_t = 1);
+ * taps_t = 3, taps_hw = 1, stride_t = 2 is `time_conv` = CausalConv3d(dim, dim, (3,1,1), stride (2,1,1)) applied to
+ * [cached last frame, chunk] (:150-165): output frame m >= 1 reads input frames (2m-2, 2m-1, 2m); frame 0 is replaced by the
+ * caller (the first chunk bypasses time_conv). */
+int ltxb200_conv_taps_strided_bf16(const void* x, const void* w, const void* bias, void* out, int B, int T, int H, int W, int Cin,
+                                   int Cout, int taps_t, int taps_hw, int stride_t, int stride_hw, int off_hw, void* stream);
 /* RMS_norm (vae.py:41-58: F.normalize over channels * sqrt(c_real) * gamma) + optional SiLU on [voxels, C] bf16 */
 int ltxb200_l2norm_silu_bf16(const void* x, void* y, int64_t voxels, int C, int c_real, const void* gamma, int apply_silu,
                              void* stream);

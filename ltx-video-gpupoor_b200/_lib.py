@@ -51,6 +51,7 @@ def _declare(lib):
         "ltxb200_latent_to_ndhwc": ([P, I, P, I, I, L, P, P, P], I),
         "ltxb200_conv3d_strided_bf16": ([P, P, P, P, I, I, I, I, I, I, I, I, P], I),
         "ltxb200_conv_taps_bf16": ([P, P, P, P, I, I, I, I, I, I, I, I, I, P, P], I),
+        "ltxb200_conv_taps_strided_bf16": ([P, P, P, P, I, I, I, I, I, I, I, I, I, I, I, P], I),
         "ltxb200_l2norm_silu_bf16": ([P, P, L, I, I, P, I, P], I),
         "ltxb200_upsample2x_nhwc_bf16": ([P, P, L, I, I, I, P], I),
         "ltxb200_softmax_rows_f32_bf16": ([P, L, P, L, I, I, F, P], I),

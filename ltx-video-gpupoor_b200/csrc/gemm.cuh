@@ -51,6 +51,8 @@ struct GemmParams {
   int c_tpad_zero;                 // temporal padding: 0 = replicate (clamped frame index, LTX), 1 = zeros (TMA OOB fill, Wan)
   int c_st, c_shw;                 // output strides (1 or 2): cT/cH/cW are OUTPUT dims, the TMA map strides over the input
   int cTin;                        // input frames (temporal clamp)
+  int c_off_hw;                    // added to the spatial tap coordinate: 0 = centred taps (h-1,h,h+1); 1 = taps (h,h+1,h+2), i.e.
+                                   // nn.ZeroPad2d((0,1,0,1)) + Conv2d(3, stride 2) of the Wan encoder (wan/modules/vae.py:90-93)
   // tile rasterisation of the persistent schedule: 0 = M fastest (one weight panel per wave, all of A re-read per
   // N tile), 1 = N fastest (a wave = a few row panels x every N tile: A streams through once, W stays in L2)
   int n_fastest;
@@ -140,8 +142,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               if (!p.c_tpad_zero) tt = tt < 0 ? 0 : (tt > p.cTin - 1 ? p.cTin - 1 : tt);        // replicate; else TMA zero-fills t < 0
             }
             if (p.c_taps_hw == 3) {
-              hh += kh - 1;
-              ww += kw - 1;
+              hh += kh - 1 + p.c_off_hw;
+              ww += kw - 1 + p.c_off_hw;
             }
             tma_load_5d(sa, &tmA, &full_bar[stage], cblk * kGemmBK, ww, hh, tt, cb);
             tma_load_2d(sb, &tmB, &full_bar[stage], tap * p.cCin + cblk * kGemmBK, tn * BN);

@@ -116,11 +116,13 @@ extern "C" int ltxb200_gemm_bf16(const void* A, int64_t lda, const void* W, int6
 // x: [B, Tin, Hin, Win, Cin]; out: [B, T, H, W, Cout] with T = (Tin - 1) / st + 1 etc. (st, shw = output strides)
 static int conv_impl(const void* x, const void* w, const void* bias, void* out, int B, int Tin, int Hin, int Win, int Cin, int Cout,
                      int taps_t, int taps_hw, int causal, int tpad_zero, int store_mode, int out_f32, const void* residual,
-                     void* stream, int st_t = 1, int st_hw = 1) {
+                     void* stream, int st_t = 1, int st_hw = 1, int off_hw = 0) {
   if (B <= 0 || Tin <= 0 || Hin <= 0 || Win <= 0 || (Cin % 64) || (Cout & 7)) return kErrBadShape;
   if ((st_t != 1 && st_t != 2) || (st_hw != 1 && st_hw != 2)) return kErrUnsupported;
-  if ((st_t != 1 || st_hw != 1) && (taps_t != 3 || taps_hw != 3 || !causal || store_mode != LTXB200_CONV_STORE_NDHWC)) return kErrUnsupported;
-  const int T = (Tin - 1) / st_t + 1, H = (Hin - 1) / st_hw + 1, W = (Win - 1) / st_hw + 1;
+  if ((st_t != 1 || st_hw != 1) && (!causal || store_mode != LTXB200_CONV_STORE_NDHWC || residual)) return kErrUnsupported;
+  if ((st_t == 2 && taps_t != 3) || (st_hw == 2 && taps_hw != 3) || (off_hw != 0 && (off_hw != 1 || taps_hw != 3))) return kErrUnsupported;
+  if (Hin - 1 - off_hw < 0 || Win - 1 - off_hw < 0) return kErrBadShape;
+  const int T = (Tin - 1) / st_t + 1, H = (Hin - 1 - off_hw) / st_hw + 1, W = (Win - 1 - off_hw) / st_hw + 1;
   if ((taps_t != 1 && taps_t != 3) || (taps_hw != 1 && taps_hw != 3)) return kErrUnsupported;
   if (!aligned16(x) || !aligned16(w) || !aligned16(out) || (bias && !aligned16(bias)) || (residual && !aligned16(residual)))
     return kErrBadAlign;
@@ -168,7 +170,7 @@ static int conv_impl(const void* x, const void* w, const void* bias, void* out, 
   p.cB = B; p.cT = T; p.cH = H; p.cW = W; p.cCin = Cin; p.cBH = BH; p.cBW = BW;
   p.c_tiles_h = (H + BH - 1) / BH; p.c_tiles_w = (W + BW - 1) / BW;
   p.c_causal = causal ? 1 : 0; p.c_taps_t = taps_t; p.c_taps_hw = taps_hw; p.c_tpad_zero = tpad_zero ? 1 : 0;
-  p.c_st = st_t; p.c_shw = st_hw; p.cTin = Tin;
+  p.c_st = st_t; p.c_shw = st_hw; p.cTin = Tin; p.c_off_hw = off_hw;
   p.n_fastest = (static_cast<long long>(Cout) * taps * Cin * 2 <= (48ll << 20)) ? 1 : 0;
   if (const char* e = getenv("LTXB200_GEMM_RASTER")) p.n_fastest = atoi(e);
   const int tiles = B * T * p.c_tiles_h * p.c_tiles_w * ((Cout + BN - 1) / BN);
@@ -194,6 +196,13 @@ extern "C" int ltxb200_conv_taps_bf16(const void* x, const void* w, const void* 
   // causal_zero_pad: 0 = causal taps (t-2,t-1,t), replicate padding; 1 = causal, zero padding; 2 = centred taps (t-1,t,t+1), zero padding
   return conv_impl(x, w, bias, out, B, T, H, W, Cin, Cout, taps_t, taps_hw, causal_zero_pad == 2 ? 0 : 1, causal_zero_pad != 0,
                    LTXB200_CONV_STORE_NDHWC, 0, residual, stream);
+}
+
+extern "C" int ltxb200_conv_taps_strided_bf16(const void* x, const void* w, const void* bias, void* out, int B, int T, int H, int W,
+                                              int Cin, int Cout, int taps_t, int taps_hw, int stride_t, int stride_hw,
+                                              int off_hw, void* stream) {
+  return conv_impl(x, w, bias, out, B, T, H, W, Cin, Cout, taps_t, taps_hw, 1, 1, LTXB200_CONV_STORE_NDHWC, 0, nullptr, stream,
+                   stride_t, stride_hw, off_hw);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -353,6 +353,24 @@ def conv_taps(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], ta
     return out
 
 
+def conv_taps_strided(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], taps_t: int, taps_hw: int,
+                      stride_t: int = 1, stride_hw: int = 1, off_hw: int = 0) -> torch.Tensor:
+    """Zero-padded causal conv with output strides (Wan encoder Resample, wan/modules/vae.py:90-97,150-165): x [B,T,H,W,Cin]
+    bf16 NDHWC, w [Cout, taps*Cin] tap-major; off_hw = 1 -> spatial taps (h, h+1, h+2) = ZeroPad2d((0,1,0,1)) + Conv2d."""
+    _req(x, name="x"); _req(w, name="w")
+    assert x.is_contiguous() and w.is_contiguous() and x.dim() == 5
+    B, T, H, W, Cin = x.shape
+    Cout = w.shape[0]
+    assert w.shape[1] == taps_t * taps_hw * taps_hw * Cin
+    To, Ho, Wo = (T - 1) // stride_t + 1, (H - 1 - off_hw) // stride_hw + 1, (W - 1 - off_hw) // stride_hw + 1
+    out = torch.empty(B, To, Ho, Wo, Cout, device=x.device, dtype=BF16)
+    with _Prof('conv_taps_bf16', 'flop', 2.0 * B * To * Ho * Wo * Cout * w.shape[1]):
+        rc = _lib.lib().ltxb200_conv_taps_strided_bf16(x.data_ptr(), w.data_ptr(), _p(bias), out.data_ptr(), B, T, H, W, Cin,
+                                                       Cout, taps_t, taps_hw, stride_t, stride_hw, off_hw, _stream())
+    _lib.check(rc, "conv_taps_strided_bf16")
+    return out
+
+
 def l2norm_silu(x: torch.Tensor, gamma: torch.Tensor, c_real: int, silu: bool = True) -> torch.Tensor:
     """x [..., C] bf16 contiguous (C = stored, 64-padded channels) -> RMS_norm(+SiLU)."""
     _req(x, name="x"); _req(gamma, name="gamma")

@@ -1,5 +1,5 @@
-"""WanVAE — B200-native drop-in for the DECODE side of wan/modules/vae.py (`WanVAE.decode`, :825-829 →
-`WanVAE_.decode` :578-609 → `Decoder3d.forward` :438-493).
+"""WanVAE — B200-native drop-in for wan/modules/vae.py: `WanVAE.decode` (:825-829 → `WanVAE_.decode` :578-609 →
+`Decoder3d.forward` :438-493) and `WanVAE.encode` (:806-816 → `WanVAE_.encode` :536-575 → `Encoder3d.forward` :329-383).
 
 The reference decodes one latent frame per call and carries a 2-frame feature cache through every causal convolution
 (CACHE_T, :14).  That streaming is equivalent to one pass over the whole sequence (proved against the unmodified reference
@@ -13,8 +13,12 @@ by oracle/gen_golden_wan_vae.py, 0.0 difference in fp64), which is what runs her
     output channels are interleaved into time (:140-143);
   * RMS_norm + SiLU: one memory-bound kernel; the single 384-wide attention head of the middle block: two GEMMs around a row
     softmax (per frame).
-Encode (`WanVAE.encode`) is SURVEY §8f#3 and raises NotImplementedError.  Same state_dict keys as `WanVAE_` (conv2.*,
-decoder.*); encoder keys are ignored.
+Encode: the reference streams chunks of 1, 4, 4, ... frames; as one pass (oracle/wan_vae_oracle.py, exact in fp64):
+  * Resample('downsample2d'|'downsample3d'): ZeroPad2d((0,1,0,1)) + Conv2d(3, stride 2) = the same implicit-GEMM kernel with a
+    striding TMA box and taps (h, h+1, h+2) (`ltxb200_conv_taps_strided_bf16`, off_hw = 1); `time_conv` (3,1,1) stride 2 =
+    the temporal-stride variant, whose output frame 0 is replaced by the bypassed first frame (:150-165);
+  * the 3 input channels are zero-padded to 64 (one k-block per tap).
+Same state_dict keys as `WanVAE_` (conv1.*, conv2.*, encoder.*, decoder.*); either half may be absent.
 """
 from __future__ import annotations
 
@@ -68,6 +72,20 @@ class WanVAE:
                 out.append(("up3d" if self.temperal_upsample[i] else "up2d", cout))
         return out
 
+    def _enc_layout(self):
+        """Encoder3d.downsamples (vae.py:302-318)"""
+        dm = self.dim_mult
+        dims = [self.dim * u for u in [1] + dm]
+        tdown = self.temperal_upsample[::-1]
+        out = []
+        for i, (cin, cout) in enumerate(zip(dims[:-1], dims[1:])):
+            for _ in range(self.num_res_blocks):
+                out.append(("res", cin, cout))
+                cin = cout
+            if i != len(dm) - 1:
+                out.append(("down3d" if tdown[i] else "down2d", cout))
+        return out
+
     def load_state_dict(self, sd: Dict[str, torch.Tensor], device=None, strict: bool = True):
         dev = self.device = torch.device(device) if device is not None else self.device
         w: Dict[str, torch.Tensor] = {}
@@ -99,6 +117,25 @@ class WanVAE:
                 conv(p + "shortcut")
 
         d0 = self.dim * self.dim_mult[-1]
+        if "encoder.conv1.weight" in sd:
+            conv("encoder.conv1")
+            for i, ent in enumerate(self._enc_layout()):
+                p = f"encoder.downsamples.{i}."
+                if ent[0] == "res":
+                    res(p, ent[1], ent[2])
+                else:
+                    conv(p + "resample.1")
+                    if ent[0] == "down3d":
+                        conv(p + "time_conv")
+            res("encoder.middle.0.", d0, d0)
+            gamma("encoder.middle.1.norm"); conv("encoder.middle.1.to_qkv"); conv("encoder.middle.1.proj")
+            res("encoder.middle.2.", d0, d0)
+            gamma("encoder.head.0"); conv("encoder.head.2"); conv("conv1")
+        if "decoder.conv1.weight" not in sd:
+            if strict and "encoder.conv1.weight" not in sd:
+                raise KeyError("state_dict holds neither encoder.* nor decoder.* keys")
+            self.w = w
+            return [], []
         conv("conv2"); conv("decoder.conv1")
         res("decoder.middle.0.", d0, d0)
         gamma("decoder.middle.1.norm"); conv("decoder.middle.1.to_qkv"); conv("decoder.middle.1.proj")
@@ -188,5 +225,41 @@ class WanVAE:
             raise NotImplementedError("any_end_frame decoding is out of scope")
         return [self.decode_one(u) for u in zs]
 
-    def encode(self, *a, **k):
-        raise NotImplementedError("Wan VAE encode is SURVEY §8f#3")
+    def _downsample(self, p, x, mode):
+        """Resample('downsample2d'|'downsample3d') (vae.py:90-97, 150-165) over the whole sequence."""
+        y = ops.conv_taps_strided(x, self.w[p + "resample.1.w"], self.w[p + "resample.1.b"], 1, 3, 1, 2, off_hw=1)
+        if mode == "down3d" and y.shape[1] > 1:
+            z = ops.conv_taps_strided(y, self.w[p + "time_conv.w"], self.w[p + "time_conv.b"], 3, 1, 2, 1)
+            z[:, 0] = y[:, 0]                      # the first chunk (one frame) bypasses time_conv and only seeds its cache
+            y = z
+        return y
+
+    @torch.no_grad()
+    def encode_one(self, video: torch.Tensor) -> torch.Tensor:
+        """video [3, 1+4k, H, W] in [-1, 1] -> mu [z_dim, 1+k, H/8, W/8] float32, (mu - mean) / std (vae.py:566-575)."""
+        if "encoder.conv1.w" not in self.w:
+            raise RuntimeError("WanVAE.encode: no encoder weights were loaded (load_state_dict with encoder.* / conv1.* keys)")
+        dev = self.device
+        c3, T, H, W = video.shape
+        if (T - 1) % 4:
+            raise ValueError("WanVAE.encode: the reference's 1,4,4,... chunking needs 1 + 4k frames")
+        xp = torch.zeros(1, T, H, W, 64, device=dev, dtype=BF16)
+        xp[0, ..., :c3] = video.to(dev).permute(1, 2, 3, 0).to(BF16)
+        x = self._conv("encoder.conv1", xp)
+        for i, ent in enumerate(self._enc_layout()):
+            p = f"encoder.downsamples.{i}."
+            x = self._res(p, x, ent[1], ent[2]) if ent[0] == "res" else self._downsample(p, x, ent[0])
+        d0 = self.dim * self.dim_mult[-1]
+        x = self._res("encoder.middle.0.", x, d0, d0)
+        x = self._attn("encoder.middle.1.", x, d0)
+        x = self._res("encoder.middle.2.", x, d0, d0)
+        x = self._conv("encoder.head.2", ops.l2norm_silu(x, self.w["encoder.head.0"], d0))
+        x = self._conv("conv1", x)                                                                  # [1, T', H', W', 64]
+        mu = x[0, ..., : self.z_dim].permute(3, 0, 1, 2).float()
+        return (mu - self.mean.to(dev).view(-1, 1, 1, 1)) * (1.0 / self.std).to(dev).view(-1, 1, 1, 1)
+
+    def encode(self, videos: List[torch.Tensor], tile_size: int = 0, any_end_frame: bool = False) -> List[torch.Tensor]:
+        """vae.py:806-816.  tile_size is accepted and ignored (see decode)."""
+        if any_end_frame:
+            raise NotImplementedError("any_end_frame encoding is out of scope")
+        return [self.encode_one(u) for u in videos]

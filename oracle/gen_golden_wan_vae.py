@@ -27,7 +27,8 @@ def build_ref(cfg, sd):
     m = WanVAE_(dim=cfg["dim"], z_dim=cfg["z_dim"], dim_mult=cfg["dim_mult"], num_res_blocks=cfg["num_res_blocks"], attn_scales=[],
                 temperal_downsample=cfg["temperal_upsample"][::-1], dropout=0.0)
     own = m.state_dict()
-    missing = [k for k in own if (k.startswith("decoder.") or k.startswith("conv2.")) and k not in sd]
+    pre = ("decoder.", "conv2.") if "conv2.weight" in sd else ("encoder.", "conv1.")
+    missing = [k for k in own if k.startswith(pre) and k not in sd]
     assert not missing, missing
     unexpected = [k for k in sd if k not in own]
     assert not unexpected, unexpected
@@ -53,6 +54,25 @@ def main():
         assert y.shape == (3, 13, 48, 80) and e < tol
     torch.save(dict(cfg=cfg, seed_weights=0, z=z.float(), out=y_ref.half()), os.path.join(GOLD, "wan_vae_decode.pt"))
     print("written", os.path.join(GOLD, "wan_vae_decode.pt"))
+
+    # ---- encode: the reference streams chunks of 1, 4, 4, ... frames with its feature caches (WanVAE_.encode :536-575)
+    sd = V.make_wan_vae_encoder_state_dict(cfg, seed=1)
+    for dtype, tol in ((torch.float64, 1e-9), (torch.float32, 2e-5)):
+        sdd = {k: v.to(dtype) for k, v in sd.items()}
+        ref = build_ref(cfg, sdd).to(dtype)
+        g = torch.Generator().manual_seed(11)
+        for shape in ((3, 9, 48, 80), (3, 1, 32, 48), (3, 13, 32, 32)):
+            video = (torch.rand(*shape, generator=g) * 2 - 1).to(dtype)
+            mean, std = torch.tensor(V.WAN_VAE_MEAN, dtype=dtype), torch.tensor(V.WAN_VAE_STD, dtype=dtype)
+            mu_ref = ref.encode(video.unsqueeze(0), [mean, 1.0 / std]).float().squeeze(0)                # WanVAE.encode (:806-816), tile_size 0
+            mu = V.wan_vae_encode(sdd, video, cfg, mean, std)
+            e = rel_l2(mu, mu_ref)
+            print(f"  wan vae encode ({dtype}) {shape}: out {tuple(mu.shape)}, rel_l2(oracle one-pass, reference streaming) = {e:.3e}")
+            assert mu.shape == (16, 1 + (shape[1] - 1) // 4, shape[2] // 8, shape[3] // 8) and e < tol
+            if shape[1] == 9:
+                keep = dict(video=video.float(), mu=mu_ref.float())
+    torch.save(dict(cfg=cfg, seed_weights=1, **keep), os.path.join(GOLD, "wan_vae_encode.pt"))
+    print("written", os.path.join(GOLD, "wan_vae_encode.pt"))
 
 
 if __name__ == "__main__":

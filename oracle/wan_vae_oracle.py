@@ -1,4 +1,4 @@
-"""CPU oracle for the Wan2.1 VAE decode (TEST INFRASTRUCTURE ONLY — see ltx_oracle.py header).
+"""CPU oracle for the Wan2.1 VAE decode and encode (TEST INFRASTRUCTURE ONLY — see ltx_oracle.py header).
 
 Plain-PyTorch restatement of WanVAE.decode -> WanVAE_.decode -> Decoder3d (wan/modules/vae.py:386-493,578-609,
 825-829) as ONE pass over the whole latent sequence.  The reference decodes one latent frame per call and threads a
@@ -10,6 +10,13 @@ feature cache through every causal convolution (CACHE_T = 2, :14, :210-227); tha
   * spatial part: nearest(-exact) x2 upsample in fp32 + Conv2d 3x3 per frame (:80-88);
   * RMS_norm = F.normalize(x, dim=channel) * sqrt(C) * gamma (:41-58);  AttentionBlock = per-frame single-head
     attention over h*w tokens with head dim C (:234-272).
+Encode (WanVAE.encode -> WanVAE_.encode -> Encoder3d, :275-383, 536-575, 806-816): the reference feeds chunks of 1, 4, 4, ...
+frames through the encoder with the same 2-frame caches; as ONE pass:
+  * Resample('downsample2d'|'downsample3d') (:90-97): per frame ZeroPad2d((0,1,0,1)) + Conv2d(3, stride 2);
+  * 'downsample3d' (:150-165): the FIRST frame bypasses `time_conv` (it only seeds the cache); every later chunk runs
+    CausalConv3d((3,1,1), stride (2,1,1)) over [last frame of the previous chunk, chunk], so output frame m >= 1 reads
+    input frames (2m-2, 2m-1, 2m): T -> 1 + (T-1)/2;
+  * mu = first z_dim channels of conv1(encoder(x)); returned as (mu - mean) / std (:566-575).
 Pinned by oracle/gen_golden_wan_vae.py against the unmodified reference run in its own streaming mode.
 """
 from __future__ import annotations
@@ -150,3 +157,91 @@ def wan_vae_decode(sd: Dict[str, Tensor], z: Tensor, cfg=WAN_VAE, mean: Optional
         x = res_block(sd, p, x) if ent[0] == "res" else resample(sd, p, x, ent[0])
     x = causal_conv3d(F.silu(rms_norm(x, sd["decoder.head.0.gamma"])), sd["decoder.head.2.weight"], sd["decoder.head.2.bias"])
     return x.clamp(-1, 1).float().squeeze(0)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# encode
+# ---------------------------------------------------------------------------------------------------------------------
+def encoder_layout(cfg) -> List[tuple]:
+    """The module list of Encoder3d.downsamples (vae.py:302-318) as ('res', cin, cout) / ('down3d'|'down2d', c) entries."""
+    dm = cfg["dim_mult"]
+    dims = [cfg["dim"] * u for u in [1] + dm]
+    tdown = cfg["temperal_upsample"][::-1]
+    out = []
+    for i, (cin, cout) in enumerate(zip(dims[:-1], dims[1:])):
+        for _ in range(cfg["num_res_blocks"]):
+            out.append(("res", cin, cout))
+            cin = cout
+        if i != len(dm) - 1:
+            out.append(("down3d" if tdown[i] else "down2d", cout))
+    return out
+
+
+def make_wan_vae_encoder_state_dict(cfg=WAN_VAE, seed: int = 0) -> Dict[str, Tensor]:
+    """Seeded random init with the reference key names (WanVAE_: conv1.*, encoder.*); AttentionBlock.proj overridden as above."""
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, Tensor] = {}
+
+    def conv(name, cout, cin, k):
+        fan = cin * math.prod(k)
+        sd[name + ".weight"] = (torch.rand(cout, cin, *k, generator=g) * 2 - 1) / math.sqrt(fan)
+        sd[name + ".bias"] = (torch.rand(cout, generator=g) * 2 - 1) / math.sqrt(fan)
+
+    def gamma(name, c, images):
+        sd[name + ".gamma"] = (1.0 + 0.1 * torch.randn(c, generator=g)).view(c, *([1, 1] if images else [1, 1, 1]))
+
+    def res(p, cin, cout):
+        gamma(p + "residual.0", cin, False); conv(p + "residual.2", cout, cin, (3, 3, 3))
+        gamma(p + "residual.3", cout, False); conv(p + "residual.6", cout, cout, (3, 3, 3))
+        if cin != cout:
+            conv(p + "shortcut", cout, cin, (1, 1, 1))
+
+    z = cfg["z_dim"]
+    conv("encoder.conv1", cfg["dim"], 3, (3, 3, 3))
+    c = cfg["dim"]
+    for i, ent in enumerate(encoder_layout(cfg)):
+        p = f"encoder.downsamples.{i}."
+        if ent[0] == "res":
+            res(p, ent[1], ent[2]); c = ent[2]
+        else:
+            conv(p + "resample.1", c, c, (3, 3))
+            if ent[0] == "down3d":
+                conv(p + "time_conv", c, c, (3, 1, 1))
+    res("encoder.middle.0.", c, c)
+    gamma("encoder.middle.1.norm", c, True)
+    conv("encoder.middle.1.to_qkv", 3 * c, c, (1, 1)); conv("encoder.middle.1.proj", c, c, (1, 1))
+    res("encoder.middle.2.", c, c)
+    gamma("encoder.head.0", c, False)
+    conv("encoder.head.2", 2 * z, c, (3, 3, 3))
+    conv("conv1", 2 * z, 2 * z, (1, 1, 1))
+    return sd
+
+
+def downsample(sd, p, x: Tensor, mode: str) -> Tensor:
+    b, c, t, h, w = x.shape
+    y = x.permute(0, 2, 1, 3, 4).reshape(b * t, c, h, w)
+    y = F.conv2d(F.pad(y, (0, 1, 0, 1)), sd[p + "resample.1.weight"], sd[p + "resample.1.bias"], stride=2)      # :90-93
+    y = y.reshape(b, t, c, y.shape[-2], y.shape[-1]).permute(0, 2, 1, 3, 4)
+    if mode == "down3d" and t > 1:
+        z = F.conv3d(y, sd[p + "time_conv.weight"], sd[p + "time_conv.bias"], stride=(2, 1, 1))                  # frames (2m-2, 2m-1, 2m)
+        y = torch.cat([y[:, :, :1], z], dim=2)
+    return y
+
+
+def wan_vae_encode(sd: Dict[str, Tensor], video: Tensor, cfg=WAN_VAE, mean: Optional[Tensor] = None, std: Optional[Tensor] = None) -> Tensor:
+    """WanVAE.encode for one video (vae.py:536-575, 806-816, tile_size 0): video [3, 1+4k, H, W] in [-1, 1] ->
+    mu [z_dim, 1+k, H/8, W/8] float32, normalised with (mu - mean) / std."""
+    assert (video.shape[1] - 1) % 4 == 0, "the reference's 1,4,4,... chunking drops trailing frames otherwise"
+    x = video.unsqueeze(0)
+    x = causal_conv3d(x, sd["encoder.conv1.weight"], sd["encoder.conv1.bias"])
+    for i, ent in enumerate(encoder_layout(cfg)):
+        p = f"encoder.downsamples.{i}."
+        x = res_block(sd, p, x) if ent[0] == "res" else downsample(sd, p, x, ent[0])
+    x = res_block(sd, "encoder.middle.0.", x)
+    x = attention_block(sd, "encoder.middle.1.", x)
+    x = res_block(sd, "encoder.middle.2.", x)
+    x = causal_conv3d(F.silu(rms_norm(x, sd["encoder.head.0.gamma"])), sd["encoder.head.2.weight"], sd["encoder.head.2.bias"])
+    mu = causal_conv3d(x, sd["conv1.weight"], sd["conv1.bias"])[:, : cfg["z_dim"]]
+    if mean is not None:
+        mu = (mu - mean.view(1, -1, 1, 1, 1).to(mu.dtype)) * (1.0 / std).view(1, -1, 1, 1, 1).to(mu.dtype)
+    return mu.float().squeeze(0)

@@ -2,6 +2,7 @@
 recorded from the UNMODIFIED reference modules (fp32, CPU)."""
 import os
 
+import pytest
 import torch
 
 from oracle import ltx_oracle as O
@@ -102,6 +103,23 @@ def test_wan_vae_decode_oracle_matches_reference(golden_dir):
     y = V.wan_vae_decode(sd, g["z"], g["cfg"], torch.tensor(V.WAN_VAE_MEAN), torch.tensor(V.WAN_VAE_STD))
     assert y.shape == (3, 13, 48, 80)
     assert O.rel_l2(y, g["out"].float()) < 2e-3      # fixture stored as fp16
+
+
+def test_wan_vae_encode_oracle_matches_reference(golden_dir):
+    """The one-pass Wan VAE encode oracle vs the fixture recorded from the unmodified reference's chunked (1, 4, 4, ...) streaming
+    encode (oracle/gen_golden_wan_vae.py: identical in fp64, 1.7e-7 in fp32); a single image and odd spatial sizes too."""
+    from oracle import wan_vae_oracle as V
+    g = _load(golden_dir, "wan_vae_encode.pt")
+    sd = V.make_wan_vae_encoder_state_dict(g["cfg"], seed=g["seed_weights"])
+    mean, std = torch.tensor(V.WAN_VAE_MEAN), torch.tensor(V.WAN_VAE_STD)
+    mu = V.wan_vae_encode(sd, g["video"], g["cfg"], mean, std)
+    assert mu.shape == (16, 3, 6, 10)
+    assert O.rel_l2(mu, g["mu"]) < 1e-5
+    # causality of the one-pass form: the first latent frame depends on the first video frame only (the reference's first chunk)
+    mu1 = V.wan_vae_encode(sd, g["video"][:, :1], g["cfg"], mean, std)
+    assert O.rel_l2(mu1, mu[:, :1]) < 1e-5
+    with pytest.raises(AssertionError):
+        V.wan_vae_encode(sd, g["video"][:, :7], g["cfg"], mean, std)
 
 
 def test_vae_encode_oracle_matches_reference(golden_dir):

@@ -76,3 +76,44 @@ def test_wan_vae_decode_vs_reference_fixture(golden_dir):
     mean, std = torch.tensor(V.WAN_VAE_MEAN), torch.tensor(V.WAN_VAE_STD)
     yo = V.wan_vae_decode(sd, g["z"], cfg, mean, std)
     assert psnr(y.cpu() * 0.5 + 0.5, yo * 0.5 + 0.5) >= 40.0
+
+
+@pytest.mark.parametrize("kt,khw,st,shw,off,H,W", [(1, 3, 1, 2, 1, 12, 20), (1, 3, 1, 2, 1, 9, 13), (3, 1, 2, 1, 0, 6, 10), (3, 3, 1, 1, 0, 5, 7)])
+def test_conv_taps_strided(kt, khw, st, shw, off, H, W):
+    """Wan encoder Resample pieces (vae.py:90-97,150-165): ZeroPad2d((0,1,0,1)) + Conv2d stride 2; time_conv stride (2,1,1)."""
+    B, T, Cin, Cout = 1, 9, 64, 128
+    x = rnd(B, T, H, W, Cin, seed=1)
+    w5 = rnd(Cout, Cin, kt, khw, khw, seed=2, scale=(kt * khw * khw * Cin) ** -0.5)
+    b = rnd(Cout, seed=3)
+    xr = x.float().permute(0, 4, 1, 2, 3)
+    lo = khw // 2 - off
+    xr = F.pad(xr, (lo, khw // 2, lo, khw // 2, kt - 1, 0))
+    ref = F.conv3d(xr, w5.float(), b.float(), stride=(st, shw, shw)).permute(0, 2, 3, 4, 1)
+    out = ops.conv_taps_strided(x, w5.permute(0, 2, 3, 4, 1).reshape(Cout, -1).contiguous(), b, kt, khw, st, shw, off)
+    torch.cuda.synchronize()
+    assert tuple(out.shape) == tuple(ref.shape)
+    assert rel_l2(out.float().cpu(), ref.cpu()) < 6e-3
+
+
+def test_wan_vae_encode_vs_reference_fixture(golden_dir):
+    g = torch.load(os.path.join(golden_dir, "wan_vae_encode.pt"), weights_only=False)
+    cfg = g["cfg"]
+    sd = V.make_wan_vae_encoder_state_dict(cfg, seed=g["seed_weights"])
+    vae = WanVAE(dim=cfg["dim"], dim_mult=cfg["dim_mult"], num_res_blocks=cfg["num_res_blocks"],
+                 temperal_downsample=cfg["temperal_upsample"][::-1])
+    vae.load_state_dict(sd)
+    mu = vae.encode([g["video"].to(DEV)], tile_size=0)[0]
+    torch.cuda.synchronize()
+    assert tuple(mu.shape) == tuple(g["mu"].shape) == (16, 3, 6, 10)
+    e = rel_l2(mu.cpu(), g["mu"])
+    print(f"wan vae encode: rel_l2 vs reference fixture = {e:.3e}")
+    assert e < 2e-2
+    # single image (the i2v conditioning frame) and the first-frame causality of the one-pass form
+    mu1 = vae.encode([g["video"][:, :1].to(DEV)])[0]
+    assert rel_l2(mu1.cpu(), g["mu"][:, :1]) < 2e-2
+    with pytest.raises(ValueError):
+        vae.encode([g["video"][:, :7].to(DEV)])
+    with pytest.raises(RuntimeError):
+        v2 = WanVAE(dim=cfg["dim"], dim_mult=cfg["dim_mult"], num_res_blocks=cfg["num_res_blocks"], temperal_downsample=cfg["temperal_upsample"][::-1])
+        v2.load_state_dict(V.make_wan_vae_decoder_state_dict(cfg, seed=0))
+        v2.encode([g["video"].to(DEV)])
