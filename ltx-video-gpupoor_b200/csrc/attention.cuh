@@ -94,27 +94,35 @@ DEVI void rescale_o(uint32_t tO, bool need, float m_new, float& m_ref, float& l,
   }
 }
 
-// exp2 of 32 scores (already in registers) -> 16 packed bf16 pairs at tP, partial row sums in ls[4]
-template <bool kScaled>
-DEVI void exp_chunk(const uint32_t* v, float sc, float neg_m, uint32_t tP, float (&ls)[4]) {
+// exp2 of 32 scores (already in registers) -> 16 packed bf16 pairs at tP, partial row sums in ls[2] (packed fp32 pairs).
+// The scale/shift and the row sum run as FFMA2 / FADD2 (half the issue slots of the scalar form), and kPolyPer8 of every
+// 8 element pairs take their exponentials from the FMA-pipe polynomial instead of MUFU.EX2, which is what bounds the
+// d = 64 kernel (profiles/scripts/mufu_bench2.cu: 14.3 -> 18.0 exp/clk/SM at 2 softmax warps per scheduler).
+#ifndef LTXB200_ATTN_POLY
+#define LTXB200_ATTN_POLY 2
+#endif
+template <bool kScaled, int kPolyPer8>
+DEVI void exp_chunk(const uint32_t* v, float sc, float neg_m, uint32_t tP, uint64_t (&ls)[2]) {
   uint32_t pk[16];
+  const uint64_t NM = pack_f32x2(neg_m, neg_m);
+  const uint64_t SC = pack_f32x2(sc, sc);
 #pragma unroll
-  for (int i = 0; i < 32; i += 4) {
-    float e0, e1, e2, e3;
-    if (kScaled) {       // v already holds scale*s + bias
-      e0 = fast_exp2(__uint_as_float(v[i]) + neg_m);
-      e1 = fast_exp2(__uint_as_float(v[i + 1]) + neg_m);
-      e2 = fast_exp2(__uint_as_float(v[i + 2]) + neg_m);
-      e3 = fast_exp2(__uint_as_float(v[i + 3]) + neg_m);
+  for (int p = 0; p < 16; ++p) {
+    const uint64_t V = pack_u32x2(v[2 * p], v[2 * p + 1]);
+    const uint64_t X = kScaled ? add_f32x2(V, NM)        // v already holds scale*s + bias
+                               : fma_f32x2(V, SC, NM);
+    float e0, e1;
+    const bool poly = !kScaled && (((p & 7) + 1) * kPolyPer8 / 8 != (p & 7) * kPolyPer8 / 8);   // spread over the 8 pairs
+    if (poly) {
+      exp2_poly_f32x2(X, e0, e1);
     } else {
-      e0 = fast_exp2(fmaf(__uint_as_float(v[i]), sc, neg_m));
-      e1 = fast_exp2(fmaf(__uint_as_float(v[i + 1]), sc, neg_m));
-      e2 = fast_exp2(fmaf(__uint_as_float(v[i + 2]), sc, neg_m));
-      e3 = fast_exp2(fmaf(__uint_as_float(v[i + 3]), sc, neg_m));
+      float x0, x1;
+      unpack_f32x2(X, x0, x1);
+      e0 = fast_exp2(x0);
+      e1 = fast_exp2(x1);
     }
-    ls[0] += e0; ls[1] += e1; ls[2] += e2; ls[3] += e3;
-    pk[i >> 1] = pack_bf16(e0, e1);
-    pk[(i >> 1) + 1] = pack_bf16(e2, e3);
+    ls[p & 1] = add_f32x2(ls[p & 1], pack_f32x2(e0, e1));
+    pk[p] = pack_bf16(e0, e1);
   }
   tmem_st16(tP, pk);
 }
@@ -182,10 +190,10 @@ DEVI void softmax_block(uint32_t tS, uint32_t tO, bool first, int kbase, int Lk,
     m_run = fmaxf(m_run, m_blk);
     rescale_o<D>(tO, m_run > m_ref + 8.0f, m_run, m_ref, l, pv_done, pv_parity);
   }
-  float ls[4] = {0.f, 0.f, 0.f, 0.f};
+  uint64_t ls[2] = {0ull, 0ull};
 #pragma unroll
   for (int c = 0; c < BN; c += 32) {
-    exp_chunk<kPredicated>(&v[c], sc, -m_ref, tS + (c >> 1), ls);
+    exp_chunk<kPredicated, LTXB200_ATTN_POLY>(&v[c], sc, -m_ref, tS + (c >> 1), ls);
     if (p_half && c + 32 == BN / 2) {            // P of keys 0..BN/2-1 is in TMEM: their P.V may start
       tmem_wait_st();
       tc_fence_before();
@@ -193,7 +201,9 @@ DEVI void softmax_block(uint32_t tS, uint32_t tO, bool first, int kbase, int Lk,
       if (lane == 0) mbar_arrive(p_half);
     }
   }
-  l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+  float l0, l1;
+  unpack_f32x2(add_f32x2(ls[0], ls[1]), l0, l1);
+  l += l0 + l1;
 }
 
 template <int D, bool kMasked>
