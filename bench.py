@@ -225,6 +225,15 @@ def run_wan(args, wl):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
+    cfgp = None
+    use_cfgp = {"1": True, "0": False}.get(os.environ.get("LTXB200_CFG_PARALLEL", ""), "auto")
+    heads = 12 if wl["model"] == "1.3B" else 40
+    if world > 1 and (use_cfgp is True or (use_cfgp == "auto" and heads % world != 0)):
+        # cond / uncond on two halves of the world, Ulysses inside each half (wan/distributed/cfg_parallel.py):
+        # Wan-1.3B has 12 heads, which 8 ranks cannot split but 2 x 4 can
+        from ltx_video_gpupoor_b200.wan.distributed.cfg_parallel import CfgParallel
+        cfgp = CfgParallel()
+        group = cfgp.sp_group if world > 2 else None
     from ltx_video_gpupoor_b200 import _lib, ops
     from ltx_video_gpupoor_b200.wan.fm_solvers_unipc import FlowUniPCMultistepScheduler
     from ltx_video_gpupoor_b200.wan.model import WAN_T2V_1_3B, WAN_T2V_14B, WanModel
@@ -272,7 +281,11 @@ def run_wan(args, wl):
     def run_steps(lat, ctx, ctx0, sch, idx):
         for i in idx:
             t = sch.timesteps_host[i]
-            c, uu = model([lat, lat], t=torch.tensor([t], device=dev), context=[ctx, ctx0], freqs=freqs)
+            if cfgp is not None:
+                c, uu = cfgp.exchange(model([lat], t=torch.tensor([t], device=dev), context=[cfgp.select(ctx, ctx0)], freqs=freqs,
+                                            x_id=cfgp.branch)[0])
+            else:
+                c, uu = model([lat, lat], t=torch.tensor([t], device=dev), context=[ctx, ctx0], freqs=freqs)
             pred = ops.cfg_combine(c.contiguous(), uu.contiguous(), wl["guide_scale"], use_alpha=i > 5, scratch=scratch)
             lat = sch.step(pred.unsqueeze(0), t, lat.unsqueeze(0), return_dict=False)[0].squeeze(0)
         return lat
@@ -375,7 +388,8 @@ def run_wan(args, wl):
                 "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": args.workload, "model": f"Wan2.1-T2V-{wl['model']} (random-init, {cfg['num_layers']} layers)",
                            "latent": list(shape), "tokens": shape[1] * shape[2] * shape[3] // 4, "schedule_steps": S,
-                           "forwards_per_step": 2, "parallelism": f"ulysses sp{world}",
+                           "forwards_per_step": 2,
+                           "parallelism": (f"cfg-parallel 2 x ulysses sp{world // 2}" if cfgp is not None else f"ulysses sp{world}"),
                            "sp_exchange": (os.environ.get("LTXB200_SP_EXCHANGE", "p2p") + (" (fused peer-memory stores over NVLink)" if os.environ.get("LTXB200_SP_EXCHANGE", "p2p") == "p2p" else " (all_to_all_single)")) if world > 1 else None,
                            "l2_policy": "per-step working set (weights + activations) far exceeds the 126 MB L2"},
                 "e2e": {"value": K / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": (noise_h.numel() * 4 + 2 * ctx_h.numel() * 2) / K,

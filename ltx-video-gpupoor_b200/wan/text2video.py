@@ -36,7 +36,7 @@ class WanT2V:
                  slg_layers=None, slg_start=0.0, slg_end=1.0, cfg_star_switch=True, cfg_zero_step=5,
                  overlapped_latents=None, return_latent_slice=None, overlap_noise=0, conditioning_latents_size=0,
                  model_filename=None, context: Optional[torch.Tensor] = None, context_null: Optional[torch.Tensor] = None,
-                 noise: Optional[torch.Tensor] = None, _per_step_latents=None, **bbargs):
+                 noise: Optional[torch.Tensor] = None, _per_step_latents=None, cfg_parallel=None, **bbargs):
         if input_frames is not None or input_ref_images is not None or target_camera is not None or overlapped_latents is not None:
             raise NotImplementedError("VACE / phantom / recam inputs are out of scope")
         if context is None or (guide_scale != 1 and context_null is None):
@@ -76,6 +76,14 @@ class WanT2V:
                 pred = self.model([latents], t=ts, context=[ctx], freqs=freqs, pipeline=self, current_step=i, slg_layers=slg)[0]
                 if pred is None:
                     return None
+            elif cfg_parallel is not None:
+                # cond on one half of the ranks, uncond on the other (distributed/cfg_parallel.py), one 2-rank all-gather
+                mine = self.model([latents], t=ts, context=[cfg_parallel.select(ctx, ctx0)], freqs=freqs, pipeline=self,
+                                  current_step=i, x_id=cfg_parallel.branch, slg_layers=slg)[0]     # x_id 1 = the unconditional pass (:1077)
+                if mine is None:
+                    return None
+                c, u = cfg_parallel.exchange(mine)
+                pred = ops.cfg_combine(c, u, guide_scale, use_alpha=bool(cfg_star_switch and i > cfg_zero_step), scratch=scratch)
             else:
                 # cond and uncond sequences in one batched forward (the reference's joint_pass list call, :509)
                 c, u = self.model([latents, latents], t=ts, context=[ctx, ctx0], freqs=freqs, pipeline=self, current_step=i,

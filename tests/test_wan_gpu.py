@@ -145,6 +145,45 @@ def test_wan_sequence_parallel_two_gpus(golden_dir):
             assert e < 3e-2
 
 
+def _cfgp_worker(rank, world, port, golden_dir, ret):
+    import torch.distributed as dist
+    from ltx_video_gpupoor_b200.wan.distributed.cfg_parallel import CfgParallel
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        g = _golden(golden_dir)
+        dev = f"cuda:{rank}"
+        cfg = g["cfg"]
+        cp = CfgParallel()
+        m = WanModel(dim=cfg["dim"], ffn_dim=cfg["ffn_dim"], num_heads=cfg["num_heads"], num_layers=cfg["num_layers"],
+                     sp_group=cp.sp_group if world > 2 else None)
+        m.load_state_dict(W.make_wan_state_dict(cfg, seed=0), device=dev)
+        steps = []
+        WanT2V(m, device=dev).generate(width=96, height=64, frame_num=9, shift=5.0, sampling_steps=4, guide_scale=5.0,
+                                       cfg_star_switch=False, context=g["ctx"], context_null=g["ctx0"], noise=g["lat"],
+                                       _per_step_latents=steps, cfg_parallel=cp)
+        torch.cuda.synchronize()
+        ret[rank] = [W.rel_l2(a.cpu(), b) for a, b in zip(steps, g["loop"])]
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_wan_cfg_parallel_loop(golden_dir, world):
+    """cond / uncond forwards on two halves of the ranks (x Ulysses SP inside each half at world 4) vs the single-GPU reference loop."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs (gpurun --gpus {world})")
+    import torch.multiprocessing as mp
+    ret = mp.Manager().dict()
+    mp.spawn(_cfgp_worker, args=(world, 30150 + os.getpid() % 300, golden_dir, ret), nprocs=world, join=True)
+    assert len(ret) == world
+    for r, errs in ret.items():
+        print(f"rank {r}: CFG-parallel loop latents rel_l2 vs reference = {[f'{e:.2e}' for e in errs]}")
+        assert max(errs) < 2e-2
+    assert all(ret[r] == ret[0] for r in ret)          # replicated scheduler state: every rank holds the same latents
+
+
 # ------------------------------------------------------------------ i2v (WanI2VCrossAttention, img_emb, y channels)
 def test_wan_i2v_forward_and_loop_vs_reference_fixture(golden_dir):
     from ltx_video_gpupoor_b200.wan.image2video import WanI2V

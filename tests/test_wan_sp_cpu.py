@@ -46,6 +46,29 @@ def test_ulysses_exchange_two_ranks_gloo():
         assert v < 1e-5, (k, v)
 
 
+def _cfgp_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from ltx_video_gpupoor_b200.wan.distributed.cfg_parallel import CfgParallel
+        cp = CfgParallel()
+        assert cp.branch == rank // (world // 2) and dist.get_world_size(cp.sp_group) == world // 2
+        assert cp.select("cond", "uncond") == ("cond" if rank < world // 2 else "uncond")
+        mine = torch.full((3, 5), float(10 * cp.branch + 1))          # cond half predicts 1, uncond half 11
+        c, u = cp.exchange(mine)
+        ret[rank] = (float(c.mean()), float(u.mean()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_cfg_parallel_groups_and_exchange_gloo():
+    """CfgParallel (distributed/cfg_parallel.py): two branch groups, pairwise exchange ordered (cond, uncond) on every rank."""
+    world = 2
+    ret = mp.Manager().dict()
+    mp.spawn(_cfgp_worker, args=(world, 31500 + (os.getpid() % 2000), ret), nprocs=world, join=True)
+    assert dict(ret) == {0: (1.0, 11.0), 1: (1.0, 11.0)}
+
+
 def test_pack_unpack_are_pure_permutations():
     from ltx_video_gpupoor_b200.wan.distributed import ulysses as U
     B, n_loc, P, H, d = 2, 3, 2, 4, 8
