@@ -509,6 +509,27 @@ def main():
         elapsed = float(t)
     steps_per_s = world * args.steps / elapsed
 
+    # ---------------- extra (NOT the headline): the same steps with share_stg_prefix=True ----------------
+    # the perturbed STG condition's rows are copied from the text condition's rows up to the first skipped block instead of being
+    # recomputed (bit-identical latents: tests/test_ltx_model_gpu.py::test_pipeline_shared_stg_prefix_is_bit_identical)
+    shared = None
+    if wl["num_conds"] == 3 and wl["skip_block_list"]:
+        st.shared_prefix = (1, 1)
+        for i in range(2):
+            pipe.denoise_step(st, i)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(args.steps):
+            pipe.denoise_step(st, (args.warmup + i) % S)
+        b.record()
+        torch.cuda.synchronize()
+        sh_ms = a.elapsed_time(b) / args.steps
+        shared = {"ms_per_step": sh_ms, "steps_per_s": 1e3 / sh_ms,
+                  "note": (f"optional pipeline kwarg share_stg_prefix=True: blocks 0..{min(wl['skip_block_list']) - 1} run for 2 conds, "
+                           "the rest for 3; identical latents; not used for value / e2e")}
+        st.shared_prefix = None
+
     # ---------------- roofline probe: one instrumented step (not part of the timed region) ----------------
     ops.PROFILER = []
     pipe.denoise_step(st, 0)
@@ -604,6 +625,10 @@ def main():
         "model_tflops": wl["num_conds"] * FWD_FLOPS * (args.layers / 28) / (ms_step / 1e3) / 1e12,
         "kernels": kernels,
     }
+    if shared is not None:
+        line["stg_prefix_sharing"] = shared
+        if decode_s is not None:
+            shared["s_per_video"] = S * shared["ms_per_step"] / 1e3 + decode_s
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

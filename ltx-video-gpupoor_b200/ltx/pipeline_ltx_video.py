@@ -161,7 +161,7 @@ class LTXVideoPipeline:
             st.x_in, freqs_cis=st.freqs_cis, encoder_hidden_states=st.enc_b, encoder_attention_mask=st.mask_b,
             timestep=st.t_in, skip_layer_mask=st.skip_layer_masks[i] if st.skip_layer_masks is not None else None,
             skip_layer_strategy=st.skip_layer_strategy, latent_shape=st.latent_shape[2:], joint_pass=st.joint_pass,
-            ltxv_model=st.ltxv_model, return_dict=False)[0]
+            ltxv_model=st.ltxv_model, return_dict=False, shared_prefix=getattr(st, "shared_prefix", None))[0]
         if noise_pred is None:
             return None
         ops.guidance_step(noise_pred.view(num_conds, N * C), st.lat32, st.ts_dev, t, num_conds=num_conds,
@@ -283,7 +283,10 @@ class LTXVideoPipeline:
             freqs_cis=freqs_cis, N=N, C=C, lat32=lat32, lat16=lat16, cmask_dev=cmask_dev, scratch=scratch, x_in=x_in,
             t_in=t_in, latent_shape=latent_shape, joint_pass=joint_pass, ltxv_model=ltxv_model, generator=generator,
             image_cond_noise_scale=image_cond_noise_scale, init_tokens=init_tokens, tokens_shape=tuple(tokens.shape),
-            stochastic_sampling=bool(stochastic_sampling)))
+            stochastic_sampling=bool(stochastic_sampling),
+            # extension (off by default): the perturbed STG condition repeats the text condition's inputs, so its rows are
+            # copies of the text rows until the first skipped block (Transformer3DModel.forward, `shared_prefix`)
+            shared_prefix=(1, int(do_cfg)) if (kwargs.get("share_stg_prefix", False) and do_stg and skip_layer_masks is not None) else None))
         self._state = st
         if kwargs.get("_prepare_only", False):
             return st

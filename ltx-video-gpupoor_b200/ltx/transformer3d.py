@@ -185,7 +185,7 @@ class Transformer3DModel:
                 attention_mask: Optional[torch.Tensor] = None, encoder_attention_mask: Optional[torch.Tensor] = None,
                 skip_layer_mask: Optional[torch.Tensor] = None, skip_layer_strategy: Optional[SkipLayerStrategy] = None,
                 latent_shape=None, joint_pass: bool = True, ltxv_model=None, mixed: bool = False,
-                return_dict: bool = True):
+                return_dict: bool = True, shared_prefix: Optional[tuple] = None):
         """transformer3d.py:328-507.  hidden_states [B,N,C_in]; freqs_cis (cos,sin) [1|B,N,D]; encoder_hidden_states
         [B,L,caption_channels]; timestep [B,1] | [B,N]; encoder_attention_mask [B,L] (1 keep / 0 drop) or bias
         [B,1,L]; skip_layer_mask [layers,B].  `joint_pass=False` (per-sample iteration for offloaded weights,
@@ -250,7 +250,29 @@ class Transformer3DModel:
                 skip_host = skip_layer_mask.to(torch.float32).cpu()                 # foreign mask: one sync per forward
             skip_dev = skip_layer_mask.to(device=dev, dtype=torch.float32).contiguous()
 
+        B_full, first_div = B, 0
+        if shared_prefix is not None:
+            n_dup, src = shared_prefix
+            assert 0 < n_dup and 0 <= src and src + n_dup <= B - n_dup, "shared_prefix: duplicates must trail their sources"
+            first_div = len(self.layers)
+            if skip_host is not None:
+                differs = (skip_host[:, B - n_dup:] != skip_host[:, src:src + n_dup]).any(dim=1)
+                if bool(differs.any()):
+                    first_div = int(differs.float().argmax())
+            if first_div > 0:
+                B = B_full - n_dup
+                x = x[: B * N]
+
+        def expand(x):
+            return torch.cat([x, x[src * N:(src + n_dup) * N]], dim=0)
+
         for li, Lw in enumerate(self.layers):
+            if B != B_full and li == first_div:
+                x, B = expand(x), B_full
+            if B != B_full:
+                ctx_l, key_bias_l = ctx[: B * Lc], (key_bias[:B] if key_bias is not None else None)
+            else:
+                ctx_l, key_bias_l = ctx, key_bias
             a = ada[li]                                                             # [B*T, 6, D]
             layer_skip = skip_host is not None and float(skip_host[li].min()) != 1.0
             x_orig = x.clone() if (layer_skip and skip_layer_strategy == SkipLayerStrategy.TransformerBlock) else None
@@ -263,26 +285,28 @@ class Transformer3DModel:
             v4 = qkv.view(B, N, 3 * D)[:, :, 2 * D:].unflatten(-1, (H, dh))
             o = ops.attention(q4, k4, v4)                                           # [B, N, H, dh]
             if layer_skip and skip_layer_strategy == SkipLayerStrategy.AttentionValues:
-                ops.stg_blend(o.view(B, N, D), qkv[:, 2 * D:], skip_dev[li])        # :1134-1139
+                ops.stg_blend(o.view(B, N, D), qkv[:, 2 * D:], skip_dev[li][:B])        # :1134-1139
             elif layer_skip and skip_layer_strategy == SkipLayerStrategy.AttentionSkip:
-                ops.stg_blend(o.view(B, N, D), nh, skip_dev[li])                    # :1127-1133
+                ops.stg_blend(o.view(B, N, D), nh, skip_dev[li][:B])                    # :1127-1133
             ops.gemm(o.view(B * N, D), Lw["o.w"], Lw["o.b"], residual=x, gate=a[:, 2], rows_per_gate=rows_per_group, out=x)
             # ---- cross attention (attention.py:294-311): query from the raw residual stream, no RoPE
             q2 = ops.gemm(x, Lw["q2.w"], Lw["q2.b"])
-            kv = ops.gemm(ctx, Lw["kv2.w"], Lw["kv2.b"])                            # [B*Lc, 2D]
+            kv = ops.gemm(ctx_l, Lw["kv2.w"], Lw["kv2.b"])                          # [B*Lc, 2D]
             ops.qk_norm_rope(q2, kv[:, :D], Lw["qn2"], Lw["kn2"], None, None, eps=1e-5)
             o2 = ops.attention(q2.view(B, N, H, dh), kv.view(B, Lc, 2 * D)[:, :, :D].unflatten(-1, (H, dh)),
-                               kv.view(B, Lc, 2 * D)[:, :, D:].unflatten(-1, (H, dh)), key_bias=key_bias)
+                               kv.view(B, Lc, 2 * D)[:, :, D:].unflatten(-1, (H, dh)), key_bias=key_bias_l)
             ops.gemm(o2.view(B * N, D), Lw["o2.w"], Lw["o2.b"], residual=x, out=x)
             # ---- feed forward (attention.py:314-351)
             nh = ops.norm_mod(x, a[:, 4], a[:, 3], rows_per_group=rows_per_group, eps=self.config.norm_eps)
             ff = ops.gemm(nh, Lw["ff1.w"], Lw["ff1.b"], act=ops.ACT_GELU_TANH)
             ops.gemm(ff, Lw["ff2.w"], Lw["ff2.b"], residual=x, gate=a[:, 5], rows_per_gate=rows_per_group, out=x)
             if x_orig is not None:
-                ops.stg_blend(x.view(B, N, D), x_orig, skip_dev[li])               # :355-362
+                ops.stg_blend(x.view(B, N, D), x_orig, skip_dev[li][:B])               # :355-362
             if ltxv_model is not None and getattr(ltxv_model, "_interrupt", False):
                 return [None]
 
+        if B != B_full:
+            x, B = expand(x), B_full
         # --- output head (:490-503)
         fin = ops.ada_add(w["final_table"], torch.cat([emb, emb], dim=1))           # [1, B*T, 2, D]
         y = ops.norm_mod(x, fin[0][:, 1], fin[0][:, 0], rows_per_group=rows_per_group, eps=1e-6, layer_norm=True)

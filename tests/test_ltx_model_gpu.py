@@ -115,6 +115,31 @@ def test_pipeline_latents_vs_reference_fixture(golden_dir):
         assert err < 3e-2
 
 
+def test_pipeline_shared_stg_prefix_is_bit_identical(golden_dir):
+    """share_stg_prefix=True (the perturbed condition's rows are copied from the text condition's rows up to the first skipped
+    block instead of being recomputed) must not change a single bit of any step's latents; every skip strategy."""
+    g = _load(golden_dir, "ltx_pipeline.pt")
+    meta = g["meta"]
+    pipe, _, _ = _pipe(meta["num_layers"])
+    kw = dict(g["cfg_stg"]["kw"])
+    for strat in (SkipLayerStrategy.AttentionValues, SkipLayerStrategy.AttentionSkip, SkipLayerStrategy.TransformerBlock):
+        kw["skip_layer_strategy"] = strat
+        for blocks in ([meta["num_layers"] - 1], [0], [1, meta["num_layers"] - 1]):
+            kw["skip_block_list"] = blocks
+            runs = []
+            for share in (False, True):
+                per_step = []
+                pipe(height=meta["H"], width=meta["W"], num_frames=meta["F"], frame_rate=meta["fps"], prompt_embeds=g["pe"],
+                     prompt_attention_mask=g["pm"], negative_prompt_embeds=g["ne"], negative_prompt_attention_mask=g["nm"],
+                     num_inference_steps=meta["steps"], generator=torch.Generator().manual_seed(g["noise_seed"]),
+                     output_type="latent", return_dict=False, is_video=True, vae_per_channel_normalize=True,
+                     _per_step_latents=per_step, share_stg_prefix=share, **kw)
+                runs.append(per_step)
+            assert len(runs[0]) == len(runs[1]) == meta["steps"]
+            for a, b in zip(*runs):
+                assert torch.equal(a, b), (strat, blocks)
+
+
 def test_pipeline_i2v_conditioning_vs_oracle():
     pipe, sd, _ = _pipe(2)
     g = torch.Generator().manual_seed(3)
