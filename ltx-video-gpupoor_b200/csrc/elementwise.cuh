@@ -146,7 +146,7 @@ norm_mod_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
 // cos/sin: [tokens_per_batch, D] bf16 (row = token index within the batch), null => no RoPE.
 // grid.y selects the tensor: 0 = q, 1 = k.  All products / sums are bf16x2 ops with the reference's rounding points.
 // ------------------------------------------------------------------------------------------
-template <int NV>
+template <int NV, bool kRope>
 __global__ void __launch_bounds__(128)
 qk_norm_rope_kernel(__nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict__ k, int Mq, int Mk, long long ldq, long long ldk,
                     const __nv_bfloat16* __restrict__ wq, const __nv_bfloat16* __restrict__ wk,
@@ -166,7 +166,18 @@ qk_norm_rope_kernel(__nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict__ k
   uint4 xv[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) xv[i] = *reinterpret_cast<const uint4*>(xr + (i * 32 + lane) * 8);
-  const long long trow = cosT ? static_cast<long long>(row % tokens_per_batch) * D : 0;
+  const long long trow = kRope ? static_cast<long long>(row % tokens_per_batch) * D : 0;
+  // D <= 2048: the row's cos / sin slices are requested together with the row itself, before the reduction, so one warp keeps
+  // 12 KB in flight instead of 4 KB then 8 x 1 KB (the kernel is latency-bound at 19 resident warps / SM: ncu warps_active 30 %)
+  constexpr bool kPrefetch = kRope && NV <= 8;
+  uint4 cv[kPrefetch ? NV : 1], sv[kPrefetch ? NV : 1];
+  if (kPrefetch) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      cv[i] = ldg16(cosT + trow + (i * 32 + lane) * 8);
+      sv[i] = ldg16(sinT + trow + (i * 32 + lane) * 8);
+    }
+  }
   float sq = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -184,8 +195,8 @@ qk_norm_rope_kernel(__nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict__ k
     const uint4 w4 = ldg16(w + c);
     uint32_t o[4] = {bf2_mul(pack_bf16(v[0] * rs, v[1] * rs), w4.x), bf2_mul(pack_bf16(v[2] * rs, v[3] * rs), w4.y),
                      bf2_mul(pack_bf16(v[4] * rs, v[5] * rs), w4.z), bf2_mul(pack_bf16(v[6] * rs, v[7] * rs), w4.w)};
-    if (cosT) {
-      const uint4 c4 = ldg16(cosT + trow + c), s4 = ldg16(sinT + trow + c);
+    if (kRope) {
+      const uint4 c4 = kPrefetch ? cv[i] : ldg16(cosT + trow + c), s4 = kPrefetch ? sv[i] : ldg16(sinT + trow + c);
       const uint32_t cs[4] = {c4.x, c4.y, c4.z, c4.w}, sn[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {

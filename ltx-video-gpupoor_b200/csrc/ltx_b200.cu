@@ -428,7 +428,8 @@ extern "C" int ltxb200_qk_norm_rope_bf16(void* q, int64_t ldq, int Mq, void* k, 
   auto C = static_cast<const __nv_bfloat16*>(cos_table);
   auto Sn = static_cast<const __nv_bfloat16*>(sin_table);
 #define QK_CASE(n) \
-  case n: qk_norm_rope_kernel<n><<<grid, 128, 0, st>>>(Q, Kp, q ? Mq : 0, Mk, ldq, ldk, WQ, WK, C, Sn, tokens_per_batch, eps); break;
+  case n: if (C) qk_norm_rope_kernel<n, true><<<grid, 128, 0, st>>>(Q, Kp, q ? Mq : 0, Mk, ldq, ldk, WQ, WK, C, Sn, tokens_per_batch, eps); \
+          else qk_norm_rope_kernel<n, false><<<grid, 128, 0, st>>>(Q, Kp, q ? Mq : 0, Mk, ldq, ldk, WQ, WK, C, Sn, tokens_per_batch, eps); break;
   switch (D / 256) {
     QK_CASE(2) QK_CASE(4) QK_CASE(6) QK_CASE(8) QK_CASE(12) QK_CASE(16) QK_CASE(20)
     default: return kErrUnsupported;
