@@ -2,10 +2,11 @@
 
 Scope: noise, UniPC schedule, RoPE tables, the per-step two-sequence forward with the i2v conditioning
 (`y` = [mask(4) | image latent(16)] channels concatenated to the noisy latent, :232-244,279-280, and the 257 CLIP tokens
-consumed by WanI2VCrossAttention), CFG with the optional CFG-Zero* projection, scheduler step.  The encoders that PRODUCE
-the conditioning — CLIP visual (:219-224), the Wan VAE encode of the padded image video (:262-277) and T5 —
-are out of scope: pass `clip_fea=` [1, 257, 1280], `y=` [20, (F-1)/4+1, H/8, W/8] and `context=` / `context_null=`.
-The result is the denoised latent [16, (F-1)/4+1, H/8, W/8] (fp32).
+consumed by WanI2VCrossAttention), CFG with the optional CFG-Zero* projection, scheduler step.  `y` is either passed in or
+built here the way the reference builds it (:232-244, 262-277): the start image (a [3, H, W] tensor in [-1, 1], already at the
+output size — PIL / lanczos resizing is media I/O) padded with F-1 zero frames goes through `WanVAE.encode` (wan/vae.py) and
+the 4-channel first-frame mask is stacked on top.  CLIP visual (:219-224) and T5 are out of scope: pass `clip_fea=`
+[1, 257, 1280] and `context=` / `context_null=`.  The result is the denoised latent [16, (F-1)/4+1, H/8, W/8] (fp32).
 """
 from __future__ import annotations
 
@@ -22,13 +23,36 @@ from .posemb_layers import get_rotary_pos_embed
 
 class WanI2V:
     def __init__(self, model: WanModel, device="cuda", num_train_timesteps: int = 1000, vae_stride=(4, 8, 8),
-                 patch_size=(1, 2, 2), z_dim: int = 16):
+                 patch_size=(1, 2, 2), z_dim: int = 16, vae=None):
         assert model.model_type == "i2v"
         self.model = model
+        self.vae = vae                                    # WanVAE with encoder weights, only needed when y= is not passed
         self.device = torch.device(device)
         self.num_train_timesteps = num_train_timesteps
         self.vae_stride, self.patch_size, self.z_dim = vae_stride, patch_size, z_dim
         self._interrupt = False
+
+    def first_frame_mask(self, frame_num: int, lat_h: int, lat_w: int) -> torch.Tensor:
+        """image2video.py:232-244 (no end frame): ones on the first video frame, repeated 4x so that the 1 + (F-1) frames fold into
+        [4, (F-1)/4+1, lat_h, lat_w]."""
+        msk = torch.ones(1, frame_num, lat_h, lat_w, device=self.device)
+        msk[:, 1:] = 0
+        msk = torch.concat([torch.repeat_interleave(msk[:, 0:1], repeats=4, dim=1), msk[:, 1:]], dim=1)
+        msk = msk.view(1, msk.shape[1] // 4, 4, lat_h, lat_w)
+        return msk.transpose(1, 2)[0]
+
+    @torch.no_grad()
+    def encode_conditioning(self, image_start: torch.Tensor, frame_num: int) -> torch.Tensor:
+        """image2video.py:262-277: y = [mask(4) | VAE latent(16) of (image, zeros x (F-1))] -> [20, (F-1)/4+1, H/8, W/8] fp32."""
+        if self.vae is None:
+            raise RuntimeError("WanI2V(vae=WanVAE with encoder weights) is needed to build y from image_start")
+        img = image_start.to(self.device, torch.float32)
+        assert img.dim() == 3 and img.shape[0] == 3, "image_start: [3, H, W] tensor in [-1, 1] at the output size"
+        h, w = img.shape[1:]
+        assert h % (self.vae_stride[1] * self.patch_size[1]) == 0 and w % (self.vae_stride[2] * self.patch_size[2]) == 0
+        enc = torch.concat([img[:, None], torch.zeros(3, frame_num - 1, h, w, device=self.device)], dim=1)
+        lat_y = self.vae.encode([enc], 0)[0]
+        return torch.concat([self.first_frame_mask(frame_num, h // self.vae_stride[1], w // self.vae_stride[2]), lat_y])
 
     @torch.no_grad()
     def generate(self, input_prompt=None, image_start=None, image_end=None, height=720, width=1280, fit_into_canvas=True,
@@ -41,8 +65,13 @@ class WanI2V:
                  noise: Optional[torch.Tensor] = None, _per_step_latents=None, **bbargs):
         if audio_proj is not None or audio_scale is not None or image_end is not None:
             raise NotImplementedError("fantasytalking audio / end-frame conditioning are out of scope")
-        if clip_fea is None or y is None:
-            raise NotImplementedError("CLIP visual and the Wan VAE encoder are out of scope: pass clip_fea= [1,257,1280] and y= [20,T,H/8,W/8]")
+        if clip_fea is None:
+            raise NotImplementedError("CLIP visual is out of scope: pass clip_fea= [1,257,1280]")
+        if y is None:
+            if not torch.is_tensor(image_start):
+                raise NotImplementedError("pass y= [20,T,H/8,W/8], or image_start= as a [3,H,W] tensor in [-1,1] (PIL resizing is media I/O)")
+            y = self.encode_conditioning(image_start, frame_num)
+            height, width = image_start.shape[1:]
         if context is None or (guide_scale != 1 and context_null is None):
             raise NotImplementedError("the T5 text encoder is out of scope: pass context= / context_null= embeddings [L, 4096]")
         if sample_solver not in ("unipc", "dpm++"):

@@ -417,3 +417,18 @@ def ulysses_attention_virtual(q: Tensor, k: Tensor, v: Tensor, P: int) -> Tensor
         for dst in range(P):                             # reverse all-to-all: token shard dst gets heads hs from rank r
             out[:, dst * (N // P):(dst + 1) * (N // P), hs] = o[:, dst * (N // P):(dst + 1) * (N // P)]
     return out
+
+
+def i2v_conditioning(vae_sd, vae_cfg, image: Tensor, frame_num: int) -> Tensor:
+    """image2video.py:232-244, 262-277 (no end frame): y = [first-frame mask (4) | WanVAE.encode([image, zeros x (F-1)]) (16)]
+    -> [20, (F-1)/4+1, H/8, W/8].  image: [3, H, W] in [-1, 1]."""
+    from . import wan_vae_oracle as V
+    h, w = image.shape[1:]
+    lat_h, lat_w = h // 8, w // 8
+    msk = torch.ones(1, frame_num, lat_h, lat_w)
+    msk[:, 1:] = 0
+    msk = torch.concat([torch.repeat_interleave(msk[:, 0:1], repeats=4, dim=1), msk[:, 1:]], dim=1)
+    msk = msk.view(1, msk.shape[1] // 4, 4, lat_h, lat_w).transpose(1, 2)[0]
+    enc = torch.concat([image[:, None], torch.zeros(3, frame_num - 1, h, w)], dim=1)
+    lat_y = V.wan_vae_encode(vae_sd, enc, vae_cfg, torch.tensor(V.WAN_VAE_MEAN), torch.tensor(V.WAN_VAE_STD))
+    return torch.concat([msk, lat_y])

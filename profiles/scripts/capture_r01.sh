@@ -3,16 +3,17 @@
 # `ncu --set full` capture per hot kernel, reduced on the box to CSV (the .ncu-rep files exceed gpurun's 64 MiB return limit).
 set -x
 O=gpurun_out
-python bench.py --steps 10 --warmup 3 > $O/r01_bench_final.json 2> $O/r01_bench_final.err
-python bench.py --steps 3 --warmup 3 --workload wan1.3b_832x480x81_sp > $O/r01_bench_wan1gpu.json 2> $O/r01_bench_wan1gpu.err
+T=${TAG:-r01}     # file prefix: r01 = first capture of the round, r01b = after the packed/poly softmax and the rope prefetch
+python bench.py --steps 10 --warmup 3 > $O/${T}_bench_final.json 2> $O/${T}_bench_final.err
+python bench.py --steps 3 --warmup 3 --workload wan1.3b_832x480x81_sp > $O/${T}_bench_wan1gpu.json 2> $O/${T}_bench_wan1gpu.err
 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-decode > $O/plain_bench.log 2>&1 &&
 LTXB200_NCU_RANGE=1 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
-    --log-file $O/r01_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-decode > $O/ncu_bench.log 2>&1
+    --log-file $O/${T}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-decode > $O/ncu_bench.log 2>&1
 python profiles/scripts/prof_kernels.py all 1 > $O/plain_all.log 2>&1 || exit 1
 cap() {  # name, kernel regex, skip, count, script arg, with_source
   ncu --set full --clock-control none --import-source on -k regex:"$2" -s $3 -c $4 -o /tmp/$1 python profiles/scripts/prof_kernels.py $5 1 > $O/ncu_$1.log 2>&1
-  ncu -i /tmp/$1.ncu-rep --page raw --csv > $O/r01_$1_raw.csv 2>/dev/null
-  if [ "$6" = "src" ]; then ncu -i /tmp/$1.ncu-rep --page source --csv > $O/r01_$1_source.csv 2>/dev/null; fi
+  ncu -i /tmp/$1.ncu-rep --page raw --csv > $O/${T}_$1_raw.csv 2>/dev/null
+  if [ "$6" = "src" ]; then ncu -i /tmp/$1.ncu-rep --page source --csv > $O/${T}_$1_source.csv 2>/dev/null; fi
   rm -f /tmp/$1.ncu-rep
 }
 cap attn_d64 attention_fwd 2 1 attn src          # 3rd launch: self-attention B3 N6144 H32 d64

@@ -319,3 +319,36 @@ def test_dpmpp_scheduler_vs_reference_fixture(golden_dir):
     W.t2v_denoise(sd, gg["cfg"], gg["lat"], gg["ctx"], gg["ctx0"], steps=4, shift=5.0, guide_scale=5.0, per_step=ref, sample_solver="dpm++")
     for a, b in zip(steps_, ref):
         assert W.rel_l2(a.cpu(), b) < 2e-2
+
+
+def test_wan_i2v_conditioning_from_image():
+    """y built inside WanI2V from the start image (mask bit-exact, VAE latent vs the encode oracle) and generate() consuming it."""
+    from ltx_video_gpupoor_b200.wan.image2video import WanI2V
+    from ltx_video_gpupoor_b200.wan.vae import WanVAE
+    from oracle import wan_vae_oracle as V
+    vcfg = dict(V.WAN_VAE, dim=32)
+    vsd = V.make_wan_vae_encoder_state_dict(vcfg, seed=1)
+    vae = WanVAE(dim=32)
+    vae.load_state_dict(vsd)
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "wan_i2v.pt"), weights_only=False)
+    cfg = g["cfg"]
+    m = WanModel(model_type="i2v", in_dim=cfg["in_dim"], dim=cfg["dim"], ffn_dim=cfg["ffn_dim"], num_heads=cfg["num_heads"],
+                 num_layers=cfg["num_layers"])
+    m.load_state_dict(W.make_wan_state_dict(cfg, seed=1))
+    pipe = WanI2V(m, vae=vae)
+    F_, H_, W_ = 9, 64, 96
+    img = torch.rand(3, H_, W_, generator=torch.Generator().manual_seed(5)) * 2 - 1
+    y = pipe.encode_conditioning(img, F_)
+    yo = W.i2v_conditioning(vsd, vcfg, img, F_)
+    assert tuple(y.shape) == tuple(yo.shape) == (20, 3, H_ // 8, W_ // 8)
+    assert torch.equal(y[:4].cpu(), yo[:4])
+    e = W.rel_l2(y[4:].cpu(), yo[4:])
+    print(f"wan i2v conditioning latent rel_l2 vs oracle = {e:.3e}")
+    assert e < 2e-2
+    steps = []
+    lat = pipe.generate(image_start=img, frame_num=F_, sampling_steps=2, guide_scale=5.0, context=g["ctx"], context_null=g["ctx0"],
+                        clip_fea=g["clip"], noise=torch.randn(16, 3, H_ // 8, W_ // 8, generator=torch.Generator().manual_seed(6)),
+                        _per_step_latents=steps)
+    assert lat is not None and len(steps) == 2 and torch.isfinite(lat).all()
+    with pytest.raises(NotImplementedError):
+        pipe.generate(image_start="photo.png", frame_num=F_, context=g["ctx"], context_null=g["ctx0"], clip_fea=g["clip"])
