@@ -325,8 +325,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const int t = m & 1, j = m >> 1;
         const uint32_t kpos = kc0 + j;
         const int st = kpos % kStages;
-        if (t == 0 && part != 0) mbar_wait(&k_full[st], (kpos / kStages) & 1);
-        if (j == 0) mbar_wait(&q_full[t], it & 1);
+        if (t == 0 && part != 0) mbar_wait_parked(&k_full[st], (kpos / kStages) & 1);
+        if (j == 0) mbar_wait_parked(&q_full[t], it & 1);
         tc_fence_after();
         const uint32_t buf = (N0 + m) % kSBufs;
         const uint64_t qa = qdesc + static_cast<uint32_t>(t * (C::kQBytes >> 4));
@@ -365,19 +365,19 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           const uint32_t N = N0 + n, buf = N % kSBufs, par = (N / kSBufs) & 1;
           const bool more = n + kSBufs < nsteps;
           if (kSplit) {
-            if (more) { mbar_wait(&s_read[buf], par); issue_s(n + kSBufs, 1); }
-            mbar_wait(&p_half[buf], par);
-            if (j == 0) mbar_wait(&o_free[t], (it & 1) ^ 1);
-            if (t == 0) mbar_wait(&v_full[sv], (vc / kStages) & 1);
+            if (more) { mbar_wait_parked(&s_read[buf], par); issue_s(n + kSBufs, 1); }
+            mbar_wait_parked(&p_half[buf], par);
+            if (j == 0) mbar_wait_parked(&o_free[t], (it & 1) ^ 1);
+            if (t == 0) mbar_wait_parked(&v_full[sv], (vc / kStages) & 1);
             tc_fence_after();
             issue_pv(t, buf, sv, 0, BN / 32, j > 0);
-            mbar_wait(&p_full[buf], par);
+            mbar_wait_parked(&p_full[buf], par);
             tc_fence_after();
             issue_pv(t, buf, sv, BN / 32, BN / 16, true);
           } else {
-            mbar_wait(&p_full[buf], par);
-            if (j == 0) mbar_wait(&o_free[t], (it & 1) ^ 1);
-            if (t == 0) mbar_wait(&v_full[sv], (vc / kStages) & 1);
+            mbar_wait_parked(&p_full[buf], par);
+            if (j == 0) mbar_wait_parked(&o_free[t], (it & 1) ^ 1);
+            if (t == 0) mbar_wait_parked(&v_full[sv], (vc / kStages) & 1);
             tc_fence_after();
             issue_pv(t, buf, sv, 0, BN / 16, j > 0);
           }

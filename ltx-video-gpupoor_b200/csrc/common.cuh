@@ -134,6 +134,32 @@ DEVI bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// wait with a suspend-time hint: the hardware parks the thread until the phase completes (or ~the hint elapses) instead of returning
+// after a few cycles, so a single issuing thread that waits most of the time does not eat its scheduler's issue slots
+DEVI void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+        : "memory");
+  } while (!ok);
+}
+// non-blocking probe (test_wait never suspends the thread): for a single thread that polls several barriers
+DEVI bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 #ifdef LTXB200_DEBUG_HANG
 // debug build: a wait that does not complete within ~1 s reports who is stuck and traps instead of hanging the GPU
 #define mbar_wait(bar, parity) ::b200::mbar_wait_dbg((bar), (parity), __LINE__)
