@@ -409,3 +409,18 @@ def test_rf_stochastic_step_vs_reference_formula():
     b = pipe(**kw, generator=torch.Generator().manual_seed(1), stochastic_sampling=True)[0]
     c = pipe(**kw, generator=torch.Generator().manual_seed(1))[0]
     assert torch.equal(a, b) and O.rel_l2(a.cpu(), c.cpu()) > 1e-2
+
+
+def test_reference_selfcheck_encoder_first_frame_causality_gpu():
+    """The reference's in-file check (causal_video_autoencoder.py:1384-1389) on the CUDA path: encoding the first frame alone gives the
+    first latent frame of the whole video (bf16 tolerance instead of atol 1e-6)."""
+    from ltx_video_gpupoor_b200.ltx.causal_video_autoencoder import CausalVideoAutoencoder
+    sd = O.make_vae_encoder_state_dict(seed=2)
+    sd.update({k: v for k, v in O.make_vae_decoder_state_dict(seed=1).items() if k.startswith("decoder.")})
+    vae = CausalVideoAutoencoder()
+    vae.load_state_dict(sd)
+    video = (torch.rand(1, 3, 17, 64, 64, generator=torch.Generator().manual_seed(3)) * 2 - 1).cuda()
+    lat_v = vae.encode(video).latent_dist.mode()
+    lat_i = vae.encode(video[:, :, :1]).latent_dist.mode()
+    assert tuple(lat_v.shape) == (1, 128, 3, 2, 2) and tuple(lat_i.shape) == (1, 128, 1, 2, 2)
+    assert O.rel_l2(lat_i.float().cpu(), lat_v[:, :, :1].float().cpu()) < 1e-2

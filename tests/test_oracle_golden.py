@@ -212,3 +212,23 @@ def test_wan_dpmpp_oracle_matches_reference(golden_dir):
             for i in range(steps):
                 x = o.step(c["v"][i], x)
                 assert W.rel_l2(x, c["x"][i]) < 1e-5
+
+
+# ---- the reference's own in-file checks, restated on the oracle -------------------------------------------------
+def test_reference_selfcheck_vae_patchify_roundtrip():
+    """causal_video_autoencoder.py:1341-1347 `test_vae_patchify_unpatchify`: unpatchify(patchify(x)) == x (here: spatial patch 4,
+    the configuration the shipped VAE uses; `vae_unpatchify` / `vae_patchify` are each other's inverse)."""
+    x = torch.randn(2, 3, 8, 64, 64, generator=torch.Generator().manual_seed(0))
+    assert torch.equal(O.vae_unpatchify(O.vae_patchify(x, 4), 4), x)
+    lat = torch.randn(2, 128, 3, 4, 6, generator=torch.Generator().manual_seed(1))
+    assert torch.equal(O.unpatchify(O.patchify(lat), 3, 4, 6), lat)          # SymmetricPatchifier round trip (symmetric_patchifier.py:33-84)
+
+
+def test_reference_selfcheck_encoder_first_frame_causality():
+    """causal_video_autoencoder.py:1350-1400 `demo_video_autoencoder_forward_backward`: the latent of the first frame alone equals
+    the first latent frame of the whole video (atol 1e-6 there, :1389) — for the LTX encoder and, same property, the Wan encoder."""
+    sd = O.make_vae_encoder_state_dict(seed=2)
+    video = torch.rand(1, 3, 9, 32, 32, generator=torch.Generator().manual_seed(3)) * 2 - 1
+    mean_v, _ = O.vae_encode_moments(sd, video)
+    mean_i, _ = O.vae_encode_moments(sd, video[:, :, :1])
+    assert torch.allclose(mean_i, mean_v[:, :, :1], atol=1e-5)
