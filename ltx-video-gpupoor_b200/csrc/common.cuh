@@ -325,6 +325,58 @@ DEVI uint64_t umma_smem_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint3
   return d;
 }
 
+// ------------------------------------------------------------------------------------------
+// CTA pair (cta_group::2): two CTAs of a cluster on one 256-row MMA tile.  Each CTA keeps its 128 rows of A, HALF of the B tile
+// and its own 128-lane accumulator; the leader (cluster rank 0) issues the MMAs, TMA loads of both CTAs complete on the leader's
+// barrier, commits are multicast to both CTAs.
+// ------------------------------------------------------------------------------------------
+DEVI uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r)); return r; }
+DEVI void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;     // clears the CTA-rank bit of a shared address: "the same location in the leader CTA"
+DEVI void tma_load_2d_2sm(void* smem, const CUtensorMap* m, uint64_t* leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::
+          "r"(smem_u32(smem)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+template <uint32_t kCols>
+DEVI void tmem_alloc_2cta(uint32_t* smem_dst) {   // whole warp, the same warp index in both CTAs
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(smem_dst)), "n"(kCols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+}
+template <uint32_t kCols>
+DEVI void tmem_dealloc_2cta(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "n"(kCols) : "memory");
+}
+DEVI void umma_commit_2cta(uint64_t* bar, uint32_t cta_mask) {   // arrives on `bar` (same offset) in every CTA of the mask
+  asm volatile(
+      "{\n\t.reg .b16 lo, hi;\n\t"
+      "mov.b32 {lo, hi}, %1;\n\t"
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], lo;\n\t}\n" ::"r"(smem_u32(bar)),
+      "r"(cta_mask)
+      : "memory");
+}
+DEVI void umma_ss_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+DEVI void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {      // arrive on the barrier at the same offset in CTA `cta` of the cluster
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
+
 // instruction descriptor for kind::f16, bf16 x bf16 -> fp32
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, uint32_t a_mn_major, uint32_t b_mn_major) {
   return (1u << 4)                 // c_format  = F32

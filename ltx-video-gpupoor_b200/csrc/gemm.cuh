@@ -58,21 +58,27 @@ struct GemmParams {
   int n_fastest;
 };
 
-template <int BN>
+template <int BN, int kCtas = 1>
 struct GemmSmem {
   static constexpr int kStageBytesA = kGemmBM * kGemmBK * 2;          // 16 KB
-  static constexpr int kStageBytesB = BN * kGemmBK * 2;
+  static constexpr int kStageBytesB = (BN / kCtas) * kGemmBK * 2;     // CTA pair: each CTA holds half of the B tile
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kStages = (BN == 256 && kCtas == 1) ? 4 : 6;
   static constexpr int kBarBytes = 256;
   static constexpr int kTotal = kStages * kStageBytes + kBarBytes + 1024;  // +1024 alignment slack
 };
 
-template <int BN, bool kConv>
+// kCtas = 2 (plain GEMM only): the tile is 256 x BN on a CTA PAIR (cluster of 2, tcgen05 cta_group::2).  Each CTA loads its 128 rows
+// of A and half of the B tile (so the shared-memory fill and operand traffic per SM drop by a third), the leader issues
+// M = 256 MMAs whose accumulator halves land in each CTA's own TMEM, and each CTA runs the epilogue of its 128 rows.
+template <int BN, bool kConv, int kCtas = 1>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmParams p) {
-  using S = GemmSmem<BN>;
+  static_assert(kCtas == 1 || (kCtas == 2 && !kConv), "the CTA-pair variant covers the plain GEMM");
+  using S = GemmSmem<BN, kCtas>;
+  const uint32_t cta_rank = (kCtas == 2) ? cluster_ctarank() : 0u;
+  const int cta_first = blockIdx.x / kCtas, cta_stride = gridDim.x / kCtas;     // persistent walk in units of CTA groups
   constexpr int kStages = S::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -85,7 +91,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int tiles_m = kConv ? p.cB * p.cT * p.c_tiles_h * p.c_tiles_w : (p.M + kGemmBM - 1) / kGemmBM;
+  const int tiles_m = kConv ? p.cB * p.cT * p.c_tiles_h * p.c_tiles_w : (p.M + kGemmBM * kCtas - 1) / (kGemmBM * kCtas);
   const int tiles_n = (p.N + BN - 1) / BN;
   const int num_tiles = tiles_m * tiles_n;
   const int kb_per_tap = kConv ? (p.cCin + kGemmBK - 1) / kGemmBK : 1;
@@ -101,13 +107,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], 4 * kCtas);        // the leader's MMA thread waits for the epilogue warps of both CTAs
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
+  if (warp == 1) {
+    if (kCtas == 2) tmem_alloc_2cta<2 * BN>(tmem_slot);
+    else tmem_alloc<2 * BN>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (kCtas == 2) cluster_sync_all();              // the peer must not signal barriers that are not initialised yet
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -117,7 +127,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                            // uniform-datapath TMA / MMA instructions directly instead of through per-lane ELECT loops
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = cta_first; tile < num_tiles; tile += cta_stride) {
         const int tm = p.n_fastest ? tile / tiles_n : tile % tiles_m, tn = p.n_fastest ? tile % tiles_n : tile / tiles_m;
         int cb = 0, ct = 0, ch0 = 0, cw0 = 0;
         if (kConv) {
@@ -130,6 +140,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * S::kStageBytes;
           uint8_t* sb = sa + S::kStageBytesA;
+          if (kCtas == 2) {
+            // both CTAs' bytes complete on the LEADER's barrier (the MMAs are issued there); only the leader arms it
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::kStageBytes);
+            tma_load_2d_2sm(sa, &tmA, &full_bar[stage], kb * kGemmBK, (tm * 2 + static_cast<int>(cta_rank)) * kGemmBM);
+            tma_load_2d_2sm(sb, &tmB, &full_bar[stage], kb * kGemmBK, tn * BN + static_cast<int>(cta_rank) * (BN / 2));
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
           if (kConv) {
             const int tap = kb / kb_per_tap, cblk = kb - tap * kb_per_tap;
@@ -156,13 +174,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    constexpr uint32_t idesc = umma_idesc_bf16(kGemmBM, BN, 0, 0);
+    // ================= MMA issuer (CTA pair: the leader only) =================
+    const int issue_tiles = (kCtas == 2 && cta_rank != 0) ? 0 : num_tiles;      // the peer's MMA warp only allocates / frees TMEM
+    constexpr uint32_t idesc = umma_idesc_bf16(kGemmBM * kCtas, BN, 0, 0);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = cta_first; tile < issue_tiles; tile += cta_stride) {
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
@@ -176,10 +195,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int k = 0; k < kGemmBK / 16; ++k) {
             const uint64_t ad = umma_smem_desc_sw128(sa + k * 32, 16, 1024);
             const uint64_t bd = umma_smem_desc_sw128(sb + k * 32, 16, 1024);
-            umma_ss(d_tmem, ad, bd, idesc, (kb | k) ? 1u : 0u);
+            if (kCtas == 2) umma_ss_2cta(d_tmem, ad, bd, idesc, (kb | k) ? 1u : 0u);
+            else umma_ss(d_tmem, ad, bd, idesc, (kb | k) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);                       // frees the smem slot when MMAs retire
-          if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);   // accumulator ready for the epilogue
+          if (kCtas == 2) {
+            umma_commit_2cta(&empty_bar[stage], 3u);                       // frees the slot in BOTH CTAs
+            if (kb == num_kb - 1) umma_commit_2cta(&tfull_bar[acc], 3u);   // both epilogues
+          } else {
+            umma_commit(&empty_bar[stage]);                       // frees the smem slot when MMAs retire
+            if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);   // accumulator ready for the epilogue
+          }
         }
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -192,8 +217,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int row_in_tile = sub * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int tm = p.n_fastest ? tile / tiles_n : tile % tiles_m, tn = p.n_fastest ? tile % tiles_n : tile / tiles_m;
+    for (int tile = cta_first; tile < num_tiles; tile += cta_stride) {
+      const int tm = (p.n_fastest ? tile / tiles_n : tile % tiles_m) * kCtas + static_cast<int>(cta_rank);   // this CTA's 128-row block
+      const int tn = p.n_fastest ? tile % tiles_n : tile / tiles_m;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * BN + (static_cast<uint32_t>(sub * 32) << 16);
@@ -326,16 +352,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (kCtas == 2 && cta_rank != 0) mbar_arrive_remote(&tempty_bar[acc], 0);
+        else mbar_arrive(&tempty_bar[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (kCtas == 2) cluster_sync_all();              // the peer may still multicast into this CTA's barriers / read its shared memory
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<2 * BN>(tmem_base);
+    if (kCtas == 2) tmem_dealloc_2cta<2 * BN>(tmem_base);
+    else tmem_dealloc<2 * BN>(tmem_base);
   }
 }
 

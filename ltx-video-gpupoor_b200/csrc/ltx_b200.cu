@@ -70,6 +70,30 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   return launch_status();
 }
 
+// CTA-pair variant: cluster of 2 along M, grid = 2 x min(super tiles, SMs / 2)
+static int launch_gemm_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_tiles, cudaStream_t st) {
+  using S = GemmSmem<256, 2>;
+  static bool configured = false;
+  auto kern = gemm_bf16_kernel<256, false, 2>;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal) != cudaSuccess) return kErrCuda;
+    configured = true;
+  }
+  const int pairs = num_sms() / 2;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * (num_tiles < pairs ? num_tiles : pairs));
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = S::kTotal;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, kern, ta, tb, p) != cudaSuccess) return kErrCuda;
+  return launch_status();
+}
+
 extern "C" int ltxb200_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K,
                                  void* out, int64_t ldc, int out_f32, const void* bias, int act,
                                  const void* residual, int64_t ldr, const void* gate, int64_t gate_ld,
@@ -81,6 +105,8 @@ extern "C" int ltxb200_gemm_bf16(const void* A, int64_t lda, const void* W, int6
       (gate && (!aligned16(gate) || (gate_ld & 7) || rows_per_gate <= 0)))
     return kErrBadAlign;
   const int BN = (N <= 128) ? 128 : 256;
+  static const int env_2cta = getenv("LTXB200_GEMM_2CTA") ? atoi(getenv("LTXB200_GEMM_2CTA")) : 1;
+  const bool two_cta = env_2cta && BN == 256 && M > 128;
   CUtensorMap ta, tb;
   {
     uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
@@ -91,7 +117,7 @@ extern "C" int ltxb200_gemm_bf16(const void* A, int64_t lda, const void* W, int6
   {
     uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
     uint64_t str[1] = {static_cast<uint64_t>(ldw) * 2};
-    uint32_t box[2] = {kGemmBK, static_cast<uint32_t>(BN)};
+    uint32_t box[2] = {kGemmBK, static_cast<uint32_t>(two_cta ? BN / 2 : BN)};     // CTA pair: each CTA loads half of the B tile
     if (make_tmap_bf16(&tb, W, 2, dims, str, box)) return kErrTensorMap;
   }
   GemmParams p{};
@@ -105,8 +131,9 @@ extern "C" int ltxb200_gemm_bf16(const void* A, int64_t lda, const void* W, int6
   // the weights of this path always fit the 126 MB L2 (<= 34 MB); A often does not (FFN-down: 302 MB)
   p.n_fastest = (static_cast<long long>(N) * K * 2 <= (48ll << 20)) ? 1 : 0;
   if (const char* e = getenv("LTXB200_GEMM_RASTER")) p.n_fastest = atoi(e);
-  const int tiles = ((M + kGemmBM - 1) / kGemmBM) * ((N + BN - 1) / BN);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (two_cta) return launch_gemm_2cta(ta, tb, p, ((M + 2 * kGemmBM - 1) / (2 * kGemmBM)) * ((N + BN - 1) / BN), st);
+  const int tiles = ((M + kGemmBM - 1) / kGemmBM) * ((N + BN - 1) / BN);
   return BN == 128 ? launch_gemm<128, false>(ta, tb, p, tiles, st) : launch_gemm<256, false>(ta, tb, p, tiles, st);
 }
 
