@@ -94,14 +94,15 @@ DEVI void exp2_poly_f32x2(uint64_t X, float& e0, float& e1) {
   e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
 }
 
-// tanh-approximated GELU, as torch F.gelu(approximate="tanh")
+// tanh-approximated GELU, as torch F.gelu(approximate="tanh"); tanh on the MUFU pipe (tanh.approx.f32, max relative error 2^-11:
+// eight times below the bf16 rounding of the result) — one MUFU instead of the ex2 + rcp pair
 DEVI float gelu_tanh(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  float u = k0 * (x + k1 * x * x * x);
-  // tanh(u) = 1 - 2/(exp(2u)+1); exp via ex2
-  float e = __expf(2.0f * u);
-  float t = 1.0f - __fdividef(2.0f, e + 1.0f);
-  return 0.5f * x * (1.0f + t);
+  const float u = k0 * fmaf(k1 * x * x, x, x);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
 }
 
 // exact GELU (torch.nn.GELU() default, used by Wan's MLPProj, model.py:583)

@@ -245,13 +245,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (p.gate) gate_row = p.gate + (m_lin / p.rows_per_gate) * p.gate_ld;
       const __nv_bfloat16* res_row = p.residual ? p.residual + m_lin * p.ldr : nullptr;
 
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      // One 32-column chunk of the accumulator row: bias / activation / gate / residual / store.  The chunk's TMEM load and its
+      // bias slice were requested one chunk earlier (see the driver loop below), so neither latency is exposed here.
+      auto process = [&](const uint32_t (&v)[32], const uint4 (&bias4)[4], int c0) {
         const int n0 = tn * BN + c0;
-        if (n0 >= p.N) break;                 // warp-uniform
-        uint32_t v[32];
-        tmem_ld32(t_addr + c0, v);
-        tmem_wait_ld();
         if (row_ok) {
           float f[32];
 #pragma unroll
@@ -261,7 +258,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
               if (full || n0 + j < p.N) {
-                const uint4 bq = *reinterpret_cast<const uint4*>(p.bias + n0 + j);
+                const uint4 bq = bias4[j >> 3];
                 const float2 b0 = unpack_bf16(bq.x), b1 = unpack_bf16(bq.y), b2 = unpack_bf16(bq.z), b3 = unpack_bf16(bq.w);
                 f[j] += b0.x; f[j + 1] += b0.y; f[j + 2] += b1.x; f[j + 3] += b1.y;
                 f[j + 4] += b2.x; f[j + 5] += b2.y; f[j + 6] += b3.x; f[j + 7] += b3.y;
@@ -348,6 +345,32 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             }
           }
+        }
+      };
+      auto load_bias = [&](uint4 (&bias4)[4], int c0) {
+        const int n0 = tn * BN + c0;
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8)
+            if (n0 + j < p.N) bias4[j >> 3] = __ldg(reinterpret_cast<const uint4*>(p.bias + n0 + j));
+        }
+      };
+      // driver: two chunks per iteration on alternating register sets; while chunk c is processed the TMEM load and the bias
+      // slice of chunk c+1 are in flight (tcgen05.wait::ld covers every outstanding load, so the next one is issued after it)
+      const int ncols = (p.N - tn * BN) < BN ? (p.N - tn * BN) : BN;          // warp-uniform
+      uint32_t va[32], vb[32];
+      uint4 ba[4], bb[4];
+      tmem_ld32(t_addr, va);
+      load_bias(ba, 0);
+#pragma unroll 1
+      for (int c0 = 0; c0 < ncols; c0 += 64) {
+        tmem_wait_ld();
+        if (c0 + 32 < ncols) { tmem_ld32(t_addr + c0 + 32, vb); load_bias(bb, c0 + 32); }
+        process(va, ba, c0);
+        if (c0 + 32 < ncols) {
+          tmem_wait_ld();
+          if (c0 + 64 < ncols) { tmem_ld32(t_addr + c0 + 64, va); load_bias(ba, c0 + 64); }
+          process(vb, bb, c0 + 32);
         }
       }
       tc_fence_before();
