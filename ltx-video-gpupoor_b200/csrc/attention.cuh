@@ -49,16 +49,23 @@ constexpr int kAttnBN = 128;   // keys per block
 
 template <int D>
 struct AttnCfg {
+#ifdef LTXB200_ATTN128_BN64
+  // d = 128 alternative: 64-key blocks with FOUR S/P buffers (4*64 + 2*128 = 512 columns) = two per tile, so a tile's next scores are
+  // computed while its current block is in the softmax (no split-phase tricks)
+  static constexpr int BN = (D == 128) ? 64 : kAttnBN;
+#else
   static constexpr int BN = kAttnBN;
-  static constexpr int kSBufs = (D == 64) ? 3 : 2;           // S/P buffers in TMEM, used in rotation by the steps
+#endif
+  static constexpr int kSBufs = (D == 64) ? 3 : (BN == 64 ? 4 : 2);           // S/P buffers in TMEM, used in rotation by the steps
   // With only two S buffers (d = 128 fills TMEM) a tile's next scores cannot be computed ahead in a spare buffer, so
   // the block is pipelined in halves instead: keys 64..127 of S(n+2) are issued as soon as softmax(n) has READ S(n)
   // (P(n) only overwrites columns 0..63), P.V of keys 0..63 starts when the first half of P(n) is written, and only
   // P.V of keys 64..127 plus the low half of S(n+2) remain between "P complete" and "next S ready".
   static constexpr bool kSplit = (kSBufs == 2);
+  static_assert(kSBufs * BN + 2 * D == 512, "TMEM budget");
   static constexpr int kQBytes = kAttnBM * D * 2;            // one Q tile
   static constexpr int kKBytes = BN * D * 2;                 // one K (or V) block
-  static constexpr int kStages = (D == 64) ? 4 : 2;          // 128 KB of K/V in flight
+  static constexpr int kStages = (128 * 1024) / (2 * kKBytes);          // 128 KB of K/V in flight
   static constexpr int kBarBytes = 512;
   static constexpr int kTotal = 2 * kQBytes + 2 * kStages * kKBytes + kBarBytes + 1024;
   static constexpr int kThreads = 384;                       // 8 softmax warps + TMA warp + MMA warp + 2 idle (warpgroup alignment)

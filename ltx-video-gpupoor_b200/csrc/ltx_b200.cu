@@ -267,7 +267,7 @@ static int attention_impl(const void* q, int64_t ldq, int64_t bsq, const void* k
   if (!aligned16(q) || !aligned16(k) || !aligned16(v) || (out && !aligned16(out)) || (ldq & 7) || (ldk & 7) || (ldv & 7) ||
       (ldo & 7) || (bsq & 7) || (bsk & 7) || (bsv & 7) || (bso & 7))
     return kErrBadAlign;
-  const int BN = kAttnBN;
+  const int BN = d == 64 ? AttnCfg<64>::BN : AttnCfg<128>::BN;       // keys per block (K / V box rows)
   CUtensorMap tq, tk, tv;
   if (make_qkv_tmap(&tq, q, B, H, Lq, d, ldq, bsq, kAttnBM) || make_qkv_tmap(&tk, k, B, H, Lk, d, ldk, bsk, BN) ||
       make_qkv_tmap(&tv, v, B, H, Lk, d, ldv, bsv, BN))
