@@ -254,3 +254,48 @@ def test_guidance_step(mode):
                       cond_mask=cmask, scratch=scratch, latents_bf16=lb)
     assert rel(lat.view(1, N, C), ref) < 2e-3
     assert torch.equal(lb, lat.to(BF))
+
+
+# ------------------------------------------------------------------ BASELINE.json's full sizes (size-independent properties)
+def test_attention_full_size_properties():
+    """LTX self-attention at the bench shape (N = 6144, d = 64) and a Wan-length sequence that is not a multiple of the block
+    (N = 32760, d = 128, 3 heads): (1) against torch SDPA in fp32 on the same GPU (a library reference, fast enough at this size),
+    (2) softmax rows sum to one: with V = 1 the output is exactly 1 up to bf16 rounding, (3) permuting the keys (and V with them)
+    leaves the output unchanged — the online softmax does not depend on the block order."""
+    for (B, H, N, d) in ((1, 4, 6144, 64), (1, 3, 32760, 128)):
+        g = torch.Generator().manual_seed(N)
+        q, k, v = [(torch.randn(B, N, H, d, generator=g)).to(BF).to(DEV) for _ in range(3)]
+        out = ops.attention(q, k, v)
+        ref = F.scaled_dot_product_attention(q.float().transpose(1, 2), k.float().transpose(1, 2), v.float().transpose(1, 2)).transpose(1, 2)
+        e = float((out.float() - ref).norm() / ref.norm())
+        print(f"attention full size N={N} d={d}: rel_l2 vs fp32 SDPA = {e:.3e}")
+        assert e < 1e-2
+        ones = torch.ones_like(v)
+        o1 = ops.attention(q, k, ones).float()
+        assert float((o1 - 1).abs().max()) < 1e-2
+        perm = torch.randperm(N, generator=g).to(DEV)
+        o2 = ops.attention(q, k[:, perm].contiguous(), v[:, perm].contiguous())
+        assert float((o2.float() - out.float()).norm() / out.float().norm()) < 6e-3
+
+
+def test_gemm_full_size_linearity():
+    """The three LTX GEMM shapes at the bench size (M = 18432 rows = 3 conds x 6144 tokens) through the CTA-pair kernel: against
+    torch's bf16 matmul with fp32 accumulation on the same GPU, and linearity gemm(a1 + a2) = gemm(a1) + gemm(a2) with fp32 outputs."""
+    M = 18432
+    for (N, K) in ((6144, 2048), (8192, 2048), (2048, 8192)):
+        g = torch.Generator().manual_seed(N + K)
+        a1 = (torch.randn(M, K, generator=g)).to(BF).to(DEV)
+        a2 = (torch.randn(M, K, generator=g) * 0.5).to(BF).to(DEV)
+        w = (torch.randn(N, K, generator=g) * K ** -0.5).to(BF).to(DEV)
+        o1 = ops.gemm(a1, w, None, out_f32=True)
+        ref = (a1.float() @ w.float().t())
+        e = float((o1 - ref).norm() / ref.norm())
+        print(f"gemm {M}x{N}x{K}: rel_l2 vs fp32 matmul = {e:.3e}")
+        assert e < 2e-3
+        a12 = (a1.float() + a2.float())
+        exact = a12.to(BF).float() == a12                     # rows where the bf16 sum is exact make the identity testable
+        rows = exact.all(dim=1).nonzero().flatten()[:64]
+        if rows.numel():
+            o12 = ops.gemm(a12.to(BF)[rows].contiguous(), w, None, out_f32=True)
+            o2 = ops.gemm(a2[rows].contiguous(), w, None, out_f32=True)
+            assert float((o12 - (o1[rows] + o2)).abs().max()) < 2e-2 * float(o12.abs().max())
