@@ -80,3 +80,13 @@ if which in ("all", "ew"):
               8.0 * M * D + 4.0 * 6144 * D)
     q2 = torch.randn(M, D, device=dev).bfloat16()
     timeit_bw("qk_norm (cross-attn q only) 18432x2048", lambda: ops.qk_norm_rope(q2, None, w, None), 4.0 * M * D)
+if which in ("wangemm",):
+    M = 65520
+    for (name, N, K, act) in (("wan qkv", 4608, 1536, None), ("wan o / q", 1536, 1536, None), ("wan ffn_up gelu", 8960, 1536, ops.ACT_GELU_TANH),
+                              ("wan ffn_down", 1536, 8960, None)):
+        a = torch.randn(M, K, device=dev).bfloat16(); w = torch.randn(N, K, device=dev).bfloat16() * 0.02; bias = torch.randn(N, device=dev).bfloat16()
+        if act is None:
+            timeit(f"gemm {name} {M}x{N}x{K}", lambda: ops.gemm(a, w, bias), 2.0 * M * N * K)
+        else:
+            timeit(f"gemm {name} {M}x{N}x{K}", lambda: ops.gemm(a, w, bias, act=act), 2.0 * M * N * K)
+        del a, w
