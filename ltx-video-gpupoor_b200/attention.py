@@ -85,8 +85,9 @@ def pay_attention(qkv_list, dropout_p=0.0, softmax_scale=None, causal=False, win
     fix = lambda t: t if (t.stride(3) == 1 and t.stride(2) == d) else t.contiguous()
     q, k, v = fix(q), fix(k), fix(v)
     bias = None if attention_mask is None else _key_bias_from_mask(attention_mask, b, H, k.shape[1])
-    # like the sdpa path of the reference, softmax_scale is not honoured unless given explicitly
-    out = ops.attention(q, k, v, key_bias=bias, scale=float(softmax_scale) if softmax_scale else 0.0)
+    # like the sdpa path of the reference (sdpa_wrapper never receives softmax_scale, utils/attention.py:99-116, 283-288), the scale
+    # is head_dim ** -0.5 whatever `softmax_scale` says — pinned by oracle/gen_golden_attention.py case "dtypes"
+    out = ops.attention(q, k, v, key_bias=bias, scale=0.0)
     if final_padding > 0:   # utils/attention.py:395-396: tail is uninitialised padding
         out = torch.cat([out, torch.empty(b, final_padding, H, d, device=out.device, dtype=out.dtype)], dim=1)
     return out.to(out_dtype)

@@ -2,6 +2,8 @@
 (the oracle's functions where one exists).  Tolerances are for bf16 inputs/outputs with fp32 accumulation."""
 import math
 
+import os
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -299,3 +301,25 @@ def test_gemm_full_size_linearity():
             o12 = ops.gemm(a12.to(BF)[rows].contiguous(), w, None, out_f32=True)
             o2 = ops.gemm(a2[rows].contiguous(), w, None, out_f32=True)
             assert float((o12 - (o1[rows] + o2)).abs().max()) < 2e-2 * float(o12.abs().max())
+
+
+def test_pay_attention_entry_point_vs_reference_fixture(golden_dir):
+    """Row a1: `pay_attention` (the drop-in of utils/attention.py:161) against outputs of the unmodified reference function on the
+    same inputs (tests/golden/pay_attention.pt), with the reference's calling conventions."""
+    from ltx_video_gpupoor_b200.attention import get_attention_modes, get_supported_attention_modes, pay_attention
+    assert get_attention_modes() == get_supported_attention_modes() == ["b200"]
+    g = torch.load(os.path.join(golden_dir, "pay_attention.pt"), weights_only=False)
+    for name, c in g.items():
+        kw = {k: (v.to(DEV) if torch.is_tensor(v) and k == "attention_mask" else v) for k, v in c["kw"].items()}
+        lst = [c["q"].to(DEV), c["k"].to(DEV), c["v"].to(DEV)]
+        y = pay_attention(lst, **kw)
+        torch.cuda.synchronize()
+        assert lst == [], "ownership of q/k/v passes to the callee (utils/attention.py:185-186)"
+        assert y.dtype == c["q"].dtype and tuple(y.shape) == tuple(c["out"].shape)
+        e = float((y[:, : c["valid"]].float().cpu() - c["out"][:, : c["valid"]].float()).norm() / c["out"][:, : c["valid"]].float().norm())
+        print(f"pay_attention[{name}] rel_l2 vs reference = {e:.3e}")
+        assert e < 1e-2, name
+    with pytest.raises(NotImplementedError):
+        pay_attention([g["plain"]["q"].to(DEV), g["plain"]["k"].to(DEV), g["plain"]["v"].to(DEV)], causal=True)
+    with pytest.raises(Exception):
+        pay_attention([g["plain"]["q"], g["plain"]["k"], g["plain"]["v"]])          # CPU tensors: no fallback

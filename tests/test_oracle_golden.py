@@ -232,3 +232,18 @@ def test_reference_selfcheck_encoder_first_frame_causality():
     mean_v, _ = O.vae_encode_moments(sd, video)
     mean_i, _ = O.vae_encode_moments(sd, video[:, :, :1])
     assert torch.allclose(mean_i, mean_v[:, :, :1], atol=1e-5)
+
+
+def test_pay_attention_oracle_matches_reference(golden_dir):
+    """Row a1 of the scope table: the attention entry point.  oracle/attention_oracle.py vs the fixture recorded from the unmodified
+    `pay_attention` (utils/attention.py:161-398, sdpa path): plain, additive key mask, k_lens runs in a batch, q_lens/k_lens with the
+    uninitialised tail, dtype contract; and the ownership convention (the caller's list is emptied)."""
+    from oracle import attention_oracle as A
+    g = _load(golden_dir, "pay_attention.pt")
+    assert set(g) == {"plain", "mask", "k_lens_batch", "q_k_lens_single", "dtypes"}
+    for name, c in g.items():
+        lst = [c["q"].clone(), c["k"].clone(), c["v"].clone()]
+        y = A.pay_attention(lst, **{k: v for k, v in c["kw"].items() if k != "softmax_scale"})
+        assert lst == []
+        assert y.dtype == c["out"].dtype == c["q"].dtype and y.shape == c["out"].shape
+        assert O.rel_l2(y[:, : c["valid"]].float(), c["out"][:, : c["valid"]].float()) < (1e-2 if name == "dtypes" else 1e-5), name
