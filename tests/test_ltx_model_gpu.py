@@ -424,3 +424,33 @@ def test_reference_selfcheck_encoder_first_frame_causality_gpu():
     lat_i = vae.encode(video[:, :, :1]).latent_dist.mode()
     assert tuple(lat_v.shape) == (1, 128, 3, 2, 2) and tuple(lat_i.shape) == (1, 128, 1, 2, 2)
     assert O.rel_l2(lat_i.float().cpu(), lat_v[:, :, :1].float().cpu()) < 1e-2
+
+
+def test_pipeline_callbacks_and_interrupt(golden_dir):
+    """Drop-in boundary: progress `callback(step_idx, latents|None, is_start, ...)` (pipeline_ltx_video.py:1100-1101,
+    1243-1248), `callback_on_step_end(pipe, i, t, {})` (:1255-1256), and `ltxv_model._interrupt` polled between transformer blocks
+    (transformer3d.py:468-469 -> forward returns [None]; the pipeline returns None)."""
+    from types import SimpleNamespace
+    g = _load(golden_dir, "ltx_pipeline.pt")
+    meta = g["meta"]
+    pipe, _, _ = _pipe(meta["num_layers"])
+    seen, ends = [], []
+    kw = dict(height=meta["H"], width=meta["W"], num_frames=meta["F"], frame_rate=meta["fps"], prompt_embeds=g["pe"], prompt_attention_mask=g["pm"],
+              num_inference_steps=3, guidance_scale=1.0, stg_scale=0.0, rescaling_scale=1.0, generator=torch.Generator().manual_seed(1),
+              output_type="latent", return_dict=False, is_video=True, vae_per_channel_normalize=True)
+    model = SimpleNamespace(_interrupt=False)
+    out = pipe(callback=lambda i, lat, is_start, **k: seen.append((i, None if lat is None else tuple(lat.shape), is_start, dict(k))),
+               callback_on_step_end=lambda p, i, t, d: ends.append((i, float(t))), ltxv_model=model, pass_no=2, **kw)
+    assert out is not None
+    assert seen[0] == (-1, None, True, {"override_num_inference_steps": 3, "pass_no": 2})
+    assert [s[0] for s in seen[1:]] == [0, 1, 2] and all(s[1] == (128, 3, 4, 6) and s[2] is False and s[3] == {"pass_no": 2} for s in seen[1:])
+    assert [e[0] for e in ends] == [0, 1, 2] and ends[0][1] > ends[1][1] > ends[2][1]
+    # interrupt raised by the UI thread after the first step: the next forward returns [None], the call returns None
+    def stop_after_first(i, lat, is_start, **k):
+        if i == 0:
+            model._interrupt = True
+    assert pipe(callback=stop_after_first, ltxv_model=model, **kw) is None
+    tr = pipe.transformer
+    y = tr(torch.zeros(1, 72, 128), freqs_cis=tr.precompute_freqs_cis(torch.zeros(1, 3, 72, device="cuda")), encoder_hidden_states=g["pe"],
+           timestep=torch.ones(1, 1), encoder_attention_mask=g["pm"], latent_shape=(3, 4, 6), ltxv_model=model, return_dict=False)
+    assert y == [None]

@@ -352,3 +352,24 @@ def test_wan_i2v_conditioning_from_image():
     assert lat is not None and len(steps) == 2 and torch.isfinite(lat).all()
     with pytest.raises(NotImplementedError):
         pipe.generate(image_start="photo.png", frame_num=F_, context=g["ctx"], context_null=g["ctx0"], clip_fea=g["clip"])
+
+
+def test_wan_callbacks_and_interrupt(golden_dir):
+    """Drop-in boundary: `callback(-1, None, True)` then `callback(i, latents, False)` per step (text2video.py:465-466, 574-575);
+    `self._interrupt` set from outside makes generate() return None; WanModel.forward returns [None] * len(x) (model.py:1074-1075)."""
+    g = _golden(golden_dir)
+    m, _ = _model(g["cfg"])
+    pipe = WanT2V(m)
+    seen = []
+    kw = dict(width=96, height=64, frame_num=9, shift=5.0, sampling_steps=3, guide_scale=5.0, context=g["ctx"], context_null=g["ctx0"], noise=g["lat"])
+    out = pipe.generate(callback=lambda i, lat, is_start, *a, **k: seen.append((i, None if lat is None else tuple(lat.shape), is_start)), **kw)
+    assert out is not None and tuple(out.shape) == tuple(g["lat"].shape)
+    assert seen == [(-1, None, True)] + [(i, tuple(g["lat"].shape), False) for i in range(3)]
+
+    def stop(i, lat, is_start, *a, **k):
+        if i == 0:
+            pipe._interrupt = True
+    assert pipe.generate(callback=stop, **kw) is None
+    cos, sin = get_rotary_pos_embed(g["lat"].shape[1:])
+    y = m([g["lat"].to(DEV), g["lat"].to(DEV)], t=g["t"].to(DEV), context=[g["ctx"].to(DEV), g["ctx0"].to(DEV)], freqs=(cos, sin), pipeline=pipe)
+    assert y == [None, None]
