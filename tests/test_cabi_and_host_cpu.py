@@ -160,3 +160,22 @@ def test_checkpoint_formats_round_trip(tmp_path):
                            "diffusion_model.transformer_blocks.0.attn1.to_q.lora_up.weight": up,
                            "diffusion_model.transformer_blocks.0.attn1.to_q.alpha": torch.tensor(4.0)}, multiplier=0.5)
     assert n == 1 and torch.allclose(sdw["transformer_blocks.0.attn1.to_q.weight"], W0 + 0.5 * (4.0 / 2) * up @ down, atol=1e-6)
+
+
+def test_torch_custom_ops_registered_with_fake_kernels():
+    """The torch.library layer over the C ABI (custom_ops.py): every op is in torch.ops.ltxb200, traces with shape-only fake
+    tensors (no GPU, no library call), and refuses CPU tensors at run time like the rest of the package."""
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    from ltx_video_gpupoor_b200 import custom_ops
+    for name in custom_ops.OPS:
+        assert hasattr(torch.ops.ltxb200, name), name
+    with FakeTensorMode():
+        a, w, b = torch.empty(48, 64, dtype=torch.bfloat16), torch.empty(256, 64, dtype=torch.bfloat16), torch.empty(256, dtype=torch.bfloat16)
+        assert torch.ops.ltxb200.gemm(a, w, b, 1).shape == (48, 256)
+        q, k = torch.empty(2, 96, 4, 64, dtype=torch.bfloat16), torch.empty(2, 80, 4, 64, dtype=torch.bfloat16)
+        assert torch.ops.ltxb200.attention(q, k, k, None, 0.0).shape == (2, 96, 4, 64)
+        x = torch.empty(1, 3, 8, 8, 64, dtype=torch.bfloat16)
+        assert torch.ops.ltxb200.conv3d(x, torch.empty(128, 27 * 64, dtype=torch.bfloat16), None, True).shape == (1, 3, 8, 8, 128)
+        assert torch.ops.ltxb200.norm_mod(a, None, None, 0, 1e-6, False).shape == (48, 64)
+    with pytest.raises(Exception):
+        torch.ops.ltxb200.gemm(torch.zeros(8, 64, dtype=torch.bfloat16), torch.zeros(16, 64, dtype=torch.bfloat16), None, 0)

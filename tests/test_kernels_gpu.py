@@ -323,3 +323,16 @@ def test_pay_attention_entry_point_vs_reference_fixture(golden_dir):
         pay_attention([g["plain"]["q"].to(DEV), g["plain"]["k"].to(DEV), g["plain"]["v"].to(DEV)], causal=True)
     with pytest.raises(Exception):
         pay_attention([g["plain"]["q"], g["plain"]["k"], g["plain"]["v"]])          # CPU tensors: no fallback
+
+
+def test_torch_custom_ops_match_direct_calls():
+    """torch.ops.ltxb200.* (custom_ops.py) run the same kernels as ops.py; torch.compile treats them as opaque ops."""
+    from ltx_video_gpupoor_b200 import custom_ops  # noqa: F401
+    a, w, b = rnd(300, 128, seed=1), rnd(512, 128, seed=2, scale=0.1), rnd(512, seed=3)
+    assert torch.equal(torch.ops.ltxb200.gemm(a, w, b, ops.ACT_GELU_TANH), ops.gemm(a, w, b, act=ops.ACT_GELU_TANH))
+    q, k, v = rnd(1, 200, 2, 64, seed=4), rnd(1, 150, 2, 64, seed=5), rnd(1, 150, 2, 64, seed=6)
+    assert torch.equal(torch.ops.ltxb200.attention(q, k, v, None, 0.0), ops.attention(q, k, v))
+    res, gate = rnd(300, 512, seed=7), rnd(3, 512, seed=8)
+    assert torch.equal(torch.ops.ltxb200.gemm_gate_residual(a, w, b, res, gate, 100), ops.gemm(a, w, b, residual=res, gate=gate, rows_per_gate=100))
+    f = torch.compile(lambda a_, w_, b_: torch.ops.ltxb200.gemm(a_, w_, b_, 0) * 2, fullgraph=True, backend="eager")   # dynamo trace only
+    assert torch.equal(f(a, w, b), ops.gemm(a, w, b) * 2)
