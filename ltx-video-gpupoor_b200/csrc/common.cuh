@@ -344,6 +344,13 @@ DEVI void tma_load_2d_2sm(void* smem, const CUtensorMap* m, uint64_t* leader_bar
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0), "r"(c1)
       : "memory");
 }
+DEVI void tma_load_5d_2sm(void* smem, const CUtensorMap* m, uint64_t* leader_bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], "
+      "[%2];\n" ::"r"(smem_u32(smem)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
 template <uint32_t kCols>
 DEVI void tmem_alloc_2cta(uint32_t* smem_dst) {   // whole warp, the same warp index in both CTAs
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(smem_dst)), "n"(kCols) : "memory");

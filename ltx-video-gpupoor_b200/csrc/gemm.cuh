@@ -68,14 +68,14 @@ struct GemmSmem {
   static constexpr int kTotal = kStages * kStageBytes + kBarBytes + 1024;  // +1024 alignment slack
 };
 
-// kCtas = 2 (plain GEMM only): the tile is 256 x BN on a CTA PAIR (cluster of 2, tcgen05 cta_group::2).  Each CTA loads its 128 rows
+// kCtas = 2: the tile is 256 x BN on a CTA PAIR (for the convolution: two consecutive 128-voxel patches) (cluster of 2, tcgen05 cta_group::2).  Each CTA loads its 128 rows
 // of A and half of the B tile (so the shared-memory fill and operand traffic per SM drop by a third), the leader issues
 // M = 256 MMAs whose accumulator halves land in each CTA's own TMEM, and each CTA runs the epilogue of its 128 rows.
 template <int BN, bool kConv, int kCtas = 1>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmParams p) {
-  static_assert(kCtas == 1 || (kCtas == 2 && !kConv), "the CTA-pair variant covers the plain GEMM");
+  static_assert(kCtas == 1 || kCtas == 2, "one CTA or a CTA pair");
   using S = GemmSmem<BN, kCtas>;
   const uint32_t cta_rank = (kCtas == 2) ? cluster_ctarank() : 0u;
   const int cta_first = blockIdx.x / kCtas, cta_stride = gridDim.x / kCtas;     // persistent walk in units of CTA groups
@@ -91,7 +91,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int tiles_m = kConv ? p.cB * p.cT * p.c_tiles_h * p.c_tiles_w : (p.M + kGemmBM * kCtas - 1) / (kGemmBM * kCtas);
+  const int tiles_m = kConv ? (p.cB * p.cT * p.c_tiles_h * p.c_tiles_w + kCtas - 1) / kCtas : (p.M + kGemmBM * kCtas - 1) / (kGemmBM * kCtas);
   const int tiles_n = (p.N + BN - 1) / BN;
   const int num_tiles = tiles_m * tiles_n;
   const int kb_per_tap = kConv ? (p.cCin + kGemmBK - 1) / kGemmBK : 1;
@@ -128,10 +128,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = cta_first; tile < num_tiles; tile += cta_stride) {
-        const int tm = p.n_fastest ? tile / tiles_n : tile % tiles_m, tn = p.n_fastest ? tile % tiles_n : tile / tiles_m;
+        const int tm = (p.n_fastest ? tile / tiles_n : tile % tiles_m) * kCtas + static_cast<int>(cta_rank);   // this CTA's 128-row block
+        const int tn = p.n_fastest ? tile % tiles_n : tile / tiles_m;
         int cb = 0, ct = 0, ch0 = 0, cw0 = 0;
         if (kConv) {
-          int r = tm;
+          int r = tm;                            // an odd patch count leaves the last pair's second CTA with cb == cB: TMA zero-fills
           cw0 = (r % p.c_tiles_w) * p.cBW; r /= p.c_tiles_w;
           ch0 = (r % p.c_tiles_h) * p.cBH; r /= p.c_tiles_h;
           ct = r % p.cT; cb = r / p.cT;
@@ -140,15 +141,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * S::kStageBytes;
           uint8_t* sb = sa + S::kStageBytesA;
-          if (kCtas == 2) {
-            // both CTAs' bytes complete on the LEADER's barrier (the MMAs are issued there); only the leader arms it
-            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::kStageBytes);
-            tma_load_2d_2sm(sa, &tmA, &full_bar[stage], kb * kGemmBK, (tm * 2 + static_cast<int>(cta_rank)) * kGemmBM);
-            tma_load_2d_2sm(sb, &tmB, &full_bar[stage], kb * kGemmBK, tn * BN + static_cast<int>(cta_rank) * (BN / 2));
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
-            continue;
-          }
-          mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
+          // CTA pair: both CTAs' bytes complete on the LEADER's barrier (the MMAs are issued there); only the leader arms it
+          if (kCtas == 1 || cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], kCtas * S::kStageBytes);
+          const int brow = tn * BN + static_cast<int>(cta_rank) * (BN / kCtas);      // this CTA's part of the B tile
           if (kConv) {
             const int tap = kb / kb_per_tap, cblk = kb - tap * kb_per_tap;
             const int thw = p.c_taps_hw * p.c_taps_hw;
@@ -163,11 +158,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               hh += kh - 1 + p.c_off_hw;
               ww += kw - 1 + p.c_off_hw;
             }
-            tma_load_5d(sa, &tmA, &full_bar[stage], cblk * kGemmBK, ww, hh, tt, cb);
-            tma_load_2d(sb, &tmB, &full_bar[stage], tap * p.cCin + cblk * kGemmBK, tn * BN);
+            if (kCtas == 2) {
+              tma_load_5d_2sm(sa, &tmA, &full_bar[stage], cblk * kGemmBK, ww, hh, tt, cb);
+              tma_load_2d_2sm(sb, &tmB, &full_bar[stage], tap * p.cCin + cblk * kGemmBK, brow);
+            } else {
+              tma_load_5d(sa, &tmA, &full_bar[stage], cblk * kGemmBK, ww, hh, tt, cb);
+              tma_load_2d(sb, &tmB, &full_bar[stage], tap * p.cCin + cblk * kGemmBK, brow);
+            }
+          } else if (kCtas == 2) {
+            tma_load_2d_2sm(sa, &tmA, &full_bar[stage], kb * kGemmBK, tm * kGemmBM);
+            tma_load_2d_2sm(sb, &tmB, &full_bar[stage], kb * kGemmBK, brow);
           } else {
             tma_load_2d(sa, &tmA, &full_bar[stage], kb * kGemmBK, tm * kGemmBM);
-            tma_load_2d(sb, &tmB, &full_bar[stage], kb * kGemmBK, tn * BN);
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * kGemmBK, brow);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -235,7 +238,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         ot = r % p.cT; ob = r / p.cT;
         oh = h0 + row_in_tile / p.cBW;
         ow = w0 + row_in_tile % p.cBW;
-        row_ok = (oh < p.cH) && (ow < p.cW);
+        row_ok = (oh < p.cH) && (ow < p.cW) && (ob < p.cB);
         m_lin = ((static_cast<long long>(ob) * p.cT + ot) * p.cH + oh) * p.cW + ow;
       } else {
         m_lin = static_cast<long long>(tm) * kGemmBM + row_in_tile;

@@ -71,10 +71,11 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
 }
 
 // CTA-pair variant: cluster of 2 along M, grid = 2 x min(super tiles, SMs / 2)
+template <int BN, bool kConv>
 static int launch_gemm_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_tiles, cudaStream_t st) {
-  using S = GemmSmem<256, 2>;
+  using S = GemmSmem<BN, 2>;
   static bool configured = false;
-  auto kern = gemm_bf16_kernel<256, false, 2>;
+  auto kern = gemm_bf16_kernel<BN, kConv, 2>;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal) != cudaSuccess) return kErrCuda;
     configured = true;
@@ -132,7 +133,7 @@ extern "C" int ltxb200_gemm_bf16(const void* A, int64_t lda, const void* W, int6
   p.n_fastest = (static_cast<long long>(N) * K * 2 <= (48ll << 20)) ? 1 : 0;
   if (const char* e = getenv("LTXB200_GEMM_RASTER")) p.n_fastest = atoi(e);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (two_cta) return launch_gemm_2cta(ta, tb, p, ((M + 2 * kGemmBM - 1) / (2 * kGemmBM)) * ((N + BN - 1) / BN), st);
+  if (two_cta) return launch_gemm_2cta<256, false>(ta, tb, p, ((M + 2 * kGemmBM - 1) / (2 * kGemmBM)) * ((N + BN - 1) / BN), st);
   const int tiles = ((M + kGemmBM - 1) / kGemmBM) * ((N + BN - 1) / BN);
   return BN == 128 ? launch_gemm<128, false>(ta, tb, p, tiles, st) : launch_gemm<256, false>(ta, tb, p, tiles, st);
 }
@@ -167,6 +168,12 @@ static int conv_impl(const void* x, const void* w, const void* bias, void* out, 
   }
   const int BH = shapes[best][0], BW = shapes[best][1];
   const int BN = (Cout <= 128) ? 128 : 256;
+  // CTA pairs for the convolution are implemented and parity-tested but OFF by default: the full 768x512x121 VAE decode measured
+  // 58.7 ms without and 58.3 ms with them (the decode is bound by its activation traffic, not by operand fill).
+  // LTXB200_CONV_2CTA: unset / 0 = never, 1 = when there are enough patches to fill the machine twice, 2 = always (tests).
+  const char* e2 = getenv("LTXB200_CONV_2CTA");
+  const int env_2cta = e2 ? atoi(e2) : 0;
+  const bool two_cta = env_2cta == 2 || (env_2cta == 1 && static_cast<long long>(B) * T * ((H + BH - 1) / BH) * ((W + BW - 1) / BW) >= 2 * num_sms());
   const int taps = taps_t * taps_hw * taps_hw;
   CUtensorMap ta, tb;
   {
@@ -182,7 +189,7 @@ static int conv_impl(const void* x, const void* w, const void* bias, void* out, 
   {
     uint64_t dims[2] = {static_cast<uint64_t>(taps) * Cin, static_cast<uint64_t>(Cout)};
     uint64_t str[1] = {static_cast<uint64_t>(taps) * Cin * 2};
-    uint32_t box[2] = {kGemmBK, static_cast<uint32_t>(BN)};
+    uint32_t box[2] = {kGemmBK, static_cast<uint32_t>(two_cta ? BN / 2 : BN)};      // CTA pair: each CTA loads half of the weight tile
     if (make_tmap_bf16(&tb, w, 2, dims, str, box)) return kErrTensorMap;
   }
   GemmParams p{};
@@ -200,8 +207,13 @@ static int conv_impl(const void* x, const void* w, const void* bias, void* out, 
   p.c_st = st_t; p.c_shw = st_hw; p.cTin = Tin; p.c_off_hw = off_hw;
   p.n_fastest = (static_cast<long long>(Cout) * taps * Cin * 2 <= (48ll << 20)) ? 1 : 0;
   if (const char* e = getenv("LTXB200_GEMM_RASTER")) p.n_fastest = atoi(e);
-  const int tiles = B * T * p.c_tiles_h * p.c_tiles_w * ((Cout + BN - 1) / BN);
+  const int patches = B * T * p.c_tiles_h * p.c_tiles_w;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (two_cta) {
+    const int tiles2 = ((patches + 1) / 2) * ((Cout + BN - 1) / BN);
+    return BN == 128 ? launch_gemm_2cta<128, true>(ta, tb, p, tiles2, st) : launch_gemm_2cta<256, true>(ta, tb, p, tiles2, st);
+  }
+  const int tiles = patches * ((Cout + BN - 1) / BN);
   return BN == 128 ? launch_gemm<128, true>(ta, tb, p, tiles, st) : launch_gemm<256, true>(ta, tb, p, tiles, st);
 }
 

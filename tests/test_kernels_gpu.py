@@ -336,3 +336,19 @@ def test_torch_custom_ops_match_direct_calls():
     assert torch.equal(torch.ops.ltxb200.gemm_gate_residual(a, w, b, res, gate, 100), ops.gemm(a, w, b, residual=res, gate=gate, rows_per_gate=100))
     f = torch.compile(lambda a_, w_, b_: torch.ops.ltxb200.gemm(a_, w_, b_, 0) * 2, fullgraph=True, backend="eager")   # dynamo trace only
     assert torch.equal(f(a, w, b), ops.gemm(a, w, b) * 2)
+
+
+def test_conv3d_cta_pair_matches_single_cta(monkeypatch):
+    """The CTA-pair (cta_group::2) form of the implicit-GEMM convolution (LTXB200_CONV_2CTA=2 forces it) gives the same result as the
+    single-CTA kernel, including an odd patch count (the last pair's second CTA is all padding) and both tile widths."""
+    for (B, T, H, W, Cin, Cout, causal) in ((1, 3, 8, 16, 64, 128, True), (1, 3, 9, 20, 128, 256, False), (1, 5, 8, 16, 64, 64, True)):
+        x = rnd(B, T, H, W, Cin, seed=1)
+        w5 = rnd(Cout, Cin, 3, 3, 3, seed=2, scale=(27 * Cin) ** -0.5)
+        b = rnd(Cout, seed=3)
+        monkeypatch.setenv("LTXB200_CONV_2CTA", "0")
+        one = ops.conv3d(x, pack_w(w5), b, causal=causal)
+        monkeypatch.setenv("LTXB200_CONV_2CTA", "2")
+        two = ops.conv3d(x, pack_w(w5), b, causal=causal)
+        torch.cuda.synchronize()
+        assert torch.equal(one, two)
+        assert rel(two, ref_conv(x, w5, b, causal).permute(0, 2, 3, 4, 1)) < 6e-3
