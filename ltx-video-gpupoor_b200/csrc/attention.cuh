@@ -49,6 +49,14 @@ constexpr int kAttnBN = 128;   // keys per block
 
 template <int D>
 struct AttnCfg {
+  // kHalf (d = 64, -DLTXB200_ATTN64_HALFROW): every query row is shared by TWO threads (64 score columns each), i.e. 16 softmax warps =
+  // 4 per scheduler instead of 2, which is what the exp loop needs to hide its latencies (mufu_bench2: 18.0 -> 22.3 exp/clk/SM);
+  // the two halves exchange their block maxima through shared memory and a 64-thread named barrier.
+#ifdef LTXB200_ATTN64_HALFROW
+  static constexpr bool kHalf = (D == 64);
+#else
+  static constexpr bool kHalf = false;
+#endif
 #ifdef LTXB200_ATTN128_BN64
   // d = 128 alternative: 64-key blocks with FOUR S/P buffers (4*64 + 2*128 = 512 columns) = two per tile, so a tile's next scores are
   // computed while its current block is in the softmax (no split-phase tricks)
@@ -66,11 +74,12 @@ struct AttnCfg {
   static constexpr int kQBytes = kAttnBM * D * 2;            // one Q tile
   static constexpr int kKBytes = BN * D * 2;                 // one K (or V) block
   static constexpr int kStages = (128 * 1024) / (2 * kKBytes);          // 128 KB of K/V in flight
-  static constexpr int kBarBytes = 512;
+  static constexpr int kBarBytes = 512 + (kHalf ? 2 * 2 * 2 * 128 * 4 + 2 * 2 * 128 * 4 : 0);   // + max / sum exchange slots of the half rows
   static constexpr int kTotal = 2 * kQBytes + 2 * kStages * kKBytes + kBarBytes + 1024;
-  static constexpr int kThreads = 384;                       // 8 softmax warps + TMA warp + MMA warp + 2 idle (warpgroup alignment)
+  static constexpr int kSoftmaxWarps = kHalf ? 16 : 8;
+  static constexpr int kThreads = (kSoftmaxWarps + 4) * 32;  // softmax warps + TMA warp + MMA warp + 2 idle (warpgroup alignment)
   static constexpr uint32_t kTmemCols = 512;                 // kSBufs*BN + 2*D = 512 for both head dims
-  static constexpr int kSoftmaxRegs = 208, kOtherRegs = 64;  // setmaxnreg: the softmax warpgroups take the registers
+  static constexpr int kSoftmaxRegs = kHalf ? 104 : 208, kOtherRegs = 64;  // setmaxnreg: the softmax warpgroups take the registers
 };
 
 DEVI float fmax3(float a, float b, float c) {
@@ -82,7 +91,7 @@ DEVI float fmax3(float a, float b, float c) {
 // Lazy rescale of O_t and l: the reference max moves to m_new only for rows whose running max outgrew it by more
 // than 2^8 (warp-uniform branch: the TMEM ops are warp-collective), after the previous block's P.V MMA has retired.
 template <int D>
-DEVI void rescale_o(uint32_t tO, bool need, float m_new, float& m_ref, float& l, uint64_t* pv_done, uint32_t pv_parity) {
+DEVI void rescale_o(uint32_t tO, bool need, float m_new, float& m_ref, float& l, uint64_t* pv_done, uint32_t pv_parity) {   // D = columns of O this thread owns
   if (__any_sync(0xffffffffu, need)) {
     mbar_wait(pv_done, pv_parity);
     tc_fence_after();
@@ -213,6 +222,66 @@ DEVI void softmax_block(uint32_t tS, uint32_t tO, bool first, int kbase, int Lk,
   l += l0 + l1;
 }
 
+// Half-row form of softmax_block (kHalf): this thread owns columns [half*BN/2, +BN/2) of the row's scores, its partner thread (same
+// TMEM lane, the warp four further on) the other half.  Block maxima meet in shared memory (slot parity = block parity, so a slot is
+// rewritten only after the partner has passed the following barrier); P goes to this thread's half of the P columns, the row sum
+// stays partial (the halves are added in the epilogue), the lazy rescale touches this thread's half of the O columns.
+template <int D, int BN, bool kPredicated>
+DEVI void softmax_block_half(uint32_t tS, uint32_t tO_half, int half, bool first, int kbase, int Lk, const float* bias, float sc,
+                             float& m_ref, float& m_run, float& l, uint64_t* pv_done, uint32_t pv_parity, float* x_mine,
+                             const float* x_partner, int bar_id) {
+  constexpr int NC = BN / 2;
+  const float kLog2e = 1.4426950408889634f;
+  const int c_off = half * NC;
+  uint32_t v[NC];
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+  tmem_ld32(tS + c_off, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+#pragma unroll
+  for (int c = 0; c < NC; c += 32) {
+    tmem_wait_ld();
+    if (c + 32 < NC) tmem_ld32(tS + c_off + c + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c + 32]));
+    if (kPredicated) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int k = kbase + c_off + c + i;
+        float s = __uint_as_float(v[c + i]) * sc;
+        if (bias && k < Lk) s = fmaf(__ldg(bias + k), kLog2e, s);
+        if (k >= Lk) s = -INFINITY;
+        v[c + i] = __float_as_uint(s);
+        mx0 = fmaxf(mx0, s);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        mx0 = fmax3(mx0, __uint_as_float(v[c + i]), __uint_as_float(v[c + i + 1]));
+        mx1 = fmax3(mx1, __uint_as_float(v[c + i + 2]), __uint_as_float(v[c + i + 3]));
+      }
+    }
+  }
+  float m_blk = fmaxf(mx0, mx1);
+  if (!kPredicated) m_blk *= sc;
+  *x_mine = m_blk;
+  // both halves have their scores in registers and their maximum published once this barrier is passed (so the partner may also
+  // overwrite "my" score columns with its half of P)
+  tc_fence_before();
+  asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+  tc_fence_after();
+  m_blk = fmaxf(m_blk, *x_partner);
+  if (first) {
+    m_run = m_blk;
+    m_ref = (m_blk == -INFINITY) ? 0.f : m_blk;
+  } else {
+    m_run = fmaxf(m_run, m_blk);
+    rescale_o<D / 2>(tO_half, m_run > m_ref + 8.0f, m_run, m_ref, l, pv_done, pv_parity);
+  }
+  uint64_t ls[2] = {0ull, 0ull};
+#pragma unroll
+  for (int c = 0; c < NC; c += 32) exp_chunk<kPredicated, LTXB200_ATTN_POLY>(&v[c], sc, -m_ref, tS + ((c_off + c) >> 1), ls);
+  float l0, l1;
+  unpack_f32x2(add_f32x2(ls[0], ls[1]), l0, l1);
+  l += l0 + l1;
+}
+
 template <int D, bool kMasked>
 __global__ void __launch_bounds__(AttnCfg<D>::kThreads, 1)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -223,7 +292,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   constexpr int kSBufs = C::kSBufs;
   constexpr bool kSplit = C::kSplit;
   constexpr int kChunks = D / 64;                    // 64-wide (128 B) column chunks per row
-  constexpr int kTmaWarp = 8, kMmaWarp = 9;
+  constexpr bool kHalf = C::kHalf;
+  constexpr int kSmWarps = C::kSoftmaxWarps;
+  constexpr int kTmaWarp = kSmWarps, kMmaWarp = kSmWarps + 1;
   constexpr uint32_t kColS0 = 0, kColO0 = kSBufs * BN;
 
   extern __shared__ uint8_t smem_raw[];
@@ -260,11 +331,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       mbar_init(&q_empty[t], 1);
       mbar_init(&pv_done[t], 1);
       mbar_init(&o_done[t], 1);
-      mbar_init(&o_free[t], 4);
+      mbar_init(&o_free[t], kSmWarps / 2);
     }
     for (int i = 0; i < kSBufs; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 4);
+      mbar_init(&p_full[i], kSmWarps / 2);
       mbar_init(&s_read[i], 4);
       mbar_init(&p_half[i], 4);
     }
@@ -282,7 +353,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= 8) {
+  if (warp >= kSmWarps) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(C::kOtherRegs));
     if (warp == kTmaWarp && elect_one()) {
       // ================= TMA producer =================
@@ -400,11 +471,16 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   } else {
     // ================= softmax / correction / epilogue: warpgroup t owns query tile t =================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(C::kSoftmaxRegs));
-    const int t = warp >> 2;
+    const int t = kHalf ? (warp >> 3) : (warp >> 2);          // query tile of this warp
+    const int half = kHalf ? ((warp >> 2) & 1) : 0;           // which half of the score columns (kHalf)
     const int sub = warp & 3;
     const int row = sub * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(sub * 32) << 16;
     const uint32_t tO = tmem_base + kColO0 + t * D + lane_addr;
+    // kHalf exchange slots behind the barriers: xmax[tile][half][parity][row], xsum[tile][half][row]
+    float* xmax = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
+    float* xsum = xmax + 2 * 2 * 2 * 128;
+    const int pair_bar = 1 + t * 4 + sub;      // named barrier of the two warps that share these 32 rows
     uint32_t G = 0;                  // global key-block counter of this tile; its step is N = 2*G + t
     int it = 0;
     for (int w = blockIdx.x; w < p.total; w += gridDim.x, ++it) {
@@ -418,6 +494,16 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const int kbase = j * BN;
         const uint32_t tS = tmem_base + kColS0 + buf * BN + lane_addr;
         // full blocks without a bias take the lean path; the tail block / biased blocks take the predicated one
+        if constexpr (kHalf) {
+          float* xm = xmax + ((t * 2 + half) * 2 + (G & 1)) * 128 + row;
+          const float* xp = xmax + ((t * 2 + (half ^ 1)) * 2 + (G & 1)) * 128 + row;
+          if (kMasked && (bias != nullptr || kbase + BN > p.Lk))
+            softmax_block_half<D, BN, true>(tS, tO + half * (D / 2), half, j == 0, kbase, p.Lk, bias, p.scale_log2, m_ref, m_run, l, &pv_done[t],
+                                            (G - 1) & 1, xm, xp, pair_bar);
+          else
+            softmax_block_half<D, BN, false>(tS, tO + half * (D / 2), half, j == 0, kbase, p.Lk, bias, p.scale_log2, m_ref, m_run, l, &pv_done[t],
+                                             (G - 1) & 1, xm, xp, pair_bar);
+        } else
         if (kMasked && (bias != nullptr || kbase + BN > p.Lk))
           softmax_block<D, BN, true>(tS, tO, j == 0, kbase, p.Lk, bias, p.scale_log2, m_ref, m_run, l, &pv_done[t], (G - 1) & 1,
                                       kSplit ? &s_read[buf] : nullptr, kSplit ? &p_half[buf] : nullptr, lane);
@@ -432,6 +518,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       // ---- epilogue: O / l -> bf16 -> global ----
       mbar_wait(&o_done[t], it & 1);
       tc_fence_after();
+      if constexpr (kHalf) {                      // the row sum is the sum of the two halves' partial sums
+        xsum[(t * 2 + half) * 128 + row] = l;
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        l += xsum[(t * 2 + (half ^ 1)) * 128 + row];
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");      // the slot is free for the next item
+      }
       const float inv = (l > 0.f) ? __fdividef(1.0f, l) : 0.f;
       const int q = qp * 256 + t * kAttnBM + row;
       __nv_bfloat16* orow;
@@ -443,7 +535,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         orow = p.out + static_cast<long long>(b) * p.out_bs + static_cast<long long>(q) * p.out_ld + h * D;
       }
 #pragma unroll 1
-      for (int c = 0; c < D; c += 32) {
+      for (int c = kHalf ? half * (D / 2) : 0; c < (kHalf ? (half + 1) * (D / 2) : D); c += 32) {
         uint32_t o[32];
         tmem_ld32(tO + c, o);
         tmem_wait_ld();
