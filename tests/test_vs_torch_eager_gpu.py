@@ -67,3 +67,33 @@ def test_full_size_forward_vs_torch_eager_on_the_same_gpu(monkeypatch):
           f"{t_ref:.1f} ms, CUDA drop-in {t_ours:.1f} ms -> {t_ref / t_ours:.2f}x; rel_l2 between them {e:.2e}")
     assert e < 2e-2
     assert t_ours < t_ref
+
+
+def test_wan_full_size_forward_vs_torch_eager_on_the_same_gpu(monkeypatch):
+    """Wan2.1-1.3B at BASELINE config 3's size (latent 16x21x60x104 -> N = 32760 tokens, cond + uncond sequences), 2 of the 30 layers:
+    the oracle in bf16 on the GPU with torch SDPA (flash kernels; model.py:168-171 -> pay_attention) vs WanModel."""
+    from ltx_video_gpupoor_b200.wan.model import WanModel
+    from ltx_video_gpupoor_b200.wan.posemb_layers import get_rotary_pos_embed
+    from oracle import wan_oracle as W
+    L = 2
+    cfg = dict(W.WAN_1_3B, num_layers=L)
+    sd = W.make_wan_state_dict(cfg, seed=0)
+    m = WanModel(dim=cfg["dim"], ffn_dim=cfg["ffn_dim"], num_heads=cfg["num_heads"], num_layers=L)
+    m.load_state_dict(sd)
+    sd_gpu = {k: v.to(DEV, BF) for k, v in sd.items()}
+    g = torch.Generator().manual_seed(5)
+    lat = torch.randn(16, 21, 60, 104, generator=g).to(DEV)
+    ctx, ctx0 = torch.randn(128, 4096, generator=g).to(DEV, BF), torch.randn(128, 4096, generator=g).to(DEV, BF)
+    t = torch.tensor([700.0], device=DEV)
+    cos, sin = get_rotary_pos_embed(lat.shape[1:])
+    cos, sin = cos.to(DEV), sin.to(DEV)
+
+    monkeypatch.setattr(W, "attention_core", _sdpa_core)
+    with torch.no_grad():
+        t_ref, y_ref = _time(lambda: W.wan_forward(sd_gpu, cfg, [lat, lat], t, [ctx, ctx0], cos, sin), reps=2)
+        t_ours, y = _time(lambda: m([lat, lat], t=t, context=[ctx, ctx0], freqs=(cos, sin)), reps=2)
+    e = max(O.rel_l2(a.float().cpu(), b.float().cpu()) for a, b in zip(y, y_ref))
+    print(f"\nWan-1.3B full-size forward, {L} layers x 2 sequences x 32760 tokens on one B200: torch eager bf16 + SDPA {t_ref:.1f} ms, "
+          f"CUDA drop-in {t_ours:.1f} ms -> {t_ref / t_ours:.2f}x; rel_l2 between them {e:.2e}")
+    assert e < 2e-2
+    assert t_ours < t_ref
