@@ -149,18 +149,6 @@ DEVI void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
         : "memory");
   } while (!ok);
 }
-// non-blocking probe (test_wait never suspends the thread): for a single thread that polls several barriers
-DEVI bool mbar_test(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred P1;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
-      "selp.b32 %0, 1, 0, P1;\n\t}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
 #ifdef LTXB200_DEBUG_HANG
 // debug build: a wait that does not complete within ~1 s reports who is stuck and traps instead of hanging the GPU
 #define mbar_wait(bar, parity) ::b200::mbar_wait_dbg((bar), (parity), __LINE__)
