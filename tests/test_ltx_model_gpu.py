@@ -454,3 +454,32 @@ def test_pipeline_callbacks_and_interrupt(golden_dir):
     y = tr(torch.zeros(1, 72, 128), freqs_cis=tr.precompute_freqs_cis(torch.zeros(1, 3, 72, device="cuda")), encoder_hidden_states=g["pe"],
            timestep=torch.ones(1, 1), encoder_attention_mask=g["pm"], latent_shape=(3, 4, 6), ltxv_model=model, return_dict=False)
     assert y == [None]
+
+
+def test_transformer_13b_geometry_head_dim_128():
+    """The LTX-Video 13B (0.9.7) transformer uses 32 heads x 128 = 4096 channels, 48 layers; what the reference app runs for the
+    multi-scale flow.  Same code path at a reduced width (8 heads x 128 = 1024, 2 layers, 1024 % 6 == 4096 % 6 == 4 for the RoPE
+    padding columns): the d = 128 attention kernel and the wider-head RoPE/norm kernels inside Transformer3DModel vs the fp32 oracle."""
+    cfg = dict(O.LTX_2B, num_layers=2, num_attention_heads=8, attention_head_dim=128, cross_attention_dim=1024)
+    sd = O.make_transformer_state_dict(cfg, seed=3)
+    m = Transformer3DModel(num_layers=2, num_attention_heads=8, attention_head_dim=128, cross_attention_dim=1024)
+    m.load_state_dict(sd)
+    f, h, w = 3, 6, 8
+    g = torch.Generator().manual_seed(9)
+    hidden = torch.randn(2, f * h * w, 128, generator=g)
+    enc = torch.randn(2, 24, 4096, generator=g)
+    mask = torch.ones(2, 24)
+    mask[1, 17:] = 0
+    t = torch.tensor([[0.9], [0.4]])
+    coords = O.latent_to_pixel_coords(O.latent_coords(f, h, w, 1)).float()
+    coords[:, 0] *= 1.0 / 25.0
+    cos_sin = O.precompute_freqs_cis(coords, 1024, cfg["rope_theta"], cfg["rope_max_pos"])
+    ref = O.transformer_forward(sd, cfg, hidden, cos_sin, enc, t, mask, latent_shape=(f, h, w))
+    fc = m.precompute_freqs_cis(coords.to(DEV))
+    assert O.rel_l2(fc[0].float().cpu(), cos_sin[0]) < 4e-3
+    y = m(hidden.to(DEV), freqs_cis=fc, encoder_hidden_states=enc.to(DEV), timestep=t.to(DEV), encoder_attention_mask=mask.to(DEV),
+          latent_shape=(f, h, w), return_dict=False)[0]
+    torch.cuda.synchronize()
+    err = O.rel_l2(y.float().cpu(), ref)
+    print(f"transformer[13B geometry, d=128] rel_l2 vs fp32 oracle = {err:.3e}")
+    assert err < TOL_MODEL_OUT
