@@ -111,3 +111,15 @@ def test_wan_oracle_matches_reference_fixture(golden_dir):
     W.t2v_denoise(sd, cfg, g["lat"].double(), g["ctx"].double(), g["ctx0"].double(), steps=4, shift=5.0, guide_scale=5.0, per_step=steps)
     for a, b in zip(steps, g["loop"]):
         assert W.rel_l2(a, b) < 5e-5
+
+
+def test_wan_rope_tables_riflex_bit_exact(golden_dir):
+    """get_rotary_pos_embed(enable_RIFLEx=...) against rows recorded from the unmodified reference (oracle/gen_golden_rope.py)."""
+    from ltx_video_gpupoor_b200.wan.posemb_layers import get_rotary_pos_embed
+    g = torch.load(os.path.join(golden_dir, "wan_rope_riflex.pt"), weights_only=False)
+    assert len(g) == 4
+    for (size, rf), (c_ref, s_ref) in g.items():
+        cos, sin = get_rotary_pos_embed(size, enable_RIFLEx=rf)
+        assert torch.equal(cos[::7], c_ref) and torch.equal(sin[::7], s_ref), (size, rf)
+    a, b = get_rotary_pos_embed((33, 8, 12), False), get_rotary_pos_embed((33, 8, 12), True)
+    assert not torch.equal(a[0][:, :44], b[0][:, :44]) and torch.equal(a[0][:, 44:], b[0][:, 44:])      # only the time axis changes
