@@ -86,11 +86,16 @@ class LTXVideoPipeline:
         return self.transformer.device
 
     # ---------------------------------------------------------------------------------------------
-    def prepare_latents(self, latents, media_items, timestep, latent_shape, dtype, device, generator):
-        """pipeline_ltx_video.py:632-710: noise drawn in the patchified shape (b, f*h*w, c) on the generator's device."""
+    def prepare_latents(self, latents, media_items, timestep, latent_shape, dtype, device, generator,
+                        vae_per_channel_normalize: bool = True):
+        """pipeline_ltx_video.py:632-710: noise drawn in the patchified shape (b, f*h*w, c) on the generator's device; `media_items`
+        (img2img / vid2vid, :682-687) are encoded with the VAE — `latent_dist.sample()` draws from the global RNG as in the
+        reference — and noised to the first timestep like user-provided latents."""
+        assert latents is None or media_items is None, "Cannot provide both latents and media_items. Please provide only one of the two."
+        assert (latents is None and media_items is None) or timestep < 1.0, \
+            "Input media_item or latents are provided, but they will be replaced with noise."
         if media_items is not None:
-            raise NotImplementedError("media_items need the VAE encoder (SURVEY §8f#3)")
-        assert latents is None or timestep < 1.0, "Input latents are provided, but they will be replaced with noise."
+            latents = vae_encode(media_items.to(device), self.vae, vae_per_channel_normalize=vae_per_channel_normalize)
         b, c, f, h, w = latent_shape
         gdev = generator.device if isinstance(generator, torch.Generator) else device
         noise = torch.randn((b, f * h * w, c), generator=generator, device=gdev, dtype=dtype).to(device)
@@ -257,7 +262,8 @@ class LTXVideoPipeline:
 
         # ---- latents (:1056-1088); drawn in prompt_embeds' dtype like the reference (:1061), kept as an fp32 master copy
         noise_dtype = prompt_embeds.dtype if prompt_embeds.dtype in (torch.float32, BF16) else torch.float32
-        init = self.prepare_latents(latents, media_items, ts_host[0], latent_shape, noise_dtype, device, generator)
+        init = self.prepare_latents(latents, media_items, ts_host[0], latent_shape, noise_dtype, device, generator,
+                                    vae_per_channel_normalize=vae_per_channel_normalize)
         tokens, pixel_coords, conditioning_mask, num_cond_latents = self.prepare_conditioning(
             conditioning_items, init.clone(), num_frames, height, width, vae_per_channel_normalize=vae_per_channel_normalize,
             generator=generator)

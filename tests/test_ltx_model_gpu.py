@@ -483,3 +483,29 @@ def test_transformer_13b_geometry_head_dim_128():
     err = O.rel_l2(y.float().cpu(), ref)
     print(f"transformer[13B geometry, d=128] rel_l2 vs fp32 oracle = {err:.3e}")
     assert err < TOL_MODEL_OUT
+
+
+def test_pipeline_media_items_vid2vid():
+    """`media_items` (pipeline_ltx_video.py:682-710): the video is encoded with the VAE, noised to the first kept timestep and denoised from
+    there — identical to handing the same encoded latents in through `latents=` (the reference treats both alike, :688-710)."""
+    from ltx_video_gpupoor_b200.ltx.causal_video_autoencoder import vae_encode
+    pipe, _, _ = _pipe(2)
+    vsd = O.make_vae_encoder_state_dict(seed=2)
+    vsd.update({k: v for k, v in O.make_vae_decoder_state_dict(seed=1).items() if k.startswith("decoder.")})
+    pipe.vae.load_state_dict(vsd)
+    g = torch.Generator().manual_seed(4)
+    video = (torch.rand(1, 3, 17, 128, 192, generator=g) * 2 - 1)
+    pe, pm = torch.randn(1, 16, 4096, generator=g), torch.ones(1, 16)
+    kw = dict(height=128, width=192, num_frames=17, frame_rate=25.0, prompt_embeds=pe, prompt_attention_mask=pm, num_inference_steps=4,
+              skip_initial_inference_steps=2, guidance_scale=1.0, stg_scale=0.0, rescaling_scale=1.0, output_type="latent", return_dict=False,
+              is_video=True, vae_per_channel_normalize=True)
+    torch.manual_seed(11)
+    a = pipe(media_items=video, generator=torch.Generator().manual_seed(7), **kw)[0]
+    torch.manual_seed(11)
+    lat = vae_encode(video.cuda(), pipe.vae, vae_per_channel_normalize=True)
+    b = pipe(latents=lat, generator=torch.Generator().manual_seed(7), **kw)[0]
+    assert tuple(a.shape) == (1, 128, 3, 4, 6) and torch.equal(a, b)
+    with pytest.raises(AssertionError):
+        pipe(media_items=video, latents=lat, generator=torch.Generator().manual_seed(7), **kw)
+    with pytest.raises(AssertionError):                       # no skipped steps: the first timestep is 1.0 and the media would be replaced by noise
+        pipe(media_items=video, generator=torch.Generator().manual_seed(7), **{**kw, "skip_initial_inference_steps": 0})
