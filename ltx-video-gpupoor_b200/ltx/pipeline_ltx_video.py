@@ -105,20 +105,40 @@ class LTXVideoPipeline:
         assert tuple(latents.shape) == tuple(latent_shape)
         return timestep * noise + (1 - timestep) * latents.to(device=device, dtype=dtype)
 
+    @staticmethod
+    def _handle_non_first_conditioning_sequence(init_latents, cmask, latents, media_frame_number: int, strength: float,
+                                                num_prefix_latent_frames: int = 2):
+        """pipeline_ltx_video.py:1614-1687 with the defaults the caller uses (prefix mode "concat"): the conditioning sequence minus
+        its first two latent frames is blended into the noise at its position; the two prefix frames are returned to be appended as
+        extra tokens."""
+        f_l, f_p = latents.shape[2], num_prefix_latent_frames
+        assert f_l >= f_p and media_frame_number % 8 == 0
+        if f_l > f_p:
+            f0 = media_frame_number // 8 + f_p
+            f1 = f0 + f_l - f_p
+            init_latents[:, :, f0:f1] = torch.lerp(init_latents[:, :, f0:f1], latents[:, :, f_p:], strength)
+            cmask[:, f0:f1] = strength
+        return init_latents, cmask, latents[:, :, :f_p]
+
     def prepare_conditioning(self, conditioning_items, init_latents, num_frames, height, width,
                              vae_per_channel_normalize: bool = False, generator=None):
-        """pipeline_ltx_video.py:1344-1548, first-frame / first-sequence (media_frame_number == 0) conditioning from pixels
-        (encoded with the VAE, :1420-1424) or pre-encoded latents; returns (patchified latents, pixel coords,
-        conditioning mask | None, num extra tokens)."""
+        """pipeline_ltx_video.py:1344-1548: conditioning from pixels (encoded with the VAE, :1420-1424) or pre-encoded latents.
+        media_frame_number == 0: the latents are blended into the start of the noise and marked in the mask (:1427-1448);
+        otherwise (:1449-1503) a single frame — or the two-frame prefix of a sequence whose remainder is blended in place — is
+        noised, patchified and PREPENDED as extra tokens whose pixel coordinates carry the target frame number.
+        Returns (patchified latents, pixel coords, conditioning mask | None, number of extra tokens)."""
         cmask = None
+        extra_lat, extra_px, extra_mask, extra_n = [], [], [], 0
+        scale = get_vae_size_scale_factor(self.vae)
+        causal_fix = self.transformer.config.causal_temporal_positioning
         if conditioning_items:
             cmask = torch.zeros(init_latents[:, 0].shape, dtype=torch.float32, device=init_latents.device)
             for item in conditioning_items:
-                if item.media_frame_number != 0:
-                    raise NotImplementedError("only media_frame_number == 0 conditioning is implemented")
+                fno = int(item.media_frame_number)
                 if item.latents is None:
                     m = item.media_item
                     assert m is not None and m.ndim == 5 and m.shape[2] % 8 == 1                  # :1409-1415
+                    assert fno >= 0 and fno + m.shape[2] <= num_frames
                     if tuple(m.shape[-2:]) != (height, width):
                         raise NotImplementedError("conditioning media must have the target size (resize / border stripping is not implemented)")
                     lat = vae_encode(m, self.vae, vae_per_channel_normalize=vae_per_channel_normalize,
@@ -127,15 +147,35 @@ class LTXVideoPipeline:
                     lat = item.latents.to(device=init_latents.device, dtype=init_latents.dtype)
                 _, _, f_l, h_l, w_l = lat.shape
                 s = item.conditioning_strength
-                init_latents[:, :, :f_l, :h_l, :w_l] = torch.lerp(init_latents[:, :, :f_l, :h_l, :w_l], lat, s)   # :1436-1445
-                cmask[:, :f_l, :h_l, :w_l] = s
+                if fno == 0:
+                    init_latents[:, :, :f_l, :h_l, :w_l] = torch.lerp(init_latents[:, :, :f_l, :h_l, :w_l], lat, s)   # :1436-1445
+                    cmask[:, :f_l, :h_l, :w_l] = s
+                    continue
+                assert (h_l, w_l) == tuple(init_latents.shape[-2:]), "non-first conditioning items must have the target size (:1410-1412)"
+                if f_l > 1:                                                                        # a sequence (n_frames > 1)
+                    init_latents, cmask, lat = self._handle_non_first_conditioning_sequence(init_latents, cmask, lat, fno, s)
+                gdev = generator.device if isinstance(generator, torch.Generator) else lat.device
+                noise = torch.randn(lat.shape, generator=generator if isinstance(generator, torch.Generator) else None,
+                                    device=gdev, dtype=lat.dtype).to(lat.device)                  # :1466-1471
+                lat = torch.lerp(noise, lat, s)
+                tok, lc = self.patchifier.patchify(lat)
+                px = latent_to_pixel_coords_from_factors(lc, scale, causal_fix)
+                px[:, 0] += fno                                                                    # :1487
+                extra_n += tok.shape[1]
+                extra_lat.append(tok)
+                extra_px.append(px)
+                extra_mask.append(torch.full(tok.shape[:2], s, dtype=torch.float32, device=init_latents.device))
         tokens, coords = self.patchifier.patchify(init_latents)
-        px = latent_to_pixel_coords_from_factors(coords, get_vae_size_scale_factor(self.vae),
-                                                 self.transformer.config.causal_temporal_positioning)
+        px = latent_to_pixel_coords_from_factors(coords, scale, causal_fix)
         if cmask is None:
             return tokens, px, None, 0
         cm, _ = self.patchifier.patchify(cmask.unsqueeze(1))
-        return tokens, px, cm.squeeze(-1), 0
+        cm = cm.squeeze(-1)
+        if extra_lat:                                                                              # :1519-1528
+            tokens = torch.cat([*extra_lat, tokens], dim=1)
+            px = torch.cat([*extra_px, px], dim=2)
+            cm = torch.cat([*extra_mask, cm], dim=1)
+        return tokens, px, cm, extra_n
 
     def _step_noise(self, st):
         """rf.py:372 `torch.randn_like(sample)` for the stochastic sampler, drawn from the call's generator when there is one."""
@@ -302,7 +342,7 @@ class LTXVideoPipeline:
             if per_step is not None:
                 per_step.append(st.lat32.view(1, N, C).clone())
             if callback is not None:
-                prev = st.lat32.view(N, C).transpose(0, 1).reshape(C, latent_num_frames, latent_height, latent_width)
+                prev = st.lat32.view(N, C)[num_cond_latents:].transpose(0, 1).reshape(C, latent_num_frames, latent_height, latent_width)
                 callback(i, prev, False, pass_no=pass_no)
             if callback_on_step_end is not None:
                 callback_on_step_end(self, i, ts_host[i], {})

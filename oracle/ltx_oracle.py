@@ -461,9 +461,11 @@ def denoise_loop(sd, cfg, latents: Tensor, enc: Tensor, enc_mask: Tensor, *, num
                  skip_block_list: Optional[list] = None, strategy: Optional[str] = None,
                  conditioning_mask: Optional[Tensor] = None, model_dtype=torch.float32,
                  per_step: Optional[list] = None, timesteps: Optional[Tensor] = None,
-                 guidance_timesteps: Optional[List[float]] = None) -> Tensor:
+                 guidance_timesteps: Optional[List[float]] = None, pixel_coords: Optional[Tensor] = None) -> Tensor:
     """LTXVideoPipeline.__call__ denoise loop (pipeline_ltx_video.py:919-1268) on patchified
     latents [b, N, C]; returns final patchified latents.  image_cond_noise_scale = 0.
+    pixel_coords [b, 3, N]: the coordinates prepare_conditioning returned (:1076-1093) when extra keyframe tokens were prepended;
+    default = the plain latent grid.
     guidance_scale / stg_scale / rescaling_scale / skip_block_list may be per-guidance-timestep lists (:959-1017)."""
     b, N, C = latents.shape
     D = cfg["num_attention_heads"] * cfg["attention_head_dim"]
@@ -501,8 +503,8 @@ def denoise_loop(sd, cfg, latents: Tensor, enc: Tensor, enc_mask: Tensor, *, num
         enc_b = torch.cat([neg_enc, enc]); mask_b = torch.cat([neg_mask, enc_mask])
     if do_stg:
         enc_b = torch.cat([enc_b, enc]); mask_b = torch.cat([mask_b, enc_mask])
-    coords = latent_to_pixel_coords(latent_coords(num_frames_lat, lat_h, lat_w, b, latents.device))
-    frac = coords.to(torch.float32)
+    coords = pixel_coords if pixel_coords is not None else latent_to_pixel_coords(latent_coords(num_frames_lat, lat_h, lat_w, b, latents.device))
+    frac = coords.to(torch.float32).clone()
     frac[:, 0] = frac[:, 0] * (1.0 / frame_rate)                                     # :1086-1087
     cos_sin = precompute_freqs_cis(frac, D, cfg["rope_theta"], cfg["rope_max_pos"], model_dtype)
     cmask = None if conditioning_mask is None else torch.cat([conditioning_mask] * num_conds)

@@ -179,3 +179,26 @@ def test_torch_custom_ops_registered_with_fake_kernels():
         assert torch.ops.ltxb200.norm_mod(a, None, None, 0, 1e-6, False).shape == (48, 64)
     with pytest.raises(Exception):
         torch.ops.ltxb200.gemm(torch.zeros(8, 64, dtype=torch.bfloat16), torch.zeros(16, 64, dtype=torch.bfloat16), None, 0)
+
+
+def test_prepare_conditioning_keyframes_bit_exact(golden_dir):
+    """LTXVideoPipeline.prepare_conditioning (host-side torch code; pre-encoded conditioning latents, so no GPU is involved) against the
+    outputs of the unmodified reference method for first-frame, keyframe, first+last, mid-sequence and prefix-only-sequence conditioning
+    (oracle/gen_golden_conditioning.py): tokens, pixel coordinates, mask and extra-token count."""
+    from types import SimpleNamespace
+    from ltx_video_gpupoor_b200.ltx.pipeline_ltx_video import ConditioningItem, LTXVideoPipeline
+    from ltx_video_gpupoor_b200.ltx.symmetric_patchifier import SymmetricPatchifier
+    g = torch.load(os.path.join(golden_dir, "ltx_conditioning.pt"), weights_only=False)
+    F_l, H_l, W_l, num_frames, height, width = g["geom"]
+    pipe = LTXVideoPipeline.__new__(LTXVideoPipeline)
+    pipe.vae = SimpleNamespace(spatial_downscale_factor=32, temporal_downscale_factor=8)
+    pipe.patchifier = SymmetricPatchifier(1)
+    pipe.transformer = SimpleNamespace(config=SimpleNamespace(causal_temporal_positioning=True))
+    assert len(g["cases"]) == 5
+    for name, c in g["cases"].items():
+        init = torch.randn(1, 128, F_l, H_l, W_l, generator=torch.Generator().manual_seed(1))
+        items = [ConditioningItem(latents=g["enc"][n].clone(), media_frame_number=f, conditioning_strength=s) for n, f, s in c["items"]]
+        tok, px, cm, extra = pipe.prepare_conditioning(items, init, num_frames, height, width, vae_per_channel_normalize=True,
+                                                       generator=torch.Generator().manual_seed(2))
+        assert extra == c["extra"] and torch.equal(tok, c["tokens"]) and torch.equal(cm, c["mask"]), name
+        assert torch.equal(px.to(c["coords"].dtype), c["coords"]), name

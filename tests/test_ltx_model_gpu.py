@@ -509,3 +509,32 @@ def test_pipeline_media_items_vid2vid():
         pipe(media_items=video, latents=lat, generator=torch.Generator().manual_seed(7), **kw)
     with pytest.raises(AssertionError):                       # no skipped steps: the first timestep is 1.0 and the media would be replaced by noise
         pipe(media_items=video, generator=torch.Generator().manual_seed(7), **{**kw, "skip_initial_inference_steps": 0})
+
+
+def test_pipeline_keyframe_conditioning_vs_oracle():
+    """A conditioning frame in the MIDDLE of the video (media_frame_number = 16, pipeline_ltx_video.py:1449-1503): its noised latent is
+    prepended as 24 extra tokens with their own pixel coordinates and per-token timesteps, and dropped again before unpatchify; the loop
+    is compared with the oracle driven by the same tokens / coordinates / mask."""
+    pipe, sd, _ = _pipe(2)
+    g = torch.Generator().manual_seed(3)
+    pe, pm = torch.randn(1, 16, 4096, generator=g), torch.ones(1, 16)
+    key = torch.randn(1, 128, 1, 4, 6, generator=g)
+    items = lambda: [ConditioningItem(latents=key.clone(), media_frame_number=16, conditioning_strength=1.0)]
+    per_step = []
+    out = pipe(height=128, width=192, num_frames=33, frame_rate=25.0, prompt_embeds=pe, prompt_attention_mask=pm, num_inference_steps=3,
+               guidance_scale=1.0, stg_scale=0.0, rescaling_scale=1.0, generator=torch.Generator().manual_seed(5), output_type="latent",
+               return_dict=False, is_video=True, conditioning_items=items(), _per_step_latents=per_step)[0]
+    assert tuple(out.shape) == (1, 128, 5, 4, 6) and per_step[0].shape[1] == 120 + 24
+    # the same RNG stream on the host: initial noise, then the keyframe noise inside prepare_conditioning
+    gen = torch.Generator().manual_seed(5)
+    init = O.unpatchify(torch.randn(1, 120, 128, generator=gen), 5, 4, 6)
+    tok, px, cm, extra = pipe.prepare_conditioning(items(), init.clone(), 33, 128, 192, vae_per_channel_normalize=True, generator=gen)
+    assert extra == 24
+    ref_steps = []
+    O.denoise_loop(sd, O.LTX_2B, tok.float(), pe, pm, num_frames_lat=5, lat_h=4, lat_w=6, frame_rate=25.0, num_steps=3,
+                   conditioning_mask=cm, per_step=ref_steps, pixel_coords=px)
+    for i, (a, b) in enumerate(zip(per_step, ref_steps)):
+        err = O.rel_l2(a.cpu(), b)
+        print(f"keyframe conditioning step {i}: rel_l2 = {err:.3e}")
+        assert err < TOL_LATENTS
+    assert torch.equal(per_step[-1][:, :24].cpu(), tok[:, :24].float())          # the hard-conditioned keyframe tokens are never touched
