@@ -5,7 +5,8 @@ Scope: noise, UniPC schedule, RoPE tables, the per-step two-seq
 consumed by WanI2VCrossAttention), CFG with the optional CFG-Zero* projection, scheduler step.  `y` is either passed in or
 built here the way the reference builds it (:232-244, 262-277): the start image (a [3, H, W] tensor in [-1, 1], already at the
 output size — PIL / lanczos resizing is media I/O) padded with F-1 zero frames goes through `WanVAE.encode` (wan/vae.py) and
-the 4-channel first-frame mask is stacked on top.  CLIP visual (:219-224) and T5 are out of scope: pass `clip_fea=`
+the 4-channel conditioning-frame mask is stacked on top; an end image (`image_end`, :191-199) adds one frame that is encoded without the
+VAE's feature caches.  CLIP visual (:219-224) and T5 are out of scope: pass `clip_fea=`
 [1, 257, 1280] and `context=` / `context_null=`.  The result is the denoised latent [16, (F-1)/4+1, H/8, W/8] (fp32).
 """
 from __future__ import annotations
@@ -32,27 +33,45 @@ class WanI2V:
         self.vae_stride, self.patch_size, self.z_dim = vae_stride, patch_size, z_dim
         self._interrupt = False
 
-    def first_frame_mask(self, frame_num: int, lat_h: int, lat_w: int) -> torch.Tensor:
-        """image2video.py:232-244 (no end frame): ones on the first video frame, repeated 4x so that the 1 + (F-1) frames fold into
-        [4, (F-1)/4+1, lat_h, lat_w]."""
+    def first_frame_mask(self, frame_num: int, lat_h: int, lat_w: int, any_end_frame: bool = False,
+                         add_frames_for_end_image: bool = True) -> torch.Tensor:
+        """image2video.py:232-244: ones on the conditioning frames (the first, and the last when there is an end image), the first (and an
+        ADDED last) frame repeated 4x so that the frames fold into [4, latent frames, lat_h, lat_w]."""
         msk = torch.ones(1, frame_num, lat_h, lat_w, device=self.device)
-        msk[:, 1:] = 0
-        msk = torch.concat([torch.repeat_interleave(msk[:, 0:1], repeats=4, dim=1), msk[:, 1:]], dim=1)
+        if any_end_frame:
+            msk[:, 1:-1] = 0
+            if add_frames_for_end_image:
+                msk = torch.concat([torch.repeat_interleave(msk[:, 0:1], repeats=4, dim=1), msk[:, 1:-1],
+                                    torch.repeat_interleave(msk[:, -1:], repeats=4, dim=1)], dim=1)
+            else:
+                msk = torch.concat([torch.repeat_interleave(msk[:, 0:1], repeats=4, dim=1), msk[:, 1:]], dim=1)
+        else:
+            msk[:, 1:] = 0
+            msk = torch.concat([torch.repeat_interleave(msk[:, 0:1], repeats=4, dim=1), msk[:, 1:]], dim=1)
         msk = msk.view(1, msk.shape[1] // 4, 4, lat_h, lat_w)
         return msk.transpose(1, 2)[0]
 
     @torch.no_grad()
-    def encode_conditioning(self, image_start: torch.Tensor, frame_num: int) -> torch.Tensor:
-        """image2video.py:262-277: y = [mask(4) | VAE latent(16) of (image, zeros x (F-1))] -> [20, (F-1)/4+1, H/8, W/8] fp32."""
+    def encode_conditioning(self, image_start: torch.Tensor, frame_num: int, image_end: Optional[torch.Tensor] = None,
+                            add_frames_for_end_image: bool = True) -> torch.Tensor:
+        """image2video.py:262-277: y = [mask(4) | VAE latent(16) of (image, zeros ..., [end image])] -> [20, latent frames, H/8, W/8] fp32.
+        `frame_num` is the frame count AFTER the reference's `frame_num += 1` for an added end frame (:196-199)."""
         if self.vae is None:
             raise RuntimeError("WanI2V(vae=WanVAE with encoder weights) is needed to build y from image_start")
         img = image_start.to(self.device, torch.float32)
         assert img.dim() == 3 and img.shape[0] == 3, "image_start: [3, H, W] tensor in [-1, 1] at the output size"
         h, w = img.shape[1:]
         assert h % (self.vae_stride[1] * self.patch_size[1]) == 0 and w % (self.vae_stride[2] * self.patch_size[2]) == 0
-        enc = torch.concat([img[:, None], torch.zeros(3, frame_num - 1, h, w, device=self.device)], dim=1)
-        lat_y = self.vae.encode([enc], 0)[0]
-        return torch.concat([self.first_frame_mask(frame_num, h // self.vae_stride[1], w // self.vae_stride[2]), lat_y])
+        any_end = image_end is not None
+        if any_end:
+            end = image_end.to(self.device, torch.float32)
+            assert tuple(end.shape) == tuple(img.shape)
+            enc = torch.concat([img[:, None], torch.zeros(3, frame_num - 2, h, w, device=self.device), end[:, None]], dim=1)
+        else:
+            enc = torch.concat([img[:, None], torch.zeros(3, frame_num - 1, h, w, device=self.device)], dim=1)
+        lat_y = self.vae.encode([enc], 0, any_end_frame=any_end and add_frames_for_end_image)[0]
+        msk = self.first_frame_mask(frame_num, h // self.vae_stride[1], w // self.vae_stride[2], any_end, add_frames_for_end_image)
+        return torch.concat([msk, lat_y])
 
     @torch.no_grad()
     def generate(self, input_prompt=None, image_start=None, image_end=None, height=720, width=1280, fit_into_canvas=True,
@@ -63,21 +82,29 @@ class WanI2V:
                  context: Optional[torch.Tensor] = None, context_null: Optional[torch.Tensor] = None,
                  clip_fea: Optional[torch.Tensor] = None, y: Optional[torch.Tensor] = None,
                  noise: Optional[torch.Tensor] = None, _per_step_latents=None, **bbargs):
-        if audio_proj is not None or audio_scale is not None or image_end is not None:
-            raise NotImplementedError("fantasytalking audio / end-frame conditioning are out of scope")
+        if audio_proj is not None or audio_scale is not None:
+            raise NotImplementedError("fantasytalking audio conditioning is out of scope")
+        any_end_frame = image_end is not None
+        add_frames_for_end_image = model_filename is None or "image2video" in model_filename or "fantasy" in model_filename   # :191
+        lat_frames = (frame_num - 1) // self.vae_stride[0] + 1
+        if any_end_frame and add_frames_for_end_image:                                        # :194-199
+            frame_num += 1
+            lat_frames = (frame_num - 2) // self.vae_stride[0] + 2
         if clip_fea is None:
             raise NotImplementedError("CLIP visual is out of scope: pass clip_fea= [1,257,1280]")
         if y is None:
             if not torch.is_tensor(image_start):
                 raise NotImplementedError("pass y= [20,T,H/8,W/8], or image_start= as a [3,H,W] tensor in [-1,1] (PIL resizing is media I/O)")
-            y = self.encode_conditioning(image_start, frame_num)
+            if any_end_frame and not torch.is_tensor(image_end):
+                raise NotImplementedError("image_end= must be a [3,H,W] tensor in [-1,1] (PIL resizing is media I/O)")
+            y = self.encode_conditioning(image_start, frame_num, image_end, add_frames_for_end_image)
             height, width = image_start.shape[1:]
         if context is None or (guide_scale != 1 and context_null is None):
             raise NotImplementedError("the T5 text encoder is out of scope: pass context= / context_null= embeddings [L, 4096]")
         if sample_solver not in ("unipc", "dpm++"):
             raise NotImplementedError("Unsupported solver.")
         dev = self.device
-        target_shape = (self.z_dim, (frame_num - 1) // self.vae_stride[0] + 1, height // self.vae_stride[1], width // self.vae_stride[2])
+        target_shape = (self.z_dim, lat_frames, height // self.vae_stride[1], width // self.vae_stride[2])
         assert tuple(y.shape) == (20,) + target_shape[1:], f"y must be [20, {target_shape[1:]}]"
         if noise is None:
             seed_g = torch.Generator(device=dev)

@@ -222,7 +222,9 @@ class WanVAE:
         """vae.py:825-829.  tile_size is accepted and ignored: 180 GB of HBM hold the whole video (the reference tiles to fit
         consumer cards, :92-115)."""
         if any_end_frame:
-            raise NotImplementedError("any_end_frame decoding is out of scope")
+            # vae.py:597-601: the last latent frame is decoded on its own, without the feature caches (one image), and appended;
+            # conv2 is 1x1x1, so splitting before it is the same computation (oracle: exact in fp64)
+            return [torch.cat([self.decode_one(u[:, :-1]), self.decode_one(u[:, -1:])], dim=1) for u in zs]
         return [self.decode_one(u) for u in zs]
 
     def _downsample(self, p, x, mode):
@@ -261,5 +263,6 @@ class WanVAE:
     def encode(self, videos: List[torch.Tensor], tile_size: int = 0, any_end_frame: bool = False) -> List[torch.Tensor]:
         """vae.py:806-816.  tile_size is accepted and ignored (see decode)."""
         if any_end_frame:
-            raise NotImplementedError("any_end_frame encoding is out of scope")
+            # vae.py:541-542, 553-557: the last frame is encoded on its own, without the feature caches, and appended (conv1 is 1x1x1)
+            return [torch.cat([self.encode_one(u[:, :-1]), self.encode_one(u[:, -1:])], dim=1) for u in videos]
         return [self.encode_one(u) for u in videos]

@@ -52,7 +52,13 @@ def main():
         e = rel_l2(y, y_ref)
         print(f"  wan vae decode ({dtype}): out {tuple(y.shape)}, rel_l2(oracle batched, reference streaming) = {e:.3e}, clamp hits {(y_ref.abs() >= 1).float().mean():.3f}")
         assert y.shape == (3, 13, 48, 80) and e < tol
-    torch.save(dict(cfg=cfg, seed_weights=0, z=z.float(), out=y_ref.half()), os.path.join(GOLD, "wan_vae_decode.pt"))
+        # any_end_frame: the last latent frame is an independent image (no feature caches)
+        y_ref_e = ref.decode(z.unsqueeze(0), [mean, 1.0 / std], any_end_frame=True).clamp_(-1, 1).float().squeeze(0)
+        y_e = V.wan_vae_decode(sdd, z, cfg, mean, std, any_end_frame=True)
+        ee = rel_l2(y_e, y_ref_e)
+        print(f"  wan vae decode any_end_frame ({dtype}): out {tuple(y_e.shape)}, rel_l2 = {ee:.3e}")
+        assert y_e.shape == (3, 10, 48, 80) and ee < tol
+    torch.save(dict(cfg=cfg, seed_weights=0, z=z.float(), out=y_ref.half(), out_end_frame=y_ref_e.half()), os.path.join(GOLD, "wan_vae_decode.pt"))
     print("written", os.path.join(GOLD, "wan_vae_decode.pt"))
 
     # ---- encode: the reference streams chunks of 1, 4, 4, ... frames with its feature caches (WanVAE_.encode :536-575)
@@ -71,6 +77,13 @@ def main():
             assert mu.shape == (16, 1 + (shape[1] - 1) // 4, shape[2] // 8, shape[3] // 8) and e < tol
             if shape[1] == 9:
                 keep = dict(video=video.float(), mu=mu_ref.float())
+                video_e = torch.cat([video, (torch.rand(3, 1, *shape[2:], generator=g) * 2 - 1).to(dtype)], dim=1)      # + an end frame
+                mu_ref_e = ref.encode(video_e.unsqueeze(0), [mean, 1.0 / std], any_end_frame=True).float().squeeze(0)
+                mu_e = V.wan_vae_encode(sdd, video_e, cfg, mean, std, any_end_frame=True)
+                ee = rel_l2(mu_e, mu_ref_e)
+                print(f"  wan vae encode any_end_frame ({dtype}): out {tuple(mu_e.shape)}, rel_l2 = {ee:.3e}")
+                assert mu_e.shape == (16, 4, 6, 10) and ee < tol
+                keep.update(video_end_frame=video_e.float(), mu_end_frame=mu_ref_e.float())
     torch.save(dict(cfg=cfg, seed_weights=1, **keep), os.path.join(GOLD, "wan_vae_encode.pt"))
     print("written", os.path.join(GOLD, "wan_vae_encode.pt"))
 

@@ -419,16 +419,26 @@ def ulysses_attention_virtual(q: Tensor, k: Tensor, v: Tensor, P: int) -> Tensor
     return out
 
 
-def i2v_conditioning(vae_sd, vae_cfg, image: Tensor, frame_num: int) -> Tensor:
-    """image2video.py:232-244, 262-277 (no end frame): y = [first-frame mask (4) | WanVAE.encode([image, zeros x (F-1)]) (16)]
-    -> [20, (F-1)/4+1, H/8, W/8].  image: [3, H, W] in [-1, 1]."""
+def i2v_conditioning(vae_sd, vae_cfg, image: Tensor, frame_num: int, image_end: Optional[Tensor] = None,
+                     add_frames_for_end_image: bool = True) -> Tensor:
+    """image2video.py:232-244, 262-277: y = [conditioning-frame mask (4) | WanVAE.encode([image, zeros ..., (end image)]) (16)]
+    -> [20, latent frames, H/8, W/8].  image(s): [3, H, W] in [-1, 1]; frame_num = the count after `frame_num += 1` for an added end frame."""
     from . import wan_vae_oracle as V
     h, w = image.shape[1:]
     lat_h, lat_w = h // 8, w // 8
     msk = torch.ones(1, frame_num, lat_h, lat_w)
-    msk[:, 1:] = 0
-    msk = torch.concat([torch.repeat_interleave(msk[:, 0:1], repeats=4, dim=1), msk[:, 1:]], dim=1)
+    if image_end is not None:
+        msk[:, 1:-1] = 0
+        if add_frames_for_end_image:
+            msk = torch.concat([torch.repeat_interleave(msk[:, 0:1], repeats=4, dim=1), msk[:, 1:-1], torch.repeat_interleave(msk[:, -1:], repeats=4, dim=1)], dim=1)
+        else:
+            msk = torch.concat([torch.repeat_interleave(msk[:, 0:1], repeats=4, dim=1), msk[:, 1:]], dim=1)
+        enc = torch.concat([image[:, None], torch.zeros(3, frame_num - 2, h, w), image_end[:, None]], dim=1)
+    else:
+        msk[:, 1:] = 0
+        msk = torch.concat([torch.repeat_interleave(msk[:, 0:1], repeats=4, dim=1), msk[:, 1:]], dim=1)
+        enc = torch.concat([image[:, None], torch.zeros(3, frame_num - 1, h, w)], dim=1)
     msk = msk.view(1, msk.shape[1] // 4, 4, lat_h, lat_w).transpose(1, 2)[0]
-    enc = torch.concat([image[:, None], torch.zeros(3, frame_num - 1, h, w)], dim=1)
-    lat_y = V.wan_vae_encode(vae_sd, enc, vae_cfg, torch.tensor(V.WAN_VAE_MEAN), torch.tensor(V.WAN_VAE_STD))
+    lat_y = V.wan_vae_encode(vae_sd, enc, vae_cfg, torch.tensor(V.WAN_VAE_MEAN), torch.tensor(V.WAN_VAE_STD),
+                             any_end_frame=image_end is not None and add_frames_for_end_image)
     return torch.concat([msk, lat_y])

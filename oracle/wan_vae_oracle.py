@@ -142,12 +142,23 @@ def resample(sd, p, x: Tensor, mode: str) -> Tensor:
     return y.reshape(b, t, c // 2, 2 * h, 2 * w).permute(0, 2, 1, 3, 4)
 
 
-def wan_vae_decode(sd: Dict[str, Tensor], z: Tensor, cfg=WAN_VAE, mean: Optional[Tensor] = None, std: Optional[Tensor] = None) -> Tensor:
-    """WanVAE.decode for one video (vae.py:578-609, 825-829): z [16, T, H, W] -> [3, 1 + 4(T-1), 8H, 8W] in [-1, 1] (float32)."""
+def wan_vae_decode(sd: Dict[str, Tensor], z: Tensor, cfg=WAN_VAE, mean: Optional[Tensor] = None, std: Optional[Tensor] = None,
+                   any_end_frame: bool = False) -> Tensor:
+    """WanVAE.decode for one video (vae.py:578-609, 825-829): z [16, T, H, W] -> [3, 1 + 4(T-1), 8H, 8W] in [-1, 1] (float32).
+    any_end_frame (:597-601): the LAST latent frame is decoded on its own, without the feature caches (one image), and appended:
+    [16, T, H, W] -> [3, 1 + 4(T-2) + 1, 8H, 8W]."""
     x = z.unsqueeze(0)
     if mean is not None:
         x = x * std.view(1, -1, 1, 1, 1).to(x.dtype) + mean.view(1, -1, 1, 1, 1).to(x.dtype)      # z / (1/std) + mean (:581-586)
     x = causal_conv3d(x, sd["conv2.weight"], sd["conv2.bias"])
+    if any_end_frame:
+        parts = [_decoder(sd, x[:, :, :-1], cfg), _decoder(sd, x[:, :, -1:], cfg)]
+        return torch.cat(parts, dim=2).clamp(-1, 1).float().squeeze(0)
+    return _decoder(sd, x, cfg).clamp(-1, 1).float().squeeze(0)
+
+
+def _decoder(sd: Dict[str, Tensor], x: Tensor, cfg) -> Tensor:
+    """Decoder3d.forward over a whole (sub)sequence (vae.py:438-493)"""
     x = causal_conv3d(x, sd["decoder.conv1.weight"], sd["decoder.conv1.bias"])
     x = res_block(sd, "decoder.middle.0.", x)
     x = attention_block(sd, "decoder.middle.1.", x)
@@ -155,8 +166,7 @@ def wan_vae_decode(sd: Dict[str, Tensor], z: Tensor, cfg=WAN_VAE, mean: Optional
     for i, ent in enumerate(decoder_layout(cfg)):
         p = f"decoder.upsamples.{i}."
         x = res_block(sd, p, x) if ent[0] == "res" else resample(sd, p, x, ent[0])
-    x = causal_conv3d(F.silu(rms_norm(x, sd["decoder.head.0.gamma"])), sd["decoder.head.2.weight"], sd["decoder.head.2.bias"])
-    return x.clamp(-1, 1).float().squeeze(0)
+    return causal_conv3d(F.silu(rms_norm(x, sd["decoder.head.0.gamma"])), sd["decoder.head.2.weight"], sd["decoder.head.2.bias"])
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -228,11 +238,27 @@ def downsample(sd, p, x: Tensor, mode: str) -> Tensor:
     return y
 
 
-def wan_vae_encode(sd: Dict[str, Tensor], video: Tensor, cfg=WAN_VAE, mean: Optional[Tensor] = None, std: Optional[Tensor] = None) -> Tensor:
+def wan_vae_encode(sd: Dict[str, Tensor], video: Tensor, cfg=WAN_VAE, mean: Optional[Tensor] = None, std: Optional[Tensor] = None,
+                   any_end_frame: bool = False) -> Tensor:
     """WanVAE.encode for one video (vae.py:536-575, 806-816, tile_size 0): video [3, 1+4k, H, W] in [-1, 1] ->
-    mu [z_dim, 1+k, H/8, W/8] float32, normalised with (mu - mean) / std."""
-    assert (video.shape[1] - 1) % 4 == 0, "the reference's 1,4,4,... chunking drops trailing frames otherwise"
+    mu [z_dim, 1+k, H/8, W/8] float32, normalised with (mu - mean) / std.
+    any_end_frame (:541-542, 553-557): the LAST frame is encoded on its own, without the feature caches, and appended:
+    video [3, 1+4k+1, H, W] -> mu [z_dim, 1+k+1, H/8, W/8]."""
     x = video.unsqueeze(0)
+    if any_end_frame:
+        assert (video.shape[1] - 2) % 4 == 0
+        x = torch.cat([_encoder(sd, x[:, :, :-1], cfg), _encoder(sd, x[:, :, -1:], cfg)], dim=2)
+    else:
+        assert (video.shape[1] - 1) % 4 == 0, "the reference's 1,4,4,... chunking drops trailing frames otherwise"
+        x = _encoder(sd, x, cfg)
+    mu = causal_conv3d(x, sd["conv1.weight"], sd["conv1.bias"])[:, : cfg["z_dim"]]
+    if mean is not None:
+        mu = (mu - mean.view(1, -1, 1, 1, 1).to(mu.dtype)) * (1.0 / std).view(1, -1, 1, 1, 1).to(mu.dtype)
+    return mu.float().squeeze(0)
+
+
+def _encoder(sd: Dict[str, Tensor], x: Tensor, cfg) -> Tensor:
+    """Encoder3d.forward over a whole (sub)sequence (vae.py:329-383)"""
     x = causal_conv3d(x, sd["encoder.conv1.weight"], sd["encoder.conv1.bias"])
     for i, ent in enumerate(encoder_layout(cfg)):
         p = f"encoder.downsamples.{i}."
@@ -240,8 +266,4 @@ def wan_vae_encode(sd: Dict[str, Tensor], video: Tensor, cfg=WAN_VAE, mean: Opti
     x = res_block(sd, "encoder.middle.0.", x)
     x = attention_block(sd, "encoder.middle.1.", x)
     x = res_block(sd, "encoder.middle.2.", x)
-    x = causal_conv3d(F.silu(rms_norm(x, sd["encoder.head.0.gamma"])), sd["encoder.head.2.weight"], sd["encoder.head.2.bias"])
-    mu = causal_conv3d(x, sd["conv1.weight"], sd["conv1.bias"])[:, : cfg["z_dim"]]
-    if mean is not None:
-        mu = (mu - mean.view(1, -1, 1, 1, 1).to(mu.dtype)) * (1.0 / std).view(1, -1, 1, 1, 1).to(mu.dtype)
-    return mu.float().squeeze(0)
+    return causal_conv3d(F.silu(rms_norm(x, sd["encoder.head.0.gamma"])), sd["encoder.head.2.weight"], sd["encoder.head.2.bias"])

@@ -247,3 +247,19 @@ def test_pay_attention_oracle_matches_reference(golden_dir):
         assert lst == []
         assert y.dtype == c["out"].dtype == c["q"].dtype and y.shape == c["out"].shape
         assert O.rel_l2(y[:, : c["valid"]].float(), c["out"][:, : c["valid"]].float()) < (1e-2 if name == "dtypes" else 1e-5), name
+
+
+def test_wan_vae_any_end_frame_oracle_matches_reference(golden_dir):
+    """any_end_frame (wan/modules/vae.py:541-557, 597-601): the last (latent) frame is coded on its own, without the feature caches.  The
+    one-pass oracle vs fixtures recorded from the unmodified reference's streaming encode / decode (identical in fp64)."""
+    from oracle import wan_vae_oracle as V
+    mean, std = torch.tensor(V.WAN_VAE_MEAN), torch.tensor(V.WAN_VAE_STD)
+    g = _load(golden_dir, "wan_vae_encode.pt")
+    sd = V.make_wan_vae_encoder_state_dict(g["cfg"], seed=g["seed_weights"])
+    mu = V.wan_vae_encode(sd, g["video_end_frame"], g["cfg"], mean, std, any_end_frame=True)
+    assert mu.shape == (16, 4, 6, 10) and O.rel_l2(mu, g["mu_end_frame"]) < 1e-5
+    assert O.rel_l2(mu[:, :3], g["mu"]) < 1e-5                      # the prefix is the plain encode of the first 9 frames
+    d = _load(golden_dir, "wan_vae_decode.pt")
+    sdd = V.make_wan_vae_decoder_state_dict(d["cfg"], seed=d["seed_weights"])
+    y = V.wan_vae_decode(sdd, d["z"], d["cfg"], mean, std, any_end_frame=True)
+    assert y.shape == (3, 10, 48, 80) and O.rel_l2(y, d["out_end_frame"].float()) < 2e-3

@@ -373,3 +373,32 @@ def test_wan_callbacks_and_interrupt(golden_dir):
     cos, sin = get_rotary_pos_embed(g["lat"].shape[1:])
     y = m([g["lat"].to(DEV), g["lat"].to(DEV)], t=g["t"].to(DEV), context=[g["ctx"].to(DEV), g["ctx0"].to(DEV)], freqs=(cos, sin), pipeline=pipe)
     assert y == [None, None]
+
+
+def test_wan_i2v_end_frame_conditioning():
+    """image_end (image2video.py:191-199, 232-244, 262-277): one frame is added, the mask marks first and last frame, the end image is
+    encoded without feature caches; y vs the oracle, and generate() runs on the longer latent."""
+    from ltx_video_gpupoor_b200.wan.image2video import WanI2V
+    from ltx_video_gpupoor_b200.wan.vae import WanVAE
+    from oracle import wan_vae_oracle as V
+    vcfg = dict(V.WAN_VAE, dim=32)
+    vsd = V.make_wan_vae_encoder_state_dict(vcfg, seed=1)
+    vae = WanVAE(dim=32)
+    vae.load_state_dict(vsd)
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "wan_i2v.pt"), weights_only=False)
+    cfg = g["cfg"]
+    m = WanModel(model_type="i2v", in_dim=cfg["in_dim"], dim=cfg["dim"], ffn_dim=cfg["ffn_dim"], num_heads=cfg["num_heads"], num_layers=cfg["num_layers"])
+    m.load_state_dict(W.make_wan_state_dict(cfg, seed=1))
+    pipe = WanI2V(m, vae=vae)
+    gen = torch.Generator().manual_seed(5)
+    img, end = torch.rand(3, 64, 96, generator=gen) * 2 - 1, torch.rand(3, 64, 96, generator=gen) * 2 - 1
+    for add in (True, False):
+        fn = 10 if add else 9
+        y = pipe.encode_conditioning(img, fn, image_end=end, add_frames_for_end_image=add)
+        yo = W.i2v_conditioning(vsd, vcfg, img, fn, image_end=end, add_frames_for_end_image=add)
+        assert tuple(y.shape) == tuple(yo.shape) == (20, 4 if add else 3, 8, 12)
+        assert torch.equal(y[:4].cpu(), yo[:4])
+        assert W.rel_l2(y[4:].cpu(), yo[4:]) < 2e-2
+    lat = pipe.generate(image_start=img, image_end=end, frame_num=9, sampling_steps=2, guide_scale=5.0, context=g["ctx"], context_null=g["ctx0"],
+                        clip_fea=g["clip"], seed=3)
+    assert lat is not None and tuple(lat.shape) == (16, 4, 8, 12) and torch.isfinite(lat).all()

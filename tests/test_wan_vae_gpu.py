@@ -117,3 +117,26 @@ def test_wan_vae_encode_vs_reference_fixture(golden_dir):
         v2 = WanVAE(dim=cfg["dim"], dim_mult=cfg["dim_mult"], num_res_blocks=cfg["num_res_blocks"], temperal_downsample=cfg["temperal_upsample"][::-1])
         v2.load_state_dict(V.make_wan_vae_decoder_state_dict(cfg, seed=0))
         v2.encode([g["video"].to(DEV)])
+
+
+def test_wan_vae_any_end_frame_vs_reference_fixture(golden_dir):
+    """WanVAE.encode / decode with any_end_frame=True (last frame coded without the feature caches) against the reference's outputs."""
+    g = torch.load(os.path.join(golden_dir, "wan_vae_encode.pt"), weights_only=False)
+    cfg = g["cfg"]
+    mk = lambda: WanVAE(dim=cfg["dim"], dim_mult=cfg["dim_mult"], num_res_blocks=cfg["num_res_blocks"], temperal_downsample=cfg["temperal_upsample"][::-1])
+    vae = mk()
+    vae.load_state_dict(V.make_wan_vae_encoder_state_dict(cfg, seed=g["seed_weights"]))
+    mu = vae.encode([g["video_end_frame"].to(DEV)], tile_size=0, any_end_frame=True)[0]
+    assert tuple(mu.shape) == (16, 4, 6, 10)
+    e = rel_l2(mu.cpu(), g["mu_end_frame"])
+    print(f"wan vae encode any_end_frame: rel_l2 vs reference = {e:.3e}")
+    assert e < 2e-2
+    d = torch.load(os.path.join(golden_dir, "wan_vae_decode.pt"), weights_only=False)
+    vae2 = mk()
+    vae2.load_state_dict(V.make_wan_vae_decoder_state_dict(d["cfg"], seed=d["seed_weights"]))
+    y = vae2.decode([d["z"].to(DEV)], tile_size=0, any_end_frame=True)[0]
+    torch.cuda.synchronize()
+    assert tuple(y.shape) == (3, 10, 48, 80)
+    p = psnr(y.cpu() * 0.5 + 0.5, d["out_end_frame"].float() * 0.5 + 0.5)
+    print(f"wan vae decode any_end_frame: PSNR vs reference = {p:.1f} dB")
+    assert p >= 40.0
