@@ -263,3 +263,25 @@ def test_wan_vae_any_end_frame_oracle_matches_reference(golden_dir):
     sdd = V.make_wan_vae_decoder_state_dict(d["cfg"], seed=d["seed_weights"])
     y = V.wan_vae_decode(sdd, d["z"], d["cfg"], mean, std, any_end_frame=True)
     assert y.shape == (3, 10, 48, 80) and O.rel_l2(y, d["out_end_frame"].float()) < 2e-3
+
+
+def test_baseline_config0_full_depth_matches_reference(golden_dir):
+    """BASELINE.json configs[0] exactly (LTX-2B, 28 layers, 256x256x9, 4 steps + VAE decode, fp32 on CPU): the oracle's
+    denoise loop and decode vs the latents / frames the unmodified reference pipeline produced (oracle/gen_golden_config0.py)."""
+    g = _load(golden_dir, "ltx_config0.pt")
+    m = g["meta"]
+    f, h, w = m["latent"]
+    sd = O.make_transformer_state_dict(O.LTX_2B, seed=m["seed_weights"], num_layers=m["num_layers"])
+    pe = torch.randn(1, 32, 4096, generator=torch.Generator().manual_seed(m["seed_prompt"]))
+    noise = torch.randn(1, f * h * w, 128, generator=torch.Generator("cpu").manual_seed(m["seed_noise"]))
+    per_step = []
+    with torch.no_grad():
+        lat = O.denoise_loop(sd, O.LTX_2B, noise, pe, torch.ones(1, 32), num_frames_lat=f, lat_h=h, lat_w=w,
+                             frame_rate=m["fps"], num_steps=m["steps"], per_step=per_step)
+        del sd
+        assert O.rel_l2(O.unpatchify(lat, f, h, w), g["latents"]) < 2e-4
+        for a, b in zip(per_step, g["per_step_oracle"]):
+            assert O.rel_l2(a, b) < 2e-4
+        img = O.postprocess(O.vae_decode(O.make_vae_decoder_state_dict(seed=m["seed_vae"]), O.unpatchify(lat, f, h, w)))
+    assert tuple(img.shape) == (1, 3, m["F"], m["H"], m["W"])
+    assert O.psnr(img, g["frames"].float()) > 60          # fixture frames are stored in fp16
