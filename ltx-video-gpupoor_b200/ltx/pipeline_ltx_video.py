@@ -269,7 +269,7 @@ class LTXVideoPipeline:
         # ---- per-step guidance tables (:958-1017)
         if guidance_timesteps:
             mapping = []
-            for t_ in ts_host:
+            for t_ in ts:          # 0-d fp32 tensors, like the reference: `val <= t_` is evaluated in fp32, so a threshold EQUAL to a timestep matches
                 idx = [i for i, val in enumerate(guidance_timesteps) if val <= t_]
                 mapping.append(idx[0] if len(idx) > 0 else (len(guidance_timesteps) - 1))
         per = lambda v: [v] * n_steps if not isinstance(v, list) else [v[mapping[i]] for i in range(n_steps)]

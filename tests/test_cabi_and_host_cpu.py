@@ -202,3 +202,17 @@ def test_prepare_conditioning_keyframes_bit_exact(golden_dir):
                                                        generator=torch.Generator().manual_seed(2))
         assert extra == c["extra"] and torch.equal(tok, c["tokens"]) and torch.equal(cm, c["mask"]), name
         assert torch.equal(px.to(c["coords"].dtype), c["coords"]), name
+
+
+def test_guidance_and_timestep_tables_bit_exact(golden_dir):
+    """LTXVideoPipeline.__call__'s host-side tables (retrieve_timesteps with skip_initial / skip_final / strength / explicit timesteps, the
+    guidance_timesteps mapping, list-valued guidance / STG / rescaling scales, nested skip_block_list, skip-layer masks, cond-batch size, first
+    timestep argument) against what the unmodified reference built for its own presets (ltx_video/configs/*.yaml) and two edge cases
+    (oracle/gen_golden_schedule.py).  Runs the product pipeline up to the loop on a CPU stand-in transformer: no kernel is launched."""
+    from oracle.schedule_tables import compare, product_tables
+    g = torch.load(os.path.join(golden_dir, "ltx_schedule_tables.pt"), weights_only=False)
+    assert len(g["cases"]) == 7
+    for name, c in g["cases"].items():
+        lat = g["init_latents"].clone() if c["needs_latents"] else None
+        mine = product_tables(g["num_layers"], g["geom"], g["pe"], g["pm"], g["ne"], g["pm"], lat, dict(c["kwargs"]))
+        compare(name, mine, c["ref"])
