@@ -275,7 +275,9 @@ class Transformer3DModel:
                 ctx_l, key_bias_l = ctx, key_bias
             a = ada[li]                                                             # [B*T, 6, D]
             layer_skip = skip_host is not None and float(skip_host[li].min()) != 1.0
-            x_orig = x.clone() if (layer_skip and skip_layer_strategy == SkipLayerStrategy.TransformerBlock) else None
+            # SkipLayerStrategy.Residual needs no branch: the reference only applies it under `attn.residual_connection`
+            # (attention.py:1161-1168), which BasicTransformerBlock never enables, so the mask is ignored there as it is here.
+            x_orig =x.clone() if (layer_skip and skip_layer_strategy == SkipLayerStrategy.TransformerBlock) else None
             # ---- self attention (attention.py:233-288)
             nh = ops.norm_mod(x, a[:, 1], a[:, 0], rows_per_group=rows_per_group, eps=self.config.norm_eps)
             qkv = ops.gemm(nh, Lw["qkv.w"], Lw["qkv.b"])                            # [B*N, 3D]

@@ -216,3 +216,12 @@ def test_guidance_and_timestep_tables_bit_exact(golden_dir):
         lat = g["init_latents"].clone() if c["needs_latents"] else None
         mine = product_tables(g["num_layers"], g["geom"], g["pe"], g["pm"], g["ne"], g["pm"], lat, dict(c["kwargs"]))
         compare(name, mine, c["ref"])
+
+
+def test_checkpoint_format_tables_match_reference(golden_dir):
+    """The diffusers <-> native config mapping, the configs themselves and the ordered key-rename tables against the ones dumped from the
+    unmodified reference module (oracle/gen_golden_formats.py; ltx_video/utils/diffusers_config_mapping.py)."""
+    import json
+    from oracle.format_tables import check_format_tables
+    with open(os.path.join(golden_dir, "ltx_format_tables.json")) as f:
+        check_format_tables(json.load(f))
