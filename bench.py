@@ -102,9 +102,10 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port of the reference algorithm on the host cores
 # ------------------------------------------------------------------------------------------------------------
-def cpu_sample(wl, layers=(1, 2)):
+def cpu_sample(wl, layers=(1, 3)):
     """Bounded sample of one denoise step on the CPU: full-size (N=6144, L=256) transformer forward of the oracle
-    with 1 and 2 layers; per-layer and fixed costs are separated and extrapolated to 28 layers x num_conds."""
+    with 1 and 3 layers (a two-layer difference per sample keeps host timing noise out of the slope); per-layer and
+    fixed costs are separated and extrapolated to 28 layers x num_conds."""
     from oracle import ltx_oracle as O
     torch.manual_seed(0)
     f, h, w = wl["num_frames"] // 8 + 1, wl["height"] // 32, wl["width"] // 32
@@ -130,6 +131,16 @@ def cpu_sample(wl, layers=(1, 2)):
     return dict(step_s=step_s, t_layer=t_layer, t_fixed=t_fixed, raw=times, tokens=N)
 
 
+def ltx_config(workload, wl, layers, world):
+    """`config` of the JSON line: identical for the b200 arm and the reference arm."""
+    tokens = (wl["num_frames"] // 8 + 1) * (wl["height"] // 32) * (wl["width"] // 32)
+    return {"workload": workload, "network": "LTX-Video 2B (random-init, 28 layers)" if layers == 28 else f"INVALID: {layers} layers",
+            "height": wl["height"], "width": wl["width"], "num_frames": wl["num_frames"], "tokens": tokens,
+            "schedule_steps": wl["schedule_steps"], "num_conds": wl["num_conds"], "prompt_tokens": wl["prompt_tokens"],
+            "parallelism": f"replicas x{world}",
+            "l2_policy": "per-step working set (3.8 GB weights + activations) far exceeds the 126 MB L2; no flush needed"}
+
+
 def run_reference(args, wl_name, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -137,17 +148,17 @@ def run_reference(args, wl_name, wl):
     cores = torch.get_num_threads()
     vals = []
     for i in range(args.warmup + args.steps):
-        s = cpu_sample(wl, layers=(1, 2))
+        s = cpu_sample(wl)
         if i >= args.warmup:
             vals.append(s["step_s"])
     step_s = sum(vals) / len(vals)
     v = 1.0 / step_s
     sample = (f"oracle port (torch fp32, {cores} threads) of Transformer3DModel.forward at full size N={s['tokens']}, "
-              f"L={wl['prompt_tokens']}: 1- and 2-layer forwards timed, extrapolated to 28 layers x {wl['num_conds']} conds per step")
+              f"L={wl['prompt_tokens']}: 1- and 3-layer forwards timed, extrapolated to 28 layers x {wl['num_conds']} conds per step")
     line = {"impl": "reference", "metric": "denoise_steps_per_s", "value": v, "unit": "steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": wl_name, **{k: wl[k] for k in ("height", "width", "num_frames", "schedule_steps", "num_conds")}},
+            "config": ltx_config(wl_name, wl, 28, args.gpus),
             "cpu_baseline": {"value": v, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -210,7 +221,7 @@ def run_wan(args, wl):
         print(json.dumps({"impl": "reference", "metric": "denoise_steps_per_s", "value": v, "unit": "steps/s", "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
                           "scaling": "strong", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-                          "config": {"workload": args.workload, "model": f"Wan2.1-T2V-{wl['model']}", "tokens": smp["tokens"]},
+                          "config": {"workload": args.workload, "network": f"Wan2.1-T2V-{wl['model']}", "tokens": smp["tokens"]},
                           "cpu_baseline": {"value": v, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
                           "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
@@ -386,7 +397,7 @@ def run_wan(args, wl):
         line = {"metric": "denoise_steps_per_s", "value": steps_per_s, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": args.workload, "model": f"Wan2.1-T2V-{wl['model']} (random-init, {cfg['num_layers']} layers)",
+                "config": {"workload": args.workload, "network": f"Wan2.1-T2V-{wl['model']} (random-init, {cfg['num_layers']} layers)",
                            "latent": list(shape), "tokens": shape[1] * shape[2] * shape[3] // 4, "schedule_steps": S,
                            "forwards_per_step": 2,
                            "parallelism": (f"cfg-parallel 2 x ulysses sp{world // 2}" if cfgp is not None else f"ulysses sp{world}"),
@@ -608,7 +619,7 @@ def main():
         cores = torch.get_num_threads()
         cpu_baseline = {"value": 1.0 / s["step_s"], "unit": "steps/s", "cores": cores, "kind": "port",
                         "sample": (f"oracle port (torch fp32, {cores} threads) of the transformer forward at full size "
-                                   f"N={s['tokens']}: 1- and 2-layer forwards ({s['raw'][1]:.1f}s, {s['raw'][2]:.1f}s) "
+                                   f"N={s['tokens']}: 1- and 3-layer forwards ({s['raw'][1]:.1f}s, {s['raw'][3]:.1f}s) "
                                    f"extrapolated to 28 layers x {wl['num_conds']} conds per denoise step")}
 
     ms_step = elapsed / args.steps * 1e3
@@ -616,10 +627,7 @@ def main():
         "metric": "denoise_steps_per_s", "value": steps_per_s, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": args.workload, "model": "LTX-Video 2B (random-init, 28 layers)" if args.layers == 28 else f"INVALID: {args.layers} layers",
-                   "height": wl["height"], "width": wl["width"], "num_frames": wl["num_frames"], "tokens": st.N,
-                   "schedule_steps": S, "num_conds": wl["num_conds"], "prompt_tokens": Lp, "parallelism": f"replicas x{world}",
-                   "l2_policy": "per-step working set (3.8 GB weights + activations) far exceeds the 126 MB L2; no flush needed"},
+        "config": ltx_config(args.workload, wl, args.layers, world),
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
         "s_per_video": (S * ms_step / 1e3 + decode_s) if decode_s is not None else None, "vae_decode_s": decode_s,
         "model_tflops": wl["num_conds"] * FWD_FLOPS * (args.layers / 28) / (ms_step / 1e3) / 1e12,
