@@ -109,6 +109,22 @@ class CausalVideoAutoencoder:
     def get_VAE_tile_size(vae_config, device_mem_capacity, mixed_precision):
         return (0, 0)
 
+    # vae.py:117-154 — the tiling switches exist so reference callers keep working; they select nothing here (whole-video decode / encode)
+    def set_tiling_params(self, sample_size: int = 512, overlap_factor: float = 0.25):
+        self.tile_sample_min_size, self.tile_latent_min_size, self.tile_overlap_factor = sample_size, int(sample_size / 32), overlap_factor
+
+    def enable_z_tiling(self, z_sample_size: int = 4):
+        self.z_sample_size = z_sample_size
+
+    def disable_z_tiling(self):
+        pass
+
+    def enable_hw_tiling(self):
+        pass
+
+    def disable_hw_tiling(self):
+        pass
+
     @property
     def spatial_downscale_factor(self):
         n = len([b for b in self._cfg["blocks"] if b[0] in ("compress_space", "compress_all", "compress_all_res", "compress_space_res")])

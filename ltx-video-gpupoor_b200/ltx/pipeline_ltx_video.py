@@ -399,9 +399,10 @@ class LTXMultiScalePipeline:
         downscaled_height = x_height - (x_height % video_pipeline.vae_scale_factor)
         kwargs["output_type"] = "latent"
         kwargs["width"], kwargs["height"] = downscaled_width, downscaled_height
-        z_tile, hw_tile = kwargs.pop("VAE_tile_size", (0, 0)) or (0, 0)
-        if z_tile > 0 or hw_tile > 0:
-            raise NotImplementedError("VAE tiling is a low-memory workaround (vae.py:365-408) that is not needed on 180 GB")
+        # VAE_tile_size = (z_tile, hw_tile): the reference's callers always pass it (vae.py:92-115 answers (4, 0) on any GPU >= 24 GB) to
+        # decode in overlapping temporal / spatial tiles that are blended back together (vae.py:223-263, 365-408) — a low-memory
+        # approximation of the whole-video decode.  180 GB hold the whole video, so the value is accepted and the exact decode runs.
+        kwargs.pop("VAE_tile_size", None)
         ltxv_model = kwargs.get("ltxv_model")
         for k in ("prompt", "negative_prompt", "device", "enhance_prompt"):
             kwargs.pop(k, None)                         # consumed by encode_prompt / the prompt enhancer in the reference (:1824-1850)
