@@ -123,3 +123,21 @@ def test_wan_rope_tables_riflex_bit_exact(golden_dir):
         assert torch.equal(cos[::7], c_ref) and torch.equal(sin[::7], s_ref), (size, rf)
     a, b = get_rotary_pos_embed((33, 8, 12), False), get_rotary_pos_embed((33, 8, 12), True)
     assert not torch.equal(a[0][:, :44], b[0][:, :44]) and torch.equal(a[0][:, 44:], b[0][:, 44:])      # only the time axis changes
+
+
+def test_wan_1_3b_full_depth_oracle_matches_reference_fixture(golden_dir):
+    """BASELINE.json configs[3]'s network at full width and depth (dim 1536, 12 heads, ffn 8960, 30 layers, 1.42 B seeded weights): the oracle
+    in fp32 against the joint forward and the 3-step CFG loop recorded from the unmodified reference in fp64 (oracle/gen_golden_wan_full.py)."""
+    g = torch.load(os.path.join(golden_dir, "wan_1_3b_full.pt"), weights_only=False)
+    cfg = g["cfg"]
+    assert (cfg["dim"], cfg["num_heads"], cfg["ffn_dim"], cfg["num_layers"]) == (1536, 12, 8960, 30)
+    sd = W.make_wan_state_dict(cfg, seed=g["seed_weights"])
+    cos, sin = W.rope_tables(g["lat"].shape[1:])
+    with torch.no_grad():
+        y = W.wan_forward(sd, cfg, [g["lat"], g["lat"]], g["t"], [g["ctx"], g["ctx0"]], cos, sin)
+        for a, b in zip(y, g["fwd"]):
+            assert W.rel_l2(a, b) < 2e-4              # fp32 oracle vs fp64 reference through 30 layers
+        steps = []
+        W.t2v_denoise(sd, cfg, g["lat"], g["ctx"], g["ctx0"], steps=g["steps"], shift=g["shift"], guide_scale=g["guide"], per_step=steps)
+    for a, b in zip(steps, g["loop"]):
+        assert W.rel_l2(a, b) < 2e-4
