@@ -52,6 +52,35 @@ def sd3_resolution_dependent_timestep_shift(samples_shape, timesteps: torch.Tens
     return shifts
 
 
+def linear_quadratic_schedule(num_steps: int, threshold_noise: float = 0.025, linear_steps: Optional[int] = None) -> torch.Tensor:
+    """rf.py:25-47 ("LinearQuadratic" sampler): noise level rises linearly to `threshold_noise` over the first half of the steps and
+    quadratically to 1 over the rest; returned as timesteps 1 - level.  Python-float arithmetic in the reference's operation order
+    (the table is compared bit for bit)."""
+    if num_steps == 1:
+        return torch.tensor([1.0])
+    n_lin = num_steps // 2 if linear_steps is None else linear_steps
+    n_quad = num_steps - n_lin
+    levels = [i * threshold_noise / n_lin for i in range(n_lin)]
+    gap = n_lin - threshold_noise * num_steps
+    a = gap / (n_lin * n_quad ** 2)
+    b = threshold_noise / n_lin - 2 * gap / (n_quad ** 2)
+    c = a * (n_lin ** 2)
+    levels += [a * (i ** 2) + b * i + c for i in range(n_lin, num_steps)]
+    return torch.tensor([1.0 - x for x in levels])
+
+
+def simple_diffusion_resolution_dependent_timestep_shift(samples_shape, timesteps: torch.Tensor, n: int = 32 * 32) -> torch.Tensor:
+    """rf.py:50-66 ("SimpleDiffusion" shifting): log-SNR moved by 2*log(tokens / base resolution)."""
+    if len(samples_shape) == 3:
+        _, m, _ = samples_shape
+    elif len(samples_shape) in [4, 5]:
+        m = math.prod(samples_shape[2:])
+    else:
+        raise ValueError("Samples must have shape (b, t, c), (b, c, h, w) or (b, c, f, h, w)")
+    snr = (timesteps / (1 - timesteps)) ** 2
+    return torch.sigmoid(0.5 * (torch.log(snr) + 2 * math.log(m / n)))
+
+
 @dataclass
 class RectifiedFlowSchedulerOutput:
     prev_sample: torch.Tensor
@@ -64,19 +93,45 @@ class RectifiedFlowScheduler:
     def __init__(self, num_train_timesteps=1000, shifting: Optional[str] = "SD3", base_resolution=None,
                  target_shift_terminal: Optional[float] = 0.1, sampler: Optional[str] = "Uniform",
                  shift: Optional[float] = None, **_):
-        if sampler != "Uniform":
-            raise NotImplementedError("only the 'Uniform' sampler of OURS_SCHEDULER_CONFIG is implemented")
-        if shifting not in (None, "SD3"):
-            raise NotImplementedError("only SD3 shifting is implemented")
+        """Defaults are OURS_SCHEDULER_CONFIG (diffusers_config_mapping.py:63-72), the configuration every released checkpoint carries
+        (the reference class itself defaults to no shifting, rf.py:180-188; it is always built through from_config / from_pretrained)."""
+        if sampler not in ("Uniform", "LinearQuadratic", "Constant"):
+            raise ValueError(f"unknown sampler {sampler!r}")
+        if shifting not in (None, "SD3", "SimpleDiffusion"):
+            raise ValueError(f"unknown shifting {shifting!r}")
+        if base_resolution is None:
+            base_resolution = 32 ** 2                      # the reference constructor's default (rf.py:184)
         self.config = SimpleNamespace(num_train_timesteps=num_train_timesteps, shifting=shifting,
                                       base_resolution=base_resolution, target_shift_terminal=target_shift_terminal,
                                       sampler=sampler, shift=shift)
         self.init_noise_sigma = 1.0
         self.num_inference_steps = None
-        self.shifting = shifting
-        self.target_shift_terminal = target_shift_terminal
-        self.timesteps = self.sigmas = torch.linspace(1, 1 / num_train_timesteps, num_train_timesteps)
+        self.sampler, self.shifting, self.shift = sampler, shifting, shift
+        self.base_resolution, self.target_shift_terminal = base_resolution, target_shift_terminal
+        self.timesteps = self.sigmas = self.get_initial_timesteps(num_train_timesteps, shift=shift)
         self._scratch = None
+
+    def get_initial_timesteps(self, num_timesteps: int, shift: Optional[float] = None) -> torch.Tensor:
+        """rf.py:201-214"""
+        if self.sampler == "LinearQuadratic":
+            return linear_quadratic_schedule(num_timesteps)
+        uniform = torch.linspace(1, 1 / num_timesteps, num_timesteps)
+        if self.sampler == "Constant":
+            assert shift is not None, "Shift must be provided for constant time shift sampler."
+            return time_shift(shift, 1, uniform)
+        return uniform
+
+    @staticmethod
+    def from_pretrained(pretrained_model_path):
+        """rf.py:262-268: a JSON scheduler config.  A single-file .safetensors checkpoint (config in its metadata, as the model classes read
+        it) is accepted as well."""
+        import json
+        if str(pretrained_model_path).endswith(".safetensors"):
+            from safetensors import safe_open
+            with safe_open(str(pretrained_model_path), framework="pt", device="cpu") as f:
+                return RectifiedFlowScheduler.from_config(json.loads(f.metadata()["config"])["scheduler"])
+        with open(pretrained_model_path, "r", encoding="utf-8") as reader:
+            return RectifiedFlowScheduler.from_config(json.loads(reader.read()))
 
     @classmethod
     def from_config(cls, config: dict):
@@ -85,6 +140,8 @@ class RectifiedFlowScheduler:
     def shift_timesteps(self, samples_shape, timesteps):
         if self.shifting == "SD3":
             return sd3_resolution_dependent_timestep_shift(samples_shape, timesteps, self.target_shift_terminal)
+        if self.shifting == "SimpleDiffusion":
+            return simple_diffusion_resolution_dependent_timestep_shift(samples_shape, timesteps, self.base_resolution)
         return timesteps
 
     def set_timesteps(self, num_inference_steps: Optional[int] = None, samples_shape=None, timesteps=None,
@@ -94,8 +151,7 @@ class RectifiedFlowScheduler:
             raise ValueError("You cannot provide both `timesteps` and `num_inference_steps`.")
         if timesteps is None:
             num_inference_steps = min(self.config.num_train_timesteps, num_inference_steps)
-            timesteps = torch.linspace(1, 1 / num_inference_steps, num_inference_steps)
-            timesteps = self.shift_timesteps(samples_shape, timesteps)
+            timesteps = self.shift_timesteps(samples_shape, self.get_initial_timesteps(num_inference_steps, shift=self.shift))
         else:
             timesteps = torch.as_tensor(timesteps, dtype=torch.float32).cpu()
             num_inference_steps = len(timesteps)

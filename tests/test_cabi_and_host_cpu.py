@@ -225,3 +225,27 @@ def test_checkpoint_format_tables_match_reference(golden_dir):
     from oracle.format_tables import check_format_tables
     with open(os.path.join(golden_dir, "ltx_format_tables.json")) as f:
         check_format_tables(json.load(f))
+
+
+def test_rf_scheduler_samplers_and_shiftings_bit_exact(golden_dir, tmp_path):
+    """RectifiedFlowScheduler.set_timesteps for every sampler x shifting combination of the reference class ("Uniform" / "LinearQuadratic" /
+    "Constant" x none / "SD3" (+ terminal stretch) / "SimpleDiffusion"), 1..40 steps, three sample shapes: 105 tables recorded from the unmodified
+    reference scheduler (oracle/gen_golden_rf_variants.py), bit for bit; from_pretrained on a JSON config and on a single-file checkpoint."""
+    import json
+    from safetensors.torch import save_file
+    from ltx_video_gpupoor_b200.ltx.rf import RectifiedFlowScheduler
+    g = torch.load(os.path.join(golden_dir, "rf_scheduler_variants.pt"), weights_only=False)
+    assert len(g["tables"]) == 105
+    for (name, steps, shape), ref in g["tables"].items():
+        s = RectifiedFlowScheduler.from_config(dict(g["configs"][name], num_train_timesteps=1000))
+        s.set_timesteps(steps, samples_shape=shape)
+        assert s.timesteps.dtype == ref.dtype and torch.allclose(s.timesteps, ref, rtol=0, atol=0, equal_nan=True), (name, steps, shape)
+    cfg = dict(g["configs"]["linear_quadratic_sd3_terminal"], num_train_timesteps=1000, _class_name="RectifiedFlowScheduler")
+    (tmp_path / "scheduler_config.json").write_text(json.dumps(cfg))
+    save_file({"x": torch.zeros(1)}, str(tmp_path / "ckpt.safetensors"), metadata={"config": json.dumps({"scheduler": cfg})})
+    for path in (tmp_path / "scheduler_config.json", tmp_path / "ckpt.safetensors"):
+        s = RectifiedFlowScheduler.from_pretrained(path)
+        s.set_timesteps(30, samples_shape=(1, 128, 16, 16, 24))
+        assert torch.equal(s.timesteps, g["tables"][("linear_quadratic_sd3_terminal", 30, (1, 128, 16, 16, 24))])
+    with pytest.raises(ValueError):
+        RectifiedFlowScheduler(sampler="Nope")
