@@ -106,6 +106,14 @@ class LTXVideoPipeline:
         return timestep * noise + (1 - timestep) * latents.to(device=device, dtype=dtype)
 
     @staticmethod
+    def resize_tensor(media_items: torch.Tensor, height: int, width: int) -> torch.Tensor:
+        """pipeline_ltx_video.py:748-760: per-frame F.interpolate(mode="bilinear", align_corners=False) of [b, c, n, h, w] pixels
+        (the fp32 resize kernel; planes = b*c*n)."""
+        if tuple(media_items.shape[-2:]) != (height, width):
+            media_items = ops.bilinear_resize(media_items.to(torch.float32).contiguous(), height, width).to(media_items.dtype)
+        return media_items
+
+    @staticmethod
     def _handle_non_first_conditioning_sequence(init_latents, cmask, latents, media_frame_number: int, strength: float,
                                                 num_prefix_latent_frames: int = 2):
         """pipeline_ltx_video.py:1614-1687 with the defaults the caller uses (prefix mode "concat"): the conditioning sequence minus
@@ -139,8 +147,11 @@ class LTXVideoPipeline:
                     m = item.media_item
                     assert m is not None and m.ndim == 5 and m.shape[2] % 8 == 1                  # :1409-1415
                     assert fno >= 0 and fno + m.shape[2] <= num_frames
-                    if tuple(m.shape[-2:]) != (height, width):
-                        raise NotImplementedError("conditioning media must have the target size (resize / border stripping is not implemented)")
+                    if item.media_x or item.media_y:                                              # :1556-1559
+                        raise ValueError("Provide media_item in the target size for spatial conditioning.")
+                    # :1402-1404 every item is brought to the target size first (the multi-scale first pass relies on it), so the
+                    # spatial offset / border stripping of :1566-1612 never sees a smaller item
+                    m = self.resize_tensor(m.to(init_latents.device), height, width)
                     lat = vae_encode(m, self.vae, vae_per_channel_normalize=vae_per_channel_normalize,
                                      noise=item.encode_noise).to(device=init_latents.device, dtype=init_latents.dtype)
                 else:
