@@ -402,8 +402,20 @@ def case_multiscale():
     print("written", os.path.join(GOLD, "ltx_multiscale.pt"))
 
 
+def case_sinusoid():
+    """The timestep sinusoid of AdaLayerNormSingle: diffusers' get_timestep_embedding, which the reference VENDORS
+    (ltx_video/models/transformers/embeddings.py:10-50) — so this piece of the diffusers boundary is pinned by reference code.
+    The oracle's restatement must match it bit for bit (flip_sin_to_cos=True, downscale_freq_shift=0, 256 channels)."""
+    from ltx_video.models.transformers.embeddings import get_timestep_embedding
+    t = torch.cat([torch.tensor([0.0, 1.0, 0.5, 999.0, 1000.0]), torch.rand(59, generator=torch.Generator().manual_seed(9)) * 1000])
+    ref = get_timestep_embedding(t, 256, flip_sin_to_cos=True, downscale_freq_shift=0)
+    assert torch.equal(O.timestep_sinusoid(t, 256), ref), "timestep sinusoid not bit-exact"
+    print("  timestep sinusoid: bit-exact against the reference's vendored get_timestep_embedding", tuple(ref.shape))
+    torch.save(dict(t=t, emb=ref), os.path.join(GOLD, "timestep_sinusoid.pt"))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["patchifier", "scheduler", "transformer", "vae", "vae_encode", "pipeline", "multiscale"]
+    which = sys.argv[1:] or ["patchifier", "scheduler", "sinusoid", "transformer", "vae", "vae_encode", "pipeline", "multiscale"]
     for w in which:
         print(f"[{w}]")
         globals()["case_" + w]()

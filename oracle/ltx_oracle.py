@@ -11,7 +11,8 @@ and asserts this file reproduces them (fp32, CPU) before writing tests/golden/*.
 The diffusers pieces the reference calls (AdaLayerNormSingle, RMSNorm, GELU,
 PixArtAlphaTextProjection) are third-party (diffusers>=0.31, requirements.txt:4,
 not vendored): they are restated here from the published v0.31 source; no
-reference test pins them ("parity unpinned" for that boundary).
+reference test pins them ("parity unpinned" for that boundary), except the timestep
+sinusoid, which the reference vendors (ltx_video/models/transformers/embeddings.py:10-50): bit-exact fixture.
 
 Every function cites the reference file:line it follows.
 """

@@ -7,20 +7,12 @@ from torch import nn
 
 def get_timestep_embedding(timesteps, embedding_dim, flip_sin_to_cos=False,
                            downscale_freq_shift=1, scale=1, max_period=10000):
-    assert len(timesteps.shape) == 1
-    half_dim = embedding_dim // 2
-    exponent = -math.log(max_period) * torch.arange(
-        start=0, end=half_dim, dtype=torch.float32, device=timesteps.device)
-    exponent = exponent / (half_dim - downscale_freq_shift)
-    emb = torch.exp(exponent)
-    emb = timesteps[:, None].float() * emb[None, :]
-    emb = scale * emb
-    emb = torch.cat([torch.sin(emb), torch.cos(emb)], dim=-1)
-    if flip_sin_to_cos:
-        emb = torch.cat([emb[:, half_dim:], emb[:, :half_dim]], dim=-1)
-    if embedding_dim % 2 == 1:
-        emb = F.pad(emb, (0, 1, 0, 0))
-    return emb
+    """The reference vendors this diffusers function itself (ltx_video/models/transformers/embeddings.py:10-50, "Adapted from
+    diffusers/models/embeddings.py"), so the stand-in delegates to the reference's copy: the sinusoid that AdaLayerNormSingle's
+    `Timesteps` computes is thereby PINNED by reference code, not by a restatement."""
+    from ltx_video.models.transformers.embeddings import get_timestep_embedding as vendored
+    return vendored(timesteps, embedding_dim, flip_sin_to_cos=flip_sin_to_cos, downscale_freq_shift=downscale_freq_shift,
+                    scale=scale, max_period=max_period)
 
 
 class Timesteps(nn.Module):

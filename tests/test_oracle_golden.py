@@ -285,3 +285,10 @@ def test_baseline_config0_full_depth_matches_reference(golden_dir):
         img = O.postprocess(O.vae_decode(O.make_vae_decoder_state_dict(seed=m["seed_vae"]), O.unpatchify(lat, f, h, w)))
     assert tuple(img.shape) == (1, 3, m["F"], m["H"], m["W"])
     assert O.psnr(img, g["frames"].float()) > 60          # fixture frames are stored in fp16
+
+
+def test_timestep_sinusoid_bit_exact(golden_dir):
+    """The oracle's timestep sinusoid vs the reference's vendored get_timestep_embedding (ltx_video/models/transformers/embeddings.py:10-50),
+    the one diffusers function on the path that the reference tree itself contains."""
+    g = _load(golden_dir, "timestep_sinusoid.pt")
+    assert torch.equal(O.timestep_sinusoid(g["t"], 256), g["emb"])
