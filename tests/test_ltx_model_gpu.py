@@ -538,3 +538,63 @@ def test_pipeline_keyframe_conditioning_vs_oracle():
         print(f"keyframe conditioning step {i}: rel_l2 = {err:.3e}")
         assert err < TOL_LATENTS
     assert torch.equal(per_step[-1][:, :24].cpu(), tok[:, :24].float())          # the hard-conditioned keyframe tokens are never touched
+
+
+def test_ltx_transformer_without_prompt_mask_equals_all_ones_mask():
+    """`encoder_attention_mask=None` must give the all-ones-mask result (the unbiased cross-attention path differs only
+    in which exponentials come from the polynomial), so that the pipeline may drop an all-ones mask."""
+    from ltx_video_gpupoor_b200.ltx.transformer3d import Transformer3DModel
+    from oracle import ltx_oracle as O
+    f, h, w, Lc = 3, 4, 6, 32
+    m = Transformer3DModel(num_layers=2)
+    m.load_state_dict(O.make_transformer_state_dict(O.LTX_2B, seed=0, num_layers=2))
+    g = torch.Generator().manual_seed(11)
+    hidden = torch.randn(2, f * h * w, 128, generator=g)
+    enc = torch.randn(2, Lc, 4096, generator=g)
+    coords = O.latent_to_pixel_coords(O.latent_coords(f, h, w, 1)).float()
+    coords[:, 0] /= 25.0
+    fc = m.precompute_freqs_cis(coords.to(DEV))
+    kw = dict(freqs_cis=fc, encoder_hidden_states=enc.to(DEV), timestep=torch.full((2, 1), 0.7, device=DEV), latent_shape=(f, h, w),
+              return_dict=False)
+    y1 = m(hidden.to(DEV), encoder_attention_mask=torch.ones(2, Lc, device=DEV), **kw)[0]
+    y0 = m(hidden.to(DEV), encoder_attention_mask=None, **kw)[0]
+    torch.cuda.synchronize()
+    e = O.rel_l2(y0.float().cpu(), y1.float().cpu())
+    print(f"transformer without mask vs all-ones mask: rel_l2 = {e:.3e}")
+    assert e < 5e-3
+
+
+def test_pipeline_resizes_conditioning_media_like_the_reference():
+    """pipeline_ltx_video.py:748-760, 1402-1404: a conditioning image of another size is bilinearly resized (align_corners=False) to the
+    target size before the VAE encoder — what the multi-scale first pass relies on.  Passing the image at 192x288 must give the latents
+    of passing F.interpolate(image, (128, 192)) directly."""
+    import torch.nn.functional as F
+    from ltx_video_gpupoor_b200.ltx.causal_video_autoencoder import CausalVideoAutoencoder
+    from ltx_video_gpupoor_b200.ltx.pipeline_ltx_video import ConditioningItem, LTXVideoPipeline
+    from ltx_video_gpupoor_b200.ltx.rf import RectifiedFlowScheduler
+    from ltx_video_gpupoor_b200.ltx.symmetric_patchifier import SymmetricPatchifier
+    from ltx_video_gpupoor_b200.ltx.transformer3d import Transformer3DModel
+    from oracle import ltx_oracle as O
+    m = Transformer3DModel(num_layers=2)
+    m.load_state_dict(O.make_transformer_state_dict(O.LTX_2B, seed=0, num_layers=2))
+    vae = CausalVideoAutoencoder()
+    vsd = dict(O.make_vae_decoder_state_dict(seed=1))
+    vsd.update(O.make_vae_encoder_state_dict(seed=2))
+    vae.load_state_dict(vsd)
+    pipe = LTXVideoPipeline(vae=vae, transformer=m, scheduler=RectifiedFlowScheduler(), patchifier=SymmetricPatchifier(1))
+    g = torch.Generator().manual_seed(4)
+    pe, pm = torch.randn(1, 16, 4096, generator=g), torch.ones(1, 16)
+    big = torch.rand(1, 3, 1, 192, 288, generator=g) * 2 - 1
+    small = F.interpolate(big[:, :, 0], size=(128, 192), mode="bilinear", align_corners=False)[:, :, None]
+    noise_e = torch.zeros(1, 128, 1, 4, 6)
+    outs = []
+    for image in (big, small):
+        outs.append(pipe(height=128, width=192, num_frames=17, frame_rate=25.0, prompt_embeds=pe, prompt_attention_mask=pm,
+                         num_inference_steps=2, guidance_scale=1.0, stg_scale=0.0, rescaling_scale=1.0,
+                         generator=torch.Generator().manual_seed(5), output_type="latent", return_dict=False, is_video=True,
+                         vae_per_channel_normalize=True,
+                         conditioning_items=[ConditioningItem(media_item=image, media_frame_number=0, conditioning_strength=1.0,
+                                                              encode_noise=noise_e)])[0].float().cpu())
+    e = O.rel_l2(outs[0], outs[1])
+    print(f"resized-in-pipeline vs pre-resized conditioning image: latents rel_l2 = {e:.3e}")
+    assert e < 2e-3
