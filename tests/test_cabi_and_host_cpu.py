@@ -249,3 +249,24 @@ def test_rf_scheduler_samplers_and_shiftings_bit_exact(golden_dir, tmp_path):
         assert torch.equal(s.timesteps, g["tables"][("linear_quadratic_sd3_terminal", 30, (1, 128, 16, 16, 24))])
     with pytest.raises(ValueError):
         RectifiedFlowScheduler(sampler="Nope")
+
+
+def test_every_compute_entry_point_rejects_null_arguments():
+    """All-null / all-zero arguments must come back as an error code from every compute entry point of the C ABI (validation runs before
+    any CUDA call or pointer use, so this is safe on a machine without a GPU) — never a crash, never 0."""
+    import ctypes
+    from ltx_video_gpupoor_b200 import _lib
+    lib = _lib.lib()
+    skipped = {"ltxb200_abi_version", "ltxb200_error_string", "ltxb200_launch_count", "ltxb200_comm_open", "ltxb200_comm_close",
+               "ltxb200_comm_free"}                                     # queries, and calls whose only argument is a CUDA IPC handle / pointer
+    checked = 0
+    for name in _lib.EXPORTED_SYMBOLS:
+        if name in skipped:
+            continue
+        fn = getattr(lib, name)
+        args = [0.0 if t is ctypes.c_float else (None if (t is ctypes.c_void_p or hasattr(t, "contents")) else 0) for t in fn.argtypes]
+        rc = fn(*args)
+        assert rc < 0, f"{name} accepted null arguments (rc {rc})"
+        assert lib.ltxb200_error_string(rc), name
+        checked += 1
+    assert checked >= 35
