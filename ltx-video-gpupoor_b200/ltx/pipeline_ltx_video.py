@@ -105,6 +105,12 @@ class LTXVideoPipeline:
         assert tuple(latents.shape) == tuple(latent_shape)
         return timestep * noise + (1 - timestep) * latents.to(device=device, dtype=dtype)
 
+    def trim_conditioning_sequence(self, start_frame: int, sequence_num_frames: int, target_num_frames: int) -> int:
+        """pipeline_ltx_video.py:1689-1707 (called by ltxv.py:495-499 while it loads conditioning media): the longest prefix of a
+        conditioning sequence that fits before the end of the video and holds 8k + 1 frames."""
+        fits = min(sequence_num_frames, target_num_frames - start_frame)
+        return (fits - 1) // self.video_scale_factor * self.video_scale_factor + 1
+
     @staticmethod
     def resize_tensor(media_items: torch.Tensor, height: int, width: int) -> torch.Tensor:
         """pipeline_ltx_video.py:748-760: per-frame F.interpolate(mode="bilinear", align_corners=False) of [b, c, n, h, w] pixels

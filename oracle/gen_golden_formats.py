@@ -37,6 +37,30 @@ def main():
     with open(path, "w") as f:
         json.dump(out, f, indent=1, sort_keys=False)
     print("written", path)
+    trim_sequence_grid()
+
+
+def trim_sequence_grid():
+    """LTXVideoPipeline.trim_conditioning_sequence (pipeline_ltx_video.py:1689-1707): the reference method on a grid of
+    (start frame, sequence length, video length) -> tests/golden/ltx_trim_sequence.json; the product method must agree on every row."""
+    from types import SimpleNamespace
+    import ltx_video.pipelines.pipeline_ltx_video as R
+    from ltx_video_gpupoor_b200.ltx.pipeline_ltx_video import LTXVideoPipeline
+    ours = LTXVideoPipeline.__new__(LTXVideoPipeline)
+    ours.video_scale_factor = 8
+    ref = SimpleNamespace(video_scale_factor=8)
+    rows = []
+    for start in (0, 8, 16, 24, 40, 96):
+        for n in (1, 9, 17, 25, 33, 49, 57, 97, 121, 130):
+            for target in (9, 17, 33, 97, 121, 257):
+                if target - start < 1:
+                    continue
+                r = R.LTXVideoPipeline.trim_conditioning_sequence(ref, start, n, target)
+                assert ours.trim_conditioning_sequence(start, n, target) == r
+                rows.append([start, n, target, r])
+    with open(os.path.join(ROOT, "tests", "golden", "ltx_trim_sequence.json"), "w") as f:
+        json.dump(rows, f)
+    print("written tests/golden/ltx_trim_sequence.json:", len(rows), "rows identical")
 
 
 if __name__ == "__main__":

@@ -270,3 +270,16 @@ def test_every_compute_entry_point_rejects_null_arguments():
         assert lib.ltxb200_error_string(rc), name
         checked += 1
     assert checked >= 35
+
+
+def test_trim_conditioning_sequence_matches_reference(golden_dir):
+    """LTXVideoPipeline.trim_conditioning_sequence (pipeline_ltx_video.py:1689-1707) on the grid recorded from the reference method."""
+    import json
+    from ltx_video_gpupoor_b200.ltx.pipeline_ltx_video import LTXVideoPipeline
+    pipe = LTXVideoPipeline.__new__(LTXVideoPipeline)
+    pipe.video_scale_factor = 8
+    with open(os.path.join(golden_dir, "ltx_trim_sequence.json")) as f:
+        rows = json.load(f)
+    assert len(rows) > 200
+    for start, n, target, expected in rows:
+        assert pipe.trim_conditioning_sequence(start, n, target) == expected
