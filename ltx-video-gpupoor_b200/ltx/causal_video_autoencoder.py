@@ -20,6 +20,7 @@ from typing import Dict, List, Optional, Tuple
 import torch
 
 from .. import ops
+from ..module_like import ModuleLike
 
 BF16 = torch.bfloat16
 
@@ -69,7 +70,7 @@ class _Decoder:
     timestep_conditioning = False
 
 
-class CausalVideoAutoencoder:
+class CausalVideoAutoencoder(ModuleLike):
     def __init__(self, **config):
         cfg = dict(LTX_VAE_CONFIG)
         cfg.update({k: v for k, v in config.items()})

@@ -12,6 +12,7 @@ from typing import Dict, Optional
 import torch
 
 from .. import ops
+from ..module_like import ModuleLike
 
 BF16 = torch.bfloat16
 
@@ -24,7 +25,7 @@ def _pack(w: torch.Tensor, perm: Optional[torch.Tensor] = None) -> torch.Tensor:
     return w.permute(*order).reshape(w.shape[0], -1).to(BF16).contiguous()
 
 
-class LatentUpsampler:
+class LatentUpsampler(ModuleLike):
     def __init__(self, in_channels: int = 128, mid_channels: int = 512, num_blocks_per_stage: int = 4, dims: int = 3,
                  spatial_upsample: bool = True, temporal_upsample: bool = False):
         if dims != 3 or not spatial_upsample or temporal_upsample:

@@ -18,6 +18,7 @@ from typing import Any, Dict, List, Optional
 import torch
 
 from .. import ops
+from ..module_like import ModuleLike
 from .skip_layer_strategy import SkipLayerStrategy
 
 BF16 = torch.bfloat16
@@ -38,7 +39,7 @@ LTX_2B_CONFIG = dict(
 )
 
 
-class Transformer3DModel:
+class Transformer3DModel(ModuleLike):
     def __init__(self, **config):
         cfg = dict(LTX_2B_CONFIG)
         cfg.update({k: v for k, v in config.items() if not k.startswith("_")})

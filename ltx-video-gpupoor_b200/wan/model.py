@@ -27,6 +27,7 @@ from typing import Dict, List, Optional
 import torch
 
 from .. import ops
+from ..module_like import ModuleLike
 
 BF16 = torch.bfloat16
 
@@ -38,7 +39,7 @@ WAN_I2V_14B = dict(WAN_T2V_14B, model_type="i2v", in_dim=36)                    
 CLIP_TOKENS = 257                                                                         # WanI2VCrossAttention :306-307
 
 
-class WanModel:
+class WanModel(ModuleLike):
     def __init__(self, vace_layers=None, vace_in_dim=None, model_type="t2v", patch_size=(1, 2, 2), text_len=512,
                  in_dim=16, dim=2048, ffn_dim=8192, freq_dim=256, text_dim=4096, out_dim=16, num_heads=16,
                  num_layers=32, window_size=(-1, -1), qk_norm=True, cross_attn_norm=True, eps=1e-6, recammaster=False,

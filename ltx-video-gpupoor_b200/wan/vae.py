@@ -28,6 +28,7 @@ from typing import Dict, List, Optional
 import torch
 
 from .. import ops
+from ..module_like import ModuleLike
 
 BF16 = torch.bfloat16
 WAN_VAE_MEAN = [-0.7571, -0.7089, -0.9113, 0.1075, -0.1745, 0.9653, -0.1517, 1.5508, 0.4134, -0.0715, 0.5517, -0.3632, -0.1922,
@@ -44,7 +45,7 @@ def _pad8(c: int) -> int:
     return (c + 7) // 8 * 8
 
 
-class WanVAE:
+class WanVAE(ModuleLike):
     def __init__(self, z_dim: int = 16, vae_pth: Optional[str] = None, dtype=torch.float, device="cuda", dim: int = 96,
                  dim_mult=(1, 2, 4, 4), num_res_blocks: int = 2, temperal_downsample=(False, True, True)):
         self.z_dim, self.dim, self.dim_mult, self.num_res_blocks = z_dim, dim, list(dim_mult), num_res_blocks

@@ -283,3 +283,23 @@ def test_trim_conditioning_sequence_matches_reference(golden_dir):
     assert len(rows) > 200
     for start, n, target, expected in rows:
         assert pipe.trim_conditioning_sequence(start, n, target) == expected
+
+
+def test_model_objects_accept_the_reference_loaders_module_calls():
+    """`model.eval().requires_grad_(False)` (wan/text2video.py:101), `vae.to(torch.bfloat16)`, `latent_upsampler.to("cpu").eval()`
+    (ltx_video/ltxv.py:176,199-200) keep working on the drop-in classes; anything that would change what the packed bf16 weights are is refused."""
+    from ltx_video_gpupoor_b200.ltx.causal_video_autoencoder import CausalVideoAutoencoder
+    from ltx_video_gpupoor_b200.ltx.latent_upsampler import LatentUpsampler
+    from ltx_video_gpupoor_b200.ltx.transformer3d import Transformer3DModel
+    from ltx_video_gpupoor_b200.wan.model import WanModel
+    from ltx_video_gpupoor_b200.wan.vae import WanVAE
+    objs = [Transformer3DModel(num_layers=1), CausalVideoAutoencoder(), LatentUpsampler(in_channels=128, mid_channels=256, num_blocks_per_stage=1, dims=3),
+            WanModel(dim=256, ffn_dim=512, num_heads=2, num_layers=1), WanVAE()]
+    for m in objs:
+        assert m.eval().requires_grad_(False) is m
+        assert m.to(torch.bfloat16) is m and m.to("cpu").eval() is m and m.to(device="cuda", dtype=torch.bfloat16) is m
+        m._model_dtype = torch.bfloat16                      # ltxv.py:177,193 tag the objects
+        with pytest.raises(NotImplementedError):
+            m.to(torch.float16)
+        with pytest.raises(NotImplementedError):
+            m.requires_grad_(True)
