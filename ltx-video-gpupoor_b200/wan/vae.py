@@ -59,6 +59,11 @@ class WanVAE(ModuleLike):
             raise NotImplementedError("checkpoint loading is out of scope: call load_state_dict(state_dict)")
 
     # ---------------------------------------------------------------------------------------------
+    @staticmethod
+    def get_VAE_tile_size(vae_config, device_mem_capacity, mixed_precision):
+        """wan/modules/vae.py:789-811 answers 0 (no tiling) from 24 GB up; `tile_size` is accepted by encode / decode and selects nothing."""
+        return 0
+
     def _layout(self):
         dm = self.dim_mult
         dims = [self.dim * u for u in [dm[-1]] + dm[::-1]]
