@@ -7,7 +7,8 @@ built here the way the reference builds it (:232-244, 262-277): the start image 
 output size — PIL / lanczos resizing is media I/O) padded with F-1 zero frames goes through `WanVAE.encode` (wan/vae.py) and
 the 4-channel conditioning-frame mask is stacked on top; an end image (`image_end`, :191-199) adds one frame that is encoded without the
 VAE's feature caches.  CLIP visual (:219-224) and T5 are out of scope: pass `clip_fea=`
-[1, 257, 1280] and `context=` / `context_null=`.  The result is the denoised latent [16, (F-1)/4+1, H/8, W/8] (fp32).
+[1, 257, 1280] and `context=` / `context_null=`.  The result is the denoised latent [16, (F-1)/4+1, H/8, W/8] (fp32); with an added end
+frame it has one latent frame more — decode it with `WanVAE.decode(..., any_end_frame=True)` and drop the last pixel frame, as :419-424 does.
 """
 from __future__ import annotations
 

@@ -93,5 +93,72 @@ def main():
     print("written tests/golden/wan_generate.pt")
 
 
+def _mask(frame_num, lat_h, lat_w, any_end, added):
+    """The oracle's statement of the conditioning-frame mask (image2video.py:232-244) -> [4, latent frames, lat_h, lat_w]."""
+    m = torch.zeros(frame_num, lat_h, lat_w)
+    m[0] = 1
+    if any_end:
+        m[-1] = 1
+    parts = [m[:1].repeat(4, 1, 1), m[1:-1] if (any_end and added) else m[1:]]
+    if any_end and added:
+        parts.append(m[-1:].repeat(4, 1, 1))
+    m = torch.cat(parts)
+    return m.view(m.shape[0] // 4, 4, lat_h, lat_w).transpose(0, 1)
+
+
+def main_i2v():
+    """WanI2V.generate (wan/image2video.py:124-428), the reference's own method on a stand-in self: CLIP and the VAE encoder answer with fixed
+    tensors (they are inputs of this path), so what is pinned is the frame / latent-frame arithmetic incl. the added end frame, the mask and
+    `y = [mask | latent]`, the noise from `seed`, and the loop with clip_fea / y on the i2v WanModel."""
+    import_reference_text2video()
+    import wan.image2video as I
+    from mmgp import offload
+    from PIL import Image
+    offload.last_offload_obj = SimpleNamespace(unload_all=lambda: None)          # image2video.py:264 frees the text encoder / CLIP here
+    cfg = dict(TINY, model_type="i2v", in_dim=36, clip_dim=1280)
+    sd = {k: v.double() for k, v in W.make_wan_state_dict(cfg, seed=1).items()}
+    ref = build_ref(cfg, sd)
+    g = torch.Generator().manual_seed(5)
+    clip = torch.randn(1, 257, 1280, generator=g).double()
+    ctx, ctx0 = torch.randn(20, 4096, generator=g).double(), torch.randn(11, 4096, generator=g).double()
+    lat_y = {3: torch.randn(16, 3, 8, 12, generator=g).double(), 4: torch.randn(16, 4, 8, 12, generator=g).double()}   # by latent frames
+    seen = {}
+
+    def encode(videos, tile, any_end_frame=False):
+        f = videos[0].shape[1]
+        seen.update(frames=f, any_end_frame=any_end_frame)
+        return [lat_y[(f - 2) // 4 + 2 if any_end_frame else (f - 1) // 4 + 1]]
+    me = SimpleNamespace(device=torch.device("cpu"), dtype=torch.float64, VAE_dtype=torch.float32, _interrupt=False, sample_neg_prompt="neg",
+                         vae_stride=(4, 8, 8), patch_size=(1, 2, 2), num_train_timesteps=1000, model=_Fp64Model(ref),
+                         text_encoder=lambda prompts, device: [ctx if prompts[0] == "pos" else ctx0],
+                         clip=SimpleNamespace(model=SimpleNamespace(image_size=224), visual=lambda imgs: clip),
+                         vae=SimpleNamespace(encode=encode, decode=lambda x0, tile, any_end_frame=False: x0))
+    img = Image.new("RGB", (96, 64), (120, 30, 200))
+    out = {}
+    for name, kw in {"start_image": dict(image_end=None, sampling_steps=4, guide_scale=5.0, cfg_star_switch=True, cfg_zero_step=1, joint_pass=True),
+                     "start_and_end_image": dict(image_end=img, sampling_steps=3, guide_scale=5.0, cfg_star_switch=False, cfg_zero_step=5,
+                                                 joint_pass=False)}.items():
+        seed = 77
+        lat_ref = I.WanI2V.generate(me, "pos", img, height=64, width=96, frame_num=9, shift=5.0, seed=seed, n_prompt="",
+                                    sample_solver="unipc", model_filename="wan2.1_image2video_480p_14B_bf16.safetensors", **kw)
+        any_end = kw["image_end"] is not None
+        frames, lat_frames = (10, 4) if any_end else (9, 3)                                  # :191-199
+        assert seen["frames"] == frames and seen["any_end_frame"] == any_end
+        noise = torch.randn(16, lat_frames, 8, 12, dtype=torch.float32, generator=torch.Generator().manual_seed(seed))
+        y = torch.cat([_mask(frames, 8, 12, any_end, True).double(), lat_y[lat_frames]])
+        mine = W.t2v_denoise(sd, cfg, noise.double(), ctx, ctx0, steps=kw["sampling_steps"], shift=5.0, guide_scale=kw["guide_scale"],
+                             cfg_star_switch=kw["cfg_star_switch"], cfg_zero_step=kw["cfg_zero_step"], clip_fea=clip, y=y)
+        if any_end:
+            mine = mine[:, :-1]                                                                # :422-424 drops the added frame after decoding
+        e = rel_l2(mine, lat_ref)
+        print(f"  WanI2V.generate[{name}]: rel_l2(oracle loop, reference method) = {e:.3e}")
+        assert e < 5e-5, name
+        out[name] = dict(kw={k: v for k, v in kw.items() if k != "image_end"}, any_end=any_end, seed=seed, frames=frames,
+                         lat_frames=lat_frames, y=y.float(), latents=lat_ref.float().clone())
+    torch.save(dict(cfg=cfg, clip=clip.float(), ctx=ctx.float(), ctx0=ctx0.float(), cases=out), os.path.join(GOLD, "wan_i2v_generate.pt"))
+    print("written tests/golden/wan_i2v_generate.pt")
+
+
 if __name__ == "__main__":
     main()
+    main_i2v()

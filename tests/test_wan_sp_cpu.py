@@ -159,3 +159,27 @@ def test_oracle_loop_matches_reference_generate_method(golden_dir):
                                 guide_scale=kw["guide_scale"], cfg_star_switch=kw["cfg_star_switch"], cfg_zero_step=kw["cfg_zero_step"],
                                 sample_solver=kw["sample_solver"])
         assert W.rel_l2(lat, g["cases"][name]["latents"]) < 5e-5, name
+
+
+def test_i2v_oracle_loop_and_product_mask_match_reference_generate_method(golden_dir):
+    """WanI2V.generate, the reference's own method on a stand-in self (oracle/gen_golden_wan_generate.py:main_i2v): the oracle's i2v loop on
+    `y = [mask | latent]` vs the returned latents — start image, and start + end image (one frame added, mask on both ends, last latent frame
+    dropped) — and the PRODUCT's first_frame_mask (host-side torch) against the mask rows of that y, bit for bit."""
+    from types import SimpleNamespace
+    from ltx_video_gpupoor_b200.wan.image2video import WanI2V
+    g = torch.load(os.path.join(golden_dir, "wan_i2v_generate.pt"), weights_only=False)
+    cfg = g["cfg"]
+    sd = {k: v.double() for k, v in W.make_wan_state_dict(cfg, seed=1).items()}
+    pipe = WanI2V(SimpleNamespace(model_type="i2v"), device="cpu")
+    assert len(g["cases"]) == 2
+    for name, c in g["cases"].items():
+        kw = c["kw"]
+        assert torch.equal(pipe.first_frame_mask(c["frames"], 8, 12, c["any_end"], True), c["y"][:4]), name
+        noise = torch.randn(16, c["lat_frames"], 8, 12, dtype=torch.float32, generator=torch.Generator().manual_seed(c["seed"]))
+        with torch.no_grad():
+            lat = W.t2v_denoise(sd, cfg, noise.double(), g["ctx"].double(), g["ctx0"].double(), steps=kw["sampling_steps"], shift=5.0,
+                                guide_scale=kw["guide_scale"], cfg_star_switch=kw["cfg_star_switch"], cfg_zero_step=kw["cfg_zero_step"],
+                                clip_fea=g["clip"].double(), y=c["y"].double())
+        if c["any_end"]:
+            lat = lat[:, :-1]
+        assert W.rel_l2(lat, c["latents"]) < 5e-5, name
