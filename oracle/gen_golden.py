@@ -88,6 +88,13 @@ def case_transformer():
                     ltxv_model=_NoInterrupt(), return_dict=False)[0]
         y = O.transformer_forward(sd, cfg, hidden, (cos, sin), enc, ts, mask, skip, strat, (f, h, w))
         _check(f"transformer[{tag}]", y, y_ref)
+        # joint_pass=False (transformer3d.py:472-487) walks the blocks sample by sample to save memory: same arithmetic per sample, so
+        # the drop-in runs every sample in one batch whatever the flag says
+        y_seq = ref(hidden.clone(), freqs_cis=(cos_ref, sin_ref), encoder_hidden_states=enc,
+                    timestep=ts, encoder_attention_mask=mask, skip_layer_mask=skip,
+                    skip_layer_strategy=strat_ref, latent_shape=(f, h, w), joint_pass=False,
+                    ltxv_model=_NoInterrupt(), return_dict=False)[0]
+        _check(f"transformer[{tag}] joint_pass=False vs True (reference)", y_seq, y_ref, tol=2e-6)
         out[tag] = dict(hidden=hidden, enc=enc, mask=mask, timestep=ts, out=y_ref,
                         skip=skip)
     out["rope_cos_row5"] = cos_ref[0, 5].clone()
