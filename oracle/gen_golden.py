@@ -314,6 +314,55 @@ def case_pipeline():
     torch.save(out, os.path.join(GOLD, "ltx_pipeline.pt"))
 
 
+def case_pipeline_i2v():
+    """BASELINE configs[2] in small, end to end through the reference's OWN __call__: a pixel-space ConditioningItem goes through the
+    reference VAE ENCODER inside prepare_conditioning (:1396-1448), the loop runs with the per-token timesteps / conditioning mask and
+    image_cond_noise_scale = 0; the oracle composes vae_encode + first-frame blend + denoise_loop and must give the same latents."""
+    from ltx_video.pipelines.pipeline_ltx_video import ConditioningItem, LTXVideoPipeline
+    from ltx_video.schedulers.rf import RectifiedFlowScheduler
+    from ltx_video.models.transformers.symmetric_patchifier import SymmetricPatchifier
+    from ltx_video.utils.diffusers_config_mapping import OURS_SCHEDULER_CONFIG
+    cfg, L = O.LTX_2B, 2
+    sd = O.make_transformer_state_dict(cfg, seed=0, num_layers=L)
+    tr = build_ref_transformer(L, sd)
+    esd = O.make_vae_encoder_state_dict(seed=2)                     # encoder.* + the latent statistics
+    vae = build_ref_vae(dict(O.make_vae_decoder_state_dict(seed=1), std_of_means=esd["std_of_means"], mean_of_means=esd["mean_of_means"]))
+    vae.encoder.load_state_dict({k[len("encoder."):]: v for k, v in esd.items() if k.startswith("encoder.")}, strict=True)
+    pipe = LTXVideoPipeline(tokenizer=None, text_encoder=None, vae=vae, transformer=tr,
+                            scheduler=RectifiedFlowScheduler.from_config(dict(OURS_SCHEDULER_CONFIG)),
+                            patchifier=SymmetricPatchifier(patch_size=1), prompt_enhancer_image_caption_model=None,
+                            prompt_enhancer_image_caption_processor=None, prompt_enhancer_llm_model=None, prompt_enhancer_llm_tokenizer=None)
+    H, W, F_, fps, steps = 128, 192, 17, 25.0, 3                   # latent (1,128,3,4,6)
+    g = torch.Generator().manual_seed(4)
+    pe, pm = torch.randn(1, 16, 4096, generator=g), torch.ones(1, 16)
+    image = torch.rand(1, 3, 1, H, W, generator=g) * 2 - 1
+    cwd = os.getcwd()
+    os.chdir("/tmp")
+    try:
+        torch.manual_seed(123)                                       # latent_dist.sample() draws from the global RNG (vae_encode.py:77)
+        with _cuda_to_cpu():
+            lat = pipe(height=H, width=W, num_frames=F_, frame_rate=fps, prompt_embeds=pe, prompt_attention_mask=pm,
+                       negative_prompt_embeds=None, negative_prompt_attention_mask=None, num_inference_steps=steps,
+                       generator=torch.Generator().manual_seed(5), output_type="latent", return_dict=False, joint_pass=True,
+                       ltxv_model=_NoInterrupt(), is_video=True, vae_per_channel_normalize=True, guidance_scale=1.0, stg_scale=0.0,
+                       rescaling_scale=1.0, image_cond_noise_scale=0.0,
+                       conditioning_items=[ConditioningItem(media_item=image, media_frame_number=0, conditioning_strength=1.0)])[0]
+    finally:
+        os.chdir(cwd)
+    torch.manual_seed(123)
+    noise_e = torch.randn(1, 128, 1, 4, 6)
+    cond_lat = O.vae_encode(esd, image, noise=noise_e)
+    init = O.unpatchify(torch.randn(1, 72, 128, generator=torch.Generator().manual_seed(5)), 3, 4, 6).clone()
+    init[:, :, :1] = cond_lat
+    cmask = torch.zeros(1, 3, 4, 6)
+    cmask[:, :1] = 1.0
+    mine = O.denoise_loop(sd, cfg, O.patchify(init), pe, pm, num_frames_lat=3, lat_h=4, lat_w=6, frame_rate=fps, num_steps=steps,
+                          conditioning_mask=cmask.reshape(1, -1))
+    _check("pipeline i2v from pixels (reference __call__ vs oracle composition)", O.unpatchify(mine, 3, 4, 6), lat, tol=5e-5)
+    torch.save(dict(meta=dict(H=H, W=W, F=F_, fps=fps, steps=steps, num_layers=L), pe=pe, pm=pm, image=image, noise_e=noise_e,
+                    noise_seed=5, latents=lat.clone()), os.path.join(GOLD, "ltx_pipeline_i2v.pt"))
+
+
 def build_ref_upsampler(sd, in_channels, mid_channels, nb):
     from ltx_video.models.autoencoders.latent_upsampler import LatentUpsampler
     m = LatentUpsampler(in_channels=in_channels, mid_channels=mid_channels, num_blocks_per_stage=nb, dims=3,
@@ -422,7 +471,7 @@ def case_sinusoid():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["patchifier", "scheduler", "sinusoid", "transformer", "vae", "vae_encode", "pipeline", "multiscale"]
+    which = sys.argv[1:] or ["patchifier", "scheduler", "sinusoid", "transformer", "vae", "vae_encode", "pipeline", "pipeline_i2v", "multiscale"]
     for w in which:
         print(f"[{w}]")
         globals()["case_" + w]()

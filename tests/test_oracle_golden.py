@@ -292,3 +292,21 @@ def test_timestep_sinusoid_bit_exact(golden_dir):
     the one diffusers function on the path that the reference tree itself contains."""
     g = _load(golden_dir, "timestep_sinusoid.pt")
     assert torch.equal(O.timestep_sinusoid(g["t"], 256), g["emb"])
+
+
+def test_pipeline_i2v_from_pixels_matches_reference_call(golden_dir):
+    """The oracle's composition for pixel-space first-frame conditioning (vae_encode -> blend into the noise -> loop with the conditioning
+    mask) vs the latents of the reference's own LTXVideoPipeline.__call__ with a ConditioningItem(media_item=...) (gen_golden.py:case_pipeline_i2v)."""
+    g = _load(golden_dir, "ltx_pipeline_i2v.pt")
+    m = g["meta"]
+    sd = O.make_transformer_state_dict(O.LTX_2B, seed=0, num_layers=m["num_layers"])
+    esd = O.make_vae_encoder_state_dict(seed=2)
+    with torch.no_grad():
+        cond_lat = O.vae_encode(esd, g["image"], noise=g["noise_e"])
+        init = O.unpatchify(torch.randn(1, 72, 128, generator=torch.Generator().manual_seed(g["noise_seed"])), 3, 4, 6).clone()
+        init[:, :, :1] = cond_lat
+        cmask = torch.zeros(1, 3, 4, 6)
+        cmask[:, :1] = 1.0
+        lat = O.denoise_loop(sd, O.LTX_2B, O.patchify(init), g["pe"], g["pm"], num_frames_lat=3, lat_h=4, lat_w=6, frame_rate=m["fps"],
+                             num_steps=m["steps"], conditioning_mask=cmask.reshape(1, -1))
+    assert O.rel_l2(O.unpatchify(lat, 3, 4, 6), g["latents"]) < 5e-5
