@@ -75,5 +75,63 @@ def main():
     print("written tests/golden/ltx_conditioning.pt")
 
 
+def keyframe_loop():
+    """The whole call with a keyframe in the middle of the video, through the reference's OWN __call__ (its vae_encode answering with fixed
+    latents): extra conditioning tokens with their own pixel coordinates and per-token timesteps are prepended (:1449-1503), carried through
+    the loop and dropped before unpatchify (:1258-1262).  The composition the GPU test checks the CUDA path against — product
+    prepare_conditioning -> oracle denoise_loop(pixel_coords, conditioning_mask) -> drop the extra tokens — must give the same latents."""
+    import ltx_video.pipelines.pipeline_ltx_video as R
+    from ltx_video.models.transformers.symmetric_patchifier import SymmetricPatchifier as RefPatchifier
+    from ltx_video.schedulers.rf import RectifiedFlowScheduler
+    from ltx_video.utils.diffusers_config_mapping import OURS_SCHEDULER_CONFIG
+    from ltx_video_gpupoor_b200.ltx.pipeline_ltx_video import ConditioningItem, LTXVideoPipeline
+    from ltx_video_gpupoor_b200.ltx.symmetric_patchifier import SymmetricPatchifier
+    from oracle import ltx_oracle as O
+    from oracle.gen_golden import _NoInterrupt, _check, _cuda_to_cpu, build_ref_transformer, build_ref_vae
+    torch.set_grad_enabled(False)
+    L = 2
+    sd = O.make_transformer_state_dict(O.LTX_2B, seed=0, num_layers=L)
+    tr = build_ref_transformer(L, sd)
+    vae = build_ref_vae(O.make_vae_decoder_state_dict(seed=1))
+    g = torch.Generator().manual_seed(3)
+    pe, pm = torch.randn(1, 16, 4096, generator=g), torch.ones(1, 16)
+    key = torch.randn(1, 128, 1, 4, 6, generator=g)
+    R.vae_encode = lambda media, vae_, vae_per_channel_normalize=False: key.clone()
+    pipe = R.LTXVideoPipeline(tokenizer=None, text_encoder=None, vae=vae, transformer=tr,
+                              scheduler=RectifiedFlowScheduler.from_config(dict(OURS_SCHEDULER_CONFIG)), patchifier=RefPatchifier(patch_size=1),
+                              prompt_enhancer_image_caption_model=None, prompt_enhancer_image_caption_processor=None,
+                              prompt_enhancer_llm_model=None, prompt_enhancer_llm_tokenizer=None)
+    H, W, F_, fps, steps, fno = 128, 192, 33, 25.0, 3, 16            # latent (1,128,5,4,6) + 24 extra tokens
+    cwd = os.getcwd()
+    os.chdir("/tmp")
+    try:
+        with _cuda_to_cpu():
+            lat = pipe(height=H, width=W, num_frames=F_, frame_rate=fps, prompt_embeds=pe, prompt_attention_mask=pm,
+                       negative_prompt_embeds=None, negative_prompt_attention_mask=None, num_inference_steps=steps,
+                       generator=torch.Generator().manual_seed(5), output_type="latent", return_dict=False, joint_pass=True,
+                       ltxv_model=_NoInterrupt(), is_video=True, vae_per_channel_normalize=True, guidance_scale=1.0, stg_scale=0.0,
+                       rescaling_scale=1.0, image_cond_noise_scale=0.0,
+                       conditioning_items=[R.ConditioningItem(media_item=torch.zeros(1, 3, 1, H, W), media_frame_number=fno,
+                                                              conditioning_strength=1.0)])[0]
+    finally:
+        os.chdir(cwd)
+    ours = LTXVideoPipeline.__new__(LTXVideoPipeline)
+    ours.vae = SimpleNamespace(spatial_downscale_factor=32, temporal_downscale_factor=8)
+    ours.patchifier = SymmetricPatchifier(1)
+    ours.transformer = SimpleNamespace(config=SimpleNamespace(causal_temporal_positioning=bool(getattr(tr.config, "causal_temporal_positioning", False))))
+    gen = torch.Generator().manual_seed(5)                           # one stream: initial noise, then the keyframe noise (:1466-1471)
+    init = O.unpatchify(torch.randn(1, 120, 128, generator=gen), 5, 4, 6)
+    tok, px, cm, extra = ours.prepare_conditioning([ConditioningItem(latents=key.clone(), media_frame_number=fno, conditioning_strength=1.0)],
+                                                   init.clone(), F_, H, W, vae_per_channel_normalize=True, generator=gen)
+    assert extra == 24
+    mine = O.denoise_loop(sd, O.LTX_2B, tok.float(), pe, pm, num_frames_lat=5, lat_h=4, lat_w=6, frame_rate=fps, num_steps=steps,
+                          conditioning_mask=cm, pixel_coords=px)
+    _check("keyframe call (reference __call__ vs prepare_conditioning + oracle loop)", O.unpatchify(mine[:, extra:], 5, 4, 6), lat, tol=5e-5)
+    torch.save(dict(meta=dict(H=H, W=W, F=F_, fps=fps, steps=steps, num_layers=L, frame=fno), pe=pe, pm=pm, key=key, noise_seed=5, latents=lat.clone()),
+               os.path.join(ROOT, "tests", "golden", "ltx_keyframe_loop.pt"))
+    print("written tests/golden/ltx_keyframe_loop.pt")
+
+
 if __name__ == "__main__":
     main()
+    keyframe_loop()

@@ -310,3 +310,28 @@ def test_pipeline_i2v_from_pixels_matches_reference_call(golden_dir):
         lat = O.denoise_loop(sd, O.LTX_2B, O.patchify(init), g["pe"], g["pm"], num_frames_lat=3, lat_h=4, lat_w=6, frame_rate=m["fps"],
                              num_steps=m["steps"], conditioning_mask=cmask.reshape(1, -1))
     assert O.rel_l2(O.unpatchify(lat, 3, 4, 6), g["latents"]) < 5e-5
+
+
+def test_keyframe_call_matches_reference_call(golden_dir):
+    """A keyframe in the middle of the video through the reference's own __call__ (oracle/gen_golden_conditioning.py:keyframe_loop) vs the
+    composition the GPU test uses as its checker: product prepare_conditioning (host torch code) -> oracle loop with the extra tokens'
+    pixel coordinates and per-token timesteps -> extra tokens dropped."""
+    from types import SimpleNamespace
+    from ltx_video_gpupoor_b200.ltx.pipeline_ltx_video import ConditioningItem, LTXVideoPipeline
+    from ltx_video_gpupoor_b200.ltx.symmetric_patchifier import SymmetricPatchifier
+    g = _load(golden_dir, "ltx_keyframe_loop.pt")
+    m = g["meta"]
+    sd = O.make_transformer_state_dict(O.LTX_2B, seed=0, num_layers=m["num_layers"])
+    pipe = LTXVideoPipeline.__new__(LTXVideoPipeline)
+    pipe.vae = SimpleNamespace(spatial_downscale_factor=32, temporal_downscale_factor=8)
+    pipe.patchifier = SymmetricPatchifier(1)
+    pipe.transformer = SimpleNamespace(config=SimpleNamespace(causal_temporal_positioning=False))
+    gen = torch.Generator().manual_seed(g["noise_seed"])
+    init = O.unpatchify(torch.randn(1, 120, 128, generator=gen), 5, 4, 6)
+    tok, px, cm, extra = pipe.prepare_conditioning([ConditioningItem(latents=g["key"].clone(), media_frame_number=m["frame"], conditioning_strength=1.0)],
+                                                   init.clone(), m["F"], m["H"], m["W"], vae_per_channel_normalize=True, generator=gen)
+    assert extra == 24
+    with torch.no_grad():
+        lat = O.denoise_loop(sd, O.LTX_2B, tok.float(), g["pe"], g["pm"], num_frames_lat=5, lat_h=4, lat_w=6, frame_rate=m["fps"],
+                             num_steps=m["steps"], conditioning_mask=cm, pixel_coords=px)
+    assert O.rel_l2(O.unpatchify(lat[:, extra:], 5, 4, 6), g["latents"]) < 5e-5
