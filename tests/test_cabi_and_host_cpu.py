@@ -303,3 +303,28 @@ def test_model_objects_accept_the_reference_loaders_module_calls():
             m.to(torch.float16)
         with pytest.raises(NotImplementedError):
             m.requires_grad_(True)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the arm the driver runs first): one JSON line with the contract's keys, the b200 arm's config, zero copy
+    bytes; under a multi-rank launch only rank 0 works and prints."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"], cwd=root, env=env,
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    r = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "1", "--warmup", "0"], cwd=root, env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "denoise_steps_per_s" and d["unit"] == "steps/s" and d["value"] > 0
+    assert d["higher_is_better"] is True and d["steps"] == 1 and d["n_gpus"] == 1 and d["vs_baseline"] is None
+    assert d["config"]["workload"] == "ltx2b_768x512x121_cfg_stg" and d["config"]["tokens"] == 6144 and d["config"]["num_conds"] == 3
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
