@@ -208,8 +208,9 @@ class LTXVideoPipeline:
         if st.cmask_dev is not None and st.image_cond_noise_scale > 0.0:
             # :606-629 add timestep-dependent noise to hard-conditioned tokens (host-side glue, i2v only)
             gen = st.generator
-            noise = torch.randn(st.tokens_shape, generator=gen,
-                                device=gen.device if isinstance(gen, torch.Generator) else device, dtype=BF16).to(device)
+            # drawn in the dtype the reference's latents have (= prompt_embeds' dtype, :1061), so the same generator gives the same noise
+            noise = torch.randn(st.tokens_shape, generator=gen, device=gen.device if isinstance(gen, torch.Generator) else device,
+                                dtype=st.init_tokens.dtype).to(device)
             need = (st.cmask_dev.view(1, N) > 1.0 - 1e-6).unsqueeze(-1)
             noised = st.init_tokens.float() + st.image_cond_noise_scale * noise.float() * (t ** 2)
             st.lat32 = torch.where(need, noised, st.lat32.view(1, N, C)).contiguous().view(-1)

@@ -359,8 +359,29 @@ def case_pipeline_i2v():
     mine = O.denoise_loop(sd, cfg, O.patchify(init), pe, pm, num_frames_lat=3, lat_h=4, lat_w=6, frame_rate=fps, num_steps=steps,
                           conditioning_mask=cmask.reshape(1, -1))
     _check("pipeline i2v from pixels (reference __call__ vs oracle composition)", O.unpatchify(mine, 3, 4, 6), lat, tol=5e-5)
+    # the same call with image_cond_noise_scale = 0.15 (the app's value, ltxv.py; :606-629): the hard-conditioned first-frame tokens are
+    # re-noised from the call's generator at the start of every step
+    os.chdir("/tmp")
+    try:
+        torch.manual_seed(123)
+        with _cuda_to_cpu():
+            lat_n = pipe(height=H, width=W, num_frames=F_, frame_rate=fps, prompt_embeds=pe, prompt_attention_mask=pm,
+                         negative_prompt_embeds=None, negative_prompt_attention_mask=None, num_inference_steps=steps,
+                         generator=torch.Generator().manual_seed(5), output_type="latent", return_dict=False, joint_pass=True,
+                         ltxv_model=_NoInterrupt(), is_video=True, vae_per_channel_normalize=True, guidance_scale=1.0, stg_scale=0.0,
+                         rescaling_scale=1.0, image_cond_noise_scale=0.15,
+                         conditioning_items=[ConditioningItem(media_item=image, media_frame_number=0, conditioning_strength=1.0)])[0]
+    finally:
+        os.chdir(cwd)
+    gen = torch.Generator().manual_seed(5)                          # one stream: initial noise, then one draw per step
+    init = O.unpatchify(torch.randn(1, 72, 128, generator=gen), 3, 4, 6).clone()
+    init[:, :, :1] = cond_lat
+    mine_n = O.denoise_loop(sd, cfg, O.patchify(init), pe, pm, num_frames_lat=3, lat_h=4, lat_w=6, frame_rate=fps, num_steps=steps,
+                            conditioning_mask=cmask.reshape(1, -1), image_cond_noise_scale=0.15, generator=gen)
+    _check("pipeline i2v, image_cond_noise_scale 0.15", O.unpatchify(mine_n, 3, 4, 6), lat_n, tol=5e-5)
+    print(f"  (image_cond_noise 0.15 vs 0: final latents differ by {O.rel_l2(lat_n, lat):.3e}; first frame {O.rel_l2(lat_n[:, :, :1], lat[:, :, :1]):.3e})")
     torch.save(dict(meta=dict(H=H, W=W, F=F_, fps=fps, steps=steps, num_layers=L), pe=pe, pm=pm, image=image, noise_e=noise_e,
-                    noise_seed=5, latents=lat.clone()), os.path.join(GOLD, "ltx_pipeline_i2v.pt"))
+                    noise_seed=5, latents=lat.clone(), latents_cond_noise_0p15=lat_n.clone()), os.path.join(GOLD, "ltx_pipeline_i2v.pt"))
 
 
 def build_ref_upsampler(sd, in_channels, mid_channels, nb):

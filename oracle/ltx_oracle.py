@@ -462,9 +462,11 @@ def denoise_loop(sd, cfg, latents: Tensor, enc: Tensor, enc_mask: Tensor, *, num
                  skip_block_list: Optional[list] = None, strategy: Optional[str] = None,
                  conditioning_mask: Optional[Tensor] = None, model_dtype=torch.float32,
                  per_step: Optional[list] = None, timesteps: Optional[Tensor] = None,
-                 guidance_timesteps: Optional[List[float]] = None, pixel_coords: Optional[Tensor] = None) -> Tensor:
+                 guidance_timesteps: Optional[List[float]] = None, pixel_coords: Optional[Tensor] = None,
+                 image_cond_noise_scale: float = 0.0, generator: Optional[torch.Generator] = None) -> Tensor:
     """LTXVideoPipeline.__call__ denoise loop (pipeline_ltx_video.py:919-1268) on patchified
-    latents [b, N, C]; returns final patchified latents.  image_cond_noise_scale = 0.
+    latents [b, N, C]; returns final patchified latents.  image_cond_noise_scale > 0 re-noises the hard-conditioned tokens at the
+    start of every step from `generator` (add_noise_to_image_conditioning_latents, :606-629, called at :1105-1113).
     pixel_coords [b, 3, N]: the coordinates prepare_conditioning returned (:1076-1093) when extra keyframe tokens were prepended;
     default = the plain latent grid.
     guidance_scale / stg_scale / rescaling_scale / skip_block_list may be per-guidance-timestep lists (:959-1017)."""
@@ -509,7 +511,12 @@ def denoise_loop(sd, cfg, latents: Tensor, enc: Tensor, enc_mask: Tensor, *, num
     frac[:, 0] = frac[:, 0] * (1.0 / frame_rate)                                     # :1086-1087
     cos_sin = precompute_freqs_cis(frac, D, cfg["rope_theta"], cfg["rope_max_pos"], model_dtype)
     cmask = None if conditioning_mask is None else torch.cat([conditioning_mask] * num_conds)
+    init_latents = latents.clone()                                                    # :1078
     for i, t in enumerate(timesteps):
+        if conditioning_mask is not None and image_cond_noise_scale > 0.0:           # :606-629
+            noise = torch.randn(latents.shape, generator=generator, dtype=latents.dtype, device=latents.device)
+            hard = (conditioning_mask > 1.0 - 1e-6).unsqueeze(-1)
+            latents = torch.where(hard, init_latents + image_cond_noise_scale * noise * (t ** 2), latents)
         x_in = torch.cat([latents] * num_conds) if num_conds > 1 else latents
         cur_t = t[None].expand(x_in.shape[0]).unsqueeze(-1)                          # [B,1]
         if cmask is not None:

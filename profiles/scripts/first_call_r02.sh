@@ -1,5 +1,5 @@
 #!/bin/bash
-# First gpurun call of round 2 (one B200, ~6 GPU-minutes): (1) the GPU test written after round 1's GPU minutes were spent,
+# First gpurun call of round 2 (one B200, ~6 GPU-minutes): (1) the GPU tests written after round 1's GPU minutes were spent,
 # (2) the whole GPU suite, (3) the reference arm and the default bench line back to back, as the driver runs them.
 #   gpurun --timeout 900 -- 'bash profiles/scripts/first_call_r02.sh'
 set -x

@@ -335,3 +335,22 @@ def test_keyframe_call_matches_reference_call(golden_dir):
         lat = O.denoise_loop(sd, O.LTX_2B, tok.float(), g["pe"], g["pm"], num_frames_lat=5, lat_h=4, lat_w=6, frame_rate=m["fps"],
                              num_steps=m["steps"], conditioning_mask=cm, pixel_coords=px)
     assert O.rel_l2(O.unpatchify(lat[:, extra:], 5, 4, 6), g["latents"]) < 5e-5
+
+
+def test_pipeline_i2v_image_cond_noise_matches_reference_call(golden_dir):
+    """image_cond_noise_scale = 0.15 (pipeline_ltx_video.py:606-629, 1105-1113): the hard-conditioned tokens are re-noised from the call's
+    generator at the start of every step.  Oracle loop vs the reference's own __call__ (gen_golden.py:case_pipeline_i2v)."""
+    g = _load(golden_dir, "ltx_pipeline_i2v.pt")
+    m = g["meta"]
+    sd = O.make_transformer_state_dict(O.LTX_2B, seed=0, num_layers=m["num_layers"])
+    with torch.no_grad():
+        cond_lat = O.vae_encode(O.make_vae_encoder_state_dict(seed=2), g["image"], noise=g["noise_e"])
+        gen = torch.Generator().manual_seed(g["noise_seed"])
+        init = O.unpatchify(torch.randn(1, 72, 128, generator=gen), 3, 4, 6).clone()
+        init[:, :, :1] = cond_lat
+        cmask = torch.zeros(1, 3, 4, 6)
+        cmask[:, :1] = 1.0
+        lat = O.denoise_loop(sd, O.LTX_2B, O.patchify(init), g["pe"], g["pm"], num_frames_lat=3, lat_h=4, lat_w=6, frame_rate=m["fps"],
+                             num_steps=m["steps"], conditioning_mask=cmask.reshape(1, -1), image_cond_noise_scale=0.15, generator=gen)
+    assert O.rel_l2(O.unpatchify(lat, 3, 4, 6), g["latents_cond_noise_0p15"]) < 5e-5
+    assert O.rel_l2(g["latents_cond_noise_0p15"], g["latents"]) > 1e-4          # 7.5e-4: the noise is scaled by t^2 and only the last draw survives

@@ -44,3 +44,43 @@ def test_wan_1_3b_full_depth_vs_reference_fixture(golden_dir):
         e = W.rel_l2(a.cpu(), b)
         print(f"wan-1.3B (30 layers) loop step {i}: latents rel_l2 vs reference = {e:.3e}")
         assert e < 2e-2
+
+
+def test_pipeline_i2v_image_cond_noise_vs_reference_fixture(golden_dir):
+    """image_cond_noise_scale = 0.15 through the CUDA pipeline (pixel-space first-frame conditioning, fp32 prompt embeddings so that the
+    per-step noise is drawn in fp32 from the same CPU generator as in the reference) vs the latents of the reference's own __call__."""
+    from ltx_video_gpupoor_b200.ltx.causal_video_autoencoder import CausalVideoAutoencoder
+    from ltx_video_gpupoor_b200.ltx.pipeline_ltx_video import ConditioningItem, LTXVideoPipeline
+    from ltx_video_gpupoor_b200.ltx.rf import RectifiedFlowScheduler
+    from ltx_video_gpupoor_b200.ltx.symmetric_patchifier import SymmetricPatchifier
+    from ltx_video_gpupoor_b200.ltx.transformer3d import Transformer3DModel
+    from oracle import ltx_oracle as O
+    g = torch.load(os.path.join(golden_dir, "ltx_pipeline_i2v.pt"), weights_only=False)
+    m = g["meta"]
+    tr = Transformer3DModel(num_layers=m["num_layers"])
+    tr.load_state_dict(O.make_transformer_state_dict(O.LTX_2B, seed=0, num_layers=m["num_layers"]))
+    vae = CausalVideoAutoencoder()
+    vsd = dict(O.make_vae_decoder_state_dict(seed=1))
+    vsd.update(O.make_vae_encoder_state_dict(seed=2))
+    vae.load_state_dict(vsd)
+    pipe = LTXVideoPipeline(vae=vae, transformer=tr, scheduler=RectifiedFlowScheduler(), patchifier=SymmetricPatchifier(1))
+    outs = {}
+    for scale, key in ((0.0, "latents"), (0.15, "latents_cond_noise_0p15")):
+        lat = pipe(height=m["H"], width=m["W"], num_frames=m["F"], frame_rate=m["fps"], prompt_embeds=g["pe"], prompt_attention_mask=g["pm"],
+                   num_inference_steps=m["steps"], guidance_scale=1.0, stg_scale=0.0, rescaling_scale=1.0,
+                   generator=torch.Generator().manual_seed(g["noise_seed"]), output_type="latent", return_dict=False, is_video=True,
+                   vae_per_channel_normalize=True, image_cond_noise_scale=scale,
+                   conditioning_items=[ConditioningItem(media_item=g["image"], media_frame_number=0, conditioning_strength=1.0,
+                                                        encode_noise=g["noise_e"])])[0]
+        torch.cuda.synchronize()
+        outs[key] = lat.float().cpu()
+        e = O.rel_l2(outs[key], g[key])
+        print(f"i2v from pixels, image_cond_noise_scale {scale}: latents rel_l2 vs the reference's own __call__ = {e:.3e}")
+        assert e < 2e-2
+    # the hard-conditioned first latent frame is never touched by the model update: what the noise leaves there is
+    # 0.15 * (last draw) * t_last^2 exactly, so the DIFFERENCE of the two runs must be the reference's difference (same generator stream)
+    d_ours = (outs["latents_cond_noise_0p15"] - outs["latents"])[:, :, :1]
+    d_ref = (g["latents_cond_noise_0p15"] - g["latents"])[:, :, :1]
+    e = O.rel_l2(d_ours, d_ref)
+    print(f"first-frame noise term vs the reference's: rel_l2 = {e:.3e}")
+    assert e < 2e-2
