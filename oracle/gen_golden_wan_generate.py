@@ -30,6 +30,8 @@ CASES = {
     "unipc_cfg_zero_star": dict(sample_solver="unipc", sampling_steps=4, guide_scale=5.0, cfg_star_switch=True, cfg_zero_step=1, joint_pass=False),
     "unipc_joint_plain_cfg": dict(sample_solver="unipc", sampling_steps=4, guide_scale=5.0, cfg_star_switch=False, cfg_zero_step=5, joint_pass=True),
     "dpmpp_cfg_zero_star": dict(sample_solver="dpm++", sampling_steps=5, guide_scale=3.0, cfg_star_switch=True, cfg_zero_step=0, joint_pass=True),
+    "unipc_joint_slg": dict(sample_solver="unipc", sampling_steps=4, guide_scale=5.0, cfg_star_switch=True, cfg_zero_step=0, joint_pass=True,
+                            slg_layers=[1], slg_start=0.25, slg_end=0.75),
     "unipc_no_guidance": dict(sample_solver="unipc", sampling_steps=3, guide_scale=1, cfg_star_switch=True, cfg_zero_step=5, joint_pass=False),
 }
 
@@ -84,7 +86,8 @@ def main():
                                     model_filename="wan2.1_text2video_1.3B_bf16.safetensors", **kw)
         noise = torch.randn(16, 3, 8, 12, dtype=torch.float32, generator=torch.Generator().manual_seed(seed))      # :410
         mine = W.t2v_denoise(sd, cfg, noise.double(), ctx, ctx0, steps=kw["sampling_steps"], shift=5.0, guide_scale=kw["guide_scale"],
-                             cfg_star_switch=kw["cfg_star_switch"], cfg_zero_step=kw["cfg_zero_step"], sample_solver=kw["sample_solver"])
+                             cfg_star_switch=kw["cfg_star_switch"], cfg_zero_step=kw["cfg_zero_step"], sample_solver=kw["sample_solver"],
+                             slg_layers=kw.get("slg_layers"), slg_start=kw.get("slg_start", 0.0), slg_end=kw.get("slg_end", 1.0))
         e = rel_l2(mine, lat_ref)
         print(f"  WanT2V.generate[{name}]: rel_l2(oracle loop, reference method) = {e:.3e}")
         assert e < 5e-5, name

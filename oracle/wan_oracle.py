@@ -374,9 +374,11 @@ class DPMpp:
 def t2v_denoise(sd, cfg, noise: Tensor, context: Tensor, context_null: Tensor, steps: int, shift: float = 5.0,
                 guide_scale: float = 5.0, per_step: Optional[list] = None, attn_fn=None,
                 cfg_star_switch: bool = False, cfg_zero_step: int = 5, clip_fea: Optional[Tensor] = None,
-                y: Optional[Tensor] = None, sample_solver: str = "unipc") -> Tensor:
+                y: Optional[Tensor] = None, sample_solver: str = "unipc", slg_layers: Optional[Sequence[int]] = None,
+                slg_start: float = 0.0, slg_end: float = 1.0) -> Tensor:
     """WanT2V.generate denoise loop, UniPC, plain CFG (text2video.py:399-575).  noise [16, F, H, W] fp32.
-    With clip_fea / y it is the WanI2V.generate loop (image2video.py:328-414): same y and CLIP tokens for both passes."""
+    With clip_fea / y it is the WanI2V.generate loop (image2video.py:328-414): same y and CLIP tokens for both passes.
+    slg_layers: skip-layer guidance in the joint pass on the steps int(slg_start*steps) <= i < int(slg_end*steps) (text2video.py:492)."""
     sch = UniPC() if sample_solver == "unipc" else DPMpp()
     sch.set_timesteps(steps, shift)
     cos, sin = rope_tables(noise.shape[1:])
@@ -386,7 +388,8 @@ def t2v_denoise(sd, cfg, noise: Tensor, context: Tensor, context_null: Tensor, s
         if guide_scale == 1:
             pred = wan_forward(sd, cfg, [lat], ts, [context], cos, sin, attn_fn, clip_fea=clip_fea, y=y)[0]
         else:
-            c, u = wan_forward(sd, cfg, [lat, lat], ts, [context, context_null], cos, sin, attn_fn, clip_fea=clip_fea, y=y)
+            slg = slg_layers if int(slg_start * steps) <= i < int(slg_end * steps) else None
+            c, u = wan_forward(sd, cfg, [lat, lat], ts, [context, context_null], cos, sin, attn_fn, clip_fea=clip_fea, y=y, slg_layers=slg)
             if cfg_star_switch and i > cfg_zero_step:                                     # :551-561 (optimized_scale :31-42)
                 alpha = torch.sum(c.flatten() * u.flatten()) / (torch.sum(u.flatten() ** 2) + 1e-8)
                 u = u * alpha

@@ -146,18 +146,19 @@ def test_wan_1_3b_full_depth_oracle_matches_reference_fixture(golden_dir):
 def test_oracle_loop_matches_reference_generate_method(golden_dir):
     """The oracle's denoise loop vs the latents the reference's OWN WanT2V.generate method returned (oracle/gen_golden_wan_generate.py: the
     unmodified method called on a stand-in self): noise from `seed`, UniPC / dpm++, CFG-Zero* around cfg_zero_step, joint and two-call
-    passes, guide_scale == 1."""
+    passes, skip-layer guidance on a window of steps, guide_scale == 1."""
     g = torch.load(os.path.join(golden_dir, "wan_generate.pt"), weights_only=False)
     cfg = g["cfg"]
     sd = {k: v.double() for k, v in W.make_wan_state_dict(cfg, seed=0).items()}
-    assert len(g["cases"]) == 4
+    assert len(g["cases"]) == 5
     for name, c in g["cases"].items():
         kw = c["kw"]
         noise = torch.randn(16, 3, 8, 12, dtype=torch.float32, generator=torch.Generator().manual_seed(c["seed"]))
         with torch.no_grad():
             lat = W.t2v_denoise(sd, cfg, noise.double(), g["ctx"].double(), g["ctx0"].double(), steps=kw["sampling_steps"], shift=5.0,
                                 guide_scale=kw["guide_scale"], cfg_star_switch=kw["cfg_star_switch"], cfg_zero_step=kw["cfg_zero_step"],
-                                sample_solver=kw["sample_solver"])
+                                sample_solver=kw["sample_solver"], slg_layers=kw.get("slg_layers"), slg_start=kw.get("slg_start", 0.0),
+                                slg_end=kw.get("slg_end", 1.0))
         assert W.rel_l2(lat, g["cases"][name]["latents"]) < 5e-5, name
 
 
