@@ -1,7 +1,8 @@
 """GPU tests written AFTER round 1's GPU minutes were spent: they have never run on a B200, so they are opt-in
 (LTXB200_UNVERIFIED_TESTS=1) and must not decide a round-end result before they have been seen green once.  First thing to run
-in the next round; move them into test_wan_gpu.py once they pass.  (The two LTX tests written with them ran green
-with the round's last GPU seconds — profiles/r01d_late_gpu_tests.log — and live in test_ltx_model_gpu.py.)
+in the next round (DESIGN.md §8 item 6, §2 image_cond_noise_scale); move them into test_wan_gpu.py / test_ltx_model_gpu.py once they pass.
+(Two other LTX tests written at the same time ran green with the round's last GPU seconds — profiles/r01d_late_gpu_tests.log — and already
+live in test_ltx_model_gpu.py.)
     LTXB200_UNVERIFIED_TESTS=1 python -m pytest tests/test_zz_unverified_gpu.py -m gpu -x -q -s"""
 import os
 
