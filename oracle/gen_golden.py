@@ -125,11 +125,21 @@ def case_scheduler():
         a = s.step(v, tt, x, return_dict=False)[0]
         b = O.rf_step(v, tt, x, s.timesteps)
         assert torch.equal(a, b)
+        # stochastic sampler (:369-373): the reference draws its noise from the global RNG
+        stoch = []
+        for tq in (s.timesteps[0][None, None], s.timesteps[steps // 2][None, None], s.timesteps[-1][None, None], tt):
+            torch.manual_seed(77)
+            a_s = s.step(v, tq, x, return_dict=False, stochastic_sampling=True)[0]
+            torch.manual_seed(77)
+            nz = torch.randn_like(x)
+            b_s = O.rf_step_stochastic(v, tq, x, s.timesteps, nz)
+            assert O.rel_l2(b_s, a_s) < 1e-6, O.rel_l2(b_s, a_s)
+            stoch.append(dict(t=tq.clone(), noise=nz, out=a_s.clone()))
         a0 = s.step(v, s.timesteps[1], x, return_dict=False)[0]
         assert torch.equal(a0, O.rf_step(v, s.timesteps[1], x, s.timesteps))
         out[f"{steps}_{'x'.join(map(str, shape))}"] = dict(steps=steps, shape=shape, timesteps=s.timesteps.clone(),
-                                                           x=x, v=v, tt=tt, stepped=a)
-    print("  scheduler: timesteps + step bit-exact")
+                                                           x=x, v=v, tt=tt, stepped=a, stochastic=stoch)
+    print("  scheduler: timesteps + step bit-exact; stochastic step <= 1e-6")
     torch.save(out, os.path.join(GOLD, "rf_scheduler.pt"))
 
 

@@ -424,6 +424,16 @@ def rf_step(model_output: Tensor, timestep: Tensor, sample: Tensor, timesteps: T
     return sample - dt * model_output
 
 
+def rf_step_stochastic(model_output: Tensor, timestep: Tensor, sample: Tensor, timesteps: Tensor, noise: Tensor) -> Tensor:
+    """RectifiedFlowScheduler.step, stochastic_sampling branch (rf.py:369-373, add_noise :382-392): the x0 estimate x - t*v is re-noised
+    to the next lower timestep with `noise` (the reference draws torch.randn_like(sample) from the global RNG)."""
+    dt = sample - rf_step(torch.ones_like(model_output), timestep, sample, timesteps)      # = dt, broadcast like the deterministic branch
+    t = timestep[..., None] if timestep.ndim == 2 else timestep
+    x0 = sample - t * model_output
+    nxt = t - dt
+    return (1 - nxt) * x0 + nxt * noise
+
+
 # --------------------------------------------------------------------------------------
 # Guidance arithmetic + denoise loop (pipeline_ltx_video.py:1103-1256,1309-1342)
 # --------------------------------------------------------------------------------------

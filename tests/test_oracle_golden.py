@@ -28,6 +28,8 @@ def test_rf_scheduler_bit_exact(golden_dir):
         ts = O.rf_timesteps(case["steps"], case["shape"])
         assert torch.equal(ts, case["timesteps"])
         assert torch.equal(O.rf_step(case["v"], case["tt"], case["x"], ts), case["stepped"])
+        for st in case["stochastic"]:                       # stochastic sampler (rf.py:369-373) with the noise the reference drew
+            assert O.rel_l2(O.rf_step_stochastic(case["v"], st["t"], case["x"], ts, st["noise"]), st["out"]) < 1e-6
 
 
 def test_known_timesteps():
