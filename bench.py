@@ -9,6 +9,11 @@ transformer forwards (joint batch) + guidance + scheduler update.  `value` = den
 resident in HBM; `e2e` = the same metric through LTXVideoPipeline.__call__ with pinned HOST prompt embeddings
 and a device->host read of the result.  LTX is single-GPU whole-model (replicas only): with N>1
 every rank denoises its own video, no data-path collective, value = N*K / max-over-ranks time ("weak").
+
+The part of the path that SHARDS is Wan's Ulysses sequence parallelism (BASELINE.json configs[3]); every run of the default workload
+therefore also carries a `wan_sp` block: ONE Wan2.1-1.3B 832x480x81 video split over all N ranks (strong scaling; N = 1 is the
+single-GPU step, so the driver's 1/2/4/8 runs form a self-contained curve), preceded by an in-run parity check of the
+sequence-parallel forward against the fixture recorded from the unmodified reference (tests/golden/wan_t2v_h4.pt).
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -137,32 +142,69 @@ def ltx_config(workload, wl, layers, world):
     return {"workload": workload, "network": "LTX-Video 2B (random-init, 28 layers)" if layers == 28 else f"INVALID: {layers} layers",
             "height": wl["height"], "width": wl["width"], "num_frames": wl["num_frames"], "tokens": tokens,
             "schedule_steps": wl["schedule_steps"], "num_conds": wl["num_conds"], "prompt_tokens": wl["prompt_tokens"],
-            "parallelism": f"replicas x{world}",
+            "parallelism": f"replicas x{world}", "prompt_mask": "all ones (every prompt token valid): zero key bias",
             "l2_policy": "per-step working set (3.8 GB weights + activations) far exceeds the 126 MB L2; no flush needed"}
 
 
+def host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm uses every host core it can get."""
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0)) or n
+    except AttributeError:
+        pass
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
+def cpu_reference_sample(wl):
+    """One bounded sample of a full-size denoise step on the host cores.  Runs the UNMODIFIED reference (oracle/_ref, populated
+    from /root/reference by oracle/build_ref.py) when it is there — kind "reference" — and the pinned oracle port otherwise."""
+    cores = host_threads()
+    from oracle import ref_runner
+    if ref_runner.available():
+        s = ref_runner.full_size_sample(wl)
+        kind, what = "reference", "the unmodified reference Transformer3DModel.forward (oracle/_ref, fp32)"
+    else:
+        s = cpu_sample(wl)
+        kind, what = "port", "oracle port of Transformer3DModel.forward (torch fp32)"
+    sample = (f"{what} on {cores} host threads at full size N={s['tokens']}, L={wl['prompt_tokens']}: 1- and 3-layer forwards timed "
+              f"({s['raw'][1]:.1f} s, {s['raw'][3]:.1f} s), EXTRAPOLATED to 28 layers x {wl['num_conds']} conds per denoise step")
+    return s, {"value": 1.0 / s["step_s"], "unit": "steps/s", "cores": cores, "kind": kind, "sample": sample, "extrapolated": True,
+               "sample_wall_s": s.get("sample_s", sum(s["raw"].values()))}
+
+
 def run_reference(args, wl_name, wl):
+    """The reference's own CPU implementation of the path on the box's host cores.  ONE bounded sample per run whatever K is
+    (a full 768x512x121 step takes minutes on a CPU: the full-size figure is extrapolated from 1- and 3-layer forwards and marked
+    so), plus BASELINE configs[0] — 256x256x9, 4 steps + VAE decode — run FOR REAL through the reference's LTXVideoPipeline."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = torch.get_num_threads()
-    vals = []
-    for i in range(args.warmup + args.steps):
-        s = cpu_sample(wl)
-        if i >= args.warmup:
-            vals.append(s["step_s"])
-    step_s = sum(vals) / len(vals)
-    v = 1.0 / step_s
-    sample = (f"oracle port (torch fp32, {cores} threads) of Transformer3DModel.forward at full size N={s['tokens']}, "
-              f"L={wl['prompt_tokens']}: 1- and 3-layer forwards timed, extrapolated to 28 layers x {wl['num_conds']} conds per step")
+    t_start = time.perf_counter()
+    s, base = cpu_reference_sample(wl)
+    v, step_s = base["value"], s["step_s"]
+    config0 = None
+    if not os.environ.get("LTXB200_BENCH_SKIP_CONFIG0"):
+        try:
+            from oracle import ref_runner
+            if ref_runner.available():
+                c0 = ref_runner.config0()
+                config0 = {"workload": "BASELINE configs[0]: LTX-2B (28 layers) t2v 256x256x9, 4 steps + VAE decode, fp32, host CPU",
+                           "measured": True, "extrapolated": False, "steps_per_s": c0["steps_per_s"], "denoise_loop_s": c0["loop_s"],
+                           "s_per_video": c0["video_s"], "cores": base["cores"],
+                           "api": "unmodified reference LTXVideoPipeline.__call__ (oracle/_ref)"}
+        except Exception as exc:                      # never lose the line over the extra
+            config0 = {"error": repr(exc)[:300]}
     line = {"impl": "reference", "metric": "denoise_steps_per_s", "value": v, "unit": "steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": ltx_config(wl_name, wl, 28, args.gpus),
-            "cpu_baseline": {"value": v, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "extrapolated": True,
+            "timed": {"samples": 1, "sample_wall_s": base["sample_wall_s"], "run_wall_s": None,
+                      "note": "steps/warmup echo the request; ONE bounded sample is timed per run (see cpu_baseline.sample)"},
+            "config": ltx_config(wl_name, wl, 28, args.gpus), "cpu_baseline": base, "config0_real": config0,
             "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    line["timed"]["run_wall_s"] = time.perf_counter() - t_start
     print(json.dumps(line))
-
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -204,54 +246,64 @@ def wan_cpu_sample(wl):
     return dict(step_s=step_s, tokens=N_full, fit=dict(a=a, b=b), sample_tokens=[n1, n2], per_layer_s=[t1, t2])
 
 
-def run_wan(args, wl):
-    if args.impl == "reference":
-        if int(os.environ.get("RANK", "0")) != 0:
-            return
-        cores = torch.get_num_threads()
-        vals = []
-        for i in range(args.warmup + args.steps):
-            smp = wan_cpu_sample(wl)
-            if i >= args.warmup:
-                vals.append(smp["step_s"])
-        step_s = sum(vals) / len(vals)
-        v = 1.0 / step_s
-        sample = (f"oracle port (torch fp32, {cores} threads) of WanModel.forward, full width, 1- and 2-layer forwards at "
-                  f"{smp['sample_tokens']} tokens; per-layer cost fitted a*N + b*N^2 and extrapolated to N={smp['tokens']}, all layers, 2 forwards/step")
-        print(json.dumps({"impl": "reference", "metric": "denoise_steps_per_s", "value": v, "unit": "steps/s", "n_gpus": args.gpus,
-                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
-                          "scaling": "strong", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-                          "config": {"workload": args.workload, "network": f"Wan2.1-T2V-{wl['model']}", "tokens": smp["tokens"]},
-                          "cpu_baseline": {"value": v, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
-                          "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
-        return
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    dist = None
-    group = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
-        group = dist.group.WORLD
-    cfgp = None
+def rel_l2(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def wan_groups(wl, world):
+    """Ulysses over all ranks when the heads divide, otherwise (Wan-1.3B on 8 GPUs: 12 heads) cond / uncond on the two halves
+    of the world with Ulysses inside each half (wan/distributed/cfg_parallel.py).  -> (cfgp | None, sp_group | None, sp_size)"""
+    if world == 1:
+        return None, None, 1
+    import torch.distributed as dist
     use_cfgp = {"1": True, "0": False}.get(os.environ.get("LTXB200_CFG_PARALLEL", ""), "auto")
     heads = 12 if wl["model"] == "1.3B" else 40
-    if world > 1 and (use_cfgp is True or (use_cfgp == "auto" and heads % world != 0)):
-        # cond / uncond on two halves of the world, Ulysses inside each half (wan/distributed/cfg_parallel.py):
-        # Wan-1.3B has 12 heads, which 8 ranks cannot split but 2 x 4 can
+    if use_cfgp is True or (use_cfgp == "auto" and heads % world != 0):
         from ltx_video_gpupoor_b200.wan.distributed.cfg_parallel import CfgParallel
         cfgp = CfgParallel()
-        group = cfgp.sp_group if world > 2 else None
-    from ltx_video_gpupoor_b200 import _lib, ops
-    from ltx_video_gpupoor_b200.wan.fm_solvers_unipc import FlowUniPCMultistepScheduler
-    from ltx_video_gpupoor_b200.wan.model import WAN_T2V_1_3B, WAN_T2V_14B, WanModel
-    from ltx_video_gpupoor_b200.wan.posemb_layers import get_rotary_pos_embed
+        return cfgp, (cfgp.sp_group if world > 2 else None), world // 2
+    return None, dist.group.WORLD, world
 
+
+def wan_sp_parity(dev, world, cfgp, group, sp_size):
+    """The 2-layer / 4-head forward of the fixture recorded from the UNMODIFIED reference (tests/golden/wan_t2v_h4.pt, fp64 reference,
+    oracle/gen_golden_wan.py) on this run's sequence-parallel group — q/k-norm + RoPE + head scatter in token chunks on the side
+    stream, attention with the return scatter, the peer-store head gather — against the single-GPU reference output.  Max over ranks."""
+    from ltx_video_gpupoor_b200.wan.init_weights import seeded_wan_state_dict
+    from ltx_video_gpupoor_b200.wan.model import WanModel
+    from ltx_video_gpupoor_b200.wan.posemb_layers import get_rotary_pos_embed
+    g = torch.load(os.path.join(ROOT, "tests", "golden", "wan_t2v_h4.pt"), weights_only=False)
+    cfg = g["cfg"]
+    if cfg["num_heads"] % sp_size:
+        return {"skipped": f"fixture has {cfg['num_heads']} heads, group size {sp_size}"}
+    m = WanModel(dim=cfg["dim"], ffn_dim=cfg["ffn_dim"], num_heads=cfg["num_heads"], num_layers=cfg["num_layers"], sp_group=group)
+    m.load_state_dict(seeded_wan_state_dict(cfg, seed=g["seed_weights"]), device=dev)
+    cos, sin = get_rotary_pos_embed(g["lat"].shape[1:])
+    lat, ctx, ctx0 = g["lat"].to(dev), g["ctx"].to(dev), g["ctx0"].to(dev)
+    if group is not None:
+        ex = m._peer_exchange(2, (lat.shape[1] * lat.shape[2] * lat.shape[3] // 4) // sp_size)
+        ex.min_chunk_rows = 8                      # the fixture has 96 tokens: chunk anyway, so the overlapped path is what is checked
+    for _ in range(3):                             # several forwards: buffers, parities and epoch flags are reused across calls
+        y = m([lat, lat], t=g["t"].to(dev), context=[ctx, ctx0], freqs=(cos, sin))
+    torch.cuda.synchronize()
+    err = max(rel_l2(a.cpu(), b) for a, b in zip(y, g["fwd"]))
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([err], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        err = float(t)
+    m.close()
+    return {"sp_parity_rel_l2": err, "tolerance": 2e-2, "ok": bool(err < 2e-2), "group_size": sp_size,
+            "exchange": m.sp_exchange if group is not None else None,
+            "fixture": "tests/golden/wan_t2v_h4.pt (unmodified reference WanModel.forward, fp64; 2 layers, 4 heads, 96 tokens, 2 sequences)"}
+
+
+def wan_build(wl, dev, cfgp, group, layers=None):
+    from ltx_video_gpupoor_b200.wan.model import WAN_T2V_1_3B, WAN_T2V_14B, WanModel
     cfg = dict(WAN_T2V_1_3B if wl["model"] == "1.3B" else WAN_T2V_14B)
-    cfg["num_layers"] = args.layers if args.layers != 28 else cfg["num_layers"]
+    if layers:
+        cfg["num_layers"] = layers
     gen = torch.Generator(device=dev).manual_seed(0)          # same seed on every rank: replicated weights
     D, Fd = cfg["dim"], cfg["ffn_dim"]
 
@@ -278,7 +330,18 @@ def run_wan(args, wl):
     model = WanModel(**{k: v for k, v in cfg.items() if k not in ("qk_norm", "cross_attn_norm")}, sp_group=group)
     model.load_state_dict(sd, device=dev)
     del sd
+    return model, cfg
 
+
+def wan_measure(wl, dev, world, local_rank, model, cfgp, steps, warmup, e2e=True):
+    """Timed steps of ONE video split over all ranks (strong scaling), device-resident, CUDA events, max over ranks; then one
+    instrumented step for the per-kernel table and (optionally) the end-to-end loop with host buffers."""
+    from ltx_video_gpupoor_b200 import _lib, ops
+    from ltx_video_gpupoor_b200.wan.fm_solvers_unipc import FlowUniPCMultistepScheduler
+    from ltx_video_gpupoor_b200.wan.posemb_layers import get_rotary_pos_embed
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
     shape = (16, (wl["frame_num"] - 1) // 4 + 1, wl["height"] // 8, wl["width"] // 8)
     g = torch.Generator().manual_seed(42)
     ctx_h = torch.randn(wl["prompt_tokens"], 4096, generator=g).to(torch.bfloat16).pin_memory()
@@ -309,7 +372,7 @@ def run_wan(args, wl):
     sch = FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False)
     sch.set_timesteps(S, device=dev, shift=wl["shift"])
     ctx, ctx0, lat = ctx_h.to(dev), ctx0_h.to(dev), noise_h.to(dev)
-    lat = run_steps(lat, ctx, ctx0, sch, range(args.warmup))
+    lat = run_steps(lat, ctx, ctx0, sch, range(warmup))
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -318,7 +381,7 @@ def run_wan(args, wl):
     if os.environ.get("LTXB200_NCU_RANGE"):
         torch.cuda.profiler.start()
     e0.record()
-    lat = run_steps(lat, ctx, ctx0, sch, range(args.warmup, args.warmup + args.steps))
+    lat = run_steps(lat, ctx, ctx0, sch, range(warmup, warmup + steps))
     e1.record()
     if os.environ.get("LTXB200_NCU_RANGE"):
         torch.cuda.synchronize()
@@ -331,10 +394,9 @@ def run_wan(args, wl):
         tt = torch.tensor([elapsed], device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         elapsed = float(tt)
-    steps_per_s = args.steps / elapsed            # ONE video split over all ranks: strong scaling
 
-    ops.PROFILER = []
-    run_steps(lat, ctx, ctx0, sch, [args.warmup + args.steps])
+    ops.PROFILER = []                               # instrumented step: single stream (the chunk overlap is off), events per launch
+    run_steps(lat, ctx, ctx0, sch, [warmup + steps])
     torch.cuda.synchronize()
     prof, ops.PROFILER = ops.PROFILER, None
     agg = {}
@@ -353,21 +415,89 @@ def run_wan(args, wl):
     kernels = {k: {"ms_per_step": round(v["ms"], 3), "launches": v["n"], "share": round(v["ms"] / total_ms, 4),
                    ("tflops" if v["kind"] == "flop" else "gbs"): round(v["amount"] / (v["ms"] * 1e-3) / (1e12 if v["kind"] == "flop" else 1e9), 1)}
                for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
+    out = dict(elapsed=elapsed, ms_per_step=elapsed / steps * 1e3, steps_per_s=steps / elapsed, launches=int(launches), clocks=clocks,
+               roofline=roofline, kernels=kernels, serialised_kernel_ms=total_ms, shape=shape)
+    if e2e:
+        # host noise + host prompt embeddings in, latents back to the host, K steps of a K-step schedule
+        K = max(steps, 2)
+        barrier()
+        t0 = time.perf_counter()
+        sch2 = FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False)
+        sch2.set_timesteps(K, device=dev, shift=wl["shift"])
+        o = run_steps(noise_h.to(dev, non_blocking=True), ctx_h.to(dev, non_blocking=True), ctx0_h.to(dev, non_blocking=True), sch2, range(K))
+        out_h = o.cpu()
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        if dist is not None:
+            tt = torch.tensor([e2e_s], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e_s = float(tt)
+        out["e2e"] = {"value": K / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": (noise_h.numel() * 4 + 2 * ctx_h.numel() * 2) / K,
+                      "d2h_bytes_per_step": out_h.numel() * 4 / K, "steps_in_call": K}
+    return out
 
-    # e2e: host noise + host prompt embeddings in, latents back to the host, K steps of a K-step schedule
-    K = max(args.steps, 2)
-    barrier()
-    t0 = time.perf_counter()
-    sch2 = FlowUniPCMultistepScheduler(num_train_timesteps=1000, shift=1, use_dynamic_shifting=False)
-    sch2.set_timesteps(K, device=dev, shift=wl["shift"])
-    out = run_steps(noise_h.to(dev, non_blocking=True), ctx_h.to(dev, non_blocking=True), ctx0_h.to(dev, non_blocking=True), sch2, range(K))
-    out_h = out.cpu()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    if dist is not None:
-        tt = torch.tensor([e2e_s], device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_s = float(tt)
+
+def wan_parallelism(world, cfgp):
+    return f"cfg-parallel 2 x ulysses sp{world // 2}" if cfgp is not None else f"ulysses sp{world}"
+
+
+def wan_sp_block(dev, world, rank, local_rank, steps=10, warmup=3):
+    """The `wan_sp` block of the default (LTX) line: BASELINE configs[3] — Wan2.1 T2V-1.3B 832x480x81 — one video over all N ranks."""
+    wl = WAN_WORKLOADS["wan1.3b_832x480x81_sp"]
+    cfgp, group, sp_size = wan_groups(wl, world)
+    parity = wan_sp_parity(dev, world, cfgp, group, sp_size)
+    model, cfg = wan_build(wl, dev, cfgp, group)
+    r = wan_measure(wl, dev, world, local_rank, model, cfgp, steps, warmup, e2e=False)
+    model.close()
+    del model
+    torch.cuda.empty_cache()
+    k = r["kernels"]
+    pick = lambda n: k.get(n, {}).get("ms_per_step")
+    return {"workload": "wan1.3b_832x480x81_sp (BASELINE configs[3]): ONE video over all ranks, strong scaling",
+            "network": f"Wan2.1-T2V-1.3B (random-init, {cfg['num_layers']} layers)", "tokens": r["shape"][1] * r["shape"][2] * r["shape"][3] // 4,
+            "n_gpus": world, "parallelism": wan_parallelism(world, cfgp), "steps": steps, "warmup": warmup,
+            "ms_per_step": r["ms_per_step"], "steps_per_s": r["steps_per_s"], "s_per_50_step_video_denoise": 50 * r["ms_per_step"] / 1e3,
+            "scaling": "strong", "forwards_per_step": 2,
+            "exchange": (os.environ.get("LTXB200_SP_EXCHANGE", "p2p") + f" (peer-memory stores over NVLink fused into the producing kernels; "
+                         f"QKV projection + scatter in {os.environ.get('LTXB200_SP_CHUNKS', '4')} token chunks on two streams)") if sp_size > 1 else None,
+            "exchange_kernels_ms_per_step_serialised": {"qk_norm_rope_wan_scatter": pick("qk_norm_rope_wan_scatter_bf16"), "comm_wait": pick("comm_wait"),
+                                                        "peer_allgather": pick("peer_allgather")},
+            "serialised_kernel_ms": r["serialised_kernel_ms"], "gpu_launches": r["launches"], "clocks": r["clocks"],
+            "kernels": k, "parity": parity, "sp_parity_rel_l2": parity.get("sp_parity_rel_l2"),
+            "model_tflops_per_gpu": 2 * wl["fwd_flops"] / (r["ms_per_step"] / 1e3) / 1e12 / world}
+
+
+def run_wan(args, wl):
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        cores = host_threads()
+        smp = wan_cpu_sample(wl)
+        step_s = smp["step_s"]
+        v = 1.0 / step_s
+        sample = (f"oracle port (torch fp32, {cores} threads) of WanModel.forward, full width, 1- and 2-layer forwards at "
+                  f"{smp['sample_tokens']} tokens; per-layer cost fitted a*N + b*N^2 and EXTRAPOLATED to N={smp['tokens']}, all layers, 2 forwards/step")
+        print(json.dumps({"impl": "reference", "metric": "denoise_steps_per_s", "value": v, "unit": "steps/s", "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
+                          "scaling": "strong", "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "extrapolated": True,
+                          "config": {"workload": args.workload, "network": f"Wan2.1-T2V-{wl['model']}", "tokens": smp["tokens"]},
+                          "cpu_baseline": {"value": v, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample, "extrapolated": True},
+                          "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    cfgp, group, sp_size = wan_groups(wl, world)
+    parity = wan_sp_parity(dev, world, cfgp, group, sp_size) if wl["model"] == "1.3B" or sp_size in (1, 2, 4) else None
+    model, cfg = wan_build(wl, dev, cfgp, group, layers=args.layers if args.layers != 28 else None)
+    r = wan_measure(wl, dev, world, local_rank, model, cfgp, args.steps, args.warmup)
+    shape, S = r["shape"], wl["schedule_steps"]
     decode_s = None
     if rank == 0 and not args.no_decode and wl["model"] == "1.3B":
         # WanVAE.decode of the full latent video on one GPU (text2video.py:590): part of s/video
@@ -388,31 +518,79 @@ def run_wan(args, wl):
     if rank == 0:
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
+            cores = host_threads()
             smp = wan_cpu_sample(wl)
-            cores = torch.get_num_threads()
-            cpu_baseline = {"value": 1.0 / smp["step_s"], "unit": "steps/s", "cores": cores, "kind": "port",
+            cpu_baseline = {"value": 1.0 / smp["step_s"], "unit": "steps/s", "cores": cores, "kind": "port", "extrapolated": True,
                             "sample": (f"oracle port (torch fp32, {cores} threads) of WanModel.forward, full width, 1- and 2-layer forwards at "
                                        f"{smp['sample_tokens']} tokens; per-layer cost fitted a*N + b*N^2, extrapolated to N={smp['tokens']}, all layers, 2 forwards/step")}
-        ms_step = elapsed / args.steps * 1e3
-        line = {"metric": "denoise_steps_per_s", "value": steps_per_s, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+        ms_step = r["ms_per_step"]
+        line = {"metric": "denoise_steps_per_s", "value": r["steps_per_s"], "unit": "steps/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": args.workload, "network": f"Wan2.1-T2V-{wl['model']} (random-init, {cfg['num_layers']} layers)",
                            "latent": list(shape), "tokens": shape[1] * shape[2] * shape[3] // 4, "schedule_steps": S,
-                           "forwards_per_step": 2,
-                           "parallelism": (f"cfg-parallel 2 x ulysses sp{world // 2}" if cfgp is not None else f"ulysses sp{world}"),
+                           "forwards_per_step": 2, "parallelism": wan_parallelism(world, cfgp),
                            "sp_exchange": (os.environ.get("LTXB200_SP_EXCHANGE", "p2p") + (" (fused peer-memory stores over NVLink)" if os.environ.get("LTXB200_SP_EXCHANGE", "p2p") == "p2p" else " (all_to_all_single)")) if world > 1 else None,
+                           "sp_chunks": int(os.environ.get("LTXB200_SP_CHUNKS", "4")) if sp_size > 1 else None,
                            "l2_policy": "per-step working set (weights + activations) far exceeds the 126 MB L2"},
-                "e2e": {"value": K / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": (noise_h.numel() * 4 + 2 * ctx_h.numel() * 2) / K,
-                        "d2h_bytes_per_step": out_h.numel() * 4 / K, "steps_in_call": K},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "e2e": r["e2e"], "gpu_launches": r["launches"], "clocks": r["clocks"], "roofline": r["roofline"], "cpu_baseline": cpu_baseline,
                 "s_per_video_denoise": S * ms_step / 1e3, "vae_decode_s": decode_s,
                 "s_per_video": (S * ms_step / 1e3 + decode_s) if decode_s is not None else None,
                 "model_tflops_per_gpu": 2 * wl["fwd_flops"] * (cfg["num_layers"] / (30 if wl["model"] == "1.3B" else 40)) / (ms_step / 1e3) / 1e12 / world,
-                "kernels": kernels}
+                "parity": parity, "kernels": r["kernels"]}
         print(json.dumps(line))
+    model.close()
     if dist is not None:
         dist.destroy_process_group()
+
+def gpu_library_baseline(wl, cfg, tr, dev, ours_ms):
+    """Per-step time of the library path on this GPU: the pinned oracle restatement of the reference's PyTorch modules in bf16 with
+    torch.nn.functional.scaled_dot_product_attention (what LTX-Video-GPUPoor executes with `_attention = "sdpa"`), same random
+    weights, same shapes as the timed step.  A reported baseline, measured, not extrapolated."""
+    import torch.nn.functional as F
+    from ltx_video_gpupoor_b200.ltx.init_weights import random_transformer_state_dict
+    from oracle import ltx_oracle as O
+    BF = torch.bfloat16
+    sd = random_transformer_state_dict(cfg, seed=0, device=dev)
+    B, Lp = wl["num_conds"], wl["prompt_tokens"]
+    f, h, w = wl["num_frames"] // 8 + 1, wl["height"] // 32, wl["width"] // 32
+    N = f * h * w
+    g = torch.Generator().manual_seed(3)
+    hidden = torch.randn(1, N, 128, generator=g).expand(B, N, 128).contiguous().to(dev, BF)
+    enc = torch.randn(B, Lp, 4096, generator=g).to(dev, BF)
+    mask = torch.ones(B, Lp, device=dev)
+    t = torch.full((B, 1), 0.7, device=dev)
+    coords = O.latent_to_pixel_coords(O.latent_coords(f, h, w, 1)).float()
+    coords[:, 0] *= 1.0 / wl["frame_rate"]
+    cos, sin = O.precompute_freqs_cis(coords.to(dev), 2048, 10000.0, (20, 2048, 2048), out_dtype=BF)
+
+    def sdpa(q, k, v, bias=None):                  # utils/attention.py:99-116 on the GPU: torch SDPA on [B, H, L, d]
+        return F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2),
+                                              attn_mask=None if bias is None else bias.to(q.dtype)).transpose(1, 2)
+
+    saved, O.attention_core = O.attention_core, sdpa
+    try:
+        with torch.no_grad():
+            fwd = lambda: O.transformer_forward(sd, O.LTX_2B, hidden, (cos, sin), enc, t, mask, latent_shape=(f, h, w))
+            y_ref = fwd()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(3):
+                y_ref = fwd()
+            b.record()
+            torch.cuda.synchronize()
+            lib_ms = a.elapsed_time(b) / 3
+            y = tr(hidden, freqs_cis=(cos, sin), encoder_hidden_states=enc, timestep=t, encoder_attention_mask=mask,
+                   latent_shape=(f, h, w), return_dict=False)[0]
+            torch.cuda.synchronize()
+    finally:
+        O.attention_core = saved
+    return {"what": "torch eager bf16 + F.scaled_dot_product_attention (the reference's GPU path, `_attention='sdpa'`): oracle restatement of the "
+                    "reference modules on this GPU, same weights, 28 layers x %d conds x %d tokens, transformer forward only" % (B, N),
+            "ms_per_step": lib_ms, "steps_per_s": 1e3 / lib_ms, "this_repo_ms_per_step": ours_ms, "speedup_vs_library": lib_ms / ours_ms,
+            "rel_l2_between_them_one_forward": rel_l2(y.float().cpu(), y_ref.float().cpu()), "extrapolated": False}
+
 
 # ------------------------------------------------------------------------------------------------------------
 def main():
@@ -424,6 +602,8 @@ def main():
     ap.add_argument("--workload", default="ltx2b_768x512x121_cfg_stg", choices=sorted(WORKLOADS) + sorted(WAN_WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
+    ap.add_argument("--no-wan-sp", action="store_true", help="skip the Wan2.1 sequence-parallel block of the default line")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the torch-eager-on-GPU library baseline")
     ap.add_argument("--layers", type=int, default=28, help="debug only: fewer layers makes the number INVALID")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 0)
@@ -566,7 +746,11 @@ def main():
         except Exception:
             traffic = None
     roofline = {"kernel": top, "bound": bound, "achieved": achieved, "peak": peak, "peak_source": pk["src"] + " (sustained: kernel timed inside a long step)",
-                "unit": unit, "frac": achieved / peak, "traffic": traffic, "launches_per_step": d["n"],
+                "unit": unit, "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": ("static: dram__bytes_read.sum + dram__bytes_write.sum of this kernel's largest launch (FFN-down, 18432x2048x8192) from the "
+                                   "committed ncu --set full capture profiles/r01c_ncu_gemm_raw.csv via profiles/traffic.json; NOT measured in this run "
+                                   "(ncu cannot run inside bench.py)") if traffic is not None else None,
+                "launches_per_step": d["n"],
                 "avg_launch_ms": d["ms"] / d["n"], "share_of_step": d["ms"] / total_ms,
                 "algorithmic_per_launch": d["amount"] / d["n"]}
     kernels = {k: {"ms_per_step": round(v["ms"], 3), "launches": v["n"], "share": round(v["ms"] / total_ms, 4),
@@ -608,6 +792,26 @@ def main():
         decode_s = a.elapsed_time(b) / 1e3
         del img
 
+    # ---------------- the library bar on the same box (NOT this repo's path): the reference's GPU path = plain PyTorch bf16 modules
+    # with torch SDPA (`_attention = "sdpa"`), here the pinned restatement of those modules on this GPU with the SAME weights,
+    # all 28 layers x 3 conds, one transformer forward per step (guidance + scheduler arithmetic not included: it favours the baseline)
+    gpu_lib = None
+    if rank == 0 and not args.no_gpu_baseline:
+        try:
+            gpu_lib = gpu_library_baseline(wl, cfg, tr, dev, elapsed / args.steps * 1e3)
+        except Exception as exc:                       # an extra must never cost the headline line
+            gpu_lib = {"error": repr(exc)[:300]}
+    # ---------------- the part of the path that shards: Wan2.1-1.3B Ulysses sequence parallel over ALL ranks (strong scaling) ----------------
+    wan_sp = None
+    if not args.no_wan_sp:
+        del pipe, tr, vae, st
+        torch.cuda.empty_cache()
+        try:
+            wan_sp = wan_sp_block(dev, world, rank, local_rank)
+        except Exception as exc:
+            import traceback
+            wan_sp = {"error": repr(exc)[:300], "trace": traceback.format_exc()[-600:]}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -615,12 +819,7 @@ def main():
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        s = cpu_sample(wl)
-        cores = torch.get_num_threads()
-        cpu_baseline = {"value": 1.0 / s["step_s"], "unit": "steps/s", "cores": cores, "kind": "port",
-                        "sample": (f"oracle port (torch fp32, {cores} threads) of the transformer forward at full size "
-                                   f"N={s['tokens']}: 1- and 3-layer forwards ({s['raw'][1]:.1f}s, {s['raw'][3]:.1f}s) "
-                                   f"extrapolated to 28 layers x {wl['num_conds']} conds per denoise step")}
+        _, cpu_baseline = cpu_reference_sample(wl)
 
     ms_step = elapsed / args.steps * 1e3
     line = {
@@ -637,28 +836,10 @@ def main():
         line["stg_prefix_sharing"] = shared
         if decode_s is not None:
             shared["s_per_video"] = S * shared["ms_per_step"] / 1e3 + decode_s
-    # ---------------- extra (NOT the headline, N = 1 only, last so that nothing else depends on it): the all-ones prompt mask dropped ----
-    # without a key bias the cross-attention launches take the unmasked kernel (same arithmetic; the no-mask forward
-    # is covered by tests/test_ltx_model_gpu.py::test_ltx_transformer_without_prompt_mask_equals_all_ones_mask)
-    if dist is None and bool(torch.all(pm_h == 1)) and bool(torch.all(nm_h == 1)):
-        saved_mask = st.mask_b
-        try:
-            st.mask_b = None
-            for i in range(2):
-                pipe.denoise_step(st, i)
-            torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for i in range(args.steps):
-                pipe.denoise_step(st, (args.warmup + i) % S)
-            b.record()
-            torch.cuda.synchronize()
-            line["no_prompt_mask"] = {"ms_per_step": a.elapsed_time(b) / args.steps,
-                                      "note": "all-ones prompt mask passed as None (unmasked cross-attention kernel); not used for value / e2e"}
-        except Exception as exc:                       # an extra must never cost the headline line
-            line["no_prompt_mask"] = {"error": repr(exc)[:200]}
-        finally:
-            st.mask_b = saved_mask
+    if gpu_lib is not None:
+        line["gpu_library_baseline"] = gpu_lib
+    if wan_sp is not None:
+        line["wan_sp"] = wan_sp
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

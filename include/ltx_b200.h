@@ -221,8 +221,19 @@ int ltxb200_comm_alloc(size_t bytes, void** dev_ptr, void* ipc_handle_64B);   /*
 int ltxb200_comm_open(const void* ipc_handle_64B, void** dev_ptr);            /* map a peer's buffer (enables P2P lazily) */
 int ltxb200_comm_close(void* dev_ptr);
 int ltxb200_comm_free(void* dev_ptr);
-/* stream-ordered wait until flags[0..P) (this rank's flag array) have all reached `epoch` */
+/* stream-ordered wait until flags[0..P) (this rank's flag array) have all reached `epoch`.  The wait is bounded
+ * (LTXB200_COMM_TIMEOUT_MS, default 20 s): a peer that never publishes costs the timeout, not a hung GPU. */
 int ltxb200_comm_wait(const void* flags, int P, unsigned int epoch, void* stream);
+/* the same with an error path: on timeout (timeout_ms, 0 = the default above) the kernel stores (source rank + 1) | epoch << 8
+ * into *status_dev (device word; sticky — later waits given the same word return immediately) and *status_host (a word of
+ * pinned, device-accessible host memory the host polls without synchronising), then returns.  Either may be NULL. */
+int ltxb200_comm_wait_status(const void* flags, int P, unsigned int epoch, void* status_dev, void* status_host,
+                             unsigned int timeout_ms, void* stream);
+/* all-gather by peer stores (the head output gather, xdit_context_parallel.py:142 `get_sp_group().all_gather(x, dim=1)`):
+ * segment b (of nseg, seg_bytes each, 16-byte multiple) of the contiguous local `src` is stored at byte offset
+ * (b*P + rank)*seg_bytes of dst_ptrs[r] on every rank r, then flag[rank] = epoch is published on every peer. */
+int ltxb200_peer_allgather(const void* src, int64_t seg_bytes, int nseg, int P, int rank, void* const* dst_ptrs,
+                           void* const* flag_ptrs, unsigned int epoch, void* counter, void* stream);
 /* Wan q/k RMSNorm + RoPE (as ltxb200_qk_norm_rope_wan_bf16) on the local fused QKV rows [B*n_loc, 3*D], v passed through,
  * each head group stored into recv_ptrs[g] laid out [N, B, 3, H/P, head_dim] in global token order; then flag[rank] =
  * epoch is published on every peer.  recv_ptrs / flag_ptrs: HOST arrays of P device pointers (peer mappings). */
@@ -231,6 +242,16 @@ int ltxb200_qk_norm_rope_wan_scatter_bf16(const void* qkv, int64_t ld, int M, in
                                           int tokens_per_batch, int token_offset, float eps, int B, int P, int rank,
                                           void* const* recv_ptrs, void* const* flag_ptrs, unsigned int epoch,
                                           void* counter, void* stream);
+/* the same over rows [row0, row0 + rows) of the M local rows only: one exchange may be issued as several launches (token
+ * chunks, so that the peer stores of chunk i overlap the QKV projection of chunk i+1 on another stream).  `signal_ctas` =
+ * the sum of ltxb200_scatter_signal_ctas(rows_c) over all launches of the exchange; the last CTA of the last launch to
+ * finish publishes the flag. */
+int ltxb200_qk_norm_rope_wan_scatter_rows_bf16(const void* qkv, int64_t ld, int M, int row0, int rows, int D, const void* wq,
+                                               const void* wk, const float* cos_table, const float* sin_table, int head_dim,
+                                               int tokens_per_batch, int token_offset, float eps, int B, int P, int rank,
+                                               void* const* recv_ptrs, void* const* flag_ptrs, unsigned int epoch,
+                                               void* counter, unsigned int signal_ctas, void* stream);
+unsigned int ltxb200_scatter_signal_ctas(int rows);
 /* ltxb200_attention_bf16 whose epilogue stores query token t's row to out_ptrs[t / tokens_per_peer] at row
  * b*tokens_per_peer + t % tokens_per_peer, head head_offset + h of a [B*tokens_per_peer, ldo] matrix (the Ulysses
  * return exchange, xdit_context_parallel.py:186-190), then publishes the epoch flag on every peer. */

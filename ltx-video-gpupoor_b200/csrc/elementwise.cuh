@@ -275,18 +275,19 @@ qk_norm_rope_wan_kernel(__nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict
 // slice is stored straight into the receive buffer of the rank that owns those heads,
 //   recv_g[T, b, sel, h_local, :]   (T = global token, sel = q|k|v, g = head / Hp),
 // i.e. [N, B, 3, Hp, d] in global token order -- exactly the layout the attention kernel's TMA maps read.
-// grid.y = 3 (q, k, v).  The last CTA publishes the epoch flag on every peer (comm.cuh).
+// grid.y = 3 (q, k, v).  The launch covers rows [row0, row_end) of the M local rows; `signal_ctas` CTAs (of this and the other
+// launches of the same exchange) arrive before the last one publishes the epoch flag on every peer (comm.cuh).
 template <int NV>
 __global__ void __launch_bounds__(128)
-qk_norm_rope_wan_scatter_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int M, const __nv_bfloat16* __restrict__ wq,
+qk_norm_rope_wan_scatter_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int row0, int row_end, const __nv_bfloat16* __restrict__ wq,
                                 const __nv_bfloat16* __restrict__ wk, const float* __restrict__ cosT,
                                 const float* __restrict__ sinT, int head_dim, int tokens_per_batch, int token_offset,
-                                float eps, int B, int Hp, const PeerPtrs pp) {
+                                float eps, int B, int Hp, const PeerPtrs pp, unsigned int signal_ctas) {
   constexpr int D = NV * 256;
   const int sel = blockIdx.y;                       // 0 q, 1 k, 2 v
-  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int row = row0 + blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (row < M) {
+  if (row < row_end) {
     const __nv_bfloat16* xr = qkv + row * ld + sel * D;
     uint4 xv[NV];
 #pragma unroll
@@ -336,7 +337,7 @@ qk_norm_rope_wan_scatter_kernel(const __nv_bfloat16* __restrict__ qkv, long long
       *reinterpret_cast<uint4*>(dst) = r;
     }
   }
-  peer_signal_done(pp, gridDim.x * gridDim.y);
+  peer_signal_done(pp, signal_ctas);
 }
 
 // out = sum_j coef[j] * x[j]   (fp32, up to 6 terms; the UniPC predictor/corrector and CFG combine are

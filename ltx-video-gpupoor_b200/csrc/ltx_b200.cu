@@ -38,7 +38,7 @@ static inline int ew_blocks(long long work_items, int threads) {
   return static_cast<int>(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
-extern "C" int ltxb200_abi_version(void) { return 2; }
+extern "C" int ltxb200_abi_version(void) { return 3; }
 extern "C" long long ltxb200_launch_count(void) { return g_launches.load(); }
 extern "C" const char* ltxb200_error_string(int code) {
   switch (code) {
@@ -353,37 +353,73 @@ extern "C" int ltxb200_comm_open(const void* ipc_handle_64B, void** dev_ptr) {
 extern "C" int ltxb200_comm_close(void* dev_ptr) { return cudaIpcCloseMemHandle(dev_ptr) == cudaSuccess ? kOk : kErrCuda; }
 extern "C" int ltxb200_comm_free(void* dev_ptr) { return cudaFree(dev_ptr) == cudaSuccess ? kOk : kErrCuda; }
 
-extern "C" int ltxb200_comm_wait(const void* flags, int P, unsigned int epoch, void* stream) {
+extern "C" int ltxb200_comm_wait_status(const void* flags, int P, unsigned int epoch, void* status_dev, void* status_host,
+                                        unsigned int timeout_ms, void* stream) {
   if (!flags || P < 1 || P > kMaxPeers) return kErrBadShape;
-  comm_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const unsigned int*>(flags), P, epoch);
+  static const unsigned int env_ms = getenv("LTXB200_COMM_TIMEOUT_MS") ? static_cast<unsigned int>(atoi(getenv("LTXB200_COMM_TIMEOUT_MS"))) : 20000u;
+  const unsigned long long ns = static_cast<unsigned long long>(timeout_ms ? timeout_ms : env_ms) * 1000000ull;
+  comm_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const unsigned int*>(flags), P, epoch,
+                                                                    static_cast<unsigned int*>(status_dev),
+                                                                    static_cast<unsigned int*>(status_host), ns);
   return launch_status();
 }
 
-extern "C" int ltxb200_qk_norm_rope_wan_scatter_bf16(const void* qkv, int64_t ld, int M, int D, const void* wq, const void* wk,
-                                                     const float* cos_table, const float* sin_table, int head_dim,
-                                                     int tokens_per_batch, int token_offset, float eps, int B, int P,
-                                                     int rank, void* const* recv_ptrs, void* const* flag_ptrs,
-                                                     unsigned int epoch, void* counter, void* stream) {
+extern "C" int ltxb200_comm_wait(const void* flags, int P, unsigned int epoch, void* stream) {
+  return ltxb200_comm_wait_status(flags, P, epoch, nullptr, nullptr, 0, stream);
+}
+
+extern "C" int ltxb200_peer_allgather(const void* src, int64_t seg_bytes, int nseg, int P, int rank, void* const* dst_ptrs,
+                                      void* const* flag_ptrs, unsigned int epoch, void* counter, void* stream) {
+  if (!src || seg_bytes <= 0 || (seg_bytes & 15) || nseg <= 0) return kErrBadShape;
+  if (!aligned16(src)) return kErrBadAlign;
+  PeerPtrs pp;
+  if (int rc = fill_peers(&pp, P, rank, dst_ptrs, flag_ptrs, epoch, counter)) return rc;
+  const long long vec = seg_bytes / 16;
+  peer_allgather_kernel<<<ew_blocks(vec * nseg, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(src), vec, nseg, pp);
+  return launch_status();
+}
+
+// CTAs one launch over `rows` rows contributes to the arrival counter
+static inline unsigned int scatter_ctas(int rows) { return static_cast<unsigned int>((rows + 3) / 4) * 3u; }
+
+extern "C" int ltxb200_qk_norm_rope_wan_scatter_rows_bf16(const void* qkv, int64_t ld, int M, int row0, int rows, int D, const void* wq,
+                                                          const void* wk, const float* cos_table, const float* sin_table,
+                                                          int head_dim, int tokens_per_batch, int token_offset, float eps, int B,
+                                                          int P, int rank, void* const* recv_ptrs, void* const* flag_ptrs,
+                                                          unsigned int epoch, void* counter, unsigned int signal_ctas, void* stream) {
   if (M <= 0 || D <= 0 || (D % 256) || B <= 0 || tokens_per_batch <= 0 || M != B * tokens_per_batch) return kErrBadShape;
+  if (row0 < 0 || rows <= 0 || row0 + rows > M || signal_ctas < scatter_ctas(rows)) return kErrBadShape;
   if (!qkv || !aligned16(qkv) || (ld & 7) || !wq || !wk || !cos_table || !sin_table || !aligned16(cos_table) || !aligned16(sin_table))
     return kErrBadAlign;
   if (head_dim <= 0 || (head_dim & 7) || (D % head_dim) || ((D / head_dim) % P)) return kErrBadShape;
   PeerPtrs pp;
   if (int rc = fill_peers(&pp, P, rank, recv_ptrs, flag_ptrs, epoch, counter)) return rc;
   const int Hp = D / head_dim / P;
-  dim3 grid((M + 3) / 4, 3);
+  dim3 grid((rows + 3) / 4, 3);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   auto X = static_cast<const __nv_bfloat16*>(qkv);
   auto WQ = static_cast<const __nv_bfloat16*>(wq);
   auto WK = static_cast<const __nv_bfloat16*>(wk);
 #define QKS_CASE(n) \
-  case n: qk_norm_rope_wan_scatter_kernel<n><<<grid, 128, 0, st>>>(X, ld, M, WQ, WK, cos_table, sin_table, head_dim, tokens_per_batch, token_offset, eps, B, Hp, pp); break;
+  case n: qk_norm_rope_wan_scatter_kernel<n><<<grid, 128, 0, st>>>(X, ld, row0, row0 + rows, WQ, WK, cos_table, sin_table, head_dim, tokens_per_batch, token_offset, eps, B, Hp, pp, signal_ctas); break;
   switch (D / 256) {
     QKS_CASE(1) QKS_CASE(2) QKS_CASE(4) QKS_CASE(6) QKS_CASE(8) QKS_CASE(12) QKS_CASE(16) QKS_CASE(20)
     default: return kErrUnsupported;
   }
 #undef QKS_CASE
   return launch_status();
+}
+
+extern "C" unsigned int ltxb200_scatter_signal_ctas(int rows) { return rows > 0 ? scatter_ctas(rows) : 0u; }
+
+extern "C" int ltxb200_qk_norm_rope_wan_scatter_bf16(const void* qkv, int64_t ld, int M, int D, const void* wq, const void* wk,
+                                                     const float* cos_table, const float* sin_table, int head_dim,
+                                                     int tokens_per_batch, int token_offset, float eps, int B, int P,
+                                                     int rank, void* const* recv_ptrs, void* const* flag_ptrs,
+                                                     unsigned int epoch, void* counter, void* stream) {
+  return ltxb200_qk_norm_rope_wan_scatter_rows_bf16(qkv, ld, M, 0, M, D, wq, wk, cos_table, sin_table, head_dim, tokens_per_batch,
+                                                    token_offset, eps, B, P, rank, recv_ptrs, flag_ptrs, epoch, counter,
+                                                    M > 0 ? scatter_ctas(M) : 0u, stream);
 }
 
 extern "C" int ltxb200_attention_scatter_bf16(const void* q, int64_t ldq, int64_t bsq, const void* k, int64_t ldk, int64_t bsk,

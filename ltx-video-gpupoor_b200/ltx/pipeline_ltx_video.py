@@ -6,8 +6,8 @@ conditioning_items, output_type, …)`) and semantics of the denoise loop (:1103
 per-step guidance tables, cond batching [uncond, text, perturbed], per-token timesteps for conditioned
 tokens, cfg-star / STG / std-rescale guidance, rectified-flow Euler step with the conditioning mask, and
 the final VAE decode.  What differs is execution: latents live in fp32 on the device, each step is
-(optional CUDA-graph replay of) the transformer forward + one fused guidance/step kernel group, and
-nothing in the loop synchronises with the host.  Text encoding, prompt enhancement, media loading and the
+the transformer forward + one fused guidance/step kernel group, and nothing in the loop synchronises with the
+host (CUDA-graph replay of the step was measured and not kept: the loop is not launch-bound).  Text encoding, prompt enhancement, media loading and the
 multi-scale wrapper are out of scope.
 """
 from __future__ import annotations
@@ -78,8 +78,6 @@ class LTXVideoPipeline:
         self.patchifier = patchifier or SymmetricPatchifier(1)
         self.video_scale_factor, self.vae_scale_factor, _ = get_vae_size_scale_factor(vae) if vae is not None else (8, 32, 32)
         self.allowed_inference_steps = allowed_inference_steps
-        self.use_cuda_graph = False
-        self._graphs = {}
 
     @property
     def _execution_device(self):
@@ -317,6 +315,10 @@ class LTXVideoPipeline:
             enc_b = torch.cat([enc_b, pe], dim=0)
             mask_b = torch.cat([mask_b, pm], dim=0)
         enc_b, mask_b = enc_b.contiguous(), mask_b.contiguous()
+        # an all-ones prompt mask is a zero key bias ((1 - 1) * -10000, transformer3d.py:411-415): pass none at all, so that the 28
+        # cross-attention launches per forward take the kernel's unmasked path (one host read per CALL, not per step)
+        if bool((mask_b == 1).all()):
+            mask_b = None
 
         # ---- latents (:1056-1088); drawn in prompt_embeds' dtype like the reference (:1061), kept as an fp32 master copy
         noise_dtype = prompt_embeds.dtype if prompt_embeds.dtype in (torch.float32, BF16) else torch.float32

@@ -165,27 +165,43 @@ class RectifiedFlowScheduler:
 
     def step(self, model_output: torch.Tensor, timestep, sample: torch.Tensor, return_dict: bool = True,
              stochastic_sampling: Optional[bool] = False, **kwargs) -> Union[RectifiedFlowSchedulerOutput, Tuple]:
-        """rf.py:311-380.  `timestep`: 0-d (global) or [1,1]; per-token timesteps are expressed through the pipeline's conditioning
-        mask path (`ops.guidance_step`).  stochastic_sampling (:370-373) re-noises the x0 estimate to the next timestep; the
-        N(0,1) draw comes from `generator=` / `noise=` in kwargs (the reference uses the global RNG)."""
+        """rf.py:311-380 for a GLOBAL timestep (0-d, or any one-element tensor): prev = sample - dt * model_output, or with
+        stochastic_sampling (:370-373) add_noise(sample - t * model_output, randn, t - dt); computed in fp32 by the linear-combination
+        kernel (fp32 predictions are not truncated) and returned in the promoted dtype of `sample` and `model_output`, as the
+        reference's tensor arithmetic does.  The N(0,1) draw comes from `generator=` / `noise=` in kwargs (the reference uses the
+        global RNG).  Per-token [B, N] timesteps (:361-367) exist for conditioned tokens and go through the pipeline's fused
+        guidance/step kernel with its conditioning mask (`LTXVideoPipeline.denoise_step`): NotImplementedError here."""
         if self.num_inference_steps is None:
             raise ValueError("Number of inference steps is 'None', you need to run 'set_timesteps' after creating the scheduler")
-        t = float(torch.as_tensor(timestep).reshape(-1)[0])
-        assert torch.as_tensor(timestep).numel() == 1, "use the pipeline path for per-token timesteps"
+        tt = torch.as_tensor(timestep)
+        if tt.numel() != 1:
+            raise NotImplementedError("per-token timesteps are handled by LTXVideoPipeline.denoise_step (fused guidance/step kernel)")
+        t = float(tt.reshape(-1)[0])
         dev = model_output.device
-        lat = sample.to(torch.float32).contiguous().clone().view(-1)
-        pred = model_output.to(torch.bfloat16).contiguous().view(1, -1)
-        ts = self.timesteps.to(device=dev, dtype=torch.float32).contiguous()
-        noise = None
+        out_dtype = torch.promote_types(sample.dtype, model_output.dtype)
+        lower = 0.0
+        for v in self.timesteps_host.tolist():          # descending: the first one strictly below t - eps is the closest
+            if v < t - 1e-6:
+                lower = float(v)
+                break
+        x = sample.to(device=dev, dtype=torch.float32).contiguous().view(-1)
+        v = model_output.to(torch.float32).contiguous().view(-1)
+        n = x.numel()
+        pad = (-n) % 4                                   # the kernel works on float4
+        if pad:
+            x, v = torch.nn.functional.pad(x, (0, pad)), torch.nn.functional.pad(v, (0, pad))
+        out = torch.empty_like(x)
         if stochastic_sampling:
             noise = kwargs.get("noise")
             if noise is None:
                 noise = torch.randn(sample.shape, device=dev, dtype=torch.float32, generator=kwargs.get("generator"))
-            noise = noise.to(device=dev, dtype=torch.float32).contiguous().view(-1)
-        ops.guidance_step(pred, lat, ts, t, num_conds=1, has_cfg=False, has_stg=False, do_rescale=False,
-                          guidance_scale=1.0, stg_scale=0.0, rescale=1.0, channels=sample.shape[-1], cond_mask=None,
-                          scratch=None, noise=noise)
-        prev = lat.view(sample.shape)
+            z = noise.to(device=dev, dtype=torch.float32).contiguous().view(-1)
+            if pad:
+                z = torch.nn.functional.pad(z, (0, pad))
+            ops.lincomb(out, [(1.0 - lower, x), (-(1.0 - lower) * t, v), (lower, z)])
+        else:
+            ops.lincomb(out, [(1.0, x), (-(t - lower), v)])
+        prev = out[:n].view(sample.shape).to(out_dtype)
         if not return_dict:
             return (prev,)
         return RectifiedFlowSchedulerOutput(prev_sample=prev)

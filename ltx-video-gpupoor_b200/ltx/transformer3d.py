@@ -5,8 +5,7 @@ Same constructor config keys, same state_dict layout (reference key names), same
 companion API (`precompute_freqs_cis`, `create_skip_layer_mask`, `.config`, `.dtype`, `.in_channels`).
 All arithmetic runs in hand-written sm_100a kernels through the C ABI (`ops`): every Linear is the
 tcgen05/TMEM GEMM with fused bias / GELU / gate / residual epilogues, attention is the TMEM flash
-kernel, norms / modulation / QK-norm+RoPE are single-pass memory-bound kernels.  The layer loop is
-allocation-stable so that it can be captured in a CUDA graph (see `LTXVideoPipeline`).
+kernel, norms / modulation / QK-norm+RoPE are single-pass memory-bound kernels.
 """
 from __future__ import annotations
 
@@ -69,7 +68,6 @@ class Transformer3DModel(ModuleLike):
         self.device = torch.device("cuda")
         self.w: Dict[str, torch.Tensor] = {}
         self.layers: List[Dict[str, torch.Tensor]] = []
-        self._skip_host: Dict[int, torch.Tensor] = {}
 
     @classmethod
     def from_config(cls, config: dict):
@@ -151,7 +149,7 @@ class Transformer3DModel(ModuleLike):
         for block_idx in skip_block_list:
             mask[block_idx, ptb_index::num_conds] = 0
             host[block_idx, ptb_index::num_conds] = 0
-        self._skip_host[mask.data_ptr()] = host        # lets forward() pick skipped layers without a device sync
+        mask._ltxb200_host = host                      # lets forward() pick skipped layers without a device sync (lives and dies with the mask)
         return mask
 
     def get_fractional_positions(self, indices_grid):
@@ -246,8 +244,8 @@ class Transformer3DModel(ModuleLike):
 
         skip_host = None
         if skip_layer_mask is not None:
-            skip_host = self._skip_host.get(skip_layer_mask.data_ptr())
-            if skip_host is None:
+            skip_host = getattr(skip_layer_mask, "_ltxb200_host", None)
+            if skip_host is None or tuple(skip_host.shape) != tuple(skip_layer_mask.shape):
                 skip_host = skip_layer_mask.to(torch.float32).cpu()                 # foreign mask: one sync per forward
             skip_dev = skip_layer_mask.to(device=dev, dtype=torch.float32).contiguous()
 

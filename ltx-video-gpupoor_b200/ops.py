@@ -265,12 +265,14 @@ def pixelnorm_silu(x: torch.Tensor, silu: bool = True, eps: float = 1e-8, scale:
     if scale is not None:
         _req(scale, name="scale"); _req(shift, name="shift")
         assert scale.is_contiguous() and shift.is_contiguous() and scale.numel() == C and shift.numel() == C
-        _lib.check(_lib.lib().ltxb200_pixelnorm_mod_silu_bf16(x.data_ptr(), y.data_ptr(), x.numel() // C, C, float(eps),
-                                                              scale.data_ptr(), shift.data_ptr(), int(silu), _stream()),
-                   "pixelnorm_mod_silu")
+        with _Prof('pixelnorm_silu_bf16', 'byte', 4.0 * x.numel()):
+            rc = _lib.lib().ltxb200_pixelnorm_mod_silu_bf16(x.data_ptr(), y.data_ptr(), x.numel() // C, C, float(eps),
+                                                            scale.data_ptr(), shift.data_ptr(), int(silu), _stream())
+        _lib.check(rc, "pixelnorm_mod_silu")
         return y
-    _lib.check(_lib.lib().ltxb200_pixelnorm_silu_bf16(x.data_ptr(), y.data_ptr(), x.numel() // C, C, float(eps),
-                                                      int(silu), _stream()), "pixelnorm_silu")
+    with _Prof('pixelnorm_silu_bf16', 'byte', 4.0 * x.numel()):
+        rc = _lib.lib().ltxb200_pixelnorm_silu_bf16(x.data_ptr(), y.data_ptr(), x.numel() // C, C, float(eps), int(silu), _stream())
+    _lib.check(rc, "pixelnorm_silu")
     return y
 
 

@@ -56,23 +56,37 @@ class PeerExchange:
 
       recv[par]  [N, B, 3, H/P, d]   filled by every rank's qk_norm_rope_wan_scatter kernel
       back[par]  [B*n_loc, H*d]      filled by every rank's attention epilogue
-      flags      [2 exchanges][2 parities][P] uint32 epochs, counters [2] (local)
+      gath       [B, P, n_loc, out]  fp32 head output of every rank (the final all-gather, also peer stores)
+      flags      [3 exchanges][2 parities][P] uint32 epochs, counters [3] (local), status word (device) + one pinned host word
+
+    The way in is issued in `chunks` token chunks: chunk c's QKV projection runs on the caller's stream and its
+    norm + RoPE + scatter on a side stream, so the peer stores of chunk c overlap the GEMM of chunk c+1 (the stores are
+    NVLink-bound, the GEMM tensor-bound); only the last chunk's stores are exposed.  LTXB200_SP_CHUNKS (default 4; 1 = the
+    unchunked round-1 form).
+
+    Failure handling: every wait is bounded (csrc/comm.cuh); a peer that never publishes makes the waiting kernel record
+    (source rank, epoch) in a host-visible word instead of spinning forever, and the next call here raises.
     """
 
-    def __init__(self, group, B: int, n_loc: int, H: int, d: int, device):
+    def __init__(self, group, B: int, n_loc: int, H: int, d: int, device, gather_width: int = 0):
         import ctypes
+        import os
         import torch.distributed as dist
         from ... import _lib
         self.lib = _lib.lib()
         self._check = _lib.check
+        self._err = _lib.LtxB200Error
         self.group, self.P, self.rank = group, dist.get_world_size(group), dist.get_rank(group)
         P = self.P
         assert H % P == 0 and P <= 8
         self.B, self.n_loc, self.H, self.d, self.Hp, self.N = B, n_loc, H, d, H // P, P * n_loc
         self.device = device
+        self.gather_width = gather_width
         recv_b = self.N * B * 3 * self.Hp * d * 2
         back_b = B * n_loc * H * d * 2
         self.sizes = dict(recv0=recv_b, recv1=recv_b, back0=back_b, back1=back_b, ctl=4096)
+        if gather_width:
+            self.sizes["gath0"] = self.sizes["gath1"] = B * P * n_loc * gather_width * 4
         self.local, handles = {}, {}
         for name, nbytes in self.sizes.items():
             ptr = ctypes.c_void_p()
@@ -95,57 +109,132 @@ class PeerExchange:
         dist.barrier(group=group)
         VP = ctypes.c_void_p * P
         self._arr = lambda vals: VP(*vals)
-        # flag words: exchange e (0 = qkv scatter, 1 = attention return), parity par -> ctl + (e*2+par)*64 bytes; counters after
+        # flag words: exchange e (0 = qkv scatter, 1 = attention return, 2 = head gather), parity par -> ctl + (e*2+par)*64 bytes;
+        # counters and the device status word after them
         self.flag_off = lambda e, par: (e * 2 + par) * 64
         self.counter_off = lambda e: 1024 + e * 64
+        self.status_off = 2048
+        self.status_host = torch.zeros(16, dtype=torch.int32).pin_memory()     # UVA: the kernel stores into it directly
         self.calls = 0
+        self.gather_calls = 0
+        self.chunks = max(1, int(os.environ.get("LTXB200_SP_CHUNKS", "4")))
+        self.min_chunk_rows = 1024                 # below this a chunk's GEMM no longer fills the machine (tests lower it)
+        self.side = torch.cuda.Stream(device=device)
+        self._closed = False
 
-    def _view(self, name, shape):
+    def _view(self, name, shape, dtype=torch.bfloat16):
         """torch view of a LOCAL comm buffer (no copy): wraps the raw pointer through the CUDA array interface."""
         n = 1
         for s in shape:
             n *= s
+        item = torch.empty(0, dtype=dtype).element_size()
 
         class _Raw:
             pass
         raw = _Raw()
-        raw.__cuda_array_interface__ = {"shape": (n,), "typestr": "<u2", "data": (self.local[name], False), "version": 2}
-        return torch.as_tensor(raw, device=self.device).view(torch.bfloat16).view(*shape)
+        raw.__cuda_array_interface__ = {"shape": (n,), "typestr": "<u2" if item == 2 else "<u4", "data": (self.local[name], False),
+                                        "version": 2}
+        return torch.as_tensor(raw, device=self.device).view(dtype).view(*shape)
 
-    def self_attention(self, qkv, wq, wk, cos, sin, eps, stream_ptr):
-        """qkv [B*n_loc, 3*H*d] raw projection rows -> attention output rows [B*n_loc, H*d] (view of back[par])."""
+    def check(self):
+        """Raise if a bounded wait of an earlier call gave up (polls the pinned host word; no synchronisation)."""
+        code = int(self.status_host[0])
+        if code:
+            raise self._err(f"sequence-parallel exchange timed out on rank {self.rank}: peer {(code & 0xff) - 1} never published epoch "
+                            f"{code >> 8} (a rank crashed or issued a different kernel sequence); results since then are invalid")
+
+    def _wait(self, e, par, epoch, stream_ptr):
+        from ... import ops
+        with ops._Prof("comm_wait", "byte", 0.0):
+            self._check(self.lib.ltxb200_comm_wait_status(self.local["ctl"] + self.flag_off(e, par), self.P, epoch,
+                                                          self.local["ctl"] + self.status_off, self.status_host.data_ptr(), 0,
+                                                          stream_ptr), "comm_wait")
+
+    def self_attention(self, x_mod, w_qkv, b_qkv, wq, wk, cos, sin, eps):
+        """x_mod [B*n_loc, D] modulated rows -> attention output rows [B*n_loc, H*d] (view of back[par]).  Runs the fused QKV
+        projection (chunked), q/k norm + RoPE + head scatter, attention with the return scatter in its epilogue, and the waits."""
+        from ... import ops
+        self.check()
         par = self.calls & 1
         epoch = self.calls // 2 + 1
         self.calls += 1
         B, n_loc, H, d, Hp, N, P = self.B, self.n_loc, self.H, self.d, self.Hp, self.N, self.P
         D = H * d
+        M = B * n_loc
         lib, ctl = self.lib, "ctl"
         f0 = self._arr([p + self.flag_off(0, par) for p in self.peer[ctl]])
         f1 = self._arr([p + self.flag_off(1, par) for p in self.peer[ctl]])
         recv, back = f"recv{par}", f"back{par}"
-        from ... import ops
-        with ops._Prof("qk_norm_rope_wan_scatter_bf16", "byte", 2.0 * 2 * B * n_loc * 3 * D):
-          self._check(lib.ltxb200_qk_norm_rope_wan_scatter_bf16(
-            qkv.data_ptr(), qkv.stride(0), B * n_loc, D, wq.data_ptr(), wk.data_ptr(), cos.data_ptr(), sin.data_ptr(), d,
-            n_loc, self.rank * n_loc, float(eps), B, P, self.rank, self._arr(self.peer[recv]), f0, epoch,
-            self.local[ctl] + self.counter_off(0), stream_ptr), "qk_norm_rope_wan_scatter")
-        with ops._Prof("comm_wait", "byte", 0.0):
-            self._check(lib.ltxb200_comm_wait(self.local[ctl] + self.flag_off(0, par), P, epoch, stream_ptr), "comm_wait")
+        recv_ptrs = self._arr(self.peer[recv])
+        main = torch.cuda.current_stream()
+        # chunk boundaries: multiples of 256 rows (the GEMM's CTA-pair tile) so that no chunk ends in a partial tile but the last
+        nch = min(self.chunks, max(1, M // self.min_chunk_rows))
+        align = 256 if M // nch >= 512 else 8
+        step = ((M + nch - 1) // nch + align - 1) // align * align
+        bounds = [(r0, min(M, r0 + step)) for r0 in range(0, M, step)]
+        total_ctas = sum(int(lib.ltxb200_scatter_signal_ctas(r1 - r0)) for r0, r1 in bounds)
+        qkv = torch.empty(M, 3 * D, device=x_mod.device, dtype=x_mod.dtype)
+        overlap = len(bounds) > 1 and ops.PROFILER is None       # the per-launch event timing of the bench probe needs one stream
+        for r0, r1 in bounds:
+            ops.gemm(x_mod[r0:r1], w_qkv, b_qkv, out=qkv[r0:r1])
+            if overlap:
+                self.side.wait_stream(main)
+            st = self.side if overlap else main
+            with torch.cuda.stream(st):
+                with ops._Prof("qk_norm_rope_wan_scatter_bf16", "byte", 2.0 * 2 * (r1 - r0) * 3 * D):
+                    self._check(lib.ltxb200_qk_norm_rope_wan_scatter_rows_bf16(
+                        qkv.data_ptr(), qkv.stride(0), M, r0, r1 - r0, D, wq.data_ptr(), wk.data_ptr(), cos.data_ptr(), sin.data_ptr(),
+                        d, n_loc, self.rank * n_loc, float(eps), B, P, self.rank, recv_ptrs, f0, epoch,
+                        self.local[ctl] + self.counter_off(0), total_ctas, st.cuda_stream), "qk_norm_rope_wan_scatter")
+        if overlap:
+            main.wait_stream(self.side)          # also orders every later reuse of `qkv`'s memory after the side stream's reads
+        sp = main.cuda_stream
+        self._wait(0, par, epoch, sp)
         base = self.local[recv]
         tok = B * 3 * Hp * d                    # elements per global token in recv
         q, k, v = base, base + Hp * d * 2, base + 2 * Hp * d * 2
         with ops._Prof("attention_bf16", "flop", 4.0 * B * Hp * N * N * d):
-          self._check(lib.ltxb200_attention_scatter_bf16(
-            q, tok, 3 * Hp * d, k, tok, 3 * Hp * d, v, tok, 3 * Hp * d, D, B, Hp, N, N, d, 0.0, None, P, self.rank,
-            self._arr(self.peer[back]), f1, epoch, self.local[ctl] + self.counter_off(1), n_loc, self.rank * Hp, stream_ptr),
-            "attention_scatter")
-        with ops._Prof("comm_wait", "byte", 0.0):
-            self._check(lib.ltxb200_comm_wait(self.local[ctl] + self.flag_off(1, par), P, epoch, stream_ptr), "comm_wait")
+            self._check(lib.ltxb200_attention_scatter_bf16(
+                q, tok, 3 * Hp * d, k, tok, 3 * Hp * d, v, tok, 3 * Hp * d, D, B, Hp, N, N, d, 0.0, None, P, self.rank,
+                self._arr(self.peer[back]), f1, epoch, self.local[ctl] + self.counter_off(1), n_loc, self.rank * Hp, sp),
+                "attention_scatter")
+        self._wait(1, par, epoch, sp)
         return self._view(back, (B * n_loc, D))
 
+    def all_gather_rows(self, out: torch.Tensor) -> torch.Tensor:
+        """out [B, n_loc, W] fp32 (this rank's token shard of the head output) -> [B, N, W] with every rank's shard, by peer stores
+        (xdit_context_parallel.py:142).  Returns a view of a double-buffered comm buffer: valid until the call after the next one."""
+        from ... import ops
+        assert self.gather_width and out.dtype == torch.float32 and out.is_contiguous()
+        B, n_loc, W, P = self.B, self.n_loc, self.gather_width, self.P
+        assert tuple(out.shape) == (B, n_loc, W)
+        par = self.gather_calls & 1
+        epoch = self.gather_calls // 2 + 1
+        self.gather_calls += 1
+        name = f"gath{par}"
+        sp = torch.cuda.current_stream().cuda_stream
+        f2 = self._arr([p + self.flag_off(2, par) for p in self.peer["ctl"]])
+        with ops._Prof("peer_allgather", "byte", 4.0 * out.numel() * (P + 1)):
+            self._check(self.lib.ltxb200_peer_allgather(out.data_ptr(), n_loc * W * 4, B, P, self.rank, self._arr(self.peer[name]), f2,
+                                                        epoch, self.local["ctl"] + self.counter_off(2), sp), "peer_allgather")
+        self._wait(2, par, epoch, sp)
+        return self._view(name, (B, P * n_loc, W), torch.float32)
+
     def close(self):
+        """Collective over the group: unmap the peers' buffers, then (after a barrier, so that nobody frees memory a peer still
+        has mapped) free the local ones.  Idempotent."""
+        if self._closed:
+            return
+        self._closed = True
+        torch.cuda.synchronize(self.device)
         for p in self._opened:
             self.lib.ltxb200_comm_close(p)
+        try:
+            import torch.distributed as dist
+            if dist.is_initialized():
+                dist.barrier(group=self.group)
+        except Exception:
+            pass
         for p in self.local.values():
             self.lib.ltxb200_comm_free(p)
         self._opened, self.local = [], {}

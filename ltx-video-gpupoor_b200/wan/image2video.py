@@ -7,11 +7,14 @@ built here the way the reference builds it (:232-244, 262-277): the start image 
 output size — PIL / lanczos resizing is media I/O) padded with F-1 zero frames goes through `WanVAE.encode` (wan/vae.py) and
 the 4-channel conditioning-frame mask is stacked on top; an end image (`image_end`, :191-199) adds one frame that is encoded without the
 VAE's feature caches.  CLIP visual (:219-224) and T5 are out of scope: pass `clip_fea=`
-[1, 257, 1280] and `context=` / `context_null=`.  The result is the denoised latent [16, (F-1)/4+1, H/8, W/8] (fp32); with an added end
-frame it has one latent frame more — decode it with `WanVAE.decode(..., any_end_frame=True)` and drop the last pixel frame, as :419-424 does.
+[1, 257, 1280] and `context=` / `context_null=`.  Returns what the reference returns (:414-424): the video decoded by
+`self.vae.decode(..., any_end_frame=...)` with the pixel frame of an added end image dropped, [3, F, H, W] fp32 in [-1, 1].  Without a `vae`
+(or with `return_latents=True`, the parity tests' hook) the denoised latent [16, (F-1)/4+1, H/8, W/8] (fp32) comes back instead.
 """
 from __future__ import annotations
 
+import random
+import sys
 from typing import Optional
 
 import torch
@@ -21,6 +24,7 @@ from .fm_solvers import FlowDPMSolverMultistepScheduler, get_sampling_sigmas, re
 from .fm_solvers_unipc import FlowUniPCMultistepScheduler
 from .model import WanModel
 from .posemb_layers import get_rotary_pos_embed
+from .text2video import _interrupted
 
 
 class WanI2V:
@@ -82,7 +86,7 @@ class WanI2V:
                  audio_proj=None, audio_context_lens=None, model_filename=None,
                  context: Optional[torch.Tensor] = None, context_null: Optional[torch.Tensor] = None,
                  clip_fea: Optional[torch.Tensor] = None, y: Optional[torch.Tensor] = None,
-                 noise: Optional[torch.Tensor] = None, _per_step_latents=None, **bbargs):
+                 noise: Optional[torch.Tensor] = None, _per_step_latents=None, return_latents: bool = False, **bbargs):
         if audio_proj is not None or audio_scale is not None:
             raise NotImplementedError("fantasytalking audio conditioning is out of scope")
         any_end_frame = image_end is not None
@@ -109,7 +113,7 @@ class WanI2V:
         assert tuple(y.shape) == (20,) + target_shape[1:], f"y must be [20, {target_shape[1:]}]"
         if noise is None:
             seed_g = torch.Generator(device=dev)
-            seed_g.manual_seed(seed if seed >= 0 else 0)
+            seed_g.manual_seed(seed if seed >= 0 else random.randint(0, sys.maxsize))                    # :226
             noise = torch.randn(*target_shape, dtype=torch.float32, device=dev, generator=seed_g)     # :226-230
         latents = noise.to(device=dev, dtype=torch.float32).contiguous()
         assert tuple(latents.shape) == tuple(target_shape)
@@ -150,6 +154,12 @@ class WanI2V:
                 _per_step_latents.append(latents.clone())
             if callback is not None:
                 callback(i, latents, False)
-            if self._interrupt:
+            if _interrupted(self, self.model.sp_group is not None, dev):
                 return None
-        return latents
+        if return_latents or self.vae is None:
+            return latents
+        # image2video.py:414-420: decode (the appended end frame without feature caches), drop the frame added for the end image
+        video = self.vae.decode([latents], VAE_tile_size, any_end_frame=any_end_frame and add_frames_for_end_image)[0]
+        if any_end_frame and add_frames_for_end_image:
+            video = video[:, :-1]
+        return video

@@ -152,11 +152,28 @@ class WanModel(ModuleLike):
         return dist.get_world_size(g), dist.get_rank(g)
 
     def _peer_exchange(self, B: int, n_loc: int):
+        """One set of peer-mapped buffers per (sequences, local tokens) shape; every rank sees the same sequence of shapes, so
+        creation and the eviction of the oldest shape beyond four are collective."""
         key = (B, n_loc)
         if key not in self._sp_bufs:
             from .distributed.ulysses import PeerExchange
-            self._sp_bufs[key] = PeerExchange(self.sp_group, B, n_loc, self.num_heads, 128, self.device)
+            while len(self._sp_bufs) >= 4:
+                self._sp_bufs.pop(next(iter(self._sp_bufs))).close()
+            self._sp_bufs[key] = PeerExchange(self.sp_group, B, n_loc, self.num_heads, 128, self.device,
+                                              gather_width=math.prod(self.patch_size) * self.out_dim)
         return self._sp_bufs[key]
+
+    def close(self):
+        """Release the peer-mapped exchange buffers (IPC mappings + device memory); safe to call more than once."""
+        for ex in self._sp_bufs.values():
+            ex.close()
+        self._sp_bufs = {}
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def _self_attention_sp(self, qkv: torch.Tensor, B: int, n_loc: int, P: int) -> torch.Tensor:
         """Ulysses exchange around self-attention (see distributed/ulysses.py)."""
@@ -172,8 +189,10 @@ class WanModel(ModuleLike):
         return ops.gemm(ops.gemm(te, w["time0.w"], w["time0.b"], act=ops.ACT_SILU), w["time2.w"], w["time2.b"])
 
     def _teacache_should_calc(self, e: torch.Tensor, current_step: int, x_id: int) -> bool:
-        """model.py:1029-1049: the conditional pass (x_id 0) decides, the others follow."""
-        if x_id != 0:
+        """model.py:1029-1049: the conditional pass (x_id 0) decides, the others follow.  Under CFG-parallel the ranks of the
+        unconditional half only ever run x_id 1; the decision is a function of the replicated time embedding alone, so they take
+        it themselves (`_teacache_every_rank_decides`, set by WanT2V.generate) and both halves skip the same steps."""
+        if x_id != 0 and not getattr(self, "_teacache_every_rank_decides", False):
             return self.should_calc
         if current_step <= self.teacache_start_step or current_step == self.num_steps - 1:
             should_calc = True
@@ -231,13 +250,14 @@ class WanModel(ModuleLike):
         M, Lc, Lw = B * n_loc, self.text_len, self.layers[li]
         m = mods[li]                                                              # [1, 6, D]
         xm = ops.norm_mod(xs, m[:, 1], m[:, 0], rows_per_group=M, eps=eps, layer_norm=True)        # :437-441
-        qkv = ops.gemm(xm, Lw["qkv.w"], Lw["qkv.b"])
         if P > 1 and self.sp_exchange == "p2p":
-            # q/k norm + RoPE fused with the head scatter, attention epilogue fused with the return scatter
-            o = self._peer_exchange(B, n_loc).self_attention(qkv, Lw["qn"], Lw["kn"], cos, sin, eps, ops._stream())
+            # QKV projection in token chunks, q/k norm + RoPE fused with the head scatter (overlapping the next chunk's GEMM),
+            # attention epilogue fused with the return scatter
+            o = self._peer_exchange(B, n_loc).self_attention(xm, Lw["qkv.w"], Lw["qkv.b"], Lw["qn"], Lw["kn"], cos, sin, eps)
         else:
+            qkv = ops.gemm(xm, Lw["qkv.w"], Lw["qkv.b"])
             ops.qk_norm_rope_wan(qkv[:, :D], qkv[:, D:2 * D], Lw["qn"], Lw["kn"], cos, sin, head_dim=128,
-                                 tokens_per_batch=n_loc, token_offset=rank * n_loc, eps=eps)
+                                     tokens_per_batch=n_loc, token_offset=rank * n_loc, eps=eps)
             if P == 1:
                 q3 = qkv.view(B, n_loc, 3 * D)
                 o = ops.attention(q3[:, :, :D].unflatten(-1, (H, 128)), q3[:, :, D:2 * D].unflatten(-1, (H, 128)),
@@ -328,7 +348,9 @@ class WanModel(ModuleLike):
             ori = xs.clone() if self.enable_teacache else None                         # :1065-1068
             st = SimpleNamespace(B=B, n_loc=n_loc, P=P, rank=rank, mods=mods, ctx=ctx, ctx_img=ctx_img, cos=cos, sin=sin)
             for li in range(self.num_layers):
-                if pipeline is not None and getattr(pipeline, "_interrupt", False):
+                # mid-forward interrupts only on a single rank: with peers every rank must issue the same kernel sequence (the
+                # exchange kernels wait for each other); the loops check `_interrupt` collectively at step boundaries instead
+                if P == 1 and pipeline is not None and getattr(pipeline, "_interrupt", False):
                     return [None] * B
                 if (x_id != 0 or joint_pass) and slg_layers is not None and li in slg_layers:      # :1077-1080
                     if not joint_pass:
@@ -348,9 +370,11 @@ class WanModel(ModuleLike):
         eh = ops.ada_add(w["head_mod"], torch.cat([e, e], dim=1))                     # [1, 1, 2, D] = modulation + e (:566)
         yh = ops.norm_mod(xs, eh[0][:, 1], eh[0][:, 0], rows_per_group=M, eps=eps, layer_norm=True)
         out = ops.gemm(yh, w["head.w"], w["head.b"], out_f32=True).view(B, n_loc, -1)  # [B, n_loc, 64] fp32
-        if P > 1:
+        if P > 1 and self.sp_exchange == "p2p":                                        # :142, as peer stores + flag (no collective call)
+            out = self._peer_exchange(B, n_loc).all_gather_rows(out.contiguous())
+        elif P > 1:
             import torch.distributed as dist
             parts = [torch.empty_like(out) for _ in range(P)]
-            dist.all_gather(parts, out.contiguous(), group=self.sp_group)              # :142
+            dist.all_gather(parts, out.contiguous(), group=self.sp_group)
             out = torch.cat(parts, dim=1)
         return [u.float() for u in self.unpatchify(out, grid)]

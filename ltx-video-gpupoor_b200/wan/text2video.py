@@ -1,13 +1,17 @@
 """WanT2V — B200-native drop-in for the denoise loop of wan/text2video.py:281-607 (`WanT2V.generate`).
 
 Scope: noise, UniPC schedule, RoPE tables, the per-step two-sequence forward (cond / uncond
-batched), CFG with the optional CFG-Zero* projection, scheduler step.  Text encoding (T5), the Wan VAE
-(§8f#1 "next"), VACE / phantom / recam are out of scope: prompt embeddings are passed in
-(`context=`, `context_null=`) and the result is the denoised latent [16, (F-1)/4+1, H/8, W/8] (fp32).
+batched), CFG with the optional CFG-Zero* projection, scheduler step, `self.vae.decode` of the result
+(text2video.py:579-596).  Text encoding (T5), VACE / phantom / recam are out of scope: prompt embeddings are passed in
+(`context=`, `context_null=`).  Returns what the reference returns — the decoded video [3, F, H, W] fp32 in [-1, 1] —
+when the pipeline holds a `vae`; without one (or with `return_latents=True`, the parity tests' hook) the denoised
+latent [16, (F-1)/4+1, H/8, W/8] (fp32).
 """
 from __future__ import annotations
 
 import math
+import random
+import sys
 from typing import Optional
 
 import torch
@@ -21,8 +25,9 @@ from .posemb_layers import get_rotary_pos_embed
 
 class WanT2V:
     def __init__(self, model: WanModel, device="cuda", num_train_timesteps: int = 1000, vae_stride=(4, 8, 8),
-                 patch_size=(1, 2, 2), z_dim: int = 16):
+                 patch_size=(1, 2, 2), z_dim: int = 16, vae=None):
         self.model = model
+        self.vae = vae                      # WanVAE (wan/vae.py) or None: generate() then returns the latents
         self.device = torch.device(device)
         self.num_train_timesteps = num_train_timesteps
         self.vae_stride, self.patch_size, self.z_dim = vae_stride, patch_size, z_dim
@@ -36,7 +41,8 @@ class WanT2V:
                  slg_layers=None, slg_start=0.0, slg_end=1.0, cfg_star_switch=True, cfg_zero_step=5,
                  overlapped_latents=None, return_latent_slice=None, overlap_noise=0, conditioning_latents_size=0,
                  model_filename=None, context: Optional[torch.Tensor] = None, context_null: Optional[torch.Tensor] = None,
-                 noise: Optional[torch.Tensor] = None, _per_step_latents=None, cfg_parallel=None, **bbargs):
+                 noise: Optional[torch.Tensor] = None, _per_step_latents=None, cfg_parallel=None,
+                 return_latents: bool = False, **bbargs):
         if input_frames is not None or input_ref_images is not None or target_camera is not None or overlapped_latents is not None:
             raise NotImplementedError("VACE / phantom / recam inputs are out of scope")
         if context is None or (guide_scale != 1 and context_null is None):
@@ -48,7 +54,7 @@ class WanT2V:
         target_shape = (self.z_dim, (F - 1) // self.vae_stride[0] + 1, height // self.vae_stride[1], width // self.vae_stride[2])
         if noise is None:
             seed_g = torch.Generator(device=dev)
-            seed_g.manual_seed(seed if seed >= 0 else 0)
+            seed_g.manual_seed(seed if seed >= 0 else random.randint(0, sys.maxsize))                    # :354
             noise = torch.randn(*target_shape, dtype=torch.float32, device=dev, generator=seed_g)     # :410
         latents = noise.to(device=dev, dtype=torch.float32).contiguous()
         assert tuple(latents.shape) == tuple(target_shape)
@@ -63,6 +69,10 @@ class WanT2V:
         scratch = torch.empty(2 * 148, device=dev, dtype=torch.float32)
         ctx = context.to(dev)
         ctx0 = context_null.to(dev) if context_null is not None else None
+        # under CFG-parallel the unconditional half never runs the x_id == 0 pass that takes the TeaCache decision (model.py:1029):
+        # the decision only depends on the (replicated) time embedding, so every rank takes it itself
+        self.model._teacache_every_rank_decides = cfg_parallel is not None
+        collective = cfg_parallel is not None or self.model.sp_group is not None
         if self.model.enable_teacache:                                                                    # :461-464
             self.model.previous_residual = [None] * 2
             if getattr(self.model, "teacache_multiplier", 0):
@@ -97,6 +107,22 @@ class WanT2V:
                 _per_step_latents.append(latents.clone())
             if callback is not None:
                 callback(i, latents, False)
-            if self._interrupt:
+            if _interrupted(self, collective, dev):
                 return None
-        return latents
+        if return_latents or self.vae is None:
+            return latents
+        if return_latent_slice is not None:                                                               # :578-595
+            return {"x": self.vae.decode([latents], VAE_tile_size)[0], "latent_slice": latents[:, return_latent_slice].clone()}
+        return self.vae.decode([latents], VAE_tile_size)[0]                                               # :590,596
+
+
+def _interrupted(pipe, collective: bool, dev) -> bool:
+    """`_interrupt` is set asynchronously by the host application on ONE process.  With several ranks the peers' kernels wait for
+    each other (Ulysses exchange flags, the CFG-parallel all-gather), so leaving the loop must be a collective decision: the flag
+    is OR-reduced once per step (one tiny all-reduce + host read) and every rank leaves at the same step boundary."""
+    if not collective:
+        return bool(pipe._interrupt)
+    import torch.distributed as dist
+    f = torch.tensor([1 if pipe._interrupt else 0], device=dev, dtype=torch.int32)
+    dist.all_reduce(f, op=dist.ReduceOp.MAX)
+    return bool(f.item())

@@ -101,9 +101,39 @@ def main():
                     cos_row=cos_r[17].clone(), sin_row=sin_r[17].clone()),
                os.path.join(GOLD, "wan_t2v.pt"))
     print("written", os.path.join(GOLD, "wan_t2v.pt"))
+    main_h4()
     main_i2v()
     main_skip()
     main_dpm()
+
+
+def main_h4():
+    """A 4-head variant (96 tokens) of the joint forward: the fixture the sequence-parallel parity checks use at group sizes 2 and 4
+    (tests/test_wan_gpu.py, and bench.py's `wan_sp.sp_parity_rel_l2` on the driver's multi-GPU boxes; the 2-head TINY model cannot be
+    split four ways).  The unmodified reference in fp64, as above."""
+    from wan.modules.posemb_layers import get_rotary_pos_embed
+    cfg = dict(W.WAN_1_3B, dim=512, ffn_dim=1280, num_heads=4, num_layers=2)
+    sd = {k: v.double() for k, v in W.make_wan_state_dict(cfg, seed=0).items()}
+    ref = build_ref(cfg, sd)
+    g = torch.Generator().manual_seed(5)
+    lat = torch.randn(16, 3, 8, 16, generator=g).double()
+    ctx = torch.randn(20, 4096, generator=g).double()
+    ctx0 = torch.randn(11, 4096, generator=g).double()
+    t = torch.tensor([937])
+    cos_r, sin_r = get_rotary_pos_embed(lat.shape[1:], enable_RIFLEx=False)
+    y_ref = ref([lat.clone(), lat.clone()], t=t, context=[ctx, ctx0], freqs=(cos_r, sin_r), pipeline=_Pipe())
+    cos, sin = W.rope_tables(lat.shape[1:])
+    y = W.wan_forward(sd, cfg, [lat, lat], t, [ctx, ctx0], cos, sin)
+    for a, b in zip(y, y_ref):
+        e = rel_l2(a, b)
+        print(f"  wan_forward (4 heads): rel_l2(oracle, reference) = {e:.3e}")
+        assert e < 2e-5
+    y4 = W.wan_forward(sd, cfg, [lat], t, [ctx], cos, sin, attn_fn=lambda q, k, v: W.ulysses_attention_virtual(q, k, v, 4))
+    assert rel_l2(y4[0], y[0]) < 1e-5
+    print("  ulysses (4 virtual ranks) == single-rank forward")
+    torch.save(dict(cfg=cfg, seed_weights=0, lat=lat.float(), ctx=ctx.float(), ctx0=ctx0.float(), t=t, fwd=[a.float().clone() for a in y_ref]),
+               os.path.join(GOLD, "wan_t2v_h4.pt"))
+    print("written", os.path.join(GOLD, "wan_t2v_h4.pt"))
 
 
 # The production coefficients (a polynomial fitted to trained checkpoints) are set by the caller; with random weights the time

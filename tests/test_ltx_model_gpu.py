@@ -22,7 +22,7 @@ from oracle import ltx_oracle as O  # noqa: E402
 DEV = "cuda"
 # bf16 weights + bf16 activations vs the fp32 reference: the reference's own bf16-vs-fp32 noise floor on the
 # raw model output is 1.5e-2; the 2e-2 contract is on LATENTS.
-TOL_MODEL_OUT = 3e-2
+TOL_MODEL_OUT = 2e-2
 TOL_LATENTS = 2e-2
 
 
@@ -112,7 +112,7 @@ def test_pipeline_latents_vs_reference_fixture(golden_dir):
             assert err < TOL_LATENTS
         err = O.rel_l2(lat.float().cpu(), g[tag]["latents"])
         print(f"pipeline[{tag}] final latents rel_l2 vs reference fixture (fp32 noise) = {err:.3e}")
-        assert err < 3e-2
+        assert err < TOL_LATENTS
 
 
 def test_pipeline_shared_stg_prefix_is_bit_identical(golden_dir):

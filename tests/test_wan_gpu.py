@@ -67,7 +67,7 @@ def test_wan_forward_vs_reference_fixture(golden_dir):
         assert a.dtype == torch.float32 and tuple(a.shape) == (16, 3, 8, 12)
         e = W.rel_l2(a.cpu(), b)
         print(f"wan forward rel_l2 vs reference = {e:.3e}")
-        assert e < 3e-2
+        assert e < 2e-2
 
 
 def test_unipc_scheduler_vs_oracle():
@@ -112,37 +112,44 @@ def _sp_worker(rank, world, port, golden_dir, ret):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
-        g = _golden(golden_dir)
+        g = torch.load(os.path.join(golden_dir, "wan_t2v_h4.pt"), weights_only=False)     # 4 heads, 96 tokens: splits 2 and 4 ways
         dev = f"cuda:{rank}"
-        sd = W.make_wan_state_dict(g["cfg"], seed=0)
         cfg = g["cfg"]
+        sd = W.make_wan_state_dict(cfg, seed=g["seed_weights"])
         m = WanModel(dim=cfg["dim"], ffn_dim=cfg["ffn_dim"], num_heads=cfg["num_heads"], num_layers=cfg["num_layers"],
                      sp_group=dist.group.WORLD)
         m.load_state_dict(sd, device=dev)
         cos, sin = get_rotary_pos_embed(g["lat"].shape[1:])
         errs = {}
-        for mode in ("p2p", "nccl"):      # fused peer-memory exchange (product path) and the NCCL all-to-all baseline
+        for mode, chunks in (("p2p", 4), ("p2p", 1), ("nccl", 1)):   # fused peer-memory exchange (chunked + overlapped, and in one piece) and the NCCL baseline
             m.sp_exchange = mode
+            if mode == "p2p":
+                ex = m._peer_exchange(2, 96 // world)
+                ex.chunks, ex.min_chunk_rows = chunks, 8              # 48 / 24 local rows: chunk anyway, so the two-stream path is what runs
             for rep in range(3):          # several forwards: the peer buffers / epoch flags are reused across calls
                 y = m([g["lat"].to(dev), g["lat"].to(dev)], t=g["t"].to(dev), context=[g["ctx"].to(dev), g["ctx0"].to(dev)], freqs=(cos, sin))
             torch.cuda.synchronize()
-            errs[mode] = max(W.rel_l2(a.cpu(), b) for a, b in zip(y, g["fwd"]))
+            errs[f"{mode}/{chunks}"] = max(W.rel_l2(a.cpu(), b) for a, b in zip(y, g["fwd"]))
+        m.close()
         ret[rank] = errs
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
-def test_wan_sequence_parallel_two_gpus(golden_dir):
+@pytest.mark.parametrize("world", [2, 4])
+def test_wan_sequence_parallel(golden_dir, world):
+    """Ulysses forward on 2 / 4 GPUs vs the single-GPU output of the unmodified reference (xdit_context_parallel.py:66-192)."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs (gpurun --gpus {world})")
     import torch.multiprocessing as mp
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_sp_worker, args=(2, 29650 + os.getpid() % 300, golden_dir, ret), nprocs=2, join=True)
-    assert len(ret) == 2
+    mp.spawn(_sp_worker, args=(world, 29650 + os.getpid() % 300, golden_dir, ret), nprocs=world, join=True)
+    assert len(ret) == world
     for r, errs in ret.items():
         for mode, e in errs.items():
-            print(f"rank {r}: SP forward ({mode} exchange) rel_l2 vs single-GPU reference = {e:.3e}")
-            assert e < 3e-2
+            print(f"rank {r}: SP{world} forward ({mode} exchange/chunks) rel_l2 vs single-GPU reference = {e:.3e}")
+            assert e < 2e-2
 
 
 def _cfgp_worker(rank, world, port, golden_dir, ret):
@@ -258,11 +265,11 @@ def test_wan_skip_layer_guidance_vs_reference_fixture(golden_dir):
     for a, b in zip(y, g["slg_fwd"]):
         e = W.rel_l2(a.cpu(), b.float())
         print(f"wan SLG joint forward rel_l2 vs reference = {e:.3e}")
-        assert e < 3e-2
+        assert e < 2e-2
     # separate passes (model.py:1078-1079): x_id 0 keeps the block, x_id 1 drops it
     c = m([lat], t=g["t"].to(DEV), context=[ctx], freqs=(cos, sin), slg_layers=g["slg_layers"], x_id=0)[0]
     u = m([lat], t=g["t"].to(DEV), context=[ctx0], freqs=(cos, sin), slg_layers=g["slg_layers"], x_id=1)[0]
-    assert W.rel_l2(c.cpu(), g["slg_fwd"][0].float()) < 3e-2 and W.rel_l2(u.cpu(), g["slg_fwd"][1].float()) < 3e-2
+    assert W.rel_l2(c.cpu(), g["slg_fwd"][0].float()) < 2e-2 and W.rel_l2(u.cpu(), g["slg_fwd"][1].float()) < 2e-2
     plain = m([lat, lat], t=g["t"].to(DEV), context=[ctx, ctx0], freqs=(cos, sin))
     assert W.rel_l2(y[1].cpu(), plain[1].cpu()) > 1e-2                          # the skipped block matters
 
@@ -402,3 +409,27 @@ def test_wan_i2v_end_frame_conditioning():
     lat = pipe.generate(image_start=img, image_end=end, frame_num=9, sampling_steps=2, guide_scale=5.0, context=g["ctx"], context_null=g["ctx0"],
                         clip_fea=g["clip"], seed=3)
     assert lat is not None and tuple(lat.shape) == (16, 4, 8, 12) and torch.isfinite(lat).all()
+
+
+def test_wan_t2v_generate_returns_the_decoded_video(golden_dir):
+    """wan/text2video.py:579-596: `generate` ends with `self.vae.decode(x0, VAE_tile_size)[0]` — [3, F, H, W] fp32 in [-1, 1]; the drop-in
+    does the same when it holds a WanVAE, and still hands back the latents with `return_latents=True` (the parity tests' hook)."""
+    from ltx_video_gpupoor_b200.wan.init_weights import random_wan_vae_decoder_state_dict
+    from ltx_video_gpupoor_b200.wan.vae import WanVAE
+    g = _golden(golden_dir)
+    m, _ = _model(g["cfg"])
+    vae = WanVAE(device=DEV)
+    vae.load_state_dict(random_wan_vae_decoder_state_dict(seed=1), device=DEV)
+    kw = dict(width=96, height=64, frame_num=9, shift=5.0, sampling_steps=2, guide_scale=5.0, cfg_star_switch=False,
+              context=g["ctx"], context_null=g["ctx0"], noise=g["lat"])
+    pipe = WanT2V(m, device=DEV, vae=vae)
+    lat = pipe.generate(return_latents=True, **kw)
+    video = pipe.generate(**kw)
+    torch.cuda.synchronize()
+    assert tuple(lat.shape) == (16, 3, 8, 12) and lat.dtype == torch.float32
+    assert tuple(video.shape) == (3, 9, 64, 96) and video.dtype == torch.float32
+    assert float(video.min()) >= -1.0 and float(video.max()) <= 1.0
+    assert torch.equal(video, vae.decode([lat], 0)[0])
+    assert tuple(WanT2V(m, device=DEV).generate(**kw).shape) == (16, 3, 8, 12)          # no vae: latents, as before
+    out = pipe.generate(return_latent_slice=slice(0, 1), **kw)                           # :578-595
+    assert set(out) == {"x", "latent_slice"} and torch.equal(out["latent_slice"], lat[:, 0:1])

@@ -184,3 +184,37 @@ def test_i2v_oracle_loop_and_product_mask_match_reference_generate_method(golden
         if c["any_end"]:
             lat = lat[:, :-1]
         assert W.rel_l2(lat, c["latents"]) < 5e-5, name
+
+
+def test_seeded_wan_init_is_the_fixture_recipe():
+    """bench.py's in-run sequence-parallel parity check builds its weights with the product-side `seeded_wan_state_dict`; they have to be
+    the weights the reference fixture tests/golden/wan_t2v_h4.pt was recorded with (oracle.make_wan_state_dict), bit for bit."""
+    import torch
+    from ltx_video_gpupoor_b200.wan.init_weights import seeded_wan_state_dict
+    from oracle import wan_oracle as W
+    cfg = dict(W.WAN_1_3B, dim=512, ffn_dim=1280, num_heads=4, num_layers=2)
+    a, b = W.make_wan_state_dict(cfg, seed=0), seeded_wan_state_dict(cfg, seed=0)
+    assert list(a) == list(b) and all(torch.equal(a[k], b[k]) for k in a)
+
+
+def test_teacache_decision_is_taken_on_both_halves_under_cfg_parallel(monkeypatch):
+    """under CFG-parallel the unconditional half only runs x_id = 1 forwards and used to follow a `should_calc` nobody
+    updated.  With `_teacache_every_rank_decides` (set by WanT2V.generate when cfg_parallel is given) both halves take the same
+    skip decisions from the replicated time embedding, and they are the decisions of the single-process x_id = 0 pass."""
+    from ltx_video_gpupoor_b200 import ops
+    from ltx_video_gpupoor_b200.wan.model import WanModel
+    dist_seq = [0.0, 0.04, 0.03, 0.09, 0.02, 0.05, 0.2, 0.01]
+    it = {}
+    monkeypatch.setattr(ops, "rel_l1", lambda a, b: it["seq"].pop(0))
+
+    def run(x_id, every):
+        m = WanModel(dim=256, ffn_dim=512, num_heads=2, num_layers=1)
+        m.enable_teacache, m.rel_l1_thresh, m.teacache_start_step, m.num_steps = True, 0.1, 1, len(dist_seq)
+        m._teacache_every_rank_decides = every
+        it["seq"] = list(dist_seq)[1:] * 2
+        return [m._teacache_should_calc(object(), i, x_id) for i in range(len(dist_seq))]
+
+    cond = run(0, False)
+    assert cond == run(0, True) == run(1, True)          # both CFG-parallel halves == the single-process decision
+    assert False in cond and True in cond
+    assert run(1, False) == [True] * len(dist_seq)       # the old behaviour: the uncond half never skipped
