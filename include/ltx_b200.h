@@ -172,6 +172,12 @@ int ltxb200_pixelnorm_mod_silu_bf16(const void* x, void* y, int64_t voxels, int 
 int ltxb200_latent_to_ndhwc(const void* z, int is_f32, void* out, int B, int C, int64_t FHW, const float* stdv,
                             const float* meanv, void* stream);
 
+/* ltxb200_conv3d_bf16 (NDHWC store) with ResnetBlock3D's next PixelNorm + SiLU (causal_video_autoencoder.py:1212-1240, pixel_norm.py:12)
+ * fused into the epilogue, for Cout <= 256 (one N tile holds the whole channel vector): out2[b,t,h,w,:] =
+ * silu(bf16(y / sqrt(mean_c(y^2) + eps))) with y the row as stored (bf16, after bias and residual).
+ * norm_mode 1: `out` (the raw row: the next block's residual) AND out2;  2: out2 only (`out` may be NULL). */
+int ltxb200_conv3d_norm_bf16(const void* x, const void* w, const void* bias, void* out, void* out2, int B, int T, int H, int W,
+                             int Cin, int Cout, int causal, const void* residual, int norm_mode, float eps, void* stream);
 /* 3x3x3 CAUSAL convolution (two replicated leading frames, zero spatial padding) with output strides stride_t / stride_hw in
  * {1, 2}: x [B,T,H,W,Cin] -> out [B,(T-1)/stride_t+1,(H-1)/stride_hw+1,(W-1)/stride_hw+1,Cout].  The "compress_all/time/space"
  * blocks of the LTX VAE Encoder (causal_video_autoencoder.py:404-447 via make_conv_nd(stride=...)); the TMA descriptor strides

@@ -277,6 +277,10 @@ qk_norm_rope_wan_kernel(__nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict
 // i.e. [N, B, 3, Hp, d] in global token order -- exactly the layout the attention kernel's TMA maps read.
 // grid.y = 3 (q, k, v).  The launch covers rows [row0, row_end) of the M local rows; `signal_ctas` CTAs (of this and the other
 // launches of the same exchange) arrive before the last one publishes the epoch flag on every peer (comm.cuh).
+// Rows are walked grid-stride by a BOUNDED grid (2 CTAs per SM and selector) with the next row's loads in flight: (a) every CTA
+// ends with a system-scope fence that waits for its peer stores to be acknowledged over NVLink, which the round-1 form paid once
+// per 4 rows; (b) a grid of thousands of 128-thread CTAs fills every SM's thread slots, so a GEMM launched next to it on another
+// stream (the next token chunk's QKV projection) could not become resident and the overlap never happened.
 template <int NV>
 __global__ void __launch_bounds__(128)
 qk_norm_rope_wan_scatter_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, int row0, int row_end, const __nv_bfloat16* __restrict__ wq,
@@ -284,14 +288,24 @@ qk_norm_rope_wan_scatter_kernel(const __nv_bfloat16* __restrict__ qkv, long long
                                 const float* __restrict__ sinT, int head_dim, int tokens_per_batch, int token_offset,
                                 float eps, int B, int Hp, const PeerPtrs pp, unsigned int signal_ctas) {
   constexpr int D = NV * 256;
+  constexpr bool kPrefetch = NV <= 8;               // wider rows would not fit two copies in registers
   const int sel = blockIdx.y;                       // 0 q, 1 k, 2 v
-  const int row = row0 + blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  const int stride = gridDim.x * 4;
+  int row = row0 + blockIdx.x * 4 + (threadIdx.x >> 5);
+  const __nv_bfloat16* w = sel == 1 ? wk : wq;
+  const int group_cols = Hp * head_dim;
+  uint4 xv[NV], xn[kPrefetch ? NV : 1];
   if (row < row_end) {
-    const __nv_bfloat16* xr = qkv + row * ld + sel * D;
-    uint4 xv[NV];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) xv[i] = *reinterpret_cast<const uint4*>(xr + (i * 32 + lane) * 8);
+    for (int i = 0; i < NV; ++i) xv[i] = *reinterpret_cast<const uint4*>(qkv + row * ld + sel * D + (i * 32 + lane) * 8);
+  }
+  for (; row < row_end; row += stride) {
+    const int nrow = row + stride;
+    if (kPrefetch && nrow < row_end) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) xn[kPrefetch ? i : 0] = *reinterpret_cast<const uint4*>(qkv + nrow * ld + sel * D + (i * 32 + lane) * 8);
+    }
     const int b = row / tokens_per_batch, n = row - b * tokens_per_batch;
     const long long T = token_offset + n;
     float rs = 1.f;
@@ -306,9 +320,7 @@ qk_norm_rope_wan_scatter_kernel(const __nv_bfloat16* __restrict__ qkv, long long
       }
       rs = rsqrtf(warp_sum(sq) * (1.0f / D) + eps);
     }
-    const __nv_bfloat16* w = sel == 1 ? wk : wq;
     const long long trow = T * head_dim;
-    const int group_cols = Hp * head_dim;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = (i * 32 + lane) * 8;
@@ -335,6 +347,13 @@ qk_norm_rope_wan_scatter_kernel(const __nv_bfloat16* __restrict__ qkv, long long
       const int g = c / group_cols, cc = c - g * group_cols;
       __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(pp.data[g]) + ((T * B + b) * 3 + sel) * group_cols + cc;
       *reinterpret_cast<uint4*>(dst) = r;
+    }
+    if (kPrefetch) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) xv[i] = xn[kPrefetch ? i : 0];
+    } else if (nrow < row_end) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) xv[i] = *reinterpret_cast<const uint4*>(qkv + nrow * ld + sel * D + (i * 32 + lane) * 8);
     }
   }
   peer_signal_done(pp, signal_ctas);

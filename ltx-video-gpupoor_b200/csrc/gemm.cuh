@@ -41,6 +41,12 @@ struct GemmParams {
   long long gate_ld;
   int out_f32;
   int store_mode;
+  // fused PixelNorm (+ SiLU) of the OUTPUT row (row-major store, the whole channel vector in one N tile: N <= BN):
+  //   norm_mode 1: `out` as usual and out2 = silu(pixelnorm(bf16(out row)));   2: only out2 (the raw row is not stored)
+  // (ResnetBlock3D.norm1 / norm2 + non_linearity of the LTX VAE, causal_video_autoencoder.py:1212-1240, in the producing conv)
+  int norm_mode;
+  __nv_bfloat16* out2;             // [M, N] bf16, row stride N
+  float norm_eps;
   // conv geometry (kConv only): activation [B, T, H, W, Cin], tile = BH x BW patch
   int cB, cT, cH, cW, cCin;
   int cBH, cBW;
@@ -67,6 +73,185 @@ struct GemmSmem {
   static constexpr int kBarBytes = 256;
   static constexpr int kTotal = kStages * kStageBytes + kBarBytes + 1024;  // +1024 alignment slack
 };
+
+// Epilogue of one accumulator row (one thread = one TMEM lane = one output row / voxel): BN fp32 columns at t_addr -> bias /
+// activation / gate / residual -> store in the requested layout.  Shared by the GEMM / implicit-GEMM kernel below and the
+// halo-tiled convolution (conv_halo.cuh).
+template <int BN>
+DEVI void epilogue_row(const GemmParams& p, uint32_t t_addr, int tn, bool row_ok, long long m_lin, int ob, int ot, int oh, int ow) {
+  const __nv_bfloat16* gate_row = nullptr;
+  if (p.gate) gate_row = p.gate + (m_lin / p.rows_per_gate) * p.gate_ld;
+  const __nv_bfloat16* res_row = p.residual ? p.residual + m_lin * p.ldr : nullptr;
+  float sumsq = 0.f;
+
+  // One 32-column chunk of the accumulator row: bias / activation / gate / residual / store.  The chunk's TMEM load and its
+  // bias slice were requested one chunk earlier (see the driver loop below), so neither latency is exposed here.
+  auto process = [&](const uint32_t (&v)[32], const uint4 (&bias4)[4], int c0) {
+    const int n0 = tn * BN + c0;
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+    const bool full = (n0 + 32 <= p.N);
+    if (row_ok) {
+      if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          if (full || n0 + j < p.N) {
+            const uint4 bq = bias4[j >> 3];
+            const float2 b0 = unpack_bf16(bq.x), b1 = unpack_bf16(bq.y), b2 = unpack_bf16(bq.z), b3 = unpack_bf16(bq.w);
+            f[j] += b0.x; f[j + 1] += b0.y; f[j + 2] += b1.x; f[j + 3] += b1.y;
+            f[j + 4] += b2.x; f[j + 5] += b2.y; f[j + 6] += b3.x; f[j + 7] += b3.y;
+          }
+        }
+      }
+      if (p.act == kActGeluTanh) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = gelu_tanh(f[j]);
+      } else if (p.act == kActSilu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __fdividef(f[j], 1.0f + __expf(-f[j]));
+      } else if (p.act == kActGeluErf) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+      }
+      if (gate_row) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          if (full || n0 + j < p.N) {
+            const uint4 gq = *reinterpret_cast<const uint4*>(gate_row + n0 + j);
+            const float2 g0 = unpack_bf16(gq.x), g1 = unpack_bf16(gq.y), g2 = unpack_bf16(gq.z), g3 = unpack_bf16(gq.w);
+            f[j] *= g0.x; f[j + 1] *= g0.y; f[j + 2] *= g1.x; f[j + 3] *= g1.y;
+            f[j + 4] *= g2.x; f[j + 5] *= g2.y; f[j + 6] *= g3.x; f[j + 7] *= g3.y;
+          }
+        }
+      }
+      if (res_row) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          if (full || n0 + j < p.N) {
+            const uint4 rq = *reinterpret_cast<const uint4*>(res_row + n0 + j);
+            const float2 r0 = unpack_bf16(rq.x), r1 = unpack_bf16(rq.y), r2 = unpack_bf16(rq.z), r3 = unpack_bf16(rq.w);
+            f[j] += r0.x; f[j + 1] += r0.y; f[j + 2] += r1.x; f[j + 3] += r1.y;
+            f[j + 4] += r2.x; f[j + 5] += r2.y; f[j + 6] += r3.x; f[j + 7] += r3.y;
+          }
+        }
+      }
+    }
+    if (p.norm_mode) {                         // warp-uniform; the TMEM store is warp-collective, so rows outside the tensor take part too
+      // the statistic is taken over the values as they are stored (bf16), like the standalone kernel that read them back
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        f[j] = __bfloat162float(__float2bfloat16_rn(f[j]));
+        if (full || n0 + j < p.N) sumsq = fmaf(f[j], f[j], sumsq);
+      }
+      uint32_t wb[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) wb[j] = __float_as_uint(f[j]);
+      tmem_st32(t_addr + c0, wb);              // kept in the accumulator's own columns for the second pass
+    }
+    if (row_ok && p.norm_mode != 2) {
+      // ---- store ----
+      if (p.store_mode == kStoreRowMajor) {
+        if (p.out_f32) {
+          float* o = reinterpret_cast<float*>(p.out) + m_lin * p.ldc + n0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            if (full || n0 + j < p.N) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+        } else {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + m_lin * p.ldc + n0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8)
+            if (full || n0 + j < p.N)
+              *reinterpret_cast<uint4*>(o + j) = make_uint4(pack_bf16(f[j], f[j + 1]), pack_bf16(f[j + 2], f[j + 3]),
+                                                            pack_bf16(f[j + 4], f[j + 5]), pack_bf16(f[j + 6], f[j + 7]));
+        }
+      } else if (p.store_mode == kStoreConvD2S) {
+        // N = 8*C, channel n = ((p1*2+p2)*2+p3)*C + c  ->  out[b, 2t+p1-1, 2h+p2, 2w+p3, c]  (NDHWC, T' = 2T-1)
+        const int C = p.N >> 3;
+        const int q = n0 / C, c = n0 - q * C;             // 32-col chunk never straddles (C % 32 == 0)
+        const int p1 = q >> 2, p2 = (q >> 1) & 1, p3 = q & 1;
+        const int t2 = 2 * ot + p1 - 1;
+        if (t2 >= 0) {
+          const long long vox = ((static_cast<long long>(ob) * (2 * p.cT - 1) + t2) * (2 * p.cH) + (2 * oh + p2)) * (2 * p.cW) + (2 * ow + p3);
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + vox * C + c;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8)
+            *reinterpret_cast<uint4*>(o + j) = make_uint4(pack_bf16(f[j], f[j + 1]), pack_bf16(f[j + 2], f[j + 3]),
+                                                          pack_bf16(f[j + 4], f[j + 5]), pack_bf16(f[j + 6], f[j + 7]));
+        }
+      } else {
+        // kStoreConvUnpatch: N = Cimg*16, n = (c*4+q)*4 + r -> out[b, c, t, 4h+q, 4w+r]  (NCFHW, fp32 or bf16)
+        const long long HW4 = static_cast<long long>(4 * p.cH) * (4 * p.cW);
+        const int Cimg = p.N >> 4;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const int n = n0 + j;
+          if (n < p.N) {
+            const int c = n >> 4, q = (n >> 2) & 3;
+            const long long off = ((static_cast<long long>(ob) * Cimg + c) * p.cT + ot) * HW4 +
+                                  static_cast<long long>(4 * oh + q) * (4 * p.cW) + 4 * ow;
+            if (p.out_f32)
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            else
+              *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off) =
+                  make_uint2(pack_bf16(f[j], f[j + 1]), pack_bf16(f[j + 2], f[j + 3]));
+          }
+        }
+      }
+    }
+  };
+  auto load_bias = [&](uint4 (&bias4)[4], int c0) {
+    const int n0 = tn * BN + c0;
+    if (p.bias) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8)
+        if (n0 + j < p.N) bias4[j >> 3] = __ldg(reinterpret_cast<const uint4*>(p.bias + n0 + j));
+    }
+  };
+  // driver: two chunks per iteration on alternating register sets; while chunk c is processed the TMEM load and the bias
+  // slice of chunk c+1 are in flight (tcgen05.wait::ld covers every outstanding load, so the next one is issued after it)
+  const int ncols = (p.N - tn * BN) < BN ? (p.N - tn * BN) : BN;          // warp-uniform
+  uint32_t va[32], vb[32];
+  uint4 ba[4], bb[4];
+  tmem_ld32(t_addr, va);
+  load_bias(ba, 0);
+#pragma unroll 1
+  for (int c0 = 0; c0 < ncols; c0 += 64) {
+    tmem_wait_ld();
+    if (c0 + 32 < ncols) { tmem_ld32(t_addr + c0 + 32, vb); load_bias(bb, c0 + 32); }
+    process(va, ba, c0);
+    if (c0 + 32 < ncols) {
+      tmem_wait_ld();
+      if (c0 + 64 < ncols) { tmem_ld32(t_addr + c0 + 64, va); load_bias(ba, c0 + 64); }
+      process(vb, bb, c0 + 32);
+    }
+  }
+  if (p.norm_mode) {
+    // second pass: x * rsqrt(mean(x^2) + eps) -> bf16 -> SiLU -> out2, from the rounded values parked in TMEM
+    tmem_wait_st();
+    const float inv = 1.0f / sqrtf(sumsq / static_cast<float>(p.N) + p.norm_eps);
+    __nv_bfloat16* o2 = p.out2 + m_lin * p.N;
+#pragma unroll 1
+    for (int c0 = 0; c0 < ncols; c0 += 32) {
+      tmem_ld32(t_addr + c0, va);
+      tmem_wait_ld();
+      if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          if (c0 + j < p.N) {
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float t = __bfloat162float(__float2bfloat16_rn(__uint_as_float(va[j + e]) * inv));
+              o[e] = __fdividef(t, 1.0f + __expf(-t));
+            }
+            *reinterpret_cast<uint4*>(o2 + c0 + j) = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+          }
+        }
+      }
+    }
+  }
+}
 
 // kCtas = 2: the tile is 256 x BN on a CTA PAIR (for the convolution: two consecutive 128-voxel patches) (cluster of 2, tcgen05 cta_group::2).  Each CTA loads its 128 rows
 // of A and half of the B tile (so the shared-memory fill and operand traffic per SM drop by a third), the leader issues
@@ -244,138 +429,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         m_lin = static_cast<long long>(tm) * kGemmBM + row_in_tile;
         row_ok = m_lin < p.M;
       }
-      const __nv_bfloat16* gate_row = nullptr;
-      if (p.gate) gate_row = p.gate + (m_lin / p.rows_per_gate) * p.gate_ld;
-      const __nv_bfloat16* res_row = p.residual ? p.residual + m_lin * p.ldr : nullptr;
-
-      // One 32-column chunk of the accumulator row: bias / activation / gate / residual / store.  The chunk's TMEM load and its
-      // bias slice were requested one chunk earlier (see the driver loop below), so neither latency is exposed here.
-      auto process = [&](const uint32_t (&v)[32], const uint4 (&bias4)[4], int c0) {
-        const int n0 = tn * BN + c0;
-        if (row_ok) {
-          float f[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          const bool full = (n0 + 32 <= p.N);
-          if (p.bias) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (full || n0 + j < p.N) {
-                const uint4 bq = bias4[j >> 3];
-                const float2 b0 = unpack_bf16(bq.x), b1 = unpack_bf16(bq.y), b2 = unpack_bf16(bq.z), b3 = unpack_bf16(bq.w);
-                f[j] += b0.x; f[j + 1] += b0.y; f[j + 2] += b1.x; f[j + 3] += b1.y;
-                f[j + 4] += b2.x; f[j + 5] += b2.y; f[j + 6] += b3.x; f[j + 7] += b3.y;
-              }
-            }
-          }
-          if (p.act == kActGeluTanh) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = gelu_tanh(f[j]);
-          } else if (p.act == kActSilu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __fdividef(f[j], 1.0f + __expf(-f[j]));
-          } else if (p.act == kActGeluErf) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-          }
-          if (gate_row) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (full || n0 + j < p.N) {
-                const uint4 gq = *reinterpret_cast<const uint4*>(gate_row + n0 + j);
-                const float2 g0 = unpack_bf16(gq.x), g1 = unpack_bf16(gq.y), g2 = unpack_bf16(gq.z), g3 = unpack_bf16(gq.w);
-                f[j] *= g0.x; f[j + 1] *= g0.y; f[j + 2] *= g1.x; f[j + 3] *= g1.y;
-                f[j + 4] *= g2.x; f[j + 5] *= g2.y; f[j + 6] *= g3.x; f[j + 7] *= g3.y;
-              }
-            }
-          }
-          if (res_row) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (full || n0 + j < p.N) {
-                const uint4 rq = *reinterpret_cast<const uint4*>(res_row + n0 + j);
-                const float2 r0 = unpack_bf16(rq.x), r1 = unpack_bf16(rq.y), r2 = unpack_bf16(rq.z), r3 = unpack_bf16(rq.w);
-                f[j] += r0.x; f[j + 1] += r0.y; f[j + 2] += r1.x; f[j + 3] += r1.y;
-                f[j + 4] += r2.x; f[j + 5] += r2.y; f[j + 6] += r3.x; f[j + 7] += r3.y;
-              }
-            }
-          }
-          // ---- store ----
-          if (p.store_mode == kStoreRowMajor) {
-            if (p.out_f32) {
-              float* o = reinterpret_cast<float*>(p.out) + m_lin * p.ldc + n0;
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                if (full || n0 + j < p.N) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-            } else {
-              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + m_lin * p.ldc + n0;
-#pragma unroll
-              for (int j = 0; j < 32; j += 8)
-                if (full || n0 + j < p.N)
-                  *reinterpret_cast<uint4*>(o + j) = make_uint4(pack_bf16(f[j], f[j + 1]), pack_bf16(f[j + 2], f[j + 3]),
-                                                                pack_bf16(f[j + 4], f[j + 5]), pack_bf16(f[j + 6], f[j + 7]));
-            }
-          } else if (p.store_mode == kStoreConvD2S) {
-            // N = 8*C, channel n = ((p1*2+p2)*2+p3)*C + c  ->  out[b, 2t+p1-1, 2h+p2, 2w+p3, c]  (NDHWC, T' = 2T-1)
-            const int C = p.N >> 3;
-            const int q = n0 / C, c = n0 - q * C;             // 32-col chunk never straddles (C % 32 == 0)
-            const int p1 = q >> 2, p2 = (q >> 1) & 1, p3 = q & 1;
-            const int t2 = 2 * ot + p1 - 1;
-            if (t2 >= 0) {
-              const long long vox = ((static_cast<long long>(ob) * (2 * p.cT - 1) + t2) * (2 * p.cH) + (2 * oh + p2)) * (2 * p.cW) + (2 * ow + p3);
-              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + vox * C + c;
-#pragma unroll
-              for (int j = 0; j < 32; j += 8)
-                *reinterpret_cast<uint4*>(o + j) = make_uint4(pack_bf16(f[j], f[j + 1]), pack_bf16(f[j + 2], f[j + 3]),
-                                                              pack_bf16(f[j + 4], f[j + 5]), pack_bf16(f[j + 6], f[j + 7]));
-            }
-          } else {
-            // kStoreConvUnpatch: N = Cimg*16, n = (c*4+q)*4 + r -> out[b, c, t, 4h+q, 4w+r]  (NCFHW, fp32 or bf16)
-            const long long HW4 = static_cast<long long>(4 * p.cH) * (4 * p.cW);
-            const int Cimg = p.N >> 4;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const int n = n0 + j;
-              if (n < p.N) {
-                const int c = n >> 4, q = (n >> 2) & 3;
-                const long long off = ((static_cast<long long>(ob) * Cimg + c) * p.cT + ot) * HW4 +
-                                      static_cast<long long>(4 * oh + q) * (4 * p.cW) + 4 * ow;
-                if (p.out_f32)
-                  *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                else
-                  *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off) =
-                      make_uint2(pack_bf16(f[j], f[j + 1]), pack_bf16(f[j + 2], f[j + 3]));
-              }
-            }
-          }
-        }
-      };
-      auto load_bias = [&](uint4 (&bias4)[4], int c0) {
-        const int n0 = tn * BN + c0;
-        if (p.bias) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8)
-            if (n0 + j < p.N) bias4[j >> 3] = __ldg(reinterpret_cast<const uint4*>(p.bias + n0 + j));
-        }
-      };
-      // driver: two chunks per iteration on alternating register sets; while chunk c is processed the TMEM load and the bias
-      // slice of chunk c+1 are in flight (tcgen05.wait::ld covers every outstanding load, so the next one is issued after it)
-      const int ncols = (p.N - tn * BN) < BN ? (p.N - tn * BN) : BN;          // warp-uniform
-      uint32_t va[32], vb[32];
-      uint4 ba[4], bb[4];
-      tmem_ld32(t_addr, va);
-      load_bias(ba, 0);
-#pragma unroll 1
-      for (int c0 = 0; c0 < ncols; c0 += 64) {
-        tmem_wait_ld();
-        if (c0 + 32 < ncols) { tmem_ld32(t_addr + c0 + 32, vb); load_bias(bb, c0 + 32); }
-        process(va, ba, c0);
-        if (c0 + 32 < ncols) {
-          tmem_wait_ld();
-          if (c0 + 64 < ncols) { tmem_ld32(t_addr + c0 + 64, va); load_bias(ba, c0 + 64); }
-          process(vb, bb, c0 + 32);
-        }
-      }
+      epilogue_row<BN>(p, t_addr, tn, row_ok, m_lin, ob, ot, oh, ow);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {

@@ -8,6 +8,7 @@
 #include "attention.cuh"
 #include "comm.cuh"
 #include "common.cuh"
+#include "conv_halo.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
 #include "tensormap.h"
@@ -95,6 +96,21 @@ static int launch_gemm_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const 
   return launch_status();
 }
 
+// halo-tiled convolution (conv_halo.cuh): one CTA per SM, persistent over 16x16 patches
+template <int BN>
+static int launch_conv_halo(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_tiles, cudaStream_t st) {
+  using S = ConvHaloSmem<BN>;
+  static bool configured = false;
+  auto kern = conv3d_halo_kernel<BN>;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal) != cudaSuccess) return kErrCuda;
+    configured = true;
+  }
+  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  kern<<<grid, kGemmThreads, S::kTotal, st>>>(ta, tb, p);
+  return launch_status();
+}
+
 extern "C" int ltxb200_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K,
                                  void* out, int64_t ldc, int out_f32, const void* bias, int act,
                                  const void* residual, int64_t ldr, const void* gate, int64_t gate_ld,
@@ -144,7 +160,14 @@ extern "C" int ltxb200_gemm_bf16(const void* A, int64_t lda, const void* W, int6
 // x: [B, Tin, Hin, Win, Cin]; out: [B, T, H, W, Cout] with T = (Tin - 1) / st + 1 etc. (st, shw = output strides)
 static int conv_impl(const void* x, const void* w, const void* bias, void* out, int B, int Tin, int Hin, int Win, int Cin, int Cout,
                      int taps_t, int taps_hw, int causal, int tpad_zero, int store_mode, int out_f32, const void* residual,
-                     void* stream, int st_t = 1, int st_hw = 1, int off_hw = 0) {
+                     void* stream, int st_t = 1, int st_hw = 1, int off_hw = 0, int norm_mode = 0, void* out2 = nullptr,
+                     float norm_eps = 0.f) {
+  if (norm_mode) {      // fused PixelNorm + SiLU second output: one N tile must hold the whole channel vector
+    if ((norm_mode != 1 && norm_mode != 2) || !out2 || !aligned16(out2) || Cout > 256 || store_mode != LTXB200_CONV_STORE_NDHWC || out_f32)
+      return kErrUnsupported;
+    if (norm_mode == 1 && !out) return kErrBadAlign;
+    if (norm_mode == 2 && !out) out = out2;           // never written; keeps the pointer checks below uniform
+  }
   if (B <= 0 || Tin <= 0 || Hin <= 0 || Win <= 0 || (Cin % 64) || (Cout & 7)) return kErrBadShape;
   if ((st_t != 1 && st_t != 2) || (st_hw != 1 && st_hw != 2)) return kErrUnsupported;
   if ((st_t != 1 || st_hw != 1) && (!causal || store_mode != LTXB200_CONV_STORE_NDHWC || residual)) return kErrUnsupported;
@@ -157,6 +180,48 @@ static int conv_impl(const void* x, const void* w, const void* bias, void* out, 
   if (store_mode == LTXB200_CONV_STORE_D2S && ((Cout % 8) || ((Cout / 8) % 32))) return kErrBadShape;
   if (store_mode == LTXB200_CONV_STORE_UNPATCH && (Cout % 16)) return kErrBadShape;
   if (store_mode != LTXB200_CONV_STORE_NDHWC && residual) return kErrUnsupported;
+  // Narrow outputs (Cout <= 128) with 3x3 spatial taps and unit stride: the halo-tiled kernel (conv_halo.cuh), which re-uses every
+  // activation box for three taps and every weight tile for two 128-voxel halves (the plain implicit GEMM is bound by L2 -> SM
+  // traffic at these shapes: profiles/r02_ncu_summary.md).  LTXB200_CONV_HALO=0 keeps the plain kernel (A/B, tests).
+  const char* eh = getenv("LTXB200_CONV_HALO");
+  const int env_halo = eh ? atoi(eh) : 1;
+  if (env_halo && taps_hw == 3 && st_t == 1 && st_hw == 1 && off_hw == 0 && Cout <= 128) {
+    const int taps = taps_t * 9;
+    const int BNh = Cout <= 64 ? 64 : 128;
+    CUtensorMap ta, tb;
+    {
+      uint64_t dims[5] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(Win), static_cast<uint64_t>(Hin),
+                          static_cast<uint64_t>(Tin), static_cast<uint64_t>(B)};
+      uint64_t str[4] = {static_cast<uint64_t>(Cin) * 2, static_cast<uint64_t>(Win) * Cin * 2,
+                         static_cast<uint64_t>(Hin) * Win * Cin * 2, static_cast<uint64_t>(Tin) * Hin * Win * Cin * 2};
+      uint32_t box[5] = {kGemmBK, kHaloTile, kHaloTile + 2, 1, 1};
+      if (make_tmap_bf16(&ta, x, 5, dims, str, box)) return kErrTensorMap;
+    }
+    {
+      uint64_t dims[2] = {static_cast<uint64_t>(taps) * Cin, static_cast<uint64_t>(Cout)};
+      uint64_t str[1] = {static_cast<uint64_t>(taps) * Cin * 2};
+      uint32_t box[2] = {kGemmBK, static_cast<uint32_t>(BNh)};
+      if (make_tmap_bf16(&tb, w, 2, dims, str, box)) return kErrTensorMap;
+    }
+    GemmParams p{};
+    p.M = B * T * H * W; p.N = Cout; p.K = taps * Cin;
+    p.out = out; p.ldc = Cout; p.out_f32 = out_f32;
+    p.bias = static_cast<const __nv_bfloat16*>(bias);
+    p.act = kActNone;
+    p.residual = static_cast<const __nv_bfloat16*>(residual); p.ldr = Cout;
+    p.gate = nullptr; p.rows_per_gate = 1;
+    p.store_mode = store_mode == LTXB200_CONV_STORE_NDHWC ? kStoreRowMajor
+                   : (store_mode == LTXB200_CONV_STORE_D2S ? kStoreConvD2S : kStoreConvUnpatch);
+    p.cB = B; p.cT = T; p.cH = H; p.cW = W; p.cCin = Cin; p.cBH = kHaloTile; p.cBW = kHaloTile;
+    p.c_tiles_h = (H + kHaloTile - 1) / kHaloTile; p.c_tiles_w = (W + kHaloTile - 1) / kHaloTile;
+    p.c_causal = causal ? 1 : 0; p.c_taps_t = taps_t; p.c_taps_hw = 3; p.c_tpad_zero = tpad_zero ? 1 : 0;
+    p.c_st = 1; p.c_shw = 1; p.cTin = Tin; p.c_off_hw = 0;
+    p.norm_mode = norm_mode; p.out2 = static_cast<__nv_bfloat16*>(out2); p.norm_eps = norm_eps;
+    const long long tiles = static_cast<long long>(B) * T * p.c_tiles_h * p.c_tiles_w;
+    if (tiles > 0x7fffffffLL) return kErrBadShape;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return BNh == 64 ? launch_conv_halo<64>(ta, tb, p, static_cast<int>(tiles), st) : launch_conv_halo<128>(ta, tb, p, static_cast<int>(tiles), st);
+  }
   // pick the 128-voxel patch shape with the least padding
   static const int shapes[8][2] = {{8, 16}, {16, 8}, {4, 32}, {32, 4}, {2, 64}, {64, 2}, {1, 128}, {128, 1}};
   int best = 0;
@@ -205,6 +270,7 @@ static int conv_impl(const void* x, const void* w, const void* bias, void* out, 
   p.c_tiles_h = (H + BH - 1) / BH; p.c_tiles_w = (W + BW - 1) / BW;
   p.c_causal = causal ? 1 : 0; p.c_taps_t = taps_t; p.c_taps_hw = taps_hw; p.c_tpad_zero = tpad_zero ? 1 : 0;
   p.c_st = st_t; p.c_shw = st_hw; p.cTin = Tin; p.c_off_hw = off_hw;
+  p.norm_mode = norm_mode; p.out2 = static_cast<__nv_bfloat16*>(out2); p.norm_eps = norm_eps;
   p.n_fastest = (static_cast<long long>(Cout) * taps * Cin * 2 <= (48ll << 20)) ? 1 : 0;
   if (const char* e = getenv("LTXB200_GEMM_RASTER")) p.n_fastest = atoi(e);
   const int patches = B * T * p.c_tiles_h * p.c_tiles_w;
@@ -221,6 +287,14 @@ extern "C" int ltxb200_conv3d_bf16(const void* x, const void* w, const void* bia
                                    int W, int Cin, int Cout, int causal, int store_mode, int out_f32,
                                    const void* residual, void* stream) {
   return conv_impl(x, w, bias, out, B, T, H, W, Cin, Cout, 3, 3, causal, 0, store_mode, out_f32, residual, stream);
+}
+
+extern "C" int ltxb200_conv3d_norm_bf16(const void* x, const void* w, const void* bias, void* out, void* out2, int B, int T, int H,
+                                        int W, int Cin, int Cout, int causal, const void* residual, int norm_mode, float eps,
+                                        void* stream) {
+  if (norm_mode != 1 && norm_mode != 2) return kErrBadShape;
+  return conv_impl(x, w, bias, out, B, T, H, W, Cin, Cout, 3, 3, causal, 0, LTXB200_CONV_STORE_NDHWC, 0, residual, stream, 1, 1, 0,
+                   norm_mode, out2, eps);
 }
 
 extern "C" int ltxb200_conv3d_strided_bf16(const void* x, const void* w, const void* bias, void* out, int B, int T, int H, int W,
@@ -379,8 +453,13 @@ extern "C" int ltxb200_peer_allgather(const void* src, int64_t seg_bytes, int ns
   return launch_status();
 }
 
-// CTAs one launch over `rows` rows contributes to the arrival counter
-static inline unsigned int scatter_ctas(int rows) { return static_cast<unsigned int>((rows + 3) / 4) * 3u; }
+// grid.x of one scatter launch over `rows` rows (grid-stride: at most 2 CTAs of 4 warps per SM and selector), and the CTAs it
+// contributes to the arrival counter (x 3 selectors)
+static inline unsigned int scatter_blocks(int rows) {
+  const unsigned int want = static_cast<unsigned int>((rows + 3) / 4), cap = static_cast<unsigned int>(num_sms()) * 2u;
+  return want < cap ? want : cap;
+}
+static inline unsigned int scatter_ctas(int rows) { return scatter_blocks(rows) * 3u; }
 
 extern "C" int ltxb200_qk_norm_rope_wan_scatter_rows_bf16(const void* qkv, int64_t ld, int M, int row0, int rows, int D, const void* wq,
                                                           const void* wk, const float* cos_table, const float* sin_table,
@@ -395,7 +474,7 @@ extern "C" int ltxb200_qk_norm_rope_wan_scatter_rows_bf16(const void* qkv, int64
   PeerPtrs pp;
   if (int rc = fill_peers(&pp, P, rank, recv_ptrs, flag_ptrs, epoch, counter)) return rc;
   const int Hp = D / head_dim / P;
-  dim3 grid((rows + 3) / 4, 3);
+  dim3 grid(scatter_blocks(rows), 3);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   auto X = static_cast<const __nv_bfloat16*>(qkv);
   auto WQ = static_cast<const __nv_bfloat16*>(wq);

@@ -268,16 +268,11 @@ class CausalVideoAutoencoder(ModuleLike):
         xp[..., : C * ps * ps] = (x.to(self.device, torch.float32).view(B, C, Fr, h, ps, wd, ps)
                                   .permute(0, 2, 3, 5, 1, 6, 4).reshape(B, Fr, h, wd, C * ps * ps).to(BF16))
         y = ops.conv3d(xp, *w["enc.conv_in"], causal=True)
-        for kind, idx, cin, cout, n in self.enc_plan:
-            p = f"encoder.down_blocks.{idx}."
-            if kind == "res_x":
-                for j in range(n):
-                    y = self._resnet(y, w[p + f"{j}.conv1"], w[p + f"{j}.conv2"], True)
-            elif kind == "res_x_y":
-                y = self._resnet(y, w[p + "conv1"], w[p + "conv2"], True, w[p + "shortcut"], w[p + "norm3"])
-            else:
-                y = ops.conv3d_strided(y, *w[p + "conv"], stride_t=2, stride_hw=2)
-        y = ops.conv3d(ops.pixelnorm_silu(y), *w["enc.conv_out"], causal=True)            # [B, F', H', W', 136]
+        y, yn = self._run_blocks(y, self.enc_plan, "encoder.down_blocks.", True, None,
+                                 lambda t, p: ops.conv3d_strided(t, *w[p + "conv"], stride_t=2, stride_hw=2))
+        if yn is None:
+            yn = ops.pixelnorm_silu(y)
+        y = ops.conv3d(yn, *w["enc.conv_out"], causal=True)                               # [B, F', H', W', 136]
         lc = self._cfg["latent_channels"]
         mom = y[..., : lc + 1].permute(0, 4, 1, 2, 3).float()
         return mom[:, :lc].contiguous(), mom[:, lc:].contiguous()
@@ -295,21 +290,63 @@ class CausalVideoAutoencoder(ModuleLike):
         """PixArtAlphaCombinedTimestepSizeEmbeddings(dim, 0): Timesteps(256) -> Linear -> SiLU -> Linear; t [1] fp32 -> [1, dim]"""
         return ops.gemm(ops.gemm(ops.timestep_embed(t, 256), tw[0], tw[1], act=ops.ACT_SILU), tw[2], tw[3])
 
-    def _resnet(self, x, c1, c2, causal, shortcut=None, norm3=None, ada=None):
+    @staticmethod
+    def _conv_want(h, c, causal, residual, want):
+        """One convolution of a res block and the PixelNorm + SiLU of its OUTPUT (the next convolution's input), fused into the conv's
+        epilogue when one N tile holds the whole channel vector (Cout <= 256).  want: "raw" -> (y, None); "both" -> (y, silu(pn(y)));
+        "norm" -> (None, silu(pn(y))) (the raw row is never written)."""
+        if want == "raw":
+            return ops.conv3d(h, c[0], c[1], causal=causal, residual=residual), None
+        if c[0].shape[0] > 256:
+            y = ops.conv3d(h, c[0], c[1], causal=causal, residual=residual)
+            return (y if want == "both" else None), ops.pixelnorm_silu(y)
+        return ops.conv3d_norm(h, c[0], c[1], causal=causal, residual=residual, keep_raw=(want == "both"))
+
+    def _resnet(self, x, c1, c2, causal, shortcut=None, norm3=None, ada=None, xn=None, want="raw"):
         """ResnetBlock3D.forward (causal_video_autoencoder.py:1197-1258); `ada` [4, C] = scale_shift_table + timestep embedding
-        (shift1, scale1, shift2, scale2) for timestep-conditioned decoders (:1212-1237)."""
+        (shift1, scale1, shift2, scale2) for timestep-conditioned decoders (:1212-1237).  `xn` = silu(pixelnorm(x)) when the kernel that
+        produced x already wrote it; returns (y, silu(pixelnorm(y))) as `want` asks (see _conv_want)."""
         if ada is not None:
             h = ops.conv3d(ops.pixelnorm_silu(x, scale=ada[1], shift=ada[0]), c1[0], c1[1], causal=causal)
             h = ops.pixelnorm_silu(h, scale=ada[3], shift=ada[2])
-            return ops.conv3d(h, c2[0], c2[1], causal=causal, residual=x)
-        h = ops.conv3d(ops.pixelnorm_silu(x), c1[0], c1[1], causal=causal)
-        h = ops.pixelnorm_silu(h)
+            return ops.conv3d(h, c2[0], c2[1], causal=causal, residual=x), None
+        if xn is None:
+            xn = ops.pixelnorm_silu(x)
+        _, hn = self._conv_want(xn, c1, causal, None, "norm")                      # norm2 + SiLU of conv1's output, in conv1's epilogue
         res = x
         if shortcut is not None:
             B, T, H, W, C = x.shape
             xs = ops.norm_mod(x.view(-1, C), weight=norm3[0], bias=norm3[1], eps=1e-6, layer_norm=True)
             res = ops.gemm(xs, shortcut[0], shortcut[1]).view(B, T, H, W, -1)
-        return ops.conv3d(h, c2[0], c2[1], causal=causal, residual=res)
+        return self._conv_want(hn, c2, causal, res, want)                           # + the NEXT block's norm1 + SiLU
+
+    def _run_blocks(self, x, plan, prefix, causal, ada_fn, resample_fn, head_want="norm"):
+        """The res-block / resample sequence of the encoder or decoder.  Every block is told what its consumer reads: the next res block
+        needs the raw tensor (residual) and its PixelNorm + SiLU, a resampling convolution only the raw tensor, the output head only
+        the normalised one.  -> (x | None, silu(pixelnorm(x)))"""
+        w = self.w
+        flat = []
+        for kind, idx, cin, cout, n in plan:
+            p = f"{prefix}{idx}."
+            if kind == "res_x":
+                flat += [("res", p, j, n, cin) for j in range(n)]
+            elif kind == "res_x_y":
+                flat.append(("resxy", p, 0, 1, cin))
+            else:
+                flat.append(("resample", p, 0, 1, cin))
+        xn = None
+        for i, (kind, p, j, n, cin) in enumerate(flat):
+            nxt = flat[i + 1][0] if i + 1 < len(flat) else "head"
+            want = "raw" if nxt == "resample" else (head_want if nxt == "head" else "both")
+            if kind == "resample":
+                x, xn = resample_fn(x, p), None
+                continue
+            ada = ada_fn(p, n, cin)[j] if (ada_fn is not None and kind == "res") else None
+            if kind == "res":
+                x, xn = self._resnet(x, w[p + f"{j}.conv1"], w[p + f"{j}.conv2"], causal, ada=ada, xn=xn, want=want)
+            else:
+                x, xn = self._resnet(x, w[p + "conv1"], w[p + "conv2"], causal, w[p + "shortcut"], w[p + "norm3"], xn=xn, want=want)
+        return x, xn
 
     def _decode(self, z: torch.Tensor, target_shape=None, timestep=None, per_channel_normalize: bool = False,
                 out_f32: bool = False) -> torch.Tensor:
@@ -331,22 +368,22 @@ class CausalVideoAutoencoder(ModuleLike):
                 raise NotImplementedError("timestep-conditioned decode handles one video per call")
             ts = (torch.as_tensor(timestep, dtype=torch.float32).flatten()[:1] * self.timestep_scale_multiplier).to(self.device)
         x = ops.conv3d(x, *w["conv_in"], causal=causal)
-        for kind, idx, cin, cout, n in self.plan:
-            p = f"decoder.up_blocks.{idx}."
-            if kind == "res_x":
-                ada = ops.ada_add(w[p + "sst"], self._time_embed(ts, w[p + "temb"])).view(n, 4, cin) if tc else None
-                for j in range(n):
-                    x = self._resnet(x, w[p + f"{j}.conv1"], w[p + f"{j}.conv2"], causal, ada=ada[j] if tc else None)
-            elif kind == "res_x_y":
-                x = self._resnet(x, w[p + "conv1"], w[p + "conv2"], causal, w[p + "shortcut"], w[p + "norm3"])
-            else:
-                x = ops.conv3d(x, *w[p + "conv"], causal=causal, store=ops.CONV_D2S)
+        ada_cache = {}
+
+        def ada_fn(p, n, cin):          # UNetMidBlock3D: one timestep embedding per stage + per-block tables (:850-853, 1207-1210)
+            if p not in ada_cache:
+                ada_cache[p] = ops.ada_add(w[p + "sst"], self._time_embed(ts, w[p + "temb"])).view(n, 4, cin)
+            return ada_cache[p]
+
+        x, xn = self._run_blocks(x, self.plan, "decoder.up_blocks.", causal, ada_fn if tc else None,
+                                 lambda t, p: ops.conv3d(t, *w[p + "conv"], causal=causal, store=ops.CONV_D2S),
+                                 head_want="raw" if tc else "norm")      # the conditioned head modulates the norm: it reads the raw tensor
         if tc:                                                                         # :773-797
             ada = ops.ada_add(w["last_sst"], self._time_embed(ts, w["last_temb"])).view(2, -1)
-            x = ops.pixelnorm_silu(x, scale=ada[1], shift=ada[0])
-        else:
-            x = ops.pixelnorm_silu(x)
-        return ops.conv3d(x, *w["conv_out"], causal=causal, store=ops.CONV_UNPATCH, out_f32=out_f32)
+            xn = ops.pixelnorm_silu(x, scale=ada[1], shift=ada[0])
+        elif xn is None:
+            xn = ops.pixelnorm_silu(x)
+        return ops.conv3d(xn, *w["conv_out"], causal=causal, store=ops.CONV_UNPATCH, out_f32=out_f32)
 
     def decode(self, z: torch.Tensor, return_dict: bool = True, target_shape=None, timestep=None):
         """vae.py:357-413 (tiling branches are low-VRAM workarounds and are not needed on 180 GB)."""

@@ -108,6 +108,26 @@ def conv3d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], causa
     return out
 
 
+def conv3d_norm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], causal: bool = False,
+                residual: Optional[torch.Tensor] = None, keep_raw: bool = True, eps: float = 1e-8):
+    """conv3d (NDHWC) whose epilogue also writes silu(pixelnorm(y)) of its own output row (Cout <= 256): returns (y | None, y_norm).
+    keep_raw=False skips the raw output (it is only needed as the next block's residual)."""
+    _req(x, name="x"); _req(w, name="w")
+    assert x.is_contiguous() and w.is_contiguous() and x.dim() == 5
+    B, T, H, W, Cin = x.shape
+    Cout = w.shape[0]
+    assert w.shape[1] == 27 * Cin and Cout <= 256
+    out = torch.empty(B, T, H, W, Cout, device=x.device, dtype=BF16) if keep_raw else None
+    out2 = torch.empty(B, T, H, W, Cout, device=x.device, dtype=BF16)
+    if residual is not None:
+        _req(residual, name="residual"); assert residual.is_contiguous() and tuple(residual.shape) == tuple(out2.shape)
+    with _Prof('conv3d_bf16', 'flop', 2.0 * B * T * H * W * Cout * 27 * Cin):
+        rc = _lib.lib().ltxb200_conv3d_norm_bf16(x.data_ptr(), w.data_ptr(), _p(bias), _p(out), out2.data_ptr(), B, T, H, W, Cin, Cout,
+                                                 1 if causal else 0, _p(residual), 1 if keep_raw else 2, float(eps), _stream())
+    _lib.check(rc, "conv3d_norm_bf16")
+    return out, out2
+
+
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_bias: Optional[torch.Tensor] = None,
               scale: float = 0.0, out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
     """q [B,Lq,H,d], k/v [B,Lk,H,d] bf16 (strided views allowed, head stride must be d) -> [B,Lq,H,d].

@@ -175,17 +175,31 @@ class PeerExchange:
         total_ctas = sum(int(lib.ltxb200_scatter_signal_ctas(r1 - r0)) for r0, r1 in bounds)
         qkv = torch.empty(M, 3 * D, device=x_mod.device, dtype=x_mod.dtype)
         overlap = len(bounds) > 1 and ops.PROFILER is None       # the per-launch event timing of the bench probe needs one stream
+        def scatter(r0, r1, st):
+            with ops._Prof("qk_norm_rope_wan_scatter_bf16", "byte", 2.0 * 2 * (r1 - r0) * 3 * D):
+                self._check(lib.ltxb200_qk_norm_rope_wan_scatter_rows_bf16(
+                    qkv.data_ptr(), qkv.stride(0), M, r0, r1 - r0, D, wq.data_ptr(), wk.data_ptr(), cos.data_ptr(), sin.data_ptr(),
+                    d, n_loc, self.rank * n_loc, float(eps), B, P, self.rank, recv_ptrs, f0, epoch,
+                    self.local[ctl] + self.counter_off(0), total_ctas, st.cuda_stream), "qk_norm_rope_wan_scatter")
+
+        # chunk c's GEMM is enqueued BEFORE chunk c-1's scatter: both become runnable when GEMM c-1 retires and the block scheduler
+        # serves launches in order, so the GEMM's CTAs (one per SM, ~200 KB of shared memory) take their slots first and the
+        # scatter's small CTAs fill in beside them
+        prev = None
         for r0, r1 in bounds:
             ops.gemm(x_mod[r0:r1], w_qkv, b_qkv, out=qkv[r0:r1])
-            if overlap:
-                self.side.wait_stream(main)
-            st = self.side if overlap else main
-            with torch.cuda.stream(st):
-                with ops._Prof("qk_norm_rope_wan_scatter_bf16", "byte", 2.0 * 2 * (r1 - r0) * 3 * D):
-                    self._check(lib.ltxb200_qk_norm_rope_wan_scatter_rows_bf16(
-                        qkv.data_ptr(), qkv.stride(0), M, r0, r1 - r0, D, wq.data_ptr(), wk.data_ptr(), cos.data_ptr(), sin.data_ptr(),
-                        d, n_loc, self.rank * n_loc, float(eps), B, P, self.rank, recv_ptrs, f0, epoch,
-                        self.local[ctl] + self.counter_off(0), total_ctas, st.cuda_stream), "qk_norm_rope_wan_scatter")
+            if not overlap:
+                scatter(r0, r1, main)
+                continue
+            ev = torch.cuda.Event()
+            ev.record(main)
+            if prev is not None:
+                self.side.wait_event(prev[2])
+                scatter(prev[0], prev[1], self.side)
+            prev = (r0, r1, ev)
+        if overlap:
+            self.side.wait_event(prev[2])
+            scatter(prev[0], prev[1], self.side)
         if overlap:
             main.wait_stream(self.side)          # also orders every later reuse of `qkv`'s memory after the side stream's reads
         sp = main.cuda_stream

@@ -352,3 +352,74 @@ def test_conv3d_cta_pair_matches_single_cta(monkeypatch):
         torch.cuda.synchronize()
         assert torch.equal(one, two)
         assert rel(two, ref_conv(x, w5, b, causal).permute(0, 2, 3, 4, 1)) < 6e-3
+
+
+@pytest.mark.parametrize("B,T,H,W,Cin,Cout,causal", [(1, 3, 16, 16, 128, 128, False),      # exactly one 16x16 patch per frame
+                                                     (1, 2, 21, 37, 128, 128, True),        # ragged: partial patches on both axes
+                                                     (2, 3, 5, 7, 64, 48, False),           # smaller than a patch, BN = 64 tile
+                                                     (1, 4, 32, 48, 256, 128, False),       # 4 channel slices, 6 patches per frame
+                                                     (1, 1, 3, 3, 64, 64, True)])
+def test_conv3d_halo_tiled(B, T, H, W, Cin, Cout, causal, monkeypatch):
+    """The halo-tiled convolution (conv_halo.cuh; default for Cout <= 128, 3x3 spatial taps, unit stride) against fp32 torch and against
+    the plain implicit-GEMM kernel (LTXB200_CONV_HALO=0) on the same inputs: same result up to the order of the fp32 accumulation."""
+    x = rnd(B, T, H, W, Cin, seed=1)
+    w5 = rnd(Cout, Cin, 3, 3, 3, seed=2, scale=(27 * Cin) ** -0.5)
+    b = rnd(Cout, seed=3)
+    res = rnd(B, T, H, W, Cout, seed=4)
+    ref = ref_conv(x, w5, b, causal).permute(0, 2, 3, 4, 1)
+    monkeypatch.setenv("LTXB200_CONV_HALO", "0")
+    plain = ops.conv3d(x, pack_w(w5), b, causal=causal, residual=res)
+    monkeypatch.setenv("LTXB200_CONV_HALO", "1")
+    halo = ops.conv3d(x, pack_w(w5), b, causal=causal, residual=res)
+    halo_nores = ops.conv3d(x, pack_w(w5), b, causal=causal)
+    torch.cuda.synchronize()
+    assert rel(halo, ref + res.float()) < 6e-3 and rel(halo_nores, ref) < 6e-3
+    assert rel(halo, plain.float()) < 2e-3
+    # Wan-style variants through conv_taps: zero temporal padding (causal) and a purely spatial 1x3x3 convolution
+    xz = torch.cat([torch.zeros_like(x[:, :1]).repeat(1, 2, 1, 1, 1), x], dim=1).float().permute(0, 4, 1, 2, 3)
+    refz = F.conv3d(xz, w5.float(), b.float(), padding=(0, 1, 1)).permute(0, 2, 3, 4, 1)
+    assert rel(ops.conv_taps(x, pack_w(w5), b, 3, 3, zero_pad_t=True), refz) < 6e-3
+    w2 = w5[:, :, 1].contiguous()                                                              # [Cout, Cin, 3, 3]
+    ref2 = F.conv2d(x.float().reshape(B * T, H, W, Cin).permute(0, 3, 1, 2), w2.float(), b.float(), padding=1).permute(0, 2, 3, 1)
+    out2 = ops.conv_taps(x, w2.permute(0, 2, 3, 1).reshape(Cout, -1).contiguous(), b, 1, 3)
+    assert rel(out2.reshape(B * T, H, W, Cout), ref2) < 6e-3
+
+
+def test_conv3d_halo_unpatch_store(monkeypatch):
+    """conv_out of the LTX VAE decoder (128 -> 48 channels, unpatchify store to NCFHW) on the halo-tiled kernel's 64-column tile."""
+    B, T, H, W, Cin = 1, 3, 18, 20, 128
+    x = rnd(B, T, H, W, Cin, seed=1)
+    w5 = rnd(48, Cin, 3, 3, 3, seed=4, scale=(27 * Cin) ** -0.5)
+    b = rnd(48, seed=5)
+    ref = O.vae_unpatchify(ref_conv(x, w5, b, False), 4)
+    perm = torch.arange(48).reshape(3, 4, 4).permute(0, 2, 1).reshape(-1).to(DEV)
+    monkeypatch.setenv("LTXB200_CONV_HALO", "1")
+    out = ops.conv3d(x, pack_w(w5[perm]), b[perm].contiguous(), store=ops.CONV_UNPATCH, out_f32=True)
+    assert out.shape == ref.shape and rel(out, ref) < 6e-3
+
+
+@pytest.mark.parametrize("Cin,Cout,H,W", [(128, 128, 16, 16), (128, 128, 9, 21), (256, 256, 8, 16), (64, 48, 5, 7)])
+@pytest.mark.parametrize("keep_raw", [True, False])
+def test_conv3d_fused_pixelnorm_silu_output(Cin, Cout, H, W, keep_raw):
+    """ltxb200_conv3d_norm_bf16: the convolution's epilogue also writes silu(pixelnorm(y)) of its own output row (halo-tiled kernel for
+    Cout <= 128, plain implicit GEMM with the 256-column tile above) == conv3d followed by the standalone pixelnorm_silu kernel."""
+    B, T = 1, 3
+    x = rnd(B, T, H, W, Cin, seed=1)
+    w5 = rnd(Cout, Cin, 3, 3, 3, seed=2, scale=(27 * Cin) ** -0.5)
+    b = rnd(Cout, seed=3)
+    res = rnd(B, T, H, W, Cout, seed=4)
+    y_ref = ops.conv3d(x, pack_w(w5), b, residual=res)
+    if Cout % 64 == 0:
+        n_ref = ops.pixelnorm_silu(y_ref)
+    else:                                        # the standalone kernel has no 48-channel form: fp32 torch on the stored bf16 row
+        yf = y_ref.float()
+        t = (yf * torch.rsqrt(yf.pow(2).mean(-1, keepdim=True) + 1e-8)).bfloat16().float()
+        n_ref = F.silu(t).bfloat16()
+    y, n = ops.conv3d_norm(x, pack_w(w5), b, residual=res, keep_raw=keep_raw)
+    torch.cuda.synchronize()
+    assert (y is None) == (not keep_raw)
+    if keep_raw:
+        assert torch.equal(y, y_ref)
+    assert rel(n, n_ref.float()) < 2e-3
+    yf = (ref_conv(x, w5, b, False).permute(0, 2, 3, 4, 1) + res.float())
+    assert rel(n, F.silu(yf * torch.rsqrt(yf.pow(2).mean(-1, keepdim=True) + 1e-8))) < 8e-3

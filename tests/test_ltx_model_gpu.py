@@ -395,11 +395,16 @@ def test_rf_stochastic_step_vs_reference_formula():
     for i in (0, 2, 4):
         t, tn = float(ts[i]), float(ts[i + 1]) if i + 1 < len(ts) else 0.0
         out = s.step(v.to(DEV), ts[i], x.to(DEV), return_dict=False, stochastic_sampling=True, noise=nz.to(DEV))[0]
-        vb = v.bfloat16().float()
-        ref = (1 - tn) * (x - t * vb) + tn * nz
-        assert O.rel_l2(out.cpu(), ref) < 1e-5
+        ref = (1 - tn) * (x - t * v) + tn * nz                # fp32 predictions stay fp32 (the reference's tensor arithmetic)
+        assert out.dtype == torch.float32 and O.rel_l2(out.cpu(), ref) < 1e-5
         det = s.step(v.to(DEV), ts[i], x.to(DEV), return_dict=False)[0]
-        assert O.rel_l2(det.cpu(), x - (t - tn) * vb) < 1e-5
+        assert O.rel_l2(det.cpu(), x - (t - tn) * v) < 1e-5
+        # bf16 model output and bf16 sample: the result comes back in the promoted dtype, as `sample - dt * model_output` would
+        det16 = s.step(v.to(DEV, torch.bfloat16), ts[i], x.to(DEV, torch.bfloat16), return_dict=False)[0]
+        assert det16.dtype == torch.bfloat16
+        assert O.rel_l2(det16.float().cpu(), x.bfloat16().float() - (t - tn) * v.bfloat16().float()) < 8e-3
+    with pytest.raises(NotImplementedError):                  # per-token timesteps belong to the pipeline's fused step
+        s.step(v.to(DEV), torch.full((1, 72), 0.5), x.to(DEV))
     # through the pipeline: runs, is reproducible for a seeded generator, and differs from the deterministic sampler
     pipe, sd, _ = _pipe(1)
     kw = dict(height=128, width=192, num_frames=17, frame_rate=25.0, prompt_embeds=torch.randn(1, 16, 4096, generator=g),

@@ -355,7 +355,7 @@ def test_wan_i2v_conditioning_from_image():
     steps = []
     lat = pipe.generate(image_start=img, frame_num=F_, sampling_steps=2, guide_scale=5.0, context=g["ctx"], context_null=g["ctx0"],
                         clip_fea=g["clip"], noise=torch.randn(16, 3, H_ // 8, W_ // 8, generator=torch.Generator().manual_seed(6)),
-                        _per_step_latents=steps)
+                        _per_step_latents=steps, return_latents=True)
     assert lat is not None and len(steps) == 2 and torch.isfinite(lat).all()
     with pytest.raises(NotImplementedError):
         pipe.generate(image_start="photo.png", frame_num=F_, context=g["ctx"], context_null=g["ctx0"], clip_fea=g["clip"])
@@ -390,6 +390,7 @@ def test_wan_i2v_end_frame_conditioning():
     from oracle import wan_vae_oracle as V
     vcfg = dict(V.WAN_VAE, dim=32)
     vsd = V.make_wan_vae_encoder_state_dict(vcfg, seed=1)
+    vsd.update(V.make_wan_vae_decoder_state_dict(vcfg, seed=2))              # + decoder: generate() ends with vae.decode (image2video.py:414-420)
     vae = WanVAE(dim=32)
     vae.load_state_dict(vsd)
     g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "wan_i2v.pt"), weights_only=False)
@@ -407,8 +408,14 @@ def test_wan_i2v_end_frame_conditioning():
         assert torch.equal(y[:4].cpu(), yo[:4])
         assert W.rel_l2(y[4:].cpu(), yo[4:]) < 2e-2
     lat = pipe.generate(image_start=img, image_end=end, frame_num=9, sampling_steps=2, guide_scale=5.0, context=g["ctx"], context_null=g["ctx0"],
-                        clip_fea=g["clip"], seed=3)
+                        clip_fea=g["clip"], seed=3, return_latents=True)
     assert lat is not None and tuple(lat.shape) == (16, 4, 8, 12) and torch.isfinite(lat).all()
+    # what the reference returns (:414-420): the decoded video, the end image's latent frame decoded without feature caches and the
+    # pixel frame that was added for it dropped again -> frame_num frames
+    video = pipe.generate(image_start=img, image_end=end, frame_num=9, sampling_steps=2, guide_scale=5.0, context=g["ctx"], context_null=g["ctx0"],
+                          clip_fea=g["clip"], seed=3)
+    assert tuple(video.shape) == (3, 9, 64, 96) and torch.isfinite(video).all() and float(video.abs().max()) <= 1.0
+    assert torch.equal(video, vae.decode([lat], 0, any_end_frame=True)[0][:, :-1])
 
 
 def test_wan_t2v_generate_returns_the_decoded_video(golden_dir):
