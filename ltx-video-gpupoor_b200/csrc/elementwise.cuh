@@ -208,6 +208,81 @@ qk_norm_rope_kernel(__nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict__ k
   }
 }
 
+// The same arithmetic with the rows of one TOKEN handled by one warp: its q row and k row for every sequence of the batch (the
+// guidance conds share the token grid, so they share the token's cos / sin row).  The table row is loaded once and kept in registers
+// for the 2*B rows — table traffic L2 -> SM drops from 2*B reads per token to one — and the next row is prefetched while the current
+// one is reduced.  q / k: [B*tokens, D] views, row = b * tokens + tok.  Bit-identical to qk_norm_rope_kernel.
+template <int NV>
+__global__ void __launch_bounds__(128)
+qk_norm_rope_tok_kernel(__nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict__ k, int B, int tokens, long long ldq, long long ldk,
+                        const __nv_bfloat16* __restrict__ wq, const __nv_bfloat16* __restrict__ wk,
+                        const __nv_bfloat16* __restrict__ cosT, const __nv_bfloat16* __restrict__ sinT, float eps) {
+  constexpr int D = NV * 256;
+  const int tok = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (tok >= tokens) return;
+  uint4 cv[NV], sv[NV], xv[NV], xn[NV];
+  auto row_ptr = [&](int r) -> __nv_bfloat16* {
+    const int b = r % B;
+    return (r < B) ? q + (static_cast<long long>(b) * tokens + tok) * ldq : k + (static_cast<long long>(b) * tokens + tok) * ldk;
+  };
+  {
+    const __nv_bfloat16* x0 = row_ptr(0);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) xv[i] = *reinterpret_cast<const uint4*>(x0 + (i * 32 + lane) * 8);
+    const long long trow = static_cast<long long>(tok) * D;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      cv[i] = ldg16(cosT + trow + (i * 32 + lane) * 8);
+      sv[i] = ldg16(sinT + trow + (i * 32 + lane) * 8);
+    }
+  }
+#pragma unroll 1
+  for (int r = 0; r < 2 * B; ++r) {
+    __nv_bfloat16* xr = row_ptr(r);
+    if (r + 1 < 2 * B) {
+      const __nv_bfloat16* xnext = row_ptr(r + 1);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) xn[i] = *reinterpret_cast<const uint4*>(xnext + (i * 32 + lane) * 8);
+    }
+    const __nv_bfloat16* w = (r < B) ? wq : wk;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float v[8];
+      unpack8(xv[i], v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sq += v[j] * v[j];
+    }
+    const float rs = rsqrtf(warp_sum(sq) * (1.0f / D) + eps);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      float v[8];
+      unpack8(xv[i], v);
+      const uint4 w4 = ldg16(w + c);
+      uint32_t o[4] = {bf2_mul(pack_bf16(v[0] * rs, v[1] * rs), w4.x), bf2_mul(pack_bf16(v[2] * rs, v[3] * rs), w4.y),
+                       bf2_mul(pack_bf16(v[4] * rs, v[5] * rs), w4.z), bf2_mul(pack_bf16(v[6] * rs, v[7] * rs), w4.w)};
+      const uint32_t cs[4] = {cv[i].x, cv[i].y, cv[i].z, cv[i].w}, sn[4] = {sv[i].x, sv[i].y, sv[i].z, sv[i].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t rot = __byte_perm(o[j], 0, 0x1032) ^ 0x00008000u;     // (-y[2i+1], y[2i])
+        o[j] = bf2_add(bf2_mul(o[j], cs[j]), bf2_mul(rot, sn[j]));
+      }
+      *reinterpret_cast<uint4*>(xr + c) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) xv[i] = xn[i];
+  }
+}
+
+DEVI void load_cos_sin(const float* __restrict__ cosT, const float* __restrict__ sinT, long long off, float (&cs)[8], float (&sn)[8]) {
+  const float4 c0 = __ldg(reinterpret_cast<const float4*>(cosT + off)), c1 = __ldg(reinterpret_cast<const float4*>(cosT + off + 4));
+  const float4 s0 = __ldg(reinterpret_cast<const float4*>(sinT + off)), s1 = __ldg(reinterpret_cast<const float4*>(sinT + off + 4));
+  cs[0] = c0.x; cs[1] = c0.y; cs[2] = c0.z; cs[3] = c0.w; cs[4] = c1.x; cs[5] = c1.y; cs[6] = c1.z; cs[7] = c1.w;
+  sn[0] = s0.x; sn[1] = s0.y; sn[2] = s0.z; sn[3] = s0.w; sn[4] = s1.x; sn[5] = s1.y; sn[6] = s1.z; sn[7] = s1.w;
+}
+
 // ------------------------------------------------------------------------------------------
 // Wan q/k RMSNorm (full inner dim, affine, eps 1e-6, two bf16 roundings: model.py:104-111) + 3-axis RoPE
 // applied per head with fp32 [tokens, HD] cos/sin tables, fp32 math, one rounding
@@ -241,6 +316,12 @@ qk_norm_rope_wan_kernel(__nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict
     for (int j = 0; j < 8; ++j) sq += v[i][j] * v[i][j];
   const float rs = rsqrtf(warp_sum(sq) * (1.0f / D) + eps);
   const long long trow = cosT ? static_cast<long long>(token_offset + row % tokens_per_batch) * head_dim : 0;
+  // every head of a token shares the token's cos / sin row, and a lane's column offset inside its head is the same in every
+  // 256-column chunk when head_dim divides 256 (it is 128): the 16 table values are loaded ONCE per row instead of once per chunk
+  // (the per-chunk form moved 4x more table bytes than q/k bytes from L2 to the SM)
+  const bool hoist = cosT && (256 % head_dim) == 0;
+  float cs[8], sn[8];
+  if (hoist) load_cos_sin(cosT, sinT, trow + (lane * 8) % head_dim, cs, sn);
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = (i * 32 + lane) * 8;
@@ -252,11 +333,7 @@ qk_norm_rope_wan_kernel(__nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict
                          bf2_mul(pack_bf16(vv[4] * rs, vv[5] * rs), w4.z), bf2_mul(pack_bf16(vv[6] * rs, vv[7] * rs), w4.w)), o);
     }
     if (cosT) {
-      const int hd = c % head_dim;
-      const float4 c0 = *reinterpret_cast<const float4*>(cosT + trow + hd), c1 = *reinterpret_cast<const float4*>(cosT + trow + hd + 4);
-      const float4 s0 = *reinterpret_cast<const float4*>(sinT + trow + hd), s1 = *reinterpret_cast<const float4*>(sinT + trow + hd + 4);
-      const float cs[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-      const float sn[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+      if (!hoist) load_cos_sin(cosT, sinT, trow + c % head_dim, cs, sn);
       float r[8];
 #pragma unroll
       for (int j = 0; j < 8; j += 2) {
@@ -321,6 +398,9 @@ qk_norm_rope_wan_scatter_kernel(const __nv_bfloat16* __restrict__ qkv, long long
       rs = rsqrtf(warp_sum(sq) * (1.0f / D) + eps);
     }
     const long long trow = T * head_dim;
+    const bool hoist = (256 % head_dim) == 0;       // see qk_norm_rope_wan_kernel: one table read per row, not per chunk
+    float cs[8], sn[8];
+    if (sel < 2 && hoist) load_cos_sin(cosT, sinT, trow + (lane * 8) % head_dim, cs, sn);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = (i * 32 + lane) * 8;
@@ -331,11 +411,7 @@ qk_norm_rope_wan_scatter_kernel(const __nv_bfloat16* __restrict__ qkv, long long
         const uint4 w4 = ldg16(w + c);
         unpack8(make_uint4(bf2_mul(pack_bf16(v[0] * rs, v[1] * rs), w4.x), bf2_mul(pack_bf16(v[2] * rs, v[3] * rs), w4.y),
                            bf2_mul(pack_bf16(v[4] * rs, v[5] * rs), w4.z), bf2_mul(pack_bf16(v[6] * rs, v[7] * rs), w4.w)), o);
-        const int hd = c % head_dim;
-        const float4 c0 = *reinterpret_cast<const float4*>(cosT + trow + hd), c1 = *reinterpret_cast<const float4*>(cosT + trow + hd + 4);
-        const float4 s0 = *reinterpret_cast<const float4*>(sinT + trow + hd), s1 = *reinterpret_cast<const float4*>(sinT + trow + hd + 4);
-        const float cs[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-        const float sn[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        if (!hoist) load_cos_sin(cosT, sinT, trow + c % head_dim, cs, sn);
         float q[8];
 #pragma unroll
         for (int j = 0; j < 8; j += 2) {

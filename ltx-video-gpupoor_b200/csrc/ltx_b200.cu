@@ -581,6 +581,20 @@ extern "C" int ltxb200_qk_norm_rope_bf16(void* q, int64_t ldq, int Mq, void* k, 
   auto WK = static_cast<const __nv_bfloat16*>(wk);
   auto C = static_cast<const __nv_bfloat16*>(cos_table);
   auto Sn = static_cast<const __nv_bfloat16*>(sin_table);
+  // self-attention shape (q and k rows of the same B*tokens grid, RoPE): one warp per TOKEN, the table row read once for all 2*B rows
+  static const int env_tok = getenv("LTXB200_ROPE_TOKEN_MAJOR") ? atoi(getenv("LTXB200_ROPE_TOKEN_MAJOR")) : 1;
+  if (env_tok && C && q && k && Mq == Mk && (Mq % tokens_per_batch) == 0 && D <= 2048) {
+    const int Bq = Mq / tokens_per_batch;
+    dim3 gt((tokens_per_batch + 3) / 4);
+#define QKT_CASE(n) \
+  case n: qk_norm_rope_tok_kernel<n><<<gt, 128, 0, st>>>(Q, Kp, Bq, tokens_per_batch, ldq, ldk, WQ, WK, C, Sn, eps); break;
+    switch (D / 256) {
+      QKT_CASE(2) QKT_CASE(4) QKT_CASE(6) QKT_CASE(8)
+      default: return kErrUnsupported;
+    }
+#undef QKT_CASE
+    return launch_status();
+  }
 #define QK_CASE(n) \
   case n: if (C) qk_norm_rope_kernel<n, true><<<grid, 128, 0, st>>>(Q, Kp, q ? Mq : 0, Mk, ldq, ldk, WQ, WK, C, Sn, tokens_per_batch, eps); \
           else qk_norm_rope_kernel<n, false><<<grid, 128, 0, st>>>(Q, Kp, q ? Mq : 0, Mk, ldq, ldk, WQ, WK, C, Sn, tokens_per_batch, eps); break;

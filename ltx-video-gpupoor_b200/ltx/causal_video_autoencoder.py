@@ -13,6 +13,7 @@ kernels, always causal; the stride-2 "compress_all" convolutions run on a TMA de
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from types import SimpleNamespace
 from typing import Dict, List, Optional, Tuple
@@ -297,7 +298,7 @@ class CausalVideoAutoencoder(ModuleLike):
         "norm" -> (None, silu(pn(y))) (the raw row is never written)."""
         if want == "raw":
             return ops.conv3d(h, c[0], c[1], causal=causal, residual=residual), None
-        if c[0].shape[0] > 256:
+        if c[0].shape[0] > 256 or os.environ.get("LTXB200_VAE_FUSED_NORM") == "0":      # the switch exists for A/B runs and tests
             y = ops.conv3d(h, c[0], c[1], causal=causal, residual=residual)
             return (y if want == "both" else None), ops.pixelnorm_silu(y)
         return ops.conv3d_norm(h, c[0], c[1], causal=causal, residual=residual, keep_raw=(want == "both"))

@@ -200,9 +200,10 @@ class LTXVideoPipeline:
 
     def denoise_step(self, st, i: int):
         """One iteration of the loop at pipeline_ltx_video.py:1104-1256: cond batch, timestep tensor, transformer
-        forward, guidance, scheduler step.  No host synchronisation."""
+        forward, guidance, scheduler step.  No host synchronisation.  The batch is laid out cond-major like the reference's
+        torch.cat([negative, positive, positive]) (:1034-1051): row c * b + j is cond c of sample j."""
         t = st.ts_host[i]
-        N, C, num_conds, device = st.N, st.C, st.num_conds, self._execution_device
+        N, C, num_conds, bsz, device = st.N, st.C, st.num_conds, st.bsz, self._execution_device
         if st.cmask_dev is not None and st.image_cond_noise_scale > 0.0:
             # :606-629 add timestep-dependent noise to hard-conditioned tokens (host-side glue, i2v only)
             gen = st.generator
@@ -213,7 +214,7 @@ class LTXVideoPipeline:
             noised = st.init_tokens.float() + st.image_cond_noise_scale * noise.float() * (t ** 2)
             st.lat32 = torch.where(need, noised, st.lat32.view(1, N, C)).contiguous().view(-1)
             st.lat16 = st.lat32.to(BF16)
-        st.x_in.copy_(st.lat16.view(1, N, C).expand(num_conds, N, C))
+        st.x_in.view(num_conds, bsz, N, C).copy_(st.lat16.view(1, bsz, N, C).expand(num_conds, bsz, N, C))
         if st.cmask_dev is None:
             st.t_in.fill_(t)
         else:
@@ -225,11 +226,14 @@ class LTXVideoPipeline:
             ltxv_model=st.ltxv_model, return_dict=False, shared_prefix=getattr(st, "shared_prefix", None))[0]
         if noise_pred is None:
             return None
-        ops.guidance_step(noise_pred.view(num_conds, N * C), st.lat32, st.ts_dev, t, num_conds=num_conds,
-                          has_cfg=st.do_cfg, has_stg=st.do_stg, do_rescale=st.do_rescaling,
-                          guidance_scale=st.guidance_scale[i], stg_scale=st.stg_scale[i], rescale=st.rescaling_scale[i],
-                          channels=C, cond_mask=st.cmask_dev, scratch=st.scratch, latents_bf16=st.lat16,
-                          noise=self._step_noise(st) if st.stochastic_sampling else None)
+        n = N * C
+        pred = noise_pred.view(-1)
+        for j in range(bsz):            # guidance statistics (cfg-star projection, std rescale) are per sample (:1183-1222)
+            ops.guidance_step(pred[j * n:], st.lat32[j * n:(j + 1) * n], st.ts_dev, t, num_conds=num_conds,
+                              has_cfg=st.do_cfg, has_stg=st.do_stg, do_rescale=st.do_rescaling,
+                              guidance_scale=st.guidance_scale[i], stg_scale=st.stg_scale[i], rescale=st.rescaling_scale[i],
+                              channels=C, cond_mask=st.cmask_dev, scratch=st.scratch, latents_bf16=st.lat16[j * n:(j + 1) * n],
+                              noise=self._step_noise(st) if st.stochastic_sampling else None, cond_stride=bsz * n)
         return st
 
     # ---------------------------------------------------------------------------------------------
@@ -261,15 +265,21 @@ class LTXVideoPipeline:
         device = self._execution_device
         tr = self.transformer
         batch_size = prompt_embeds.shape[0]
-        if batch_size * num_images_per_prompt != 1:
-            raise NotImplementedError("the fused guidance/step kernel handles one video per call (replicas give batch)")
+        if num_images_per_prompt and num_images_per_prompt > 1:                   # :849-872 every prompt repeated per image
+            rep = lambda t_: None if t_ is None else t_.repeat_interleave(num_images_per_prompt, dim=0)
+            prompt_embeds, prompt_attention_mask = rep(prompt_embeds), rep(prompt_attention_mask)
+            negative_prompt_embeds, negative_prompt_attention_mask = rep(negative_prompt_embeds), rep(negative_prompt_attention_mask)
+        bsz = batch_size * (num_images_per_prompt or 1)
+        if bsz != 1 and (conditioning_items or media_items is not None or image_cond_noise_scale or stochastic_sampling):
+            raise NotImplementedError("more than one video per call is implemented for plain t2v (no conditioning items / media / "
+                                      "stochastic sampling)")
 
         video_scale = self.video_scale_factor if is_video else 1
         latent_height, latent_width = height // self.vae_scale_factor, width // self.vae_scale_factor
         latent_num_frames = num_frames // video_scale
         if is_video:
             latent_num_frames += 1
-        latent_shape = (batch_size * num_images_per_prompt, tr.config.in_channels, latent_num_frames, latent_height, latent_width)
+        latent_shape = (bsz, tr.config.in_channels, latent_num_frames, latent_height, latent_width)
 
         ts, num_inference_steps = retrieve_timesteps(self.scheduler, num_inference_steps, None, timesteps, max_timestep=strength,
                                                      skip_initial_inference_steps=skip_initial_inference_steps,
@@ -302,7 +312,7 @@ class LTXVideoPipeline:
                 skip_block_list = [skip_block_list[mapping[i]] for i in range(n_steps)]
         skip_layer_masks = None
         if do_stg and skip_block_list is not None:
-            skip_layer_masks = [tr.create_skip_layer_mask(batch_size, num_conds, num_conds - 1, sb) for sb in skip_block_list]
+            skip_layer_masks = [tr.create_skip_layer_mask(bsz, num_conds, num_conds - 1, sb) for sb in skip_block_list]
 
         # ---- cond batch [uncond, text, perturbed] (:1034-1051)
         pe = prompt_embeds.to(device=device, dtype=BF16)
@@ -332,12 +342,12 @@ class LTXVideoPipeline:
         frac[:, 0] = frac[:, 0] * (1.0 / frame_rate)
         freqs_cis = tr.precompute_freqs_cis(frac[:1])
         N, C = tokens.shape[1], tokens.shape[2]
-        lat32 = tokens.to(torch.float32).contiguous().view(-1)            # [N*C] fp32 master copy
+        lat32 = tokens.to(torch.float32).contiguous().view(-1)            # [b*N*C] fp32 master copy
         lat16 = tokens.to(BF16).contiguous().view(-1)                      # bf16 model input
         cmask_dev = None if conditioning_mask is None else conditioning_mask.to(device=device, dtype=torch.float32).contiguous().view(-1)
         scratch = torch.empty(8 * 148, device=device, dtype=torch.float32)
-        x_in = torch.empty(num_conds, N, C, device=device, dtype=BF16)
-        t_in = torch.empty(num_conds, N if cmask_dev is not None else 1, device=device, dtype=torch.float32)
+        x_in = torch.empty(num_conds * bsz, N, C, device=device, dtype=BF16)
+        t_in = torch.empty(num_conds * bsz, N if cmask_dev is not None else 1, device=device, dtype=torch.float32)
 
         if callback is not None:
             callback(-1, None, True, override_num_inference_steps=num_inference_steps, pass_no=pass_no)
@@ -346,13 +356,13 @@ class LTXVideoPipeline:
             ts_host=ts_host, ts_dev=ts_dev, num_conds=num_conds, do_cfg=do_cfg, do_stg=do_stg, do_rescaling=do_rescaling,
             guidance_scale=guidance_scale, stg_scale=stg_scale, rescaling_scale=rescaling_scale,
             skip_layer_masks=skip_layer_masks, skip_layer_strategy=skip_layer_strategy, enc_b=enc_b, mask_b=mask_b,
-            freqs_cis=freqs_cis, N=N, C=C, lat32=lat32, lat16=lat16, cmask_dev=cmask_dev, scratch=scratch, x_in=x_in,
+            freqs_cis=freqs_cis, N=N, C=C, bsz=bsz, lat32=lat32, lat16=lat16, cmask_dev=cmask_dev, scratch=scratch, x_in=x_in,
             t_in=t_in, latent_shape=latent_shape, joint_pass=joint_pass, ltxv_model=ltxv_model, generator=generator,
             image_cond_noise_scale=image_cond_noise_scale, init_tokens=init_tokens, tokens_shape=tuple(tokens.shape),
             stochastic_sampling=bool(stochastic_sampling),
             # extension (off by default): the perturbed STG condition repeats the text condition's inputs, so its rows are
             # copies of the text rows until the first skipped block (Transformer3DModel.forward, `shared_prefix`)
-            shared_prefix=(1, int(do_cfg)) if (kwargs.get("share_stg_prefix", False) and do_stg and skip_layer_masks is not None) else None))
+            shared_prefix=(bsz, int(do_cfg) * bsz) if (kwargs.get("share_stg_prefix", False) and do_stg and skip_layer_masks is not None and bsz == 1) else None))
         self._state = st
         if kwargs.get("_prepare_only", False):
             return st
@@ -360,15 +370,15 @@ class LTXVideoPipeline:
             if self.denoise_step(st, i) is None:
                 return None
             if per_step is not None:
-                per_step.append(st.lat32.view(1, N, C).clone())
+                per_step.append(st.lat32.view(bsz, N, C).clone())
             if callback is not None:
-                prev = st.lat32.view(N, C)[num_cond_latents:].transpose(0, 1).reshape(C, latent_num_frames, latent_height, latent_width)
+                prev = st.lat32.view(bsz, N, C)[0, num_cond_latents:].transpose(0, 1).reshape(C, latent_num_frames, latent_height, latent_width)
                 callback(i, prev, False, pass_no=pass_no)
             if callback_on_step_end is not None:
                 callback_on_step_end(self, i, ts_host[i], {})
         lat32 = st.lat32
 
-        lat = lat32.view(1, N, C)[:, num_cond_latents:]
+        lat = lat32.view(bsz, N, C)[:, num_cond_latents:]
         lat = self.patchifier.unpatchify(lat, latent_height, latent_width, tr.in_channels // math.prod(self.patchifier.patch_size))
         if output_type != "latent":
             if getattr(self.vae.decoder, "timestep_conditioning", False):          # :1271-1285 re-noise for the conditioned decoder

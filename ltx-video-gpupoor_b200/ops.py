@@ -258,13 +258,17 @@ def cast_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tens
 def guidance_step(pred: torch.Tensor, latents: torch.Tensor, timesteps: torch.Tensor, t: float, *, num_conds: int,
                   has_cfg: bool, has_stg: bool, do_rescale: bool, guidance_scale: float, stg_scale: float,
                   rescale: float, channels: int, cond_mask: Optional[torch.Tensor], scratch: Optional[torch.Tensor],
-                  latents_bf16: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None):
-    """pred [num_conds, n] bf16 (batch 1), latents [n] fp32 in place; `noise` [n] fp32 selects the stochastic update (rf.py:370-373)."""
+                  latents_bf16: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None,
+                  cond_stride: Optional[int] = None):
+    """One sample: latents [n] fp32 in place; its prediction for cond c starts c * cond_stride elements after `pred` (bf16;
+    default cond_stride = n, i.e. pred [num_conds, n]; a batch of b samples laid out cond-major passes the sample's slice and
+    cond_stride = b * n); `noise` [n] fp32 selects the stochastic update (rf.py:370-373)."""
     _req(pred, name="pred"); _req(latents, torch.float32, "latents"); _req(timesteps, torch.float32, "timesteps")
     assert pred.is_contiguous() and latents.is_contiguous()
     n = latents.numel()
-    assert pred.numel() == num_conds * n
-    args = (pred.data_ptr(), n, n, channels, int(has_cfg), int(has_stg), int(do_rescale), float(guidance_scale), float(stg_scale),
+    cond_stride = n if cond_stride is None else int(cond_stride)
+    assert cond_stride >= n and pred.numel() >= (num_conds - 1) * cond_stride + n
+    args = (pred.data_ptr(), cond_stride, n, channels, int(has_cfg), int(has_stg), int(do_rescale), float(guidance_scale), float(stg_scale),
             float(rescale), latents.data_ptr(), _p(latents_bf16), timesteps.data_ptr(), timesteps.numel(), float(t), _p(cond_mask),
             _p(scratch))
     with _Prof('guidance_step', 'byte', n * (2.0 * num_conds + 10.0)):

@@ -90,3 +90,20 @@ if which in ("wangemm",):
         else:
             timeit(f"gemm {name} {M}x{N}x{K}", lambda: ops.gemm(a, w, bias, act=act), 2.0 * M * N * K)
         del a, w
+if which in ("all", "wanew"):
+    # Wan-1.3B self-attention q/k norm + RoPE on the fused QKV rows of both sequences (2 x 32760 tokens), fp32 [N, 128] tables
+    M, D = 65520, 1536
+    qkv = torch.randn(M, 3 * D, device=dev).bfloat16()
+    w = torch.randn(D, device=dev).bfloat16()
+    cos = torch.randn(32760, 128, device=dev); sin = torch.randn(32760, 128, device=dev)
+    for _ in range(3):
+        ops.qk_norm_rope_wan(qkv[:, :D], qkv[:, D:2 * D], w, w, cos, sin, head_dim=128, tokens_per_batch=32760)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        ops.qk_norm_rope_wan(qkv[:, :D], qkv[:, D:2 * D], w, w, cos, sin, head_dim=128, tokens_per_batch=32760)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / reps
+    print(f"qk_norm_rope_wan q,k 65520x1536: {ms * 1e3:.1f} us  {8.0 * M * D / ms / 1e6:.0f} GB/s", flush=True)

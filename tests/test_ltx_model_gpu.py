@@ -603,3 +603,34 @@ def test_pipeline_resizes_conditioning_media_like_the_reference():
     e = O.rel_l2(outs[0], outs[1])
     print(f"resized-in-pipeline vs pre-resized conditioning image: latents rel_l2 = {e:.3e}")
     assert e < 2e-3
+
+
+def test_pipeline_two_videos_per_call():
+    """pipeline_ltx_video.py:632-710, 1034-1051: more than one video per call (batch = prompts x num_images_per_prompt).  The cond batch is
+    cond-major ([negative x b, positive x b]); guidance statistics are per sample.  Sample 0 of the 2-video call is bit-identical to the
+    1-video call with the same seed (the generator's stream starts with its noise), and both samples match the oracle loop run on the batch."""
+    pipe, sd, _ = _pipe(2)
+    g = torch.Generator().manual_seed(21)
+    pe, ne = torch.randn(2, 24, 4096, generator=g), torch.randn(2, 24, 4096, generator=g)
+    pm = torch.ones(2, 24)
+    pm[1, 17:] = 0
+    kw = dict(height=128, width=192, num_frames=17, frame_rate=25.0, num_inference_steps=3, guidance_scale=3.0, stg_scale=0.0, rescaling_scale=1.0,
+              output_type="latent", return_dict=False, is_video=True, vae_per_channel_normalize=True)
+    two = pipe(prompt_embeds=pe, prompt_attention_mask=pm, negative_prompt_embeds=ne, negative_prompt_attention_mask=pm,
+               generator=torch.Generator().manual_seed(5), **kw)[0]
+    one = pipe(prompt_embeds=pe[:1], prompt_attention_mask=pm[:1], negative_prompt_embeds=ne[:1], negative_prompt_attention_mask=pm[:1],
+               generator=torch.Generator().manual_seed(5), **kw)[0]
+    torch.cuda.synchronize()
+    assert tuple(two.shape) == (2, 128, 3, 4, 6) and tuple(one.shape) == (1, 128, 3, 4, 6)
+    assert torch.equal(two[:1], one)
+    noise = torch.randn(2, 72, 128, generator=torch.Generator().manual_seed(5))
+    for j in range(2):                # the oracle loop handles one video at a time: sample j = its slice of the noise and its prompts
+        ref = O.denoise_loop(sd, O.LTX_2B, noise[j:j + 1], pe[j:j + 1], pm[j:j + 1], num_frames_lat=3, lat_h=4, lat_w=6, frame_rate=25.0,
+                             num_steps=3, neg_enc=ne[j:j + 1], neg_mask=pm[j:j + 1], guidance_scale=3.0)
+        e = O.rel_l2(two[j:j + 1].float().cpu(), O.unpatchify(ref, 3, 4, 6))
+        print(f"2 videos per call, sample {j}: final latents rel_l2 vs the oracle loop = {e:.3e}")
+        assert e < TOL_LATENTS
+    # num_images_per_prompt repeats every prompt (:849-872)
+    rep = pipe(prompt_embeds=pe[:1], prompt_attention_mask=pm[:1], negative_prompt_embeds=ne[:1], negative_prompt_attention_mask=pm[:1],
+               num_images_per_prompt=2, generator=torch.Generator().manual_seed(5), **kw)[0]
+    assert tuple(rep.shape) == (2, 128, 3, 4, 6) and torch.equal(rep[:1], one)
