@@ -37,6 +37,10 @@ WORKLOADS = {
     "ltx2b_768x512x121_i2v_cfg_stg": dict(height=512, width=768, num_frames=121, frame_rate=25.0, schedule_steps=30,
                                           guidance_scale=3.0, stg_scale=1.0, rescaling_scale=0.7, skip_block_list=[19],
                                           prompt_tokens=256, num_conds=3, i2v=True),
+    # the model the reference APP actually loads (ltx_video/ltxv.py:171-194: LTX-Video 13B 0.9.7, 48 layers, 32 heads x 128): same step, 13B widths
+    "ltx13b_768x512x121_cfg_stg": dict(height=512, width=768, num_frames=121, frame_rate=25.0, schedule_steps=30,
+                                       guidance_scale=3.0, stg_scale=1.0, rescaling_scale=0.7, skip_block_list=[28],
+                                       prompt_tokens=256, num_conds=3, arch="13b"),
     "ltx2b_768x512x121_noguidance": dict(height=512, width=768, num_frames=121, frame_rate=25.0, schedule_steps=30,
                                          guidance_scale=1.0, stg_scale=0.0, rescaling_scale=1.0, skip_block_list=None,
                                          prompt_tokens=256, num_conds=1),
@@ -51,6 +55,14 @@ WAN_WORKLOADS = {
 }
 LAYER_FLOPS = 1.048e12      # per layer per cond at N=6144
 FWD_FLOPS = 29.36e12
+LTX_ARCH = {"2b": dict(layers=28, overrides={}, name="LTX-Video 2B"),
+            "13b": dict(layers=48, overrides=dict(attention_head_dim=128, cross_attention_dim=4096), name="LTX-Video 13B")}
+
+
+def ltx_fwd_flops(wl, layers, tokens):
+    """28*N*D^2 (q,k,v,o + cross q,o + FFN 4x) + 4*N^2*D self-attention + 4*N*L*D cross-attention, per layer per cond"""
+    D = 32 * (128 if wl.get("arch") == "13b" else 64)
+    return layers * (28.0 * tokens * D * D + 4.0 * tokens * tokens * D + 4.0 * tokens * wl["prompt_tokens"] * D)
 
 
 def peaks():
@@ -139,7 +151,8 @@ def cpu_sample(wl, layers=(1, 3)):
 def ltx_config(workload, wl, layers, world):
     """`config` of the JSON line: identical for the b200 arm and the reference arm."""
     tokens = (wl["num_frames"] // 8 + 1) * (wl["height"] // 32) * (wl["width"] // 32)
-    return {"workload": workload, "network": "LTX-Video 2B (random-init, 28 layers)" if layers == 28 else f"INVALID: {layers} layers",
+    arch = LTX_ARCH[wl.get("arch", "2b")]
+    return {"workload": workload, "network": f"{arch['name']} (random-init, {layers} layers)" if layers == arch["layers"] else f"INVALID: {layers} layers",
             "height": wl["height"], "width": wl["width"], "num_frames": wl["num_frames"], "tokens": tokens,
             "schedule_steps": wl["schedule_steps"], "num_conds": wl["num_conds"], "prompt_tokens": wl["prompt_tokens"],
             "parallelism": f"replicas x{world}", "prompt_mask": "all ones (every prompt token valid): zero key bias",
@@ -201,7 +214,7 @@ def run_reference(args, wl_name, wl):
             "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "extrapolated": True,
             "timed": {"samples": 1, "sample_wall_s": base["sample_wall_s"], "run_wall_s": None,
                       "note": "steps/warmup echo the request; ONE bounded sample is timed per run (see cpu_baseline.sample)"},
-            "config": ltx_config(wl_name, wl, 28, args.gpus), "cpu_baseline": base, "config0_real": config0,
+            "config": ltx_config(wl_name, wl, LTX_ARCH[wl.get("arch", "2b")]["layers"], args.gpus), "cpu_baseline": base, "config0_real": config0,
             "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     line["timed"]["run_wall_s"] = time.perf_counter() - t_start
     print(json.dumps(line))
@@ -459,7 +472,7 @@ def wan_sp_block(dev, world, rank, local_rank, steps=10, warmup=3):
             "ms_per_step": r["ms_per_step"], "steps_per_s": r["steps_per_s"], "s_per_50_step_video_denoise": 50 * r["ms_per_step"] / 1e3,
             "scaling": "strong", "forwards_per_step": 2,
             "exchange": (os.environ.get("LTXB200_SP_EXCHANGE", "p2p") + f" (peer-memory stores over NVLink fused into the producing kernels; "
-                         f"QKV projection + scatter in {os.environ.get('LTXB200_SP_CHUNKS', '4')} token chunks on two streams)") if sp_size > 1 else None,
+                         f"token chunks per exchange: {os.environ.get('LTXB200_SP_CHUNKS', '1')})") if sp_size > 1 else None,
             "exchange_kernels_ms_per_step_serialised": {"qk_norm_rope_wan_scatter": pick("qk_norm_rope_wan_scatter_bf16"), "comm_wait": pick("comm_wait"),
                                                         "peer_allgather": pick("peer_allgather")},
             "serialised_kernel_ms": r["serialised_kernel_ms"], "gpu_launches": r["launches"], "clocks": r["clocks"],
@@ -531,7 +544,7 @@ def run_wan(args, wl):
                            "latent": list(shape), "tokens": shape[1] * shape[2] * shape[3] // 4, "schedule_steps": S,
                            "forwards_per_step": 2, "parallelism": wan_parallelism(world, cfgp),
                            "sp_exchange": (os.environ.get("LTXB200_SP_EXCHANGE", "p2p") + (" (fused peer-memory stores over NVLink)" if os.environ.get("LTXB200_SP_EXCHANGE", "p2p") == "p2p" else " (all_to_all_single)")) if world > 1 else None,
-                           "sp_chunks": int(os.environ.get("LTXB200_SP_CHUNKS", "4")) if sp_size > 1 else None,
+                           "sp_chunks": int(os.environ.get("LTXB200_SP_CHUNKS", "1")) if sp_size > 1 else None,
                            "l2_policy": "per-step working set (weights + activations) far exceeds the 126 MB L2"},
                 "e2e": r["e2e"], "gpu_launches": r["launches"], "clocks": r["clocks"], "roofline": r["roofline"], "cpu_baseline": cpu_baseline,
                 "s_per_video_denoise": S * ms_step / 1e3, "vae_decode_s": decode_s,
@@ -634,7 +647,12 @@ def main():
     from ltx_video_gpupoor_b200.ltx.symmetric_patchifier import SymmetricPatchifier
     from ltx_video_gpupoor_b200.ltx.transformer3d import LTX_2B_CONFIG, Transformer3DModel
 
-    cfg = dict(LTX_2B_CONFIG, num_layers=args.layers)
+    arch = LTX_ARCH[wl.get("arch", "2b")]
+    if args.layers == 28:                          # the default = the architecture's full depth
+        args.layers = arch["layers"]
+    if wl.get("arch", "2b") != "2b":               # the CPU / torch-eager baselines are wired for the headline 2B architecture
+        args.no_cpu_baseline = args.no_gpu_baseline = args.no_wan_sp = True
+    cfg = dict(LTX_2B_CONFIG, num_layers=args.layers, **arch["overrides"])
     tr = Transformer3DModel(**cfg)
     tr.load_state_dict(random_transformer_state_dict(cfg, seed=0, device=dev), device=dev)
     vae = CausalVideoAutoencoder()
@@ -829,7 +847,7 @@ def main():
         "config": ltx_config(args.workload, wl, args.layers, world),
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
         "s_per_video": (S * ms_step / 1e3 + decode_s) if decode_s is not None else None, "vae_decode_s": decode_s,
-        "model_tflops": wl["num_conds"] * FWD_FLOPS * (args.layers / 28) / (ms_step / 1e3) / 1e12,
+        "model_tflops": wl["num_conds"] * ltx_fwd_flops(wl, args.layers, (wl["num_frames"] // 8 + 1) * (wl["height"] // 32) * (wl["width"] // 32)) / (ms_step / 1e3) / 1e12,
         "kernels": kernels,
     }
     if shared is not None:

@@ -59,10 +59,12 @@ class PeerExchange:
       gath       [B, P, n_loc, out]  fp32 head output of every rank (the final all-gather, also peer stores)
       flags      [3 exchanges][2 parities][P] uint32 epochs, counters [3] (local), status word (device) + one pinned host word
 
-    The way in is issued in `chunks` token chunks: chunk c's QKV projection runs on the caller's stream and its
-    norm + RoPE + scatter on a side stream, so the peer stores of chunk c overlap the GEMM of chunk c+1 (the stores are
-    NVLink-bound, the GEMM tensor-bound); only the last chunk's stores are exposed.  LTXB200_SP_CHUNKS (default 4; 1 = the
-    unchunked round-1 form).
+    The way in CAN be issued in `chunks` token chunks (LTXB200_SP_CHUNKS > 1): chunk c's QKV projection on the caller's stream and
+    chunk c-1's norm + RoPE + scatter on a side stream.  Measured and NOT the default: on one GPU the QKV GEMM (179 us) and the scatter
+    (65 us) take 229-233 us on two streams against 244 us back to back (profiles/scripts/overlap_probe.py) — the GEMM runs at the
+    L2 -> SM bandwidth cap, the scatter is pure memory traffic, so the two serialise on the memory system — and the Wan-1.3B step at
+    2 / 4 GPUs is 0.4-1.3 ms SLOWER with 4 chunks (smaller GEMMs, more launches): profiles/r02_wan_sp_chunk_ab.md.  What did pay
+    was making the scatter itself cheaper (bounded grid-stride grid, one RoPE table read per row: 11.8 -> 8.3 ms per step at SP2).
 
     Failure handling: every wait is bounded (csrc/comm.cuh); a peer that never publishes makes the waiting kernel record
     (source rank, epoch) in a host-visible word instead of spinning forever, and the next call here raises.
@@ -117,7 +119,7 @@ class PeerExchange:
         self.status_host = torch.zeros(16, dtype=torch.int32).pin_memory()     # UVA: the kernel stores into it directly
         self.calls = 0
         self.gather_calls = 0
-        self.chunks = max(1, int(os.environ.get("LTXB200_SP_CHUNKS", "4")))
+        self.chunks = max(1, int(os.environ.get("LTXB200_SP_CHUNKS", "1")))
         self.min_chunk_rows = 1024                 # below this a chunk's GEMM no longer fills the machine (tests lower it)
         self.side = torch.cuda.Stream(device=device)
         self._closed = False
