@@ -172,6 +172,18 @@ int ltxb200_pixelnorm_mod_silu_bf16(const void* x, void* y, int64_t voxels, int 
 int ltxb200_latent_to_ndhwc(const void* z, int is_f32, void* out, int B, int C, int64_t FHW, const float* stdv,
                             const float* meanv, void* stream);
 
+/* ---- `mixed` precision (transformer3d.py:343,439-442; pipeline_ltx_video.py:1061,1152-1177; ltxv.py:186): the residual stream and the
+ * AdaLN modulation stay fp32, only the Linear inputs are bf16 (the reference wraps the forward in torch.autocast). ---- */
+/* out[M,N] (fp32, may alias residual) = act(A @ W^T + bias) * gate[m / rows_per_gate] + residual, gate / residual fp32 */
+int ltxb200_gemm_bf16_f32res(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K, float* out, int64_t ldc,
+                             const void* bias, int act, const float* residual, int64_t ldr, const float* gate, int64_t gate_ld,
+                             int rows_per_gate, void* stream);
+/* y (bf16) = norm(x fp32) * (1 + scale[g]) + shift[g], scale / shift fp32 rows (NULL = plain norm), one rounding at the end */
+int ltxb200_norm_mod_f32in(const float* x, int64_t ldx, void* y, int64_t ldy, int M, int D, const float* scale, const float* shift,
+                           int64_t mod_ld, int rows_per_group, float eps, int layer_norm, void* stream);
+/* ada32[l, g, :] = fp32(table[l, :]) + fp32(temb[g, :])  (table [L, JD], temb [G, JD] bf16 -> [L, G, JD] fp32) */
+int ltxb200_ada_add_f32(const void* table, const void* temb, float* out, int L, int G, int JD, void* stream);
+
 /* ltxb200_conv3d_bf16 (NDHWC store) with ResnetBlock3D's next PixelNorm + SiLU (causal_video_autoencoder.py:1212-1240, pixel_norm.py:12)
  * fused into the epilogue, for Cout <= 256 (one N tile holds the whole channel vector): out2[b,t,h,w,:] =
  * silu(bf16(y / sqrt(mean_c(y^2) + eps))) with y the row as stored (bf16, after bias and residual).

@@ -49,6 +49,9 @@ def _declare(lib):
         "ltxb200_pixelnorm_silu_bf16": ([P, P, L, I, F, I, P], I),
         "ltxb200_pixelnorm_mod_silu_bf16": ([P, P, L, I, F, P, P, I, P], I),
         "ltxb200_latent_to_ndhwc": ([P, I, P, I, I, L, P, P, P], I),
+        "ltxb200_gemm_bf16_f32res": ([P, L, P, L, I, I, I, P, L, P, I, P, L, P, L, I, P], I),
+        "ltxb200_norm_mod_f32in": ([P, L, P, L, I, I, P, P, L, I, F, I, P], I),
+        "ltxb200_ada_add_f32": ([P, P, P, I, I, I, P], I),
         "ltxb200_conv3d_norm_bf16": ([P, P, P, P, P, I, I, I, I, I, I, I, P, I, F, P], I),
         "ltxb200_conv3d_strided_bf16": ([P, P, P, P, I, I, I, I, I, I, I, I, P], I),
         "ltxb200_conv_taps_bf16": ([P, P, P, P, I, I, I, I, I, I, I, I, I, P, P], I),

@@ -140,6 +140,83 @@ norm_mod_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------
+// `mixed` precision (transformer3d.py:439-442, pipeline_ltx_video.py:1152-1177): the residual stream and the AdaLN
+// modulation stay fp32, only the Linear inputs are bf16 (torch.autocast).  Same norm + modulate as norm_mod_kernel with an fp32
+// row in, fp32 scale / shift, ONE rounding at the end:  y = bf16( norm(x) * (1 + scale[g]) + shift[g] ).
+// ------------------------------------------------------------------------------------------
+template <int NV, bool kLayerNorm>
+__global__ void __launch_bounds__(128)
+norm_mod_f32in_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int M, long long ldx, long long ldy,
+                      const float* __restrict__ scale, const float* __restrict__ shift, long long mod_ld, int rows_per_group,
+                      float eps) {
+  constexpr int D = NV * 256;
+  const int lane = threadIdx.x & 31;
+  const int stride = gridDim.x * 4;
+  for (int row = blockIdx.x * 4 + (threadIdx.x >> 5); row < M; row += stride) {
+    const float* xr = x + row * ldx;
+    float v[NV][8];
+    float sum = 0.f, sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 a = *reinterpret_cast<const float4*>(xr + (i * 32 + lane) * 8), b = *reinterpret_cast<const float4*>(xr + (i * 32 + lane) * 8 + 4);
+      v[i][0] = a.x; v[i][1] = a.y; v[i][2] = a.z; v[i][3] = a.w; v[i][4] = b.x; v[i][5] = b.y; v[i][6] = b.z; v[i][7] = b.w;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { sum += v[i][j]; sq += v[i][j] * v[i][j]; }
+    }
+    float mean = 0.f, rs;
+    if (kLayerNorm) {
+      mean = warp_sum(sum) * (1.0f / D);
+      float var = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; var += d * d; }
+      rs = rsqrtf(warp_sum(var) * (1.0f / D) + eps);
+    } else {
+      rs = rsqrtf(warp_sum(sq) * (1.0f / D) + eps);
+    }
+    const long long g = row / rows_per_group;
+    const float* sc = scale ? scale + g * mod_ld : nullptr;
+    const float* sh = shift ? shift + g * mod_ld : nullptr;
+    __nv_bfloat16* yr = y + row * ldy;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rs;
+      if (sc) {
+        const float4 s0 = __ldg(reinterpret_cast<const float4*>(sc + c)), s1 = __ldg(reinterpret_cast<const float4*>(sc + c + 4));
+        const float4 t0 = __ldg(reinterpret_cast<const float4*>(sh + c)), t1 = __ldg(reinterpret_cast<const float4*>(sh + c + 4));
+        const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w}, tt[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(o[j], 1.0f + ss[j], tt[j]);
+      }
+      store8(yr + c, o);
+    }
+  }
+}
+
+// ada32[l, g, j, :] = fp32(table[l, j, :]) + fp32(temb[g, j*D:(j+1)*D])  -- the fp32 sum of the bf16 parameters / embeddings that
+// `scale_shift_table[None, None] + timestep.float()` forms in mixed mode
+__global__ void ada_add_f32_kernel(const __nv_bfloat16* __restrict__ table, const __nv_bfloat16* __restrict__ temb,
+                                   float* __restrict__ out, int L, int G, int JD) {
+  const long long n8 = static_cast<long long>(L) * G * JD / 8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long e = i * 8;
+    const int c = static_cast<int>(e % JD);
+    const int g = static_cast<int>((e / JD) % G);
+    const int l = static_cast<int>(e / JD / G);
+    float a[8], b[8];
+    load8(table + static_cast<long long>(l) * JD + c, a);
+    load8(temb + static_cast<long long>(g) * JD + c, b);
+    *reinterpret_cast<float4*>(out + e) = make_float4(a[0] + b[0], a[1] + b[1], a[2] + b[2], a[3] + b[3]);
+    *reinterpret_cast<float4*>(out + e + 4) = make_float4(a[4] + b[4], a[5] + b[5], a[6] + b[6], a[7] + b[7]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // LTX q/k RMSNorm (over the full inner dim, affine, eps 1e-5) + interleaved-pair RoPE, in place on
 // the q and k column slices of a fused QKV buffer (attention.py:1040-1055, 960-975, 477-479).
 //   y = bf16(x * rsqrt(mean(x^2)+eps)) * w ;  out = y*cos + rot(y)*sin,  rot: (2i,2i+1) -> (-y[2i+1], y[2i])

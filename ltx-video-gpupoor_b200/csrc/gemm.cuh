@@ -39,6 +39,9 @@ struct GemmParams {
   const __nv_bfloat16* gate;       // [ceil(M/rows_per_gate), gate_ld] or null
   int rows_per_gate;
   long long gate_ld;
+  // `mixed` precision: fp32 residual stream and fp32 gate (same strides, in elements); used instead of the bf16 pointers when set
+  const float* residual32;
+  const float* gate32;
   int out_f32;
   int store_mode;
   // fused PixelNorm (+ SiLU) of the OUTPUT row (row-major store, the whole channel vector in one N tile: N <= BN):
@@ -82,6 +85,8 @@ DEVI void epilogue_row(const GemmParams& p, uint32_t t_addr, int tn, bool row_ok
   const __nv_bfloat16* gate_row = nullptr;
   if (p.gate) gate_row = p.gate + (m_lin / p.rows_per_gate) * p.gate_ld;
   const __nv_bfloat16* res_row = p.residual ? p.residual + m_lin * p.ldr : nullptr;
+  const float* gate32_row = p.gate32 ? p.gate32 + (m_lin / p.rows_per_gate) * p.gate_ld : nullptr;
+  const float* res32_row = p.residual32 ? p.residual32 + m_lin * p.ldr : nullptr;
   float sumsq = 0.f;
 
   // One 32-column chunk of the accumulator row: bias / activation / gate / residual / store.  The chunk's TMEM load and its
@@ -122,6 +127,24 @@ DEVI void epilogue_row(const GemmParams& p, uint32_t t_addr, int tn, bool row_ok
             const float2 g0 = unpack_bf16(gq.x), g1 = unpack_bf16(gq.y), g2 = unpack_bf16(gq.z), g3 = unpack_bf16(gq.w);
             f[j] *= g0.x; f[j + 1] *= g0.y; f[j + 2] *= g1.x; f[j + 3] *= g1.y;
             f[j + 4] *= g2.x; f[j + 5] *= g2.y; f[j + 6] *= g3.x; f[j + 7] *= g3.y;
+          }
+        }
+      }
+      if (gate32_row) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          if (full || n0 + j < p.N) {
+            const float4 g4 = *reinterpret_cast<const float4*>(gate32_row + n0 + j);
+            f[j] *= g4.x; f[j + 1] *= g4.y; f[j + 2] *= g4.z; f[j + 3] *= g4.w;
+          }
+        }
+      }
+      if (res32_row) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          if (full || n0 + j < p.N) {
+            const float4 r4 = *reinterpret_cast<const float4*>(res32_row + n0 + j);
+            f[j] += r4.x; f[j + 1] += r4.y; f[j + 2] += r4.z; f[j + 3] += r4.w;
           }
         }
       }

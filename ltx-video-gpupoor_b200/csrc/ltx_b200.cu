@@ -111,15 +111,15 @@ static int launch_conv_halo(const CUtensorMap& ta, const CUtensorMap& tb, const 
   return launch_status();
 }
 
-extern "C" int ltxb200_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K,
-                                 void* out, int64_t ldc, int out_f32, const void* bias, int act,
-                                 const void* residual, int64_t ldr, const void* gate, int64_t gate_ld,
-                                 int rows_per_gate, void* stream) {
+static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K,
+                     void* out, int64_t ldc, int out_f32, const void* bias, int act,
+                     const void* residual, int64_t ldr, const void* gate, int64_t gate_ld,
+                     int rows_per_gate, int mod_f32, void* stream) {
   if (M <= 0 || N <= 0 || K <= 0 || (K & 7) || (N & 7)) return kErrBadShape;
   if (!aligned16(A) || !aligned16(W) || !aligned16(out) || (lda & 7) || (ldw & 7) || (ldc & (out_f32 ? 3 : 7)))
     return kErrBadAlign;
-  if ((bias && !aligned16(bias)) || (residual && (!aligned16(residual) || (ldr & 7))) ||
-      (gate && (!aligned16(gate) || (gate_ld & 7) || rows_per_gate <= 0)))
+  if ((bias && !aligned16(bias)) || (residual && (!aligned16(residual) || (ldr & (mod_f32 ? 3 : 7)))) ||
+      (gate && (!aligned16(gate) || (gate_ld & (mod_f32 ? 3 : 7)) || rows_per_gate <= 0)))
     return kErrBadAlign;
   const int BN = (N <= 128) ? 128 : 256;
   static const int env_2cta = getenv("LTXB200_GEMM_2CTA") ? atoi(getenv("LTXB200_GEMM_2CTA")) : 1;
@@ -142,8 +142,9 @@ extern "C" int ltxb200_gemm_bf16(const void* A, int64_t lda, const void* W, int6
   p.out = out; p.ldc = ldc; p.out_f32 = out_f32;
   p.bias = static_cast<const __nv_bfloat16*>(bias);
   p.act = act;
-  p.residual = static_cast<const __nv_bfloat16*>(residual); p.ldr = ldr;
-  p.gate = static_cast<const __nv_bfloat16*>(gate); p.gate_ld = gate_ld; p.rows_per_gate = rows_per_gate > 0 ? rows_per_gate : 1;
+  if (mod_f32) { p.residual32 = static_cast<const float*>(residual); p.gate32 = static_cast<const float*>(gate); }
+  else { p.residual = static_cast<const __nv_bfloat16*>(residual); p.gate = static_cast<const __nv_bfloat16*>(gate); }
+  p.ldr = ldr; p.gate_ld = gate_ld; p.rows_per_gate = rows_per_gate > 0 ? rows_per_gate : 1;
   p.store_mode = kStoreRowMajor;
   // the weights of this path always fit the 126 MB L2 (<= 34 MB); A often does not (FFN-down: 302 MB)
   p.n_fastest = (static_cast<long long>(N) * K * 2 <= (48ll << 20)) ? 1 : 0;
@@ -152,6 +153,19 @@ extern "C" int ltxb200_gemm_bf16(const void* A, int64_t lda, const void* W, int6
   if (two_cta) return launch_gemm_2cta<256, false>(ta, tb, p, ((M + 2 * kGemmBM - 1) / (2 * kGemmBM)) * ((N + BN - 1) / BN), st);
   const int tiles = ((M + kGemmBM - 1) / kGemmBM) * ((N + BN - 1) / BN);
   return BN == 128 ? launch_gemm<128, false>(ta, tb, p, tiles, st) : launch_gemm<256, false>(ta, tb, p, tiles, st);
+}
+
+extern "C" int ltxb200_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K,
+                                 void* out, int64_t ldc, int out_f32, const void* bias, int act,
+                                 const void* residual, int64_t ldr, const void* gate, int64_t gate_ld,
+                                 int rows_per_gate, void* stream) {
+  return gemm_impl(A, lda, W, ldw, M, N, K, out, ldc, out_f32, bias, act, residual, ldr, gate, gate_ld, rows_per_gate, 0, stream);
+}
+
+extern "C" int ltxb200_gemm_bf16_f32res(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K,
+                                        float* out, int64_t ldc, const void* bias, int act, const float* residual, int64_t ldr,
+                                        const float* gate, int64_t gate_ld, int rows_per_gate, void* stream) {
+  return gemm_impl(A, lda, W, ldw, M, N, K, out, ldc, 1, bias, act, residual, ldr, gate, gate_ld, rows_per_gate, 1, stream);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -563,6 +577,40 @@ extern "C" int ltxb200_norm_mod_bf16(const void* x, int64_t ldx, void* y, int64_
   auto Bs = static_cast<const __nv_bfloat16*>(bias);
   return layer_norm ? launch_norm<true>(D / 256, X, Y, M, ldx, ldy, SC, SH, mod_ld, rpg, Wt, Bs, eps, st)
                     : launch_norm<false>(D / 256, X, Y, M, ldx, ldy, SC, SH, mod_ld, rpg, Wt, Bs, eps, st);
+}
+
+extern "C" int ltxb200_norm_mod_f32in(const float* x, int64_t ldx, void* y, int64_t ldy, int M, int D, const float* scale,
+                                      const float* shift, int64_t mod_ld, int rows_per_group, float eps, int layer_norm,
+                                      void* stream) {
+  if (M <= 0 || D <= 0 || (D % 256)) return kErrBadShape;
+  if (!x || !y || !aligned16(x) || !aligned16(y) || (ldx & 3) || (ldy & 7) || (scale && (!aligned16(scale) || (mod_ld & 3))) ||
+      (shift && !aligned16(shift)))
+    return kErrBadAlign;
+  if ((scale == nullptr) != (shift == nullptr)) return kErrBadShape;
+  const int rpg = rows_per_group > 0 ? rows_per_group : M;
+  int grid = (M + 3) / 4;
+  const int cap = num_sms() * 4;
+  if (grid > cap) grid = cap;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  auto Y = static_cast<__nv_bfloat16*>(y);
+#define NMF_CASE(n) \
+  case n: if (layer_norm) norm_mod_f32in_kernel<n, true><<<grid, 128, 0, st>>>(x, Y, M, ldx, ldy, scale, shift, mod_ld, rpg, eps); \
+          else norm_mod_f32in_kernel<n, false><<<grid, 128, 0, st>>>(x, Y, M, ldx, ldy, scale, shift, mod_ld, rpg, eps); break;
+  switch (D / 256) {
+    NMF_CASE(2) NMF_CASE(4) NMF_CASE(8) NMF_CASE(16)
+    default: return kErrUnsupported;
+  }
+#undef NMF_CASE
+  return launch_status();
+}
+
+extern "C" int ltxb200_ada_add_f32(const void* table, const void* temb, float* out, int L, int G, int JD, void* stream) {
+  if (L <= 0 || G <= 0 || JD <= 0 || (JD & 7)) return kErrBadShape;
+  if (!aligned16(table) || !aligned16(temb) || !aligned16(out)) return kErrBadAlign;
+  const long long n8 = static_cast<long long>(L) * G * JD / 8;
+  ada_add_f32_kernel<<<ew_blocks(n8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(table), static_cast<const __nv_bfloat16*>(temb), out, L, G, JD);
+  return launch_status();
 }
 
 extern "C" int ltxb200_qk_norm_rope_bf16(void* q, int64_t ldq, int Mq, void* k, int64_t ldk, int Mk, int D,

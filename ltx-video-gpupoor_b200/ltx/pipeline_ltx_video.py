@@ -223,7 +223,8 @@ class LTXVideoPipeline:
             st.x_in, freqs_cis=st.freqs_cis, encoder_hidden_states=st.enc_b, encoder_attention_mask=st.mask_b,
             timestep=st.t_in, skip_layer_mask=st.skip_layer_masks[i] if st.skip_layer_masks is not None else None,
             skip_layer_strategy=st.skip_layer_strategy, latent_shape=st.latent_shape[2:], joint_pass=st.joint_pass,
-            ltxv_model=st.ltxv_model, return_dict=False, shared_prefix=getattr(st, "shared_prefix", None))[0]
+            ltxv_model=st.ltxv_model, return_dict=False, shared_prefix=getattr(st, "shared_prefix", None),
+            mixed=getattr(st, "mixed", False))[0]
         if noise_pred is None:
             return None
         n = N * C
@@ -256,8 +257,6 @@ class LTXVideoPipeline:
                  pass_no: int = -1, ltxv_model=None, callback=None, **kwargs):
         if prompt is not None or prompt_embeds is None:
             raise NotImplementedError("text encoding is out of scope: pass prompt_embeds / prompt_attention_mask")
-        if mixed_precision:
-            raise NotImplementedError("mixed_precision (fp32 residual stream) is not implemented")
         is_video = kwargs.get("is_video", False)
         vae_per_channel_normalize = kwargs.get("vae_per_channel_normalize", True)
         image_cond_noise_scale = kwargs.get("image_cond_noise_scale", 0.0)
@@ -332,6 +331,8 @@ class LTXVideoPipeline:
 
         # ---- latents (:1056-1088); drawn in prompt_embeds' dtype like the reference (:1061), kept as an fp32 master copy
         noise_dtype = prompt_embeds.dtype if prompt_embeds.dtype in (torch.float32, BF16) else torch.float32
+        if mixed_precision:
+            noise_dtype = torch.float32                                               # :1061
         init = self.prepare_latents(latents, media_items, ts_host[0], latent_shape, noise_dtype, device, generator,
                                     vae_per_channel_normalize=vae_per_channel_normalize)
         tokens, pixel_coords, conditioning_mask, num_cond_latents = self.prepare_conditioning(
@@ -359,7 +360,7 @@ class LTXVideoPipeline:
             freqs_cis=freqs_cis, N=N, C=C, bsz=bsz, lat32=lat32, lat16=lat16, cmask_dev=cmask_dev, scratch=scratch, x_in=x_in,
             t_in=t_in, latent_shape=latent_shape, joint_pass=joint_pass, ltxv_model=ltxv_model, generator=generator,
             image_cond_noise_scale=image_cond_noise_scale, init_tokens=init_tokens, tokens_shape=tuple(tokens.shape),
-            stochastic_sampling=bool(stochastic_sampling),
+            stochastic_sampling=bool(stochastic_sampling), mixed=bool(mixed_precision),
             # extension (off by default): the perturbed STG condition repeats the text condition's inputs, so its rows are
             # copies of the text rows until the first skipped block (Transformer3DModel.forward, `shared_prefix`)
             shared_prefix=(bsz, int(do_cfg) * bsz) if (kwargs.get("share_stg_prefix", False) and do_stg and skip_layer_masks is not None and bsz == 1) else None))

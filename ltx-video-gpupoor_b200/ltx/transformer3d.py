@@ -191,8 +191,8 @@ class Transformer3DModel(ModuleLike):
         :472-487) computes the same function and is executed as the batched pass here."""
         if attention_mask is not None:
             raise NotImplementedError("self-attention masks are never passed on the reference path")
-        if mixed:
-            raise NotImplementedError("mixed (fp32 residual stream) is not implemented; bf16 only")
+        if mixed and skip_layer_strategy == SkipLayerStrategy.TransformerBlock and skip_layer_mask is not None:
+            raise NotImplementedError("mixed precision with SkipLayerStrategy.TransformerBlock (fp32 blend of the residual stream)")
         w, D, H, dh = self.w, self.inner_dim, self.num_attention_heads, self.attention_head_dim
         dev = self.device
         B, N, Cin = hidden_states.shape
@@ -224,7 +224,9 @@ class Transformer3DModel(ModuleLike):
         e1 = ops.gemm(tp, w["t_l1.w"], w["t_l1.b"], act=ops.ACT_SILU)
         emb = ops.gemm(e1, w["t_l2.w"], w["t_l2.b"])                               # embedded_timestep [B*T, D]
         temb6 = ops.gemm(ops.act(emb, ops.ACT_SILU), w["t_lin.w"], w["t_lin.b"])     # [B*T, 6D]
-        ada = ops.ada_add(w["block_tables"], temb6)                                 # [L, B*T, 6, D]
+        # mixed (:439-442): `timestep.float()`, `hidden_states.float()` — the modulation tables and the residual stream are fp32,
+        # the Linear layers see bf16 inputs (autocast) and their outputs are accumulated into the fp32 stream by the GEMM epilogue
+        ada = ops.ada_add_f32(w["block_tables"], temb6) if mixed else ops.ada_add(w["block_tables"], temb6)     # [L, B*T, 6, D]
 
         # --- caption projection (:446-451)
         enc = encoder_hidden_states.to(device=dev, dtype=BF16)
@@ -241,6 +243,10 @@ class Transformer3DModel(ModuleLike):
         cos, sin = cos.contiguous(), sin.contiguous()
 
         x = ops.gemm(x_in, w["patchify_proj.w"], w["patchify_proj.b"])             # [B*N, D]
+        if mixed:
+            x = x.float()                                                           # the bf16 projection, upcast (:418, :442)
+        norm_mod = ops.norm_mod_f32in if mixed else ops.norm_mod
+        gemm_res = ops.gemm_f32res if mixed else ops.gemm
 
         skip_host = None
         if skip_layer_mask is not None:
@@ -278,7 +284,7 @@ class Transformer3DModel(ModuleLike):
             # (attention.py:1161-1168), which BasicTransformerBlock never enables, so the mask is ignored there as it is here.
             x_orig =x.clone() if (layer_skip and skip_layer_strategy == SkipLayerStrategy.TransformerBlock) else None
             # ---- self attention (attention.py:233-288)
-            nh = ops.norm_mod(x, a[:, 1], a[:, 0], rows_per_group=rows_per_group, eps=self.config.norm_eps)
+            nh = norm_mod(x, a[:, 1], a[:, 0], rows_per_group=rows_per_group, eps=self.config.norm_eps)
             qkv = ops.gemm(nh, Lw["qkv.w"], Lw["qkv.b"])                            # [B*N, 3D]
             ops.qk_norm_rope(qkv[:, :D], qkv[:, D:2 * D], Lw["qn"], Lw["kn"], cos, sin, tokens_per_batch=N, eps=1e-5)
             q4 = qkv.view(B, N, 3 * D)[:, :, :D].unflatten(-1, (H, dh))
@@ -289,18 +295,18 @@ class Transformer3DModel(ModuleLike):
                 ops.stg_blend(o.view(B, N, D), qkv[:, 2 * D:], skip_dev[li][:B])        # :1134-1139
             elif layer_skip and skip_layer_strategy == SkipLayerStrategy.AttentionSkip:
                 ops.stg_blend(o.view(B, N, D), nh, skip_dev[li][:B])                    # :1127-1133
-            ops.gemm(o.view(B * N, D), Lw["o.w"], Lw["o.b"], residual=x, gate=a[:, 2], rows_per_gate=rows_per_group, out=x)
+            gemm_res(o.view(B * N, D), Lw["o.w"], Lw["o.b"], residual=x, gate=a[:, 2], rows_per_gate=rows_per_group, out=x)
             # ---- cross attention (attention.py:294-311): query from the raw residual stream, no RoPE
-            q2 = ops.gemm(x, Lw["q2.w"], Lw["q2.b"])
+            q2 = ops.gemm(ops.cast_bf16(x) if mixed else x, Lw["q2.w"], Lw["q2.b"])
             kv = ops.gemm(ctx_l, Lw["kv2.w"], Lw["kv2.b"])                          # [B*Lc, 2D]
             ops.qk_norm_rope(q2, kv[:, :D], Lw["qn2"], Lw["kn2"], None, None, eps=1e-5)
             o2 = ops.attention(q2.view(B, N, H, dh), kv.view(B, Lc, 2 * D)[:, :, :D].unflatten(-1, (H, dh)),
                                kv.view(B, Lc, 2 * D)[:, :, D:].unflatten(-1, (H, dh)), key_bias=key_bias_l)
-            ops.gemm(o2.view(B * N, D), Lw["o2.w"], Lw["o2.b"], residual=x, out=x)
+            gemm_res(o2.view(B * N, D), Lw["o2.w"], Lw["o2.b"], residual=x, out=x)
             # ---- feed forward (attention.py:314-351)
-            nh = ops.norm_mod(x, a[:, 4], a[:, 3], rows_per_group=rows_per_group, eps=self.config.norm_eps)
+            nh = norm_mod(x, a[:, 4], a[:, 3], rows_per_group=rows_per_group, eps=self.config.norm_eps)
             ff = ops.gemm(nh, Lw["ff1.w"], Lw["ff1.b"], act=ops.ACT_GELU_TANH)
-            ops.gemm(ff, Lw["ff2.w"], Lw["ff2.b"], residual=x, gate=a[:, 5], rows_per_gate=rows_per_group, out=x)
+            gemm_res(ff, Lw["ff2.w"], Lw["ff2.b"], residual=x, gate=a[:, 5], rows_per_gate=rows_per_group, out=x)
             if x_orig is not None:
                 ops.stg_blend(x.view(B, N, D), x_orig, skip_dev[li][:B])               # :355-362
             if ltxv_model is not None and getattr(ltxv_model, "_interrupt", False):
@@ -309,8 +315,8 @@ class Transformer3DModel(ModuleLike):
         if B != B_full:
             x, B = expand(x), B_full
         # --- output head (:490-503)
-        fin = ops.ada_add(w["final_table"], torch.cat([emb, emb], dim=1))           # [1, B*T, 2, D]
-        y = ops.norm_mod(x, fin[0][:, 1], fin[0][:, 0], rows_per_group=rows_per_group, eps=1e-6, layer_norm=True)
+        fin = (ops.ada_add_f32 if mixed else ops.ada_add)(w["final_table"], torch.cat([emb, emb], dim=1))   # [1, B*T, 2, D]
+        y = norm_mod(x, fin[0][:, 1], fin[0][:, 0], rows_per_group=rows_per_group, eps=1e-6, layer_norm=True)
         out = ops.gemm(y, w["proj_out.w"], w["proj_out.b"]).view(B, N, self.out_channels)
         if not return_dict:
             return (out,)

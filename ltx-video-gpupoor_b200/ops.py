@@ -82,6 +82,61 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     return out
 
 
+def gemm_f32res(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
+                residual: Optional[torch.Tensor] = None, gate: Optional[torch.Tensor] = None, rows_per_gate: int = 1,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """`mixed` precision form of gemm: out fp32 [M,N] = act(a @ w.T + bias) * gate + residual with fp32 gate / residual (out may be residual)."""
+    _req(a, name="a"); _req(w, name="w")
+    assert a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1]
+    M, K = a.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty(M, N, device=a.device, dtype=torch.float32)
+    _req(out, torch.float32, "out")
+    if bias is not None:
+        _req(bias, name="bias"); assert bias.numel() == N
+    if residual is not None:
+        _req(residual, torch.float32, "residual"); assert residual.shape == (M, N)
+    if gate is not None:
+        _req(gate, torch.float32, "gate"); assert gate.dim() == 2 and gate.shape[1] == N
+    with _Prof('gemm_bf16', 'flop', 2.0 * M * N * K):
+        rc = _lib.lib().ltxb200_gemm_bf16_f32res(
+            a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, N, K, out.data_ptr(), out.stride(0), _p(bias), act,
+            _p(residual), residual.stride(0) if residual is not None else 0, _p(gate), gate.stride(0) if gate is not None else 0,
+            rows_per_gate, _stream())
+    _lib.check(rc, "gemm_bf16_f32res")
+    return out
+
+
+def norm_mod_f32in(x: torch.Tensor, scale: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None, rows_per_group: int = 0,
+                   eps: float = 1e-6, layer_norm: bool = False) -> torch.Tensor:
+    """x [M,D] fp32, scale / shift [G,D] fp32 row views -> bf16 (the `mixed` precision norm + AdaLN modulate)."""
+    _req(x, torch.float32, "x"); assert x.dim() == 2
+    M, D = x.shape
+    out = torch.empty(M, D, device=x.device, dtype=BF16)
+    mod_ld = 0
+    if scale is not None:
+        _req(scale, torch.float32, "scale"); _req(shift, torch.float32, "shift")
+        assert scale.dim() == 2 and shift.dim() == 2 and scale.stride(0) == shift.stride(0)
+        mod_ld = scale.stride(0)
+    with _Prof('norm_mod_bf16', 'byte', 6.0 * M * D):
+        rc = _lib.lib().ltxb200_norm_mod_f32in(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), M, D, _p(scale), _p(shift), mod_ld,
+                                               rows_per_group, float(eps), 1 if layer_norm else 0, _stream())
+    _lib.check(rc, "norm_mod_f32in")
+    return out
+
+
+def ada_add_f32(table: torch.Tensor, temb: torch.Tensor) -> torch.Tensor:
+    """table [L, J, D], temb [G, J*D] bf16 -> [L, G, J, D] fp32 (sum formed in fp32)"""
+    _req(table, name="table"); _req(temb, name="temb")
+    L, J, D = table.shape
+    G = temb.shape[0]
+    assert table.is_contiguous() and temb.is_contiguous() and temb.shape[1] == J * D
+    out = torch.empty(L, G, J, D, device=table.device, dtype=torch.float32)
+    _lib.check(_lib.lib().ltxb200_ada_add_f32(table.data_ptr(), temb.data_ptr(), out.data_ptr(), L, G, J * D, _stream()), "ada_add_f32")
+    return out
+
+
 CONV_NDHWC, CONV_D2S, CONV_UNPATCH = 0, 1, 2
 
 

@@ -634,3 +634,45 @@ def test_pipeline_two_videos_per_call():
     rep = pipe(prompt_embeds=pe[:1], prompt_attention_mask=pm[:1], negative_prompt_embeds=ne[:1], negative_prompt_attention_mask=pm[:1],
                num_images_per_prompt=2, generator=torch.Generator().manual_seed(5), **kw)[0]
     assert tuple(rep.shape) == (2, 128, 3, 4, 6) and torch.equal(rep[:1], one)
+
+
+def test_transformer_and_pipeline_mixed_precision(golden_dir):
+    """`mixed=True` (transformer3d.py:343,439-442 / `mixed_precision=True`, pipeline_ltx_video.py:1061,1152-1177): fp32 residual stream and
+    fp32 AdaLN tables, bf16 Linear inputs.  Against the fp32 reference fixture the mixed forward must be inside the contract and not
+    further away than the plain bf16 forward; the pipeline call with mixed_precision=True must match the oracle loop."""
+    g = _load(golden_dir, "ltx_transformer.pt")
+    meta = g["meta"]
+    m, sd = _model(meta["num_layers"], meta["seed_weights"])
+    f, h, w = meta["f"], meta["h"], meta["w"]
+    coords = O.latent_to_pixel_coords(O.latent_coords(f, h, w, 1)).float()
+    coords[:, 0] *= 1.0 / 25.0
+    fc = m.precompute_freqs_cis(coords.to(DEV))
+    for tag, strat in (("t2v", None), ("stg", SkipLayerStrategy.AttentionValues)):
+        c = g[tag]
+        skip = None if c["skip"] is None else m.create_skip_layer_mask(1, 3, 2, [1])
+        kw = dict(freqs_cis=fc, encoder_hidden_states=c["enc"].to(DEV), timestep=c["timestep"].to(DEV), encoder_attention_mask=c["mask"].to(DEV),
+                  skip_layer_mask=skip, skip_layer_strategy=strat, latent_shape=(f, h, w), return_dict=False)
+        y16 = m(c["hidden"].to(DEV), **kw)[0]
+        y32 = m(c["hidden"].to(DEV), mixed=True, **kw)[0]
+        torch.cuda.synchronize()
+        e16, e32 = O.rel_l2(y16.float().cpu(), c["out"]), O.rel_l2(y32.float().cpu(), c["out"])
+        print(f"transformer[{tag}] rel_l2 vs reference fp32: bf16 stream {e16:.3e}, mixed (fp32 stream) {e32:.3e}")
+        assert y32.dtype == torch.bfloat16 and e32 < TOL_MODEL_OUT and e32 < 1.05 * e16
+    with pytest.raises(NotImplementedError):
+        m(g["stg"]["hidden"].to(DEV), freqs_cis=fc, encoder_hidden_states=g["stg"]["enc"].to(DEV), timestep=g["stg"]["timestep"].to(DEV),
+          skip_layer_mask=m.create_skip_layer_mask(1, 3, 2, [1]), skip_layer_strategy=SkipLayerStrategy.TransformerBlock,
+          latent_shape=(f, h, w), mixed=True)
+    pipe, sd, _ = _pipe(2)
+    gen = torch.Generator().manual_seed(31)
+    pe, pm = torch.randn(1, 24, 4096, generator=gen), torch.ones(1, 24)
+    steps = []
+    pipe(height=128, width=192, num_frames=17, frame_rate=25.0, prompt_embeds=pe, prompt_attention_mask=pm, num_inference_steps=3,
+         guidance_scale=1.0, stg_scale=0.0, rescaling_scale=1.0, generator=torch.Generator().manual_seed(8), output_type="latent",
+         return_dict=False, is_video=True, mixed_precision=True, _per_step_latents=steps)
+    noise = torch.randn(1, 72, 128, generator=torch.Generator().manual_seed(8))
+    ref = []
+    O.denoise_loop(sd, O.LTX_2B, noise, pe, pm, num_frames_lat=3, lat_h=4, lat_w=6, frame_rate=25.0, num_steps=3, per_step=ref)
+    for i, (a, b) in enumerate(zip(steps, ref)):
+        e = O.rel_l2(a.cpu(), b)
+        print(f"pipeline mixed_precision step {i}: latents rel_l2 vs the fp32 oracle = {e:.3e}")
+        assert e < TOL_LATENTS
