@@ -262,14 +262,23 @@ int ltxb200_qk_norm_rope_wan_scatter_bf16(const void* qkv, int64_t ld, int M, in
                                           void* counter, void* stream);
 /* the same over rows [row0, row0 + rows) of the M local rows only: one exchange may be issued as several launches (token
  * chunks, so that the peer stores of chunk i overlap the QKV projection of chunk i+1 on another stream).  `signal_ctas` =
- * the sum of ltxb200_scatter_signal_ctas(rows_c) over all launches of the exchange; the last CTA of the last launch to
- * finish publishes the flag. */
+ * the sum of ltxb200_scatter_signal_ctas(rows_c) * nsel / 3 over all launches of the exchange; the last CTA of the last launch
+ * to finish publishes the flag.  nsel = 3: q, k and v;  nsel = 2: q and k only. */
 int ltxb200_qk_norm_rope_wan_scatter_rows_bf16(const void* qkv, int64_t ld, int M, int row0, int rows, int D, const void* wq,
                                                const void* wk, const float* cos_table, const float* sin_table, int head_dim,
                                                int tokens_per_batch, int token_offset, float eps, int B, int P, int rank,
                                                void* const* recv_ptrs, void* const* flag_ptrs, unsigned int epoch,
-                                               void* counter, unsigned int signal_ctas, void* stream);
+                                               void* counter, unsigned int signal_ctas, int nsel, void* stream);
+/* CTAs one launch over `rows` rows adds to the arrival counter with nsel = 3 (q, k, v); with nsel = 2 (V already sent by
+ * ltxb200_gemm_qkv_vscatter_bf16) it is two thirds of that */
 unsigned int ltxb200_scatter_signal_ctas(int rows);
+/* The fused QKV projection out[M, 3D] = A @ W^T + bias of the LOCAL token shard whose V third (columns 2D..3D, no normalisation needed) is
+ * stored by the GEMM epilogue straight into recv_ptrs[g] ([N, B, 3, H/P, head_dim], global token order) of the rank that owns the heads,
+ * while q and k (columns 0..2D) stay local for the scatter kernel above (nsel = 2), which also publishes the exchange's flag:
+ * a third of the head<->sequence all-to-all (xdit_context_parallel.py:179-184) leaves the GPU during the GEMM.  row0 = first local row of A. */
+int ltxb200_gemm_qkv_vscatter_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int K, int D, void* out, int64_t ldc,
+                                   const void* bias, int head_dim, int tokens_per_batch, int token_offset, int row0, int B, int P,
+                                   int rank, void* const* recv_ptrs, void* stream);
 /* ltxb200_attention_bf16 whose epilogue stores query token t's row to out_ptrs[t / tokens_per_peer] at row
  * b*tokens_per_peer + t % tokens_per_peer, head head_offset + h of a [B*tokens_per_peer, ldo] matrix (the Ulysses
  * return exchange, xdit_context_parallel.py:186-190), then publishes the epoch flag on every peer. */

@@ -66,7 +66,8 @@ def _declare(lib):
         "ltxb200_comm_wait": ([P, I, c_uint, P], I),
         "ltxb200_comm_wait_status": ([P, I, c_uint, P, P, c_uint, P], I),
         "ltxb200_peer_allgather": ([P, L, I, I, I, POINTER(c_void_p), POINTER(c_void_p), c_uint, P, P], I),
-        "ltxb200_qk_norm_rope_wan_scatter_rows_bf16": ([P, L, I, I, I, I, P, P, P, P, I, I, I, F, I, I, I, POINTER(c_void_p), POINTER(c_void_p), c_uint, P, c_uint, P], I),
+        "ltxb200_qk_norm_rope_wan_scatter_rows_bf16": ([P, L, I, I, I, I, P, P, P, P, I, I, I, F, I, I, I, POINTER(c_void_p), POINTER(c_void_p), c_uint, P, c_uint, I, P], I),
+        "ltxb200_gemm_qkv_vscatter_bf16": ([P, L, P, L, I, I, I, P, L, P, I, I, I, I, I, I, I, POINTER(c_void_p), P], I),
         "ltxb200_scatter_signal_ctas": ([I], c_uint),
         "ltxb200_qk_norm_rope_wan_scatter_bf16": ([P, L, I, I, P, P, P, P, I, I, I, F, I, I, I, POINTER(c_void_p), POINTER(c_void_p), c_uint, P, P], I),
         "ltxb200_attention_scatter_bf16": ([P, L, L, P, L, L, P, L, L, L, I, I, I, I, I, F, P, I, I, POINTER(c_void_p), POINTER(c_void_p), c_uint, P, I, I, P], I),

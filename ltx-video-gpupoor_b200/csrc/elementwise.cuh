@@ -429,7 +429,7 @@ qk_norm_rope_wan_kernel(__nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict
 // slice is stored straight into the receive buffer of the rank that owns those heads,
 //   recv_g[T, b, sel, h_local, :]   (T = global token, sel = q|k|v, g = head / Hp),
 // i.e. [N, B, 3, Hp, d] in global token order -- exactly the layout the attention kernel's TMA maps read.
-// grid.y = 3 (q, k, v).  The launch covers rows [row0, row_end) of the M local rows; `signal_ctas` CTAs (of this and the other
+// grid.y = 3 (q, k, v), or 2 when the V third already left from the QKV GEMM's epilogue (GemmParams::vs_peers).  The launch covers rows [row0, row_end) of the M local rows; `signal_ctas` CTAs (of this and the other
 // launches of the same exchange) arrive before the last one publishes the epoch flag on every peer (comm.cuh).
 // Rows are walked grid-stride by a BOUNDED grid (2 CTAs per SM and selector) with the next row's loads in flight: (a) every CTA
 // ends with a system-scope fence that waits for its peer stores to be acknowledged over NVLink, which the round-1 form paid once

@@ -13,6 +13,7 @@
 // replicate padding from clamping the frame coordinate (causal_conv3d.py:44-59).
 #pragma once
 #include "common.cuh"
+#include "comm.cuh"
 
 namespace b200 {
 
@@ -39,6 +40,12 @@ struct GemmParams {
   const __nv_bfloat16* gate;       // [ceil(M/rows_per_gate), gate_ld] or null
   int rows_per_gate;
   long long gate_ld;
+  // Ulysses sequence parallelism: the columns >= vs_col0 of a row-major bf16 output (the V third of the fused QKV projection, which needs
+  // no normalisation) are stored straight into the receive buffer of the rank that owns their heads, laid out [N, B, 3, H/P, d] in global
+  // token order (elementwise.cuh, qk_norm_rope_wan_scatter_kernel): one third of the exchange leaves from this epilogue, spread over the
+  // GEMM's run time, instead of being re-read and stored by the scatter kernel.  vs_peers.P == 0: off.
+  PeerPtrs vs_peers;
+  int vs_col0, vs_group_cols, vs_B, vs_tokens_per_batch, vs_token_offset, vs_row0;
   // `mixed` precision: fp32 residual stream and fp32 gate (same strides, in elements); used instead of the bf16 pointers when set
   const float* residual32;
   const float* gate32;
@@ -182,6 +189,13 @@ DEVI void epilogue_row(const GemmParams& p, uint32_t t_addr, int tn, bool row_ok
             if (full || n0 + j < p.N) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
         } else {
           __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + m_lin * p.ldc + n0;
+          if (p.vs_peers.P > 0 && n0 >= p.vs_col0) {         // warp-uniform: a 32-column chunk never straddles a head group
+            const long long row = p.vs_row0 + m_lin;
+            const int b = static_cast<int>(row / p.vs_tokens_per_batch);
+            const long long T = p.vs_token_offset + (row - static_cast<long long>(b) * p.vs_tokens_per_batch);
+            const int c = n0 - p.vs_col0, g = c / p.vs_group_cols;
+            o = static_cast<__nv_bfloat16*>(p.vs_peers.data[g]) + ((T * p.vs_B + b) * 3 + 2) * p.vs_group_cols + (c - g * p.vs_group_cols);
+          }
 #pragma unroll
           for (int j = 0; j < 32; j += 8)
             if (full || n0 + j < p.N)

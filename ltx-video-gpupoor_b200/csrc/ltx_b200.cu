@@ -111,10 +111,17 @@ static int launch_conv_halo(const CUtensorMap& ta, const CUtensorMap& tb, const 
   return launch_status();
 }
 
+static int fill_peers(PeerPtrs* pp, int P, int rank, void* const* data_ptrs, void* const* flag_ptrs, unsigned int epoch, void* counter);
+
+struct VScatter {          // see GemmParams::vs_peers
+  PeerPtrs peers;
+  int col0, group_cols, B, tokens_per_batch, token_offset, row0;
+};
+
 static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K,
                      void* out, int64_t ldc, int out_f32, const void* bias, int act,
                      const void* residual, int64_t ldr, const void* gate, int64_t gate_ld,
-                     int rows_per_gate, int mod_f32, void* stream) {
+                     int rows_per_gate, int mod_f32, void* stream, const VScatter* vs = nullptr) {
   if (M <= 0 || N <= 0 || K <= 0 || (K & 7) || (N & 7)) return kErrBadShape;
   if (!aligned16(A) || !aligned16(W) || !aligned16(out) || (lda & 7) || (ldw & 7) || (ldc & (out_f32 ? 3 : 7)))
     return kErrBadAlign;
@@ -146,6 +153,10 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, int
   else { p.residual = static_cast<const __nv_bfloat16*>(residual); p.gate = static_cast<const __nv_bfloat16*>(gate); }
   p.ldr = ldr; p.gate_ld = gate_ld; p.rows_per_gate = rows_per_gate > 0 ? rows_per_gate : 1;
   p.store_mode = kStoreRowMajor;
+  if (vs) {
+    p.vs_peers = vs->peers; p.vs_col0 = vs->col0; p.vs_group_cols = vs->group_cols; p.vs_B = vs->B;
+    p.vs_tokens_per_batch = vs->tokens_per_batch; p.vs_token_offset = vs->token_offset; p.vs_row0 = vs->row0;
+  }
   // the weights of this path always fit the 126 MB L2 (<= 34 MB); A often does not (FFN-down: 302 MB)
   p.n_fastest = (static_cast<long long>(N) * K * 2 <= (48ll << 20)) ? 1 : 0;
   if (const char* e = getenv("LTXB200_GEMM_RASTER")) p.n_fastest = atoi(e);
@@ -160,6 +171,23 @@ extern "C" int ltxb200_gemm_bf16(const void* A, int64_t lda, const void* W, int6
                                  const void* residual, int64_t ldr, const void* gate, int64_t gate_ld,
                                  int rows_per_gate, void* stream) {
   return gemm_impl(A, lda, W, ldw, M, N, K, out, ldc, out_f32, bias, act, residual, ldr, gate, gate_ld, rows_per_gate, 0, stream);
+}
+
+extern "C" int ltxb200_gemm_qkv_vscatter_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int K, int D, void* out,
+                                             int64_t ldc, const void* bias, int head_dim, int tokens_per_batch, int token_offset,
+                                             int row0, int B, int P, int rank, void* const* recv_ptrs, void* stream) {
+  if (D <= 0 || head_dim <= 0 || (head_dim % 32) || (D % head_dim) || ((D / head_dim) % P) || B <= 0 || tokens_per_batch <= 0 || row0 < 0)
+    return kErrBadShape;
+  VScatter vs{};
+  // no flag is touched here: the q/k scatter kernel that follows in the stream publishes the exchange's epoch
+  if (!recv_ptrs || P < 1 || P > kMaxPeers || rank < 0 || rank >= P) return kErrBadShape;
+  for (int r = 0; r < P; ++r) {
+    if (!recv_ptrs[r] || !aligned16(recv_ptrs[r])) return kErrBadAlign;
+    vs.peers.data[r] = recv_ptrs[r];
+  }
+  vs.peers.P = P; vs.peers.rank = rank;
+  vs.col0 = 2 * D; vs.group_cols = D / P; vs.B = B; vs.tokens_per_batch = tokens_per_batch; vs.token_offset = token_offset; vs.row0 = row0;
+  return gemm_impl(A, lda, W, ldw, M, 3 * D, K, out, ldc, 0, bias, kActNone, nullptr, 0, nullptr, 0, 1, 0, stream, &vs);
 }
 
 extern "C" int ltxb200_gemm_bf16_f32res(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K,
@@ -468,7 +496,7 @@ extern "C" int ltxb200_peer_allgather(const void* src, int64_t seg_bytes, int ns
 }
 
 // grid.x of one scatter launch over `rows` rows (grid-stride: at most 2 CTAs of 4 warps per SM and selector), and the CTAs it
-// contributes to the arrival counter (x 3 selectors)
+// contributes to the arrival counter (x 3 selectors; x 2 when V leaves from the GEMM epilogue)
 static inline unsigned int scatter_blocks(int rows) {
   const unsigned int want = static_cast<unsigned int>((rows + 3) / 4), cap = static_cast<unsigned int>(num_sms()) * 2u;
   return want < cap ? want : cap;
@@ -479,16 +507,16 @@ extern "C" int ltxb200_qk_norm_rope_wan_scatter_rows_bf16(const void* qkv, int64
                                                           const void* wk, const float* cos_table, const float* sin_table,
                                                           int head_dim, int tokens_per_batch, int token_offset, float eps, int B,
                                                           int P, int rank, void* const* recv_ptrs, void* const* flag_ptrs,
-                                                          unsigned int epoch, void* counter, unsigned int signal_ctas, void* stream) {
+                                                          unsigned int epoch, void* counter, unsigned int signal_ctas, int nsel, void* stream) {
   if (M <= 0 || D <= 0 || (D % 256) || B <= 0 || tokens_per_batch <= 0 || M != B * tokens_per_batch) return kErrBadShape;
-  if (row0 < 0 || rows <= 0 || row0 + rows > M || signal_ctas < scatter_ctas(rows)) return kErrBadShape;
+  if ((nsel != 2 && nsel != 3) || row0 < 0 || rows <= 0 || row0 + rows > M || signal_ctas < scatter_blocks(rows) * nsel) return kErrBadShape;
   if (!qkv || !aligned16(qkv) || (ld & 7) || !wq || !wk || !cos_table || !sin_table || !aligned16(cos_table) || !aligned16(sin_table))
     return kErrBadAlign;
   if (head_dim <= 0 || (head_dim & 7) || (D % head_dim) || ((D / head_dim) % P)) return kErrBadShape;
   PeerPtrs pp;
   if (int rc = fill_peers(&pp, P, rank, recv_ptrs, flag_ptrs, epoch, counter)) return rc;
   const int Hp = D / head_dim / P;
-  dim3 grid(scatter_blocks(rows), 3);
+  dim3 grid(scatter_blocks(rows), nsel);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   auto X = static_cast<const __nv_bfloat16*>(qkv);
   auto WQ = static_cast<const __nv_bfloat16*>(wq);
@@ -503,7 +531,7 @@ extern "C" int ltxb200_qk_norm_rope_wan_scatter_rows_bf16(const void* qkv, int64
   return launch_status();
 }
 
-extern "C" unsigned int ltxb200_scatter_signal_ctas(int rows) { return rows > 0 ? scatter_ctas(rows) : 0u; }
+extern "C" unsigned int ltxb200_scatter_signal_ctas(int rows) { return rows > 0 ? scatter_ctas(rows) : 0u; }   // per 3 selectors
 
 extern "C" int ltxb200_qk_norm_rope_wan_scatter_bf16(const void* qkv, int64_t ld, int M, int D, const void* wq, const void* wk,
                                                      const float* cos_table, const float* sin_table, int head_dim,
@@ -512,7 +540,7 @@ extern "C" int ltxb200_qk_norm_rope_wan_scatter_bf16(const void* qkv, int64_t ld
                                                      unsigned int epoch, void* counter, void* stream) {
   return ltxb200_qk_norm_rope_wan_scatter_rows_bf16(qkv, ld, M, 0, M, D, wq, wk, cos_table, sin_table, head_dim, tokens_per_batch,
                                                     token_offset, eps, B, P, rank, recv_ptrs, flag_ptrs, epoch, counter,
-                                                    M > 0 ? scatter_ctas(M) : 0u, stream);
+                                                    M > 0 ? scatter_ctas(M) : 0u, 3, stream);
 }
 
 extern "C" int ltxb200_attention_scatter_bf16(const void* q, int64_t ldq, int64_t bsq, const void* k, int64_t ldk, int64_t bsk,

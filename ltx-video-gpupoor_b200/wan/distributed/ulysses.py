@@ -121,6 +121,7 @@ class PeerExchange:
         self.gather_calls = 0
         self.chunks = max(1, int(os.environ.get("LTXB200_SP_CHUNKS", "1")))
         self.min_chunk_rows = 1024                 # below this a chunk's GEMM no longer fills the machine (tests lower it)
+        self.v_from_gemm = os.environ.get("LTXB200_SP_V_FROM_GEMM", "0") == "1"
         self.side = torch.cuda.Stream(device=device)
         self._closed = False
 
@@ -174,7 +175,12 @@ class PeerExchange:
         align = 256 if M // nch >= 512 else 8
         step = ((M + nch - 1) // nch + align - 1) // align * align
         bounds = [(r0, min(M, r0 + step)) for r0 in range(0, M, step)]
-        total_ctas = sum(int(lib.ltxb200_scatter_signal_ctas(r1 - r0)) for r0, r1 in bounds)
+        # LTXB200_SP_V_FROM_GEMM=1: V (a third of the exchange, no normalisation needed) leaves from the QKV GEMM's own epilogue and the
+        # scatter kernel handles q and k only.  Parity-tested, measured neutral at 4 GPUs (scatter -1.0 ms, GEMM +1.1 ms per step: the
+        # exchange is NVLink-bound wherever its stores are issued), so off by default
+        vgemm = self.v_from_gemm
+        nsel = 2 if vgemm else 3
+        total_ctas = sum(int(lib.ltxb200_scatter_signal_ctas(r1 - r0)) * nsel // 3 for r0, r1 in bounds)
         qkv = torch.empty(M, 3 * D, device=x_mod.device, dtype=x_mod.dtype)
         overlap = len(bounds) > 1 and ops.PROFILER is None       # the per-launch event timing of the bench probe needs one stream
         def scatter(r0, r1, st):
@@ -182,14 +188,23 @@ class PeerExchange:
                 self._check(lib.ltxb200_qk_norm_rope_wan_scatter_rows_bf16(
                     qkv.data_ptr(), qkv.stride(0), M, r0, r1 - r0, D, wq.data_ptr(), wk.data_ptr(), cos.data_ptr(), sin.data_ptr(),
                     d, n_loc, self.rank * n_loc, float(eps), B, P, self.rank, recv_ptrs, f0, epoch,
-                    self.local[ctl] + self.counter_off(0), total_ctas, st.cuda_stream), "qk_norm_rope_wan_scatter")
+                    self.local[ctl] + self.counter_off(0), total_ctas, nsel, st.cuda_stream), "qk_norm_rope_wan_scatter")
+
+        def qkv_gemm(r0, r1):
+            if not vgemm:
+                return ops.gemm(x_mod[r0:r1], w_qkv, b_qkv, out=qkv[r0:r1])
+            a, o = x_mod[r0:r1], qkv[r0:r1]
+            with ops._Prof('gemm_bf16', 'flop', 2.0 * (r1 - r0) * 3 * D * a.shape[1]):
+                self._check(lib.ltxb200_gemm_qkv_vscatter_bf16(
+                    a.data_ptr(), a.stride(0), w_qkv.data_ptr(), w_qkv.stride(0), r1 - r0, a.shape[1], D, o.data_ptr(), o.stride(0),
+                    b_qkv.data_ptr(), d, n_loc, self.rank * n_loc, r0, B, P, self.rank, recv_ptrs, main.cuda_stream), "gemm_qkv_vscatter")
 
         # chunk c's GEMM is enqueued BEFORE chunk c-1's scatter: both become runnable when GEMM c-1 retires and the block scheduler
         # serves launches in order, so the GEMM's CTAs (one per SM, ~200 KB of shared memory) take their slots first and the
         # scatter's small CTAs fill in beside them
         prev = None
         for r0, r1 in bounds:
-            ops.gemm(x_mod[r0:r1], w_qkv, b_qkv, out=qkv[r0:r1])
+            qkv_gemm(r0, r1)
             if not overlap:
                 scatter(r0, r1, main)
                 continue

@@ -29,7 +29,7 @@ def scatter(stream):
     epoch[0] += 1
     _lib.check(lib.ltxb200_qk_norm_rope_wan_scatter_rows_bf16(
         qkv2.data_ptr(), qkv2.stride(0), M, 0, M, D, wn.data_ptr(), wn.data_ptr(), cos.data_ptr(), sin.data_ptr(), 128, M, 0, 1e-6, 1, 1, 0,
-        VP(recv.data_ptr()), VP(ctl.data_ptr()), epoch[0], ctl.data_ptr() + 256, lib.ltxb200_scatter_signal_ctas(M), stream.cuda_stream), "scatter")
+        VP(recv.data_ptr()), VP(ctl.data_ptr()), epoch[0], ctl.data_ptr() + 256, lib.ltxb200_scatter_signal_ctas(M), 3, stream.cuda_stream), "scatter")
 
 
 def gemm():

@@ -121,15 +121,17 @@ def _sp_worker(rank, world, port, golden_dir, ret):
         m.load_state_dict(sd, device=dev)
         cos, sin = get_rotary_pos_embed(g["lat"].shape[1:])
         errs = {}
-        for mode, chunks in (("p2p", 4), ("p2p", 1), ("nccl", 1)):   # fused peer-memory exchange (chunked + overlapped, and in one piece) and the NCCL baseline
+        # fused peer-memory exchange — V from the QKV GEMM's epilogue (the default) or from the scatter kernel, in one piece or chunked on
+        # two streams — and the NCCL all-to-all baseline
+        for mode, chunks, vgemm in (("p2p", 1, True), ("p2p", 4, True), ("p2p", 1, False), ("p2p", 4, False), ("nccl", 1, False)):
             m.sp_exchange = mode
             if mode == "p2p":
                 ex = m._peer_exchange(2, 96 // world)
-                ex.chunks, ex.min_chunk_rows = chunks, 8              # 48 / 24 local rows: chunk anyway, so the two-stream path is what runs
+                ex.chunks, ex.min_chunk_rows, ex.v_from_gemm = chunks, 8, vgemm   # 48 / 24 local rows: chunk anyway, so the two-stream path runs
             for rep in range(3):          # several forwards: the peer buffers / epoch flags are reused across calls
                 y = m([g["lat"].to(dev), g["lat"].to(dev)], t=g["t"].to(dev), context=[g["ctx"].to(dev), g["ctx0"].to(dev)], freqs=(cos, sin))
             torch.cuda.synchronize()
-            errs[f"{mode}/{chunks}"] = max(W.rel_l2(a.cpu(), b) for a, b in zip(y, g["fwd"]))
+            errs[f"{mode}/chunks {chunks}/v-from-gemm {vgemm}"] = max(W.rel_l2(a.cpu(), b) for a, b in zip(y, g["fwd"]))
         m.close()
         ret[rank] = errs
     finally:
@@ -148,7 +150,7 @@ def test_wan_sequence_parallel(golden_dir, world):
     assert len(ret) == world
     for r, errs in ret.items():
         for mode, e in errs.items():
-            print(f"rank {r}: SP{world} forward ({mode} exchange/chunks) rel_l2 vs single-GPU reference = {e:.3e}")
+            print(f"rank {r}: SP{world} forward ({mode}) rel_l2 vs single-GPU reference = {e:.3e}")
             assert e < 2e-2
 
 
