@@ -224,6 +224,14 @@ int ltxb200_upsample2x_nhwc_bf16(const void* x, void* y, int64_t frames, int H, 
 int ltxb200_softmax_rows_f32_bf16(const float* s, int64_t ld_s, void* p, int64_t ld_p, int rows, int cols, float scale,
                                   void* stream);
 
+/* ltxb200_attention_bf16 with per-batch key lengths instead of an additive bias: batch element b attends to keys [0, key_lens[b]) only
+ * (device int32 [B], 1 <= key_lens[b] <= Lk).  For a right-padded prompt this is the reference's (1 - mask) * -10000 bias
+ * (transformer3d.py:411-415; utils/attention.py:179-180 forces sdpa for masks) without the bias pass and without the padded key blocks:
+ * exp(-10000 + s - m) is exactly 0 in fp32, so the result is the same. */
+int ltxb200_attention_klens_bf16(const void* q, int64_t ldq, int64_t bsq, const void* k, int64_t ldk, int64_t bsk, const void* v,
+                                 int64_t ldv, int64_t bsv, void* out, int64_t ldo, int64_t bso, int B, int H, int Lq, int Lk, int d,
+                                 float scale, const int* key_lens, void* stream);
+
 /* as ltxb200_attention_bf16, but out += attention(q, k, v) (bf16 read-modify-write in the epilogue): the image-token
  * branch of WanI2VCrossAttention, `x += img_x` (wan/modules/model.py:329-337), without a separate add pass. */
 int ltxb200_attention_acc_bf16(const void* q, int64_t ldq, int64_t bsq, const void* k, int64_t ldk, int64_t bsk,

@@ -27,6 +27,7 @@ def _declare(lib):
         "ltxb200_gemm_bf16": ([P, L, P, L, I, I, I, P, L, I, P, I, P, L, P, L, I, P], I),
         "ltxb200_conv3d_bf16": ([P, P, P, P, I, I, I, I, I, I, I, I, I, P, P], I),
         "ltxb200_attention_bf16": ([P, L, L, P, L, L, P, L, L, P, L, L, I, I, I, I, I, F, P, P], I),
+        "ltxb200_attention_klens_bf16": ([P, L, L, P, L, L, P, L, L, P, L, L, I, I, I, I, I, F, P, P], I),
         "ltxb200_attention_acc_bf16": ([P, L, L, P, L, L, P, L, L, P, L, L, I, I, I, I, I, F, P, P], I),
         "ltxb200_norm_mod_bf16": ([P, L, P, L, I, I, P, P, L, I, P, P, F, I, P], I),
         "ltxb200_qk_norm_rope_bf16": ([P, L, I, P, L, I, I, P, P, P, P, I, F, P], I),

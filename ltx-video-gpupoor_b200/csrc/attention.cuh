@@ -33,6 +33,8 @@ struct AttnParams {
   int B, H, Lq, Lk;
   float scale_log2;              // softmax scale * log2(e)
   const float* key_bias;         // [B, Lk] additive (natural-log domain) or null
+  const int* key_lens;           // [B] valid keys per batch element (1 <= key_lens[b] <= Lk) or null: keys beyond are ignored, i.e. the
+                                 // right-padded prompt mask of cross-attention WITHOUT a bias pass and without the padded key blocks
   __nv_bfloat16* out;            // [B, Lq, H*d] contiguous rows, row stride out_ld
   long long out_ld, out_bs;
   int pairs;                     // ceil(Lq / 256)
@@ -319,8 +321,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_half + kSBufs);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nblk = (p.Lk + BN - 1) / BN;
-  const int nsteps = 2 * nblk;
+  // key blocks of a work item: all of Lk, or the batch element's own valid prefix (key_lens)
+  auto item_keys = [&](int b) -> int { return p.key_lens ? __ldg(p.key_lens + b) : p.Lk; };
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ);
@@ -361,6 +363,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       int it = 0;
       for (int w = blockIdx.x; w < p.total; w += gridDim.x, ++it) {
         const int qp = w % p.pairs, bh = w / p.pairs, h = bh % p.H, b = bh / p.H;
+        const int nblk = (item_keys(b) + BN - 1) / BN;
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           mbar_wait_backoff(&q_empty[t], (it & 1) ^ 1);
@@ -397,6 +400,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       uint32_t kc0 = 0, vc = 0;      // K ring position of the item's first block / V ring counter
       uint32_t N0 = 0;               // global step counter at the start of the item
       int it = 0;
+      int nblk = 0, nsteps = 0;      // key blocks / steps of the CURRENT item (set at the top of the item loop)
       // S(m), m = item-local step: tile m&1, key block m>>1, TMEM buffer (N0+m) % kSBufs.
       // part: -1 = all BN keys; 1 = keys BN/2.. (issued first in split mode); 0 = keys 0..BN/2-1 (completes S(m))
       auto issue_s = [&](int m, int part) {
@@ -433,6 +437,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           umma_ts(to, tp + ks * 8, va + static_cast<uint32_t>(ks * (2048 >> 4)), idesc_o, (acc || ks > ks0) ? 1u : 0u);
       };
       for (int w = blockIdx.x; w < p.total; w += gridDim.x, ++it) {
+        nblk = (item_keys((w / p.pairs) / p.H) + BN - 1) / BN;
+        nsteps = 2 * nblk;
 #pragma unroll 1
         for (int m = 0; m < kSBufs && m < nsteps; ++m) issue_s(m, -1);
         // step n: O_t += P(n).V(j), then S(n + kSBufs) into the buffer P(n) leaves
@@ -486,6 +492,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     for (int w = blockIdx.x; w < p.total; w += gridDim.x, ++it) {
       const int qp = w % p.pairs, bh = w / p.pairs, h = bh % p.H, b = bh / p.H;
       const float* bias = p.key_bias ? p.key_bias + static_cast<long long>(b) * p.Lk : nullptr;
+      const int Lk_b = item_keys(b);
+      const int nblk = (Lk_b + BN - 1) / BN;
       float m_ref = 0.f, m_run = 0.f, l = 0.f;
       for (int j = 0; j < nblk; ++j, ++G) {
         const uint32_t N = 2 * G + t, buf = N % kSBufs;
@@ -497,18 +505,18 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         if constexpr (kHalf) {
           float* xm = xmax + ((t * 2 + half) * 2 + (G & 1)) * 128 + row;
           const float* xp = xmax + ((t * 2 + (half ^ 1)) * 2 + (G & 1)) * 128 + row;
-          if (kMasked && (bias != nullptr || kbase + BN > p.Lk))
-            softmax_block_half<D, BN, true>(tS, tO + half * (D / 2), half, j == 0, kbase, p.Lk, bias, p.scale_log2, m_ref, m_run, l, &pv_done[t],
+          if (kMasked && (bias != nullptr || kbase + BN > Lk_b))
+            softmax_block_half<D, BN, true>(tS, tO + half * (D / 2), half, j == 0, kbase, Lk_b, bias, p.scale_log2, m_ref, m_run, l, &pv_done[t],
                                             (G - 1) & 1, xm, xp, pair_bar);
           else
-            softmax_block_half<D, BN, false>(tS, tO + half * (D / 2), half, j == 0, kbase, p.Lk, bias, p.scale_log2, m_ref, m_run, l, &pv_done[t],
+            softmax_block_half<D, BN, false>(tS, tO + half * (D / 2), half, j == 0, kbase, Lk_b, bias, p.scale_log2, m_ref, m_run, l, &pv_done[t],
                                              (G - 1) & 1, xm, xp, pair_bar);
         } else
-        if (kMasked && (bias != nullptr || kbase + BN > p.Lk))
-          softmax_block<D, BN, true>(tS, tO, j == 0, kbase, p.Lk, bias, p.scale_log2, m_ref, m_run, l, &pv_done[t], (G - 1) & 1,
+        if (kMasked && (bias != nullptr || kbase + BN > Lk_b))
+          softmax_block<D, BN, true>(tS, tO, j == 0, kbase, Lk_b, bias, p.scale_log2, m_ref, m_run, l, &pv_done[t], (G - 1) & 1,
                                       kSplit ? &s_read[buf] : nullptr, kSplit ? &p_half[buf] : nullptr, lane);
         else
-          softmax_block<D, BN, false>(tS, tO, j == 0, kbase, p.Lk, bias, p.scale_log2, m_ref, m_run, l, &pv_done[t], (G - 1) & 1,
+          softmax_block<D, BN, false>(tS, tO, j == 0, kbase, Lk_b, bias, p.scale_log2, m_ref, m_run, l, &pv_done[t], (G - 1) & 1,
                                       kSplit ? &s_read[buf] : nullptr, kSplit ? &p_half[buf] : nullptr, lane);
         tmem_wait_st();
         tc_fence_before();

@@ -388,7 +388,7 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
 static int attention_impl(const void* q, int64_t ldq, int64_t bsq, const void* k, int64_t ldk, int64_t bsk,
                           const void* v, int64_t ldv, int64_t bsv, void* out, int64_t ldo, int64_t bso, int B, int H,
                           int Lq, int Lk, int d, float scale, const float* key_bias, const PeerPtrs* peers,
-                          int tokens_per_peer, int head_offset, int accumulate, void* stream) {
+                          int tokens_per_peer, int head_offset, int accumulate, void* stream, const int* key_lens = nullptr) {
   if (B <= 0 || H <= 0 || Lq <= 0 || Lk <= 0 || B > 65535 || H > 65535) return kErrBadShape;
   if (d != 64 && d != 128) return kErrUnsupported;
   if (!peers && !out) return kErrBadAlign;
@@ -405,6 +405,7 @@ static int attention_impl(const void* q, int64_t ldq, int64_t bsq, const void* k
   const float sc = scale > 0.f ? scale : 1.0f / sqrtf(static_cast<float>(d));
   p.scale_log2 = sc * 1.4426950408889634f;
   p.key_bias = key_bias;
+  p.key_lens = key_lens;
   p.out = static_cast<__nv_bfloat16*>(out); p.out_ld = ldo; p.out_bs = bso;
   p.pairs = (Lq + 2 * kAttnBM - 1) / (2 * kAttnBM);
   const long long total = static_cast<long long>(B) * H * p.pairs;
@@ -413,7 +414,7 @@ static int attention_impl(const void* q, int64_t ldq, int64_t bsq, const void* k
   if (peers) { p.peers = *peers; p.tokens_per_peer = tokens_per_peer; p.head_offset = head_offset; }
   p.accumulate = accumulate;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const bool masked = (key_bias != nullptr) || (Lk % BN != 0);
+  const bool masked = (key_bias != nullptr) || (Lk % BN != 0) || (key_lens != nullptr);
   if (d == 64) return masked ? launch_attn<64, true>(tq, tk, tv, p, st) : launch_attn<64, false>(tq, tk, tv, p, st);
   return masked ? launch_attn<128, true>(tq, tk, tv, p, st) : launch_attn<128, false>(tq, tk, tv, p, st);
 }
@@ -423,6 +424,13 @@ extern "C" int ltxb200_attention_bf16(const void* q, int64_t ldq, int64_t bsq, c
                                       int B, int H, int Lq, int Lk, int d, float scale, const float* key_bias,
                                       void* stream) {
   return attention_impl(q, ldq, bsq, k, ldk, bsk, v, ldv, bsv, out, ldo, bso, B, H, Lq, Lk, d, scale, key_bias, nullptr, 0, 0, 0, stream);
+}
+
+extern "C" int ltxb200_attention_klens_bf16(const void* q, int64_t ldq, int64_t bsq, const void* k, int64_t ldk, int64_t bsk,
+                                            const void* v, int64_t ldv, int64_t bsv, void* out, int64_t ldo, int64_t bso,
+                                            int B, int H, int Lq, int Lk, int d, float scale, const int* key_lens, void* stream) {
+  if (!key_lens) return kErrBadAlign;
+  return attention_impl(q, ldq, bsq, k, ldk, bsk, v, ldv, bsv, out, ldo, bso, B, H, Lq, Lk, d, scale, nullptr, nullptr, 0, 0, 0, stream, key_lens);
 }
 
 extern "C" int ltxb200_attention_acc_bf16(const void* q, int64_t ldq, int64_t bsq, const void* k, int64_t ldk, int64_t bsk,

@@ -224,7 +224,7 @@ class LTXVideoPipeline:
             timestep=st.t_in, skip_layer_mask=st.skip_layer_masks[i] if st.skip_layer_masks is not None else None,
             skip_layer_strategy=st.skip_layer_strategy, latent_shape=st.latent_shape[2:], joint_pass=st.joint_pass,
             ltxv_model=st.ltxv_model, return_dict=False, shared_prefix=getattr(st, "shared_prefix", None),
-            mixed=getattr(st, "mixed", False))[0]
+            mixed=getattr(st, "mixed", False), encoder_key_lens=getattr(st, "key_lens_b", None))[0]
         if noise_pred is None:
             return None
         n = N * C
@@ -326,8 +326,16 @@ class LTXVideoPipeline:
         enc_b, mask_b = enc_b.contiguous(), mask_b.contiguous()
         # an all-ones prompt mask is a zero key bias ((1 - 1) * -10000, transformer3d.py:411-415): pass none at all, so that the 28
         # cross-attention launches per forward take the kernel's unmasked path (one host read per CALL, not per step)
+        key_lens_b = None
         if bool((mask_b == 1).all()):
             mask_b = None
+        else:
+            # a RIGHT-PADDED mask (ones, then zeros: what the tokenizer's padding="max_length" gives) is a per-sample key length: the
+            # kernel then skips the padded key blocks and the bias pass altogether (Transformer3DModel.forward, `encoder_key_lens`)
+            mh = (mask_b > 0).to("cpu")
+            lens = mh.sum(dim=1)
+            if bool((lens >= 1).all()) and bool((mh == (torch.arange(mh.shape[1])[None, :] < lens[:, None])).all()):
+                key_lens_b = lens.to(device=device, dtype=torch.int32).contiguous()
 
         # ---- latents (:1056-1088); drawn in prompt_embeds' dtype like the reference (:1061), kept as an fp32 master copy
         noise_dtype = prompt_embeds.dtype if prompt_embeds.dtype in (torch.float32, BF16) else torch.float32
@@ -360,7 +368,7 @@ class LTXVideoPipeline:
             freqs_cis=freqs_cis, N=N, C=C, bsz=bsz, lat32=lat32, lat16=lat16, cmask_dev=cmask_dev, scratch=scratch, x_in=x_in,
             t_in=t_in, latent_shape=latent_shape, joint_pass=joint_pass, ltxv_model=ltxv_model, generator=generator,
             image_cond_noise_scale=image_cond_noise_scale, init_tokens=init_tokens, tokens_shape=tuple(tokens.shape),
-            stochastic_sampling=bool(stochastic_sampling), mixed=bool(mixed_precision),
+            stochastic_sampling=bool(stochastic_sampling), mixed=bool(mixed_precision), key_lens_b=key_lens_b,
             # extension (off by default): the perturbed STG condition repeats the text condition's inputs, so its rows are
             # copies of the text rows until the first skipped block (Transformer3DModel.forward, `shared_prefix`)
             shared_prefix=(bsz, int(do_cfg) * bsz) if (kwargs.get("share_stg_prefix", False) and do_stg and skip_layer_masks is not None and bsz == 1) else None))

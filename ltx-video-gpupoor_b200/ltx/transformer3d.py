@@ -184,7 +184,7 @@ class Transformer3DModel(ModuleLike):
                 attention_mask: Optional[torch.Tensor] = None, encoder_attention_mask: Optional[torch.Tensor] = None,
                 skip_layer_mask: Optional[torch.Tensor] = None, skip_layer_strategy: Optional[SkipLayerStrategy] = None,
                 latent_shape=None, joint_pass: bool = True, ltxv_model=None, mixed: bool = False,
-                return_dict: bool = True, shared_prefix: Optional[tuple] = None):
+                return_dict: bool = True, shared_prefix: Optional[tuple] = None, encoder_key_lens: Optional[torch.Tensor] = None):
         """transformer3d.py:328-507.  hidden_states [B,N,C_in]; freqs_cis (cos,sin) [1|B,N,D]; encoder_hidden_states
         [B,L,caption_channels]; timestep [B,1] | [B,N]; encoder_attention_mask [B,L] (1 keep / 0 drop) or bias
         [B,1,L]; skip_layer_mask [layers,B].  `joint_pass=False` (per-sample iteration for offloaded weights,
@@ -201,6 +201,13 @@ class Transformer3DModel(ModuleLike):
             x_in = x_in.contiguous()
 
         # --- cross-attention key bias (transformer3d.py:411-415): (1-mask)*-10000 in the model dtype
+        # extension: `encoder_key_lens` int32 [B] = number of valid prompt tokens when the mask is RIGHT-PADDED (ones then zeros, what the
+        # tokenizer produces): the same attention as the (1 - mask) * -10000 bias (exp(-10000 + ...) is exactly 0 in fp32) without the bias
+        # pass and without the padded key blocks.  The pipeline derives it once per call from the host mask; it replaces the mask here.
+        key_lens = None
+        if encoder_key_lens is not None:
+            key_lens = encoder_key_lens.to(device=dev, dtype=torch.int32).contiguous()
+            encoder_attention_mask = None
         key_bias = None
         if encoder_attention_mask is not None:
             m = encoder_attention_mask.to(dev)
@@ -276,8 +283,9 @@ class Transformer3DModel(ModuleLike):
                 x, B = expand(x), B_full
             if B != B_full:
                 ctx_l, key_bias_l = ctx[: B * Lc], (key_bias[:B] if key_bias is not None else None)
+                key_lens_l = key_lens[:B] if key_lens is not None else None
             else:
-                ctx_l, key_bias_l = ctx, key_bias
+                ctx_l, key_bias_l, key_lens_l = ctx, key_bias, key_lens
             a = ada[li]                                                             # [B*T, 6, D]
             layer_skip = skip_host is not None and float(skip_host[li].min()) != 1.0
             # SkipLayerStrategy.Residual needs no branch: the reference only applies it under `attn.residual_connection`
@@ -301,7 +309,7 @@ class Transformer3DModel(ModuleLike):
             kv = ops.gemm(ctx_l, Lw["kv2.w"], Lw["kv2.b"])                          # [B*Lc, 2D]
             ops.qk_norm_rope(q2, kv[:, :D], Lw["qn2"], Lw["kn2"], None, None, eps=1e-5)
             o2 = ops.attention(q2.view(B, N, H, dh), kv.view(B, Lc, 2 * D)[:, :, :D].unflatten(-1, (H, dh)),
-                               kv.view(B, Lc, 2 * D)[:, :, D:].unflatten(-1, (H, dh)), key_bias=key_bias_l)
+                               kv.view(B, Lc, 2 * D)[:, :, D:].unflatten(-1, (H, dh)), key_bias=key_bias_l, key_lens=key_lens_l)
             gemm_res(o2.view(B * N, D), Lw["o2.w"], Lw["o2.b"], residual=x, out=x)
             # ---- feed forward (attention.py:314-351)
             nh = norm_mod(x, a[:, 4], a[:, 3], rows_per_group=rows_per_group, eps=self.config.norm_eps)

@@ -184,9 +184,11 @@ def conv3d_norm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], 
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_bias: Optional[torch.Tensor] = None,
-              scale: float = 0.0, out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+              scale: float = 0.0, out: Optional[torch.Tensor] = None, accumulate: bool = False,
+              key_lens: Optional[torch.Tensor] = None) -> torch.Tensor:
     """q [B,Lq,H,d], k/v [B,Lk,H,d] bf16 (strided views allowed, head stride must be d) -> [B,Lq,H,d].
-    accumulate: out += attention (out must be given)."""
+    accumulate: out += attention (out must be given).  key_lens int32 [B] (device): batch element b attends to its first key_lens[b]
+    keys only (a right-padded prompt mask without the bias pass / the padded key blocks); exclusive with key_bias."""
     for t, n in ((q, "q"), (k, "k"), (v, "v")):
         _req(t, name=n)
         assert t.dim() == 4 and t.stride(2) == t.shape[3], f"{n}: heads must be packed (stride(2) == d)"
@@ -199,12 +201,16 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, key_bias: Optio
     _req(out, name="out")
     if key_bias is not None:
         _req(key_bias, torch.float32, "key_bias"); assert key_bias.shape == (B, Lk) and key_bias.is_contiguous()
+    args = (q.data_ptr(), q.stride(1), q.stride(0), k.data_ptr(), k.stride(1), k.stride(0),
+            v.data_ptr(), v.stride(1), v.stride(0), out.data_ptr(), out.stride(1), out.stride(0), B, H, Lq, Lk, d, float(scale))
     with _Prof('attention_bf16', 'flop', 4.0 * B * H * Lq * Lk * d):
-        fn = _lib.lib().ltxb200_attention_acc_bf16 if accumulate else _lib.lib().ltxb200_attention_bf16
-        rc = fn(
-        q.data_ptr(), q.stride(1), q.stride(0), k.data_ptr(), k.stride(1), k.stride(0),
-        v.data_ptr(), v.stride(1), v.stride(0), out.data_ptr(), out.stride(1), out.stride(0),
-        B, H, Lq, Lk, d, float(scale), _p(key_bias), _stream())
+        if key_lens is not None:
+            _req(key_lens, torch.int32, "key_lens")
+            assert key_bias is None and not accumulate and key_lens.shape == (B,) and key_lens.is_contiguous()
+            rc = _lib.lib().ltxb200_attention_klens_bf16(*args, key_lens.data_ptr(), _stream())
+        else:
+            fn = _lib.lib().ltxb200_attention_acc_bf16 if accumulate else _lib.lib().ltxb200_attention_bf16
+            rc = fn(*args, _p(key_bias), _stream())
     _lib.check(rc, "attention_bf16")
     return out
 

@@ -37,6 +37,9 @@ if which in ("all", "attn", "xattn"):
     bias = torch.zeros(B, L, device=dev)
     timeit("cross-attention d64 B3 N6144 L256 bias", lambda: ops.attention(q, k, v, key_bias=bias), 4.0 * B * H * N * L * d)
     timeit("cross-attention d64 B3 N6144 L256 nobias", lambda: ops.attention(q, k, v), 4.0 * B * H * N * L * d)
+    for lens in ([256, 256, 256], [200, 120, 200], [100, 30, 100]):
+        kl = torch.tensor(lens, dtype=torch.int32, device=dev)
+        timeit(f"cross-attention d64 B3 N6144 L256 key_lens {lens} (flops counted on 256 keys)", lambda: ops.attention(q, k, v, key_lens=kl), 4.0 * B * H * N * L * d)
 if which in ("all", "attn128"):
     B, N, H, d = 1, 32760, 12, 128
     q, k, v = [torch.randn(B, N, H, d, device=dev).bfloat16() for _ in range(3)]

@@ -423,3 +423,26 @@ def test_conv3d_fused_pixelnorm_silu_output(Cin, Cout, H, W, keep_raw):
     assert rel(n, n_ref.float()) < 2e-3
     yf = (ref_conv(x, w5, b, False).permute(0, 2, 3, 4, 1) + res.float())
     assert rel(n, F.silu(yf * torch.rsqrt(yf.pow(2).mean(-1, keepdim=True) + 1e-8))) < 8e-3
+
+
+@pytest.mark.parametrize("d", [64, 128])
+@pytest.mark.parametrize("B,H,Lq,Lk,lens", [(3, 4, 700, 256, [256, 77, 1]), (2, 2, 1300, 256, [129, 128]), (4, 32, 6144, 256, [200, 200, 31, 256]),
+                                           (2, 3, 300, 640, [513, 60])])
+def test_attention_key_lens(d, B, H, Lq, Lk, lens):
+    """Per-batch key lengths (ltxb200_attention_klens_bf16): element b attends to its first lens[b] keys — the right-padded prompt mask of
+    cross-attention without the bias pass and without the padded key blocks.  Same result as the (1 - mask) * -10000 bias the reference
+    builds (transformer3d.py:411-415) and as the fp32 reference; every CTA walks items with DIFFERENT numbers of key blocks here."""
+    q, k, v = rnd(B, Lq, H, d, seed=1), rnd(B, Lk, H, d, seed=2), rnd(B, Lk, H, d, seed=3)
+    kl = torch.tensor(lens, dtype=torch.int32, device=DEV)
+    bias = torch.zeros(B, Lk, device=DEV)
+    for b, n in enumerate(lens):
+        bias[b, n:] = -10000.0
+    out = ops.attention(q, k, v, key_lens=kl)
+    out_bias = ops.attention(q, k, v, key_bias=bias)
+    torch.cuda.synchronize()
+    assert rel(out, out_bias.float()) < 4e-3
+    if B * H * Lq * Lk <= 3 * 4 * 1300 * 640:
+        assert rel(out, ref_attn(q, k, v, bias)) < 1e-2
+    # run it again right behind an ordinary launch: ring / barrier phases must not depend on a launch-wide block count
+    o2 = ops.attention(q, k, v, key_lens=kl)
+    assert torch.equal(o2, out)

@@ -676,3 +676,37 @@ def test_transformer_and_pipeline_mixed_precision(golden_dir):
         e = O.rel_l2(a.cpu(), b)
         print(f"pipeline mixed_precision step {i}: latents rel_l2 vs the fp32 oracle = {e:.3e}")
         assert e < TOL_LATENTS
+
+
+def test_pipeline_right_padded_prompt_mask_uses_key_lengths():
+    """A right-padded prompt mask (what the tokenizer produces) is turned into per-sample key lengths once per call (no bias pass, padded
+    key blocks skipped); a mask with a hole in it keeps the additive bias.  Both must give the latents of the oracle loop, and the
+    key-length path must agree with the bias path on the same mask."""
+    pipe, sd, _ = _pipe(2)
+    g = torch.Generator().manual_seed(17)
+    pe, ne = torch.randn(1, 200, 4096, generator=g), torch.randn(1, 200, 4096, generator=g)
+    pm, nm = torch.ones(1, 200), torch.ones(1, 200)
+    pm[:, 141:] = 0
+    nm[:, 9:] = 0
+    kw = dict(height=128, width=192, num_frames=17, frame_rate=25.0, prompt_embeds=pe, negative_prompt_embeds=ne, num_inference_steps=3,
+              guidance_scale=3.0, stg_scale=0.0, rescaling_scale=1.0, output_type="latent", return_dict=False, is_video=True)
+    a = pipe(prompt_attention_mask=pm, negative_prompt_attention_mask=nm, generator=torch.Generator().manual_seed(4), **kw)[0]
+    assert pipe._state.key_lens_b is not None and pipe._state.mask_b is not None and pipe._state.key_lens_b.tolist() == [9, 141]
+    saved = pipe._state.key_lens_b
+    st = pipe(prompt_attention_mask=pm, negative_prompt_attention_mask=nm, generator=torch.Generator().manual_seed(4), _prepare_only=True, **kw)
+    st.key_lens_b = None                                     # the same call on the additive-bias path
+    for i in range(3):
+        pipe.denoise_step(st, i)
+    b = pipe.patchifier.unpatchify(st.lat32.view(1, st.N, st.C), 4, 6, 128)
+    torch.cuda.synchronize()
+    e_ab = O.rel_l2(a.float().cpu(), b.float().cpu())
+    noise = torch.randn(1, 72, 128, generator=torch.Generator().manual_seed(4))
+    ref = O.denoise_loop(sd, O.LTX_2B, noise, pe, pm, num_frames_lat=3, lat_h=4, lat_w=6, frame_rate=25.0, num_steps=3, neg_enc=ne, neg_mask=nm,
+                         guidance_scale=3.0)
+    e = O.rel_l2(a.float().cpu(), O.unpatchify(ref, 3, 4, 6))
+    print(f"right-padded masks as key lengths {saved.tolist()}: final latents rel_l2 vs oracle {e:.3e}; vs the additive-bias path {e_ab:.3e}")
+    assert e < TOL_LATENTS and e_ab < 5e-3
+    pm2 = pm.clone()
+    pm2[:, 20] = 0                                           # a hole: not a key length
+    pipe(prompt_attention_mask=pm2, negative_prompt_attention_mask=nm, generator=torch.Generator().manual_seed(4), **kw)
+    assert pipe._state.key_lens_b is None and pipe._state.mask_b is not None
