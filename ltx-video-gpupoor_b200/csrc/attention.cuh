@@ -154,6 +154,10 @@ DEVI void softmax_block(uint32_t tS, uint32_t tO, bool first, int kbase, int Lk,
                         uint64_t* s_read, uint64_t* p_half, int lane) {
   const float kLog2e = 1.4426950408889634f;
   const bool bias_vec = bias != nullptr && ((reinterpret_cast<uintptr_t>(bias) | (static_cast<uintptr_t>(kbase) << 2)) & 15) == 0;
+  // A partial key block WITHOUT a bias (the tail of a sequence; the last block of a right-padded prompt given as a key length) takes the
+  // lean path too: the raw scores of the keys beyond Lk are replaced by -inf (exp2 gives 0, the polynomial 2^-126) and everything else —
+  // max on the raw scores, scale folded into the exp, packed arithmetic, polynomial share — is the code of a full block.
+  const bool lean_tail = kPredicated && bias == nullptr;        // warp-uniform
   uint32_t v[BN];
   float mx0 = -INFINITY, mx1 = -INFINITY;
   tmem_ld32(tS, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
@@ -161,7 +165,19 @@ DEVI void softmax_block(uint32_t tS, uint32_t tO, bool first, int kbase, int Lk,
   for (int c = 0; c < BN; c += 32) {
     tmem_wait_ld();
     if (c + 32 < BN) tmem_ld32(tS + c + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c + 32]));
-    if (kPredicated) {
+    if (lean_tail) {
+      const int nv = Lk - kbase - c;                            // valid keys in this 32-column chunk
+      if (nv < 32) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i >= nv) v[c + i] = 0xff800000u;                  // -inf
+      }
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        mx0 = fmax3(mx0, __uint_as_float(v[c + i]), __uint_as_float(v[c + i + 1]));
+        mx1 = fmax3(mx1, __uint_as_float(v[c + i + 2]), __uint_as_float(v[c + i + 3]));
+      }
+    } else if (kPredicated) {
       if (kbase + BN <= Lk && bias_vec) {
         // full block with a 16B-aligned bias row: vector loads (every lane reads the same addresses: one broadcast
         // transaction each), no tail predication
@@ -200,7 +216,7 @@ DEVI void softmax_block(uint32_t tS, uint32_t tO, bool first, int kbase, int Lk,
     if (lane == 0) mbar_arrive(s_read);
   }
   float m_blk = fmaxf(mx0, mx1);
-  if (!kPredicated) m_blk *= sc;                 // scale > 0: max commutes with the scaling
+  if (!kPredicated || lean_tail) m_blk *= sc;    // scale > 0: max commutes with the scaling
   if (first) {
     m_run = m_blk;
     m_ref = (m_blk == -INFINITY) ? 0.f : m_blk;
@@ -211,7 +227,8 @@ DEVI void softmax_block(uint32_t tS, uint32_t tO, bool first, int kbase, int Lk,
   uint64_t ls[2] = {0ull, 0ull};
 #pragma unroll
   for (int c = 0; c < BN; c += 32) {
-    exp_chunk<kPredicated, LTXB200_ATTN_POLY>(&v[c], sc, -m_ref, tS + (c >> 1), ls);
+    if (kPredicated && !lean_tail) exp_chunk<true, LTXB200_ATTN_POLY>(&v[c], sc, -m_ref, tS + (c >> 1), ls);
+    else exp_chunk<false, LTXB200_ATTN_POLY>(&v[c], sc, -m_ref, tS + (c >> 1), ls);
     if (p_half && c + 32 == BN / 2) {            // P of keys 0..BN/2-1 is in TMEM: their P.V may start
       tmem_wait_st();
       tc_fence_before();

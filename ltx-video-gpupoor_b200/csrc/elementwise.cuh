@@ -353,6 +353,81 @@ qk_norm_rope_tok_kernel(__nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict
   }
 }
 
+// Wide rows (D = 4096: LTX-Video 13B): the token's q / k rows do not fit one warp's registers next to the table row and the prefetched
+// next row, so a token is handled by a warp PAIR (each warp NVH chunks = half of the columns, its half of the cos / sin row resident);
+// the two partial sums of squares meet in shared memory (slot parity = row parity: a slot is rewritten only after the barrier of the
+// following row).  Same arithmetic per element; the row statistic is the sum of two warp sums instead of one (fp32 rounding only).
+template <int NVH>
+__global__ void __launch_bounds__(128)
+qk_norm_rope_tok2_kernel(__nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict__ k, int B, int tokens, long long ldq, long long ldk,
+                         const __nv_bfloat16* __restrict__ wq, const __nv_bfloat16* __restrict__ wk,
+                         const __nv_bfloat16* __restrict__ cosT, const __nv_bfloat16* __restrict__ sinT, float eps) {
+  constexpr int D = NVH * 512;
+  __shared__ float red[2][2][2];                      // [token of the CTA][row parity][half]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tp = warp >> 1, half = warp & 1;
+  const int tok_raw = blockIdx.x * 2 + tp;
+  const bool active = tok_raw < tokens;
+  const int tok = active ? tok_raw : tokens - 1;      // idle pair: same loads, no stores (keeps the barriers uniform)
+  const int col0 = half * NVH * 256;
+  uint4 cv[NVH], sv[NVH], xv[NVH], xn[NVH];
+  auto row_ptr = [&](int r) -> __nv_bfloat16* {
+    const int b = r % B;
+    return ((r < B) ? q + (static_cast<long long>(b) * tokens + tok) * ldq : k + (static_cast<long long>(b) * tokens + tok) * ldk) + col0;
+  };
+  {
+    const __nv_bfloat16* x0 = row_ptr(0);
+#pragma unroll
+    for (int i = 0; i < NVH; ++i) xv[i] = *reinterpret_cast<const uint4*>(x0 + (i * 32 + lane) * 8);
+    const long long trow = static_cast<long long>(tok) * D + col0;
+#pragma unroll
+    for (int i = 0; i < NVH; ++i) {
+      cv[i] = ldg16(cosT + trow + (i * 32 + lane) * 8);
+      sv[i] = ldg16(sinT + trow + (i * 32 + lane) * 8);
+    }
+  }
+#pragma unroll 1
+  for (int r = 0; r < 2 * B; ++r) {
+    __nv_bfloat16* xr = row_ptr(r);
+    if (r + 1 < 2 * B) {
+      const __nv_bfloat16* xnext = row_ptr(r + 1);
+#pragma unroll
+      for (int i = 0; i < NVH; ++i) xn[i] = *reinterpret_cast<const uint4*>(xnext + (i * 32 + lane) * 8);
+    }
+    const __nv_bfloat16* w = ((r < B) ? wq : wk) + col0;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NVH; ++i) {
+      float v[8];
+      unpack8(xv[i], v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sq += v[j] * v[j];
+    }
+    sq = warp_sum(sq);
+    if (lane == 0) red[tp][r & 1][half] = sq;
+    __syncthreads();
+    const float rs = rsqrtf((red[tp][r & 1][0] + red[tp][r & 1][1]) * (1.0f / D) + eps);
+#pragma unroll
+    for (int i = 0; i < NVH; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      float v[8];
+      unpack8(xv[i], v);
+      const uint4 w4 = ldg16(w + c);
+      uint32_t o[4] = {bf2_mul(pack_bf16(v[0] * rs, v[1] * rs), w4.x), bf2_mul(pack_bf16(v[2] * rs, v[3] * rs), w4.y),
+                       bf2_mul(pack_bf16(v[4] * rs, v[5] * rs), w4.z), bf2_mul(pack_bf16(v[6] * rs, v[7] * rs), w4.w)};
+      const uint32_t cs[4] = {cv[i].x, cv[i].y, cv[i].z, cv[i].w}, sn[4] = {sv[i].x, sv[i].y, sv[i].z, sv[i].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t rot = __byte_perm(o[j], 0, 0x1032) ^ 0x00008000u;     // (-y[2i+1], y[2i])
+        o[j] = bf2_add(bf2_mul(o[j], cs[j]), bf2_mul(rot, sn[j]));
+      }
+      if (active) *reinterpret_cast<uint4*>(xr + c) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+#pragma unroll
+    for (int i = 0; i < NVH; ++i) xv[i] = xn[i];
+  }
+}
+
 DEVI void load_cos_sin(const float* __restrict__ cosT, const float* __restrict__ sinT, long long off, float (&cs)[8], float (&sn)[8]) {
   const float4 c0 = __ldg(reinterpret_cast<const float4*>(cosT + off)), c1 = __ldg(reinterpret_cast<const float4*>(cosT + off + 4));
   const float4 s0 = __ldg(reinterpret_cast<const float4*>(sinT + off)), s1 = __ldg(reinterpret_cast<const float4*>(sinT + off + 4));
@@ -367,7 +442,7 @@ DEVI void load_cos_sin(const float* __restrict__ cosT, const float* __restrict__
 // first global token under Ulysses sequence parallelism, xdit_context_parallel.py:52-57).
 // ------------------------------------------------------------------------------------------
 template <int NV>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, (NV > 12 ? 3 : 1))      // wide rows: cap the allocation at 168 registers (3 CTAs / SM), not 255
 qk_norm_rope_wan_kernel(__nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict__ k, int Mq, int Mk, long long ldq,
                         long long ldk, const __nv_bfloat16* __restrict__ wq, const __nv_bfloat16* __restrict__ wk,
                         const float* __restrict__ cosT, const float* __restrict__ sinT, int head_dim,
@@ -383,15 +458,20 @@ qk_norm_rope_wan_kernel(__nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
   __nv_bfloat16* xr = base + row * ld;
-  float v[NV][8];
+  uint4 xv[NV];                                       // the row stays PACKED between the passes (160 unpacked floats at D = 5120 would spill)
 #pragma unroll
-  for (int i = 0; i < NV; ++i) load8(xr + (i * 32 + lane) * 8, v[i]);
+  for (int i = 0; i < NV; ++i) xv[i] = *reinterpret_cast<const uint4*>(xr + (i * 32 + lane) * 8);
   float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < NV; ++i)
+  for (int i = 0; i < NV; ++i) {
+    float t[8];
+    unpack8(xv[i], t);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) sq += v[i][j] * v[i][j];
+    for (int j = 0; j < 8; ++j) sq += t[j] * t[j];
+  }
   const float rs = rsqrtf(warp_sum(sq) * (1.0f / D) + eps);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) asm volatile("" : "+r"(xv[i].x), "+r"(xv[i].y), "+r"(xv[i].z), "+r"(xv[i].w));   // keep it packed (no CSE with the pass above)
   const long long trow = cosT ? static_cast<long long>(token_offset + row % tokens_per_batch) * head_dim : 0;
   // every head of a token shares the token's cos / sin row, and a lane's column offset inside its head is the same in every
   // 256-column chunk when head_dim divides 256 (it is 128): the 16 table values are loaded ONCE per row instead of once per chunk
@@ -405,7 +485,8 @@ qk_norm_rope_wan_kernel(__nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict
     float o[8];
     {
       const uint4 w4 = ldg16(w + c);
-      const float (&vv)[8] = v[i];
+      float vv[8];
+      unpack8(xv[i], vv);
       unpack8(make_uint4(bf2_mul(pack_bf16(vv[0] * rs, vv[1] * rs), w4.x), bf2_mul(pack_bf16(vv[2] * rs, vv[3] * rs), w4.y),
                          bf2_mul(pack_bf16(vv[4] * rs, vv[5] * rs), w4.z), bf2_mul(pack_bf16(vv[6] * rs, vv[7] * rs), w4.w)), o);
     }
@@ -421,6 +502,7 @@ qk_norm_rope_wan_kernel(__nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict
     } else {
       store8(xr + c, o);
     }
+    if (NV > 12) asm volatile("" ::: "memory");       // wide rows: keep later chunks' weight loads from being hoisted (registers)
   }
 }
 

@@ -667,6 +667,11 @@ extern "C" int ltxb200_qk_norm_rope_bf16(void* q, int64_t ldq, int Mq, void* k, 
   auto Sn = static_cast<const __nv_bfloat16*>(sin_table);
   // self-attention shape (q and k rows of the same B*tokens grid, RoPE): one warp per TOKEN, the table row read once for all 2*B rows
   static const int env_tok = getenv("LTXB200_ROPE_TOKEN_MAJOR") ? atoi(getenv("LTXB200_ROPE_TOKEN_MAJOR")) : 1;
+  if (env_tok && C && q && k && Mq == Mk && (Mq % tokens_per_batch) == 0 && D == 4096) {          // LTX-Video 13B: a warp pair per token
+    const int Bq = Mq / tokens_per_batch;
+    qk_norm_rope_tok2_kernel<8><<<dim3((tokens_per_batch + 1) / 2), 128, 0, st>>>(Q, Kp, Bq, tokens_per_batch, ldq, ldk, WQ, WK, C, Sn, eps);
+    return launch_status();
+  }
   if (env_tok && C && q && k && Mq == Mk && (Mq % tokens_per_batch) == 0 && D <= 2048) {
     const int Bq = Mq / tokens_per_batch;
     dim3 gt((tokens_per_batch + 3) / 4);

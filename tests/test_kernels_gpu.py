@@ -151,7 +151,7 @@ def test_conv3d_d2s_and_unpatch():
 
 
 # ------------------------------------------------------------------ memory-bound kernels
-@pytest.mark.parametrize("D", [2048, 1536, 512])
+@pytest.mark.parametrize("D", [2048, 1536, 512, 4096, 5120])
 @pytest.mark.parametrize("ln", [False, True])
 def test_norm_mod(D, ln):
     M, rpg = 77, 20
@@ -171,14 +171,16 @@ def test_norm_mod(D, ln):
                    F.layer_norm(xf, (D,), w.float(), b.float(), eps=1e-6)) < 5e-3
 
 
-def test_qk_norm_rope_matches_oracle():
-    B, N, D = 2, 96, 2048
+@pytest.mark.parametrize("B,N,D", [(2, 96, 2048), (3, 95, 4096), (1, 96, 1024)])
+def test_qk_norm_rope_matches_oracle(B, N, D):
+    """D = 2048: one warp per token (qk_norm_rope_tok_kernel); D = 4096 (LTX-Video 13B): a warp pair per token, odd token count;
+    both against the fp32 reference and with the v third of the fused buffer untouched"""
     qkv = rnd(B * N, 3 * D, seed=1)
     wq, wk = (1 + 0.1 * rnd(D, seed=2).float()).to(BF), (1 + 0.1 * rnd(D, seed=3).float()).to(BF)
     coords = O.latent_to_pixel_coords(O.latent_coords(2, 6, 8, 1)).float()
     coords[:, 0] /= 25.0
     cos, sin = O.precompute_freqs_cis(coords, D, 10000.0, (20, 2048, 2048), BF)
-    cos, sin = cos[0].contiguous().to(DEV), sin[0].contiguous().to(DEV)
+    cos, sin = cos[0, :N].contiguous().to(DEV), sin[0, :N].contiguous().to(DEV)
     q, k = qkv[:, :D], qkv[:, D:2 * D]
     refq = O.apply_rotary_emb(O.rms_norm(q.float().view(B, N, D), 1e-5, wq.float()), cos.float(), sin.float())
     refk = O.apply_rotary_emb(O.rms_norm(k.float().view(B, N, D), 1e-5, wk.float()), cos.float(), sin.float())
