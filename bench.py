@@ -188,21 +188,35 @@ def cpu_reference_sample(wl):
 
 
 def run_reference(args, wl_name, wl):
-    """The reference's own CPU implementation of the path on the box's host cores.  ONE bounded sample per run whatever K is
-    (a full 768x512x121 step takes minutes on a CPU: the full-size figure is extrapolated from 1- and 3-layer forwards and marked
-    so), plus BASELINE configs[0] — 256x256x9, 4 steps + VAE decode — run FOR REAL through the reference's LTXVideoPipeline."""
+    """The reference's own CPU implementation of the path on the box's host cores.  ONE bounded sample per run whatever K is:
+    for the 2B workloads ONE WHOLE denoise step of the bench workload, for real — the unmodified reference Transformer3DModel.forward
+    at full size, all 28 layers, all guidance conditions in one batch (30-60 s on the 16-32 host threads of a GPU box; nothing
+    extrapolated) — plus BASELINE configs[0] — 256x256x9, 4 steps + VAE decode — through the reference's LTXVideoPipeline.
+    LTXB200_REF_EXTRAPOLATE=1, the 13B workload or a missing oracle/_ref fall back to the 1- and 3-layer sample, marked extrapolated."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     t_start = time.perf_counter()
-    s, base = cpu_reference_sample(wl)
+    from oracle import ref_runner
+    real = ref_runner.available() and wl.get("arch", "2b") == "2b" and not os.environ.get("LTXB200_REF_EXTRAPOLATE")
+    tr = None
+    if real:
+        cores = host_threads()
+        tr = ref_runner.reference_2b_transformer()
+        s = ref_runner.full_step_real(wl, tr)
+        base = {"value": 1.0 / s["step_s"], "unit": "steps/s", "cores": cores, "kind": "reference", "extrapolated": False,
+                "sample": (f"ONE whole denoise step, measured: the unmodified reference Transformer3DModel.forward (oracle/_ref, fp32) on {cores} host "
+                           f"threads at full size N={s['tokens']}, L={wl['prompt_tokens']}, all 28 layers, {s['conds']} guidance conditions in one batch "
+                           f"(STG skip-layer mask included): {s['step_s']:.1f} s"),
+                "sample_wall_s": s["step_s"]}
+    else:
+        s, base = cpu_reference_sample(wl)
     v, step_s = base["value"], s["step_s"]
     config0 = None
     if not os.environ.get("LTXB200_BENCH_SKIP_CONFIG0"):
         try:
-            from oracle import ref_runner
             if ref_runner.available():
-                c0 = ref_runner.config0()
+                c0 = ref_runner.config0(tr=tr)
                 config0 = {"workload": "BASELINE configs[0]: LTX-2B (28 layers) t2v 256x256x9, 4 steps + VAE decode, fp32, host CPU",
                            "measured": True, "extrapolated": False, "steps_per_s": c0["steps_per_s"], "denoise_loop_s": c0["loop_s"],
                            "s_per_video": c0["video_s"], "cores": base["cores"],
@@ -211,7 +225,7 @@ def run_reference(args, wl_name, wl):
             config0 = {"error": repr(exc)[:300]}
     line = {"impl": "reference", "metric": "denoise_steps_per_s", "value": v, "unit": "steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "extrapolated": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "extrapolated": bool(base.get("extrapolated")),
             "timed": {"samples": 1, "sample_wall_s": base["sample_wall_s"], "run_wall_s": None,
                       "note": "steps/warmup echo the request; ONE bounded sample is timed per run (see cpu_baseline.sample)"},
             "config": ltx_config(wl_name, wl, LTX_ARCH[wl.get("arch", "2b")]["layers"], args.gpus), "cpu_baseline": base, "config0_real": config0,

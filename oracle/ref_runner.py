@@ -6,6 +6,9 @@ Two measurements:
   * `config0()`         — BASELINE.json configs[0] for real: the reference LTXVideoPipeline.__call__
                           (pipeline_ltx_video.py:763) with its own Transformer3DModel (28 layers) and CausalVideoAutoencoder,
                           t2v 256x256x9, 4 denoise steps + VAE decode, fp32;
+  * `full_step_real()`   — configs[1] for real: ONE whole denoise step of the bench workload (768x512x121 -> 6144 tokens, all 28
+                          layers, all num_conds guidance conditions in one batched forward incl. the STG skip-layer mask — the
+                          call pipeline_ltx_video.py:1153-1177 makes once per step), timed, nothing extrapolated (30-60 s);
   * `full_size_sample()` — a bounded sample of configs[1] (768x512x121 -> 6144 tokens): the reference
                           Transformer3DModel.forward (transformer3d.py:328) at full size with 1 and 3 layers; per-layer and
                           fixed costs are separated and EXTRAPOLATED to 28 layers x num_conds (one full step takes minutes).
@@ -111,7 +114,51 @@ def full_size_sample(wl: dict, layers=(1, 3)) -> dict:
     return dict(step_s=step_s, t_layer=t_layer, t_fixed=t_fixed, raw=times, tokens=N, sample_s=sum(times.values()))
 
 
-def config0(steps: int = 4) -> dict:
+def _full_size_inputs(wl, batch):
+    from oracle import ltx_oracle as O
+    torch.manual_seed(0)
+    f, h, w = wl["num_frames"] // 8 + 1, wl["height"] // 32, wl["width"] // 32
+    N = f * h * w
+    hidden = torch.randn(batch, N, 128)
+    enc = torch.randn(batch, wl["prompt_tokens"], 4096)
+    mask = torch.ones(batch, wl["prompt_tokens"])
+    coords = O.latent_to_pixel_coords(O.latent_coords(f, h, w, 1)).float()
+    coords[:, 0] /= wl["frame_rate"]
+    ts = torch.full((batch, 1), 0.5)
+    return (f, h, w), N, hidden, enc, mask, coords.expand(batch, -1, -1).contiguous(), ts
+
+
+def reference_2b_transformer():
+    """The unmodified reference Transformer3DModel at the full 28 layers (1.92 B seeded fp32 weights)."""
+    _install()
+    from oracle import ltx_oracle as O
+    sd = O.make_transformer_state_dict(O.LTX_2B, seed=0, num_layers=28)
+    return _ref_transformer(28, sd)
+
+
+def full_step_real(wl: dict, tr=None) -> dict:
+    """ONE whole denoise step of the bench workload through the reference's own Transformer3DModel.forward: every layer, every
+    guidance condition (batched the way pipeline_ltx_video.py:1034-1051 batches them, STG skip-layer mask :1137-1150 included).
+    The guidance arithmetic and the scheduler update that complete a step (:1189-1235) are elementwise work on 3 MB tensors."""
+    _install()
+    from ltx_video.utils.skip_layer_strategy import SkipLayerStrategy
+    if tr is None:
+        tr = reference_2b_transformer()
+    conds = wl["num_conds"]
+    latent_shape, N, hidden, enc, mask, coords, ts = _full_size_inputs(wl, conds)
+    freqs = tr.precompute_freqs_cis(coords)
+    kw = {}
+    if conds == 3:                                 # the 2B preset: STG on block 19, perturbed condition last
+        kw = dict(skip_layer_mask=tr.create_skip_layer_mask(1, conds, conds - 1, [19]), skip_layer_strategy=SkipLayerStrategy.AttentionValues)
+    t0 = time.perf_counter()
+    out = tr(hidden, freqs_cis=freqs, encoder_hidden_states=enc, timestep=ts, encoder_attention_mask=mask, latent_shape=latent_shape,
+             joint_pass=True, ltxv_model=_NoInterrupt(), return_dict=False, **kw)[0]
+    step_s = time.perf_counter() - t0
+    assert out.shape == hidden.shape and bool(torch.isfinite(out).all())
+    return dict(step_s=step_s, tokens=N, conds=conds, layers=28, sample_s=step_s)
+
+
+def config0(steps: int = 4, tr=None) -> dict:
     """BASELINE configs[0], timed for real through the reference's own pipeline call (loop alone, then loop + decode)."""
     _install()
     from ltx_video.models.autoencoders.causal_video_autoencoder import CausalVideoAutoencoder
@@ -120,9 +167,8 @@ def config0(steps: int = 4) -> dict:
     from ltx_video.schedulers.rf import RectifiedFlowScheduler
     from ltx_video.utils.diffusers_config_mapping import OURS_SCHEDULER_CONFIG, OURS_VAE_CONFIG
     from oracle import ltx_oracle as O
-    sd = O.make_transformer_state_dict(O.LTX_2B, seed=0, num_layers=28)
-    tr = _ref_transformer(28, sd)
-    del sd
+    if tr is None:
+        tr = reference_2b_transformer()
     vsd = O.make_vae_decoder_state_dict(seed=1)
     vae = CausalVideoAutoencoder.from_config(dict(OURS_VAE_CONFIG))
     vae.decoder.load_state_dict({k[len("decoder."):]: v for k, v in vsd.items() if k.startswith("decoder.")}, strict=True)
