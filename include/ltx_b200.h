@@ -97,6 +97,15 @@ int ltxb200_qk_norm_rope_wan_bf16(void* q, int64_t ldq, int Mq, void* k, int64_t
  * (wan/utils/fm_solvers_unipc.py:321,458-484,590-626; wan/text2video.py:562).  out may alias an input. */
 int ltxb200_lincomb_f32(float* out, int64_t n, int terms, const float* const* xs, const float* coefs, void* stream);
 
+/* RectifiedFlowScheduler.step with PER-TOKEN timesteps (ltx_video/schedulers/rf.py:361-375): token r (timestep tok_timesteps[r])
+ * looks up the next entry of the descending `schedule` strictly below its timestep - 1e-6 (0 if none) and takes
+ *   out = x - (t - lower) * v                              (noise == NULL), or
+ *   out = (1 - next) * (x - t * v) + next * noise, next = t - (t - lower)   (stochastic sampling, rf.py:370-373; add_noise :382-392).
+ * x, v, noise, out: [tokens, channels] fp32 (channels % 4 == 0); fp32 arithmetic with the reference expression's rounding
+ * points (no contraction): equal to the PyTorch result bit for bit.  out may alias x.  (ABI version 4.) */
+int ltxb200_rf_step_tokens_f32(float* out, const float* x, const float* v, const float* noise, const float* tok_timesteps,
+                               int64_t tokens, int channels, const float* schedule, int num_steps, void* stream);
+
 /* ada[l,g,j,:] = table[l,j,:] + temb[g, j*D:(j+1)*D]  (attention.py:239-241), JD = 6*D. */
 int ltxb200_ada_add_bf16(const void* table, const void* temb, void* out, int L, int G, int JD, void* stream);
 

@@ -33,6 +33,7 @@ def _declare(lib):
         "ltxb200_qk_norm_rope_bf16": ([P, L, I, P, L, I, I, P, P, P, P, I, F, P], I),
         "ltxb200_qk_norm_rope_wan_bf16": ([P, L, I, P, L, I, I, P, P, P, P, I, I, I, F, P], I),
         "ltxb200_lincomb_f32": ([P, L, I, P, P, P], I),
+        "ltxb200_rf_step_tokens_f32": ([P, P, P, P, P, L, I, P, I, P], I),
         "ltxb200_ada_add_bf16": ([P, P, P, I, I, I, P], I),
         "ltxb200_act_bf16": ([P, P, L, I, P], I),
         "ltxb200_stg_blend_bf16": ([P, P, L, P, I, L, I, P], I),

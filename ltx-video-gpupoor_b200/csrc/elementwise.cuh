@@ -617,6 +617,45 @@ __global__ void lincomb_f32_kernel(float* __restrict__ out, long long n, const L
 }
 
 // ------------------------------------------------------------------------------------------
+// RectifiedFlowScheduler.step with PER-TOKEN timesteps (rf.py:361-375): every token finds the next schedule entry strictly below
+// its own timestep - 1e-6 (0 if none) and takes   prev = x - (t - lower) * v,   or with `noise` (rf.py:370-373)
+// prev = (1 - next) * (x - t * v) + next * noise, next = t - (t - lower).   fp32 with the reference's rounding points (separate multiply and add, no
+// contraction), so the result equals the PyTorch expression bit for bit.  x, v, noise, out: [tokens, channels] fp32.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rf_step_tokens_kernel(float* __restrict__ out, const float* __restrict__ x, const float* __restrict__ v, const float* __restrict__ noise,
+                      const float* __restrict__ tok_t, long long tokens, int channels, const float* __restrict__ schedule, int num_steps) {
+  const int c4 = channels / 4;
+  const long long n4 = tokens * c4;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n4; i += static_cast<long long>(gridDim.x) * 256) {
+    const float t = __ldg(tok_t + i / c4);
+    float lower = 0.f;
+    for (int s = 0; s < num_steps; ++s) {
+      const float ts = __ldg(schedule + s);
+      if (ts < __fsub_rn(t, 1e-6f)) { lower = ts; break; }       // the schedule descends: the first hit is the largest
+    }
+    const float dt = __fsub_rn(t, lower);
+    const float4 xv = reinterpret_cast<const float4*>(x)[i], vv = reinterpret_cast<const float4*>(v)[i];
+    float4 o;
+    if (noise) {
+      const float4 z = reinterpret_cast<const float4*>(noise)[i];
+      const float nxt = __fsub_rn(t, dt);                        // next_timestep = timestep - dt, as the reference rounds it (:372)
+      const float a = __fsub_rn(1.0f, nxt);
+      o.x = __fadd_rn(__fmul_rn(a, __fsub_rn(xv.x, __fmul_rn(t, vv.x))), __fmul_rn(nxt, z.x));
+      o.y = __fadd_rn(__fmul_rn(a, __fsub_rn(xv.y, __fmul_rn(t, vv.y))), __fmul_rn(nxt, z.y));
+      o.z = __fadd_rn(__fmul_rn(a, __fsub_rn(xv.z, __fmul_rn(t, vv.z))), __fmul_rn(nxt, z.z));
+      o.w = __fadd_rn(__fmul_rn(a, __fsub_rn(xv.w, __fmul_rn(t, vv.w))), __fmul_rn(nxt, z.w));
+    } else {
+      o.x = __fsub_rn(xv.x, __fmul_rn(dt, vv.x));
+      o.y = __fsub_rn(xv.y, __fmul_rn(dt, vv.y));
+      o.z = __fsub_rn(xv.z, __fmul_rn(dt, vv.z));
+      o.w = __fsub_rn(xv.w, __fmul_rn(dt, vv.w));
+    }
+    reinterpret_cast<float4*>(out)[i] = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // ada[l, g, j, :] = table[l, j, :] + temb[g, j*D:(j+1)*D]   (bf16 add; attention.py:239-241)
 // ------------------------------------------------------------------------------------------
 __global__ void ada_add_kernel(const __nv_bfloat16* __restrict__ table, const __nv_bfloat16* __restrict__ temb,

@@ -39,7 +39,7 @@ static inline int ew_blocks(long long work_items, int threads) {
   return static_cast<int>(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
-extern "C" int ltxb200_abi_version(void) { return 3; }
+extern "C" int ltxb200_abi_version(void) { return 4; }
 extern "C" long long ltxb200_launch_count(void) { return g_launches.load(); }
 extern "C" const char* ltxb200_error_string(int code) {
   switch (code) {
@@ -733,6 +733,16 @@ extern "C" int ltxb200_lincomb_f32(float* out, int64_t n, int terms, const float
     p.c[j] = coefs[j];
   }
   lincomb_f32_kernel<<<ew_blocks(n / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(out, n, p);
+  return launch_status();
+}
+
+extern "C" int ltxb200_rf_step_tokens_f32(float* out, const float* x, const float* v, const float* noise, const float* tok_timesteps,
+                                          int64_t tokens, int channels, const float* schedule, int num_steps, void* stream) {
+  if (tokens <= 0 || channels <= 0 || (channels & 3) || num_steps < 0 || !out || !x || !v || !tok_timesteps || (num_steps > 0 && !schedule))
+    return kErrBadShape;
+  if (!aligned16(out) || !aligned16(x) || !aligned16(v) || (noise && !aligned16(noise))) return kErrBadAlign;
+  rf_step_tokens_kernel<<<ew_blocks(tokens * (channels / 4), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      out, x, v, noise, tok_timesteps, tokens, channels, schedule, num_steps);
   return launch_status();
 }
 

@@ -165,17 +165,35 @@ class RectifiedFlowScheduler:
 
     def step(self, model_output: torch.Tensor, timestep, sample: torch.Tensor, return_dict: bool = True,
              stochastic_sampling: Optional[bool] = False, **kwargs) -> Union[RectifiedFlowSchedulerOutput, Tuple]:
-        """rf.py:311-380 for a GLOBAL timestep (0-d, or any one-element tensor): prev = sample - dt * model_output, or with
-        stochastic_sampling (:370-373) add_noise(sample - t * model_output, randn, t - dt); computed in fp32 by the linear-combination
-        kernel (fp32 predictions are not truncated) and returned in the promoted dtype of `sample` and `model_output`, as the
-        reference's tensor arithmetic does.  The N(0,1) draw comes from `generator=` / `noise=` in kwargs (the reference uses the
-        global RNG).  Per-token [B, N] timesteps (:361-367) exist for conditioned tokens and go through the pipeline's fused
-        guidance/step kernel with its conditioning mask (`LTXVideoPipeline.denoise_step`): NotImplementedError here."""
+        """rf.py:311-380: prev = sample - dt * model_output, or with stochastic_sampling (:370-373)
+        add_noise(sample - t * model_output, randn, t - dt); fp32 arithmetic (fp32 predictions are not truncated), result in the promoted
+        dtype of `sample` and `model_output`, as the reference's tensor arithmetic gives.  The N(0,1) draw comes from `generator=` /
+        `noise=` in kwargs (the reference uses the global RNG).  A GLOBAL timestep (0-d, or any one-element tensor) is a host scalar
+        on the linear-combination kernel; PER-TOKEN timesteps [B, N] (:361-367; sample [B, N, C]) go through `ltxb200_rf_step_tokens_f32`,
+        which repeats the reference expression's fp32 rounding points (bit-identical to the reference on fp32 inputs)."""
         if self.num_inference_steps is None:
             raise ValueError("Number of inference steps is 'None', you need to run 'set_timesteps' after creating the scheduler")
         tt = torch.as_tensor(timestep)
         if tt.numel() != 1:
-            raise NotImplementedError("per-token timesteps are handled by LTXVideoPipeline.denoise_step (fused guidance/step kernel)")
+            assert tt.ndim == 2, "timestep must be 0-d (global) or [B, N] (per token)"                   # rf.py:362
+            assert sample.dim() == 3 and tuple(sample.shape[:2]) == tuple(tt.shape) and model_output.shape == sample.shape
+            dev = model_output.device
+            out_dtype = torch.promote_types(torch.promote_types(sample.dtype, model_output.dtype), tt.dtype if tt.is_floating_point() else torch.float32)
+            C = sample.shape[-1]
+            x = sample.to(device=dev, dtype=torch.float32).contiguous().view(-1, C)
+            v = model_output.to(torch.float32).contiguous().view(-1, C)
+            z = None
+            if stochastic_sampling:
+                z = kwargs.get("noise")
+                if z is None:
+                    z = torch.randn(sample.shape, device=dev, dtype=torch.float32, generator=kwargs.get("generator"))
+                z = z.to(device=dev, dtype=torch.float32).contiguous().view(-1, C)
+            sched = self.timesteps_host.to(device=dev, dtype=torch.float32).contiguous()
+            prev = ops.rf_step_tokens(x, v, tt.to(device=dev, dtype=torch.float32).contiguous().view(-1), sched, noise=z)
+            prev = prev.view(sample.shape).to(out_dtype)
+            if not return_dict:
+                return (prev,)
+            return RectifiedFlowSchedulerOutput(prev_sample=prev)
         t = float(tt.reshape(-1)[0])
         dev = model_output.device
         out_dtype = torch.promote_types(sample.dtype, model_output.dtype)

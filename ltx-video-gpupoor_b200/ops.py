@@ -402,6 +402,24 @@ def lincomb(out: torch.Tensor, terms) -> torch.Tensor:
     return out
 
 
+def rf_step_tokens(x: torch.Tensor, v: torch.Tensor, tok_timesteps: torch.Tensor, schedule: torch.Tensor,
+                   noise: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """rf.py:361-375 with per-token timesteps: x, v (and noise) [tokens, C] fp32, tok_timesteps [tokens] fp32, schedule [S] fp32 descending."""
+    _req(x, torch.float32, "x"); _req(v, torch.float32, "v"); _req(tok_timesteps, torch.float32, "tok_timesteps"); _req(schedule, torch.float32, "schedule")
+    assert x.dim() == 2 and x.shape == v.shape and x.is_contiguous() and v.is_contiguous()
+    tokens, C = x.shape
+    assert tok_timesteps.is_contiguous() and tok_timesteps.numel() == tokens and schedule.is_contiguous() and C % 4 == 0
+    if noise is not None:
+        _req(noise, torch.float32, "noise"); assert noise.is_contiguous() and noise.shape == x.shape
+    out = torch.empty_like(x) if out is None else out
+    _req(out, torch.float32, "out"); assert out.is_contiguous() and out.shape == x.shape
+    with _Prof("rf_step_tokens_f32", "byte", 4.0 * x.numel() * (3 + (noise is not None))):
+        rc = _lib.lib().ltxb200_rf_step_tokens_f32(out.data_ptr(), x.data_ptr(), v.data_ptr(), _p(noise), tok_timesteps.data_ptr(), tokens, C,
+                                                   schedule.data_ptr(), schedule.numel(), _stream())
+    _lib.check(rc, "rf_step_tokens_f32")
+    return out
+
+
 def cfg_combine(cond: torch.Tensor, uncond: torch.Tensor, guide_scale: float, use_alpha: bool,
                 scratch: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _req(cond, torch.float32, "cond"); _req(uncond, torch.float32, "uncond")

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/ltx_b200.h but not exported"
     assert sorted(_lib.EXPORTED_SYMBOLS) == names, "ctypes signatures out of sync with the header"
-    assert lib.ltxb200_abi_version() == 3
+    assert lib.ltxb200_abi_version() == 4
     assert lib.ltxb200_error_string(-2).decode().startswith("pointer")
 
 

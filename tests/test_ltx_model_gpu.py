@@ -403,8 +403,13 @@ def test_rf_stochastic_step_vs_reference_formula():
         det16 = s.step(v.to(DEV, torch.bfloat16), ts[i], x.to(DEV, torch.bfloat16), return_dict=False)[0]
         assert det16.dtype == torch.bfloat16
         assert O.rel_l2(det16.float().cpu(), x.bfloat16().float() - (t - tn) * v.bfloat16().float()) < 8e-3
-    with pytest.raises(NotImplementedError):                  # per-token timesteps belong to the pipeline's fused step
-        s.step(v.to(DEV), torch.full((1, 72), 0.5), x.to(DEV))
+    # per-token [B, N] timesteps (rf.py:361-367): every token looks up its own next-lower schedule entry
+    tok = torch.rand(1, 72, generator=g)
+    tok[0, :3] = torch.tensor([float(ts[1]), float(ts[-1]), 1e-7])          # exactly on the schedule / on its last entry / below everything
+    out = s.step(v.to(DEV), tok.to(DEV), x.to(DEV), return_dict=False)[0]
+    assert out.dtype == torch.float32 and torch.equal(out.cpu(), O.rf_step(v, tok, x, ts))
+    out = s.step(v.to(DEV), tok.to(DEV), x.to(DEV), return_dict=False, stochastic_sampling=True, noise=nz.to(DEV))[0]
+    assert torch.equal(out.cpu(), O.rf_step_stochastic(v, tok, x, ts, nz))
     # through the pipeline: runs, is reproducible for a seeded generator, and differs from the deterministic sampler
     pipe, sd, _ = _pipe(1)
     kw = dict(height=128, width=192, num_frames=17, frame_rate=25.0, prompt_embeds=torch.randn(1, 16, 4096, generator=g),
@@ -414,6 +419,22 @@ def test_rf_stochastic_step_vs_reference_formula():
     b = pipe(**kw, generator=torch.Generator().manual_seed(1), stochastic_sampling=True)[0]
     c = pipe(**kw, generator=torch.Generator().manual_seed(1))[0]
     assert torch.equal(a, b) and O.rel_l2(a.cpu(), c.cpu()) > 1e-2
+
+
+def test_rf_step_per_token_timesteps_vs_reference_fixture(golden_dir):
+    """`RectifiedFlowScheduler.step` with per-token [B, N] timesteps against what the unmodified reference scheduler returned
+    (`rf_scheduler.pt`: deterministic and stochastic, the noise the reference drew replayed): fp32, bit for bit."""
+    g = _load(golden_dir, "rf_scheduler.pt")
+    for case in g.values():
+        s = RectifiedFlowScheduler()
+        s.set_timesteps(case["steps"], samples_shape=case["shape"], device=DEV)
+        assert torch.equal(s.timesteps_host, case["timesteps"])
+        out = s.step(case["v"].to(DEV), case["tt"].to(DEV), case["x"].to(DEV), return_dict=False)[0]
+        assert torch.equal(out.cpu(), case["stepped"])
+        st = case["stochastic"][-1]
+        assert st["t"].shape == case["tt"].shape
+        out = s.step(case["v"].to(DEV), st["t"].to(DEV), case["x"].to(DEV), return_dict=False, stochastic_sampling=True, noise=st["noise"].to(DEV))[0]
+        assert torch.equal(out.cpu(), st["out"])
 
 
 def test_reference_selfcheck_encoder_first_frame_causality_gpu():
