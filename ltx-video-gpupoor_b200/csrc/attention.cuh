@@ -116,12 +116,26 @@ DEVI void rescale_o(uint32_t tO, bool need, float m_new, float& m_ref, float& l,
 // The scale/shift and the row sum run as FFMA2 / FADD2 (half the issue slots of the scalar form), and kPolyPer8 of every
 // 8 element pairs take their exponentials from the FMA-pipe polynomial instead of MUFU.EX2, which is what bounds the
 // d = 64 kernel (profiles/scripts/mufu_bench2.cu: 14.3 -> 18.0 exp/clk/SM at 2 softmax warps per scheduler).
-#ifndef LTXB200_ATTN_POLY
-#define LTXB200_ATTN_POLY 2
+// Share (of every 8 pairs) and degree of the polynomial exponentials, per head dim.  Measured on one box (profiles/r02_ncu_summary.md,
+// attention section): d = 64 — degree 3 x 2/8: 916 TF/s, degree 2 x 2/8: 935, degree 3 x 3/8: 917, degree 2 x 3/8: 967, x 4/8: 919, x 5/8: 882.
+#ifndef LTXB200_ATTN_POLY_D64
+#define LTXB200_ATTN_POLY_D64 3
 #endif
-template <bool kScaled, int kPolyPer8>
-DEVI void exp_chunk(const uint32_t* v, float sc, float neg_m, uint32_t tP, uint64_t (&ls)[2]) {
-  uint32_t pk[16];
+#ifndef LTXB200_ATTN_POLY_DEG_D64
+#define LTXB200_ATTN_POLY_DEG_D64 2
+#endif
+#ifndef LTXB200_ATTN_POLY_D128
+#define LTXB200_ATTN_POLY_D128 2
+#endif
+#ifndef LTXB200_ATTN_POLY_DEG_D128
+#define LTXB200_ATTN_POLY_DEG_D128 3
+#endif
+template <int D> struct AttnPoly {
+  static constexpr int kPer8 = (D == 64) ? LTXB200_ATTN_POLY_D64 : LTXB200_ATTN_POLY_D128;
+  static constexpr int kDeg = (D == 64) ? LTXB200_ATTN_POLY_DEG_D64 : LTXB200_ATTN_POLY_DEG_D128;
+};
+template <bool kScaled, int kPolyPer8, int kDeg>
+DEVI void exp_chunk_pk(const uint32_t* v, float sc, float neg_m, uint32_t (&pk)[16], uint64_t (&ls)[2]) {
   const uint64_t NM = pack_f32x2(neg_m, neg_m);
   const uint64_t SC = pack_f32x2(sc, sc);
 #pragma unroll
@@ -132,7 +146,7 @@ DEVI void exp_chunk(const uint32_t* v, float sc, float neg_m, uint32_t tP, uint6
     float e0, e1;
     const bool poly = !kScaled && (((p & 7) + 1) * kPolyPer8 / 8 != (p & 7) * kPolyPer8 / 8);   // spread over the 8 pairs
     if (poly) {
-      exp2_poly_f32x2(X, e0, e1);
+      exp2_poly_f32x2<kDeg>(X, e0, e1);
     } else {
       float x0, x1;
       unpack_f32x2(X, x0, x1);
@@ -142,6 +156,38 @@ DEVI void exp_chunk(const uint32_t* v, float sc, float neg_m, uint32_t tP, uint6
     ls[p & 1] = add_f32x2(ls[p & 1], pack_f32x2(e0, e1));
     pk[p] = pack_bf16(e0, e1);
   }
+}
+// the two halves of exp_chunk_pk as separate steps (attention64p.cuh issues the next block's TMEM loads between them):
+// scale_chunk: 32 raw scores -> 16 packed pairs x = s*scale - m;   exp_pairs: kN pairs [p0, p0 + kN) -> bf16 pairs + row sums
+DEVI void scale_chunk(const uint32_t* v, float sc, float neg_m, uint64_t (&X)[16]) {
+  const uint64_t NM = pack_f32x2(neg_m, neg_m);
+  const uint64_t SC = pack_f32x2(sc, sc);
+#pragma unroll
+  for (int p = 0; p < 16; ++p) X[p] = fma_f32x2(pack_u32x2(v[2 * p], v[2 * p + 1]), SC, NM);
+}
+template <int kPolyPer8, int kDeg, int kP0, int kN>
+DEVI void exp_pairs(const uint64_t (&X)[16], uint32_t (&pk)[16], uint64_t (&ls)[2]) {
+#pragma unroll
+  for (int p = kP0; p < kP0 + kN; ++p) {
+    float e0, e1;
+    const bool poly = (((p & 7) + 1) * kPolyPer8 / 8 != (p & 7) * kPolyPer8 / 8);   // spread over the 8 pairs
+    if (poly) {
+      exp2_poly_f32x2<kDeg>(X[p], e0, e1);
+    } else {
+      float x0, x1;
+      unpack_f32x2(X[p], x0, x1);
+      e0 = fast_exp2(x0);
+      e1 = fast_exp2(x1);
+    }
+    ls[p & 1] = add_f32x2(ls[p & 1], pack_f32x2(e0, e1));
+    pk[p] = pack_bf16(e0, e1);
+  }
+}
+
+template <bool kScaled, int kPolyPer8, int kDeg>
+DEVI void exp_chunk(const uint32_t* v, float sc, float neg_m, uint32_t tP, uint64_t (&ls)[2]) {
+  uint32_t pk[16];
+  exp_chunk_pk<kScaled, kPolyPer8, kDeg>(v, sc, neg_m, pk, ls);
   tmem_st16(tP, pk);
 }
 
@@ -227,8 +273,8 @@ DEVI void softmax_block(uint32_t tS, uint32_t tO, bool first, int kbase, int Lk,
   uint64_t ls[2] = {0ull, 0ull};
 #pragma unroll
   for (int c = 0; c < BN; c += 32) {
-    if (kPredicated && !lean_tail) exp_chunk<true, LTXB200_ATTN_POLY>(&v[c], sc, -m_ref, tS + (c >> 1), ls);
-    else exp_chunk<false, LTXB200_ATTN_POLY>(&v[c], sc, -m_ref, tS + (c >> 1), ls);
+    if (kPredicated && !lean_tail) exp_chunk<true, AttnPoly<D>::kPer8, AttnPoly<D>::kDeg>(&v[c], sc, -m_ref, tS + (c >> 1), ls);
+    else exp_chunk<false, AttnPoly<D>::kPer8, AttnPoly<D>::kDeg>(&v[c], sc, -m_ref, tS + (c >> 1), ls);
     if (p_half && c + 32 == BN / 2) {            // P of keys 0..BN/2-1 is in TMEM: their P.V may start
       tmem_wait_st();
       tc_fence_before();
@@ -295,7 +341,7 @@ DEVI void softmax_block_half(uint32_t tS, uint32_t tO_half, int half, bool first
   }
   uint64_t ls[2] = {0ull, 0ull};
 #pragma unroll
-  for (int c = 0; c < NC; c += 32) exp_chunk<kPredicated, LTXB200_ATTN_POLY>(&v[c], sc, -m_ref, tS + ((c_off + c) >> 1), ls);
+  for (int c = 0; c < NC; c += 32) exp_chunk<kPredicated, AttnPoly<D>::kPer8, AttnPoly<D>::kDeg>(&v[c], sc, -m_ref, tS + ((c_off + c) >> 1), ls);
   float l0, l1;
   unpack_f32x2(add_f32x2(ls[0], ls[1]), l0, l1);
   l += l0 + l1;

@@ -74,8 +74,9 @@ DEVI uint64_t sub_f32x2(uint64_t a, uint64_t b) { uint64_t d; asm("sub.rn.f32x2 
 
 // Two exp2 evaluated on the FMA pipe instead of MUFU.EX2 (the softmax of the attention kernel is bound by the 16-lane XU
 // pipe at d = 64): Cody-Waite split x = r + f with the 1.5*2^23 rounding constant (r lands in the low mantissa bits of t),
-// minimax degree-3 polynomial for 2^f on [-0.5, 0.5] (max relative error 7.5e-5, 50x below the bf16 rounding of P that
-// follows), exponent added as an integer.  Inputs below -126 give 2^-126 instead of 0.
+// minimax polynomial for 2^f on [-0.5, 0.5] (degree 3: max relative error 7.5e-5, 50x below the bf16 rounding of P that
+// follows; degree 2: 1.7e-3, the size of that rounding), exponent added as an integer.  Inputs below -126 give 2^-126 instead of 0.
+template <int kDeg = 3>
 DEVI void exp2_poly_f32x2(uint64_t X, float& e0, float& e1) {
   float x0, x1;
   unpack_f32x2(X, x0, x1);
@@ -84,9 +85,16 @@ DEVI void exp2_poly_f32x2(uint64_t X, float& e0, float& e1) {
   const uint64_t MAG = pack_f32x2(12582912.f, 12582912.f);
   const uint64_t T = add_f32x2(Xc, MAG);
   const uint64_t Fr = sub_f32x2(Xc, sub_f32x2(T, MAG));
-  uint64_t P = fma_f32x2(Fr, pack_f32x2(0.0551716648f, 0.0551716648f), pack_f32x2(0.2426111251f, 0.2426111251f));
-  P = fma_f32x2(P, Fr, pack_f32x2(0.6932609677f, 0.6932609677f));
-  P = fma_f32x2(P, Fr, pack_f32x2(0.9999280572f, 0.9999280572f));
+  uint64_t P;
+  if constexpr (kDeg == 2) {
+    // degree 2: max relative error 1.7e-3 (the bf16 rounding of P that follows: 2e-3), one FFMA2 less per pair
+    P = fma_f32x2(Fr, pack_f32x2(0.23842894f, 0.23842894f), pack_f32x2(0.70344801f, 0.70344801f));
+    P = fma_f32x2(P, Fr, pack_f32x2(1.00044314f, 1.00044314f));
+  } else {
+    P = fma_f32x2(Fr, pack_f32x2(0.0551716648f, 0.0551716648f), pack_f32x2(0.2426111251f, 0.2426111251f));
+    P = fma_f32x2(P, Fr, pack_f32x2(0.6932609677f, 0.6932609677f));
+    P = fma_f32x2(P, Fr, pack_f32x2(0.9999280572f, 0.9999280572f));
+  }
   float p0, p1, t0, t1;
   unpack_f32x2(P, p0, p1);
   unpack_f32x2(T, t0, t1);

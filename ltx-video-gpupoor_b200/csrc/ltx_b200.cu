@@ -6,6 +6,7 @@
 #include <cstring>
 
 #include "attention.cuh"
+#include "attention64p.cuh"
 #include "comm.cuh"
 #include "common.cuh"
 #include "conv_halo.cuh"
@@ -385,6 +386,29 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
   return launch_status();
 }
 
+// d = 64, no bias / key lengths, Lk % 128 == 0, plain output: the cross-block pipelined kernel (attention64p.cuh), OPT-IN with
+// LTXB200_ATTN64P=1.  Parity-green, and measured 2-3 % behind attention_fwd_kernel<64, false> on the LTX shape (same box, every
+// polynomial setting but one; profiles/r02_attn64_ab.md), so the three-buffer kernel stays the default.
+static int launch_attn64p(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, cudaStream_t st) {
+  using C = Attn64PCfg;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(attention64p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal) != cudaSuccess) return kErrCuda;
+    configured = true;
+  }
+  const int grid = p.total < num_sms() ? p.total : num_sms();
+  attention64p_kernel<<<grid, C::kThreads, C::kTotal, st>>>(tq, tk, tv, p);
+  return launch_status();
+}
+static bool attn64p_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("LTXB200_ATTN64P");
+    on = (e && e[0] == '1') ? 1 : 0;
+  }
+  return on == 1;
+}
+
 static int attention_impl(const void* q, int64_t ldq, int64_t bsq, const void* k, int64_t ldk, int64_t bsk,
                           const void* v, int64_t ldv, int64_t bsv, void* out, int64_t ldo, int64_t bso, int B, int H,
                           int Lq, int Lk, int d, float scale, const float* key_bias, const PeerPtrs* peers,
@@ -415,6 +439,7 @@ static int attention_impl(const void* q, int64_t ldq, int64_t bsq, const void* k
   p.accumulate = accumulate;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool masked = (key_bias != nullptr) || (Lk % BN != 0) || (key_lens != nullptr);
+  if (d == 64 && !masked && !peers && !accumulate && Lk >= 2 * BN && attn64p_enabled()) return launch_attn64p(tq, tk, tv, p, st);
   if (d == 64) return masked ? launch_attn<64, true>(tq, tk, tv, p, st) : launch_attn<64, false>(tq, tk, tv, p, st);
   return masked ? launch_attn<128, true>(tq, tk, tv, p, st) : launch_attn<128, false>(tq, tk, tv, p, st);
 }

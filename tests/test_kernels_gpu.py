@@ -448,3 +448,15 @@ def test_attention_key_lens(d, B, H, Lq, Lk, lens):
     # run it again right behind an ordinary launch: ring / barrier phases must not depend on a launch-wide block count
     o2 = ops.attention(q, k, v, key_lens=kl)
     assert torch.equal(o2, out)
+
+
+def test_attention64_pipelined_variant_parity():
+    """The opt-in cross-block pipelined d = 64 kernel (csrc/attention64p.cuh, LTXB200_ATTN64P=1; the switch is read once per process, hence the
+    subprocess): parity on shapes with several work items per CTA, partial query tiles and strided fused-QKV operands, deterministic."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, LTXB200_ATTN64P="1")
+    r = subprocess.run([sys.executable, os.path.join(root, "profiles", "scripts", "attn64p_check.py")], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-800:] + r.stderr[-800:]
+    assert "ATTN64P = 1" in r.stdout
