@@ -49,7 +49,7 @@ struct AttnParams {
 
 constexpr int kAttnBN = 128;   // keys per block
 
-template <int D>
+template <int D, bool kMasked = true>
 struct AttnCfg {
   // kHalf (d = 64, -DLTXB200_ATTN64_HALFROW): every query row is shared by TWO threads (64 score columns each), i.e. 16 softmax warps =
   // 4 per scheduler instead of 2, which is what the exp loop needs to hide its latencies (mufu_bench2: 18.0 -> 22.3 exp/clk/SM);
@@ -59,28 +59,42 @@ struct AttnCfg {
 #else
   static constexpr bool kHalf = false;
 #endif
+  // kOnes (d = 64, unmasked kernel, -DLTXB200_ATTN64_ONES): the softmax ROW SUM comes out of the tensor pipe.  Every V stage is followed in
+  // shared memory by a constant tile of bf16 ones, which the P.V MMA reads as 16 more value columns (N = 80): accumulator columns 64..79
+  // of a tile hold sum_k P[row, k] — fp32, over exactly the bf16-rounded P the MMA multiplies — so the softmax threads drop the 64 packed
+  // adds per 128 scores (10 % of their instruction stream) and the lazy rescale of O rescales the sum with it.  TMEM then only fits three
+  // score buffers of 96 columns (3 * 96 + 2 * 80 = 448 <= 512).  Parity-green and measured NEUTRAL (968.7 vs 965.0 TF/s on one box,
+  // profiles/r02_attn64_ab.md §4): what the adds save, the per-block fixed costs of 64 instead of 48 key blocks take back.  Off by default.
+#ifdef LTXB200_ATTN64_ONES
+  static constexpr bool kOnes = (D == 64) && !kMasked && !kHalf;
+#else
+  static constexpr bool kOnes = false;
+#endif
 #ifdef LTXB200_ATTN128_BN64
   // d = 128 alternative: 64-key blocks with FOUR S/P buffers (4*64 + 2*128 = 512 columns) = two per tile, so a tile's next scores are
   // computed while its current block is in the softmax (no split-phase tricks)
-  static constexpr int BN = (D == 128) ? 64 : kAttnBN;
+  static constexpr int BN = (D == 128) ? 64 : (kOnes ? 96 : kAttnBN);
 #else
-  static constexpr int BN = kAttnBN;
+  static constexpr int BN = kOnes ? 96 : kAttnBN;
 #endif
+  static constexpr int kOW = D + (kOnes ? 16 : 0);                            // accumulator columns per tile: O (| 16 copies of the row sum)
   static constexpr int kSBufs = (D == 64) ? 3 : (BN == 64 ? 4 : 2);           // S/P buffers in TMEM, used in rotation by the steps
   // With only two S buffers (d = 128 fills TMEM) a tile's next scores cannot be computed ahead in a spare buffer, so
   // the block is pipelined in halves instead: keys 64..127 of S(n+2) are issued as soon as softmax(n) has READ S(n)
   // (P(n) only overwrites columns 0..63), P.V of keys 0..63 starts when the first half of P(n) is written, and only
   // P.V of keys 64..127 plus the low half of S(n+2) remain between "P complete" and "next S ready".
   static constexpr bool kSplit = (kSBufs == 2);
-  static_assert(kSBufs * BN + 2 * D == 512, "TMEM budget");
+  static_assert(kSBufs * BN + 2 * kOW <= 512, "TMEM budget");
   static constexpr int kQBytes = kAttnBM * D * 2;            // one Q tile
   static constexpr int kKBytes = BN * D * 2;                 // one K (or V) block
-  static constexpr int kStages = (128 * 1024) / (2 * kKBytes);          // 128 KB of K/V in flight
+  static constexpr int kVBytes = kKBytes + (kOnes ? BN * 128 : 0);            // V stage: the block (+ the ones tile, [BN][64] bf16 1.0)
+  static constexpr int kStages = kOnes ? 5 : (128 * 1024) / (2 * kKBytes);    // 128 KB of K/V in flight (kOnes: 5 x 36 KB)
   static constexpr int kBarBytes = 512 + (kHalf ? 2 * 2 * 2 * 128 * 4 + 2 * 2 * 128 * 4 : 0);   // + max / sum exchange slots of the half rows
-  static constexpr int kTotal = 2 * kQBytes + 2 * kStages * kKBytes + kBarBytes + 1024;
+  static constexpr int kTotal = 2 * kQBytes + kStages * (kKBytes + kVBytes) + kBarBytes + 1024;
+  static_assert(kTotal <= 227 * 1024, "shared memory budget");
   static constexpr int kSoftmaxWarps = kHalf ? 16 : 8;
   static constexpr int kThreads = (kSoftmaxWarps + 4) * 32;  // softmax warps + TMA warp + MMA warp + 2 idle (warpgroup alignment)
-  static constexpr uint32_t kTmemCols = 512;                 // kSBufs*BN + 2*D = 512 for both head dims
+  static constexpr uint32_t kTmemCols = 512;
   static constexpr int kSoftmaxRegs = kHalf ? 104 : 208, kOtherRegs = 64;  // setmaxnreg: the softmax warpgroups take the registers
 };
 
@@ -134,7 +148,7 @@ template <int D> struct AttnPoly {
   static constexpr int kPer8 = (D == 64) ? LTXB200_ATTN_POLY_D64 : LTXB200_ATTN_POLY_D128;
   static constexpr int kDeg = (D == 64) ? LTXB200_ATTN_POLY_DEG_D64 : LTXB200_ATTN_POLY_DEG_D128;
 };
-template <bool kScaled, int kPolyPer8, int kDeg>
+template <bool kScaled, int kPolyPer8, int kDeg, bool kSum = true>
 DEVI void exp_chunk_pk(const uint32_t* v, float sc, float neg_m, uint32_t (&pk)[16], uint64_t (&ls)[2]) {
   const uint64_t NM = pack_f32x2(neg_m, neg_m);
   const uint64_t SC = pack_f32x2(sc, sc);
@@ -153,7 +167,7 @@ DEVI void exp_chunk_pk(const uint32_t* v, float sc, float neg_m, uint32_t (&pk)[
       e0 = fast_exp2(x0);
       e1 = fast_exp2(x1);
     }
-    ls[p & 1] = add_f32x2(ls[p & 1], pack_f32x2(e0, e1));
+    if (kSum) ls[p & 1] = add_f32x2(ls[p & 1], pack_f32x2(e0, e1));
     pk[p] = pack_bf16(e0, e1);
   }
 }
@@ -184,17 +198,17 @@ DEVI void exp_pairs(const uint64_t (&X)[16], uint32_t (&pk)[16], uint64_t (&ls)[
   }
 }
 
-template <bool kScaled, int kPolyPer8, int kDeg>
+template <bool kScaled, int kPolyPer8, int kDeg, bool kSum = true>
 DEVI void exp_chunk(const uint32_t* v, float sc, float neg_m, uint32_t tP, uint64_t (&ls)[2]) {
   uint32_t pk[16];
-  exp_chunk_pk<kScaled, kPolyPer8, kDeg>(v, sc, neg_m, pk, ls);
+  exp_chunk_pk<kScaled, kPolyPer8, kDeg, kSum>(v, sc, neg_m, pk, ls);
   tmem_st16(tP, pk);
 }
 
 // One key block of the online softmax for one query row (one thread): S (fp32, BN columns at tS) -> registers in
 // ONE TMEM pass -> block max -> (lazy) rescale -> exp2 -> P (bf16 pairs) over the first BN/2 columns of tS.
 // m_ref: reference max of the row (log2 domain), m_run: largest score seen so far, l: row sum relative to m_ref.
-template <int D, int BN, bool kPredicated>
+template <int D, int BN, bool kPredicated, int kOW = D, bool kSum = true>      // kOW: accumulator columns the lazy rescale covers; kSum: row sum kept here
 DEVI void softmax_block(uint32_t tS, uint32_t tO, bool first, int kbase, int Lk, const float* bias, float sc,
                         float& m_ref, float& m_run, float& l, uint64_t* pv_done, uint32_t pv_parity,
                         uint64_t* s_read, uint64_t* p_half, int lane) {
@@ -268,13 +282,13 @@ DEVI void softmax_block(uint32_t tS, uint32_t tO, bool first, int kbase, int Lk,
     m_ref = (m_blk == -INFINITY) ? 0.f : m_blk;
   } else {
     m_run = fmaxf(m_run, m_blk);
-    rescale_o<D>(tO, m_run > m_ref + 8.0f, m_run, m_ref, l, pv_done, pv_parity);
+    rescale_o<kOW>(tO, m_run > m_ref + 8.0f, m_run, m_ref, l, pv_done, pv_parity);
   }
   uint64_t ls[2] = {0ull, 0ull};
 #pragma unroll
   for (int c = 0; c < BN; c += 32) {
-    if (kPredicated && !lean_tail) exp_chunk<true, AttnPoly<D>::kPer8, AttnPoly<D>::kDeg>(&v[c], sc, -m_ref, tS + (c >> 1), ls);
-    else exp_chunk<false, AttnPoly<D>::kPer8, AttnPoly<D>::kDeg>(&v[c], sc, -m_ref, tS + (c >> 1), ls);
+    if (kPredicated && !lean_tail) exp_chunk<true, AttnPoly<D>::kPer8, AttnPoly<D>::kDeg, kSum>(&v[c], sc, -m_ref, tS + (c >> 1), ls);
+    else exp_chunk<false, AttnPoly<D>::kPer8, AttnPoly<D>::kDeg, kSum>(&v[c], sc, -m_ref, tS + (c >> 1), ls);
     if (p_half && c + 32 == BN / 2) {            // P of keys 0..BN/2-1 is in TMEM: their P.V may start
       tmem_wait_st();
       tc_fence_before();
@@ -282,9 +296,11 @@ DEVI void softmax_block(uint32_t tS, uint32_t tO, bool first, int kbase, int Lk,
       if (lane == 0) mbar_arrive(p_half);
     }
   }
-  float l0, l1;
-  unpack_f32x2(add_f32x2(ls[0], ls[1]), l0, l1);
-  l += l0 + l1;
+  if (kSum) {
+    float l0, l1;
+    unpack_f32x2(add_f32x2(ls[0], ls[1]), l0, l1);
+    l += l0 + l1;
+  }
 }
 
 // Half-row form of softmax_block (kHalf): this thread owns columns [half*BN/2, +BN/2) of the row's scores, its partner thread (same
@@ -348,11 +364,13 @@ DEVI void softmax_block_half(uint32_t tS, uint32_t tO_half, int half, bool first
 }
 
 template <int D, bool kMasked>
-__global__ void __launch_bounds__(AttnCfg<D>::kThreads, 1)
+__global__ void __launch_bounds__(AttnCfg<D, kMasked>::kThreads, 1)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
-  using C = AttnCfg<D>;
+  using C = AttnCfg<D, kMasked>;
   constexpr int BN = C::BN;
+  constexpr int kOW = C::kOW;
+  constexpr bool kOnes = C::kOnes;
   constexpr int kStages = C::kStages;
   constexpr int kSBufs = C::kSBufs;
   constexpr bool kSplit = C::kSplit;
@@ -366,8 +384,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                                 // [2][128][D]
   uint8_t* sK = sQ + 2 * C::kQBytes;                  // [kStages][BN][D]
-  uint8_t* sV = sK + kStages * C::kKBytes;            // [kStages][BN][D]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kStages * C::kKBytes);
+  uint8_t* sV = sK + kStages * C::kKBytes;            // [kStages][BN][D] (kOnes: each stage followed by its [BN][64] tile of ones)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kStages * C::kVBytes);
   uint64_t* q_full = bars;                // [2]       TMA -> MMA
   uint64_t* q_empty = q_full + 2;         // [2]       last S of the item issued: Q tile may be overwritten
   uint64_t* k_full = q_empty + 2;         // [kStages]
@@ -413,6 +431,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     fence_barrier_init();
   }
   if (warp == kMmaWarp) tmem_alloc<C::kTmemCols>(tmem_slot);
+  if constexpr (kOnes) {
+    // the constant value columns behind every V stage: all 64 columns of the tile are 1.0, so the 128-byte swizzle is immaterial
+    for (int st = 0; st < kStages; ++st) {
+      uint4* ones = reinterpret_cast<uint4*>(sV + st * C::kVBytes + C::kKBytes);
+      for (int i = threadIdx.x; i < BN * 128 / 16; i += C::kThreads) ones[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    }
+    fence_proxy_async();                               // generic-proxy stores -> visible to the MMA's shared-memory reads
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -447,14 +473,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           mbar_arrive_expect_tx(&v_full[st], C::kKBytes);
 #pragma unroll
           for (int c = 0; c < kChunks; ++c)
-            tma_load_4d(sV + st * C::kKBytes + c * (BN * 128), &tmV, &v_full[st], c * 64, h, j * BN, b);
+            tma_load_4d(sV + st * C::kVBytes + c * (BN * 128), &tmV, &v_full[st], c * 64, h, j * BN, b);
         }
       }
     } else if (warp == kMmaWarp && elect_one()) {
       // ================= MMA issuer =================
       constexpr uint32_t idesc_s = umma_idesc_bf16(kAttnBM, BN, 0, 0);   // S = Q K^T  (both K-major)
       constexpr uint32_t idesc_sh = umma_idesc_bf16(kAttnBM, BN / 2, 0, 0);   // one half of the keys
-      constexpr uint32_t idesc_o = umma_idesc_bf16(kAttnBM, D, 0, 1);    // O += P V   (V is MN-major)
+      constexpr uint32_t idesc_o = umma_idesc_bf16(kAttnBM, kOW, 0, 1);  // O += P V   (V is MN-major; kOnes: 16 more columns of ones behind it)
       // descriptors = (constant high bits | start address >> 4); tile / stage / k-step offsets are added to the
       // low word at issue time (the 14-bit address field cannot carry: shared memory is < 256 KB)
       const uint64_t qdesc = umma_smem_desc_sw128(smem_u32(sQ), 16, 1024);
@@ -493,8 +519,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       // O_t += P(n)[:, keys] . V(j)[keys, :]   (k-steps [ks0, ks1) of 16 keys)
       auto issue_pv = [&](int t, uint32_t buf, int sv, int ks0, int ks1, bool acc) {
         // B = V[16 keys (K), D (N)], N contiguous: 8-key groups 1024 B apart (SBO), 64-col groups one chunk apart (LBO)
-        const uint64_t va = vdesc + static_cast<uint32_t>(sv * (C::kKBytes >> 4));
-        const uint32_t to = tmem_base + kColO0 + t * D, tp = tmem_base + kColS0 + buf * BN;
+        const uint64_t va = vdesc + static_cast<uint32_t>(sv * (C::kVBytes >> 4));
+        const uint32_t to = tmem_base + kColO0 + t * kOW, tp = tmem_base + kColS0 + buf * BN;
 #pragma unroll
         for (int ks = ks0; ks < ks1; ++ks)
           umma_ts(to, tp + ks * 8, va + static_cast<uint32_t>(ks * (2048 >> 4)), idesc_o, (acc || ks > ks0) ? 1u : 0u);
@@ -545,7 +571,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const int sub = warp & 3;
     const int row = sub * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(sub * 32) << 16;
-    const uint32_t tO = tmem_base + kColO0 + t * D + lane_addr;
+    const uint32_t tO = tmem_base + kColO0 + t * kOW + lane_addr;
     // kHalf exchange slots behind the barriers: xmax[tile][half][parity][row], xsum[tile][half][row]
     float* xmax = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
     float* xsum = xmax + 2 * 2 * 2 * 128;
@@ -576,11 +602,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                                              (G - 1) & 1, xm, xp, pair_bar);
         } else
         if (kMasked && (bias != nullptr || kbase + BN > Lk_b))
-          softmax_block<D, BN, true>(tS, tO, j == 0, kbase, Lk_b, bias, p.scale_log2, m_ref, m_run, l, &pv_done[t], (G - 1) & 1,
-                                      kSplit ? &s_read[buf] : nullptr, kSplit ? &p_half[buf] : nullptr, lane);
+          softmax_block<D, BN, true, kOW, !kOnes>(tS, tO, j == 0, kbase, Lk_b, bias, p.scale_log2, m_ref, m_run, l, &pv_done[t], (G - 1) & 1,
+                                                  kSplit ? &s_read[buf] : nullptr, kSplit ? &p_half[buf] : nullptr, lane);
         else
-          softmax_block<D, BN, false>(tS, tO, j == 0, kbase, Lk_b, bias, p.scale_log2, m_ref, m_run, l, &pv_done[t], (G - 1) & 1,
-                                      kSplit ? &s_read[buf] : nullptr, kSplit ? &p_half[buf] : nullptr, lane);
+          softmax_block<D, BN, false, kOW, !kOnes>(tS, tO, j == 0, kbase, Lk_b, bias, p.scale_log2, m_ref, m_run, l, &pv_done[t], (G - 1) & 1,
+                                                   kSplit ? &s_read[buf] : nullptr, kSplit ? &p_half[buf] : nullptr, lane);
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
@@ -594,6 +620,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
         l += xsum[(t * 2 + (half ^ 1)) * 128 + row];
         asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");      // the slot is free for the next item
+      }
+      if constexpr (kOnes) {                      // the row sum is the tile's accumulator column D (copies in D+1 .. D+15)
+        uint32_t lr[16];
+        tmem_ld16(tO + D, lr);
+        tmem_wait_ld();
+        l = __uint_as_float(lr[0]);
       }
       const float inv = (l > 0.f) ? __fdividef(1.0f, l) : 0.f;
       const int q = qp * 256 + t * kAttnBM + row;

@@ -374,7 +374,7 @@ static int make_qkv_tmap(CUtensorMap* m, const void* base, int B, int H, int L, 
 template <int D, bool kMasked>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                        cudaStream_t st) {
-  using C = AttnCfg<D>;
+  using C = AttnCfg<D, kMasked>;
   static bool configured = false;
   auto kern = attention_fwd_kernel<D, kMasked>;
   if (!configured) {
@@ -419,7 +419,11 @@ static int attention_impl(const void* q, int64_t ldq, int64_t bsq, const void* k
   if (!aligned16(q) || !aligned16(k) || !aligned16(v) || (out && !aligned16(out)) || (ldq & 7) || (ldk & 7) || (ldv & 7) ||
       (ldo & 7) || (bsq & 7) || (bsk & 7) || (bsv & 7) || (bso & 7))
     return kErrBadAlign;
-  const int BN = d == 64 ? AttnCfg<64>::BN : AttnCfg<128>::BN;       // keys per block (K / V box rows)
+  // keys per block (K / V box rows) depend on the kernel: the unmasked d = 64 kernel walks 96-key blocks (AttnCfg::kOnes)
+  const int BNu = d == 64 ? AttnCfg<64, false>::BN : AttnCfg<128, false>::BN, BNm = d == 64 ? AttnCfg<64, true>::BN : AttnCfg<128, true>::BN;
+  const bool use64p = d == 64 && !key_bias && !key_lens && Lk % Attn64PCfg::BN == 0 && Lk >= 2 * Attn64PCfg::BN && !peers && !accumulate && attn64p_enabled();
+  const bool masked = (key_bias != nullptr) || (Lk % BNu != 0) || (key_lens != nullptr);
+  const int BN = use64p ? Attn64PCfg::BN : (masked ? BNm : BNu);
   CUtensorMap tq, tk, tv;
   if (make_qkv_tmap(&tq, q, B, H, Lq, d, ldq, bsq, kAttnBM) || make_qkv_tmap(&tk, k, B, H, Lk, d, ldk, bsk, BN) ||
       make_qkv_tmap(&tv, v, B, H, Lk, d, ldv, bsv, BN))
@@ -438,8 +442,7 @@ static int attention_impl(const void* q, int64_t ldq, int64_t bsq, const void* k
   if (peers) { p.peers = *peers; p.tokens_per_peer = tokens_per_peer; p.head_offset = head_offset; }
   p.accumulate = accumulate;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const bool masked = (key_bias != nullptr) || (Lk % BN != 0) || (key_lens != nullptr);
-  if (d == 64 && !masked && !peers && !accumulate && Lk >= 2 * BN && attn64p_enabled()) return launch_attn64p(tq, tk, tv, p, st);
+  if (use64p) return launch_attn64p(tq, tk, tv, p, st);
   if (d == 64) return masked ? launch_attn<64, true>(tq, tk, tv, p, st) : launch_attn<64, false>(tq, tk, tv, p, st);
   return masked ? launch_attn<128, true>(tq, tk, tv, p, st) : launch_attn<128, false>(tq, tk, tv, p, st);
 }

@@ -20,7 +20,8 @@ def rel(a, b):
 
 worst = 0.0
 for (B, H, Lq, Lk, scale) in [(1, 2, 128, 256, 1.0), (2, 3, 256, 384, 1.0), (1, 4, 300, 1280, 1.0), (2, 40, 600, 512, 1.0), (3, 32, 1000, 2048, 3.0),
-                              (1, 160, 515, 768, 0.3), (1, 1, 77, 4096, 5.0)]:
+                              (1, 160, 515, 768, 0.3), (1, 1, 77, 4096, 5.0), (1, 2, 128, 96, 1.0), (2, 3, 300, 960, 2.0), (3, 32, 1000, 1920, 1.0),
+                              (2, 40, 600, 192, 4.0)]:
     g = torch.Generator(device=dev).manual_seed(B * 1000 + Lq)
     qkv = torch.randn(B, max(Lq, Lk), 3 * H * 64, device=dev, generator=g) * scale
     qkv = qkv.bfloat16()
