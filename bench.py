@@ -789,6 +789,16 @@ def main():
                    ("tflops" if v["kind"] == "flop" else "gbs"): round(v["amount"] / (v["ms"] * 1e-3) / (1e12 if v["kind"] == "flop" else 1e9), 1)}
                for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
 
+    if "attention_bf16" in kernels and wl.get("arch", "2b") == "2b" and clocks.get("sm_mhz"):
+        # the pipe that bounds attention at head dim 64 is the XU pipe (16 ex2 per clock and SM), not the tensor pipe: every score costs one
+        # exponential and 4 * 64 = 256 flop; 3 of 8 exponentials run as an FMA-pipe polynomial (csrc/attention.cuh, LTXB200_ATTN_POLY_D64)
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        xu_peak = sms * 16 * clocks["sm_mhz"] * 1e6 * 256 / (1.0 - 3.0 / 8.0) / 1e12
+        kernels["attention_bf16"].update({"tensor_frac_of_sustained": round(kernels["attention_bf16"]["tflops"] / pk["tf_sust"], 3),
+                                          "xu_bound_tflops_at_step_clock": round(xu_peak, 1),
+                                          "xu_frac": round(kernels["attention_bf16"]["tflops"] / xu_peak, 3),
+                                          "note": "head dim 64: bounded by the XU (ex2) pipe; xu_bound = SMs x 16 ex2/clk x median SM clock of the step x 256 flop per score / (5/8 on MUFU)"})
+
     # ---------------- end-to-end through the public pipeline call, host buffers in the timed region ----------------
     K = max(args.steps, 2)
     pipe(prompt_embeds=pe_h, prompt_attention_mask=pm_h, negative_prompt_embeds=ne_h, negative_prompt_attention_mask=nm_h,
