@@ -70,6 +70,7 @@ DEVI uint64_t pack_u32x2(uint32_t a, uint32_t b) { uint64_t r; asm("mov.b64 %0, 
 DEVI void unpack_f32x2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
 DEVI uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) { uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 DEVI uint64_t add_f32x2(uint64_t a, uint64_t b) { uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+DEVI uint64_t mul_f32x2(uint64_t a, uint64_t b) { uint64_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 DEVI uint64_t sub_f32x2(uint64_t a, uint64_t b) { uint64_t d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 
 // Two exp2 evaluated on the FMA pipe instead of MUFU.EX2 (the softmax of the attention kernel is bound by the 16-lane XU
@@ -111,6 +112,20 @@ DEVI float gelu_tanh(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
   const float hx = 0.5f * x;
   return fmaf(hx, t, hx);
+}
+
+// the same on a packed pair: the FMA-pipe part as FMUL2 / FFMA2 (half the issue slots; the GEMM epilogue runs ONE warp per scheduler and
+// is latency-bound: at K = 2048 the scalar form let the FFN-up epilogue outlast its mainloop, tensor pipe 85 % active)
+DEVI uint64_t gelu_tanh_f32x2(uint64_t X) {
+  const uint64_t C0 = pack_f32x2(0.7978845608028654f, 0.7978845608028654f);
+  const uint64_t C1 = pack_f32x2(0.7978845608028654f * 0.044715f, 0.7978845608028654f * 0.044715f);
+  const uint64_t U = mul_f32x2(X, fma_f32x2(mul_f32x2(X, X), C1, C0));
+  float u0, u1, t0, t1;
+  unpack_f32x2(U, u0, u1);
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(u0));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(u1));
+  const uint64_t HX = mul_f32x2(X, pack_f32x2(0.5f, 0.5f));
+  return fma_f32x2(HX, pack_f32x2(t0, t1), HX);
 }
 
 // exact GELU (torch.nn.GELU() default, used by Wan's MLPProj, model.py:583)

@@ -118,7 +118,11 @@ DEVI void epilogue_row(const GemmParams& p, uint32_t t_addr, int tn, bool row_ok
       }
       if (p.act == kActGeluTanh) {
 #pragma unroll
+#ifdef LTXB200_GELU_SCALAR
         for (int j = 0; j < 32; ++j) f[j] = gelu_tanh(f[j]);
+#else
+        for (int j = 0; j < 32; j += 2) unpack_f32x2(gelu_tanh_f32x2(pack_f32x2(f[j], f[j + 1])), f[j], f[j + 1]);
+#endif
       } else if (p.act == kActSilu) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __fdividef(f[j], 1.0f + __expf(-f[j]));
