@@ -570,6 +570,61 @@ def run_wan(args, wl):
     if dist is not None:
         dist.destroy_process_group()
 
+def ltx_cond_parallel_block(pipe, wl, call_kw, dev, dist, rank, world, steps, warmup, one_gpu_ms):
+    """ONE LTX video over min(world, num_conds) GPUs: the [uncond, text, perturbed] rows of every denoise step on different ranks
+    (ltx/distributed/cond_parallel.py), predictions exchanged once per step by NCCL broadcast.  Strong scaling of the LTX path's latency —
+    the headline `value` stays replicas (throughput).  Every rank takes part in creating the group; ranks beyond it sit the block out."""
+    import torch
+    from ltx_video_gpupoor_b200.ltx.distributed.cond_parallel import cond_partition
+    P = min(world, wl["num_conds"])
+    group = dist.new_group(list(range(P)))
+    if rank >= P:
+        return None
+    g = torch.Generator().manual_seed(4242)                  # the SAME inputs on every rank of the group
+    Lp = wl["prompt_tokens"]
+    pe, ne = torch.randn(1, Lp, 4096, generator=g).to(torch.bfloat16).to(dev), torch.randn(1, Lp, 4096, generator=g).to(torch.bfloat16).to(dev)
+    pm = torch.ones(1, Lp, device=dev)
+    S = wl["schedule_steps"]
+
+    def prepare(cp):
+        return pipe(prompt_embeds=pe, prompt_attention_mask=pm, negative_prompt_embeds=ne, negative_prompt_attention_mask=pm,
+                    num_inference_steps=S, generator=torch.Generator(device=dev).manual_seed(7), output_type="latent", _prepare_only=True,
+                    **(dict(call_kw, cond_parallel_group=group) if cp else call_kw))
+
+    # parity first: two steps on the group against two steps of the whole batch on rank 0, same seed -> the same bits
+    st = prepare(True)
+    for i in range(2):
+        pipe.denoise_step(st, i)
+    identical = None
+    if rank == 0:
+        st1 = prepare(False)
+        for i in range(2):
+            pipe.denoise_step(st1, i)
+        torch.cuda.synchronize()
+        identical = bool(torch.equal(st.lat32, st1.lat32))
+        del st1
+    for i in range(warmup):
+        pipe.denoise_step(st, (2 + i) % S)
+    dist.barrier(group=group)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(steps):
+        pipe.denoise_step(st, (2 + warmup + i) % S)
+    b.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(b) / steps], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    ms = float(t)
+    n_tok = st.N * st.C * 2
+    return {"workload": "ONE video of the headline workload over the ranks of a group: guidance conditions split, strong scaling of latency",
+            "gpus": P, "conds_per_rank": [hi - lo for lo, hi in cond_partition(wl["num_conds"], P)], "steps": steps, "warmup": warmup,
+            "ms_per_step": ms, "steps_per_s": 1e3 / ms, "s_per_video_denoise": S * ms / 1e3, "one_gpu_ms_per_step": one_gpu_ms,
+            "speedup_vs_one_gpu": one_gpu_ms / ms, "strong_efficiency": one_gpu_ms / ms / P,
+            "exchange": f"NCCL broadcast of every owner's prediction rows once per step ({n_tok} B of bf16 per condition)",
+            "bit_identical_to_single_gpu": identical, "scaling": "strong"}
+
+
 def gpu_library_baseline(wl, cfg, tr, dev, ours_ms):
     """Per-step time of the library path on this GPU: the pinned oracle restatement of the reference's PyTorch modules in bf16 with
     torch.nn.functional.scaled_dot_product_attention (what LTX-Video-GPUPoor executes with `_attention = "sdpa"`), same random
@@ -630,6 +685,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
     ap.add_argument("--no-wan-sp", action="store_true", help="skip the Wan2.1 sequence-parallel block of the default line")
+    ap.add_argument("--no-cond-parallel", action="store_true", help="skip the LTX guidance-condition-parallel block (N > 1)")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the torch-eager-on-GPU library baseline")
     ap.add_argument("--layers", type=int, default=28, help="debug only: fewer layers makes the number INVALID")
     args = ap.parse_args()
@@ -665,7 +721,7 @@ def main():
     if args.layers == 28:                          # the default = the architecture's full depth
         args.layers = arch["layers"]
     if wl.get("arch", "2b") != "2b":               # the CPU / torch-eager baselines are wired for the headline 2B architecture
-        args.no_cpu_baseline = args.no_gpu_baseline = args.no_wan_sp = True
+        args.no_cpu_baseline = args.no_gpu_baseline = args.no_wan_sp = args.no_cond_parallel = True
     cfg = dict(LTX_2B_CONFIG, num_layers=args.layers, **arch["overrides"])
     tr = Transformer3DModel(**cfg)
     tr.load_state_dict(random_transformer_state_dict(cfg, seed=0, device=dev), device=dev)
@@ -837,6 +893,13 @@ def main():
     # ---------------- the library bar on the same box (NOT this repo's path): the reference's GPU path = plain PyTorch bf16 modules
     # with torch SDPA (`_attention = "sdpa"`), here the pinned restatement of those modules on this GPU with the SAME weights,
     # all 28 layers x 3 conds, one transformer forward per step (guidance + scheduler arithmetic not included: it favours the baseline)
+    # ---------------- extra at N > 1: ONE video over the guidance conditions' ranks (latency scaling of the LTX path) ----------------
+    cond_par = None
+    if dist is not None and world > 1 and wl["num_conds"] > 1 and not wl.get("i2v") and not args.no_cond_parallel:
+        try:
+            cond_par = ltx_cond_parallel_block(pipe, wl, call_kw, dev, dist, rank, world, args.steps, args.warmup, elapsed / args.steps * 1e3)
+        except Exception as exc:                       # an extra must never cost the headline line
+            cond_par = {"error": repr(exc)[:300]}
     gpu_lib = None
     if rank == 0 and not args.no_gpu_baseline:
         try:
@@ -878,6 +941,8 @@ def main():
         line["stg_prefix_sharing"] = shared
         if decode_s is not None:
             shared["s_per_video"] = S * shared["ms_per_step"] / 1e3 + decode_s
+    if cond_par is not None:
+        line["ltx_cond_parallel"] = cond_par
     if gpu_lib is not None:
         line["gpu_library_baseline"] = gpu_lib
     if wan_sp is not None:

@@ -214,20 +214,32 @@ class LTXVideoPipeline:
             noised = st.init_tokens.float() + st.image_cond_noise_scale * noise.float() * (t ** 2)
             st.lat32 = torch.where(need, noised, st.lat32.view(1, N, C)).contiguous().view(-1)
             st.lat16 = st.lat32.to(BF16)
-        st.x_in.view(num_conds, bsz, N, C).copy_(st.lat16.view(1, bsz, N, C).expand(num_conds, bsz, N, C))
-        if st.cmask_dev is None:
-            st.t_in.fill_(t)
-        else:
-            st.t_in.copy_(torch.clamp(1.0 - st.cmask_dev, max=t).view(1, N).expand(num_conds, N))   # min(t, 1-mask) :1145-1150
-        noise_pred = self.transformer(
-            st.x_in, freqs_cis=st.freqs_cis, encoder_hidden_states=st.enc_b, encoder_attention_mask=st.mask_b,
-            timestep=st.t_in, skip_layer_mask=st.skip_layer_masks[i] if st.skip_layer_masks is not None else None,
-            skip_layer_strategy=st.skip_layer_strategy, latent_shape=st.latent_shape[2:], joint_pass=st.joint_pass,
-            ltxv_model=st.ltxv_model, return_dict=False, shared_prefix=getattr(st, "shared_prefix", None),
-            mixed=getattr(st, "mixed", False), encoder_key_lens=getattr(st, "key_lens_b", None))[0]
-        if noise_pred is None:
-            return None
+        cp = getattr(st, "cond_parallel", None)
+        nl = st.num_local_conds                 # the condition rows THIS rank runs (all of them without cond_parallel_group)
+        if cp is not None and cp.any_flag(bool(getattr(st.ltxv_model, "_interrupt", False)), device):
+            return None                         # collective decision at the step boundary: no rank is left waiting in the exchange
+        noise_pred = None
+        if nl:
+            st.x_in.view(nl, bsz, N, C).copy_(st.lat16.view(1, bsz, N, C).expand(nl, bsz, N, C))
+            if st.cmask_dev is None:
+                st.t_in.fill_(t)
+            else:
+                st.t_in.copy_(torch.clamp(1.0 - st.cmask_dev, max=t).view(1, N).expand(nl, N))   # min(t, 1-mask) :1145-1150
+            noise_pred = self.transformer(
+                st.x_in, freqs_cis=st.freqs_cis, encoder_hidden_states=st.enc_b, encoder_attention_mask=st.mask_b,
+                timestep=st.t_in, skip_layer_mask=st.skip_layer_masks[i] if st.skip_layer_masks is not None else None,
+                skip_layer_strategy=st.skip_layer_strategy, latent_shape=st.latent_shape[2:], joint_pass=st.joint_pass,
+                ltxv_model=st.ltxv_model if cp is None else None, return_dict=False, shared_prefix=getattr(st, "shared_prefix", None),
+                mixed=getattr(st, "mixed", False), encoder_key_lens=getattr(st, "key_lens_b", None))[0]
+            if noise_pred is None:
+                return None
         n = N * C
+        if cp is not None:                      # every owner's prediction rows -> every rank; guidance + step stay replicated
+            lo, hi = st.cond_ranges[cp.rank]
+            if nl:
+                st.pred_full[lo * bsz:hi * bsz].copy_(noise_pred.view(nl * bsz, N, C))
+            cp.exchange(st.pred_full, bsz, st.cond_ranges)
+            noise_pred = st.pred_full
         pred = noise_pred.view(-1)
         for j in range(bsz):            # guidance statistics (cfg-star projection, std rescale) are per sample (:1183-1222)
             ops.guidance_step(pred[j * n:], st.lat32[j * n:(j + 1) * n], st.ts_dev, t, num_conds=num_conds,
@@ -355,8 +367,32 @@ class LTXVideoPipeline:
         lat16 = tokens.to(BF16).contiguous().view(-1)                      # bf16 model input
         cmask_dev = None if conditioning_mask is None else conditioning_mask.to(device=device, dtype=torch.float32).contiguous().view(-1)
         scratch = torch.empty(8 * 148, device=device, dtype=torch.float32)
-        x_in = torch.empty(num_conds * bsz, N, C, device=device, dtype=BF16)
-        t_in = torch.empty(num_conds * bsz, N if cmask_dev is not None else 1, device=device, dtype=torch.float32)
+        # ---- extension: guidance-condition parallelism (ltx/distributed/cond_parallel.py).  `cond_parallel_group=` is a
+        # torch.distributed process group whose ranks all make this same call (same inputs, same generator seed): each runs the
+        # transformer on its share of the [uncond, text, perturbed] rows, predictions are exchanged once per step.
+        cond_parallel, cond_ranges, pred_full, num_local = None, None, None, num_conds
+        if kwargs.get("cond_parallel_group") is not None:
+            from .distributed.cond_parallel import CondParallel
+            cond_parallel = CondParallel(kwargs["cond_parallel_group"])
+            cond_ranges = cond_parallel.ranges(num_conds)
+            lo, hi = cond_ranges[cond_parallel.rank]
+            num_local = hi - lo
+            rows = slice(lo * bsz, hi * bsz)
+            enc_b = enc_b[rows].contiguous()
+            mask_b = None if mask_b is None else mask_b[rows].contiguous()
+            key_lens_b = None if key_lens_b is None else key_lens_b[rows].contiguous()
+            if skip_layer_masks is not None:
+                def cut(m):
+                    if m is None:
+                        return None
+                    part = m[:, rows].contiguous()
+                    if getattr(m, "_ltxb200_host", None) is not None:
+                        part._ltxb200_host = m._ltxb200_host[:, rows].contiguous()    # keeps the forward free of a device sync
+                    return part
+                skip_layer_masks = [cut(m) for m in skip_layer_masks]
+            pred_full = torch.empty(num_conds * bsz, N, C, device=device, dtype=BF16)
+        x_in = torch.empty(max(num_local, 1) * bsz, N, C, device=device, dtype=BF16)
+        t_in = torch.empty(max(num_local, 1) * bsz, N if cmask_dev is not None else 1, device=device, dtype=torch.float32)
 
         if callback is not None:
             callback(-1, None, True, override_num_inference_steps=num_inference_steps, pass_no=pass_no)
@@ -369,9 +405,11 @@ class LTXVideoPipeline:
             t_in=t_in, latent_shape=latent_shape, joint_pass=joint_pass, ltxv_model=ltxv_model, generator=generator,
             image_cond_noise_scale=image_cond_noise_scale, init_tokens=init_tokens, tokens_shape=tuple(tokens.shape),
             stochastic_sampling=bool(stochastic_sampling), mixed=bool(mixed_precision), key_lens_b=key_lens_b,
+            cond_parallel=cond_parallel, cond_ranges=cond_ranges, pred_full=pred_full, num_local_conds=num_local,
             # extension (off by default): the perturbed STG condition repeats the text condition's inputs, so its rows are
             # copies of the text rows until the first skipped block (Transformer3DModel.forward, `shared_prefix`)
-            shared_prefix=(bsz, int(do_cfg) * bsz) if (kwargs.get("share_stg_prefix", False) and do_stg and skip_layer_masks is not None and bsz == 1) else None))
+            shared_prefix=(bsz, int(do_cfg) * bsz) if (kwargs.get("share_stg_prefix", False) and do_stg and skip_layer_masks is not None and bsz == 1
+                                                       and cond_parallel is None) else None))
         self._state = st
         if kwargs.get("_prepare_only", False):
             return st

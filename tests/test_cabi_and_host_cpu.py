@@ -335,3 +335,19 @@ def test_bench_reference_arm_contract():
     assert d["cpu_baseline"]["kind"] == ("reference" if have_ref else "port") and d["cpu_baseline"]["value"] == d["value"]
     assert d["cpu_baseline"]["cores"] == (len(os.sched_getaffinity(0)) or 1) and d["cpu_baseline"]["extrapolated"] is True
     assert d["e2e"] == {"value": d["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_cond_partition():
+    """ltx/distributed/cond_parallel.py: contiguous condition ranges per rank; ranks beyond the conditions take none."""
+    from ltx_video_gpupoor_b200.ltx.distributed.cond_parallel import cond_partition
+    assert cond_partition(3, 1) == [(0, 3)]
+    assert cond_partition(3, 2) == [(0, 2), (2, 3)]
+    assert cond_partition(3, 3) == [(0, 1), (1, 2), (2, 3)]
+    assert cond_partition(3, 4) == [(0, 1), (1, 2), (2, 3), (3, 3)]
+    assert cond_partition(2, 8)[:3] == [(0, 1), (1, 2), (2, 2)]
+    assert cond_partition(1, 2) == [(0, 1), (1, 1)]
+    for conds in (1, 2, 3):
+        for ranks in range(1, 9):
+            parts = cond_partition(conds, ranks)
+            assert len(parts) == ranks and parts[0][0] == 0 and max(hi for _, hi in parts) == conds
+            assert all(a[1] == b[0] or b == (conds, conds) for a, b in zip(parts, parts[1:]))

@@ -732,3 +732,45 @@ def test_pipeline_right_padded_prompt_mask_uses_key_lengths():
     pm2[:, 20] = 0                                           # a hole: not a key length
     pipe(prompt_attention_mask=pm2, negative_prompt_attention_mask=nm, generator=torch.Generator().manual_seed(4), **kw)
     assert pipe._state.key_lens_b is None and pipe._state.mask_b is not None
+
+
+# ------------------------------------------------------------------ guidance-condition parallelism (ltx/distributed/cond_parallel.py)
+def _cond_parallel_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        pipe, _, _ = _pipe(2)
+        g = torch.Generator().manual_seed(31)
+        pe, ne = torch.randn(1, 24, 4096, generator=g), torch.randn(1, 24, 4096, generator=g)
+        pm = torch.ones(1, 24)
+        pm[0, 19:] = 0                                                     # right-padded prompt: the key-length path, sliced per rank
+        kw = dict(height=128, width=192, num_frames=17, frame_rate=25.0, num_inference_steps=3, guidance_scale=3.0, stg_scale=1.0,
+                  rescaling_scale=0.7, skip_block_list=[1], skip_layer_strategy=SkipLayerStrategy.AttentionValues, output_type="latent",
+                  return_dict=False, is_video=True, vae_per_channel_normalize=True, prompt_embeds=pe, prompt_attention_mask=pm,
+                  negative_prompt_embeds=ne, negative_prompt_attention_mask=pm)
+        steps_cp, steps_one = [], []
+        cp = pipe(generator=torch.Generator().manual_seed(5), cond_parallel_group=dist.group.WORLD, _per_step_latents=steps_cp, **kw)[0]
+        one = pipe(generator=torch.Generator().manual_seed(5), _per_step_latents=steps_one, **kw)[0]       # all three conditions on this GPU
+        torch.cuda.synchronize()
+        ret[rank] = dict(equal=bool(torch.equal(cp, one)) and all(torch.equal(a, b) for a, b in zip(steps_cp, steps_one)),
+                         steps=len(steps_cp), latents=cp.float().cpu())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_pipeline_cond_parallel(world):
+    """The [uncond, text, perturbed] rows of a denoise step on different GPUs (2 ranks: 2 + 1 conditions, 3 ranks: one each), predictions
+    exchanged once per step, guidance + scheduler replicated: every rank ends every step with the latents of the single-GPU call, bit for bit
+    (a row's GEMM / attention / norm results do not depend on the other rows of the batch)."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs (gpurun --gpus {world if world != 3 else 4})")
+    import torch.multiprocessing as mp
+    ret = mp.Manager().dict()
+    mp.spawn(_cond_parallel_worker, args=(world, 30500 + os.getpid() % 300, ret), nprocs=world, join=True)
+    assert len(ret) == world
+    for r in range(world):
+        assert ret[r]["steps"] == 3 and ret[r]["equal"], f"rank {r}: cond-parallel latents differ from the single-GPU call"
+        assert torch.equal(ret[r]["latents"], ret[0]["latents"])
