@@ -191,8 +191,6 @@ class Transformer3DModel(ModuleLike):
         :472-487) computes the same function and is executed as the batched pass here."""
         if attention_mask is not None:
             raise NotImplementedError("self-attention masks are never passed on the reference path")
-        if mixed and skip_layer_strategy == SkipLayerStrategy.TransformerBlock and skip_layer_mask is not None:
-            raise NotImplementedError("mixed precision with SkipLayerStrategy.TransformerBlock (fp32 blend of the residual stream)")
         w, D, H, dh = self.w, self.inner_dim, self.num_attention_heads, self.attention_head_dim
         dev = self.device
         B, N, Cin = hidden_states.shape
@@ -316,7 +314,16 @@ class Transformer3DModel(ModuleLike):
             ff = ops.gemm(nh, Lw["ff1.w"], Lw["ff1.b"], act=ops.ACT_GELU_TANH)
             gemm_res(ff, Lw["ff2.w"], Lw["ff2.b"], residual=x, gate=a[:, 5], rows_per_gate=rows_per_group, out=x)
             if x_orig is not None:
-                ops.stg_blend(x.view(B, N, D), x_orig, skip_dev[li][:B])               # :355-362
+                if mixed:
+                    # fp32 residual stream: x * mask + x_orig * (1 - mask) (:355-362) with a 0 / 1 mask per batch row IS a row copy — the
+                    # rows whose mask is 0 take their block input back, the others are untouched (1 * x + 0 * x_orig is exact in fp32)
+                    mrow = skip_host[li][:B]
+                    if not bool(((mrow == 0) | (mrow == 1)).all()):
+                        raise NotImplementedError("mixed precision with a fractional SkipLayerStrategy.TransformerBlock mask")
+                    for b_ in torch.nonzero(mrow == 0).flatten().tolist():
+                        x.view(B, N, D)[b_].copy_(x_orig.view(B, N, D)[b_])
+                else:
+                    ops.stg_blend(x.view(B, N, D), x_orig, skip_dev[li][:B])           # :355-362
             if ltxv_model is not None and getattr(ltxv_model, "_interrupt", False):
                 return [None]
 
