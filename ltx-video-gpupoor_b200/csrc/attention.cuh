@@ -486,20 +486,26 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const uint64_t qdesc = umma_smem_desc_sw128(smem_u32(sQ), 16, 1024);
       const uint64_t kdesc = umma_smem_desc_sw128(smem_u32(sK), 16, 1024);
       const uint64_t vdesc = umma_smem_desc_sw128(smem_u32(sV), BN * 128, 1024);
-      uint32_t kc0 = 0, vc = 0;      // K ring position of the item's first block / V ring counter
-      uint32_t N0 = 0;               // global step counter at the start of the item
-      int it = 0;
-      int nblk = 0, nsteps = 0;      // key blocks / steps of the CURRENT item (set at the top of the item loop)
-      // S(m), m = item-local step: tile m&1, key block m>>1, TMEM buffer (N0+m) % kSBufs.
-      // part: -1 = all BN keys; 1 = keys BN/2.. (issued first in split mode); 0 = keys 0..BN/2-1 (completes S(m))
-      auto issue_s = [&](int m, int part) {
-        const int t = m & 1, j = m >> 1;
-        const uint32_t kpos = kc0 + j;
+      // Two cursors walk the CTA's work items.  The P.V cursor follows the softmax (step N: O_t += P(N).V); the S cursor runs kSBufs
+      // steps ahead of it and keeps running ACROSS item boundaries: the first score blocks of the next item are issued while the last
+      // P.V steps of the current one are still being produced, so an item with few key blocks (cross-attention: 2-4) does not pay a
+      // tensor-pipe round trip per item.  Steps are numbered globally (N = 2 * block + tile), S(N) lives in buffer N % kSBufs.
+      struct SCur { int w, it, nblk, m; uint32_t kc0, N; } sc{static_cast<int>(blockIdx.x), 0, 0, 0, 0u, 0u};
+      auto s_enter = [&]() { if (sc.w < p.total) sc.nblk = (item_keys((sc.w / p.pairs) / p.H) + BN - 1) / BN; };
+      auto s_advance = [&]() {
+        ++sc.m; ++sc.N;
+        if (sc.m == 2 * sc.nblk) { sc.kc0 += sc.nblk; sc.m = 0; sc.w += gridDim.x; ++sc.it; s_enter(); }
+      };
+      // S at the cursor: tile m&1, key block m>>1 of item sc.w.
+      // part: -1 = all BN keys; 1 = keys BN/2.. (issued first in split mode); 0 = keys 0..BN/2-1 (completes the step)
+      auto issue_s = [&](int part) {
+        const int t = sc.m & 1, j = sc.m >> 1;
+        const uint32_t kpos = sc.kc0 + j;
         const int st = kpos % kStages;
         if (t == 0 && part != 0) mbar_wait_parked(&k_full[st], (kpos / kStages) & 1);
-        if (j == 0) mbar_wait_parked(&q_full[t], it & 1);
+        if (j == 0) mbar_wait_parked(&q_full[t], sc.it & 1);
         tc_fence_after();
-        const uint32_t buf = (N0 + m) % kSBufs;
+        const uint32_t buf = sc.N % kSBufs;
         const uint64_t qa = qdesc + static_cast<uint32_t>(t * (C::kQBytes >> 4));
         const uint64_t ka = kdesc + static_cast<uint32_t>(st * (C::kKBytes >> 4)) + (part == 1 ? ((BN / 2) * 128) >> 4 : 0);
         const uint32_t ts = tmem_base + kColS0 + buf * BN + (part == 1 ? BN / 2 : 0);
@@ -512,7 +518,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
         if (part != 1) {
           umma_commit(&s_full[buf]);
-          if (j + 1 == nblk) umma_commit(&q_empty[t]);
+          if (j + 1 == sc.nblk) umma_commit(&q_empty[t]);
           if (t == 1) umma_commit(&k_empty[st]);
         }
       };
@@ -525,20 +531,24 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         for (int ks = ks0; ks < ks1; ++ks)
           umma_ts(to, tp + ks * 8, va + static_cast<uint32_t>(ks * (2048 >> 4)), idesc_o, (acc || ks > ks0) ? 1u : 0u);
       };
+      s_enter();
+#pragma unroll 1
+      for (int i = 0; i < kSBufs && sc.w < p.total; ++i) { issue_s(-1); s_advance(); }
+      uint32_t vc = 0;               // V ring counter
+      uint32_t N = 0;                // global step of the P.V cursor
+      int it = 0;
       for (int w = blockIdx.x; w < p.total; w += gridDim.x, ++it) {
-        nblk = (item_keys((w / p.pairs) / p.H) + BN - 1) / BN;
-        nsteps = 2 * nblk;
+        const int nblk = (item_keys((w / p.pairs) / p.H) + BN - 1) / BN;
+        const int nsteps = 2 * nblk;
+        // step n: O_t += P(n).V(j), then the S cursor's block into the buffer P(n) leaves
 #pragma unroll 1
-        for (int m = 0; m < kSBufs && m < nsteps; ++m) issue_s(m, -1);
-        // step n: O_t += P(n).V(j), then S(n + kSBufs) into the buffer P(n) leaves
-#pragma unroll 1
-        for (int n = 0; n < nsteps; ++n) {
+        for (int n = 0; n < nsteps; ++n, ++N) {
           const int t = n & 1, j = n >> 1;
           const int sv = vc % kStages;
-          const uint32_t N = N0 + n, buf = N % kSBufs, par = (N / kSBufs) & 1;
-          const bool more = n + kSBufs < nsteps;
+          const uint32_t buf = N % kSBufs, par = (N / kSBufs) & 1;
+          const bool more = sc.w < p.total;        // the cursor then stands at step N + kSBufs, i.e. on this step's buffer
           if (kSplit) {
-            if (more) { mbar_wait_parked(&s_read[buf], par); issue_s(n + kSBufs, 1); }
+            if (more) { mbar_wait_parked(&s_read[buf], par); issue_s(1); }
             mbar_wait_parked(&p_half[buf], par);
             if (j == 0) mbar_wait_parked(&o_free[t], (it & 1) ^ 1);
             if (t == 0) mbar_wait_parked(&v_full[sv], (vc / kStages) & 1);
@@ -557,10 +567,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           umma_commit(&pv_done[t]);
           if (t == 1) { umma_commit(&v_empty[sv]); ++vc; }
           if (j + 1 == nblk) umma_commit(&o_done[t]);
-          if (more) issue_s(n + kSBufs, kSplit ? 0 : -1);
+          if (more) { issue_s(kSplit ? 0 : -1); s_advance(); }
         }
-        N0 += nsteps;
-        kc0 += nblk;
       }
     }
   } else {
