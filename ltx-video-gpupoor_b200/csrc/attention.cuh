@@ -54,8 +54,15 @@ struct AttnCfg {
   // kHalf (d = 64, -DLTXB200_ATTN64_HALFROW): every query row is shared by TWO threads (64 score columns each), i.e. 16 softmax warps =
   // 4 per scheduler instead of 2, which is what the exp loop needs to hide its latencies (mufu_bench2: 18.0 -> 22.3 exp/clk/SM);
   // the two halves exchange their block maxima through shared memory and a 64-thread named barrier.
-#ifdef LTXB200_ATTN64_HALFROW
+#if defined(LTXB200_ATTN64_HALFROW) && defined(LTXB200_ATTN128_HALFROW)
+  static constexpr bool kHalf = true;
+#elif defined(LTXB200_ATTN64_HALFROW)
   static constexpr bool kHalf = (D == 64);
+#elif defined(LTXB200_ATTN128_HALFROW)
+  // d = 128 is bound by the latency of ONE tile's chain (S -> softmax -> P.V -> next S: TMEM holds a single S buffer per tile); two threads
+  // per row were meant to halve the softmax link of that chain.  Parity-green, measured 1196 vs 1222 TF/s on one box: the link is bound by
+  // the tile's 16 384 exponentials on the shared XU pipe, not by the instructions of one thread.  Off by default.
+  static constexpr bool kHalf = (D == 128);
 #else
   static constexpr bool kHalf = false;
 #endif
@@ -310,7 +317,7 @@ DEVI void softmax_block(uint32_t tS, uint32_t tO, bool first, int kbase, int Lk,
 template <int D, int BN, bool kPredicated>
 DEVI void softmax_block_half(uint32_t tS, uint32_t tO_half, int half, bool first, int kbase, int Lk, const float* bias, float sc,
                              float& m_ref, float& m_run, float& l, uint64_t* pv_done, uint32_t pv_parity, float* x_mine,
-                             const float* x_partner, int bar_id) {
+                             const float* x_partner, int bar_id, uint64_t* s_read = nullptr, uint64_t* p_half = nullptr, int lane = 0) {
   constexpr int NC = BN / 2;
   const float kLog2e = 1.4426950408889634f;
   const int c_off = half * NC;
@@ -346,6 +353,9 @@ DEVI void softmax_block_half(uint32_t tS, uint32_t tO_half, int half, bool first
   // overwrite "my" score columns with its half of P)
   tc_fence_before();
   asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+  if (s_read && half == 0) {                     // split mode: the whole S row is in registers (both halves): columns BN/2.. may be overwritten
+    if (lane == 0) mbar_arrive(s_read);
+  }
   tc_fence_after();
   m_blk = fmaxf(m_blk, *x_partner);
   if (first) {
@@ -358,6 +368,12 @@ DEVI void softmax_block_half(uint32_t tS, uint32_t tO_half, int half, bool first
   uint64_t ls[2] = {0ull, 0ull};
 #pragma unroll
   for (int c = 0; c < NC; c += 32) exp_chunk<kPredicated, AttnPoly<D>::kPer8, AttnPoly<D>::kDeg>(&v[c], sc, -m_ref, tS + ((c_off + c) >> 1), ls);
+  if (p_half && half == 0) {                     // split mode: P of keys 0..BN/2-1 (this half's) is in TMEM: their P.V may start
+    tmem_wait_st();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(p_half);
+  }
   float l0, l1;
   unpack_f32x2(add_f32x2(ls[0], ls[1]), l0, l1);
   l += l0 + l1;
@@ -604,10 +620,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           const float* xp = xmax + ((t * 2 + (half ^ 1)) * 2 + (G & 1)) * 128 + row;
           if (kMasked && (bias != nullptr || kbase + BN > Lk_b))
             softmax_block_half<D, BN, true>(tS, tO + half * (D / 2), half, j == 0, kbase, Lk_b, bias, p.scale_log2, m_ref, m_run, l, &pv_done[t],
-                                            (G - 1) & 1, xm, xp, pair_bar);
+                                            (G - 1) & 1, xm, xp, pair_bar, kSplit ? &s_read[buf] : nullptr, kSplit ? &p_half[buf] : nullptr, lane);
           else
             softmax_block_half<D, BN, false>(tS, tO + half * (D / 2), half, j == 0, kbase, Lk_b, bias, p.scale_log2, m_ref, m_run, l, &pv_done[t],
-                                             (G - 1) & 1, xm, xp, pair_bar);
+                                             (G - 1) & 1, xm, xp, pair_bar, kSplit ? &s_read[buf] : nullptr, kSplit ? &p_half[buf] : nullptr, lane);
         } else
         if (kMasked && (bias != nullptr || kbase + BN > Lk_b))
           softmax_block<D, BN, true, kOW, !kOnes>(tS, tO, j == 0, kbase, Lk_b, bias, p.scale_log2, m_ref, m_run, l, &pv_done[t], (G - 1) & 1,

@@ -50,6 +50,13 @@ q, k, v = [qkv[:, :, i * H * d:(i + 1) * H * d].unflatten(-1, (H, d)) for i in r
 run("attention d64 B3 N6144 H32 (this repo)", lambda: ops.attention(q, k, v), 4.0 * B * H * N * N * d)
 qt, kt, vt = [x.transpose(1, 2).contiguous() for x in (q, k, v)]
 run("attention d64 torch SDPA (library)", lambda: torch.nn.functional.scaled_dot_product_attention(qt, kt, vt), 4.0 * B * H * N * N * d)
+if "attn128" in sys.argv:
+    B, N, H, d = 1, 32760, 12, 128
+    q, k, v = [torch.randn(B, N, H, d, device=dev).bfloat16() for _ in range(3)]
+    run("attention d128 B1 N32760 H12 (this repo)", lambda: ops.attention(q, k, v), 4.0 * B * H * N * N * d)
+    qt, kt, vt = [x.transpose(1, 2).contiguous() for x in (q, k, v)]
+    run("attention d128 torch SDPA (library)", lambda: torch.nn.functional.scaled_dot_product_attention(qt, kt, vt), 4.0 * B * H * N * N * d)
+    sys.exit(0)
 for (nm, M, Nn, K, act) in [("qkv", 18432, 6144, 2048, 0), ("ffn_up+gelu", 18432, 8192, 2048, ops.ACT_GELU_TANH), ("ffn_down", 18432, 2048, 8192, 0)]:
     a = torch.randn(M, K, device=dev).bfloat16(); w = torch.randn(Nn, K, device=dev).bfloat16() * 0.02; bias = torch.randn(Nn, device=dev).bfloat16()
     run(f"gemm {nm} {M}x{Nn}x{K} (this repo)", lambda: ops.gemm(a, w, bias, act=act), 2.0 * M * Nn * K)
