@@ -91,6 +91,22 @@ struct AttnCfg {
   // (P(n) only overwrites columns 0..63), P.V of keys 0..63 starts when the first half of P(n) is written, and only
   // P.V of keys 64..127 plus the low half of S(n+2) remain between "P complete" and "next S ready".
   static constexpr bool kSplit = (kSBufs == 2);
+  // k2Mma (-DLTXB200_ATTN128_2MMA): one MMA-issuing thread PER TILE (the two idle warps of the warpgroup) instead of one for both.  A single
+  // in-order thread that waits for tile 0's P cannot issue tile 1's S_hi although its scores have been read, and vice versa; with two
+  // threads each tile's chain (S -> softmax -> P.V -> S) advances on its own and the tensor pipe interleaves whatever has been issued.
+#ifdef LTXB200_ATTN128_2MMA
+  static constexpr bool k2Mma = kSplit;
+#else
+  static constexpr bool k2Mma = false;
+#endif
+  // kSplit34: the early P signal comes after 3/4 of the block instead of 1/2, and the low half of the next scores is issued as two
+  // 32-key MMAs — keys 0..31 right behind P.V of keys 0..95, keys 32..63 behind P.V of keys 96..127 — so that only a quarter of P.V and
+  // a quarter of S remain between "P complete" and "next S ready" (256 instead of 512 tensor-pipe cycles on the tile's critical chain)
+#ifdef LTXB200_ATTN128_SPLIT34
+  static constexpr bool kSplit34 = kSplit && BN == 128 && !kHalf;
+#else
+  static constexpr bool kSplit34 = false;
+#endif
   static_assert(kSBufs * BN + 2 * kOW <= 512, "TMEM budget");
   static constexpr int kQBytes = kAttnBM * D * 2;            // one Q tile
   static constexpr int kKBytes = BN * D * 2;                 // one K (or V) block
@@ -215,7 +231,7 @@ DEVI void exp_chunk(const uint32_t* v, float sc, float neg_m, uint32_t tP, uint6
 // One key block of the online softmax for one query row (one thread): S (fp32, BN columns at tS) -> registers in
 // ONE TMEM pass -> block max -> (lazy) rescale -> exp2 -> P (bf16 pairs) over the first BN/2 columns of tS.
 // m_ref: reference max of the row (log2 domain), m_run: largest score seen so far, l: row sum relative to m_ref.
-template <int D, int BN, bool kPredicated, int kOW = D, bool kSum = true>      // kOW: accumulator columns the lazy rescale covers; kSum: row sum kept here
+template <int D, int BN, bool kPredicated, int kOW = D, bool kSum = true, int kEarly = BN / 2>   // kOW: accumulator columns the lazy rescale covers; kSum: row sum kept here; kEarly: keys written when p_half is signalled
 DEVI void softmax_block(uint32_t tS, uint32_t tO, bool first, int kbase, int Lk, const float* bias, float sc,
                         float& m_ref, float& m_run, float& l, uint64_t* pv_done, uint32_t pv_parity,
                         uint64_t* s_read, uint64_t* p_half, int lane) {
@@ -296,7 +312,7 @@ DEVI void softmax_block(uint32_t tS, uint32_t tO, bool first, int kbase, int Lk,
   for (int c = 0; c < BN; c += 32) {
     if (kPredicated && !lean_tail) exp_chunk<true, AttnPoly<D>::kPer8, AttnPoly<D>::kDeg, kSum>(&v[c], sc, -m_ref, tS + (c >> 1), ls);
     else exp_chunk<false, AttnPoly<D>::kPer8, AttnPoly<D>::kDeg, kSum>(&v[c], sc, -m_ref, tS + (c >> 1), ls);
-    if (p_half && c + 32 == BN / 2) {            // P of keys 0..BN/2-1 is in TMEM: their P.V may start
+    if (p_half && c + 32 == kEarly) {            // P of keys 0..kEarly-1 is in TMEM: their P.V may start
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
@@ -440,9 +456,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     }
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
+      mbar_init(&k_empty[i], C::k2Mma ? 2 : 1);     // k2Mma: both tiles' issuing threads release a stage
       mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 1);
+      mbar_init(&v_empty[i], C::k2Mma ? 2 : 1);
     }
     fence_barrier_init();
   }
@@ -492,10 +508,13 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             tma_load_4d(sV + st * C::kVBytes + c * (BN * 128), &tmV, &v_full[st], c * 64, h, j * BN, b);
         }
       }
-    } else if (warp == kMmaWarp && elect_one()) {
-      // ================= MMA issuer =================
+    } else if ((warp == kMmaWarp || (C::k2Mma && warp == kMmaWarp + 1)) && elect_one()) {
+      // ================= MMA issuer (k2Mma: this thread issues for tile `mt` only; otherwise for both) =================
+      constexpr int kStep = C::k2Mma ? 2 : 1;           // stride of this thread through the global steps N = 2 * block + tile
+      const int mt = C::k2Mma ? warp - kMmaWarp : 0;
       constexpr uint32_t idesc_s = umma_idesc_bf16(kAttnBM, BN, 0, 0);   // S = Q K^T  (both K-major)
       constexpr uint32_t idesc_sh = umma_idesc_bf16(kAttnBM, BN / 2, 0, 0);   // one half of the keys
+      constexpr uint32_t idesc_sq = umma_idesc_bf16(kAttnBM, BN / 4, 0, 0);   // one quarter of the keys (kSplit34)
       constexpr uint32_t idesc_o = umma_idesc_bf16(kAttnBM, kOW, 0, 1);  // O += P V   (V is MN-major; kOnes: 16 more columns of ones behind it)
       // descriptors = (constant high bits | start address >> 4); tile / stage / k-step offsets are added to the
       // low word at issue time (the 14-bit address field cannot carry: shared memory is < 256 KB)
@@ -506,36 +525,38 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       // steps ahead of it and keeps running ACROSS item boundaries: the first score blocks of the next item are issued while the last
       // P.V steps of the current one are still being produced, so an item with few key blocks (cross-attention: 2-4) does not pay a
       // tensor-pipe round trip per item.  Steps are numbered globally (N = 2 * block + tile), S(N) lives in buffer N % kSBufs.
-      struct SCur { int w, it, nblk, m; uint32_t kc0, N; } sc{static_cast<int>(blockIdx.x), 0, 0, 0, 0u, 0u};
+      struct SCur { int w, it, nblk, m; uint32_t kc0, N; } sc{static_cast<int>(blockIdx.x), 0, 0, mt, 0u, static_cast<uint32_t>(mt)};
       auto s_enter = [&]() { if (sc.w < p.total) sc.nblk = (item_keys((sc.w / p.pairs) / p.H) + BN - 1) / BN; };
       auto s_advance = [&]() {
-        ++sc.m; ++sc.N;
-        if (sc.m == 2 * sc.nblk) { sc.kc0 += sc.nblk; sc.m = 0; sc.w += gridDim.x; ++sc.it; s_enter(); }
+        sc.m += kStep; sc.N += kStep;
+        if (sc.m >= 2 * sc.nblk) { sc.kc0 += sc.nblk; sc.m = mt; sc.w += gridDim.x; ++sc.it; s_enter(); }
       };
       // S at the cursor: tile m&1, key block m>>1 of item sc.w.
-      // part: -1 = all BN keys; 1 = keys BN/2.. (issued first in split mode); 0 = keys 0..BN/2-1 (completes the step)
+      // part: -1 = all BN keys; 1 = keys BN/2.. (issued first in split mode); 0 = keys 0..BN/2-1 (completes the step);
+      //       kSplit34: 2 = keys 0..BN/4-1, 3 = keys BN/4..BN/2-1 (completes the step)
       auto issue_s = [&](int part) {
         const int t = sc.m & 1, j = sc.m >> 1;
         const uint32_t kpos = sc.kc0 + j;
         const int st = kpos % kStages;
-        if (t == 0 && part != 0) mbar_wait_parked(&k_full[st], (kpos / kStages) & 1);
+        if ((t == 0 || C::k2Mma) && (part == 1 || part < 0)) mbar_wait_parked(&k_full[st], (kpos / kStages) & 1);
         if (j == 0) mbar_wait_parked(&q_full[t], sc.it & 1);
         tc_fence_after();
         const uint32_t buf = sc.N % kSBufs;
+        const int key0 = part == 1 ? BN / 2 : (part == 3 ? BN / 4 : 0);              // first key (= first score column) of this part
         const uint64_t qa = qdesc + static_cast<uint32_t>(t * (C::kQBytes >> 4));
-        const uint64_t ka = kdesc + static_cast<uint32_t>(st * (C::kKBytes >> 4)) + (part == 1 ? ((BN / 2) * 128) >> 4 : 0);
-        const uint32_t ts = tmem_base + kColS0 + buf * BN + (part == 1 ? BN / 2 : 0);
-        const uint32_t idesc = part < 0 ? idesc_s : idesc_sh;
+        const uint64_t ka = kdesc + static_cast<uint32_t>(st * (C::kKBytes >> 4)) + static_cast<uint32_t>((key0 * 128) >> 4);
+        const uint32_t ts = tmem_base + kColS0 + buf * BN + key0;
+        const uint32_t idesc = part < 0 ? idesc_s : (part >= 2 ? idesc_sq : idesc_sh);
 #pragma unroll
         for (int ks = 0; ks < D / 16; ++ks) {
           const uint32_t offa = ((ks >> 2) * (kAttnBM * 128) + (ks & 3) * 32) >> 4;
           const uint32_t offb = ((ks >> 2) * (BN * 128) + (ks & 3) * 32) >> 4;
           umma_ss(ts, qa + offa, ka + offb, idesc, ks ? 1u : 0u);
         }
-        if (part != 1) {
+        if (part != 1 && part != 2) {
           umma_commit(&s_full[buf]);
           if (j + 1 == sc.nblk) umma_commit(&q_empty[t]);
-          if (t == 1) umma_commit(&k_empty[st]);
+          if (t == 1 || C::k2Mma) umma_commit(&k_empty[st]);
         }
       };
       // O_t += P(n)[:, keys] . V(j)[keys, :]   (k-steps [ks0, ks1) of 16 keys)
@@ -549,16 +570,16 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       };
       s_enter();
 #pragma unroll 1
-      for (int i = 0; i < kSBufs && sc.w < p.total; ++i) { issue_s(-1); s_advance(); }
+      for (int i = 0; i < kSBufs / kStep && sc.w < p.total; ++i) { issue_s(-1); s_advance(); }
       uint32_t vc = 0;               // V ring counter
-      uint32_t N = 0;                // global step of the P.V cursor
+      uint32_t N = mt;               // global step of the P.V cursor
       int it = 0;
       for (int w = blockIdx.x; w < p.total; w += gridDim.x, ++it) {
         const int nblk = (item_keys((w / p.pairs) / p.H) + BN - 1) / BN;
         const int nsteps = 2 * nblk;
         // step n: O_t += P(n).V(j), then the S cursor's block into the buffer P(n) leaves
 #pragma unroll 1
-        for (int n = 0; n < nsteps; ++n, ++N) {
+        for (int n = mt; n < nsteps; n += kStep, N += kStep) {
           const int t = n & 1, j = n >> 1;
           const int sv = vc % kStages;
           const uint32_t buf = N % kSBufs, par = (N / kSBufs) & 1;
@@ -567,12 +588,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             if (more) { mbar_wait_parked(&s_read[buf], par); issue_s(1); }
             mbar_wait_parked(&p_half[buf], par);
             if (j == 0) mbar_wait_parked(&o_free[t], (it & 1) ^ 1);
-            if (t == 0) mbar_wait_parked(&v_full[sv], (vc / kStages) & 1);
+            if (t == 0 || C::k2Mma) mbar_wait_parked(&v_full[sv], (vc / kStages) & 1);
             tc_fence_after();
-            issue_pv(t, buf, sv, 0, BN / 32, j > 0);
+            constexpr int kEarlySteps = C::kSplit34 ? 3 * BN / 64 : BN / 32;      // k-steps (16 keys) covered by the early P signal
+            issue_pv(t, buf, sv, 0, kEarlySteps, j > 0);
+            if (C::kSplit34 && more) issue_s(2);                                   // score columns 0..BN/4-1 = P of keys 0..BN/2-1: consumed
             mbar_wait_parked(&p_full[buf], par);
             tc_fence_after();
-            issue_pv(t, buf, sv, BN / 32, BN / 16, true);
+            issue_pv(t, buf, sv, kEarlySteps, BN / 16, true);
           } else {
             mbar_wait_parked(&p_full[buf], par);
             if (j == 0) mbar_wait_parked(&o_free[t], (it & 1) ^ 1);
@@ -581,9 +604,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             issue_pv(t, buf, sv, 0, BN / 16, j > 0);
           }
           umma_commit(&pv_done[t]);
-          if (t == 1) { umma_commit(&v_empty[sv]); ++vc; }
+          if (t == 1 || C::k2Mma) { umma_commit(&v_empty[sv]); ++vc; }
           if (j + 1 == nblk) umma_commit(&o_done[t]);
-          if (more) { issue_s(kSplit ? 0 : -1); s_advance(); }
+          if (more) { issue_s(kSplit ? (C::kSplit34 ? 3 : 0) : -1); s_advance(); }
         }
       }
     }
@@ -612,6 +635,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const uint32_t N = 2 * G + t, buf = N % kSBufs;
         mbar_wait(&s_full[buf], (N / kSBufs) & 1);
         tc_fence_after();
+#ifdef LTXB200_ATTN128_PINGPONG
+        // strict ping-pong of the two softmax warpgroups (named barriers 9 / 10, 256 threads each: 128 waiting + 128 arriving): a tile's
+        // softmax section runs alone on the SM while the other tile's MMAs are in flight
+        if (kSplit && !kHalf) {
+          if (G == 0 && t == 1) asm volatile("bar.arrive 9, 256;" ::: "memory");      // tile 0 goes first
+          asm volatile("bar.sync %0, 256;" ::"r"(9 + t) : "memory");
+        }
+#endif
         const int kbase = j * BN;
         const uint32_t tS = tmem_base + kColS0 + buf * BN + lane_addr;
         // full blocks without a bias take the lean path; the tail block / biased blocks take the predicated one
@@ -626,15 +657,18 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                                              (G - 1) & 1, xm, xp, pair_bar, kSplit ? &s_read[buf] : nullptr, kSplit ? &p_half[buf] : nullptr, lane);
         } else
         if (kMasked && (bias != nullptr || kbase + BN > Lk_b))
-          softmax_block<D, BN, true, kOW, !kOnes>(tS, tO, j == 0, kbase, Lk_b, bias, p.scale_log2, m_ref, m_run, l, &pv_done[t], (G - 1) & 1,
+          softmax_block<D, BN, true, kOW, !kOnes, C::kSplit34 ? 3 * BN / 4 : BN / 2>(tS, tO, j == 0, kbase, Lk_b, bias, p.scale_log2, m_ref, m_run, l, &pv_done[t], (G - 1) & 1,
                                                   kSplit ? &s_read[buf] : nullptr, kSplit ? &p_half[buf] : nullptr, lane);
         else
-          softmax_block<D, BN, false, kOW, !kOnes>(tS, tO, j == 0, kbase, Lk_b, bias, p.scale_log2, m_ref, m_run, l, &pv_done[t], (G - 1) & 1,
+          softmax_block<D, BN, false, kOW, !kOnes, C::kSplit34 ? 3 * BN / 4 : BN / 2>(tS, tO, j == 0, kbase, Lk_b, bias, p.scale_log2, m_ref, m_run, l, &pv_done[t], (G - 1) & 1,
                                                    kSplit ? &s_read[buf] : nullptr, kSplit ? &p_half[buf] : nullptr, lane);
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[buf]);
+#ifdef LTXB200_ATTN128_PINGPONG
+        if (kSplit && !kHalf) asm volatile("bar.arrive %0, 256;" ::"r"(9 + (t ^ 1)) : "memory");
+#endif
       }
       // ---- epilogue: O / l -> bf16 -> global ----
       mbar_wait(&o_done[t], it & 1);
