@@ -286,11 +286,18 @@ DEVI void softmax_block(uint32_t tS, uint32_t tO, bool first, int kbase, int Lk,
         }
       }
     } else {
+      // four independent max chains per 32-score chunk (a softmax warp that has its scheduler to itself — d = 128, where the two tiles
+      // alternate — is bound by dependency latency, not by issue slots; measured +0-3 % at d = 128, neutral at d = 64)
+      float mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
+      for (int i = 0; i < 32; i += 8) {
         mx0 = fmax3(mx0, __uint_as_float(v[c + i]), __uint_as_float(v[c + i + 1]));
         mx1 = fmax3(mx1, __uint_as_float(v[c + i + 2]), __uint_as_float(v[c + i + 3]));
+        mx2 = fmax3(mx2, __uint_as_float(v[c + i + 4]), __uint_as_float(v[c + i + 5]));
+        mx3 = fmax3(mx3, __uint_as_float(v[c + i + 6]), __uint_as_float(v[c + i + 7]));
       }
+      mx0 = fmaxf(mx0, mx2);
+      mx1 = fmaxf(mx1, mx3);
     }
   }
   if (s_read) {                                  // the whole S row is in registers: columns 64.. may be overwritten
