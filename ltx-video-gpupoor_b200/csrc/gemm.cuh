@@ -111,8 +111,11 @@ DEVI void epilogue_row(const GemmParams& p, uint32_t t_addr, int tn, bool row_ok
           if (full || n0 + j < p.N) {
             const uint4 bq = bias4[j >> 3];
             const float2 b0 = unpack_bf16(bq.x), b1 = unpack_bf16(bq.y), b2 = unpack_bf16(bq.z), b3 = unpack_bf16(bq.w);
-            f[j] += b0.x; f[j + 1] += b0.y; f[j + 2] += b1.x; f[j + 3] += b1.y;
-            f[j + 4] += b2.x; f[j + 5] += b2.y; f[j + 6] += b3.x; f[j + 7] += b3.y;
+            // packed adds (FADD2): the epilogue runs one warp per scheduler, every instruction it does not issue is latency it does not pay
+            unpack_f32x2(add_f32x2(pack_f32x2(f[j], f[j + 1]), pack_f32x2(b0.x, b0.y)), f[j], f[j + 1]);
+            unpack_f32x2(add_f32x2(pack_f32x2(f[j + 2], f[j + 3]), pack_f32x2(b1.x, b1.y)), f[j + 2], f[j + 3]);
+            unpack_f32x2(add_f32x2(pack_f32x2(f[j + 4], f[j + 5]), pack_f32x2(b2.x, b2.y)), f[j + 4], f[j + 5]);
+            unpack_f32x2(add_f32x2(pack_f32x2(f[j + 6], f[j + 7]), pack_f32x2(b3.x, b3.y)), f[j + 6], f[j + 7]);
           }
         }
       }
