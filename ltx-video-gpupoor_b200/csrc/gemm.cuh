@@ -79,7 +79,7 @@ struct GemmSmem {
   static constexpr int kStageBytesA = kGemmBM * kGemmBK * 2;          // 16 KB
   static constexpr int kStageBytesB = (BN / kCtas) * kGemmBK * 2;     // CTA pair: each CTA holds half of the B tile
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
-  static constexpr int kStages = (BN == 256 && kCtas == 1) ? 4 : 6;
+  static constexpr int kStages = ((BN == 256 && kCtas == 1) || BN == 512) ? 4 : 6;      // BN = 512 (CTA pair): 4 x 48 KB
   static constexpr int kBarBytes = 256;
   static constexpr int kTotal = kStages * kStageBytes + kBarBytes + 1024;  // +1024 alignment slack
 };
@@ -305,6 +305,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmParams p) {
   static_assert(kCtas == 1 || kCtas == 2, "one CTA or a CTA pair");
+  static_assert(BN <= 256 || (BN == 512 && kCtas == 2 && !kConv), "the 256 x 512 tile exists for the plain CTA-pair GEMM only");
+  // BN = 512: a 256 x 512 pair tile — the accumulator takes all 512 TMEM columns of each CTA, so it is SINGLE-buffered (the epilogue of
+  // a tile is not overlapped with the next mainloop) in exchange for a third less operand traffic per flop: A 16 KB + B 32 KB per CTA and
+  // k-block for 8.4 MFLOP = 175 flop/B against 131 for 256 x 256.  The GEMMs of the step run at the L2 -> SM limit (11-12 TB/s,
+  // profiles/r02_ncu_summary.md §8), so this pays where the mainloop is long against the epilogue: K >= 4096 (FFN-down).
+  constexpr int kAccBufs = (BN == 512) ? 1 : 2;
+  constexpr int kMmaN = (BN > 256) ? 256 : BN;          // columns per tcgen05.mma (N <= 256)
+  constexpr int kNSub = BN / kMmaN;
   using S = GemmSmem<BN, kCtas>;
   const uint32_t cta_rank = (kCtas == 2) ? cluster_ctarank() : 0u;
   const int cta_first = blockIdx.x / kCtas, cta_stride = gridDim.x / kCtas;     // persistent walk in units of CTA groups
@@ -341,8 +349,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     fence_barrier_init();
   }
   if (warp == 1) {
-    if (kCtas == 2) tmem_alloc_2cta<2 * BN>(tmem_slot);
-    else tmem_alloc<2 * BN>(tmem_slot);
+    if (kCtas == 2) tmem_alloc_2cta<kAccBufs * BN>(tmem_slot);
+    else tmem_alloc<kAccBufs * BN>(tmem_slot);
   }
   tc_fence_before();
   if (kCtas == 2) cluster_sync_all();              // the peer must not signal barriers that are not initialised yet
@@ -396,7 +404,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           } else if (kCtas == 2) {
             tma_load_2d_2sm(sa, &tmA, &full_bar[stage], kb * kGemmBK, tm * kGemmBM);
-            tma_load_2d_2sm(sb, &tmB, &full_bar[stage], kb * kGemmBK, brow);
+            if (kNSub == 1) {
+              tma_load_2d_2sm(sb, &tmB, &full_bar[stage], kb * kGemmBK, brow);
+            } else {
+              // each MMA reads columns [0, 128) of its 256 from the leader's B rows and [128, 256) from the peer's: CTA r keeps the B
+              // rows {sub * 256 + r * 128 ...} of the tile, so that accumulator column c is output column c
+#pragma unroll
+              for (int sub = 0; sub < kNSub; ++sub)
+                tma_load_2d_2sm(sb + sub * (kMmaN / 2) * kGemmBK * 2, &tmB, &full_bar[stage], kb * kGemmBK,
+                                tn * BN + sub * kMmaN + static_cast<int>(cta_rank) * (kMmaN / 2));
+            }
           } else {
             tma_load_2d(sa, &tmA, &full_bar[stage], kb * kGemmBK, tm * kGemmBM);
             tma_load_2d(sb, &tmB, &full_bar[stage], kb * kGemmBK, brow);
@@ -408,7 +425,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     // ================= MMA issuer (CTA pair: the leader only) =================
     const int issue_tiles = (kCtas == 2 && cta_rank != 0) ? 0 : num_tiles;      // the peer's MMA warp only allocates / frees TMEM
-    constexpr uint32_t idesc = umma_idesc_bf16(kGemmBM * kCtas, BN, 0, 0);
+    constexpr uint32_t idesc = umma_idesc_bf16(kGemmBM * kCtas, kMmaN, 0, 0);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -426,9 +443,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < kGemmBK / 16; ++k) {
             const uint64_t ad = umma_smem_desc_sw128(sa + k * 32, 16, 1024);
-            const uint64_t bd = umma_smem_desc_sw128(sb + k * 32, 16, 1024);
-            if (kCtas == 2) umma_ss_2cta(d_tmem, ad, bd, idesc, (kb | k) ? 1u : 0u);
-            else umma_ss(d_tmem, ad, bd, idesc, (kb | k) ? 1u : 0u);
+#pragma unroll
+            for (int sub = 0; sub < kNSub; ++sub) {
+              const uint64_t bd = umma_smem_desc_sw128(sb + sub * (kMmaN / kCtas) * kGemmBK * 2 + k * 32, 16, 1024);
+              if (kCtas == 2) umma_ss_2cta(d_tmem + sub * kMmaN, ad, bd, idesc, (kb | k) ? 1u : 0u);
+              else umma_ss(d_tmem + sub * kMmaN, ad, bd, idesc, (kb | k) ? 1u : 0u);
+            }
           }
           if (kCtas == 2) {
             umma_commit_2cta(&empty_bar[stage], 3u);                       // frees the slot in BOTH CTAs
@@ -441,7 +461,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == kAccBufs) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     // ================= epilogue =================
@@ -480,7 +500,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (kCtas == 2 && cta_rank != 0) mbar_arrive_remote(&tempty_bar[acc], 0);
         else mbar_arrive(&tempty_bar[acc]);
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == kAccBufs) { acc = 0; acc_phase ^= 1; }
     }
   }
 
@@ -489,8 +509,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    if (kCtas == 2) tmem_dealloc_2cta<2 * BN>(tmem_base);
-    else tmem_dealloc<2 * BN>(tmem_base);
+    if (kCtas == 2) tmem_dealloc_2cta<kAccBufs * BN>(tmem_base);
+    else tmem_dealloc<kAccBufs * BN>(tmem_base);
   }
 }
 

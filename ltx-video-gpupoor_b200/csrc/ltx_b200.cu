@@ -129,9 +129,16 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, int
   if ((bias && !aligned16(bias)) || (residual && (!aligned16(residual) || (ldr & (mod_f32 ? 3 : 7)))) ||
       (gate && (!aligned16(gate) || (gate_ld & (mod_f32 ? 3 : 7)) || rows_per_gate <= 0)))
     return kErrBadAlign;
-  const int BN = (N <= 128) ? 128 : 256;
+  int BN = (N <= 128) ? 128 : 256;
   static const int env_2cta = getenv("LTXB200_GEMM_2CTA") ? atoi(getenv("LTXB200_GEMM_2CTA")) : 1;
   const bool two_cta = env_2cta && BN == 256 && M > 128;
+  // 256 x 512 pair tiles (single-buffered accumulator, a third less operand traffic per flop), OPT-IN: parity-green, and measured
+  // slower on FFN-down (18432 x 2048 x 8192): 1485 vs 1498 TF/s burst; sustained at the power cap 1247 TF/s @ 1477 MHz vs 1290 @ 1275 MHz —
+  // the chip clocks 16 % higher on the lighter operand traffic but the un-overlapped epilogue and the two half-width MMAs per k-step cost more.
+  // LTXB200_GEMM_BN512: 0 = never (default), 1 = K >= 4096, 2 = whenever the shape allows
+  static const int env_bn512 = getenv("LTXB200_GEMM_BN512") ? atoi(getenv("LTXB200_GEMM_BN512")) : 0;
+  const bool wide = two_cta && !vs && (N % 512 == 0) && env_bn512 && (env_bn512 == 2 || K >= 4096);
+  if (wide) BN = 512;
   CUtensorMap ta, tb;
   {
     uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
@@ -142,7 +149,7 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, int
   {
     uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
     uint64_t str[1] = {static_cast<uint64_t>(ldw) * 2};
-    uint32_t box[2] = {kGemmBK, static_cast<uint32_t>(two_cta ? BN / 2 : BN)};     // CTA pair: each CTA loads half of the B tile
+    uint32_t box[2] = {kGemmBK, static_cast<uint32_t>(wide ? 128 : (two_cta ? BN / 2 : BN))};     // CTA pair: each CTA loads half of the B tile (256 x 512: in two boxes)
     if (make_tmap_bf16(&tb, W, 2, dims, str, box)) return kErrTensorMap;
   }
   GemmParams p{};
@@ -162,6 +169,7 @@ static int gemm_impl(const void* A, int64_t lda, const void* W, int64_t ldw, int
   p.n_fastest = (static_cast<long long>(N) * K * 2 <= (48ll << 20)) ? 1 : 0;
   if (const char* e = getenv("LTXB200_GEMM_RASTER")) p.n_fastest = atoi(e);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (wide) return launch_gemm_2cta<512, false>(ta, tb, p, ((M + 2 * kGemmBM - 1) / (2 * kGemmBM)) * (N / 512), st);
   if (two_cta) return launch_gemm_2cta<256, false>(ta, tb, p, ((M + 2 * kGemmBM - 1) / (2 * kGemmBM)) * ((N + BN - 1) / BN), st);
   const int tiles = ((M + kGemmBM - 1) / kGemmBM) * ((N + BN - 1) / BN);
   return BN == 128 ? launch_gemm<128, false>(ta, tb, p, tiles, st) : launch_gemm<256, false>(ta, tb, p, tiles, st);

@@ -32,7 +32,7 @@ def rel(a, b):
 # ------------------------------------------------------------------ GEMM
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 128, 128), (300, 136, 72), (1, 512, 256), (3, 12288, 2048),
                                    (6144, 2048, 2048), (1000, 8192, 2048), (777, 2048, 8192), (6144, 128, 2048),
-                                   (6144, 2048, 128)])
+                                   (6144, 2048, 128), (1000, 1024, 4160), (513, 512, 8192), (5000, 1536, 8960)])   # the last three: long K (and, with LTXB200_GEMM_BN512=1, the 256 x 512 pair tiles)
 def test_gemm_plain(M, N, K):
     a, w, b = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=K ** -0.5), rnd(N, seed=3)
     ref = a.float() @ w.float().t() + b.float()
@@ -62,6 +62,13 @@ def test_gemm_epilogues():
     o32 = ops.gemm(big[:, K:], w, None, out_f32=True)
     assert o32.dtype == torch.float32
     assert rel(o32, big[:, K:].float() @ w.float().t()) < 2e-3
+    # long K with the gate / residual epilogue, in place, and a partial last row tile (LTXB200_GEMM_BN512=1: the 256 x 512 pair tile)
+    M, N, K = 1300, 1024, 4096
+    a, w, b = rnd(M, K, seed=11), rnd(N, K, seed=12, scale=K ** -0.5), rnd(N, seed=13)
+    res, gate = rnd(M, N, seed=14), rnd((M + 99) // 100, N, seed=15)
+    ref = res.float() + gate.float().repeat_interleave(100, dim=0)[:M] * (a.float() @ w.float().t() + b.float())
+    out = ops.gemm(a, w, b, residual=res, gate=gate, rows_per_gate=100, out=res)
+    assert out.data_ptr() == res.data_ptr() and rel(out, ref) < 6e-3
 
 
 # ------------------------------------------------------------------ attention
