@@ -218,3 +218,37 @@ def test_teacache_decision_is_taken_on_both_halves_under_cfg_parallel(monkeypatc
     assert cond == run(0, True) == run(1, True)          # both CFG-parallel halves == the single-process decision
     assert False in cond and True in cond
     assert run(1, False) == [True] * len(dist_seq)       # the old behaviour: the uncond half never skipped
+
+
+def _cond_par_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from ltx_video_gpupoor_b200.ltx.distributed.cond_parallel import CondParallel
+        cp = CondParallel(dist.group.WORLD)
+        conds, bsz = 3, 2
+        ranges = cp.ranges(conds)
+        assert ranges == [(0, 2), (2, 3)] and cp.size == world and cp.rank == rank
+        # every rank owns the rows of its conditions (value = 100 * cond + sample), the others hold garbage until the exchange
+        pred = torch.full((conds * bsz, 4, 8), -1.0)
+        lo, hi = ranges[rank]
+        for c in range(lo, hi):
+            for j in range(bsz):
+                pred[c * bsz + j] = 100.0 * c + j
+        cp.exchange(pred, bsz, ranges)
+        want = torch.tensor([100.0 * c + j for c in range(conds) for j in range(bsz)])
+        ret[rank] = (bool(torch.equal(pred[:, 0, 0], want)) and bool((pred == pred[:, :1, :1]).all()),
+                     cp.any_flag(False, "cpu"), cp.any_flag(rank == 1, "cpu"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ltx_cond_parallel_exchange_gloo():
+    """Guidance-condition parallelism of the LTX loop (ltx/distributed/cond_parallel.py) on CPU: 3 conditions over 2 ranks (2 + 1), every
+    owner's prediction rows reach every rank; the `_interrupt` poll is an OR over the group."""
+    world = 2
+    ret = mp.Manager().dict()
+    mp.spawn(_cond_par_worker, args=(world, 29500 + (os.getpid() % 2000) + 7, ret), nprocs=world, join=True)
+    assert len(ret) == world
+    for r in range(world):
+        assert ret[r] == (True, False, True), (r, ret[r])
