@@ -182,6 +182,9 @@ DEVI void exp_chunk_pk(const uint32_t* v, float sc, float neg_m, uint32_t (&pk)[
                                : fma_f32x2(V, SC, NM);
     float e0, e1;
     const bool poly = !kScaled && (((p & 7) + 1) * kPolyPer8 / 8 != (p & 7) * kPolyPer8 / 8);   // spread over the 8 pairs
+#ifdef LTXB200_ABL_NOEXP                         // ablation build (wrong results): what the block costs without its exponentials
+    unpack_f32x2(X, e0, e1);
+#else
     if (poly) {
       exp2_poly_f32x2<kDeg>(X, e0, e1);
     } else {
@@ -190,7 +193,10 @@ DEVI void exp_chunk_pk(const uint32_t* v, float sc, float neg_m, uint32_t (&pk)[
       e0 = fast_exp2(x0);
       e1 = fast_exp2(x1);
     }
+#endif
+#ifndef LTXB200_ABL_NOSUM
     if (kSum) ls[p & 1] = add_f32x2(ls[p & 1], pack_f32x2(e0, e1));
+#endif
     pk[p] = pack_bf16(e0, e1);
   }
 }
@@ -289,6 +295,9 @@ DEVI void softmax_block(uint32_t tS, uint32_t tO, bool first, int kbase, int Lk,
       // four independent max chains per 32-score chunk (a softmax warp that has its scheduler to itself — d = 128, where the two tiles
       // alternate — is bound by dependency latency, not by issue slots; measured +0-3 % at d = 128, neutral at d = 64)
       float mx2 = -INFINITY, mx3 = -INFINITY;
+#ifdef LTXB200_ABL_NOMAX                         // ablation build (wrong results): the block without its max pass
+      mx0 = 0.f;
+#else
 #pragma unroll
       for (int i = 0; i < 32; i += 8) {
         mx0 = fmax3(mx0, __uint_as_float(v[c + i]), __uint_as_float(v[c + i + 1]));
@@ -296,6 +305,7 @@ DEVI void softmax_block(uint32_t tS, uint32_t tO, bool first, int kbase, int Lk,
         mx2 = fmax3(mx2, __uint_as_float(v[c + i + 4]), __uint_as_float(v[c + i + 5]));
         mx3 = fmax3(mx3, __uint_as_float(v[c + i + 6]), __uint_as_float(v[c + i + 7]));
       }
+#endif
       mx0 = fmaxf(mx0, mx2);
       mx1 = fmaxf(mx1, mx3);
     }

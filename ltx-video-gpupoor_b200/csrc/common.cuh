@@ -161,6 +161,11 @@ DEVI bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // wait with a suspend-time hint: the hardware parks the thread until the phase completes (or ~the hint elapses) instead of returning
 // after a few cycles, so a single issuing thread that waits most of the time does not eat its scheduler's issue slots
 DEVI void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+#ifdef LTXB200_MMA_SPIN                          // A/B: poll instead of parking (lower wake-up latency, more issue slots taken)
+  while (!mbar_try_wait(bar, parity)) {
+  }
+  return;
+#endif
   uint32_t ok;
   do {
     asm volatile(
