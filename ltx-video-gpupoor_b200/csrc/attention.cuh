@@ -113,7 +113,15 @@ struct AttnCfg {
   static constexpr int kVBytes = kKBytes + (kOnes ? BN * 128 : 0);            // V stage: the block (+ the ones tile, [BN][64] bf16 1.0)
   static constexpr int kStages = kOnes ? 5 : (128 * 1024) / (2 * kKBytes);    // 128 KB of K/V in flight (kOnes: 5 x 36 KB)
   static constexpr int kBarBytes = 512 + (kHalf ? 2 * 2 * 2 * 128 * 4 + 2 * 2 * 128 * 4 : 0);   // + max / sum exchange slots of the half rows
-  static constexpr int kTotal = 2 * kQBytes + kStages * (kKBytes + kVBytes) + kBarBytes + 1024;
+  // K ring one stage deeper than the V ring where shared memory allows it (d = 128: 3 x 32 KB of K, 2 x 32 KB of V): the score MMAs of
+  // block j + 1 are issued while block j is still in the softmax, i.e. K is needed a block earlier than V (-DLTXB200_ATTN_KSTAGES_EQ: equal rings)
+#ifdef LTXB200_ATTN_KSTAGES_EQ
+  static constexpr int kStagesK = kStages;
+#else
+  static constexpr int kStagesK = kStages + ((2 * kQBytes + (kStages + 1) * kKBytes + kStages * kVBytes + kBarBytes + 1024 <= 227 * 1024 && kStages < 3) ? 1 : 0);
+#endif
+  static constexpr int kStagesV = kStages;
+  static constexpr int kTotal = 2 * kQBytes + kStagesK * kKBytes + kStagesV * kVBytes + kBarBytes + 1024;
   static_assert(kTotal <= 227 * 1024, "shared memory budget");
   static constexpr int kSoftmaxWarps = kHalf ? 16 : 8;
   static constexpr int kThreads = (kSoftmaxWarps + 4) * 32;  // softmax warps + TMA warp + MMA warp + 2 idle (warpgroup alignment)
@@ -420,7 +428,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   constexpr int BN = C::BN;
   constexpr int kOW = C::kOW;
   constexpr bool kOnes = C::kOnes;
-  constexpr int kStages = C::kStages;
+  constexpr int kStagesK = C::kStagesK, kStagesV = C::kStagesV;
   constexpr int kSBufs = C::kSBufs;
   constexpr bool kSplit = C::kSplit;
   constexpr int kChunks = D / 64;                    // 64-wide (128 B) column chunks per row
@@ -432,16 +440,16 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                                 // [2][128][D]
-  uint8_t* sK = sQ + 2 * C::kQBytes;                  // [kStages][BN][D]
-  uint8_t* sV = sK + kStages * C::kKBytes;            // [kStages][BN][D] (kOnes: each stage followed by its [BN][64] tile of ones)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kStages * C::kVBytes);
+  uint8_t* sK = sQ + 2 * C::kQBytes;                  // [kStagesK][BN][D]
+  uint8_t* sV = sK + kStagesK * C::kKBytes;           // [kStagesV][BN][D] (kOnes: each stage followed by its [BN][64] tile of ones)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kStagesV * C::kVBytes);
   uint64_t* q_full = bars;                // [2]       TMA -> MMA
   uint64_t* q_empty = q_full + 2;         // [2]       last S of the item issued: Q tile may be overwritten
-  uint64_t* k_full = q_empty + 2;         // [kStages]
-  uint64_t* k_empty = k_full + kStages;
-  uint64_t* v_full = k_empty + kStages;
-  uint64_t* v_empty = v_full + kStages;
-  uint64_t* s_full = v_empty + kStages;   // [kSBufs]  S(n) complete in buffer n % kSBufs
+  uint64_t* k_full = q_empty + 2;         // [kStagesK]
+  uint64_t* k_empty = k_full + kStagesK;
+  uint64_t* v_full = k_empty + kStagesK;  // [kStagesV]
+  uint64_t* v_empty = v_full + kStagesV;
+  uint64_t* s_full = v_empty + kStagesV;  // [kSBufs]  S(n) complete in buffer n % kSBufs
   uint64_t* p_full = s_full + kSBufs;     // [kSBufs]  P(n) written over it (4 warps arrive)
   uint64_t* pv_done = p_full + kSBufs;    // [2]       P.V of tile t's block retired (lazy-rescale guard)
   uint64_t* o_done = pv_done + 2;         // [2]       last P.V of the item retired
@@ -471,9 +479,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       mbar_init(&s_read[i], 4);
       mbar_init(&p_half[i], 4);
     }
-    for (int i = 0; i < kStages; ++i) {
+    for (int i = 0; i < kStagesK; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&k_empty[i], C::k2Mma ? 2 : 1);     // k2Mma: both tiles' issuing threads release a stage
+    }
+    for (int i = 0; i < kStagesV; ++i) {
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], C::k2Mma ? 2 : 1);
     }
@@ -482,7 +492,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   if (warp == kMmaWarp) tmem_alloc<C::kTmemCols>(tmem_slot);
   if constexpr (kOnes) {
     // the constant value columns behind every V stage: all 64 columns of the tile are 1.0, so the 128-byte swizzle is immaterial
-    for (int st = 0; st < kStages; ++st) {
+    for (int st = 0; st < kStagesV; ++st) {
       uint4* ones = reinterpret_cast<uint4*>(sV + st * C::kVBytes + C::kKBytes);
       for (int i = threadIdx.x; i < BN * 128 / 16; i += C::kThreads) ones[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
     }
@@ -510,20 +520,28 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           for (int c = 0; c < kChunks; ++c)
             tma_load_4d(sQ + t * C::kQBytes + c * (kAttnBM * 128), &tmQ, &q_full[t], c * 64, h, qp * 256 + t * kAttnBM, b);
         }
-        for (int j = 0; j < nblk; ++j, ++kc) {
-          const int st = kc % kStages;
-          const uint32_t ph = (kc / kStages) & 1;
-          mbar_wait_backoff(&k_empty[st], ph ^ 1);
+        // K(j + 1) is requested before V(j): the K ring runs one block ahead of the V ring
+        auto load_k = [&](int j) {
+          const uint32_t kk = kc + j;
+          const int st = kk % kStagesK;
+          mbar_wait_backoff(&k_empty[st], ((kk / kStagesK) & 1) ^ 1);
           mbar_arrive_expect_tx(&k_full[st], C::kKBytes);
 #pragma unroll
           for (int c = 0; c < kChunks; ++c)
             tma_load_4d(sK + st * C::kKBytes + c * (BN * 128), &tmK, &k_full[st], c * 64, h, j * BN, b);
-          mbar_wait_backoff(&v_empty[st], ph ^ 1);
-          mbar_arrive_expect_tx(&v_full[st], C::kKBytes);
+        };
+        load_k(0);
+        for (int j = 0; j < nblk; ++j) {
+          if (j + 1 < nblk) load_k(j + 1);
+          const uint32_t vv = kc + j;
+          const int sv = vv % kStagesV;
+          mbar_wait_backoff(&v_empty[sv], ((vv / kStagesV) & 1) ^ 1);
+          mbar_arrive_expect_tx(&v_full[sv], C::kKBytes);
 #pragma unroll
           for (int c = 0; c < kChunks; ++c)
-            tma_load_4d(sV + st * C::kVBytes + c * (BN * 128), &tmV, &v_full[st], c * 64, h, j * BN, b);
+            tma_load_4d(sV + sv * C::kVBytes + c * (BN * 128), &tmV, &v_full[sv], c * 64, h, j * BN, b);
         }
+        kc += nblk;
       }
     } else if ((warp == kMmaWarp || (C::k2Mma && warp == kMmaWarp + 1)) && elect_one()) {
       // ================= MMA issuer (k2Mma: this thread issues for tile `mt` only; otherwise for both) =================
@@ -554,8 +572,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       auto issue_s = [&](int part) {
         const int t = sc.m & 1, j = sc.m >> 1;
         const uint32_t kpos = sc.kc0 + j;
-        const int st = kpos % kStages;
-        if ((t == 0 || C::k2Mma) && (part == 1 || part < 0)) mbar_wait_parked(&k_full[st], (kpos / kStages) & 1);
+        const int st = kpos % kStagesK;
+        if ((t == 0 || C::k2Mma) && (part == 1 || part < 0)) mbar_wait_parked(&k_full[st], (kpos / kStagesK) & 1);
         if (j == 0) mbar_wait_parked(&q_full[t], sc.it & 1);
         tc_fence_after();
         const uint32_t buf = sc.N % kSBufs;
@@ -598,14 +616,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll 1
         for (int n = mt; n < nsteps; n += kStep, N += kStep) {
           const int t = n & 1, j = n >> 1;
-          const int sv = vc % kStages;
+          const int sv = vc % kStagesV;
           const uint32_t buf = N % kSBufs, par = (N / kSBufs) & 1;
           const bool more = sc.w < p.total;        // the cursor then stands at step N + kSBufs, i.e. on this step's buffer
           if (kSplit) {
             if (more) { mbar_wait_parked(&s_read[buf], par); issue_s(1); }
             mbar_wait_parked(&p_half[buf], par);
             if (j == 0) mbar_wait_parked(&o_free[t], (it & 1) ^ 1);
-            if (t == 0 || C::k2Mma) mbar_wait_parked(&v_full[sv], (vc / kStages) & 1);
+            if (t == 0 || C::k2Mma) mbar_wait_parked(&v_full[sv], (vc / kStagesV) & 1);
             tc_fence_after();
             constexpr int kEarlySteps = C::kSplit34 ? 3 * BN / 64 : BN / 32;      // k-steps (16 keys) covered by the early P signal
             issue_pv(t, buf, sv, 0, kEarlySteps, j > 0);
@@ -616,7 +634,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           } else {
             mbar_wait_parked(&p_full[buf], par);
             if (j == 0) mbar_wait_parked(&o_free[t], (it & 1) ^ 1);
-            if (t == 0) mbar_wait_parked(&v_full[sv], (vc / kStages) & 1);
+            if (t == 0) mbar_wait_parked(&v_full[sv], (vc / kStagesV) & 1);
             tc_fence_after();
             issue_pv(t, buf, sv, 0, BN / 16, j > 0);
           }
