@@ -160,6 +160,8 @@ class LTXVideoPipeline:
                                      noise=item.encode_noise).to(device=init_latents.device, dtype=init_latents.dtype)
                 else:
                     lat = item.latents.to(device=init_latents.device, dtype=init_latents.dtype)
+                if lat.shape[0] == 1 and init_latents.shape[0] > 1:          # one conditioning item for every video of the call
+                    lat = lat.expand(init_latents.shape[0], -1, -1, -1, -1)
                 _, _, f_l, h_l, w_l = lat.shape
                 s = item.conditioning_strength
                 if fno == 0:
@@ -210,9 +212,9 @@ class LTXVideoPipeline:
             # drawn in the dtype the reference's latents have (= prompt_embeds' dtype, :1061), so the same generator gives the same noise
             noise = torch.randn(st.tokens_shape, generator=gen, device=gen.device if isinstance(gen, torch.Generator) else device,
                                 dtype=st.init_tokens.dtype).to(device)
-            need = (st.cmask_dev.view(1, N) > 1.0 - 1e-6).unsqueeze(-1)
+            need = (st.cmask_dev.view(bsz, N) > 1.0 - 1e-6).unsqueeze(-1)
             noised = st.init_tokens.float() + st.image_cond_noise_scale * noise.float() * (t ** 2)
-            st.lat32 = torch.where(need, noised, st.lat32.view(1, N, C)).contiguous().view(-1)
+            st.lat32 = torch.where(need, noised, st.lat32.view(bsz, N, C)).contiguous().view(-1)
             st.lat16 = st.lat32.to(BF16)
         cp = getattr(st, "cond_parallel", None)
         nl = st.num_local_conds                 # the condition rows THIS rank runs (all of them without cond_parallel_group)
@@ -224,7 +226,7 @@ class LTXVideoPipeline:
             if st.cmask_dev is None:
                 st.t_in.fill_(t)
             else:
-                st.t_in.copy_(torch.clamp(1.0 - st.cmask_dev, max=t).view(1, N).expand(nl, N))   # min(t, 1-mask) :1145-1150
+                st.t_in.view(nl, bsz, N).copy_(torch.clamp(1.0 - st.cmask_dev, max=t).view(1, bsz, N).expand(nl, bsz, N))   # min(t, 1-mask) :1145-1150
             noise_pred = self.transformer(
                 st.x_in, freqs_cis=st.freqs_cis, encoder_hidden_states=st.enc_b, encoder_attention_mask=st.mask_b,
                 timestep=st.t_in, skip_layer_mask=st.skip_layer_masks[i] if st.skip_layer_masks is not None else None,
@@ -245,7 +247,8 @@ class LTXVideoPipeline:
             ops.guidance_step(pred[j * n:], st.lat32[j * n:(j + 1) * n], st.ts_dev, t, num_conds=num_conds,
                               has_cfg=st.do_cfg, has_stg=st.do_stg, do_rescale=st.do_rescaling,
                               guidance_scale=st.guidance_scale[i], stg_scale=st.stg_scale[i], rescale=st.rescaling_scale[i],
-                              channels=C, cond_mask=st.cmask_dev, scratch=st.scratch, latents_bf16=st.lat16[j * n:(j + 1) * n],
+                              channels=C, cond_mask=None if st.cmask_dev is None else st.cmask_dev[j * N:(j + 1) * N], scratch=st.scratch,
+                              latents_bf16=st.lat16[j * n:(j + 1) * n],
                               noise=self._step_noise(st) if st.stochastic_sampling else None, cond_stride=bsz * n)
         return st
 
@@ -281,9 +284,6 @@ class LTXVideoPipeline:
             prompt_embeds, prompt_attention_mask = rep(prompt_embeds), rep(prompt_attention_mask)
             negative_prompt_embeds, negative_prompt_attention_mask = rep(negative_prompt_embeds), rep(negative_prompt_attention_mask)
         bsz = batch_size * (num_images_per_prompt or 1)
-        if bsz != 1 and (conditioning_items or media_items is not None or image_cond_noise_scale or stochastic_sampling):
-            raise NotImplementedError("more than one video per call is implemented for plain t2v (no conditioning items / media / "
-                                      "stochastic sampling)")
 
         video_scale = self.video_scale_factor if is_video else 1
         latent_height, latent_width = height // self.vae_scale_factor, width // self.vae_scale_factor

@@ -658,6 +658,44 @@ def test_pipeline_two_videos_per_call():
     assert tuple(rep.shape) == (2, 128, 3, 4, 6) and torch.equal(rep[:1], one)
 
 
+def test_pipeline_two_videos_with_conditioning():
+    """More than one video per call WITH conditioning (pipeline_ltx_video.py:632-710, 1344-1548 on a batch): per-sample conditioning masks and
+    per-token timesteps, a first-frame latent per video (and one shared by both).  Sample 0 equals the one-video call bit for bit; both
+    samples match the oracle loop run per video; hard-conditioned tokens are never touched."""
+    pipe, sd, _ = _pipe(2)
+    g = torch.Generator().manual_seed(23)
+    pe, pm = torch.randn(2, 16, 4096, generator=g), torch.ones(2, 16)
+    cond = torch.randn(2, 128, 1, 4, 6, generator=g)
+    kw = dict(height=128, width=192, num_frames=17, frame_rate=25.0, num_inference_steps=3, guidance_scale=1.0, stg_scale=0.0, rescaling_scale=1.0,
+              output_type="latent", return_dict=False, is_video=True, vae_per_channel_normalize=True)
+    steps2 = []
+    two = pipe(prompt_embeds=pe, prompt_attention_mask=pm, generator=torch.Generator().manual_seed(5), _per_step_latents=steps2,
+               conditioning_items=[ConditioningItem(latents=cond, media_frame_number=0, conditioning_strength=1.0)], **kw)[0]
+    one = pipe(prompt_embeds=pe[:1], prompt_attention_mask=pm[:1], generator=torch.Generator().manual_seed(5),
+               conditioning_items=[ConditioningItem(latents=cond[:1], media_frame_number=0, conditioning_strength=1.0)], **kw)[0]
+    torch.cuda.synchronize()
+    assert tuple(two.shape) == (2, 128, 3, 4, 6) and torch.equal(two[:1], one)
+    noise = torch.randn(2, 72, 128, generator=torch.Generator().manual_seed(5))
+    cmask = torch.zeros(1, 3, 4, 6); cmask[:, :1] = 1.0
+    for j in range(2):
+        init = O.unpatchify(noise[j:j + 1], 3, 4, 6).clone()
+        init[:, :, :1] = cond[j:j + 1]
+        ref = O.denoise_loop(sd, O.LTX_2B, O.patchify(init), pe[j:j + 1], pm[j:j + 1], num_frames_lat=3, lat_h=4, lat_w=6, frame_rate=25.0,
+                             num_steps=3, conditioning_mask=cmask.reshape(1, -1))
+        e = O.rel_l2(two[j:j + 1].float().cpu(), O.unpatchify(ref, 3, 4, 6))
+        print(f"2 videos with conditioning, sample {j}: final latents rel_l2 vs the oracle loop = {e:.3e}")
+        assert e < TOL_LATENTS
+        assert torch.equal(steps2[-1][j, :24].cpu(), O.patchify(init)[0, :24])           # the conditioned first frame is never touched
+    # one conditioning item shared by both videos, and the stochastic sampler on a batch (runs, reproducible, differs from the Euler step)
+    shared = pipe(prompt_embeds=pe, prompt_attention_mask=pm, generator=torch.Generator().manual_seed(5),
+                  conditioning_items=[ConditioningItem(latents=cond[:1], media_frame_number=0, conditioning_strength=1.0)], **kw)[0]
+    assert torch.equal(shared[:1], one) and torch.equal(shared[1, :, 0], shared[0, :, 0])
+    a = pipe(prompt_embeds=pe, prompt_attention_mask=pm, generator=torch.Generator().manual_seed(6), stochastic_sampling=True, **kw)[0]
+    b = pipe(prompt_embeds=pe, prompt_attention_mask=pm, generator=torch.Generator().manual_seed(6), stochastic_sampling=True, **kw)[0]
+    c = pipe(prompt_embeds=pe, prompt_attention_mask=pm, generator=torch.Generator().manual_seed(6), **kw)[0]
+    assert torch.equal(a, b) and O.rel_l2(a.cpu(), c.cpu()) > 1e-2 and O.rel_l2(a[:1].cpu(), a[1:].cpu()) > 1e-2
+
+
 def test_transformer_and_pipeline_mixed_precision(golden_dir):
     """`mixed=True` (transformer3d.py:343,439-442 / `mixed_precision=True`, pipeline_ltx_video.py:1061,1152-1177): fp32 residual stream and
     fp32 AdaLN tables, bf16 Linear inputs.  Against the fp32 reference fixture the mixed forward must be inside the contract and not
