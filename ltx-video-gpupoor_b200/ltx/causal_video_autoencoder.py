@@ -365,9 +365,12 @@ class CausalVideoAutoencoder(ModuleLike):
         tc = self.decoder.timestep_conditioning
         if tc:
             assert timestep is not None, "should pass timestep with timestep_conditioning=True"          # :757-761
-            if x.shape[0] != 1:
-                raise NotImplementedError("timestep-conditioned decode handles one video per call")
-            ts = (torch.as_tensor(timestep, dtype=torch.float32).flatten()[:1] * self.timestep_scale_multiplier).to(self.device)
+            tt = torch.as_tensor(timestep, dtype=torch.float32).flatten()
+            if tt.numel() > 1 and not bool((tt == tt[0]).all()):
+                # the reference passes one decode timestep per video (vae_encode.py:110-118) and its callers make them all equal
+                # (pipeline_ltx_video.py:1271-1285); the modulation tables here are built once per call
+                raise NotImplementedError("timestep-conditioned decode with DIFFERENT timesteps per video")
+            ts = (tt[:1] * self.timestep_scale_multiplier).to(self.device)
         x = ops.conv3d(x, *w["conv_in"], causal=causal)
         ada_cache = {}
 

@@ -196,6 +196,13 @@ def test_vae_decode_timestep_conditioned_vs_reference_fixture(golden_dir):
     assert tuple(y.shape) == (1, 3, 9, 96, 128) and ps >= 40.0
     y2 = vae_decode(g["z"].to(DEV), vae, is_video=True, vae_per_channel_normalize=True, timestep=torch.tensor([0.5]))
     assert O.psnr(O.postprocess(y2.float().cpu()), O.postprocess(g["out"].float())) < ps - 3      # the timestep is used
+    # two videos per decode (one timestep per video, all equal, as the reference's callers pass them): every video = its own decode
+    z2 = torch.cat([g["z"], g["z"].flip(-1)], dim=0).to(DEV)
+    yb = vae_decode(z2, vae, is_video=True, vae_per_channel_normalize=True, timestep=g["timestep"].flatten()[:1].repeat(2))
+    y1 = vae_decode(z2[1:], vae, is_video=True, vae_per_channel_normalize=True, timestep=g["timestep"])
+    assert tuple(yb.shape) == (2, 3, 9, 96, 128) and torch.equal(yb[:1], y) and torch.equal(yb[1:], y1)
+    with pytest.raises(NotImplementedError):
+        vae_decode(z2, vae, is_video=True, vae_per_channel_normalize=True, timestep=torch.tensor([0.05, 0.5]))
 
 
 # ------------------------------------------------------------------ VAE encode (i2v / v2v conditioning from pixels)
