@@ -218,8 +218,9 @@ class LTXVideoPipeline:
             st.lat16 = st.lat32.to(BF16)
         cp = getattr(st, "cond_parallel", None)
         nl = st.num_local_conds                 # the condition rows THIS rank runs (all of them without cond_parallel_group)
-        if cp is not None and cp.any_flag(bool(getattr(st.ltxv_model, "_interrupt", False)), device):
+        if cp is not None and st.ltxv_model is not None and cp.any_flag(bool(getattr(st.ltxv_model, "_interrupt", False)), device):
             return None                         # collective decision at the step boundary: no rank is left waiting in the exchange
+                                                # (one small all-reduce + host read per step, only when the caller passed an interrupt source)
         noise_pred = None
         if nl:
             st.x_in.view(nl, bsz, N, C).copy_(st.lat16.view(1, bsz, N, C).expand(nl, bsz, N, C))
