@@ -807,8 +807,15 @@ def _cond_parallel_worker(rank, world, port, ret):
         cp = pipe(generator=torch.Generator().manual_seed(5), cond_parallel_group=dist.group.WORLD, _per_step_latents=steps_cp, **kw)[0]
         one = pipe(generator=torch.Generator().manual_seed(5), _per_step_latents=steps_one, **kw)[0]       # all three conditions on this GPU
         torch.cuda.synchronize()
+        # an interrupt seen by ONE rank ends the call on every rank at the same step boundary (OR over the group)
+        from types import SimpleNamespace
+        stopped = pipe(generator=torch.Generator().manual_seed(5), cond_parallel_group=dist.group.WORLD,
+                       ltxv_model=SimpleNamespace(_interrupt=(rank == world - 1)), **kw)
+        running = pipe(generator=torch.Generator().manual_seed(5), cond_parallel_group=dist.group.WORLD,
+                       ltxv_model=SimpleNamespace(_interrupt=False), **kw)[0]
+        torch.cuda.synchronize()
         ret[rank] = dict(equal=bool(torch.equal(cp, one)) and all(torch.equal(a, b) for a, b in zip(steps_cp, steps_one)),
-                         steps=len(steps_cp), latents=cp.float().cpu())
+                         steps=len(steps_cp), latents=cp.float().cpu(), stopped=stopped is None, running=bool(torch.equal(running, one)))
     finally:
         dist.destroy_process_group()
 
@@ -826,4 +833,5 @@ def test_pipeline_cond_parallel(world):
     assert len(ret) == world
     for r in range(world):
         assert ret[r]["steps"] == 3 and ret[r]["equal"], f"rank {r}: cond-parallel latents differ from the single-GPU call"
+        assert ret[r]["stopped"] and ret[r]["running"], f"rank {r}: interrupt handling under cond-parallel"
         assert torch.equal(ret[r]["latents"], ret[0]["latents"])
