@@ -257,11 +257,23 @@ DEVI void softmax_block(uint32_t tS, uint32_t tO, bool first, int kbase, int Lk,
   const bool lean_tail = kPredicated && bias == nullptr;        // warp-uniform
   uint32_t v[BN];
   float mx0 = -INFINITY, mx1 = -INFINITY;
-  tmem_ld32(tS, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+  // kLoadAll: every chunk of the row is requested before the first wait (one exposed TMEM latency per block instead of one per chunk —
+  // the chunk-by-chunk form hides the latency behind the OTHER warp of the scheduler, which a tile that runs alone does not have)
+#ifdef LTXB200_ATTN_LOADALL
+  constexpr bool kLoadAll = (LTXB200_ATTN_LOADALL == 2) || (LTXB200_ATTN_LOADALL == 1 && D == 128);
+#else
+  constexpr bool kLoadAll = false;
+#endif
+  if (kLoadAll) {
+#pragma unroll
+    for (int c = 0; c < BN; c += 32) tmem_ld32(tS + c, *reinterpret_cast<uint32_t(*)[32]>(&v[c]));
+  } else {
+    tmem_ld32(tS, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+  }
 #pragma unroll
   for (int c = 0; c < BN; c += 32) {
-    tmem_wait_ld();
-    if (c + 32 < BN) tmem_ld32(tS + c + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c + 32]));
+    if (!kLoadAll || c == 0) tmem_wait_ld();
+    if (!kLoadAll && c + 32 < BN) tmem_ld32(tS + c + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c + 32]));
     if (lean_tail) {
       const int nv = Lk - kbase - c;                            // valid keys in this 32-column chunk
       if (nv < 32) {

@@ -16,5 +16,6 @@ build pingpong "-DLTXB200_ATTN128_PINGPONG" &
 build gelu_scalar "-DLTXB200_GELU_SCALAR" &
 wait
 build poly "-DLTXB200_ATTN_POLY_D64=2 -DLTXB200_ATTN_POLY_DEG_D64=3 -DLTXB200_ATTN_POLY_D128=0" &
+build loadall "-DLTXB200_ATTN_LOADALL=2" &
 build dbg "-DLTXB200_DEBUG_HANG" &
 wait
