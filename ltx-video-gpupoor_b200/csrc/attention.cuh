@@ -25,6 +25,17 @@
 #include "common.cuh"
 #include "comm.cuh"
 
+// LTXB200_ATTN_L2PF = n: the TMA producer requests the K / V blocks n key blocks ahead into L2 (0 = off)
+#ifndef LTXB200_ATTN_L2PF
+#define LTXB200_ATTN_L2PF 0
+#endif
+// the producer's waits for a free ring stage: sleep-and-probe (64 ns naps) or parked on the barrier (-DLTXB200_ATTN_PRODUCER_PARK)
+#ifdef LTXB200_ATTN_PRODUCER_PARK
+#define LTXB200_PRODUCER_WAIT(bar, par) mbar_wait_parked(bar, par)
+#else
+#define LTXB200_PRODUCER_WAIT(bar, par) mbar_wait_backoff(bar, par)
+#endif
+
 namespace b200 {
 
 constexpr int kAttnBM = 128;   // query rows per tile (= TMEM lanes)
@@ -245,10 +256,22 @@ DEVI void exp_chunk(const uint32_t* v, float sc, float neg_m, uint32_t tP, uint6
 // One key block of the online softmax for one query row (one thread): S (fp32, BN columns at tS) -> registers in
 // ONE TMEM pass -> block max -> (lazy) rescale -> exp2 -> P (bf16 pairs) over the first BN/2 columns of tS.
 // m_ref: reference max of the row (log2 domain), m_run: largest score seen so far, l: row sum relative to m_ref.
-template <int D, int BN, bool kPredicated, int kOW = D, bool kSum = true, int kEarly = BN / 2>   // kOW: accumulator columns the lazy rescale covers; kSum: row sum kept here; kEarly: keys written when p_half is signalled
+// kToLeader (CTA-pair kernel, attention128p2.cuh): the handshake barriers live in the cluster's rank-0 CTA, whose thread issues the MMAs of both
+template <bool kToLeader>
+DEVI void softmax_arrive(uint64_t* bar) {
+  if (kToLeader) mbar_arrive_remote(bar, 0);
+  else mbar_arrive(bar);
+}
+template <int D, int BN, bool kPredicated, int kOW = D, bool kSum = true, int kEarly = BN / 2, bool kToLeader = false>   // kOW: accumulator columns the lazy rescale covers; kSum: row sum kept here; kEarly: keys written when p_half is signalled
 DEVI void softmax_block(uint32_t tS, uint32_t tO, bool first, int kbase, int Lk, const float* bias, float sc,
                         float& m_ref, float& m_run, float& l, uint64_t* pv_done, uint32_t pv_parity,
                         uint64_t* s_read, uint64_t* p_half, int lane) {
+#ifdef LTXB200_ABL_NOTMEM                        // diagnostic build (wrong results): the block's barrier handshakes without its TMEM traffic and arithmetic
+  if (s_read) { tc_fence_before(); __syncwarp(); if (lane == 0) softmax_arrive<kToLeader>(s_read); }
+  if (p_half) { tc_fence_before(); __syncwarp(); if (lane == 0) softmax_arrive<kToLeader>(p_half); }
+  m_ref = 0.f; m_run = 0.f; l = 1.f;
+  return;
+#endif
   const float kLog2e = 1.4426950408889634f;
   const bool bias_vec = bias != nullptr && ((reinterpret_cast<uintptr_t>(bias) | (static_cast<uintptr_t>(kbase) << 2)) & 15) == 0;
   // A partial key block WITHOUT a bias (the tail of a sequence; the last block of a right-padded prompt given as a key length) takes the
@@ -333,7 +356,7 @@ DEVI void softmax_block(uint32_t tS, uint32_t tO, bool first, int kbase, int Lk,
   if (s_read) {                                  // the whole S row is in registers: columns 64.. may be overwritten
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(s_read);
+    if (lane == 0) softmax_arrive<kToLeader>(s_read);
   }
   float m_blk = fmaxf(mx0, mx1);
   if (!kPredicated || lean_tail) m_blk *= sc;    // scale > 0: max commutes with the scaling
@@ -353,7 +376,7 @@ DEVI void softmax_block(uint32_t tS, uint32_t tO, bool first, int kbase, int Lk,
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_half);
+      if (lane == 0) softmax_arrive<kToLeader>(p_half);
     }
   }
   if (kSum) {
@@ -536,7 +559,21 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         auto load_k = [&](int j) {
           const uint32_t kk = kc + j;
           const int st = kk % kStagesK;
-          mbar_wait_backoff(&k_empty[st], ((kk / kStagesK) & 1) ^ 1);
+#if LTXB200_ATTN_L2PF > 0
+          // K / V blocks kL2Pf ahead of the ring are requested into L2: the CTAs of a head walk its keys in near lock-step, so every block's
+          // first touch is a DRAM miss that all of them wait for; the rings (2-4 stages) are too shallow to hide that latency themselves
+          if (j + LTXB200_ATTN_L2PF < nblk) {
+#pragma unroll
+            for (int c = 0; c < kChunks; ++c) {
+              tma_prefetch_l2_4d(&tmK, c * 64, h, (j + LTXB200_ATTN_L2PF) * BN, b);
+              tma_prefetch_l2_4d(&tmV, c * 64, h, (j + LTXB200_ATTN_L2PF) * BN, b);
+            }
+          }
+#endif
+          LTXB200_PRODUCER_WAIT(&k_empty[st], ((kk / kStagesK) & 1) ^ 1);
+#ifdef LTXB200_ABL_NOLOAD                        // diagnostic build (wrong results): only the first fill of every ring stage is a real load
+          if (kk >= static_cast<uint32_t>(kStagesK)) { mbar_arrive(&k_full[st]); return; }
+#endif
           mbar_arrive_expect_tx(&k_full[st], C::kKBytes);
 #pragma unroll
           for (int c = 0; c < kChunks; ++c)
@@ -547,7 +584,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           if (j + 1 < nblk) load_k(j + 1);
           const uint32_t vv = kc + j;
           const int sv = vv % kStagesV;
-          mbar_wait_backoff(&v_empty[sv], ((vv / kStagesV) & 1) ^ 1);
+          LTXB200_PRODUCER_WAIT(&v_empty[sv], ((vv / kStagesV) & 1) ^ 1);
+#ifdef LTXB200_ABL_NOLOAD
+          if (vv >= static_cast<uint32_t>(kStagesV)) { mbar_arrive(&v_full[sv]); continue; }
+#endif
           mbar_arrive_expect_tx(&v_full[sv], C::kKBytes);
 #pragma unroll
           for (int c = 0; c < kChunks; ++c)
@@ -557,6 +597,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
     } else if ((warp == kMmaWarp || (C::k2Mma && warp == kMmaWarp + 1)) && elect_one()) {
       // ================= MMA issuer (k2Mma: this thread issues for tile `mt` only; otherwise for both) =================
+#ifdef LTXB200_ABL_FREEMMA                       // diagnostic build (wrong results): the MMA thread never waits for the softmax warps (which do
+#define LTXB200_SM_WAIT(bar, par) ((void)0)      // nothing): the rate of the tensor pipe + TMA rings alone on this kernel's instruction mix
+#else
+#define LTXB200_SM_WAIT(bar, par) mbar_wait_parked(bar, par)
+#endif
       constexpr int kStep = C::k2Mma ? 2 : 1;           // stride of this thread through the global steps N = 2 * block + tile
       const int mt = C::k2Mma ? warp - kMmaWarp : 0;
       constexpr uint32_t idesc_s = umma_idesc_bf16(kAttnBM, BN, 0, 0);   // S = Q K^T  (both K-major)
@@ -632,20 +677,20 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           const uint32_t buf = N % kSBufs, par = (N / kSBufs) & 1;
           const bool more = sc.w < p.total;        // the cursor then stands at step N + kSBufs, i.e. on this step's buffer
           if (kSplit) {
-            if (more) { mbar_wait_parked(&s_read[buf], par); issue_s(1); }
-            mbar_wait_parked(&p_half[buf], par);
-            if (j == 0) mbar_wait_parked(&o_free[t], (it & 1) ^ 1);
+            if (more) { LTXB200_SM_WAIT(&s_read[buf], par); issue_s(1); }
+            LTXB200_SM_WAIT(&p_half[buf], par);
+            if (j == 0) LTXB200_SM_WAIT(&o_free[t], (it & 1) ^ 1);
             if (t == 0 || C::k2Mma) mbar_wait_parked(&v_full[sv], (vc / kStagesV) & 1);
             tc_fence_after();
             constexpr int kEarlySteps = C::kSplit34 ? 3 * BN / 64 : BN / 32;      // k-steps (16 keys) covered by the early P signal
             issue_pv(t, buf, sv, 0, kEarlySteps, j > 0);
             if (C::kSplit34 && more) issue_s(2);                                   // score columns 0..BN/4-1 = P of keys 0..BN/2-1: consumed
-            mbar_wait_parked(&p_full[buf], par);
+            LTXB200_SM_WAIT(&p_full[buf], par);
             tc_fence_after();
             issue_pv(t, buf, sv, kEarlySteps, BN / 16, true);
           } else {
-            mbar_wait_parked(&p_full[buf], par);
-            if (j == 0) mbar_wait_parked(&o_free[t], (it & 1) ^ 1);
+            LTXB200_SM_WAIT(&p_full[buf], par);
+            if (j == 0) LTXB200_SM_WAIT(&o_free[t], (it & 1) ^ 1);
             if (t == 0) mbar_wait_parked(&v_full[sv], (vc / kStagesV) & 1);
             tc_fence_after();
             issue_pv(t, buf, sv, 0, BN / 16, j > 0);
@@ -656,6 +701,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           if (more) { issue_s(kSplit ? (C::kSplit34 ? 3 : 0) : -1); s_advance(); }
         }
       }
+#ifdef LTXB200_ABL_FREEMMA
+      if (it > 0) mbar_wait(&o_done[1], (it - 1) & 1);       // nobody else waits for the pipe to drain
+#endif
     }
   } else {
     // ================= softmax / correction / epilogue: warpgroup t owns query tile t =================
@@ -672,6 +720,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const int pair_bar = 1 + t * 4 + sub;      // named barrier of the two warps that share these 32 rows
     uint32_t G = 0;                  // global key-block counter of this tile; its step is N = 2*G + t
     int it = 0;
+#ifdef LTXB200_ABL_FREEMMA
+    if (false)
+#endif
     for (int w = blockIdx.x; w < p.total; w += gridDim.x, ++it) {
       const int qp = w % p.pairs, bh = w / p.pairs, h = bh % p.H, b = bh / p.H;
       const float* bias = p.key_bias ? p.key_bias + static_cast<long long>(b) * p.Lk : nullptr;

@@ -161,6 +161,18 @@ DEVI bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // wait with a suspend-time hint: the hardware parks the thread until the phase completes (or ~the hint elapses) instead of returning
 // after a few cycles, so a single issuing thread that waits most of the time does not eat its scheduler's issue slots
 DEVI void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+#ifdef LTXB200_DEBUG_HANG                        // debug build: report instead of hanging (the line is the helper's, the barrier address tells which)
+  {
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+      if (clock64() - t0 > 2000000000LL) {
+        printf("HANG(parked): block %d thread %d bar@%u parity %u\n", blockIdx.x, threadIdx.x, smem_u32(bar), parity);
+        __trap();
+      }
+    }
+    return;
+  }
+#endif
 #ifdef LTXB200_MMA_SPIN                          // A/B: poll instead of parking (lower wake-up latency, more issue slots taken)
   while (!mbar_try_wait(bar, parity)) {
   }
@@ -230,6 +242,12 @@ DEVI void tma_load_4d(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, i
       "[%2];\n" ::"r"(smem_u32(smem)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+// the same box requested into L2 only (no shared-memory destination, no barrier): hides the DRAM latency of a tile's first touch
+DEVI void tma_prefetch_l2_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];\n" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0),
+               "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
 }
 DEVI void tma_load_5d(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
   asm volatile(
@@ -367,6 +385,13 @@ DEVI void tma_load_5d_2sm(void* smem, const CUtensorMap* m, uint64_t* leader_bar
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
+DEVI void tma_load_4d_2sm(void* smem, const CUtensorMap* m, uint64_t* leader_bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2];\n" ::"r"(smem_u32(smem)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 template <uint32_t kCols>
 DEVI void tmem_alloc_2cta(uint32_t* smem_dst) {   // whole warp, the same warp index in both CTAs
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(smem_dst)), "n"(kCols) : "memory");
@@ -390,6 +415,15 @@ DEVI void umma_ss_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc] on a CTA pair: each CTA multiplies its own 128 TMEM lanes of A by the pair's B tile
+DEVI void umma_ts_2cta(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 DEVI void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {      // arrive on the barrier at the same offset in CTA `cta` of the cluster

@@ -7,6 +7,7 @@
 
 #include "attention.cuh"
 #include "attention64p.cuh"
+#include "attention128p2.cuh"
 #include "comm.cuh"
 #include "common.cuh"
 #include "conv_halo.cuh"
@@ -408,6 +409,39 @@ static int launch_attn64p(const CUtensorMap& tq, const CUtensorMap& tk, const CU
   attention64p_kernel<<<grid, C::kThreads, C::kTotal, st>>>(tq, tk, tv, p);
   return launch_status();
 }
+// d = 128 on a CTA pair (attention128p2.cuh), OPT-IN with LTXB200_ATTN128_2CTA=1: cluster of 2, grid = 2 x min(items of 512 query rows, SMs / 2)
+template <bool kMasked>
+static int launch_attn128p2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, cudaStream_t st) {
+  using C = Attn2CtaCfg;
+  static bool configured = false;
+  auto kern = attention128p2_kernel<kMasked>;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal) != cudaSuccess) return kErrCuda;
+    configured = true;
+  }
+  const long long items = static_cast<long long>(p.B) * p.H * ((p.Lq + C::kRowsPerItem - 1) / C::kRowsPerItem);
+  const int pairs = num_sms() / 2;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * static_cast<unsigned>(items < pairs ? items : pairs));
+  cfg.blockDim = dim3(C::kThreads);
+  cfg.dynamicSmemBytes = C::kTotal;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, kern, tq, tk, tv, p) != cudaSuccess) return kErrCuda;
+  return launch_status();
+}
+static bool attn128p2_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("LTXB200_ATTN128_2CTA");
+    on = (e && e[0] == '1') ? 1 : 0;
+  }
+  return on == 1;
+}
 static bool attn64p_enabled() {
   static int on = -1;
   if (on < 0) {
@@ -432,8 +466,9 @@ static int attention_impl(const void* q, int64_t ldq, int64_t bsq, const void* k
   const bool use64p = d == 64 && !key_bias && !key_lens && Lk % Attn64PCfg::BN == 0 && Lk >= 2 * Attn64PCfg::BN && !peers && !accumulate && attn64p_enabled();
   const bool masked = (key_bias != nullptr) || (Lk % BNu != 0) || (key_lens != nullptr);
   const int BN = use64p ? Attn64PCfg::BN : (masked ? BNm : BNu);
+  const bool use128p2 = d == 128 && BN == Attn2CtaCfg::BN && attn128p2_enabled();
   CUtensorMap tq, tk, tv;
-  if (make_qkv_tmap(&tq, q, B, H, Lq, d, ldq, bsq, kAttnBM) || make_qkv_tmap(&tk, k, B, H, Lk, d, ldk, bsk, BN) ||
+  if (make_qkv_tmap(&tq, q, B, H, Lq, d, ldq, bsq, kAttnBM) || make_qkv_tmap(&tk, k, B, H, Lk, d, ldk, bsk, use128p2 ? 32 : BN) ||
       make_qkv_tmap(&tv, v, B, H, Lk, d, ldv, bsv, BN))
     return kErrTensorMap;
   AttnParams p{};
@@ -451,6 +486,7 @@ static int attention_impl(const void* q, int64_t ldq, int64_t bsq, const void* k
   p.accumulate = accumulate;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (use64p) return launch_attn64p(tq, tk, tv, p, st);
+  if (use128p2) return masked ? launch_attn128p2<true>(tq, tk, tv, p, st) : launch_attn128p2<false>(tq, tk, tv, p, st);
   if (d == 64) return masked ? launch_attn<64, true>(tq, tk, tv, p, st) : launch_attn<64, false>(tq, tk, tv, p, st);
   return masked ? launch_attn<128, true>(tq, tk, tv, p, st) : launch_attn<128, false>(tq, tk, tv, p, st);
 }

@@ -17,5 +17,8 @@ build gelu_scalar "-DLTXB200_GELU_SCALAR" &
 wait
 build poly "-DLTXB200_ATTN_POLY_D64=2 -DLTXB200_ATTN_POLY_DEG_D64=3 -DLTXB200_ATTN_POLY_D128=0" &
 build loadall "-DLTXB200_ATTN_LOADALL=2" &
+build l2pf "-DLTXB200_ATTN_L2PF=4 -DLTXB200_ATTN_PRODUCER_PARK" &
+build ablations "-DLTXB200_ABL_NOEXP -DLTXB200_ABL_NOMAX -DLTXB200_ABL_NOSUM -DLTXB200_ABL_NOLOAD -DLTXB200_ABL_NOTMEM" &
+build freemma "-DLTXB200_ABL_FREEMMA" &
 build dbg "-DLTXB200_DEBUG_HANG" &
 wait

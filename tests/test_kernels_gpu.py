@@ -467,3 +467,17 @@ def test_attention64_pipelined_variant_parity():
     r = subprocess.run([sys.executable, os.path.join(root, "profiles", "scripts", "attn64p_check.py")], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-800:] + r.stderr[-800:]
     assert "ATTN64P = 1" in r.stdout
+
+
+def test_attention128_cta_pair_variant_parity():
+    """The opt-in CTA-pair d = 128 kernel (csrc/attention128p2.cuh, LTXB200_ATTN128_2CTA=1; the switch is read once per process, hence the
+    subprocess): cluster of 2, cta_group::2 MMAs, half of K / V per CTA, remote barrier arrivals.  Parity on partial query groups and key
+    blocks, strided fused-QKV operands, key bias / key lengths, large logits; deterministic."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, LTXB200_ATTN128_2CTA="1")
+    r = subprocess.run([sys.executable, os.path.join(root, "profiles", "scripts", "attn128p2_check.py")], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-800:] + r.stderr[-800:]
+    assert "ATTN128_2CTA = 1" in r.stdout
+
