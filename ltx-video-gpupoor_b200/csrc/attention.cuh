@@ -259,7 +259,11 @@ DEVI void exp_chunk(const uint32_t* v, float sc, float neg_m, uint32_t tP, uint6
 // kToLeader (CTA-pair kernel, attention128p2.cuh): the handshake barriers live in the cluster's rank-0 CTA, whose thread issues the MMAs of both
 template <bool kToLeader>
 DEVI void softmax_arrive(uint64_t* bar) {
+#ifdef LTXB200_ATTN128_2CTA_RELEASE               // A/B: the releasing remote arrive (a cluster-scope fence per hop)
   if (kToLeader) mbar_arrive_remote(bar, 0);
+#else
+  if (kToLeader) mbar_arrive_remote_relaxed(bar, 0);
+#endif
   else mbar_arrive(bar);
 }
 template <int D, int BN, bool kPredicated, int kOW = D, bool kSum = true, int kEarly = BN / 2, bool kToLeader = false>   // kOW: accumulator columns the lazy rescale covers; kSum: row sum kept here; kEarly: keys written when p_half is signalled

@@ -9,6 +9,7 @@
 // what cuDNN's kernel reaches per clock — i.e. the 128 x 128 single-CTA instruction mix is the limit, not the softmax around it.
 // The leader (cluster rank 0) issues all MMAs; commits are multicast to both CTAs; the peer's softmax warps arrive on the leader's
 // handshake barriers through the cluster address space; TMA loads of both CTAs complete on the leader's barriers.
+// Measured (profiles/r02_attn64_ab.md §12): level with the single-CTA kernel in burst, -1 % sustained at a 3.7 % higher SM clock.
 // OPT-IN (LTXB200_ATTN128_2CTA=1).  Reference semantics as attention.cuh (utils/attention.py:99-116).
 #pragma once
 #include "attention.cuh"
@@ -242,7 +243,7 @@ attention128p2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_remote(&p_full[buf], 0);
+        if (lane == 0) softmax_arrive<true>(&p_full[buf]);
       }
       // ---- epilogue: O / l -> bf16 -> global ----
       mbar_wait(&o_done[t], it & 1);
@@ -280,7 +281,7 @@ attention128p2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_remote(&o_free[t], 0);
+      if (lane == 0) softmax_arrive<true>(&o_free[t]);
     }
   }
 

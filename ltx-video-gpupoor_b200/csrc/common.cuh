@@ -435,6 +435,18 @@ DEVI void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {      // arrive on th
       : "memory");
 }
 
+// the same without the cluster-scope release fence (ERRBAR: ~15 % of the pair attention kernel's stall samples when every softmax hop used
+// the releasing form).  For handshakes whose payload lives in TENSOR memory: the thread has completed its tcgen05.ld / .st
+// (tcgen05.wait) and issued tcgen05.fence::before_thread_sync before it arrives; no generic-proxy data is published by the arrive.
+DEVI void mbar_arrive_remote_relaxed(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
+
 // instruction descriptor for kind::f16, bf16 x bf16 -> fp32
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, uint32_t a_mn_major, uint32_t b_mn_major) {
   return (1u << 4)                 // c_format  = F32
