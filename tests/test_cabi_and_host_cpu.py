@@ -351,3 +351,18 @@ def test_cond_partition():
             parts = cond_partition(conds, ranks)
             assert len(parts) == ranks and parts[0][0] == 0 and max(hi for _, hi in parts) == conds
             assert all(a[1] == b[0] or b == (conds, conds) for a, b in zip(parts, parts[1:]))
+
+
+def test_bench_attention_split():
+    """bench.py reports the self-attention (N x N) and cross-attention (N x prompt) launches of a step apart: the split is by flops per launch."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_for_test", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    out = bench.split_attention([(927.7e9, 1.25)] * 28 + [(38.7e9, 0.075)] * 28, 1382.5)
+    assert out["self_attention"]["launches"] == 28 and out["cross_attention"]["launches"] == 28
+    assert abs(out["self_attention"]["tflops"] - 742.2) < 0.2 and abs(out["cross_attention"]["tflops"] - 516.0) < 0.2
+    assert abs(out["self_attention"]["tensor_frac_of_sustained"] - 742.2 / 1382.5) < 1e-3
+    assert list(bench.split_attention([(5.0e9, 1.0)], 1000.0)) == ["self_attention"]      # a step with one kind of launch only
+
