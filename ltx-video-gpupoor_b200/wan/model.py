@@ -304,7 +304,9 @@ class WanModel(ModuleLike):
         C, Fr, Hh, Ww = x_list[0].shape
         grid = (Fr, Hh // 2, Ww // 2)
         N = math.prod(grid)
-        assert N % P == 0 and H % P == 0, "Ulysses needs tokens and heads divisible by the group size"
+        if N % P or H % P:
+            raise ValueError(f"Ulysses needs tokens ({N}) and heads ({H}) divisible by the group size ({P}); for 12 heads on 8 GPUs use "
+                             "CFG-parallel x Ulysses (wan/distributed/cfg_parallel.py)")
         n_loc = N // P
         # ---- embeddings (replicated; the token shard is taken right after the patch rows are built, :131-133)
         if y is not None:                       # i2v: [mask(4) | image latent(16)] channels appended to every sequence (:948-949)
@@ -314,7 +316,8 @@ class WanModel(ModuleLike):
         rows = rows[:, rank * n_loc:(rank + 1) * n_loc].to(BF16).reshape(B * n_loc, -1).contiguous()
         xs = ops.gemm(rows, w["patch.w"], w["patch.b"])                               # [B*n_loc, D]
         tt = t.to(device=dev, dtype=torch.float32).flatten().contiguous()
-        assert tt.numel() == 1, "per-frame timesteps (diffusion forcing, model.py:976) are out of scope"
+        if tt.numel() != 1:
+            raise NotImplementedError("per-frame timesteps (diffusion forcing, model.py:976) are out of scope")
         e = self._time_embedding(tt)                                                  # sinusoidal_embedding_1d (:18-28) -> [1, D]
         e0 = ops.gemm(ops.act(e, ops.ACT_SILU), w["tproj.w"], w["tproj.b"])           # [1, 6D]
         mods = ops.ada_add(w["block_mods"], e0)                                       # [L, 1, 6, D] = modulation + e0 (:436)
